@@ -1,0 +1,169 @@
+/*
+ * magic_oracle.h -- CPU restatement of MagIC's radial-loop hot path (TEST INFRASTRUCTURE ONLY).
+ *
+ * This is the parity oracle for magic_b200.  It restates, loop nest by loop nest, the reference's
+ * native (non-SHTns) path:  src/truncation.f90, src/blocking.f90, src/horizontal.f90, src/plms.f90,
+ * src/shtransforms.f90, src/sht_native.f90, src/get_nl.f90, src/get_td.f90, src/courant.f90,
+ * src/nonlinear_bcs.f90, src/rIter.f90 and the alltoallv flavour of src/mpi_transpose.f90.
+ * Every function cites the reference file:line it follows.
+ *
+ * PARITY STATUS: "parity unpinned" by reference golden vectors -- the reference holds no
+ * transform-level known-answer tests and cannot be compiled in this image (no Fortran
+ * compiler).  The oracle is pinned instead by analytic known answers and an independent scipy
+ * evaluation of the associated Legendre functions (tests/test_oracle_analytic.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may call
+ * into this library.  The product path (magic_b200/) never links or imports it.
+ *
+ * Conventions: all indices 0-based in C (Fortran lm=1.. becomes lm=0..).  Grid arrays are
+ * f[nphi][nlat] with theta fastest (Fortran f(nlat_padded,n_phi_max)); theta rows are N/S
+ * interleaved exactly as the native backend (row 2k = k-th northern node, row 2k+1 its mirror).
+ */
+#ifndef MAGIC_ORACLE_H
+#define MAGIC_ORACLE_H
+
+#include <complex.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef double _Complex orc_cplx;
+
+typedef struct orc_ctx orc_ctx;
+
+/* truncation.f90:50-124 -- derive grid sizes. Pass l_max_in>0 (n_phi_tot derived) or l_max_in==0 and
+ * n_phi_tot_in>0 (l_max derived).  out[0..6] = l_max, m_max, n_theta_max, n_phi_max, n_m_max, lm_max,
+ * n_phi_tot. */
+void orc_grid_sizes(int l_max_in, int n_phi_tot_in, int minc, int nalias, int out[7]);
+
+/* getBlocks parallel.f90:75-92 -- start[p], stop[p] are 1-based inclusive like the reference. */
+void orc_get_blocks(int n_points, int n_procs, int *start, int *stop);
+
+/* Context = initialize_truncation + initialize_blocking(st_map) + horizontal + initialize_transforms. */
+orc_ctx *orc_create(int l_max, int m_max, int minc, int n_theta_max, int n_phi_max);
+void orc_destroy(orc_ctx *c);
+void orc_set_threads(orc_ctx *c, int nthreads); /* OpenMP threads used inside the transforms */
+
+/* Introspection (pointers into the context; lifetime = context). */
+int orc_lm_max(const orc_ctx *c);
+int orc_n_m_max(const orc_ctx *c);
+const int *orc_lm2l(const orc_ctx *c);
+const int *orc_lm2m(const orc_ctx *c);
+const int *orc_lm2lmS(const orc_ctx *c);
+const int *orc_lm2lmA(const orc_ctx *c);
+const double *orc_theta_ord(const orc_ctx *c); /* n_theta, monotone north->south (gauleg output) */
+const double *orc_gauss(const orc_ctx *c);     /* n_theta, scrambled like horizontal.f90:180-188 */
+const double *orc_plm(const orc_ctx *c);       /* [n_theta/2][lm_max] */
+const double *orc_dplm(const orc_ctx *c);
+const double *orc_theta_vec(const orc_ctx *c, int which); /* 0 sinTheta 1 cosTheta 2 O_sin_theta
+                                                 3 O_sin_theta_E2 4 sinTheta_E2 5 cosn_theta_E2 */
+const double *orc_lm_vec(const orc_ctx *c, int which); /* 0 dLh 1..8 dTheta1S,1A,2S,2A,3S,3A,4S,4A */
+
+/* lo_map (blocking.f90:339-544): fills lo2st[lm_lo] = st index (0-based) and lm_balance start/stop
+ * (1-based inclusive) for n_procs ranks; snake ordering when n_procs <= l_max/2, else l-major. */
+void orc_lo_map(const orc_ctx *c, int n_procs, int *lo2st, int *lm_start, int *lm_stop);
+
+/* fft.f90:164-252 semantics on (nlat, nphi) arrays, theta fastest. */
+void orc_ifft_many(const orc_ctx *c, const orc_cplx *f /*[nphi/2+1][nlat]*/, double *g /*[nphi][nlat]*/);
+void orc_fft_many(const orc_ctx *c, const double *g, orc_cplx *f);
+
+/* shtransforms.f90 native_* (file:line at each definition in the .c) */
+void orc_native_qst_to_spat(const orc_ctx *c, const orc_cplx *Q, const orc_cplx *S, const orc_cplx *T,
+                            double *br, double *bt, double *bp, int lcut);
+void orc_native_sphtor_to_spat(const orc_ctx *c, const orc_cplx *S, const orc_cplx *T, double *bt,
+                               double *bp, int lcut);
+void orc_native_sph_to_spat(const orc_ctx *c, const orc_cplx *S, double *sc, int lcut);
+void orc_native_sph_to_grad_spat(const orc_ctx *c, const orc_cplx *S, double *gt, double *gp, int lcut);
+void orc_native_spat_to_sph(const orc_ctx *c, const double *scal, orc_cplx *fLM, int lcut);
+void orc_native_spat_to_sph_tor(const orc_ctx *c, const double *vt, const double *vp, orc_cplx *f1,
+                                orc_cplx *f2, int lcut);
+void orc_native_axi_to_spat(const orc_ctx *c, const orc_cplx *S, double *sc);
+void orc_native_toraxi_to_spat(const orc_ctx *c, const orc_cplx *T, double *bt, double *bp, int lcut);
+
+/* sht_native.f90 wrappers (the `module sht` public list, sht_native.f90:16-20) */
+void orc_scal_to_spat(const orc_ctx *c, const orc_cplx *S, double *f, int lcut);
+void orc_scal_to_grad_spat(const orc_ctx *c, const orc_cplx *S, double *gt, double *gp, int lcut);
+void orc_pol_to_grad_spat(const orc_ctx *c, const orc_cplx *S, double *gt, double *gp, int lcut);
+void orc_torpol_to_spat(const orc_ctx *c, const orc_cplx *W, const orc_cplx *dW, const orc_cplx *Z,
+                        double *vr, double *vt, double *vp, int lcut);
+void orc_sphtor_to_spat(const orc_ctx *c, const orc_cplx *dW, const orc_cplx *Z, double *vt, double *vp,
+                        int lcut);
+void orc_torpol_to_dphspat(const orc_ctx *c, const orc_cplx *dW, const orc_cplx *Z, double *dvtdp,
+                           double *dvpdp, int lcut);
+void orc_pol_to_curlr_spat(const orc_ctx *c, const orc_cplx *Q, double *cvr, int lcut);
+void orc_torpol_to_curl_spat(const orc_ctx *c, double or2, const orc_cplx *B, const orc_cplx *ddB,
+                             const orc_cplx *J, const orc_cplx *dJ, double *cvr, double *cvt, double *cvp,
+                             int lcut);
+void orc_scal_to_SH(const orc_ctx *c, const double *f, orc_cplx *fLM, int lcut);
+void orc_spat_to_qst(const orc_ctx *c, const double *f, const double *g, const double *h, orc_cplx *q,
+                     orc_cplx *s, orc_cplx *t, int lcut);
+void orc_spat_to_sphertor(const orc_ctx *c, const double *f, const double *g, orc_cplx *fLM, orc_cplx *gLM,
+                          int lcut);
+void orc_torpol_to_spat_IC(const orc_ctx *c, double r, double r_ICB, const orc_cplx *W, const orc_cplx *dW,
+                           const orc_cplx *Z, double *Br, double *Bt, double *Bp);
+void orc_torpol_to_curl_spat_IC(const orc_ctx *c, double r, double r_ICB, const orc_cplx *dB,
+                                const orc_cplx *ddB, const orc_cplx *J, const orc_cplx *dJ, double *cbr,
+                                double *cbt, double *cbp);
+void orc_axi_to_spat(const orc_ctx *c, const orc_cplx *fl_ax, double *f);
+void orc_toraxi_to_spat(const orc_ctx *c, const orc_cplx *fl_ax, double *ft, double *fp, int lcut);
+
+/* ---- radial loop (rIter.f90:94-712 + get_nl.f90 + get_td.f90 + courant.f90 + nonlinear_bcs.f90) ---- */
+
+/* Run-wide switches and constants (logic.f90 / physical_parameters.f90 values the hot path reads). */
+typedef struct {
+    int l_conv, l_mag, l_heat, l_conv_nl, l_heat_nl, l_mag_nl, l_mag_LF, l_mag_kin, l_anel, l_adv_curl,
+        l_corr, l_double_curl, l_single_matrix, l_chemical_conv, l_precession, l_centrifuge,
+        l_anelastic_liquid, l_cour_alf_damp, l_full_sphere, l_parallel_solve, l_temperature_diff;
+    int ktopv, kbotv;             /* 1 stress-free, 2 rigid */
+    int l_cond_ma, l_cond_ic, l_rot_ma, l_rot_ic;
+    int n_r_max, n_r_LCR;         /* radial levels are numbered 1..n_r_max; n_r_cmb=1, n_r_icb=n_r_max */
+    double LFfac, CorFac, epsc, epscXi, opm, ViscHeatFac, OhmLossFac;
+    double oek, po, prec_angle, dilution_fac, ra, opr;
+    double omega_ma, omega_ic, r_cmb, r_icb;
+    double courfac, alffac;
+} orc_params;
+
+/* Radial functions for the n_r levels handed to the loop (all arrays length n_r). */
+typedef struct {
+    const int *nR;   /* global 1-based level number of each local level */
+    const int *l_R;  /* lcut per level (radial.f90:291-307) */
+    const double *r, *or1, *or2, *or4, *orho1, *orho2, *beta, *rho0, *otemp1, *temp0, *visc, *lambda,
+        *epscProf, *delxr2, *delxh2;
+} orc_radial;
+
+/* R-distributed spectral inputs [n_r][lm_max] (Fortran X_Rloc(lm, nR)); any may be NULL if unused. */
+typedef struct {
+    const orc_cplx *w, *dw, *ddw, *z, *dz, *s, *ds, *p, *xi, *b, *db, *ddb, *aj, *dj;
+} orc_fields_in;
+
+/* Outputs of radialLoop (rIter.f90:125-147), [n_r][lm_max]; may be NULL when the switch is off. */
+typedef struct {
+    orc_cplx *dwdt, *dzdt, *dpdt, *dsdt, *dxidt, *dbdt, *djdt, *dVxVhLM, *dVxBhLM, *dVSrLM, *dVXirLM;
+    double *dtrkc, *dthkc; /* [n_r] */
+} orc_fields_out;
+
+/* Executes the body of `do nR=nRstart,nRstop` (rIter.f90:190-444) for n_r levels, with all output
+ * flags (lRmsCalc, lTOCalc, ...) false and lPressNext=false.  time is used by precession only. */
+void orc_radial_loop(const orc_ctx *c, const orc_params *p, const orc_radial *rad, int n_r,
+                     const orc_fields_in *in, const orc_fields_out *out, double time);
+
+/* get_nl only, on caller-provided grids (get_nl.f90:213-441): in/out arrays are [nphi][nlat] each.
+ * in: vr vt vp cvr cvt cvp s br bt bp cbr cbt cbp (13) ; out: Advr Advt Advp LFr LFt LFp VSr VSt VSp
+ * VxBr VxBt VxBp (12).  Provided so tests can check the grid-space kernel in isolation. */
+void orc_get_nl_mhd(const orc_ctx *c, const orc_params *p, int nR, int nBc, double or2, double or4,
+                    double orho1, const double *const in[13], double *const out[12]);
+
+/* mpi_transpose.f90:307-359,444-530 (type_mpiatoav) emulated in one process for n_procs ranks:
+ * lm2r: arr_LM[p] is rank p's (llm:ulm, n_r_max, n_fields) block -> arr_R[q] (lm_max, nR_loc(q), n_fields)
+ * Layouts follow the Fortran column-major declarations. */
+void orc_transp_lm2r(const orc_ctx *c, int n_procs, int n_r_max, int n_fields, const orc_cplx *const *arr_LM,
+                     orc_cplx *const *arr_R);
+void orc_transp_r2lm(const orc_ctx *c, int n_procs, int n_r_max, int n_fields, const orc_cplx *const *arr_R,
+                     orc_cplx *const *arr_LM);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
