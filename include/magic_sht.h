@@ -1,0 +1,170 @@
+/*
+ * magic_sht.h -- C ABI of magic_b200, the B200-native backend for MagIC's radial-loop hot path.
+ *
+ * This is the drop-in boundary.  A Fortran `module sht` shim binds these entry points
+ * with iso_c_binding exactly the way src/shtns.f90 binds SHTns' C API (shtns.f90:49-98,112-475): the
+ * shim passes the first element of contiguous actuals, the backend owns only its handle, tables and
+ * device buffers.  All `file:line` citations are relative to /root/reference/src/.
+ *
+ * Conventions
+ *   - complex spectra are `double[2*lm_max]` (re,im interleaved = Fortran complex(cp)), st_map order
+ *     (blocking.f90:309-317: do m=0,m_max,minc; do l=m,l_max).
+ *   - grid fields are `double[nlat_padded * n_phi_max]`, theta fastest (Fortran f(nlat_padded,n_phi_max)),
+ *     theta rows N/S interleaved like the native backend (l_scrambled_theta=.true., sht_native.f90:29).
+ *   - every function returns 0 on success, non-zero on failure (the shim calls abortRun, useful.f90:271);
+ *     magic_last_error() gives the message.  There is no CPU fallback: without a CUDA device every
+ *     compute entry point fails.
+ *   - pointers are HOST pointers unless the function name ends in _dev.
+ */
+#ifndef MAGIC_SHT_H
+#define MAGIC_SHT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct magic_sht magic_sht; /* opaque handle: one per MPI rank <-> one GPU (shtns.f90:28 `sht_l`) */
+
+const char *magic_last_error(void);
+int magic_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* initialize_sht / finalize_sht  (sht_native.f90:24-38, shtns.f90:32-100)                          */
+/* l_max,m_max,minc,n_theta_max,n_phi_max: truncation.f90:55-105.  nlat_padded >= n_theta_max is the  */
+/* leading dimension of the caller's grid arrays (truncation::nlat_padded, shtns.f90:65-72).          */
+/* *l_scrambled_theta is set to 1 (N/S interleaved rows).                                             */
+int magic_sht_create(int l_max, int m_max, int minc, int n_theta_max, int n_phi_max, int nlat_padded,
+                     int device_id, int *l_scrambled_theta, magic_sht **out);
+int magic_sht_destroy(magic_sht *h);
+
+/* Gauss-Legendre colatitudes (north->south, radians) and weights as horizontal.f90:279-340 computes
+ * them; lets the host check that both sides use the same grid. */
+int magic_sht_get_grid(const magic_sht *h, double *theta_ord, double *gauss);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* The 17 public procedures of `module sht` (sht_native.f90:16-20 == shtns.f90:22-26).               */
+/* Same argument order and meaning as the Fortran subroutines; lcut = l_R(nR).                        */
+int magic_scal_to_spat(magic_sht *h, const double *Slm, double *fieldc, int lcut);              /* :40  */
+int magic_scal_to_grad_spat(magic_sht *h, const double *Slm, double *gradtc, double *gradpc, int lcut); /* :54 */
+int magic_pol_to_grad_spat(magic_sht *h, const double *Slm, double *gradtc, double *gradpc, int lcut);  /* :70 */
+int magic_torpol_to_spat(magic_sht *h, const double *Wlm, const double *dWlm, const double *Zlm, double *vrc,
+                         double *vtc, double *vpc, int lcut);                                    /* :99  */
+int magic_sphtor_to_spat(magic_sht *h, const double *dWlm, const double *Zlm, double *vtc, double *vpc,
+                         int lcut);                                                               /* :129 */
+int magic_torpol_to_curl_spat_IC(magic_sht *h, double r, double r_ICB, const double *dBlm, const double *ddBlm,
+                                 const double *Jlm, const double *dJlm, double *cbr, double *cbt, double *cbp); /* :143 */
+int magic_torpol_to_spat_IC(magic_sht *h, double r, double r_ICB, const double *Wlm, const double *dWlm,
+                            const double *Zlm, double *Br, double *Bt, double *Bp);             /* :188 */
+int magic_torpol_to_dphspat(magic_sht *h, const double *dWlm, const double *Zlm, double *dvtdp, double *dvpdp,
+                            int lcut);                                                            /* :231 */
+int magic_pol_to_curlr_spat(magic_sht *h, const double *Qlm, double *cvrc, int lcut);           /* :274 */
+int magic_torpol_to_curl_spat(magic_sht *h, double or2, const double *Blm, const double *ddBlm, const double *Jlm,
+                              const double *dJlm, double *cvrc, double *cvtc, double *cvpc, int lcut); /* :302 */
+int magic_scal_to_SH(magic_sht *h, const double *f, double *fLM, int lcut);                     /* :338 */
+int magic_spat_to_qst(magic_sht *h, const double *f, const double *g, const double *hh, double *qLM, double *sLM,
+                      double *tLM, int lcut);                                                     /* :348 */
+int magic_spat_to_sphertor(magic_sht *h, const double *f, const double *g, double *fLM, double *gLM, int lcut); /* :366 */
+int magic_axi_to_spat(magic_sht *h, const double *fl_ax, double *f);                            /* :381 */
+int magic_toraxi_to_spat(magic_sht *h, const double *fl_ax, double *ft, double *fp, int lcut);  /* :393 */
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Batched radial loop: replaces `do nR=nRstart,nRstop` of rIter_single_t%radialLoop                 */
+/* (rIter.f90:190-444) behind a new rIter_cuda_t extends(rIter_t) (rIteration.f90:15-19).            */
+
+/* logic.f90 / physical_parameters.f90 / num_param.f90 values the loop reads (get_nl.f90:24-34,      */
+/* get_td.f90:11-21, courant.f90, rIter.f90:16-40).  Integers are Fortran logicals as 0/1.            */
+typedef struct {
+    int l_conv, l_mag, l_heat, l_conv_nl, l_heat_nl, l_mag_nl, l_mag_LF, l_mag_kin, l_anel, l_adv_curl, l_corr,
+        l_double_curl, l_single_matrix, l_chemical_conv, l_precession, l_centrifuge, l_anelastic_liquid,
+        l_cour_alf_damp, l_full_sphere, l_parallel_solve, l_temperature_diff;
+    int ktopv, kbotv;
+    int l_cond_ma, l_cond_ic, l_rot_ma, l_rot_ic;
+    int n_r_max, n_r_LCR;
+    double LFfac, CorFac, epsc, epscXi, opm, ViscHeatFac, OhmLossFac;
+    double oek, po, prec_angle, dilution_fac, ra, opr;
+    double omega_ma, omega_ic, r_cmb, r_icb;
+    double courfac, alffac;
+} magic_params;
+
+/* radial_functions the loop reads, one entry per LOCAL level (radial.f90:283-307, num_param.f90:30-31). */
+typedef struct {
+    const int *nR;  /* global 1-based level index (n_r_cmb=1 ... n_r_icb=n_r_max) */
+    const int *l_R; /* lcut per level */
+    const double *r, *or1, *or2, *or4, *orho1, *orho2, *beta, *rho0, *otemp1, *temp0, *visc, *lambda, *epscProf,
+        *delxr2, *delxh2;
+} magic_radial;
+
+/* R-distributed inputs X_Rloc(1:lm_max, nRstart:nRstop) = [n_r_loc][lm_max] complex (fields.f90:211-268).
+ * NULL where the switch is off. */
+typedef struct {
+    const double *w, *dw, *ddw, *z, *dz, *s, *ds, *p, *xi, *b, *db, *ddb, *aj, *dj;
+} magic_fields_in;
+
+/* Outputs of radialLoop (rIter.f90:125-147), same layout; dtrkc/dthkc are [n_r_loc] reals. */
+typedef struct {
+    double *dwdt, *dzdt, *dpdt, *dsdt, *dxidt, *dbdt, *djdt, *dVxVhLM, *dVxBhLM, *dVSrLM, *dVXirLM;
+    double *dtrkc, *dthkc;
+} magic_fields_out;
+
+typedef struct magic_rloop magic_rloop;
+
+/* Plan for n_r_loc local levels; level_chunk = number of levels batched per kernel wave (0 = auto from
+ * free HBM).  Copies params/radial to the device. */
+int magic_rloop_create(magic_sht *h, const magic_params *p, const magic_radial *rad, int n_r_loc, int level_chunk,
+                       magic_rloop **out);
+int magic_rloop_destroy(magic_rloop *rl);
+/* Host-pointer call: H2D of the inputs, the loop, D2H of the outputs (what rIter_cuda_t calls). */
+int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const magic_fields_out *out, double time);
+/* Device-pointer call (inputs/outputs already resident in HBM, e.g. produced by magic_transp_*_dev). */
+int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, const magic_fields_out *out, double time);
+/* Stream control + kernel accounting for the benchmark. */
+int magic_rloop_sync(magic_rloop *rl);
+long long magic_rloop_launch_count(const magic_rloop *rl);
+/* Device time (ms, CUDA events on the loop's stream) of the last run, split by stage:
+ * out[0]=total, [1]=synthesis prep, [2]=Legendre synthesis, [3]=c2r FFT, [4]=get_nl, [5]=r2c FFT,
+ * [6]=Legendre analysis, [7]=get_td epilogue. */
+int magic_rloop_last_timing(const magic_rloop *rl, double out[8]);
+/* Algorithmic FP64 flops of the Legendre stage of one run (U * 2*n_theta*lm_max per level). */
+double magic_rloop_legendre_flops(const magic_rloop *rl);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* r <-> LM redistribution: a 5th type_mpitransp (mpi_transpose.f90:18-54), alltoallv semantics of   */
+/* type_mpiatoav (:307-359, :444-530) with the lo<->st permutation fused into pack/unpack.           */
+typedef struct magic_transp magic_transp;
+
+/* NCCL bootstrap: rank 0 calls magic_transp_unique_id and broadcasts the 128 bytes (e.g. MPI_Bcast). */
+int magic_transp_unique_id(char id[128]);
+/* n_r_max levels and lm_max modes over n_procs ranks with getBlocks (parallel.f90:75-92) and
+ * lo_map snake ordering (blocking.f90:387-544); n_fields = container width (fields.f90:211-268). */
+int magic_transp_create(magic_sht *h, const char id[128], int rank, int n_procs, int n_r_max, int n_fields,
+                        magic_transp **out);
+int magic_transp_destroy(magic_transp *t);
+/* Local extents: llm, ulm (1-based inclusive, lo order), nRstart, nRstop. */
+int magic_transp_extents(const magic_transp *t, int *llm, int *ulm, int *nRstart, int *nRstop);
+/* arr_LMloc(llm:ulm, 1:n_r_max, n_fields) -> arr_Rloc(1:lm_max, nRstart:nRstop, n_fields), device pointers. */
+int magic_transp_lm2r_dev(magic_transp *t, const double *arr_LMloc, double *arr_Rloc);
+int magic_transp_r2lm_dev(magic_transp *t, const double *arr_Rloc, double *arr_LMloc);
+/* Host-pointer variants (H2D + exchange + D2H). */
+int magic_transp_lm2r(magic_transp *t, const double *arr_LMloc, double *arr_Rloc);
+int magic_transp_r2lm(magic_transp *t, const double *arr_Rloc, double *arr_LMloc);
+/* Pack/unpack halves only (no exchange), for single-process testing of the permutation kernels:
+ * lm2r: pack_lm2r fills sendbuf (ordered by destination rank, mpi_transpose.f90:320-333);
+ *       unpack_lm2r consumes recvbuf (ordered by source rank, :341-357). */
+int magic_transp_pack_lm2r_dev(magic_transp *t, const double *arr_LMloc, double *sendbuf);
+int magic_transp_unpack_lm2r_dev(magic_transp *t, const double *recvbuf, double *arr_Rloc);
+int magic_transp_pack_r2lm_dev(magic_transp *t, const double *arr_Rloc, double *sendbuf);
+int magic_transp_unpack_r2lm_dev(magic_transp *t, const double *recvbuf, double *arr_LMloc);
+/* counts/displacements in complex elements, length n_procs each (create_comm_alltoallv :120-152). */
+int magic_transp_counts(const magic_transp *t, int dir /*0 lm2r, 1 r2lm*/, long long *scounts, long long *sdisp,
+                        long long *rcounts, long long *rdisp);
+
+/* Device memory helpers so a host language without a CUDA binding can hold device buffers. */
+int magic_dev_malloc(magic_sht *h, size_t bytes, void **ptr);
+int magic_dev_free(magic_sht *h, void *ptr);
+int magic_dev_upload(magic_sht *h, void *dst_dev, const void *src_host, size_t bytes);
+int magic_dev_download(magic_sht *h, void *dst_host, const void *src_dev, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

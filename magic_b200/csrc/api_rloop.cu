@@ -1,0 +1,394 @@
+// api_rloop.cu -- C ABI: the batched radial loop (rIter.f90:94-464 without the output hooks).
+//
+// All local radial levels are processed in chunks of `level_chunk` levels; each chunk is one pass of
+//   synthesis operand assembly -> Legendre GEMM -> c2r FFT -> get_nl(+Courant) -> r2c FFT -> Legendre GEMM
+//   -> extraction -> get_td.
+// Levels are independent, so chunking changes nothing but the batch width.
+#include "../../include/magic_sht.h"
+#include "engine.cuh"
+
+using namespace magic;
+
+enum Src { S_W = 0, S_DW, S_DDW, S_Z, S_DZ, S_S, S_DS, S_P, S_XI, S_B, S_DB, S_DDB, S_AJ, S_DJ, S_COUNT };
+enum OutIdx { O_DWDT = 0, O_DZDT, O_DPDT, O_DSDT, O_DXIDT, O_DBDT, O_DJDT, O_DVXVH, O_DVXBH, O_DVSR, O_DVXIR, O_COUNT };
+
+struct magic_rloop {
+    magic_sht *h = nullptr;
+    magic_params p;
+    int n_r_loc = 0;
+    std::vector<LevelInfo> lev;
+    LevelInfo *d_lev = nullptr;
+    BatchSpec spec;
+    GridIn gi;
+    GridOut go;
+    Buffers buf;
+    std::vector<int> chunk_start, chunk_size;
+    Layout lay[2];  // at most two distinct chunk sizes
+    int lay_size[2] = {0, 0};
+    // nl_lm slots
+    int a_Advr = -1, a_VSr = -1, a_VxBr = -1, a_VXir = -1, a_heat = -1;  // scalar-class analysis columns
+    int a_Adv = -1, a_VS = -1, a_VxB = -1, a_VXi = -1;                    // vector pairs
+    // resident device copies for the host-pointer entry point
+    double *d_in[S_COUNT] = {nullptr};
+    double *d_out[O_COUNT] = {nullptr};
+    double *d_dtrkc = nullptr, *d_dthkc = nullptr;
+    bool need_in[S_COUNT] = {false};
+    bool need_out[O_COUNT] = {false};
+    cudaEvent_t ev[16];
+    double timing[8] = {0};
+    std::vector<float> acc;
+    double legendre_flops = 0;
+    std::vector<const void *> registered;
+};
+
+static void add_scal(BatchSpec &s, Term t0, Term t1, int lmask, int &field_counter, int &slot) {
+    ScalCol c{};
+    c.t[0] = t0; c.t[1] = t1; c.lmask = lmask;
+    s.scal.push_back(c);
+    slot = field_counter++;
+    s.field_s.push_back(slot);
+}
+static void add_pair(BatchSpec &s, Term S0, Term S1, Term T0, Term T1, int lmask, int &field_counter, int &slot_t, int &slot_p) {
+    VecPair v{};
+    v.S[0] = S0; v.S[1] = S1; v.T[0] = T0; v.T[1] = T1; v.lmask = lmask;
+    s.vec.push_back(v);
+    slot_t = field_counter++;
+    slot_p = field_counter++;
+    s.field_v.push_back(slot_t);
+    s.field_v.push_back(slot_p);
+}
+
+extern "C" int magic_rloop_destroy(magic_rloop *rl) {
+    if (!rl) return 0;
+    cudaSetDevice(rl->h->dev);
+    for (const void *p : rl->registered) cudaHostUnregister((void *)p);
+    for (int i = 0; i < 2; i++) layout_free(rl->lay[i]);
+    buffers_free(rl->buf);
+    for (int i = 0; i < S_COUNT; i++) cudaFree(rl->d_in[i]);
+    for (int i = 0; i < O_COUNT; i++) cudaFree(rl->d_out[i]);
+    cudaFree(rl->d_dtrkc); cudaFree(rl->d_dthkc); cudaFree(rl->d_lev);
+    for (int i = 0; i < 16; i++) cudaEventDestroy(rl->ev[i]);
+    delete rl;
+    return 0;
+}
+
+extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const magic_radial *rad, int n_r_loc, int level_chunk,
+                                  magic_rloop **out) {
+    if (!h || !pp || !rad || !out) MFAIL("magic_rloop_create: null argument");
+    if (n_r_loc < 1) MFAIL("magic_rloop_create: n_r_loc < 1");
+    *out = nullptr;
+    MCHECK(cudaSetDevice(h->dev));
+    const magic_params &P = *pp;
+    if (P.l_precession || P.l_centrifuge) {
+        // supported in the kernel; nothing to reject
+    }
+    if (P.l_full_sphere) MFAIL("magic_rloop_create: l_full_sphere (v_center_sphere) is not implemented yet");
+    magic_rloop *rl = new magic_rloop();
+    rl->h = h;
+    rl->p = P;
+    rl->n_r_loc = n_r_loc;
+    for (int i = 0; i < 16; i++) cudaEventCreate(&rl->ev[i]);
+
+    // ---- per-level flags, rIter.f90:181-218
+    bool lMagNlBc = false;
+    if (((P.l_mag_nl || P.l_mag_kin) && (P.ktopv == 1 || P.l_cond_ma || (P.ktopv == 2 && P.l_rot_ma))) ||
+        (P.kbotv == 1 || P.l_cond_ic || (P.kbotv == 2 && P.l_rot_ic)))
+        lMagNlBc = true;
+    rl->lev.resize(n_r_loc);
+    for (int i = 0; i < n_r_loc; i++) {
+        LevelInfo &L = rl->lev[i];
+        memset(&L, 0, sizeof(L));
+        L.nR = rad->nR[i];
+        L.lcut = rad->l_R[i];
+        if (L.lcut < 0 || L.lcut > h->l_max) { magic_rloop_destroy(rl); MFAIL("magic_rloop_create: l_R out of range"); }
+        bool is_cmb = L.nR == 1, is_icb = L.nR == P.n_r_max;
+        bool l_bound = is_cmb || is_icb;
+        int nBc = 0, lDeriv = 1;
+        if (is_cmb) { nBc = P.ktopv; lDeriv = 0; }
+        else if (is_icb) { nBc = P.kbotv; lDeriv = 0; }
+        bool loop_bound = l_bound;
+        if (P.l_parallel_solve || (P.l_single_matrix && P.l_temperature_diff)) { lDeriv = 1; nBc = 0; loop_bound = false; }
+        L.nBc = nBc; L.lDeriv = lDeriv; L.l_bound = l_bound ? 1 : 0;
+        L.nl_on = (!loop_bound || lMagNlBc) ? 1 : 0;
+        L.cour_on = (!P.l_full_sphere || !is_icb) ? 1 : 0;
+        L.r = rad->r[i]; L.or1 = rad->or1[i]; L.or2 = rad->or2[i]; L.or4 = rad->or4[i]; L.orho1 = rad->orho1[i];
+        L.orho2 = rad->orho2[i]; L.beta = rad->beta[i]; L.rho0 = rad->rho0[i]; L.otemp1 = rad->otemp1[i]; L.temp0 = rad->temp0[i];
+        L.visc = rad->visc[i]; L.lambda = rad->lambda[i]; L.epscProf = rad->epscProf[i]; L.delxr2 = rad->delxr2[i];
+        L.delxh2 = rad->delxh2[i];
+    }
+    if (dev_upload_vec(&rl->d_lev, rl->lev)) { magic_rloop_destroy(rl); return 1; }
+
+    // ---- column program, transform_to_grid_space rIter.f90:466-622
+    BatchSpec &S = rl->spec;
+    GridIn &gi = rl->gi;
+    int *gip = (int *)&gi;
+    for (size_t i = 0; i < sizeof(GridIn) / sizeof(int); i++) gip[i] = -1;
+    const Term N_ = {0, F_NONE};
+    int nf = 0;
+    double units_syn = 0, units_an = 0;  // scalar-equivalent Legendre passes per bulk level
+    if (P.l_conv || P.l_mag_kin) {
+        if (P.l_heat) { add_scal(S, Term{S_S, F_ONE}, N_, LM_ALL, nf, gi.s); rl->need_in[S_S] = true; units_syn += 1; }
+        if (P.l_chemical_conv) { add_scal(S, Term{S_XI, F_ONE}, N_, LM_ALL, nf, gi.xi); rl->need_in[S_XI] = true; units_syn += 1; }
+        rl->need_in[S_W] = rl->need_in[S_DW] = rl->need_in[S_Z] = true;
+        add_scal(S, Term{S_W, F_DLH}, N_, LM_VEL, nf, gi.vr);
+        add_pair(S, Term{S_DW, F_ONE}, N_, Term{S_Z, F_ONE}, N_, LM_VEL, nf, gi.vt, gi.vp);
+        units_syn += 5;
+        if (P.l_adv_curl) {
+            rl->need_in[S_DDW] = rl->need_in[S_DZ] = true;
+            add_scal(S, Term{S_Z, F_DLH}, N_, LM_VELBULK, nf, gi.cvr);
+            add_pair(S, Term{S_DZ, F_ONE}, N_, Term{S_W, F_OR2DLH}, Term{S_DDW, F_NEG}, LM_VELBULK, nf, gi.cvt, gi.cvp);
+            units_syn += 5;
+        } else {
+            rl->need_in[S_DDW] = rl->need_in[S_DZ] = true;
+            add_scal(S, Term{S_DW, F_DLH}, N_, LM_VELBULK, nf, gi.dvrdr);
+            add_pair(S, Term{S_DDW, F_ONE}, N_, Term{S_DZ, F_ONE}, N_, LM_VELBULK, nf, gi.dvtdr, gi.dvpdr);
+            add_scal(S, Term{S_Z, F_DLH}, N_, LM_VELBULK, nf, gi.cvr);
+            add_pair(S, Term{S_W, F_DLH}, N_, N_, N_, LM_VELBULK, nf, gi.dvrdt, gi.dvrdp);
+            add_pair(S, Term{S_DW, F_IM}, N_, Term{S_Z, F_IM}, N_, LM_VELBULK, nf, gi.dvtdp, gi.dvpdp);
+            units_syn += 5 + 1 + 2 + 4;
+        }
+    }
+    if (P.l_mag || P.l_mag_LF) {
+        rl->need_in[S_B] = rl->need_in[S_DB] = rl->need_in[S_AJ] = rl->need_in[S_DDB] = rl->need_in[S_DJ] = true;
+        add_scal(S, Term{S_B, F_DLH}, N_, LM_ALL, nf, gi.br);
+        add_pair(S, Term{S_DB, F_ONE}, N_, Term{S_AJ, F_ONE}, N_, LM_ALL, nf, gi.bt, gi.bp);
+        add_scal(S, Term{S_AJ, F_DLH}, N_, LM_DERIV, nf, gi.cbr);
+        add_pair(S, Term{S_DJ, F_ONE}, N_, Term{S_B, F_OR2DLH}, Term{S_DDB, F_NEG}, LM_DERIV, nf, gi.cbt, gi.cbp);
+        units_syn += 10;
+    }
+    S.nfield_in = nf;
+    // ---- products and their analysis, transform_to_lm_space rIter.f90:624-712
+    GridOut &go = rl->go;
+    int *gop = (int *)&go;
+    for (size_t i = 0; i < sizeof(GridOut) / sizeof(int); i++) gop[i] = -1;
+    int no = 0;
+    auto add_qst = [&](int &fr, int &ft, int &fp, int &slot_s, int &slot_v) {
+        fr = no++; ft = no++; fp = no++;
+        slot_s = (int)S.afield_s.size();
+        S.afield_s.push_back(fr);
+        slot_v = (int)S.afield_vt.size();
+        S.afield_vt.push_back(ft);
+        S.afield_vp.push_back(fp);
+        units_an += 5;
+    };
+    if (P.l_conv_nl || P.l_mag_LF) add_qst(go.Advr, go.Advt, go.Advp, rl->a_Advr, rl->a_Adv);
+    if (P.l_heat) {
+        add_qst(go.VSr, go.VSt, go.VSp, rl->a_VSr, rl->a_VS);
+        if (P.l_anel) { go.heat = no++; rl->a_heat = (int)S.afield_s.size(); S.afield_s.push_back(go.heat); units_an += 1; }
+    }
+    if (P.l_chemical_conv) add_qst(go.VXir, go.VXit, go.VXip, rl->a_VXir, rl->a_VXi);
+    if (P.l_mag_nl) add_qst(go.VxBr, go.VxBt, go.VxBp, rl->a_VxBr, rl->a_VxB);
+    S.nfield_out = no;
+    rl->legendre_flops = (units_syn + units_an) * 2.0 * (double)h->n_theta * (double)h->lm_max * (double)n_r_loc;
+
+    // ---- outputs needed
+    if (P.l_conv) { rl->need_out[O_DZDT] = rl->need_out[O_DWDT] = true; if (P.l_double_curl) rl->need_out[O_DVXVH] = true; }
+    if (!P.l_double_curl) rl->need_out[O_DPDT] = true;
+    if (P.l_heat) rl->need_out[O_DSDT] = rl->need_out[O_DVSR] = true;
+    if (P.l_chemical_conv) rl->need_out[O_DXIDT] = rl->need_out[O_DVXIR] = true;
+    if (P.l_mag) rl->need_out[O_DBDT] = rl->need_out[O_DJDT] = rl->need_out[O_DVXBH] = true;
+
+    // ---- chunking
+    if (level_chunk <= 0) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        Layout probe;
+        layout_sizes(h, S, 1, probe);
+        double per_level = 8.0 * ((double)probe.szBs + probe.szBv + probe.szFs + probe.szFv + probe.szBas + probe.szBav + probe.szCas + probe.szCav) +
+                           8.0 * 2.0 * h->nh * h->n_phi * (S.nfield_in + S.nfield_out);
+        level_chunk = (int)std::max(1.0, std::min((double)n_r_loc, 0.6 * (double)free_b / per_level));
+        level_chunk = std::min(level_chunk, 64);
+    }
+    level_chunk = std::min(level_chunk, n_r_loc);
+    int nchunks = (n_r_loc + level_chunk - 1) / level_chunk;
+    int base = n_r_loc / nchunks, rem = n_r_loc % nchunks, pos = 0;
+    for (int c = 0; c < nchunks; c++) {
+        int sz = base + (c < rem ? 1 : 0);
+        rl->chunk_start.push_back(pos);
+        rl->chunk_size.push_back(sz);
+        pos += sz;
+    }
+    rl->lay_size[0] = base + (rem ? 1 : 0);
+    rl->lay_size[1] = rem ? base : 0;
+    layout_sizes(h, S, rl->lay_size[0], rl->lay[0]);
+    if (buffers_alloc(h, S, rl->lay[0], rl->buf)) { magic_rloop_destroy(rl); return 1; }
+    if (layout_bind(h, S, rl->lay[0], rl->buf)) { magic_rloop_destroy(rl); return 1; }
+    if (rl->lay_size[1]) {
+        layout_sizes(h, S, rl->lay_size[1], rl->lay[1]);
+        if (layout_bind(h, S, rl->lay[1], rl->buf)) { magic_rloop_destroy(rl); return 1; }
+    }
+    MCHECK(cudaMalloc((void **)&rl->d_dtrkc, sizeof(double) * n_r_loc));
+    MCHECK(cudaMalloc((void **)&rl->d_dthkc, sizeof(double) * n_r_loc));
+    *out = rl;
+    return 0;
+}
+
+static const double *const *in_ptrs(const magic_fields_in *in, const double *tmp[S_COUNT]) {
+    tmp[S_W] = in->w; tmp[S_DW] = in->dw; tmp[S_DDW] = in->ddw; tmp[S_Z] = in->z; tmp[S_DZ] = in->dz; tmp[S_S] = in->s;
+    tmp[S_DS] = in->ds; tmp[S_P] = in->p; tmp[S_XI] = in->xi; tmp[S_B] = in->b; tmp[S_DB] = in->db; tmp[S_DDB] = in->ddb;
+    tmp[S_AJ] = in->aj; tmp[S_DJ] = in->dj;
+    return tmp;
+}
+static void out_ptrs(const magic_fields_out *o, double *tmp[O_COUNT]) {
+    tmp[O_DWDT] = o->dwdt; tmp[O_DZDT] = o->dzdt; tmp[O_DPDT] = o->dpdt; tmp[O_DSDT] = o->dsdt; tmp[O_DXIDT] = o->dxidt;
+    tmp[O_DBDT] = o->dbdt; tmp[O_DJDT] = o->djdt; tmp[O_DVXVH] = o->dVxVhLM; tmp[O_DVXBH] = o->dVxBhLM; tmp[O_DVSR] = o->dVSrLM;
+    tmp[O_DVXIR] = o->dVXirLM;
+}
+
+extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, const magic_fields_out *out, double time) {
+    if (!rl || !in || !out) MFAIL("magic_rloop_run_dev: null argument");
+    magic_sht *h = rl->h;
+    MCHECK(cudaSetDevice(h->dev));
+    const magic_params &P = rl->p;
+    const double *ip[S_COUNT];
+    double *op[O_COUNT];
+    in_ptrs(in, ip);
+    out_ptrs(out, op);
+    for (int i = 0; i < S_COUNT; i++)
+        if (rl->need_in[i] && !ip[i]) MFAIL("magic_rloop_run_dev: a required input field is null");
+    for (int i = 0; i < O_COUNT; i++)
+        if (rl->need_out[i] && !op[i]) MFAIL("magic_rloop_run_dev: a required output field is null");
+    if (!out->dtrkc || !out->dthkc) MFAIL("magic_rloop_run_dev: dtrkc/dthkc are null");
+    const size_t lm2 = 2 * (size_t)h->lm_max;
+    const size_t plane = (size_t)h->nh * h->n_phi;
+    rl->acc.assign(8, 0.f);
+    struct ChunkEv { int c; };
+    std::vector<float> stage(8, 0.f);
+    cudaEventRecord(rl->ev[15], h->stream);
+    for (size_t c = 0; c < rl->chunk_start.size(); c++) {
+        const int l0 = rl->chunk_start[c], nl = rl->chunk_size[c];
+        const Layout &L = (nl == rl->lay_size[0]) ? rl->lay[0] : rl->lay[1];
+        const LevelInfo *d_lev = rl->d_lev + l0;
+        const double *src[MAGIC_MAX_SRC];
+        for (int i = 0; i < MAGIC_MAX_SRC; i++) src[i] = (i < S_COUNT && ip[i]) ? ip[i] + (size_t)l0 * lm2 : nullptr;
+        if (run_synthesis(h, rl->spec, L, rl->buf, src, d_lev, rl->ev)) return 1;
+        // ---- get_nl + Courant
+        MCHECK(cudaMemsetAsync(rl->buf.courmax, 0, sizeof(unsigned long long) * 2 * nl, h->stream));
+        NlArgs a{};
+        NlFlags &F = a.f;
+        F.l_conv_nl = P.l_conv_nl; F.l_heat_nl = P.l_heat_nl; F.l_mag_nl = P.l_mag_nl; F.l_mag_LF = P.l_mag_LF; F.l_mag = P.l_mag;
+        F.l_mag_kin = P.l_mag_kin; F.l_adv_curl = P.l_adv_curl; F.l_anel = P.l_anel; F.l_chemical_conv = P.l_chemical_conv;
+        F.l_precession = P.l_precession; F.l_centrifuge = P.l_centrifuge; F.l_cour_alf_damp = P.l_cour_alf_damp;
+        F.l_full_sphere = P.l_full_sphere; F.n_r_LCR = P.n_r_LCR;
+        F.LFfac = P.LFfac; F.opm = P.opm; F.ViscHeatFac = P.ViscHeatFac; F.OhmLossFac = P.OhmLossFac; F.oek = P.oek; F.po = P.po;
+        F.prec_angle = P.prec_angle; F.dilution_fac = P.dilution_fac; F.ra = P.ra; F.opr = P.opr; F.omega_ma = P.omega_ma;
+        F.omega_ic = P.omega_ic; F.r_cmb = P.r_cmb; F.r_icb = P.r_icb; F.courfac = P.courfac; F.alffac = P.alffac; F.time = time;
+        a.gi = rl->gi; a.go = rl->go; a.gin = rl->buf.gin; a.gout = rl->buf.gout; a.n_lev = nl; a.nh = h->nh; a.n_phi = h->n_phi;
+        a.minc = h->minc; a.lev = d_lev; a.sinth = h->d_sinth; a.costh = h->d_costh; a.courmax = rl->buf.courmax;
+        int gx = (int)std::min<size_t>((plane + NL_THREADS - 1) / NL_THREADS, 4096);
+        get_nl_kernel<<<dim3(gx, nl), NL_THREADS, 0, h->stream>>>(a);
+        courant_finish_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(rl->buf.courmax, d_lev, nl, out->dtrkc + l0, out->dthkc + l0);
+        h->launches += 2;
+        cudaEventRecord(rl->ev[4], h->stream);
+        if (run_analysis(h, rl->spec, L, rl->buf, d_lev, rl->ev + 5)) return 1;  // ev[5..7]
+        cudaEventRecord(rl->ev[8], h->stream);
+        // ---- get_td
+        TdArgs t{};
+        t.f.l_conv = P.l_conv; t.f.l_mag = P.l_mag; t.f.l_heat = P.l_heat; t.f.l_conv_nl = P.l_conv_nl; t.f.l_mag_nl = P.l_mag_nl;
+        t.f.l_mag_kin = P.l_mag_kin; t.f.l_anel = P.l_anel; t.f.l_corr = P.l_corr; t.f.l_double_curl = P.l_double_curl;
+        t.f.l_single_matrix = P.l_single_matrix; t.f.l_chemical_conv = P.l_chemical_conv; t.f.l_anelastic_liquid = P.l_anelastic_liquid;
+        t.f.CorFac = P.CorFac; t.f.epsc = P.epsc; t.f.epscXi = P.epscXi;
+        t.n_lev = nl; t.lm_max = h->lm_max; t.l_max = h->l_max; t.minc = h->minc; t.lm2l = h->d_lm2l; t.lm2m = h->d_lm2m; t.lev = d_lev;
+        const size_t fs = (size_t)nl * lm2;  // one extracted field
+        auto ns = [&](int slot) -> const double * { return slot < 0 ? nullptr : rl->buf.nl_s + (size_t)slot * fs; };
+        auto nv = [&](int pair, int comp) -> const double * { return pair < 0 ? nullptr : rl->buf.nl_v + (size_t)(2 * pair + comp) * fs; };
+        t.AdvrLM = ns(rl->a_Advr); t.AdvtLM = nv(rl->a_Adv, 0); t.AdvpLM = nv(rl->a_Adv, 1);
+        t.VxBrLM = ns(rl->a_VxBr); t.VxBtLM = nv(rl->a_VxB, 0); t.VxBpLM = nv(rl->a_VxB, 1);
+        t.VSrLM = ns(rl->a_VSr); t.VStLM = nv(rl->a_VS, 0);
+        t.VXirLM = ns(rl->a_VXir); t.VXitLM = nv(rl->a_VXi, 0);
+        t.heatLM = ns(rl->a_heat);
+        t.w = src[S_W]; t.dw = src[S_DW]; t.ddw = src[S_DDW]; t.z = src[S_Z]; t.dz = src[S_DZ];
+        auto o = [&](int i) -> double * { return op[i] ? op[i] + (size_t)l0 * lm2 : nullptr; };
+        t.dwdt = o(O_DWDT); t.dzdt = o(O_DZDT); t.dpdt = o(O_DPDT); t.dsdt = o(O_DSDT); t.dxidt = o(O_DXIDT); t.dbdt = o(O_DBDT);
+        t.djdt = o(O_DJDT); t.dVxVhLM = o(O_DVXVH); t.dVxBhLM = o(O_DVXBH); t.dVSrLM = o(O_DVSR); t.dVXirLM = o(O_DVXIR);
+        get_td_kernel<<<dim3((h->lm_max + 255) / 256, nl), 256, 0, h->stream>>>(t);
+        h->launches++;
+        cudaEventRecord(rl->ev[9], h->stream);
+        MCHECK(cudaGetLastError());
+        if (rl->chunk_start.size() > 1 || true) {
+            // per-stage device times of this chunk (the sync also bounds the number of in-flight chunks)
+            MCHECK(cudaEventSynchronize(rl->ev[9]));
+            float ms;
+            const int pairs[7][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {5, 6}, {6, 7}, {7, 9}};
+            for (int s = 0; s < 7; s++) {
+                cudaEventElapsedTime(&ms, rl->ev[pairs[s][0]], rl->ev[pairs[s][1]]);
+                stage[s + 1] += ms;
+            }
+        }
+    }
+    cudaEventRecord(rl->ev[14], h->stream);
+    MCHECK(cudaEventSynchronize(rl->ev[14]));
+    float tot;
+    cudaEventElapsedTime(&tot, rl->ev[15], rl->ev[14]);
+    stage[0] = tot;
+    for (int i = 0; i < 8; i++) rl->timing[i] = stage[i];
+    return 0;
+}
+
+static void try_register(magic_rloop *rl, const void *p, size_t bytes) {
+    if (!p) return;
+    for (const void *q : rl->registered)
+        if (q == p) return;
+    if (cudaHostRegister((void *)p, bytes, cudaHostRegisterDefault) == cudaSuccess) rl->registered.push_back(p);
+    else cudaGetLastError();  // already pinned or not registrable: plain pageable copies still work
+}
+
+extern "C" int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const magic_fields_out *out, double time) {
+    if (!rl || !in || !out) MFAIL("magic_rloop_run: null argument");
+    magic_sht *h = rl->h;
+    MCHECK(cudaSetDevice(h->dev));
+    const size_t fbytes = sizeof(double) * 2 * (size_t)h->lm_max * rl->n_r_loc;
+    const double *ip[S_COUNT];
+    double *op[O_COUNT];
+    in_ptrs(in, ip);
+    out_ptrs(out, op);
+    magic_fields_in din{};
+    magic_fields_out dout{};
+    const double *dip[S_COUNT] = {nullptr};
+    for (int i = 0; i < S_COUNT; i++) {
+        if (!rl->need_in[i]) continue;
+        if (!ip[i]) MFAIL("magic_rloop_run: a required input field is null");
+        if (!rl->d_in[i]) MCHECK(cudaMalloc((void **)&rl->d_in[i], fbytes));
+        try_register(rl, ip[i], fbytes);
+        MCHECK(cudaMemcpyAsync(rl->d_in[i], ip[i], fbytes, cudaMemcpyHostToDevice, h->stream));
+        dip[i] = rl->d_in[i];
+    }
+    din.w = dip[S_W]; din.dw = dip[S_DW]; din.ddw = dip[S_DDW]; din.z = dip[S_Z]; din.dz = dip[S_DZ]; din.s = dip[S_S]; din.ds = dip[S_DS];
+    din.p = dip[S_P]; din.xi = dip[S_XI]; din.b = dip[S_B]; din.db = dip[S_DB]; din.ddb = dip[S_DDB]; din.aj = dip[S_AJ]; din.dj = dip[S_DJ];
+    double *dop[O_COUNT] = {nullptr};
+    for (int i = 0; i < O_COUNT; i++) {
+        if (!rl->need_out[i]) continue;
+        if (!op[i]) MFAIL("magic_rloop_run: a required output field is null");
+        if (!rl->d_out[i]) {
+            MCHECK(cudaMalloc((void **)&rl->d_out[i], fbytes));
+            MCHECK(cudaMemsetAsync(rl->d_out[i], 0, fbytes, h->stream));
+        }
+        try_register(rl, op[i], fbytes);
+        dop[i] = rl->d_out[i];
+    }
+    dout.dwdt = dop[O_DWDT]; dout.dzdt = dop[O_DZDT]; dout.dpdt = dop[O_DPDT]; dout.dsdt = dop[O_DSDT]; dout.dxidt = dop[O_DXIDT];
+    dout.dbdt = dop[O_DBDT]; dout.djdt = dop[O_DJDT]; dout.dVxVhLM = dop[O_DVXVH]; dout.dVxBhLM = dop[O_DVXBH];
+    dout.dVSrLM = dop[O_DVSR]; dout.dVXirLM = dop[O_DVXIR];
+    dout.dtrkc = rl->d_dtrkc; dout.dthkc = rl->d_dthkc;
+    if (magic_rloop_run_dev(rl, &din, &dout, time)) return 1;
+    for (int i = 0; i < O_COUNT; i++)
+        if (rl->need_out[i]) MCHECK(cudaMemcpyAsync(op[i], rl->d_out[i], fbytes, cudaMemcpyDeviceToHost, h->stream));
+    MCHECK(cudaMemcpyAsync(out->dtrkc, rl->d_dtrkc, sizeof(double) * rl->n_r_loc, cudaMemcpyDeviceToHost, h->stream));
+    MCHECK(cudaMemcpyAsync(out->dthkc, rl->d_dthkc, sizeof(double) * rl->n_r_loc, cudaMemcpyDeviceToHost, h->stream));
+    MCHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int magic_rloop_sync(magic_rloop *rl) {
+    if (!rl) MFAIL("null rloop");
+    MCHECK(cudaSetDevice(rl->h->dev));
+    MCHECK(cudaStreamSynchronize(rl->h->stream));
+    return 0;
+}
+extern "C" long long magic_rloop_launch_count(const magic_rloop *rl) { return rl ? rl->h->launches : 0; }
+extern "C" int magic_rloop_last_timing(const magic_rloop *rl, double out[8]) {
+    if (!rl) MFAIL("null rloop");
+    for (int i = 0; i < 8; i++) out[i] = rl->timing[i];
+    return 0;
+}
+extern "C" double magic_rloop_legendre_flops(const magic_rloop *rl) { return rl ? rl->legendre_flops : 0.0; }

@@ -1,0 +1,367 @@
+// api_transp.cu -- C ABI: r <-> LM redistribution (a 5th `type_mpitransp`, mpi_transpose.f90:18-54) with
+// the alltoallv semantics of type_mpiatoav: pack (:320-333 / :490-506), exchange, permuting unpack
+// (:341-357 / :515-528).  The exchange is a grouped ncclSend/ncclRecv all-to-all over NVLink; NCCL is
+// resolved at run time (dlopen) so the library loads on machines without it and single-rank use needs none.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "../../include/magic_sht.h"
+#include "engine.cuh"
+
+using namespace magic;
+
+namespace {
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+    if (g_nccl.lib) return 0;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) MFAIL(std::string("cannot load NCCL: ") + dlerror());
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
+    g_nccl.Send = (decltype(g_nccl.Send))dlsym(lib, "ncclSend");
+    g_nccl.Recv = (decltype(g_nccl.Recv))dlsym(lib, "ncclRecv");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(lib, "ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(lib, "ncclGroupEnd");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd)
+        MFAIL("NCCL library lacks required symbols");
+    g_nccl.lib = lib;
+    return 0;
+}
+
+#define NCHECK(call)                                                                                      \
+    do {                                                                                                  \
+        ncclResult_t r__ = (call);                                                                        \
+        if (r__ != ncclSuccess) {                                                                         \
+            magic::g_last_error = std::string(#call) + " -> " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error"); \
+            return 1;                                                                                     \
+        }                                                                                                 \
+    } while (0)
+
+// getBlocks, parallel.f90:75-92 (1-based inclusive)
+void get_blocks(int n_points, int n_procs, std::vector<int> &start, std::vector<int> &stop) {
+    start.assign(n_procs, 0);
+    stop.assign(n_procs, 0);
+    int n_loc = n_points / n_procs, rem = n_points - n_loc * n_procs;
+    for (int p = 0; p < n_procs; p++) {
+        start[p] = n_loc * p + std::max(p + rem - n_procs, 0) + 1;
+        stop[p] = n_loc * (p + 1) + std::max(p + rem + 1 - n_procs, 0);
+        if (p != 0) start[p] = stop[p - 1] + 1;
+    }
+}
+
+// lo_map: snake ordering for n_procs <= l_max/2 (blocking.f90:387-544), else l-major (blocking.f90:339-385).
+// Returns lo2st (0-based st index of each lo position) and the 1-based inclusive lm range of every rank.
+void build_lo_map(const magic_sht *h, int n_procs, std::vector<int> &lo2st, std::vector<int> &lm_start, std::vector<int> &lm_stop) {
+    const int l_max = h->l_max, m_max = h->m_max, minc = h->minc;
+    auto st_index = [&](int l, int m) { return h->lstart[m / minc] + (l - m); };
+    lo2st.clear();
+    if (n_procs <= l_max / 2) {
+        // deal degrees l_max..0 to ranks 0,1,..,n-1,n-1,..,0,0,1,.. ("snake")
+        std::vector<std::vector<int>> lists(n_procs);
+        int proc = 0, owner_of_l0 = 0;
+        bool up = true;
+        for (int l = l_max; l >= 0; l--) {
+            lists[proc].push_back(l);
+            if (l == 0) owner_of_l0 = proc;
+            if (up) { if (proc < n_procs - 1) proc++; else up = false; }
+            else { if (proc > 0) proc--; else up = true; }
+        }
+        // rotate so that the owner of l=0 becomes rank 0: follow the cycle pc <- (owner+pc) mod n until it closes
+        if (owner_of_l0 != 0) {
+            std::vector<int> saved = lists[0];
+            int pc = 0;
+            for (;;) {
+                int src = (owner_of_l0 + pc) % n_procs;
+                if (src != 0) lists[pc] = lists[src];
+                else { lists[pc] = saved; break; }
+                pc = src;
+            }
+        }
+        for (size_t i = 0; i < lists[0].size(); i++)
+            if (lists[0][i] == 0) { std::swap(lists[0][0], lists[0][i]); break; }
+        lm_start.assign(n_procs, 0);
+        lm_stop.assign(n_procs, 0);
+        for (int p = 0; p < n_procs; p++) {
+            lm_start[p] = (int)lo2st.size() + 1;
+            for (int l : lists[p])
+                for (int m = 0; m <= std::min(m_max, l); m += minc) lo2st.push_back(st_index(l, m));
+            lm_stop[p] = (int)lo2st.size();
+        }
+    } else {
+        get_blocks(h->lm_max, n_procs, lm_start, lm_stop);
+        for (int l = 0; l <= l_max; l++)
+            for (int m = 0; m <= std::min(m_max, l); m += minc) lo2st.push_back(st_index(l, m));
+    }
+}
+
+// ---- kernels: one thread per complex element of the packed buffer --------------------------------------
+struct PackArgs {
+    int n_procs, n_fields, n_r_max, lm_max;
+    int llm, nlm;          // my lm slab (0-based start in lo order, count)
+    int r0, nr;            // my radial slab (0-based start, count)
+    const int *rstart;     // [n_procs] 0-based first level of each rank
+    const int *rcount;     // [n_procs]
+    const int *lstart;     // [n_procs] 0-based first lo index of each rank
+    const int *lcount;     // [n_procs]
+    const long long *disp; // [n_procs+1] element displacement of each peer segment
+    const int *lo2st;
+};
+
+__device__ __forceinline__ int find_seg(const long long *disp, int n, long long idx) {
+    int lo = 0, hi = n;  // disp[lo] <= idx < disp[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (disp[mid] <= idx) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// segment q of the LM-side buffer: [f][n_r in block q][lm in my slab]
+__global__ void lmside_kernel(PackArgs a, const double2 *__restrict__ arr_LM_in, double2 *__restrict__ arr_LM_out,
+                              const double2 *__restrict__ buf_in, double2 *__restrict__ buf_out, long long total) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int q = find_seg(a.disp, a.n_procs, idx);
+    long long rel = idx - a.disp[q];
+    int lm = (int)(rel % a.nlm);
+    long long t = rel / a.nlm;
+    int r = (int)(t % a.rcount[q]), f = (int)(t / a.rcount[q]);
+    size_t pos = (size_t)lm + (size_t)a.nlm * ((size_t)(a.rstart[q] + r) + (size_t)a.n_r_max * f);
+    if (buf_out) buf_out[idx] = arr_LM_in[pos];   // pack   (mpi_transpose.f90:320-333)
+    else arr_LM_out[pos] = buf_in[idx];           // unpack (mpi_transpose.f90:515-528)
+}
+
+// segment p of the R-side buffer: [f][n_r in my slab][lm in rank p's lo slab], permuted to st order
+__global__ void rside_kernel(PackArgs a, const double2 *__restrict__ arr_R_in, double2 *__restrict__ arr_R_out,
+                             const double2 *__restrict__ buf_in, double2 *__restrict__ buf_out, long long total) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int p = find_seg(a.disp, a.n_procs, idx);
+    long long rel = idx - a.disp[p];
+    int lm = (int)(rel % a.lcount[p]);
+    long long t = rel / a.lcount[p];
+    int r = (int)(t % a.nr), f = (int)(t / a.nr);
+    int lm_st = a.lo2st[a.lstart[p] + lm];
+    size_t pos = (size_t)lm_st + (size_t)a.lm_max * ((size_t)r + (size_t)a.nr * f);
+    if (buf_out) buf_out[idx] = arr_R_in[pos];    // pack   (mpi_transpose.f90:490-506)
+    else arr_R_out[pos] = buf_in[idx];            // unpack (mpi_transpose.f90:341-357)
+}
+
+}  // namespace
+
+struct magic_transp {
+    magic_sht *h = nullptr;
+    int rank = 0, n_procs = 1, n_r_max = 0, n_fields = 0;
+    std::vector<int> rs, re, ls, le, lo2st;
+    std::vector<long long> lmside_cnt, lmside_disp, rside_cnt, rside_disp;  // complex elements
+    int *d_rstart = nullptr, *d_rcount = nullptr, *d_lstart = nullptr, *d_lcount = nullptr, *d_lo2st = nullptr;
+    long long *d_lmdisp = nullptr, *d_rdisp = nullptr;
+    double *sendbuf = nullptr, *recvbuf = nullptr, *stage_lm = nullptr, *stage_r = nullptr;
+    ncclComm_t comm = nullptr;
+    PackArgs args;
+};
+
+extern "C" int magic_transp_unique_id(char id[128]) {
+    if (nccl_load()) return 1;
+    ncclUniqueId uid;
+    NCHECK(g_nccl.GetUniqueId(&uid));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(id, &uid, 128);
+    return 0;
+}
+
+extern "C" int magic_transp_destroy(magic_transp *t) {
+    if (!t) return 0;
+    cudaSetDevice(t->h->dev);
+    if (t->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(t->comm);
+    cudaFree(t->d_rstart); cudaFree(t->d_rcount); cudaFree(t->d_lstart); cudaFree(t->d_lcount); cudaFree(t->d_lo2st);
+    cudaFree(t->d_lmdisp); cudaFree(t->d_rdisp); cudaFree(t->sendbuf); cudaFree(t->recvbuf); cudaFree(t->stage_lm); cudaFree(t->stage_r);
+    delete t;
+    return 0;
+}
+
+extern "C" int magic_transp_create(magic_sht *h, const char id[128], int rank, int n_procs, int n_r_max, int n_fields,
+                                   magic_transp **out) {
+    if (!h || !out) MFAIL("magic_transp_create: null argument");
+    *out = nullptr;
+    if (n_procs < 1 || rank < 0 || rank >= n_procs || n_r_max < n_procs || n_fields < 1) MFAIL("magic_transp_create: bad arguments");
+    if (n_procs > h->lm_max) MFAIL("magic_transp_create: more ranks than (l,m) modes");
+    MCHECK(cudaSetDevice(h->dev));
+    magic_transp *t = new magic_transp();
+    t->h = h; t->rank = rank; t->n_procs = n_procs; t->n_r_max = n_r_max; t->n_fields = n_fields;
+    get_blocks(n_r_max, n_procs, t->rs, t->re);
+    build_lo_map(h, n_procs, t->lo2st, t->ls, t->le);
+    const int nlm = t->le[rank] - t->ls[rank] + 1, nr = t->re[rank] - t->rs[rank] + 1;
+    std::vector<int> rstart(n_procs), rcount(n_procs), lstart(n_procs), lcount(n_procs);
+    t->lmside_cnt.assign(n_procs, 0); t->lmside_disp.assign(n_procs + 1, 0);
+    t->rside_cnt.assign(n_procs, 0); t->rside_disp.assign(n_procs + 1, 0);
+    for (int p = 0; p < n_procs; p++) {
+        rstart[p] = t->rs[p] - 1; rcount[p] = t->re[p] - t->rs[p] + 1;
+        lstart[p] = t->ls[p] - 1; lcount[p] = t->le[p] - t->ls[p] + 1;
+        // create_comm_alltoallv, mpi_transpose.f90:134-139
+        t->lmside_cnt[p] = (long long)rcount[p] * nlm * n_fields;
+        t->rside_cnt[p] = (long long)nr * lcount[p] * n_fields;
+        t->lmside_disp[p + 1] = t->lmside_disp[p] + t->lmside_cnt[p];
+        t->rside_disp[p + 1] = t->rside_disp[p] + t->rside_cnt[p];
+    }
+    if (dev_upload_vec(&t->d_rstart, rstart) || dev_upload_vec(&t->d_rcount, rcount) || dev_upload_vec(&t->d_lstart, lstart) ||
+        dev_upload_vec(&t->d_lcount, lcount) || dev_upload_vec(&t->d_lo2st, t->lo2st) || dev_upload_vec(&t->d_lmdisp, t->lmside_disp) ||
+        dev_upload_vec(&t->d_rdisp, t->rside_disp)) {
+        magic_transp_destroy(t);
+        return 1;
+    }
+    PackArgs &a = t->args;
+    a.n_procs = n_procs; a.n_fields = n_fields; a.n_r_max = n_r_max; a.lm_max = h->lm_max;
+    a.llm = t->ls[rank] - 1; a.nlm = nlm; a.r0 = t->rs[rank] - 1; a.nr = nr;
+    a.rstart = t->d_rstart; a.rcount = t->d_rcount; a.lstart = t->d_lstart; a.lcount = t->d_lcount; a.lo2st = t->d_lo2st;
+    a.disp = nullptr;
+    size_t maxel = (size_t)std::max(t->lmside_disp[n_procs], t->rside_disp[n_procs]);
+    MCHECK(cudaMalloc((void **)&t->sendbuf, sizeof(double) * 2 * maxel));
+    MCHECK(cudaMalloc((void **)&t->recvbuf, sizeof(double) * 2 * maxel));
+    if (n_procs > 1) {
+        if (!id) { magic_transp_destroy(t); MFAIL("magic_transp_create: NCCL id required for n_procs > 1"); }
+        if (nccl_load()) { magic_transp_destroy(t); return 1; }
+        ncclUniqueId uid;
+        memcpy(&uid, id, 128);
+        ncclResult_t r = g_nccl.CommInitRank(&t->comm, n_procs, uid, rank);
+        if (r != ncclSuccess) {
+            g_last_error = std::string("ncclCommInitRank -> ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+            t->comm = nullptr;
+            magic_transp_destroy(t);
+            return 1;
+        }
+    }
+    *out = t;
+    return 0;
+}
+
+extern "C" int magic_transp_extents(const magic_transp *t, int *llm, int *ulm, int *nRstart, int *nRstop) {
+    if (!t) MFAIL("null transposer");
+    *llm = t->ls[t->rank]; *ulm = t->le[t->rank]; *nRstart = t->rs[t->rank]; *nRstop = t->re[t->rank];
+    return 0;
+}
+
+extern "C" int magic_transp_counts(const magic_transp *t, int dir, long long *scounts, long long *sdisp, long long *rcounts,
+                                   long long *rdisp) {
+    if (!t) MFAIL("null transposer");
+    const auto &sc = dir == 0 ? t->lmside_cnt : t->rside_cnt, &sd = dir == 0 ? t->lmside_disp : t->rside_disp;
+    const auto &rc = dir == 0 ? t->rside_cnt : t->lmside_cnt, &rd = dir == 0 ? t->rside_disp : t->lmside_disp;
+    for (int p = 0; p < t->n_procs; p++) { scounts[p] = sc[p]; sdisp[p] = sd[p]; rcounts[p] = rc[p]; rdisp[p] = rd[p]; }
+    return 0;
+}
+
+static int side_launch(magic_transp *t, bool lmside, const double *arr_in, double *arr_out, const double *buf_in, double *buf_out) {
+    PackArgs a = t->args;
+    a.disp = lmside ? t->d_lmdisp : t->d_rdisp;
+    long long total = lmside ? t->lmside_disp[t->n_procs] : t->rside_disp[t->n_procs];
+    if (total == 0) return 0;
+    int blocks = (int)((total + 255) / 256);
+    if (lmside)
+        lmside_kernel<<<blocks, 256, 0, t->h->stream>>>(a, (const double2 *)arr_in, (double2 *)arr_out, (const double2 *)buf_in, (double2 *)buf_out, total);
+    else
+        rside_kernel<<<blocks, 256, 0, t->h->stream>>>(a, (const double2 *)arr_in, (double2 *)arr_out, (const double2 *)buf_in, (double2 *)buf_out, total);
+    t->h->launches++;
+    MCHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int magic_transp_pack_lm2r_dev(magic_transp *t, const double *arr_LMloc, double *sendbuf) {
+    if (!t) MFAIL("null transposer");
+    MCHECK(cudaSetDevice(t->h->dev));
+    return side_launch(t, true, arr_LMloc, nullptr, nullptr, sendbuf);
+}
+extern "C" int magic_transp_unpack_lm2r_dev(magic_transp *t, const double *recvbuf, double *arr_Rloc) {
+    if (!t) MFAIL("null transposer");
+    MCHECK(cudaSetDevice(t->h->dev));
+    return side_launch(t, false, nullptr, arr_Rloc, recvbuf, nullptr);
+}
+extern "C" int magic_transp_pack_r2lm_dev(magic_transp *t, const double *arr_Rloc, double *sendbuf) {
+    if (!t) MFAIL("null transposer");
+    MCHECK(cudaSetDevice(t->h->dev));
+    return side_launch(t, false, arr_Rloc, nullptr, nullptr, sendbuf);
+}
+extern "C" int magic_transp_unpack_r2lm_dev(magic_transp *t, const double *recvbuf, double *arr_LMloc) {
+    if (!t) MFAIL("null transposer");
+    MCHECK(cudaSetDevice(t->h->dev));
+    return side_launch(t, true, nullptr, arr_LMloc, recvbuf, nullptr);
+}
+
+// all-to-all(v): segment p of sendbuf goes to rank p, segment p of recvbuf comes from rank p
+static int exchange(magic_transp *t, const std::vector<long long> &scnt, const std::vector<long long> &sdisp,
+                    const std::vector<long long> &rcnt, const std::vector<long long> &rdisp) {
+    cudaStream_t st = t->h->stream;
+    const int me = t->rank;
+    MCHECK(cudaMemcpyAsync(t->recvbuf + 2 * rdisp[me], t->sendbuf + 2 * sdisp[me], sizeof(double) * 2 * scnt[me], cudaMemcpyDeviceToDevice, st));
+    if (t->n_procs == 1) return 0;
+    NCHECK(g_nccl.GroupStart());
+    for (int p = 0; p < t->n_procs; p++) {
+        if (p == me) continue;
+        NCHECK(g_nccl.Send(t->sendbuf + 2 * sdisp[p], (size_t)(2 * scnt[p]), ncclDouble, p, t->comm, st));
+        NCHECK(g_nccl.Recv(t->recvbuf + 2 * rdisp[p], (size_t)(2 * rcnt[p]), ncclDouble, p, t->comm, st));
+    }
+    NCHECK(g_nccl.GroupEnd());
+    return 0;
+}
+
+extern "C" int magic_transp_lm2r_dev(magic_transp *t, const double *arr_LMloc, double *arr_Rloc) {
+    if (!t) MFAIL("null transposer");
+    MCHECK(cudaSetDevice(t->h->dev));
+    if (side_launch(t, true, arr_LMloc, nullptr, nullptr, t->sendbuf)) return 1;
+    if (exchange(t, t->lmside_cnt, t->lmside_disp, t->rside_cnt, t->rside_disp)) return 1;
+    return side_launch(t, false, nullptr, arr_Rloc, t->recvbuf, nullptr);
+}
+
+extern "C" int magic_transp_r2lm_dev(magic_transp *t, const double *arr_Rloc, double *arr_LMloc) {
+    if (!t) MFAIL("null transposer");
+    MCHECK(cudaSetDevice(t->h->dev));
+    if (side_launch(t, false, arr_Rloc, nullptr, nullptr, t->sendbuf)) return 1;
+    if (exchange(t, t->rside_cnt, t->rside_disp, t->lmside_cnt, t->lmside_disp)) return 1;
+    return side_launch(t, true, nullptr, arr_LMloc, t->recvbuf, nullptr);
+}
+
+static int ensure_stage(magic_transp *t) {
+    if (t->stage_lm) return 0;
+    MCHECK(cudaMalloc((void **)&t->stage_lm, sizeof(double) * 2 * (size_t)t->lmside_disp[t->n_procs]));
+    MCHECK(cudaMalloc((void **)&t->stage_r, sizeof(double) * 2 * (size_t)t->rside_disp[t->n_procs]));
+    return 0;
+}
+
+extern "C" int magic_transp_lm2r(magic_transp *t, const double *arr_LMloc, double *arr_Rloc) {
+    if (!t) MFAIL("null transposer");
+    MCHECK(cudaSetDevice(t->h->dev));
+    if (ensure_stage(t)) return 1;
+    size_t blm = sizeof(double) * 2 * (size_t)t->lmside_disp[t->n_procs], br = sizeof(double) * 2 * (size_t)t->rside_disp[t->n_procs];
+    MCHECK(cudaMemcpyAsync(t->stage_lm, arr_LMloc, blm, cudaMemcpyHostToDevice, t->h->stream));
+    if (magic_transp_lm2r_dev(t, t->stage_lm, t->stage_r)) return 1;
+    MCHECK(cudaMemcpyAsync(arr_Rloc, t->stage_r, br, cudaMemcpyDeviceToHost, t->h->stream));
+    MCHECK(cudaStreamSynchronize(t->h->stream));
+    return 0;
+}
+
+extern "C" int magic_transp_r2lm(magic_transp *t, const double *arr_Rloc, double *arr_LMloc) {
+    if (!t) MFAIL("null transposer");
+    MCHECK(cudaSetDevice(t->h->dev));
+    if (ensure_stage(t)) return 1;
+    size_t blm = sizeof(double) * 2 * (size_t)t->lmside_disp[t->n_procs], br = sizeof(double) * 2 * (size_t)t->rside_disp[t->n_procs];
+    MCHECK(cudaMemcpyAsync(t->stage_r, arr_Rloc, br, cudaMemcpyHostToDevice, t->h->stream));
+    if (magic_transp_r2lm_dev(t, t->stage_r, t->stage_lm)) return 1;
+    MCHECK(cudaMemcpyAsync(arr_LMloc, t->stage_lm, blm, cudaMemcpyDeviceToHost, t->h->stream));
+    MCHECK(cudaStreamSynchronize(t->h->stream));
+    return 0;
+}

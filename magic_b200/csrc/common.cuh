@@ -1,0 +1,63 @@
+// common.cuh -- shared structures of magic_b200 (device + host).  Layouts are described in DESIGN.md.
+//
+//   table   per order mc four row blocks [P_even][D_odd][P_odd][D_even]; one row per degree l, NHP doubles
+//           per row (northern colatitudes k=0..nh-1, zero padded to a multiple of 16).  P = Plm,
+//           D = dPlm = sin(theta) dP/dtheta of shtransforms.f90:38-91 / plms.f90:14-189.
+//   B       Legendre-GEMM right operand, [K_pad][N] row-major per problem, N a multiple of 64,
+//           column n = (col*n_lev + lev)*2 + reim.
+//   F       (theta,m)-space, per problem (mc, s) a [nh][N] matrix with the same columns as B.
+//   grid    g[field][lev][s][k][phi]: phi fastest; s=0 holds the equatorially symmetric part E, s=1 the
+//           antisymmetric part O of the pair (north row k, south row k): north = E+O, south = E-O.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MAGIC_MAX_SRC 16
+
+namespace magic {
+
+constexpr int BK = 16;  // Legendre GEMM k-tile; all K extents are padded to multiples of BK
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 64;
+
+struct GemmProb {
+    const double *A0, *A1;  // two K segments of the table operand
+    const double *B;
+    double *C;
+    int kt0, kt1;  // k-tiles per segment
+    int M;         // valid rows of C
+    int ldb, ldc;  // leading dimensions of B and C (doubles)
+    int pad;
+};
+
+// factor applied to a spectral source when assembling synthesis operands (sht_native.f90 wrappers)
+enum FType : int { F_NONE = 0, F_ONE = 1, F_DLH = 2, F_OR2DLH = 3, F_NEG = 4, F_IM = 5 };
+struct Term { int src; int ftype; };
+// which local levels a column is computed on (rIter.f90:466-622)
+enum LMask : int { LM_ALL = 0, LM_VEL = 1, LM_VELBULK = 2, LM_DERIV = 3 };
+struct ScalCol { Term t[2]; int lmask; int pad; };
+struct VecPair { Term S[2]; Term T[2]; int lmask; int pad; };
+
+struct LevelInfo {  // per local level, device resident
+    int nR, lcut, nBc, lDeriv, nl_on, l_bound, cour_on, pad1;
+    double r, or1, or2, or4, orho1, orho2, beta, rho0, otemp1, temp0, visc, lambda, epscProf, delxr2, delxh2;
+};
+
+struct FftPlan {
+    int N, H, nfac;
+    int fac[16];
+    const double2 *tw;  // device: exp(+2 pi i k/N), k=0..N-1
+};
+
+// r2c destination: the FFT of a grid row (field,lev,s,k) is scaled and written into an analysis operand
+enum RType : int { R_NONE = 0, R_W = 1, R_WS = 2, R_NEG_WS = 3, R_MIM_WS = 4 };
+struct R2cDest {
+    int cls;    // 0 scalar-class operand, 1 vector-class operand
+    int col;    // complex column index (before *n_lev)
+    int p;      // parity problem receiving the row
+    int seg;    // 0: P segment rows [0,NHP), 1: D segment rows [NHP,2NHP)
+    int rtype;  // RType
+};
+struct R2cField { R2cDest d[2][2]; };  // [s][dest]
+
+}  // namespace magic

@@ -1,0 +1,369 @@
+// engine.cu -- SHT handle, batch layouts and pipeline stages of magic_b200.
+#include "engine.cuh"
+
+#include <algorithm>
+
+namespace magic {
+
+thread_local std::string g_last_error;
+
+// horizontal.f90:279-340 gauleg(-1,1,...) on the host (n_theta Newton solves; same iteration as the reference)
+static void gauleg_host(int n, std::vector<double> &theta_ord, std::vector<double> &gauss) {
+    const double pi = 3.14159265358979323846264338327950288;
+    const double eps = 10.0 * 2.220446049250313e-16;
+    theta_ord.assign(n, 0.0);
+    gauss.assign(n, 0.0);
+    int m = (n + 1) / 2;
+    for (int i = 1; i <= m; i++) {
+        double z = cos(pi * (((double)i - 0.25) / ((double)n + 0.5)));
+        double z1 = z + 10.0 * eps, p1 = 0, p2 = 0, p3, pp = 1;
+        while (fabs(z - z1) > eps) {
+            p1 = 1.0;
+            p2 = 0.0;
+            for (int j = 1; j <= n; j++) {
+                p3 = p2;
+                p2 = p1;
+                p1 = ((double)(2 * j - 1) * z * p2 - (double)(j - 1) * p3) / (double)j;
+            }
+            pp = (double)n * (z * p1 - p2) / (z * z - 1.0);
+            z1 = z;
+            z = z1 - p1 / pp;
+        }
+        theta_ord[i - 1] = acos(z);
+        theta_ord[n - i] = acos(-z);
+        gauss[i - 1] = 2.0 / ((1.0 - z * z) * pp * pp);
+        gauss[n - i] = gauss[i - 1];
+    }
+}
+
+static bool factor_fft(int H, FftPlan &p) {
+    p.nfac = 0;
+    int n = H;
+    while (n % 4 == 0) { p.fac[p.nfac++] = 4; n /= 4; }
+    while (n % 2 == 0) { p.fac[p.nfac++] = 2; n /= 2; }
+    while (n % 3 == 0) { p.fac[p.nfac++] = 3; n /= 3; }
+    while (n % 5 == 0) { p.fac[p.nfac++] = 5; n /= 5; }
+    return n == 1 && p.nfac <= 16;
+}
+
+int sht_init(magic_sht *h) {
+    const int l_max = h->l_max, minc = h->minc, n_m = h->n_m, nh = h->nh;
+    MCHECK(cudaSetDevice(h->dev));
+    MCHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    // st_map (blocking.f90:309-317)
+    h->lm2l.clear(); h->lm2m.clear(); h->lstart.assign(n_m, 0); h->ne.assign(n_m, 0); h->no.assign(n_m, 0);
+    for (int mc = 0; mc < n_m; mc++) {
+        int m = mc * minc;
+        h->lstart[mc] = (int)h->lm2l.size();
+        for (int l = m; l <= l_max; l++) { h->lm2l.push_back(l); h->lm2m.push_back(m); }
+        h->ne[mc] = (l_max - m) / 2 + 1;
+        h->no[mc] = (l_max - m + 1) / 2;
+    }
+    if ((int)h->lm2l.size() != h->lm_max) MFAIL("internal: lm_max mismatch");
+    gauleg_host(h->n_theta, h->theta_ord, h->gauss);
+    // table block offsets
+    h->off.assign((size_t)n_m * 4, 0);
+    long long pos = 0;
+    for (int mc = 0; mc < n_m; mc++) {
+        int rows[4] = {h->ne[mc], h->no[mc], h->no[mc], h->ne[mc]};
+        for (int b = 0; b < 4; b++) { h->off[(size_t)mc * 4 + b] = pos; pos += (long long)rows[b] * h->NHP; }
+    }
+    long long tab_doubles = pos + (long long)(GEMM_BM + 2 * BK) * std::max(h->NHP, GEMM_BM) + 1024;
+    MCHECK(cudaMalloc((void **)&h->d_tab, sizeof(double) * tab_doubles));
+    MCHECK(cudaMemsetAsync(h->d_tab, 0, sizeof(double) * tab_doubles, h->stream));
+    if (dev_upload_vec(&h->d_off, h->off)) return 1;
+    std::vector<double> sinth(nh), costh(nh), wg(nh), os2(nh), pmm(n_m);
+    const double pi = 3.14159265358979323846264338327950288;
+    for (int k = 0; k < nh; k++) {
+        double colat = h->theta_ord[k];
+        sinth[k] = sin(colat);
+        costh[k] = cos(colat);
+        wg[k] = 2.0 * pi * h->gauss[k] / (double)h->n_phi;
+        os2[k] = 1.0 / (sin(colat) * sin(colat));
+    }
+    for (int mc = 0; mc < n_m; mc++) {  // plms.f90:54-59
+        int m = mc * minc;
+        double fac = 1.0;
+        for (int j = 3; j <= 2 * m + 1; j += 2) fac = fac * (double)j / (double)(j - 1);
+        pmm[mc] = sqrt(fac);
+    }
+    double *d_pmm = nullptr;
+    if (dev_upload_vec(&h->d_sinth, sinth) || dev_upload_vec(&h->d_costh, costh) || dev_upload_vec(&h->d_wgauss, wg) ||
+        dev_upload_vec(&h->d_osin2, os2) || dev_upload_vec(&d_pmm, pmm) || dev_upload_vec(&h->d_lm2l, h->lm2l) ||
+        dev_upload_vec(&h->d_lm2m, h->lm2m) || dev_upload_vec(&h->d_lstart, h->lstart))
+        return 1;
+    {
+        dim3 grid((nh + 127) / 128, n_m);
+        build_tables_kernel<<<grid, 128, 0, h->stream>>>(h->d_tab, h->d_off, h->d_sinth, h->d_costh, d_pmm, nh, h->NHP, l_max, minc, n_m);
+        MCHECK(cudaGetLastError());
+    }
+    // FFT plan
+    h->fft.N = h->n_phi;
+    h->fft.H = h->n_phi / 2;
+    if (!factor_fft(h->fft.H, h->fft)) MFAIL("n_phi_max/2 must factor into 2,3,5 (fft.f90 supports radices 2,3,4,5)");
+    std::vector<double2> tw(h->n_phi);
+    for (int k = 0; k < h->n_phi; k++) {
+        long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)h->n_phi;
+        tw[k] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+    if (dev_upload_vec(&h->d_tw, tw)) return 1;
+    h->fft.tw = h->d_tw;
+    MCHECK(gemm_setup_attributes());
+    MCHECK(cudaFuncSetAttribute(fft_c2r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MCHECK(cudaFuncSetAttribute(fft_r2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MCHECK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_pmm);
+    return 0;
+}
+
+void sht_free(magic_sht *h) {
+    cudaFree(h->d_tab); cudaFree(h->d_off); cudaFree(h->d_sinth); cudaFree(h->d_costh); cudaFree(h->d_wgauss);
+    cudaFree(h->d_osin2); cudaFree(h->d_lm2l); cudaFree(h->d_lm2m); cudaFree(h->d_lstart); cudaFree(h->d_tw);
+    if (h->stream) cudaStreamDestroy(h->stream);
+}
+
+// ------------------------------------------------------------------------------------------------------
+void layout_sizes(const magic_sht *h, const BatchSpec &spec, int n_lev, Layout &L) {
+    const int n_m = h->n_m, nh = h->nh, NHP = h->NHP;
+    L.n_lev = n_lev;
+    L.ncol_s = (int)spec.scal.size();
+    L.npair_v = (int)spec.vec.size();
+    L.Ns = L.ncol_s ? pad_up(2 * L.ncol_s * n_lev, GEMM_BN) : 0;
+    L.Nv = L.npair_v ? pad_up(4 * L.npair_v * n_lev, GEMM_BN) : 0;
+    L.nf_s = (int)spec.afield_s.size();
+    L.npair_a = (int)spec.afield_vt.size();
+    L.Nas = L.nf_s ? pad_up(2 * L.nf_s * n_lev, GEMM_BN) : 0;
+    L.Nav = L.npair_a ? pad_up(4 * L.npair_a * n_lev, GEMM_BN) : 0;
+    L.offBs.assign((size_t)n_m * 2, 0); L.offBv.assign((size_t)n_m * 2, 0);
+    L.offCas.assign((size_t)n_m * 2, 0); L.offCav.assign((size_t)n_m * 2, 0);
+    long long pbs = 0, pbv = 0, pcs = 0, pcv = 0;
+    L.n_kts = L.n_ktv = 0;
+    for (int mc = 0; mc < n_m; mc++)
+        for (int s = 0; s < 2; s++) {
+            int prob = mc * 2 + s;
+            int Ks = s == 0 ? h->ne[mc] : h->no[mc], Ko = s == 0 ? h->no[mc] : h->ne[mc];
+            int kts = (Ks + BK - 1) / BK, kto = (Ko + BK - 1) / BK;
+            L.offBs[prob] = pbs; pbs += (long long)kts * BK * L.Ns;
+            L.offBv[prob] = pbv; pbv += (long long)(kts + kto) * BK * L.Nv;
+            L.offCas[prob] = pcs; pcs += (long long)Ks * L.Nas;
+            L.offCav[prob] = pcv; pcv += (long long)Ks * L.Nav;
+            if (L.ncol_s) L.n_kts += kts;
+            if (L.npair_v) L.n_ktv += kts + kto;
+        }
+    L.szBs = pbs; L.szBv = pbv;
+    L.szFs = (long long)n_m * 2 * nh * L.Ns; L.szFv = (long long)n_m * 2 * nh * L.Nv;
+    L.szBas = (long long)n_m * 2 * NHP * L.Nas; L.szBav = (long long)n_m * 2 * 2 * NHP * L.Nav;
+    L.szCas = pcs + (long long)GEMM_BM * L.Nas; L.szCav = pcv + (long long)GEMM_BM * L.Nav;
+}
+
+int buffers_alloc(magic_sht *h, const BatchSpec &spec, const Layout &L, Buffers &b) {
+    size_t plane = (size_t)2 * h->nh * h->n_phi;
+    struct { double **p; long long n; } items[] = {
+        {&b.Bs, L.szBs}, {&b.Bv, L.szBv}, {&b.Fs, L.szFs}, {&b.Fv, L.szFv},
+        {&b.gin, (long long)(plane * spec.nfield_in * L.n_lev)}, {&b.gout, (long long)(plane * spec.nfield_out * L.n_lev)},
+        {&b.Bas, L.szBas}, {&b.Bav, L.szBav}, {&b.Cas, L.szCas}, {&b.Cav, L.szCav},
+        {&b.nl_s, (long long)2 * L.nf_s * L.n_lev * h->lm_max}, {&b.nl_v, (long long)4 * L.npair_a * L.n_lev * h->lm_max}};
+    b.bytes = 0;
+    for (auto &it : items) {
+        size_t bytes = sizeof(double) * (size_t)std::max<long long>(it.n, 1);
+        MCHECK(cudaMalloc((void **)it.p, bytes));
+        MCHECK(cudaMemsetAsync(*it.p, 0, bytes, h->stream));
+        b.bytes += bytes;
+    }
+    MCHECK(cudaMalloc((void **)&b.courmax, sizeof(unsigned long long) * 2 * std::max(L.n_lev, 1)));
+    MCHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+void buffers_free(Buffers &b) {
+    double *ps[] = {b.Bs, b.Bv, b.Fs, b.Fv, b.gin, b.gout, b.Bas, b.Bav, b.Cas, b.Cav, b.nl_s, b.nl_v};
+    for (double *p : ps) cudaFree(p);
+    cudaFree(b.courmax);
+    b = Buffers();
+}
+
+void layout_free(Layout &L) {
+    cudaFree(L.d_offBs); cudaFree(L.d_offBv); cudaFree(L.d_offCas); cudaFree(L.d_offCav); cudaFree(L.d_kts); cudaFree(L.d_ktv);
+    cudaFree(L.d_probs_syn); cudaFree(L.d_probs_an); cudaFree(L.d_tiles_syn); cudaFree(L.d_tiles_an);
+    cudaFree(L.d_colrow_s); cudaFree(L.d_colrow_v); cudaFree(L.d_scal); cudaFree(L.d_vec); cudaFree(L.d_r2c);
+    L = Layout();
+}
+
+int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &buf) {
+    const int n_m = h->n_m, nh = h->nh, NHP = h->NHP, n_lev = L.n_lev;
+    std::vector<KTile> kts, ktv;
+    std::vector<GemmProb> ps, pa;
+    std::vector<int2> ts, ta;
+    const int mt_syn = (nh + GEMM_BM - 1) / GEMM_BM;
+    for (int mc = 0; mc < n_m; mc++) {
+        const double *Pe = h->d_tab + h->off[(size_t)mc * 4 + 0], *Do = h->d_tab + h->off[(size_t)mc * 4 + 1];
+        const double *Po = h->d_tab + h->off[(size_t)mc * 4 + 2], *De = h->d_tab + h->off[(size_t)mc * 4 + 3];
+        // ---- synthesis problems: vector class first (largest K), then scalar class
+        for (int cls = 1; cls >= 0; cls--) {
+            if ((cls == 1 && !L.npair_v) || (cls == 0 && !L.ncol_s)) continue;
+            for (int s = 0; s < 2; s++) {
+                int prob = mc * 2 + s;
+                int Ks = s == 0 ? h->ne[mc] : h->no[mc], Ko = s == 0 ? h->no[mc] : h->ne[mc];
+                int kt0 = (Ks + BK - 1) / BK, kt1 = (Ko + BK - 1) / BK;
+                GemmProb g{};
+                g.A0 = s == 0 ? Pe : Po;
+                g.M = nh;
+                if (cls == 1) {
+                    g.A1 = s == 0 ? Do : De;
+                    g.kt0 = kt0; g.kt1 = kt1;
+                    g.B = buf.Bv + L.offBv[prob];
+                    g.C = buf.Fv + (size_t)prob * nh * L.Nv;
+                    g.ldb = g.ldc = L.Nv;
+                    for (int kt = 0; kt < kt0; kt++) ktv.push_back(KTile{prob, kt, 0, kt});
+                    for (int kt = 0; kt < kt1; kt++) ktv.push_back(KTile{prob, kt0 + kt, 1, kt});
+                } else {
+                    g.A1 = g.A0;
+                    g.kt0 = kt0; g.kt1 = 0;
+                    g.B = buf.Bs + L.offBs[prob];
+                    g.C = buf.Fs + (size_t)prob * nh * L.Ns;
+                    g.ldb = g.ldc = L.Ns;
+                    for (int kt = 0; kt < kt0; kt++) kts.push_back(KTile{prob, kt, 0, kt});
+                }
+                int pid = (int)ps.size();
+                ps.push_back(g);
+                int ntn = g.ldb / GEMM_BN;
+                for (int mt = 0; mt < mt_syn; mt++)
+                    for (int nt = 0; nt < ntn; nt++) ts.push_back(make_int2(pid, (mt << 16) | nt));
+                L.flops_syn += 2.0 * nh * (double)(g.kt0 + g.kt1) * BK * g.ldb;
+            }
+        }
+        // ---- analysis problems
+        for (int cls = 1; cls >= 0; cls--) {
+            if ((cls == 1 && !L.npair_a) || (cls == 0 && !L.nf_s)) continue;
+            for (int p = 0; p < 2; p++) {
+                int prob = mc * 2 + p;
+                int Kp = p == 0 ? h->ne[mc] : h->no[mc];
+                if (Kp == 0) continue;
+                GemmProb g{};
+                g.A0 = p == 0 ? Pe : Po;
+                g.A1 = p == 0 ? De : Do;
+                g.M = Kp;
+                g.kt0 = NHP / BK;
+                if (cls == 1) {
+                    g.kt1 = NHP / BK;
+                    g.B = buf.Bav + (size_t)prob * 2 * NHP * L.Nav;
+                    g.C = buf.Cav + L.offCav[prob];
+                    g.ldb = g.ldc = L.Nav;
+                } else {
+                    g.kt1 = 0;
+                    g.B = buf.Bas + (size_t)prob * NHP * L.Nas;
+                    g.C = buf.Cas + L.offCas[prob];
+                    g.ldb = g.ldc = L.Nas;
+                }
+                int pid = (int)pa.size();
+                pa.push_back(g);
+                int ntn = g.ldb / GEMM_BN, ntm = (Kp + GEMM_BM - 1) / GEMM_BM;
+                for (int mt = 0; mt < ntm; mt++)
+                    for (int nt = 0; nt < ntn; nt++) ta.push_back(make_int2(pid, (mt << 16) | nt));
+                L.flops_an += 2.0 * Kp * (double)(g.kt0 + g.kt1) * BK * g.ldb;
+            }
+        }
+    }
+    L.n_kts = (int)kts.size(); L.n_ktv = (int)ktv.size();
+    L.ntiles_syn = (int)ts.size(); L.ntiles_an = (int)ta.size();
+    std::vector<int> crs((size_t)L.ncol_s * n_lev), crv((size_t)2 * L.npair_v * n_lev);
+    for (int c = 0; c < L.ncol_s; c++)
+        for (int lev = 0; lev < n_lev; lev++) crs[(size_t)c * n_lev + lev] = spec.field_s[c] < 0 ? -1 : spec.field_s[c] * n_lev + lev;
+    for (int c = 0; c < 2 * L.npair_v; c++)
+        for (int lev = 0; lev < n_lev; lev++) crv[(size_t)c * n_lev + lev] = spec.field_v[c] < 0 ? -1 : spec.field_v[c] * n_lev + lev;
+    std::vector<R2cField> r2c(std::max(spec.nfield_out, 1));
+    for (auto &f : r2c)
+        for (int s = 0; s < 2; s++)
+            for (int d = 0; d < 2; d++) f.d[s][d] = R2cDest{0, 0, 0, 0, R_NONE};
+    for (int i = 0; i < L.nf_s; i++)
+        for (int s = 0; s < 2; s++) r2c[spec.afield_s[i]].d[s][0] = R2cDest{0, i, s, 0, R_W};
+    for (int i = 0; i < L.npair_a; i++) {
+        int ft = spec.afield_vt[i], fp = spec.afield_vp[i];
+        // SURVEY.md appendix A / shtransforms.f90:821-860: A=fft(vp)/sin^2, B=fft(vt)/sin^2
+        r2c[ft].d[0][0] = R2cDest{1, 2 * i, 1, 1, R_WS};          // B+ -> odd  S, D segment
+        r2c[ft].d[0][1] = R2cDest{1, 2 * i + 1, 0, 0, R_MIM_WS};  // B+ -> even T, P segment
+        r2c[ft].d[1][0] = R2cDest{1, 2 * i, 0, 1, R_WS};          // B- -> even S, D segment
+        r2c[ft].d[1][1] = R2cDest{1, 2 * i + 1, 1, 0, R_MIM_WS};  // B- -> odd  T, P segment
+        r2c[fp].d[0][0] = R2cDest{1, 2 * i, 0, 0, R_MIM_WS};      // A+ -> even S, P segment
+        r2c[fp].d[0][1] = R2cDest{1, 2 * i + 1, 1, 1, R_NEG_WS};  // A+ -> odd  T, D segment
+        r2c[fp].d[1][0] = R2cDest{1, 2 * i, 1, 0, R_MIM_WS};      // A- -> odd  S, P segment
+        r2c[fp].d[1][1] = R2cDest{1, 2 * i + 1, 0, 1, R_NEG_WS};  // A- -> even T, D segment
+    }
+    if (dev_upload_vec(&L.d_offBs, L.offBs) || dev_upload_vec(&L.d_offBv, L.offBv) || dev_upload_vec(&L.d_offCas, L.offCas) ||
+        dev_upload_vec(&L.d_offCav, L.offCav) || dev_upload_vec(&L.d_kts, kts) || dev_upload_vec(&L.d_ktv, ktv) ||
+        dev_upload_vec(&L.d_probs_syn, ps) || dev_upload_vec(&L.d_probs_an, pa) || dev_upload_vec(&L.d_tiles_syn, ts) ||
+        dev_upload_vec(&L.d_tiles_an, ta) || dev_upload_vec(&L.d_colrow_s, crs) || dev_upload_vec(&L.d_colrow_v, crv) ||
+        dev_upload_vec(&L.d_scal, spec.scal) || dev_upload_vec(&L.d_vec, spec.vec) || dev_upload_vec(&L.d_r2c, r2c))
+        return 1;
+    return 0;
+}
+
+int layout_build(magic_sht *h, const BatchSpec &spec, int n_lev, Layout &L) {
+    layout_sizes(h, spec, n_lev, L);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+int run_synthesis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buffers &buf, const double *const src[MAGIC_MAX_SRC],
+                  const LevelInfo *d_lev, cudaEvent_t *ev) {
+    (void)spec;
+    SynthPrepArgs a{};
+    for (int i = 0; i < MAGIC_MAX_SRC; i++) a.src[i] = src[i];
+    a.scal = L.d_scal; a.vec = L.d_vec;
+    a.ncol_s = L.ncol_s; a.npair_v = L.npair_v; a.n_lev = L.n_lev; a.lm_max = h->lm_max;
+    a.Ns = L.Ns; a.Nv = L.Nv; a.lev = d_lev; a.lstart = h->d_lstart; a.l_max = h->l_max; a.minc = h->minc;
+    a.Bs = buf.Bs; a.Bv = buf.Bv; a.offBs = L.d_offBs; a.offBv = L.d_offBv; a.kts = L.d_kts; a.ktv = L.d_ktv;
+    if (ev) cudaEventRecord(ev[0], h->stream);
+    if (L.ncol_s && L.n_kts) { synth_prep_scal_kernel<<<L.n_kts, 256, 0, h->stream>>>(a); h->launches++; }
+    if (L.npair_v && L.n_ktv) { synth_prep_vec_kernel<<<L.n_ktv, 256, 0, h->stream>>>(a); h->launches++; }
+    if (ev) cudaEventRecord(ev[1], h->stream);
+    launch_legendre_gemm(false, L.d_probs_syn, L.d_tiles_syn, L.ntiles_syn, h->NHP, h->stream);
+    h->launches++;
+    if (ev) cudaEventRecord(ev[2], h->stream);
+    const int R = fft_rows_per_cta(h->fft.H, 8);
+    const size_t smem = (size_t)2 * R * h->fft.H * sizeof(double2);
+    if (L.ncol_s) {
+        int ncols = L.ncol_s * L.n_lev;
+        dim3 grid((ncols + R - 1) / R, 2 * h->nh);
+        fft_c2r_kernel<<<grid, FFT_THREADS, smem, h->stream>>>(h->fft, buf.Fs, L.Ns, h->n_m, h->nh, ncols, L.d_colrow_s, buf.gin, R);
+        h->launches++;
+    }
+    if (L.npair_v) {
+        int ncols = 2 * L.npair_v * L.n_lev;
+        dim3 grid((ncols + R - 1) / R, 2 * h->nh);
+        fft_c2r_kernel<<<grid, FFT_THREADS, smem, h->stream>>>(h->fft, buf.Fv, L.Nv, h->n_m, h->nh, ncols, L.d_colrow_v, buf.gin, R);
+        h->launches++;
+    }
+    if (ev) cudaEventRecord(ev[3], h->stream);
+    MCHECK(cudaGetLastError());
+    return 0;
+}
+
+int run_analysis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buffers &buf, const LevelInfo *d_lev, cudaEvent_t *ev) {
+    if (spec.nfield_out == 0) return 0;
+    const int R = fft_rows_per_cta(h->fft.H, 8);
+    const size_t smem = (size_t)2 * R * h->fft.H * sizeof(double2);
+    R2cArgs a{};
+    a.grid = buf.gout; a.n_lev = L.n_lev; a.nh = h->nh; a.n_m = h->n_m; a.NHP = h->NHP;
+    a.wgauss = h->d_wgauss; a.osin2 = h->d_osin2; a.fields = L.d_r2c;
+    a.B[0] = buf.Bas; a.B[1] = buf.Bav; a.ldB[0] = L.Nas; a.ldB[1] = L.Nav; a.minc = h->minc;
+    if (ev) cudaEventRecord(ev[0], h->stream);
+    dim3 grid((L.n_lev + R - 1) / R, 2 * h->nh, spec.nfield_out);
+    fft_r2c_kernel<<<grid, FFT_THREADS, smem, h->stream>>>(h->fft, a, R);
+    h->launches++;
+    if (ev) cudaEventRecord(ev[1], h->stream);
+    launch_legendre_gemm(true, L.d_probs_an, L.d_tiles_an, L.ntiles_an, h->NHP, h->stream);
+    h->launches++;
+    if (ev) cudaEventRecord(ev[2], h->stream);
+    ExtractArgs e{};
+    e.Cs = buf.Cas; e.Cv = buf.Cav; e.offCs = L.d_offCas; e.offCv = L.d_offCav; e.Ns = L.Nas; e.Nv = L.Nav;
+    e.n_lev = L.n_lev; e.lm_max = h->lm_max; e.nf_s = L.nf_s; e.nf_v = 2 * L.npair_a; e.lm2l = h->d_lm2l; e.lm2m = h->d_lm2m;
+    e.minc = h->minc; e.lev = d_lev; e.out_s = buf.nl_s; e.out_v = buf.nl_v;
+    dim3 g2((h->lm_max + 255) / 256, L.n_lev);
+    anal_extract_kernel<<<g2, 256, 0, h->stream>>>(e);
+    h->launches++;
+    MCHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace magic

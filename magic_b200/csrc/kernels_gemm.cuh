@@ -1,0 +1,156 @@
+// kernels_gemm.cuh -- the Legendre stage as a batched FP64 tensor-core contraction.
+//
+// Replaces the triple loops of shtransforms.f90:152-221 (synthesis) and :692-726, :797-862 (analysis).
+// For every azimuthal order m and equatorial parity the Legendre sums are a dense product
+//        C[M x N] = A[M x K] * B[K x N]
+// with A a slice of the precomputed P/D table, B the (level x field x re/im) batch.  The FP64 pipe is the
+// binding roofline; B200 executes FP64 MMA as DMMA.8x8x4 (measured 37.0 TFLOP/s vs 33.8 for
+// DFMA, profiles/fp64_peak_r01.json), there is no tcgen05 kind for f64, so the tile engine is
+// mma.sync.m8n8k4.f64 fed from shared memory by a multi-stage cp.async pipeline.
+//
+//   CTA tile 128 x 64, 8 warps as 4(M) x 2(N), warp tile 32 x 32 = 4x4 DMMA tiles, k-tile 16.
+//   A_KCONTIG=false (synthesis): A tile stored As[k][m] (m = colatitude contiguous in the table).
+//   A_KCONTIG=true  (analysis) : A tile stored As[m][k] (m = degree row, k = colatitude contiguous).
+//   Leading dimensions are == 4 (mod 16) doubles so the 16 lanes of each half-warp of an LDS.64 fragment
+//   load hit 16 distinct 8-byte banks.
+#pragma once
+#include "common.cuh"
+
+namespace magic {
+
+constexpr int G_THREADS = 256;
+constexpr int LDA_M = GEMM_BM + 4;  // As[k][m]
+constexpr int LDA_K = BK + 4;       // As[m][k]
+constexpr int LDB_S = GEMM_BN + 4;  // Bs[k][n]
+constexpr int A_TILE_M = BK * LDA_M;
+constexpr int A_TILE_K = GEMM_BM * LDA_K;
+constexpr int B_TILE = BK * LDB_S;
+constexpr int STAGES_M = 4;
+constexpr int STAGES_K = 3;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+template <bool A_KCONTIG>
+__global__ void __launch_bounds__(G_THREADS, 2)
+legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict__ tiles, int lda) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int STAGES = A_KCONTIG ? STAGES_K : STAGES_M;
+    constexpr int A_TILE = A_KCONTIG ? A_TILE_K : A_TILE_M;
+    constexpr int STAGE = A_TILE + B_TILE;
+
+    const int2 tile = tiles[blockIdx.x];
+    const GemmProb pr = probs[tile.x];
+    const int m0 = (tile.y >> 16) * GEMM_BM, n0 = (tile.y & 0xffff) * GEMM_BN;
+    const int KT = pr.kt0 + pr.kt1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+
+    auto load_stage = [&](int kt, int st) {
+        double *As = smem + st * STAGE, *Bs = As + A_TILE;
+        const double *Ab = (kt < pr.kt0) ? pr.A0 + (size_t)kt * BK * (A_KCONTIG ? 1 : lda)
+                                         : pr.A1 + (size_t)(kt - pr.kt0) * BK * (A_KCONTIG ? 1 : lda);
+        if (!A_KCONTIG) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {  // 16 rows x 64 chunks of 2 doubles
+                int idx = tid + c * G_THREADS, k = idx >> 6, mc = idx & 63;
+                cp_async16(As + k * LDA_M + mc * 2, Ab + (size_t)k * lda + m0 + mc * 2);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {  // 128 rows x 8 chunks
+                int idx = tid + c * G_THREADS, m = idx >> 3, kc = idx & 7;
+                cp_async16(As + m * LDA_K + kc * 2, Ab + (size_t)(m0 + m) * lda + kc * 2);
+            }
+        }
+        const double *Bb = pr.B + (size_t)kt * BK * pr.ldb + n0;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {  // 16 rows x 32 chunks
+            int idx = tid + c * G_THREADS, k = idx >> 5, nc = idx & 31;
+            cp_async16(Bs + k * LDB_S + nc * 2, Bb + (size_t)k * pr.ldb + nc * 2);
+        }
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < KT) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < KT) load_stage(nk, nk % STAGES);
+            cp_async_commit();
+        }
+        const double *As = smem + (kt % STAGES) * STAGE, *Bs = As + A_TILE;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; kk++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int row = wm + i * 8 + g;
+                a[i] = A_KCONTIG ? As[row * LDA_K + kk * 4 + t] : As[(kk * 4 + t) * LDA_M + row];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[(kk * 4 + t) * LDB_S + wn + j * 8 + g];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int row = m0 + wm + i * 8 + g;
+        if (row < pr.M) {
+            double *crow = pr.C + (size_t)row * pr.ldc + n0 + wn + 2 * t;
+#pragma unroll
+            for (int j = 0; j < 4; j++) *reinterpret_cast<double2 *>(crow + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+    }
+}
+
+inline size_t gemm_smem_bytes(bool a_kcontig) {
+    return sizeof(double) * (a_kcontig ? STAGES_K * (A_TILE_K + B_TILE) : STAGES_M * (A_TILE_M + B_TILE));
+}
+
+inline cudaError_t gemm_setup_attributes() {
+    cudaError_t e = cudaFuncSetAttribute(legendre_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)gemm_smem_bytes(false));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(legendre_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)gemm_smem_bytes(true));
+}
+
+inline void launch_legendre_gemm(bool a_kcontig, const GemmProb *probs, const int2 *tiles, int ntiles, int lda,
+                                 cudaStream_t st) {
+    if (ntiles <= 0) return;
+    if (a_kcontig)
+        legendre_gemm_kernel<true><<<ntiles, G_THREADS, gemm_smem_bytes(true), st>>>(probs, tiles, lda);
+    else
+        legendre_gemm_kernel<false><<<ntiles, G_THREADS, gemm_smem_bytes(false), st>>>(probs, tiles, lda);
+}
+
+}  // namespace magic

@@ -1,0 +1,296 @@
+// kernels_grid.cuh -- grid-space kernels: fused get_nl (+ Adv+=LF of rIter.f90:646-667 + Courant maxima of
+// courant.f90:209-275) and the layout converters of the per-call API.
+//
+// Grid fields live as g[field][lev][s][k][phi] (phi fastest): s=0 holds E, s=1 holds O with
+// north(k) = E+O, south(k) = E-O.  get_nl is point-wise, so one thread rebuilds both hemispheres' values
+// of a (k,phi) pair, forms the products for both, and stores their sum and difference -- exactly the
+// f1ES/f1EA combinations the analysis starts from (shtransforms.f90:704-710).
+#pragma once
+#include "common.cuh"
+
+namespace magic {
+
+// index of each synthesised field inside the synthesis grid array (-1 = absent)
+struct GridIn { int vr, vt, vp, cvr, cvt, cvp, s, br, bt, bp, cbr, cbt, cbp, xi, dvrdr, dvtdr, dvpdr, dvrdt, dvrdp, dvtdp, dvpdp; };
+// index of each product inside the product grid array (-1 = absent)
+struct GridOut { int Advr, Advt, Advp, VSr, VSt, VSp, VxBr, VxBt, VxBp, VXir, VXit, VXip, heat; };
+
+struct NlFlags {
+    int l_conv_nl, l_heat_nl, l_mag_nl, l_mag_LF, l_mag, l_mag_kin, l_adv_curl, l_anel, l_chemical_conv, l_precession,
+        l_centrifuge, l_cour_alf_damp, l_full_sphere, n_r_LCR;
+    double LFfac, opm, ViscHeatFac, OhmLossFac, oek, po, prec_angle, dilution_fac, ra, opr, omega_ma, omega_ic, r_cmb, r_icb,
+        courfac, alffac, time;
+};
+
+struct NlArgs {
+    NlFlags f;
+    GridIn gi;
+    GridOut go;
+    const double *gin;
+    double *gout;
+    int n_lev, nh, n_phi, minc;
+    const LevelInfo *lev;
+    const double *sinth, *costh;  // northern values, [nh]
+    unsigned long long *courmax;  // [n_lev][2] bit patterns of the (non-negative) maxima vr2max, vh2max
+};
+
+__device__ __forceinline__ void atomic_max_pos(unsigned long long *addr, double v) {
+    atomicMax(addr, (unsigned long long)__double_as_longlong(v));  // valid for v >= 0
+}
+
+struct PointIn { double vr, vt, vp, cvr, cvt, cvp, s, br, bt, bp, cbr, cbt, cbp, xi, dvrdr, dvtdr, dvpdr, dvrdt, dvrdp, dvtdp, dvpdp; };
+struct PointOut { double Advr, Advt, Advp, VSr, VSt, VSp, VxBr, VxBt, VxBp, VXir, VXit, VXip, heat; };
+
+// get_nl.f90:213-441 at one grid point.  ct/cn2 carry the hemisphere sign.
+__device__ __forceinline__ void nl_point(const NlFlags &F, const LevelInfo &L, const PointIn &p, double st, double ct, double os2,
+                                         double cn2, double phi, PointOut &o) {
+    const int nBc = L.nBc, nR = L.nR;
+    const double or1 = L.or1, or2 = L.or2, or4 = L.or4, orho1 = L.orho1, beta = L.beta, r = L.r;
+    double LFr = 0, LFt = 0, LFp = 0;
+    const bool lf_on = F.l_mag_LF && nBc == 0 && nR > F.n_r_LCR;
+    if (lf_on) {
+        LFr = F.LFfac * os2 * (p.cbt * p.bp - p.cbp * p.bt);
+        LFt = F.LFfac * or4 * (p.cbp * p.br - p.cbr * p.bp);
+        LFp = F.LFfac * or4 * (p.cbr * p.bt - p.cbt * p.br);
+    }
+    double Ar = 0, At = 0, Ap = 0;
+    if (F.l_conv_nl && nBc == 0) {
+        if (F.l_adv_curl) {
+            Ar = -os2 * (p.cvt * p.vp - p.cvp * p.vt);
+            At = -or4 * (p.cvp * p.vr - p.cvr * p.vp);
+            Ap = -or4 * (p.cvr * p.vt - p.cvt * p.vr);
+        } else {
+            Ar = -or2 * orho1 * (p.vr * (p.dvrdr - (2.0 * or1 + beta) * p.vr) +
+                                 os2 * (p.vt * (p.dvrdt - r * p.vt) + p.vp * (p.dvrdp - r * p.vp)));
+            At = or4 * orho1 * (-p.vr * (p.dvtdr - beta * p.vt) + p.vt * (cn2 * p.vt + p.dvpdp + p.dvrdr) + p.vp * (cn2 * p.vp - p.dvtdp));
+            Ap = or4 * orho1 * (-p.vr * (p.dvpdr - beta * p.vp) - p.vt * (p.dvtdp + p.cvr) - p.vp * p.dvpdp);
+        }
+    }
+    // rIter.f90:646-667
+    if (F.l_conv_nl && F.l_mag_LF) {
+        if (nR > F.n_r_LCR) { Ar += LFr; At += LFt; Ap += LFp; }
+    } else if (F.l_mag_LF) {
+        if (nR > F.n_r_LCR) { Ar = LFr; At = LFt; Ap = LFp; }
+        else { Ar = 0; At = 0; Ap = 0; }
+    }
+    if (F.l_precession && nBc == 0) {
+        const double posnalp = -2.0 * F.oek * F.po * sin(F.prec_angle);
+        const double ph = F.oek * F.time + phi;
+        Ar += posnalp * (1.0 / st) * r * (cos(ph) * p.vp * ct + sin(ph) * p.vt);
+        At += -posnalp * st * or2 * (cos(ph) * p.vp + sin(ph) * or1 * p.vr);
+        Ap += posnalp * st * cos(ph) * or2 * (p.vt - or1 * p.vr * ct);
+    }
+    if (F.l_centrifuge && nBc == 0) {
+        Ar += -F.dilution_fac * r * (st * st * st * st) * F.ra * F.opr * p.s;
+        At += -F.dilution_fac * r * (st * st * st) * ct * F.ra * F.opr * p.s;
+    }
+    o.Advr = Ar; o.Advt = At; o.Advp = Ap;
+    o.VSr = o.VSt = o.VSp = 0;
+    if (F.l_heat_nl && nBc == 0) {
+        o.VSr = p.vr * p.s;
+        o.VSt = or2 * p.vt * p.s;
+        o.VSp = or2 * p.vp * p.s;
+    }
+    o.VXir = o.VXit = o.VXip = 0;
+    if (F.l_chemical_conv && nBc == 0) {
+        o.VXir = p.vr * p.xi;
+        o.VXit = or2 * p.vt * p.xi;
+        o.VXip = or2 * p.vp * p.xi;
+    }
+    o.VxBr = o.VxBt = o.VxBp = 0;
+    if (F.l_mag_nl) {
+        if (nBc == 0 && nR > F.n_r_LCR) {
+            o.VxBr = orho1 * os2 * (p.vt * p.bp - p.vp * p.bt);
+            o.VxBt = orho1 * or4 * (p.vp * p.br - p.vr * p.bp);
+            o.VxBp = orho1 * or4 * (p.vr * p.bt - p.vt * p.br);
+        } else if (nBc == 1 || nR <= F.n_r_LCR) {
+            o.VxBt = or4 * orho1 * p.vp * p.br;
+            o.VxBp = -or4 * orho1 * p.vt * p.br;
+        } else if (nBc == 2) {
+            o.VxBt = or4 * orho1 * p.vp * p.br;
+            o.VxBp = 0.0;
+        }
+    }
+    o.heat = 0;
+    if (F.l_anel && nBc == 0) {
+        double t1 = p.dvrdr - (2.0 * or1 + beta) * p.vr;
+        double t2 = cn2 * p.vt + p.dvpdp + p.dvrdr - or1 * p.vr;
+        double t3 = p.dvpdp + cn2 * p.vt + or1 * p.vr;
+        double t6 = 2.0 * p.dvtdp + p.cvr - 2.0 * cn2 * p.vp;
+        double t4 = r * p.dvtdr - (2.0 + beta * r) * p.vt + or1 * p.dvrdt;
+        double t5 = r * p.dvpdr - (2.0 + beta * r) * p.vp + or1 * p.dvrdp;
+        double t7 = beta * p.vr;
+        o.heat = F.ViscHeatFac * or4 * orho1 * L.otemp1 * L.visc *
+                 (2.0 * t1 * t1 + 2.0 * t2 * t2 + 2.0 * t3 * t3 + t6 * t6 + os2 * (t4 * t4 + t5 * t5) - 2.0 * (1.0 / 3.0) * t7 * t7);
+        if (F.l_mag_nl && nR > F.n_r_LCR)
+            o.heat += F.OhmLossFac * or2 * L.otemp1 * L.lambda * (or2 * p.cbr * p.cbr + os2 * p.cbt * p.cbt + os2 * p.cbp * p.cbp);
+    }
+}
+
+constexpr int NL_THREADS = 256;
+
+__global__ void __launch_bounds__(NL_THREADS) get_nl_kernel(NlArgs a) {
+    const int lev = blockIdx.y;
+    const LevelInfo L = a.lev[lev];
+    const NlFlags &F = a.f;
+    const size_t plane = (size_t)a.nh * a.n_phi;  // one (field,lev,s) slab
+    double vr2max = 0.0, vh2max = 0.0;
+    double valri2 = 0.0, valhi2 = 0.0;
+    if (F.l_cour_alf_damp) {
+        double h = 0.5 * (1.0 + F.opm);
+        valri2 = h * h / L.delxr2;
+        valhi2 = h * h / L.delxh2;
+    }
+    const double cf2 = F.courfac * F.courfac, af2 = F.alffac * F.alffac;
+    for (size_t pt = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pt < plane; pt += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(pt / a.n_phi), j = (int)(pt - (size_t)k * a.n_phi);
+        const double st = a.sinth[k], ct = a.costh[k];
+        const double os2 = 1.0 / (st * st), cn2 = ct / st / st;
+        const double phi = (double)j * (6.283185307179586476925286766559 / (double)(a.n_phi * a.minc));
+        PointIn pn, ps;
+        auto ld = [&](int fidx, double &n, double &s) {
+            if (fidx < 0) { n = 0.0; s = 0.0; return; }
+            const double *base = a.gin + (((size_t)fidx * a.n_lev + lev) * 2) * plane + pt;
+            double e = base[0], o = base[plane];
+            n = e + o;
+            s = e - o;
+        };
+        ld(a.gi.vr, pn.vr, ps.vr); ld(a.gi.vt, pn.vt, ps.vt); ld(a.gi.vp, pn.vp, ps.vp);
+        ld(a.gi.cvr, pn.cvr, ps.cvr); ld(a.gi.cvt, pn.cvt, ps.cvt); ld(a.gi.cvp, pn.cvp, ps.cvp);
+        ld(a.gi.s, pn.s, ps.s);
+        ld(a.gi.br, pn.br, ps.br); ld(a.gi.bt, pn.bt, ps.bt); ld(a.gi.bp, pn.bp, ps.bp);
+        ld(a.gi.cbr, pn.cbr, ps.cbr); ld(a.gi.cbt, pn.cbt, ps.cbt); ld(a.gi.cbp, pn.cbp, ps.cbp);
+        ld(a.gi.xi, pn.xi, ps.xi);
+        ld(a.gi.dvrdr, pn.dvrdr, ps.dvrdr); ld(a.gi.dvtdr, pn.dvtdr, ps.dvtdr); ld(a.gi.dvpdr, pn.dvpdr, ps.dvpdr);
+        ld(a.gi.dvrdt, pn.dvrdt, ps.dvrdt); ld(a.gi.dvrdp, pn.dvrdp, ps.dvrdp);
+        ld(a.gi.dvtdp, pn.dvtdp, ps.dvtdp); ld(a.gi.dvpdp, pn.dvpdp, ps.dvpdp);
+        // torpol_to_dphspat post-scaling by 1/sin^2 (sht_native.f90:263-270)
+        pn.dvtdp *= os2; ps.dvtdp *= os2; pn.dvpdp *= os2; ps.dvpdp *= os2;
+        // boundary overrides of transform_to_grid_space (rIter.f90:555-602)
+        if (L.nBc == 1) { pn.vr = 0.0; ps.vr = 0.0; }
+        if (L.nBc == 2) {  // v_rigid_boundary, nonlinear_bcs.f90:120-175 (l_vr_cmb/icb = .false.)
+            const double r2 = (L.nR == 1) ? F.r_cmb * F.r_cmb : F.r_icb * F.r_icb;
+            const double om = (L.nR == 1) ? F.omega_ma : F.omega_ic;
+            pn.vr = ps.vr = 0.0; pn.vt = ps.vt = 0.0;
+            pn.vp = ps.vp = r2 * L.rho0 * (st * st) * om;
+        }
+        PointOut on, os;
+        if (L.nl_on) {
+            nl_point(F, L, pn, st, ct, os2, cn2, phi, on);
+            nl_point(F, L, ps, st, -ct, os2, -cn2, phi, os);
+        } else {
+            on = PointOut{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            os = on;
+        }
+        auto stf = [&](int fidx, double n, double s) {
+            if (fidx < 0) return;
+            double *base = a.gout + (((size_t)fidx * a.n_lev + lev) * 2) * plane + pt;
+            base[0] = n + s;
+            base[plane] = n - s;
+        };
+        stf(a.go.Advr, on.Advr, os.Advr); stf(a.go.Advt, on.Advt, os.Advt); stf(a.go.Advp, on.Advp, os.Advp);
+        stf(a.go.VSr, on.VSr, os.VSr); stf(a.go.VSt, on.VSt, os.VSt); stf(a.go.VSp, on.VSp, os.VSp);
+        stf(a.go.VxBr, on.VxBr, os.VxBr); stf(a.go.VxBt, on.VxBt, os.VxBt); stf(a.go.VxBp, on.VxBp, os.VxBp);
+        stf(a.go.VXir, on.VXir, os.VXir); stf(a.go.VXit, on.VXit, os.VXit); stf(a.go.VXip, on.VXip, os.VXip);
+        stf(a.go.heat, on.heat, os.heat);
+        // courant.f90:209-275 (XSH_COURANT == 0)
+        if (L.cour_on) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const PointIn &p = h == 0 ? pn : ps;
+                double vflr2 = L.orho2 * p.vr * p.vr;
+                double vflh2 = (p.vt * p.vt + p.vp * p.vp) * os2 * L.orho2;
+                if (F.l_mag && F.l_mag_LF && !F.l_mag_kin) {
+                    double valr = p.br * p.br * F.LFfac * L.orho1;
+                    double valr2 = valr * valr / (valr + valri2);
+                    if (!(valr + valri2 > 0.0)) valr2 = 0.0;
+                    vr2max = fmax(vr2max, L.or4 * (cf2 * vflr2 + af2 * valr2));
+                    double valh2 = (p.bt * p.bt + p.bp * p.bp) * F.LFfac * os2 * L.orho1;
+                    double valh2m = valh2 * valh2 / (valh2 + valhi2);
+                    if (!(valh2 + valhi2 > 0.0)) valh2m = 0.0;
+                    vh2max = fmax(vh2max, L.or2 * (cf2 * vflh2 + af2 * valh2m));
+                } else {
+                    vr2max = fmax(vr2max, cf2 * L.or4 * vflr2);
+                    vh2max = fmax(vh2max, cf2 * L.or2 * vflh2);
+                }
+            }
+        }
+    }
+    if (L.cour_on) {
+        __shared__ double red[2][NL_THREADS / 32];
+        for (int o = 16; o > 0; o >>= 1) {
+            vr2max = fmax(vr2max, __shfl_xor_sync(0xffffffffu, vr2max, o));
+            vh2max = fmax(vh2max, __shfl_xor_sync(0xffffffffu, vh2max, o));
+        }
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = vr2max; red[1][threadIdx.x >> 5] = vh2max; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < NL_THREADS / 32; w++) { vr2max = fmax(vr2max, red[0][w]); vh2max = fmax(vh2max, red[1][w]); }
+            atomic_max_pos(a.courmax + 2 * lev, vr2max);
+            atomic_max_pos(a.courmax + 2 * lev + 1, vh2max);
+        }
+    }
+}
+
+// dtrkc/dthkc from the maxima (courant.f90:272-273, rIter.f90:215-216)
+__global__ void courant_finish_kernel(const unsigned long long *courmax, const LevelInfo *lev, int n_lev, double *dtrkc, double *dthkc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lev) return;
+    double vr2max = __longlong_as_double((long long)courmax[2 * i]), vh2max = __longlong_as_double((long long)courmax[2 * i + 1]);
+    double a = 1e10, b = 1e10;
+    if (lev[i].cour_on) {
+        if (vr2max != 0.0) a = fmin(a, sqrt(lev[i].delxr2 / vr2max));
+        if (vh2max != 0.0) b = fmin(b, sqrt(lev[i].delxh2 / vh2max));
+    }
+    dtrkc[i] = a;
+    dthkc[i] = b;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Layout converters for the per-call `module sht` API: reference layout f(nlat_padded, n_phi), theta fastest,
+// rows N/S interleaved  <->  internal g[s][k][phi].  32x32 shared-memory transposes.
+__global__ void grid_export_kernel(const double *__restrict__ g /*[2][nh][nphi]*/, double *__restrict__ f, int nh, int n_phi,
+                                   int nlat_padded, const double *__restrict__ kscale /* per-k factor or null */) {
+    __shared__ double tn[32][33], ts[32][33];
+    int k0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int k = k0 + r, j = j0 + threadIdx.x;
+        if (k < nh && j < n_phi) {
+            double e = g[(size_t)k * n_phi + j], o = g[((size_t)nh + k) * n_phi + j];
+            double sc = kscale ? kscale[k] : 1.0;
+            tn[r][threadIdx.x] = (e + o) * sc;
+            ts[r][threadIdx.x] = (e - o) * sc;
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int j = j0 + r, k = k0 + threadIdx.x;
+        if (k < nh && j < n_phi) {
+            f[(size_t)j * nlat_padded + 2 * k] = tn[threadIdx.x][r];
+            f[(size_t)j * nlat_padded + 2 * k + 1] = ts[threadIdx.x][r];
+        }
+    }
+}
+
+__global__ void grid_import_kernel(const double *__restrict__ f, double *__restrict__ g, int nh, int n_phi, int nlat_padded) {
+    __shared__ double te[32][33], to[32][33];
+    int k0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int j = j0 + r, k = k0 + threadIdx.x;
+        if (k < nh && j < n_phi) {
+            double n = f[(size_t)j * nlat_padded + 2 * k], s = f[(size_t)j * nlat_padded + 2 * k + 1];
+            te[threadIdx.x][r] = n + s;
+            to[threadIdx.x][r] = n - s;
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int k = k0 + r, j = j0 + threadIdx.x;
+        if (k < nh && j < n_phi) {
+            g[(size_t)k * n_phi + j] = te[r][threadIdx.x];
+            g[((size_t)nh + k) * n_phi + j] = to[r][threadIdx.x];
+        }
+    }
+}
+
+}  // namespace magic

@@ -1,0 +1,373 @@
+// kernels_spec.cuh -- spectral-side kernels: Legendre table build, synthesis operand assembly (the
+// sht_native.f90 wrappers), analysis extraction and the get_td epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace magic {
+
+// ------------------------------------------------------------------------------------------------------
+// Table build: plm_theta (plms.f90:14-189, norm=2) evaluated per (order mc, northern colatitude k), written in
+// the blocked layout of common.cuh.  off[mc*4 + {0,1,2,3}] = offsets (doubles) of P_even, D_odd, P_odd, D_even.
+__global__ void build_tables_kernel(double *__restrict__ tab, const long long *__restrict__ off,
+                                    const double *__restrict__ sinth, const double *__restrict__ costh,
+                                    const double *__restrict__ pmm_fac, int nh, int NHP, int l_max, int minc, int n_m) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int mc = blockIdx.y;
+    if (k >= nh) return;
+    const int m = mc * minc;
+    const double dnorm = 0.28209479177387814347403972578039;  // 1/sqrt(4 pi)
+    const double st = sinth[k], ct = costh[k];
+    double *Pe = tab + off[mc * 4 + 0], *Do = tab + off[mc * 4 + 1], *Po = tab + off[mc * 4 + 2], *De = tab + off[mc * 4 + 3];
+    double plm = pmm_fac[mc];
+    if (st != 0.0) plm = plm * pow(st, (double)m);
+    else if (m != 0) plm = 0.0;
+    // sliding window of normalised values: pm1 = P_{l-1}, p0 = P_l, pp1 = P_{l+1}
+    double plm1 = 0.0, plm2;
+    double pm1 = 0.0, p0 = dnorm * plm;
+    for (int l = m; l <= l_max; l++) {
+        // advance recurrence to degree l+1 (plms.f90:79-113)
+        int ln = l + 1;
+        plm2 = plm1;
+        plm1 = plm;
+        plm = ct * sqrt((double)((2 * ln - 1) * (2 * ln + 1)) / (double)((ln - m) * (ln + m))) * plm1 -
+              sqrt(((double)(2 * ln + 1) * (double)(ln + m - 1) * (double)(ln - m - 1)) /
+                   ((double)(2 * ln - 3) * (double)(ln - m) * (double)(ln + m))) * plm2;
+        double pp1 = dnorm * plm;
+        // sin(theta) dP/dtheta (plms.f90:117-187)
+        double d;
+        if (l == m) d = l / sqrt((double)(2 * l + 3)) * pp1;
+        else
+            d = l * sqrt((double)((l + m + 1) * (l - m + 1)) / (double)((2 * l + 1) * (2 * l + 3))) * pp1 -
+                (l + 1) * sqrt((double)((l + m) * (l - m)) / (double)((2 * l - 1) * (2 * l + 1))) * pm1;
+        int j = (l - m) >> 1;
+        if (((l - m) & 1) == 0) { Pe[(size_t)j * NHP + k] = p0; De[(size_t)j * NHP + k] = d; }
+        else { Po[(size_t)j * NHP + k] = p0; Do[(size_t)j * NHP + k] = d; }
+        pm1 = p0;
+        p0 = pp1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Synthesis operand assembly.  One CTA per k-tile (16 rows) of one problem.
+struct KTile { int prob; int kt; int seg; int jt; };  // prob = mc*2+s ; seg 0 = P rows, 1 = D rows ; jt = tile in segment
+
+struct SynthPrepArgs {
+    const double *src[MAGIC_MAX_SRC];  // complex [n_lev][lm_max]
+    const ScalCol *scal;
+    const VecPair *vec;
+    int ncol_s, npair_v, n_lev, lm_max;
+    int Ns, Nv;
+    const LevelInfo *lev;
+    const int *lstart;  // lm index of degree l=m for each mc
+    int l_max, minc;
+    double *Bs, *Bv;
+    const long long *offBs, *offBv;  // per problem, doubles
+    const KTile *kts, *ktv;
+};
+
+__device__ __forceinline__ bool level_enabled(int lmask, const LevelInfo &L) {
+    if (lmask == LM_VEL) return L.nBc != 2;
+    if (lmask == LM_VELBULK) return L.nBc == 0;
+    if (lmask == LM_DERIV) return L.lDeriv != 0;
+    return true;
+}
+
+__device__ __forceinline__ double2 eval_terms(const Term *t, const SynthPrepArgs &a, int lm, int l, int m, int lev,
+                                              double or2) {
+    double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        int ft = t[i].ftype;
+        if (ft == F_NONE) continue;
+        double2 x = *reinterpret_cast<const double2 *>(a.src[t[i].src] + 2 * ((size_t)lev * a.lm_max + lm));
+        double dlh = (double)(l * (l + 1));
+        if (ft == F_ONE) { acc.x += x.x; acc.y += x.y; }
+        else if (ft == F_DLH) { acc.x += dlh * x.x; acc.y += dlh * x.y; }
+        else if (ft == F_OR2DLH) { double f = or2 * dlh; acc.x += f * x.x; acc.y += f * x.y; }
+        else if (ft == F_NEG) { acc.x -= x.x; acc.y -= x.y; }
+        else { double dm = (double)m; acc.x += -dm * x.y; acc.y += dm * x.x; }  // F_IM: i*m*x
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(256) synth_prep_scal_kernel(SynthPrepArgs a) {
+    const KTile kt = a.kts[blockIdx.x];
+    const int mc = kt.prob >> 1, s = kt.prob & 1, m = mc * a.minc;
+    double *B = a.Bs + a.offBs[kt.prob] + (size_t)kt.kt * BK * a.Ns;
+    const int ncc = a.ncol_s * a.n_lev;
+    for (int idx = threadIdx.x; idx < BK * (a.Ns / 2); idx += blockDim.x) {
+        int r = idx / (a.Ns / 2), cc = idx - r * (a.Ns / 2);
+        double2 v = make_double2(0.0, 0.0);
+        int l = m + 2 * (kt.jt * BK + r) + s;
+        if (cc < ncc && l <= a.l_max) {
+            int col = cc / a.n_lev, lev = cc - col * a.n_lev;
+            const LevelInfo L = a.lev[lev];
+            const ScalCol sc = a.scal[col];
+            if (l <= L.lcut && level_enabled(sc.lmask, L)) v = eval_terms(sc.t, a, a.lstart[mc] + (l - m), l, m, lev, L.or2);
+        }
+        *reinterpret_cast<double2 *>(B + (size_t)r * a.Ns + 2 * cc) = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) synth_prep_vec_kernel(SynthPrepArgs a) {
+    const KTile kt = a.ktv[blockIdx.x];
+    const int mc = kt.prob >> 1, s = kt.prob & 1, m = mc * a.minc;
+    double *B = a.Bv + a.offBv[kt.prob] + (size_t)kt.kt * BK * a.Nv;
+    const int ncc = 2 * a.npair_v * a.n_lev;
+    const int par = kt.seg == 0 ? s : 1 - s;  // P rows carry parity s, D rows the other parity
+    for (int idx = threadIdx.x; idx < BK * (a.Nv / 2); idx += blockDim.x) {
+        int r = idx / (a.Nv / 2), cc = idx - r * (a.Nv / 2);
+        double2 v = make_double2(0.0, 0.0);
+        int l = m + 2 * (kt.jt * BK + r) + par;
+        if (cc < ncc && l <= a.l_max) {
+            int col = cc / a.n_lev, lev = cc - col * a.n_lev;
+            int pair = col >> 1, comp = col & 1;  // comp 0 = theta column, 1 = phi column
+            const LevelInfo L = a.lev[lev];
+            const VecPair vp = a.vec[pair];
+            if (l <= L.lcut && l > 0 && level_enabled(vp.lmask, L)) {
+                int lm = a.lstart[mc] + (l - m);
+                // Vtheta = sum (S D + i m T P), Vphi = sum (i m S P - T D)  
+                if (kt.seg == 0) {
+                    double2 x = eval_terms(comp == 0 ? vp.T : vp.S, a, lm, l, m, lev, L.or2);
+                    double dm = (double)m;
+                    v = make_double2(-dm * x.y, dm * x.x);
+                } else {
+                    if (comp == 0) v = eval_terms(vp.S, a, lm, l, m, lev, L.or2);
+                    else { double2 x = eval_terms(vp.T, a, lm, l, m, lev, L.or2); v = make_double2(-x.x, -x.y); }
+                }
+            }
+        }
+        *reinterpret_cast<double2 *>(B + (size_t)r * a.Nv + 2 * cc) = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Analysis extraction: C matrices of the analysis GEMM -> spectral arrays nl[field][lev][lm]
+// (the nonlinear_lm_t members of get_td.f90:27-45).  Vector outputs are divided by l(l+1)
+// (shtransforms.f90:866-870); degrees above lcut are exact zeros (shtransforms.f90:680,693).
+struct ExtractArgs {
+    const double *Cs, *Cv;
+    const long long *offCs, *offCv;  // per problem (mc*2+p), doubles
+    int Ns, Nv, n_lev, lm_max, nf_s, nf_v;  // nf_v = number of vector output columns (2 per pair)
+    const int *lm2l, *lm2m;
+    int minc;
+    const LevelInfo *lev;
+    double *out_s;  // [nf_s][n_lev][lm_max] complex
+    double *out_v;  // [nf_v][n_lev][lm_max] complex
+};
+
+__global__ void __launch_bounds__(256) anal_extract_kernel(ExtractArgs a) {
+    int lm = blockIdx.x * blockDim.x + threadIdx.x;
+    int lev = blockIdx.y;
+    if (lm >= a.lm_max) return;
+    const int l = a.lm2l[lm], m = a.lm2m[lm], mc = m / a.minc;
+    const int p = (l - m) & 1, j = (l - m) >> 1;
+    const bool on = l <= a.lev[lev].lcut;
+    for (int f = 0; f < a.nf_s; f++) {
+        double2 v = make_double2(0.0, 0.0);
+        if (on) v = *reinterpret_cast<const double2 *>(a.Cs + a.offCs[mc * 2 + p] + (size_t)j * a.Ns + 2 * ((size_t)f * a.n_lev + lev));
+        *reinterpret_cast<double2 *>(a.out_s + 2 * (((size_t)f * a.n_lev + lev) * a.lm_max + lm)) = v;
+    }
+    const double ll1 = (double)(l * (l + 1));
+    for (int f = 0; f < a.nf_v; f++) {
+        double2 v = make_double2(0.0, 0.0);
+        if (on) {
+            v = *reinterpret_cast<const double2 *>(a.Cv + a.offCv[mc * 2 + p] + (size_t)j * a.Nv + 2 * ((size_t)f * a.n_lev + lev));
+            if (lm > 0) { v.x = v.x / ll1; v.y = v.y / ll1; }
+        }
+        *reinterpret_cast<double2 *>(a.out_v + 2 * (((size_t)f * a.n_lev + lev) * a.lm_max + lm)) = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// get_td epilogue (get_td.f90:133-619) for one chunk of levels; thread per (lm, level).
+struct TdFlags {
+    int l_conv, l_mag, l_heat, l_conv_nl, l_mag_nl, l_mag_kin, l_anel, l_corr, l_double_curl, l_single_matrix,
+        l_chemical_conv, l_anelastic_liquid;
+    double CorFac, epsc, epscXi;
+};
+struct TdArgs {
+    TdFlags f;
+    int n_lev, lm_max, l_max, minc;
+    const int *lm2l, *lm2m;
+    const LevelInfo *lev;
+    // nonlinear_lm_t members, each [n_lev][lm_max] complex or null
+    const double *AdvrLM, *AdvtLM, *AdvpLM, *VxBrLM, *VxBtLM, *VxBpLM, *VStLM, *VSrLM, *VXitLM, *VXirLM, *heatLM;
+    // inputs (level-major, first level of the chunk)
+    const double *w, *dw, *ddw, *z, *dz;
+    // outputs
+    double *dwdt, *dzdt, *dpdt, *dsdt, *dxidt, *dbdt, *djdt, *dVxVhLM, *dVxBhLM, *dVSrLM, *dVXirLM;
+};
+
+__device__ __forceinline__ double2 ldc(const double *p, size_t i) { return *reinterpret_cast<const double2 *>(p + 2 * i); }
+__device__ __forceinline__ void stc(double *p, size_t i, double2 v) { *reinterpret_cast<double2 *>(p + 2 * i) = v; }
+__device__ __forceinline__ double2 c_scale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+__device__ __forceinline__ double2 c_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 c_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 c_im(double m, double2 a) { return make_double2(-m * a.y, m * a.x); }  // i*m*a
+
+__global__ void __launch_bounds__(256) get_td_kernel(TdArgs a) {
+    int lm = blockIdx.x * blockDim.x + threadIdx.x;
+    int lev = blockIdx.y;
+    if (lm >= a.lm_max) return;
+    const LevelInfo L = a.lev[lev];
+    const int l = a.lm2l[lm], m = a.lm2m[lm];
+    const size_t i = (size_t)lev * a.lm_max + lm;
+    const int nBc = L.nBc;
+    const double2 zero = make_double2(0.0, 0.0);
+    const double dLh = (double)(l * (l + 1)), dm = (double)m;
+    // st_map neighbours (blocking.f90:321-335): (l-1,m) or self when l==m ; (l+1,m) or none when l==l_max
+    const size_t iS = (l > m) ? i - 1 : i;
+    const bool hasA = l < a.l_max;
+    const size_t iA = i + 1;
+    auto clm = [&](int ll) { return sqrt((double)((ll + m) * (ll - m)) / (double)((2 * ll - 1) * (2 * ll + 1))); };
+    const double cl = clm(l), cl1 = clm(l + 1);
+    const double dTheta2S = (double)(l - 1) * cl, dTheta2A = (double)(l + 2) * cl1;
+    const double dTheta3S = (double)((l - 1) * (l + 1)) * cl, dTheta3A = (double)(l * (l + 2)) * cl1;
+    const double dTheta4S = ((double)(l + 1) * cl) * (double)((l - 1) * l);
+    const double dTheta4A = ((double)l * cl1) * (double)((l + 1) * (l + 2));
+    const TdFlags &F = a.f;
+    const bool bulk = (nBc == 0);
+
+    if (F.l_conv) {
+        // get_dzdt (get_td.f90:376-452)
+        if (bulk) {
+            double2 v;
+            if (lm == 0) {
+                v = zero;
+                if (F.l_corr) v = c_scale(2.0 * F.CorFac * L.or2, c_add(c_scale(dTheta3A, ldc(a.dw, iA)), c_scale(L.or1 * dTheta4A, ldc(a.w, iA))));
+            } else {
+                v = F.l_conv_nl ? c_scale(dLh, ldc(a.AdvpLM, i)) : zero;
+                if (F.l_corr) {
+                    double2 cor = zero;
+                    if (l < L.lcut) {
+                        double2 t = c_im(dm, ldc(a.z, i));
+                        t = c_add(t, c_scale(dTheta3A, ldc(a.dw, iA)));
+                        t = c_add(t, c_scale(L.or1 * dTheta4A, ldc(a.w, iA)));
+                        t = c_add(t, c_scale(dTheta3S, ldc(a.dw, iS)));
+                        t = c_sub(t, c_scale(L.or1 * dTheta4S, ldc(a.w, iS)));
+                        cor = c_scale(2.0 * F.CorFac * L.or2, t);
+                    } else if (l == L.lcut) {
+                        double2 t = c_im(dm, ldc(a.z, i));
+                        t = c_add(t, c_scale(dTheta3S, ldc(a.dw, iS)));
+                        t = c_sub(t, c_scale(L.or1 * dTheta4S, ldc(a.w, iS)));
+                        cor = c_scale(2.0 * F.CorFac * L.or2, t);
+                    }
+                    v = c_add(v, cor);
+                }
+            }
+            stc(a.dzdt, i, v);
+        }
+        if (F.l_double_curl) {
+            // get_dwdt_double_curl (get_td.f90:199-309)
+            if (bulk) {
+                double2 v, vh = zero;
+                if (lm == 0) {
+                    v = F.l_conv_nl ? c_scale(L.or2, ldc(a.AdvrLM, i)) : zero;
+                    if (F.l_corr && !F.l_single_matrix) v = c_add(v, c_scale(2.0 * F.CorFac * L.or1 * dTheta2A, ldc(a.z, iA)));
+                    stc(a.dwdt, i, v);
+                } else {
+                    if (F.l_conv_nl) {
+                        v = c_scale(dLh * L.or4 * L.orho1, ldc(a.AdvrLM, i));
+                        vh = c_scale(-L.orho1 * L.r * L.r * dLh, ldc(a.AdvtLM, i));
+                    } else v = zero;
+                    if (F.l_corr) {
+                        double2 cor = zero;
+                        if (l <= L.lcut) {
+                            double2 q = c_sub(c_scale(L.beta, ldc(a.dw, i)), ldc(a.ddw, i));
+                            q = c_add(q, c_scale((L.beta * L.or1 + L.or2) * dLh, ldc(a.w, i)));
+                            double2 t = c_im(dm, q);
+                            if (l < L.lcut && hasA) {
+                                t = c_add(t, c_scale(dTheta3A, c_sub(ldc(a.dz, iA), c_scale(L.beta, ldc(a.z, iA)))));
+                            }
+                            t = c_add(t, c_scale(dTheta3S, c_sub(ldc(a.dz, iS), c_scale(L.beta, ldc(a.z, iS)))));
+                            if (l < L.lcut && hasA)
+                                t = c_add(t, c_scale(L.or1, c_sub(c_scale(dTheta4A, ldc(a.z, iA)), c_scale(dTheta4S, ldc(a.z, iS)))));
+                            else
+                                t = c_sub(t, c_scale(L.or1 * dTheta4S, ldc(a.z, iS)));
+                            cor = c_scale(2.0 * F.CorFac * L.or2 * L.orho1, t);
+                        }
+                        v = c_add(v, cor);
+                    }
+                    stc(a.dwdt, i, v);
+                    stc(a.dVxVhLM, i, vh);
+                }
+            } else {
+                stc(a.dVxVhLM, i, zero);
+            }
+        } else if (bulk) {
+            // get_dwdt (get_td.f90:133-197)
+            double2 v = F.l_conv_nl ? c_scale(L.or2, ldc(a.AdvrLM, i)) : zero;
+            if (lm == 0) {
+                if (F.l_corr && !F.l_single_matrix) v = c_add(v, c_scale(2.0 * F.CorFac * L.or1 * dTheta2A, ldc(a.z, iA)));
+            } else if (F.l_corr) {
+                double2 cor = zero;
+                if (l < L.lcut) {
+                    double2 t = c_im(dm, ldc(a.dw, i));
+                    t = c_add(t, c_scale(dTheta2A, ldc(a.z, iA)));
+                    t = c_sub(t, c_scale(dTheta2S, ldc(a.z, iS)));
+                    cor = c_scale(2.0 * F.CorFac * L.or1, t);
+                } else if (l == L.lcut) {
+                    double2 t = c_sub(c_im(dm, ldc(a.dw, i)), c_scale(dTheta2S, ldc(a.z, iS)));
+                    cor = c_scale(2.0 * F.CorFac * L.or1, t);
+                }
+                v = c_add(v, cor);
+            }
+            stc(a.dwdt, i, v);
+        }
+    }
+    if (!F.l_double_curl && bulk && lm > 0) {
+        // get_dpdt (get_td.f90:311-374); lm=0 is never written by the reference
+        double2 v = F.l_conv_nl ? c_scale(-dLh, ldc(a.AdvtLM, i)) : zero;
+        if (F.l_corr) {
+            double2 cor = zero;
+            if (l <= L.lcut) {
+                double2 q = c_add(ldc(a.dw, i), c_scale(L.or1 * dLh, ldc(a.w, i)));
+                double2 t = c_im(-dm, q);
+                if (l < L.lcut && hasA) t = c_add(t, c_scale(dTheta3A, ldc(a.z, iA)));
+                t = c_add(t, c_scale(dTheta3S, ldc(a.z, iS)));
+                cor = c_scale(2.0 * F.CorFac * L.or2, t);
+            }
+            v = c_add(v, cor);
+        }
+        stc(a.dpdt, i, v);
+    }
+    if (F.l_heat) {
+        // get_dsdt (get_td.f90:454-521) + dVSrLM from spat_to_qst (rIter.f90:688) + rIter.f90:448-456
+        if (bulk) {
+            double2 v;
+            if (lm == 0) {
+                v = make_double2(F.epsc * L.epscProf, 0.0);
+                if (F.l_anel) v = c_add(v, F.l_anelastic_liquid ? c_scale(L.temp0, ldc(a.heatLM, i)) : ldc(a.heatLM, i));
+            } else {
+                v = c_scale(dLh, ldc(a.VStLM, i));
+                if (F.l_anel) v = c_add(v, F.l_anelastic_liquid ? c_scale(L.temp0, ldc(a.heatLM, i)) : ldc(a.heatLM, i));
+            }
+            stc(a.dsdt, i, v);
+        }
+        stc(a.dVSrLM, i, (bulk && !L.l_bound) ? ldc(a.VSrLM, i) : zero);
+    }
+    if (F.l_chemical_conv) {
+        if (bulk) stc(a.dxidt, i, lm == 0 ? make_double2(F.epscXi, 0.0) : c_scale(dLh, ldc(a.VXitLM, i)));
+        stc(a.dVXirLM, i, (bulk && !L.l_bound) ? ldc(a.VXirLM, i) : zero);
+    }
+    if (F.l_mag) {
+        // get_dbdt (get_td.f90:557-619)
+        if (bulk) {
+            if (F.l_mag_nl || F.l_mag_kin) {
+                stc(a.dbdt, i, c_scale(dLh, ldc(a.VxBpLM, i)));
+                stc(a.dVxBhLM, i, c_scale(-dLh * L.r * L.r, ldc(a.VxBtLM, i)));
+                stc(a.djdt, i, c_scale(dLh * L.or4, ldc(a.VxBrLM, i)));
+            } else {
+                stc(a.dbdt, i, zero);
+                stc(a.djdt, i, zero);
+                stc(a.dVxBhLM, i, zero);
+            }
+        } else {
+            if ((F.l_mag_nl || F.l_mag_kin) && lm > 0) stc(a.dVxBhLM, i, c_scale(-dLh * L.r * L.r, ldc(a.VxBtLM, i)));
+            else stc(a.dVxBhLM, i, zero);
+        }
+    }
+}
+
+}  // namespace magic

@@ -1,0 +1,139 @@
+"""Host-side mirror of `rIter_single_t%radialLoop` (rIter.f90:94-464): the batched radial loop.
+
+`RadialLoop.radialLoop(fields)` takes the R-distributed spectral containers of one rank and returns the
+explicit terms (dwdt, dzdt, dpdt, dsdt, dbdt, djdt, dVxVhLM, dVxBhLM, dVSrLM, dtrkc, dthkc) exactly like the
+Fortran subroutine, for all local radial levels at once.
+"""
+import ctypes as C
+from ctypes import byref, c_double, c_int, c_void_p
+
+import numpy as np
+
+from .lib import MagicError, check, load_library, ptr
+
+
+class Params(C.Structure):
+    """magic_params (include/magic_sht.h): logic.f90 / physical_parameters.f90 values the loop reads."""
+    _ints = ["l_conv", "l_mag", "l_heat", "l_conv_nl", "l_heat_nl", "l_mag_nl", "l_mag_LF", "l_mag_kin", "l_anel",
+             "l_adv_curl", "l_corr", "l_double_curl", "l_single_matrix", "l_chemical_conv", "l_precession",
+             "l_centrifuge", "l_anelastic_liquid", "l_cour_alf_damp", "l_full_sphere", "l_parallel_solve",
+             "l_temperature_diff", "ktopv", "kbotv", "l_cond_ma", "l_cond_ic", "l_rot_ma", "l_rot_ic", "n_r_max",
+             "n_r_LCR"]
+    _dbls = ["LFfac", "CorFac", "epsc", "epscXi", "opm", "ViscHeatFac", "OhmLossFac", "oek", "po", "prec_angle",
+             "dilution_fac", "ra", "opr", "omega_ma", "omega_ic", "r_cmb", "r_icb", "courfac", "alffac"]
+    _fields_ = [(n, c_int) for n in _ints] + [(n, c_double) for n in _dbls]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+RADIAL_NAMES = ["r", "or1", "or2", "or4", "orho1", "orho2", "beta", "rho0", "otemp1", "temp0", "visc", "lambda",
+                "epscProf", "delxr2", "delxh2"]
+IN_NAMES = ["w", "dw", "ddw", "z", "dz", "s", "ds", "p", "xi", "b", "db", "ddb", "aj", "dj"]
+OUT_NAMES = ["dwdt", "dzdt", "dpdt", "dsdt", "dxidt", "dbdt", "djdt", "dVxVhLM", "dVxBhLM", "dVSrLM", "dVXirLM"]
+
+
+class _Radial(C.Structure):
+    _fields_ = [("nR", c_void_p), ("l_R", c_void_p)] + [(n + "_", c_void_p) for n in RADIAL_NAMES]
+
+
+class _FieldsIn(C.Structure):
+    _fields_ = [(n, c_void_p) for n in IN_NAMES]
+
+
+class _FieldsOut(C.Structure):
+    _fields_ = [(n, c_void_p) for n in OUT_NAMES] + [("dtrkc", c_void_p), ("dthkc", c_void_p)]
+
+
+class RadialLoop:
+    """initialize_radialLoop + radialLoopG (radialLoop.f90:26-101) for the levels of one rank."""
+
+    def __init__(self, sht, params, radial, level_chunk=0):
+        """radial: dict with 'nR' (global 1-based level numbers), 'l_R' and the arrays of RADIAL_NAMES,
+        one entry per local level (radial_functions, radial.f90:283-307)."""
+        self.lib = load_library()
+        self.sht = sht
+        self.params = params
+        self.n_r_loc = len(radial["nR"])
+        keep = []
+        rad = _Radial()
+        for nm in ["nR", "l_R"]:
+            a = np.ascontiguousarray(radial[nm], dtype=np.int32)
+            keep.append(a)
+            setattr(rad, nm, a.ctypes.data)
+        for nm in RADIAL_NAMES:
+            a = np.ascontiguousarray(radial.get(nm, np.ones(self.n_r_loc)), dtype=np.float64)
+            if a.shape != (self.n_r_loc,):
+                raise ValueError(f"radial['{nm}'] must have {self.n_r_loc} entries")
+            keep.append(a)
+            setattr(rad, nm + "_", a.ctypes.data)
+        self._h = c_void_p()
+        check(self.lib.magic_rloop_create(sht.handle, byref(params), byref(rad), c_int(self.n_r_loc), c_int(level_chunk),
+                                          byref(self._h)))
+
+    def finalize(self):
+        if self._h:
+            self.lib.magic_rloop_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.finalize()
+        except Exception:
+            pass
+
+    def _structs(self, fields, outs, dtrkc, dthkc, device):
+        fin = _FieldsIn()
+        fout = _FieldsOut()
+        keep = []
+        for nm in IN_NAMES:
+            v = fields.get(nm)
+            if v is None:
+                continue
+            if device:
+                setattr(fin, nm, int(v))
+            else:
+                a = np.ascontiguousarray(v, dtype=np.complex128)
+                if a.shape != (self.n_r_loc, self.sht.lm_max):
+                    raise ValueError(f"field '{nm}' must have shape ({self.n_r_loc}, {self.sht.lm_max})")
+                keep.append(a)
+                setattr(fin, nm, a.ctypes.data)
+        for nm in OUT_NAMES:
+            v = outs.get(nm)
+            if v is None:
+                continue
+            setattr(fout, nm, int(v) if device else v.ctypes.data)
+        fout.dtrkc = int(dtrkc) if device else dtrkc.ctypes.data
+        fout.dthkc = int(dthkc) if device else dthkc.ctypes.data
+        return fin, fout, keep
+
+    def radialLoop(self, fields, time=0.0, out=None):
+        """Host-buffer call (what the Fortran rIter_cuda_t does).  fields: name -> complex128 [n_r_loc, lm_max].
+        Returns dict of outputs; pass `out` to reuse arrays."""
+        if out is None:
+            out = {nm: np.zeros((self.n_r_loc, self.sht.lm_max), dtype=np.complex128) for nm in OUT_NAMES}
+            out["dtrkc"] = np.zeros(self.n_r_loc)
+            out["dthkc"] = np.zeros(self.n_r_loc)
+        fin, fout, keep = self._structs(fields, out, out["dtrkc"], out["dthkc"], device=False)
+        check(self.lib.magic_rloop_run(self._h, byref(fin), byref(fout), c_double(time)))
+        return out
+
+    def radialLoop_dev(self, fields_dev, out_dev, dtrkc_dev, dthkc_dev, time=0.0):
+        """Device-pointer call: dict name -> int device pointer (e.g. torch tensor .data_ptr())."""
+        fin, fout, keep = self._structs(fields_dev, out_dev, dtrkc_dev, dthkc_dev, device=True)
+        check(self.lib.magic_rloop_run_dev(self._h, byref(fin), byref(fout), c_double(time)))
+
+    def sync(self):
+        check(self.lib.magic_rloop_sync(self._h))
+
+    def launch_count(self):
+        return int(self.lib.magic_rloop_launch_count(self._h))
+
+    def last_timing(self):
+        t = (c_double * 8)()
+        check(self.lib.magic_rloop_last_timing(self._h, t))
+        keys = ["total", "prep", "legendre_syn", "fft_c2r", "get_nl", "fft_r2c", "legendre_an", "get_td"]
+        return dict(zip(keys, list(t)))
+
+    def legendre_flops(self):
+        return float(self.lib.magic_rloop_legendre_flops(self._h))
