@@ -37,6 +37,12 @@ int magic_sht_create(int l_max, int m_max, int minc, int n_theta_max, int n_phi_
                      int device_id, int *l_scrambled_theta, magic_sht **out);
 int magic_sht_destroy(magic_sht *h);
 
+/* The CUDA stream (cudaStream_t) every kernel, copy and NCCL call of this handle is issued on, so a host can
+ * order its own work or record events against it. */
+void *magic_sht_stream(const magic_sht *h);
+/* Number of kernels launched on behalf of this handle so far. */
+long long magic_sht_launch_count(const magic_sht *h);
+
 /* Gauss-Legendre colatitudes (north->south, radians) and weights as horizontal.f90:279-340 computes
  * them; lets the host check that both sides use the same grid. */
 int magic_sht_get_grid(const magic_sht *h, double *theta_ord, double *gauss);
@@ -144,6 +150,10 @@ int magic_transp_extents(const magic_transp *t, int *llm, int *ulm, int *nRstart
 /* arr_LMloc(llm:ulm, 1:n_r_max, n_fields) -> arr_Rloc(1:lm_max, nRstart:nRstop, n_fields), device pointers. */
 int magic_transp_lm2r_dev(magic_transp *t, const double *arr_LMloc, double *arr_Rloc);
 int magic_transp_r2lm_dev(magic_transp *t, const double *arr_Rloc, double *arr_LMloc);
+/* Same, for a container of n_fields <= the width given at creation (one object and one NCCL communicator can
+ * serve all containers of communications.f90:66-69). */
+int magic_transp_lm2r_dev_n(magic_transp *t, int n_fields, const double *arr_LMloc, double *arr_Rloc);
+int magic_transp_r2lm_dev_n(magic_transp *t, int n_fields, const double *arr_Rloc, double *arr_LMloc);
 /* Host-pointer variants (H2D + exchange + D2H). */
 int magic_transp_lm2r(magic_transp *t, const double *arr_LMloc, double *arr_Rloc);
 int magic_transp_r2lm(magic_transp *t, const double *arr_Rloc, double *arr_LMloc);

@@ -66,6 +66,9 @@ extern "C" int magic_sht_destroy(magic_sht *h) {
     return 0;
 }
 
+extern "C" void *magic_sht_stream(const magic_sht *h) { return h ? (void *)h->stream : nullptr; }
+extern "C" long long magic_sht_launch_count(const magic_sht *h) { return h ? h->launches : 0; }
+
 extern "C" int magic_sht_get_grid(const magic_sht *h, double *theta_ord, double *gauss) {
     if (!h) MFAIL("null handle");
     for (int i = 0; i < h->n_theta; i++) { theta_ord[i] = h->theta_ord[i]; gauss[i] = h->gauss[i]; }

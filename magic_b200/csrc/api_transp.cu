@@ -119,15 +119,15 @@ struct PackArgs {
     const int *rcount;     // [n_procs]
     const int *lstart;     // [n_procs] 0-based first lo index of each rank
     const int *lcount;     // [n_procs]
-    const long long *disp; // [n_procs+1] element displacement of each peer segment
+    const long long *disp; // [n_procs+1] element displacement of each peer segment, PER FIELD
     const int *lo2st;
 };
 
-__device__ __forceinline__ int find_seg(const long long *disp, int n, long long idx) {
-    int lo = 0, hi = n;  // disp[lo] <= idx < disp[hi]
+__device__ __forceinline__ int find_seg(const long long *disp, int n, long long idx, int nf) {
+    int lo = 0, hi = n;  // nf*disp[lo] <= idx < nf*disp[hi]
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
-        if (disp[mid] <= idx) lo = mid; else hi = mid;
+        if (disp[mid] * nf <= idx) lo = mid; else hi = mid;
     }
     return lo;
 }
@@ -137,8 +137,8 @@ __global__ void lmside_kernel(PackArgs a, const double2 *__restrict__ arr_LM_in,
                               const double2 *__restrict__ buf_in, double2 *__restrict__ buf_out, long long total) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    int q = find_seg(a.disp, a.n_procs, idx);
-    long long rel = idx - a.disp[q];
+    int q = find_seg(a.disp, a.n_procs, idx, a.n_fields);
+    long long rel = idx - a.disp[q] * a.n_fields;
     int lm = (int)(rel % a.nlm);
     long long t = rel / a.nlm;
     int r = (int)(t % a.rcount[q]), f = (int)(t / a.rcount[q]);
@@ -152,8 +152,8 @@ __global__ void rside_kernel(PackArgs a, const double2 *__restrict__ arr_R_in, d
                              const double2 *__restrict__ buf_in, double2 *__restrict__ buf_out, long long total) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    int p = find_seg(a.disp, a.n_procs, idx);
-    long long rel = idx - a.disp[p];
+    int p = find_seg(a.disp, a.n_procs, idx, a.n_fields);
+    long long rel = idx - a.disp[p] * a.n_fields;
     int lm = (int)(rel % a.lcount[p]);
     long long t = rel / a.lcount[p];
     int r = (int)(t % a.nr), f = (int)(t / a.nr);
@@ -163,13 +163,25 @@ __global__ void rside_kernel(PackArgs a, const double2 *__restrict__ arr_R_in, d
     else arr_R_out[pos] = buf_in[idx];            // unpack (mpi_transpose.f90:341-357)
 }
 
+// single rank: the exchange is the identity, so lm2r / r2lm reduce to the lo<->st permutation
+__global__ void permute_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, const int *__restrict__ lo2st, int lm_max,
+                               long long rows, int to_st) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * lm_max) return;
+    long long row = idx / lm_max;
+    int lm = (int)(idx - row * lm_max);
+    size_t st = (size_t)row * lm_max + lo2st[lm];
+    if (to_st) out[st] = in[idx];
+    else out[idx] = in[st];
+}
+
 }  // namespace
 
 struct magic_transp {
     magic_sht *h = nullptr;
-    int rank = 0, n_procs = 1, n_r_max = 0, n_fields = 0;
+    int rank = 0, n_procs = 1, n_r_max = 0, n_fields = 0;  // n_fields = widest container this object serves
     std::vector<int> rs, re, ls, le, lo2st;
-    std::vector<long long> lmside_cnt, lmside_disp, rside_cnt, rside_disp;  // complex elements
+    std::vector<long long> lm1, lmd1, r1, rd1;  // per-field counts / displacements (complex elements)
     int *d_rstart = nullptr, *d_rcount = nullptr, *d_lstart = nullptr, *d_lcount = nullptr, *d_lo2st = nullptr;
     long long *d_lmdisp = nullptr, *d_rdisp = nullptr;
     double *sendbuf = nullptr, *recvbuf = nullptr, *stage_lm = nullptr, *stage_r = nullptr;
@@ -209,20 +221,20 @@ extern "C" int magic_transp_create(magic_sht *h, const char id[128], int rank, i
     build_lo_map(h, n_procs, t->lo2st, t->ls, t->le);
     const int nlm = t->le[rank] - t->ls[rank] + 1, nr = t->re[rank] - t->rs[rank] + 1;
     std::vector<int> rstart(n_procs), rcount(n_procs), lstart(n_procs), lcount(n_procs);
-    t->lmside_cnt.assign(n_procs, 0); t->lmside_disp.assign(n_procs + 1, 0);
-    t->rside_cnt.assign(n_procs, 0); t->rside_disp.assign(n_procs + 1, 0);
+    t->lm1.assign(n_procs, 0); t->lmd1.assign(n_procs + 1, 0);
+    t->r1.assign(n_procs, 0); t->rd1.assign(n_procs + 1, 0);
     for (int p = 0; p < n_procs; p++) {
         rstart[p] = t->rs[p] - 1; rcount[p] = t->re[p] - t->rs[p] + 1;
         lstart[p] = t->ls[p] - 1; lcount[p] = t->le[p] - t->ls[p] + 1;
-        // create_comm_alltoallv, mpi_transpose.f90:134-139
-        t->lmside_cnt[p] = (long long)rcount[p] * nlm * n_fields;
-        t->rside_cnt[p] = (long long)nr * lcount[p] * n_fields;
-        t->lmside_disp[p + 1] = t->lmside_disp[p] + t->lmside_cnt[p];
-        t->rside_disp[p + 1] = t->rside_disp[p] + t->rside_cnt[p];
+        // create_comm_alltoallv, mpi_transpose.f90:134-139 (per field)
+        t->lm1[p] = (long long)rcount[p] * nlm;
+        t->r1[p] = (long long)nr * lcount[p];
+        t->lmd1[p + 1] = t->lmd1[p] + t->lm1[p];
+        t->rd1[p + 1] = t->rd1[p] + t->r1[p];
     }
     if (dev_upload_vec(&t->d_rstart, rstart) || dev_upload_vec(&t->d_rcount, rcount) || dev_upload_vec(&t->d_lstart, lstart) ||
-        dev_upload_vec(&t->d_lcount, lcount) || dev_upload_vec(&t->d_lo2st, t->lo2st) || dev_upload_vec(&t->d_lmdisp, t->lmside_disp) ||
-        dev_upload_vec(&t->d_rdisp, t->rside_disp)) {
+        dev_upload_vec(&t->d_lcount, lcount) || dev_upload_vec(&t->d_lo2st, t->lo2st) || dev_upload_vec(&t->d_lmdisp, t->lmd1) ||
+        dev_upload_vec(&t->d_rdisp, t->rd1)) {
         magic_transp_destroy(t);
         return 1;
     }
@@ -231,10 +243,10 @@ extern "C" int magic_transp_create(magic_sht *h, const char id[128], int rank, i
     a.llm = t->ls[rank] - 1; a.nlm = nlm; a.r0 = t->rs[rank] - 1; a.nr = nr;
     a.rstart = t->d_rstart; a.rcount = t->d_rcount; a.lstart = t->d_lstart; a.lcount = t->d_lcount; a.lo2st = t->d_lo2st;
     a.disp = nullptr;
-    size_t maxel = (size_t)std::max(t->lmside_disp[n_procs], t->rside_disp[n_procs]);
-    MCHECK(cudaMalloc((void **)&t->sendbuf, sizeof(double) * 2 * maxel));
-    MCHECK(cudaMalloc((void **)&t->recvbuf, sizeof(double) * 2 * maxel));
     if (n_procs > 1) {
+        size_t maxel = (size_t)std::max(t->lmd1[n_procs], t->rd1[n_procs]) * n_fields;
+        MCHECK(cudaMalloc((void **)&t->sendbuf, sizeof(double) * 2 * maxel));
+        MCHECK(cudaMalloc((void **)&t->recvbuf, sizeof(double) * 2 * maxel));
         if (!id) { magic_transp_destroy(t); MFAIL("magic_transp_create: NCCL id required for n_procs > 1"); }
         if (nccl_load()) { magic_transp_destroy(t); return 1; }
         ncclUniqueId uid;
@@ -260,16 +272,18 @@ extern "C" int magic_transp_extents(const magic_transp *t, int *llm, int *ulm, i
 extern "C" int magic_transp_counts(const magic_transp *t, int dir, long long *scounts, long long *sdisp, long long *rcounts,
                                    long long *rdisp) {
     if (!t) MFAIL("null transposer");
-    const auto &sc = dir == 0 ? t->lmside_cnt : t->rside_cnt, &sd = dir == 0 ? t->lmside_disp : t->rside_disp;
-    const auto &rc = dir == 0 ? t->rside_cnt : t->lmside_cnt, &rd = dir == 0 ? t->rside_disp : t->lmside_disp;
-    for (int p = 0; p < t->n_procs; p++) { scounts[p] = sc[p]; sdisp[p] = sd[p]; rcounts[p] = rc[p]; rdisp[p] = rd[p]; }
+    const auto &sc = dir == 0 ? t->lm1 : t->r1, &sd = dir == 0 ? t->lmd1 : t->rd1;
+    const auto &rc = dir == 0 ? t->r1 : t->lm1, &rd = dir == 0 ? t->rd1 : t->lmd1;
+    const long long nf = t->n_fields;
+    for (int p = 0; p < t->n_procs; p++) { scounts[p] = nf * sc[p]; sdisp[p] = nf * sd[p]; rcounts[p] = nf * rc[p]; rdisp[p] = nf * rd[p]; }
     return 0;
 }
 
-static int side_launch(magic_transp *t, bool lmside, const double *arr_in, double *arr_out, const double *buf_in, double *buf_out) {
+static int side_launch(magic_transp *t, int nf, bool lmside, const double *arr_in, double *arr_out, const double *buf_in, double *buf_out) {
     PackArgs a = t->args;
+    a.n_fields = nf;
     a.disp = lmside ? t->d_lmdisp : t->d_rdisp;
-    long long total = lmside ? t->lmside_disp[t->n_procs] : t->rside_disp[t->n_procs];
+    long long total = (lmside ? t->lmd1[t->n_procs] : t->rd1[t->n_procs]) * nf;
     if (total == 0) return 0;
     int blocks = (int)((total + 255) / 256);
     if (lmside)
@@ -281,72 +295,89 @@ static int side_launch(magic_transp *t, bool lmside, const double *arr_in, doubl
     return 0;
 }
 
+#define TCHK(t, nf)                                                                  \
+    if (!(t)) MFAIL("null transposer");                                              \
+    if ((nf) < 1 || (nf) > (t)->n_fields) MFAIL("transposer: n_fields out of range"); \
+    MCHECK(cudaSetDevice((t)->h->dev));
+
 extern "C" int magic_transp_pack_lm2r_dev(magic_transp *t, const double *arr_LMloc, double *sendbuf) {
-    if (!t) MFAIL("null transposer");
-    MCHECK(cudaSetDevice(t->h->dev));
-    return side_launch(t, true, arr_LMloc, nullptr, nullptr, sendbuf);
+    TCHK(t, t->n_fields);
+    return side_launch(t, t->n_fields, true, arr_LMloc, nullptr, nullptr, sendbuf);
 }
 extern "C" int magic_transp_unpack_lm2r_dev(magic_transp *t, const double *recvbuf, double *arr_Rloc) {
-    if (!t) MFAIL("null transposer");
-    MCHECK(cudaSetDevice(t->h->dev));
-    return side_launch(t, false, nullptr, arr_Rloc, recvbuf, nullptr);
+    TCHK(t, t->n_fields);
+    return side_launch(t, t->n_fields, false, nullptr, arr_Rloc, recvbuf, nullptr);
 }
 extern "C" int magic_transp_pack_r2lm_dev(magic_transp *t, const double *arr_Rloc, double *sendbuf) {
-    if (!t) MFAIL("null transposer");
-    MCHECK(cudaSetDevice(t->h->dev));
-    return side_launch(t, false, arr_Rloc, nullptr, nullptr, sendbuf);
+    TCHK(t, t->n_fields);
+    return side_launch(t, t->n_fields, false, arr_Rloc, nullptr, nullptr, sendbuf);
 }
 extern "C" int magic_transp_unpack_r2lm_dev(magic_transp *t, const double *recvbuf, double *arr_LMloc) {
-    if (!t) MFAIL("null transposer");
-    MCHECK(cudaSetDevice(t->h->dev));
-    return side_launch(t, true, nullptr, arr_LMloc, recvbuf, nullptr);
+    TCHK(t, t->n_fields);
+    return side_launch(t, t->n_fields, true, nullptr, arr_LMloc, recvbuf, nullptr);
 }
 
 // all-to-all(v): segment p of sendbuf goes to rank p, segment p of recvbuf comes from rank p
-static int exchange(magic_transp *t, const std::vector<long long> &scnt, const std::vector<long long> &sdisp,
+static int exchange(magic_transp *t, long long nf, const std::vector<long long> &scnt, const std::vector<long long> &sdisp,
                     const std::vector<long long> &rcnt, const std::vector<long long> &rdisp) {
     cudaStream_t st = t->h->stream;
     const int me = t->rank;
-    MCHECK(cudaMemcpyAsync(t->recvbuf + 2 * rdisp[me], t->sendbuf + 2 * sdisp[me], sizeof(double) * 2 * scnt[me], cudaMemcpyDeviceToDevice, st));
-    if (t->n_procs == 1) return 0;
+    MCHECK(cudaMemcpyAsync(t->recvbuf + 2 * nf * rdisp[me], t->sendbuf + 2 * nf * sdisp[me], sizeof(double) * 2 * nf * scnt[me],
+                           cudaMemcpyDeviceToDevice, st));
     NCHECK(g_nccl.GroupStart());
     for (int p = 0; p < t->n_procs; p++) {
         if (p == me) continue;
-        NCHECK(g_nccl.Send(t->sendbuf + 2 * sdisp[p], (size_t)(2 * scnt[p]), ncclDouble, p, t->comm, st));
-        NCHECK(g_nccl.Recv(t->recvbuf + 2 * rdisp[p], (size_t)(2 * rcnt[p]), ncclDouble, p, t->comm, st));
+        NCHECK(g_nccl.Send(t->sendbuf + 2 * nf * sdisp[p], (size_t)(2 * nf * scnt[p]), ncclDouble, p, t->comm, st));
+        NCHECK(g_nccl.Recv(t->recvbuf + 2 * nf * rdisp[p], (size_t)(2 * nf * rcnt[p]), ncclDouble, p, t->comm, st));
     }
     NCHECK(g_nccl.GroupEnd());
     return 0;
 }
 
-extern "C" int magic_transp_lm2r_dev(magic_transp *t, const double *arr_LMloc, double *arr_Rloc) {
-    if (!t) MFAIL("null transposer");
-    MCHECK(cudaSetDevice(t->h->dev));
-    if (side_launch(t, true, arr_LMloc, nullptr, nullptr, t->sendbuf)) return 1;
-    if (exchange(t, t->lmside_cnt, t->lmside_disp, t->rside_cnt, t->rside_disp)) return 1;
-    return side_launch(t, false, nullptr, arr_Rloc, t->recvbuf, nullptr);
+static int permute_launch(magic_transp *t, int nf, const double *in, double *out, int to_st) {
+    long long rows = (long long)nf * t->n_r_max, total = rows * t->h->lm_max;
+    permute_kernel<<<(int)((total + 255) / 256), 256, 0, t->h->stream>>>((const double2 *)in, (double2 *)out, t->d_lo2st, t->h->lm_max, rows, to_st);
+    t->h->launches++;
+    MCHECK(cudaGetLastError());
+    return 0;
 }
 
+extern "C" int magic_transp_lm2r_dev_n(magic_transp *t, int nf, const double *arr_LMloc, double *arr_Rloc) {
+    TCHK(t, nf);
+    if (t->n_procs == 1) return permute_launch(t, nf, arr_LMloc, arr_Rloc, 1);
+    if (side_launch(t, nf, true, arr_LMloc, nullptr, nullptr, t->sendbuf)) return 1;
+    if (exchange(t, nf, t->lm1, t->lmd1, t->r1, t->rd1)) return 1;
+    return side_launch(t, nf, false, nullptr, arr_Rloc, t->recvbuf, nullptr);
+}
+
+extern "C" int magic_transp_r2lm_dev_n(magic_transp *t, int nf, const double *arr_Rloc, double *arr_LMloc) {
+    TCHK(t, nf);
+    if (t->n_procs == 1) return permute_launch(t, nf, arr_Rloc, arr_LMloc, 0);
+    if (side_launch(t, nf, false, arr_Rloc, nullptr, nullptr, t->sendbuf)) return 1;
+    if (exchange(t, nf, t->r1, t->rd1, t->lm1, t->lmd1)) return 1;
+    return side_launch(t, nf, true, nullptr, arr_LMloc, t->recvbuf, nullptr);
+}
+
+extern "C" int magic_transp_lm2r_dev(magic_transp *t, const double *arr_LMloc, double *arr_Rloc) {
+    if (!t) MFAIL("null transposer");
+    return magic_transp_lm2r_dev_n(t, t->n_fields, arr_LMloc, arr_Rloc);
+}
 extern "C" int magic_transp_r2lm_dev(magic_transp *t, const double *arr_Rloc, double *arr_LMloc) {
     if (!t) MFAIL("null transposer");
-    MCHECK(cudaSetDevice(t->h->dev));
-    if (side_launch(t, false, arr_Rloc, nullptr, nullptr, t->sendbuf)) return 1;
-    if (exchange(t, t->rside_cnt, t->rside_disp, t->lmside_cnt, t->lmside_disp)) return 1;
-    return side_launch(t, true, nullptr, arr_LMloc, t->recvbuf, nullptr);
+    return magic_transp_r2lm_dev_n(t, t->n_fields, arr_Rloc, arr_LMloc);
 }
 
 static int ensure_stage(magic_transp *t) {
     if (t->stage_lm) return 0;
-    MCHECK(cudaMalloc((void **)&t->stage_lm, sizeof(double) * 2 * (size_t)t->lmside_disp[t->n_procs]));
-    MCHECK(cudaMalloc((void **)&t->stage_r, sizeof(double) * 2 * (size_t)t->rside_disp[t->n_procs]));
+    MCHECK(cudaMalloc((void **)&t->stage_lm, sizeof(double) * 2 * (size_t)t->lmd1[t->n_procs] * t->n_fields));
+    MCHECK(cudaMalloc((void **)&t->stage_r, sizeof(double) * 2 * (size_t)t->rd1[t->n_procs] * t->n_fields));
     return 0;
 }
 
 extern "C" int magic_transp_lm2r(magic_transp *t, const double *arr_LMloc, double *arr_Rloc) {
-    if (!t) MFAIL("null transposer");
-    MCHECK(cudaSetDevice(t->h->dev));
+    TCHK(t, t->n_fields);
     if (ensure_stage(t)) return 1;
-    size_t blm = sizeof(double) * 2 * (size_t)t->lmside_disp[t->n_procs], br = sizeof(double) * 2 * (size_t)t->rside_disp[t->n_procs];
+    size_t blm = sizeof(double) * 2 * (size_t)t->lmd1[t->n_procs] * t->n_fields, br = sizeof(double) * 2 * (size_t)t->rd1[t->n_procs] * t->n_fields;
     MCHECK(cudaMemcpyAsync(t->stage_lm, arr_LMloc, blm, cudaMemcpyHostToDevice, t->h->stream));
     if (magic_transp_lm2r_dev(t, t->stage_lm, t->stage_r)) return 1;
     MCHECK(cudaMemcpyAsync(arr_Rloc, t->stage_r, br, cudaMemcpyDeviceToHost, t->h->stream));
@@ -355,10 +386,9 @@ extern "C" int magic_transp_lm2r(magic_transp *t, const double *arr_LMloc, doubl
 }
 
 extern "C" int magic_transp_r2lm(magic_transp *t, const double *arr_Rloc, double *arr_LMloc) {
-    if (!t) MFAIL("null transposer");
-    MCHECK(cudaSetDevice(t->h->dev));
+    TCHK(t, t->n_fields);
     if (ensure_stage(t)) return 1;
-    size_t blm = sizeof(double) * 2 * (size_t)t->lmside_disp[t->n_procs], br = sizeof(double) * 2 * (size_t)t->rside_disp[t->n_procs];
+    size_t blm = sizeof(double) * 2 * (size_t)t->lmd1[t->n_procs] * t->n_fields, br = sizeof(double) * 2 * (size_t)t->rd1[t->n_procs] * t->n_fields;
     MCHECK(cudaMemcpyAsync(t->stage_r, arr_Rloc, br, cudaMemcpyHostToDevice, t->h->stream));
     if (magic_transp_r2lm_dev(t, t->stage_r, t->stage_lm)) return 1;
     MCHECK(cudaMemcpyAsync(arr_LMloc, t->stage_lm, blm, cudaMemcpyDeviceToHost, t->h->stream));

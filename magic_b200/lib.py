@@ -14,7 +14,7 @@ class MagicError(RuntimeError):
 
 # every symbol include/magic_sht.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "magic_last_error", "magic_device_count", "magic_sht_create", "magic_sht_destroy", "magic_sht_get_grid",
+    "magic_last_error", "magic_device_count", "magic_sht_create", "magic_sht_destroy", "magic_sht_get_grid", "magic_sht_stream", "magic_sht_launch_count",
     "magic_scal_to_spat", "magic_scal_to_grad_spat", "magic_pol_to_grad_spat", "magic_torpol_to_spat",
     "magic_sphtor_to_spat", "magic_torpol_to_curl_spat_IC", "magic_torpol_to_spat_IC", "magic_torpol_to_dphspat",
     "magic_pol_to_curlr_spat", "magic_torpol_to_curl_spat", "magic_scal_to_SH", "magic_spat_to_qst",
@@ -22,7 +22,7 @@ SYMBOLS = [
     "magic_rloop_create", "magic_rloop_destroy", "magic_rloop_run", "magic_rloop_run_dev", "magic_rloop_sync",
     "magic_rloop_launch_count", "magic_rloop_last_timing", "magic_rloop_legendre_flops",
     "magic_transp_unique_id", "magic_transp_create", "magic_transp_destroy", "magic_transp_extents",
-    "magic_transp_lm2r_dev", "magic_transp_r2lm_dev", "magic_transp_lm2r", "magic_transp_r2lm",
+    "magic_transp_lm2r_dev", "magic_transp_r2lm_dev", "magic_transp_lm2r_dev_n", "magic_transp_r2lm_dev_n", "magic_transp_lm2r", "magic_transp_r2lm",
     "magic_transp_pack_lm2r_dev", "magic_transp_unpack_lm2r_dev", "magic_transp_pack_r2lm_dev",
     "magic_transp_unpack_r2lm_dev", "magic_transp_counts",
     "magic_dev_malloc", "magic_dev_free", "magic_dev_upload", "magic_dev_download",
@@ -42,6 +42,10 @@ def load_library():
     lib.magic_rloop_launch_count.argtypes = [c_void_p]
     lib.magic_rloop_legendre_flops.restype = c_double
     lib.magic_rloop_legendre_flops.argtypes = [c_void_p]
+    lib.magic_sht_stream.restype = c_void_p
+    lib.magic_sht_stream.argtypes = [c_void_p]
+    lib.magic_sht_launch_count.restype = c_longlong
+    lib.magic_sht_launch_count.argtypes = [c_void_p]
     lib.magic_dev_malloc.argtypes = [c_void_p, c_size_t, POINTER(c_void_p)]
     lib.magic_dev_free.argtypes = [c_void_p, c_void_p]
     lib.magic_dev_upload.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t]

@@ -85,6 +85,14 @@ class Sht:
             raise MagicError("Sht handle already finalized")
         return self._h
 
+    @property
+    def stream(self):
+        """cudaStream_t (int) all work of this handle is issued on."""
+        return int(self.lib.magic_sht_stream(self.handle) or 0)
+
+    def launch_count(self):
+        return int(self.lib.magic_sht_launch_count(self.handle))
+
     def get_grid(self):
         th = np.zeros(self.n_theta_max)
         g = np.zeros(self.n_theta_max)

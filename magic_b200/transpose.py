@@ -84,6 +84,12 @@ class Transposer:
     def transp_r2lm_dev(self, arr_Rloc_dev, arr_LMloc_dev):
         check(self.lib.magic_transp_r2lm_dev(self._h, c_void_p(arr_Rloc_dev), c_void_p(arr_LMloc_dev)))
 
+    def transp_lm2r_dev_n(self, n_fields, arr_LMloc_dev, arr_Rloc_dev):
+        check(self.lib.magic_transp_lm2r_dev_n(self._h, c_int(n_fields), c_void_p(arr_LMloc_dev), c_void_p(arr_Rloc_dev)))
+
+    def transp_r2lm_dev_n(self, n_fields, arr_Rloc_dev, arr_LMloc_dev):
+        check(self.lib.magic_transp_r2lm_dev_n(self._h, c_int(n_fields), c_void_p(arr_Rloc_dev), c_void_p(arr_LMloc_dev)))
+
     def pack_lm2r_dev(self, arr_dev, buf_dev):
         check(self.lib.magic_transp_pack_lm2r_dev(self._h, c_void_p(arr_dev), c_void_p(buf_dev)))
 

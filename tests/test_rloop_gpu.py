@@ -1,0 +1,116 @@
+"""GPU parity: the batched radial loop (rIter.f90:94-464) through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def oracle_params(p):
+    from oracle.oracle import Params as OParams
+    op = OParams()
+    for n, _ in p._fields_:
+        setattr(op, n, getattr(p, n))
+    return op
+
+
+def run_both(l_max, n_r_max, physics, levels, level_chunk=0, ktopv=2, kbotv=2, minc=1, n_phi_tot=0, l_R=None, seed=3):
+    from magic_b200 import RadialLoop, Sht, grid_sizes
+    from magic_b200.workload import make_fields, make_params, make_radial
+    from oracle.oracle import Oracle
+    gs = grid_sizes(l_max=l_max, n_phi_tot=n_phi_tot, minc=minc)
+    o = Oracle(gs["l_max"], minc=minc, n_theta=gs["n_theta_max"], n_phi=gs["n_phi_max"], m_max=gs["m_max"])
+    s = Sht(gs["l_max"], m_max=gs["m_max"], minc=minc, n_theta_max=gs["n_theta_max"], n_phi_max=gs["n_phi_max"])
+    p = make_params(physics, n_r_max, ktopv=ktopv, kbotv=kbotv)
+    rad_full = make_radial(n_r_max, gs["l_max"], l_R=l_R, anel=(physics == "anel"))
+    idx = np.array(levels) - 1
+    rad = {k: np.ascontiguousarray(v[idx]) for k, v in rad_full.items()}
+    fields = make_fields(physics, o.lm2l, o.lm2m, len(levels), seed)
+    rl = RadialLoop(s, p, rad, level_chunk=level_chunk)
+    got = rl.radialLoop(fields)
+    ref = o.radial_loop(oracle_params(p), rad, fields)
+    # Conditioning probe: the oracle's response to a last-bits (1e-15 relative) perturbation of its inputs.
+    # Outputs that are small differences of large sums (e.g. the toroidal part of the nonlinear force,
+    # |T| ~ 1e-3 |S| for these rough synthetic fields) cannot agree better than this between ANY two
+    # correctly rounded evaluation orders -- the reference's own -O2 and -O3 -mfma builds differ by more.
+    prng = np.random.default_rng(12345)
+    pert = {k: v * (1.0 + 1e-15 * prng.standard_normal(v.shape)) for k, v in fields.items()}
+    noise = o.radial_loop(oracle_params(p), rad, pert)
+    timing = rl.last_timing()
+    rl.finalize()
+    s.finalize_sht()
+    return o, p, rad, got, ref, (noise, timing)
+
+
+def compare(o, p, rad, got, ref, extra, names):
+    """rel. L2 <= 1e-12, or 10x the oracle's own sensitivity to a 1e-15 input perturbation where that is larger."""
+    noise = extra[0]
+    nR = rad["nR"]
+    bulk = (nR != 1) & (nR != p.n_r_max)
+    for nm in names:
+        g, r = got[nm], ref[nm]
+        if nm in ("dVxBhLM", "dVxVhLM", "dVSrLM", "dVXirLM"):
+            sel = slice(None)  # defined on every level (get_td.f90:299-307,511-519,600-617)
+        else:
+            sel = bulk         # d?dt are only written on bulk levels (get_td.f90:153,330,400,478)
+        lo = 1 if nm == "dpdt" else 0  # dpdt(lm=1) is never written by the reference
+        floor = rel_l2(noise[nm][sel][:, lo:], r[sel][:, lo:])
+        assert rel_l2(g[sel][:, lo:], r[sel][:, lo:]) < max(TOL, 10.0 * floor), (nm, floor)
+    assert np.allclose(got["dtrkc"], ref["dtrkc"], rtol=1e-12)
+    assert np.allclose(got["dthkc"], ref["dthkc"], rtol=1e-12)
+
+
+MHD_OUT = ["dwdt", "dzdt", "dpdt", "dsdt", "dbdt", "djdt", "dVxBhLM", "dVSrLM"]
+HYDRO_OUT = ["dwdt", "dzdt", "dpdt", "dsdt", "dVSrLM"]
+
+
+def test_mhd_l16_with_rigid_boundaries():
+    """dynamo_benchmark shape: l_max=16, n_r=33, rigid walls; levels include both boundaries."""
+    o, p, rad, got, ref, ex = run_both(16, 33, "mhd", [1, 2, 3, 17, 31, 32, 33])
+    compare(o, p, rad, got, ref, ex, MHD_OUT)
+
+
+def test_mhd_l16_chunked_equals_unchunked():
+    a = run_both(16, 33, "mhd", list(range(1, 12)), level_chunk=0)
+    b = run_both(16, 33, "mhd", list(range(1, 12)), level_chunk=4)  # chunks of 4,4,3 -> two layouts
+    for nm in MHD_OUT:
+        assert np.array_equal(a[3][nm], b[3][nm]), nm
+    compare(*b, MHD_OUT)
+
+
+def test_mhd_stress_free_boundaries():
+    """ktopv=kbotv=1: lMagNlBc true, get_nl runs on the boundary with nBc=1 (rIter.f90:181-187, get_nl.f90:389-392)."""
+    o, p, rad, got, ref, ex = run_both(16, 33, "mhd", [1, 2, 16, 33], ktopv=1, kbotv=1)
+    compare(o, p, rad, got, ref, ex, MHD_OUT)
+
+
+def test_hydro_minc3_variable_lcut():
+    """full_sphere-like truncation (minc=3, n_phi_tot=96) with l_R varying per level (radial.f90:291-307)."""
+    l_R = np.full(12, 32)
+    l_R[6:] = [30, 27, 23, 18, 12, 5]
+    o, p, rad, got, ref, ex = run_both(0, 12, "hydro", list(range(1, 13)), minc=3, n_phi_tot=96, l_R=l_R)
+    compare(o, p, rad, got, ref, ex, HYDRO_OUT)
+    for i, lc in enumerate(rad["l_R"]):
+        if rad["nR"][i] in (1, 12):
+            continue
+        assert np.all(got["dsdt"][i][(o.lm2l > lc)] == 0)
+
+
+def test_anelastic_hydro_ugradu():
+    """hydro_bench_anel shape (l_adv_curl=.false., viscous heating; get_nl.f90:274-308,402-436)."""
+    o, p, rad, got, ref, ex = run_both(0, 9, "anel", list(range(1, 10)), n_phi_tot=96, ktopv=1, kbotv=1)
+    compare(o, p, rad, got, ref, ex, HYDRO_OUT)
+
+
+def test_mhd_l96_bulk():
+    o, p, rad, got, ref, ex = run_both(0, 97, "mhd", [40, 41, 42], n_phi_tot=288)
+    compare(o, p, rad, got, ref, ex, MHD_OUT)
+
+
+def test_run_to_run_bitwise():
+    a = run_both(16, 33, "mhd", [5, 6, 7, 8])
+    b = run_both(16, 33, "mhd", [5, 6, 7, 8])
+    for nm in MHD_OUT + ["dtrkc", "dthkc"]:
+        assert np.array_equal(a[3][nm], b[3][nm]), nm
