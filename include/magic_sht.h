@@ -168,6 +168,13 @@ int magic_transp_unpack_r2lm_dev(magic_transp *t, const double *recvbuf, double 
 int magic_transp_counts(const magic_transp *t, int dir /*0 lm2r, 1 r2lm*/, long long *scounts, long long *sdisp,
                         long long *rcounts, long long *rdisp);
 
+/* Pure host helpers (no CUDA device needed): the decomposition the transposer uses.
+ * magic_get_blocks: getBlocks (parallel.f90:75-92), 1-based inclusive start/stop per rank.
+ * magic_lo_map: lo2st[lm_lo] = 0-based st_map index of the lm_lo-th entry of lo_map (snake ordering when
+ * n_procs <= l_max/2, blocking.f90:387-544, else l-major :339-385) and each rank's 1-based inclusive lm range. */
+int magic_get_blocks(int n_points, int n_procs, int *start, int *stop);
+int magic_lo_map(int l_max, int m_max, int minc, int n_procs, int *lo2st, int *lm_start, int *lm_stop);
+
 /* Device memory helpers so a host language without a CUDA binding can hold device buffers. */
 int magic_dev_malloc(magic_sht *h, size_t bytes, void **ptr);
 int magic_dev_free(magic_sht *h, void *ptr);

@@ -189,6 +189,30 @@ struct magic_transp {
     PackArgs args;
 };
 
+extern "C" int magic_get_blocks(int n_points, int n_procs, int *start, int *stop) {
+    if (n_procs < 1 || n_points < n_procs || !start || !stop) MFAIL("magic_get_blocks: bad arguments");
+    std::vector<int> s, e;
+    get_blocks(n_points, n_procs, s, e);
+    for (int p = 0; p < n_procs; p++) { start[p] = s[p]; stop[p] = e[p]; }
+    return 0;
+}
+
+extern "C" int magic_lo_map(int l_max, int m_max, int minc, int n_procs, int *lo2st, int *lm_start, int *lm_stop) {
+    if (l_max < 1 || minc < 1 || m_max < 0 || m_max > l_max || m_max % minc != 0 || n_procs < 1) MFAIL("magic_lo_map: bad arguments");
+    magic_sht h;  // host-only shell carrying the truncation
+    h.l_max = l_max; h.m_max = m_max; h.minc = minc; h.n_m = m_max / minc + 1;
+    h.lstart.assign(h.n_m, 0);
+    int lm = 0;
+    for (int mc = 0; mc < h.n_m; mc++) { h.lstart[mc] = lm; lm += l_max - mc * minc + 1; }
+    h.lm_max = lm;
+    if (n_procs > lm) MFAIL("magic_lo_map: more ranks than modes");
+    std::vector<int> map, s, e;
+    build_lo_map(&h, n_procs, map, s, e);
+    for (int i = 0; i < lm; i++) lo2st[i] = map[i];
+    for (int p = 0; p < n_procs; p++) { lm_start[p] = s[p]; lm_stop[p] = e[p]; }
+    return 0;
+}
+
 extern "C" int magic_transp_unique_id(char id[128]) {
     if (nccl_load()) return 1;
     ncclUniqueId uid;

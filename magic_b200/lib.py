@@ -25,6 +25,7 @@ SYMBOLS = [
     "magic_transp_lm2r_dev", "magic_transp_r2lm_dev", "magic_transp_lm2r_dev_n", "magic_transp_r2lm_dev_n", "magic_transp_lm2r", "magic_transp_r2lm",
     "magic_transp_pack_lm2r_dev", "magic_transp_unpack_lm2r_dev", "magic_transp_pack_r2lm_dev",
     "magic_transp_unpack_r2lm_dev", "magic_transp_counts",
+    "magic_get_blocks", "magic_lo_map",
     "magic_dev_malloc", "magic_dev_free", "magic_dev_upload", "magic_dev_download",
 ]
 

@@ -21,6 +21,17 @@ def get_blocks(n_points, n_procs):
     return np.array(start), np.array(stop)
 
 
+def lo_map(l_max, m_max, minc, n_procs):
+    """lo_map of blocking.f90:339-544 from the library (host only): (lo2st, lm_start, lm_stop)."""
+    lib = load_library()
+    lm_max = sum(l_max - m + 1 for m in range(0, m_max + 1, minc))
+    lo2st = np.zeros(lm_max, dtype=np.int32)
+    s = np.zeros(n_procs, dtype=np.int32)
+    e = np.zeros(n_procs, dtype=np.int32)
+    check(lib.magic_lo_map(c_int(l_max), c_int(m_max), c_int(minc), c_int(n_procs), ptr(lo2st), ptr(s), ptr(e)))
+    return lo2st, s, e
+
+
 def unique_id():
     """NCCL bootstrap id (128 bytes) -- create on rank 0 and broadcast."""
     lib = load_library()
