@@ -275,8 +275,10 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
         F.omega_ic = P.omega_ic; F.r_cmb = P.r_cmb; F.r_icb = P.r_icb; F.courfac = P.courfac; F.alffac = P.alffac; F.time = time;
         a.gi = rl->gi; a.go = rl->go; a.gin = rl->buf.gin; a.gout = rl->buf.gout; a.n_lev = nl; a.nh = h->nh; a.n_phi = h->n_phi;
         a.minc = h->minc; a.lev = d_lev; a.sinth = h->d_sinth; a.costh = h->d_costh; a.courmax = rl->buf.courmax;
-        int gx = (int)std::min<size_t>((plane + NL_THREADS - 1) / NL_THREADS, 4096);
-        get_nl_kernel<<<dim3(gx, nl), NL_THREADS, 0, h->stream>>>(a);
+        int gx = (int)((plane + NL_THREADS - 1) / NL_THREADS);
+        const bool mag = P.l_mag || P.l_mag_LF || P.l_mag_nl;
+        const bool extra = !P.l_adv_curl || P.l_anel || P.l_chemical_conv || P.l_precession || P.l_centrifuge;
+        launch_get_nl(a, mag, extra, gx, nl, h->stream);
         courant_finish_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(rl->buf.courmax, d_lev, nl, out->dtrkc + l0, out->dthkc + l0);
         h->launches += 2;
         cudaEventRecord(rl->ev[4], h->stream);

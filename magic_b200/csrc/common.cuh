@@ -27,7 +27,7 @@ struct GemmProb {
     int kt0, kt1;  // k-tiles per segment
     int M;         // valid rows of C
     int ldb, ldc;  // leading dimensions of B and C (doubles)
-    int pad;
+    int Nvalid;    // real (unpadded) column count: DMMA fragments beyond it are skipped
 };
 
 // factor applied to a spectral source when assembling synthesis operands (sht_native.f90 wrappers)

@@ -109,8 +109,7 @@ int sht_init(magic_sht *h) {
     if (dev_upload_vec(&h->d_tw, tw)) return 1;
     h->fft.tw = h->d_tw;
     MCHECK(gemm_setup_attributes());
-    MCHECK(cudaFuncSetAttribute(fft_c2r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    MCHECK(cudaFuncSetAttribute(fft_r2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MCHECK(fft_setup_attributes(h->fft.H));
     MCHECK(cudaStreamSynchronize(h->stream));
     cudaFree(d_pmm);
     return 0;
@@ -214,6 +213,7 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
                     g.B = buf.Bv + L.offBv[prob];
                     g.C = buf.Fv + (size_t)prob * nh * L.Nv;
                     g.ldb = g.ldc = L.Nv;
+                    g.Nvalid = 4 * L.npair_v * n_lev;
                     for (int kt = 0; kt < kt0; kt++) ktv.push_back(KTile{prob, kt, 0, kt});
                     for (int kt = 0; kt < kt1; kt++) ktv.push_back(KTile{prob, kt0 + kt, 1, kt});
                 } else {
@@ -222,6 +222,7 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
                     g.B = buf.Bs + L.offBs[prob];
                     g.C = buf.Fs + (size_t)prob * nh * L.Ns;
                     g.ldb = g.ldc = L.Ns;
+                    g.Nvalid = 2 * L.ncol_s * n_lev;
                     for (int kt = 0; kt < kt0; kt++) kts.push_back(KTile{prob, kt, 0, kt});
                 }
                 int pid = (int)ps.size();
@@ -249,11 +250,13 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
                     g.B = buf.Bav + (size_t)prob * 2 * NHP * L.Nav;
                     g.C = buf.Cav + L.offCav[prob];
                     g.ldb = g.ldc = L.Nav;
+                    g.Nvalid = 4 * L.npair_a * n_lev;
                 } else {
                     g.kt1 = 0;
                     g.B = buf.Bas + (size_t)prob * NHP * L.Nas;
                     g.C = buf.Cas + L.offCas[prob];
                     g.ldb = g.ldc = L.Nas;
+                    g.Nvalid = 2 * L.nf_s * n_lev;
                 }
                 int pid = (int)pa.size();
                 pa.push_back(g);
@@ -320,18 +323,12 @@ int run_synthesis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Bu
     launch_legendre_gemm(false, L.d_probs_syn, L.d_tiles_syn, L.ntiles_syn, h->NHP, h->stream);
     h->launches++;
     if (ev) cudaEventRecord(ev[2], h->stream);
-    const int R = fft_rows_per_cta(h->fft.H, 8);
-    const size_t smem = (size_t)2 * R * h->fft.H * sizeof(double2);
     if (L.ncol_s) {
-        int ncols = L.ncol_s * L.n_lev;
-        dim3 grid((ncols + R - 1) / R, 2 * h->nh);
-        fft_c2r_kernel<<<grid, FFT_THREADS, smem, h->stream>>>(h->fft, buf.Fs, L.Ns, h->n_m, h->nh, ncols, L.d_colrow_s, buf.gin, R);
+        launch_fft_c2r(h->fft, buf.Fs, L.Ns, h->n_m, h->nh, L.ncol_s * L.n_lev, L.d_colrow_s, buf.gin, h->stream);
         h->launches++;
     }
     if (L.npair_v) {
-        int ncols = 2 * L.npair_v * L.n_lev;
-        dim3 grid((ncols + R - 1) / R, 2 * h->nh);
-        fft_c2r_kernel<<<grid, FFT_THREADS, smem, h->stream>>>(h->fft, buf.Fv, L.Nv, h->n_m, h->nh, ncols, L.d_colrow_v, buf.gin, R);
+        launch_fft_c2r(h->fft, buf.Fv, L.Nv, h->n_m, h->nh, 2 * L.npair_v * L.n_lev, L.d_colrow_v, buf.gin, h->stream);
         h->launches++;
     }
     if (ev) cudaEventRecord(ev[3], h->stream);
@@ -341,15 +338,12 @@ int run_synthesis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Bu
 
 int run_analysis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buffers &buf, const LevelInfo *d_lev, cudaEvent_t *ev) {
     if (spec.nfield_out == 0) return 0;
-    const int R = fft_rows_per_cta(h->fft.H, 8);
-    const size_t smem = (size_t)2 * R * h->fft.H * sizeof(double2);
     R2cArgs a{};
     a.grid = buf.gout; a.n_lev = L.n_lev; a.nh = h->nh; a.n_m = h->n_m; a.NHP = h->NHP;
     a.wgauss = h->d_wgauss; a.osin2 = h->d_osin2; a.fields = L.d_r2c;
     a.B[0] = buf.Bas; a.B[1] = buf.Bav; a.ldB[0] = L.Nas; a.ldB[1] = L.Nav; a.minc = h->minc;
     if (ev) cudaEventRecord(ev[0], h->stream);
-    dim3 grid((L.n_lev + R - 1) / R, 2 * h->nh, spec.nfield_out);
-    fft_r2c_kernel<<<grid, FFT_THREADS, smem, h->stream>>>(h->fft, a, R);
+    launch_fft_r2c(h->fft, a, spec.nfield_out, h->stream);
     h->launches++;
     if (ev) cudaEventRecord(ev[1], h->stream);
     launch_legendre_gemm(true, L.d_probs_an, L.d_tiles_an, L.ntiles_an, h->NHP, h->stream);

@@ -3,11 +3,16 @@
 // Replaces fft.f90:164-252 (fft_many / ifft_many, Temperton FFT99) with the same transform definition
 // (fft.f90:262-268): c2r  x_j = sum_k c_k e^{+2 pi i jk/n}, c_{n-k}=conj(c_k) (unnormalised),
 //                    r2c  c_k = (1/n) sum_j x_j e^{-2 pi i jk/n}.
-// A real transform of length N is done as a complex transform of length H=N/2 (Cooley-Lewis-Welch
-// packing, as fft991 does) with a mixed-radix {4,2,3,5} Stockham autosort held in shared memory; one
-// CTA owns R rows.  The c2r kernel gathers its input from the (theta,m)-space matrices written by the
-// Legendre GEMM (zero padding of orders mc >= n_m_max, shtransforms.f90:224-232, is implicit); the r2c
-// kernel scatters its output, already weighted for the quadrature, into the analysis GEMM operands.
+// A real transform of length N is done as a complex transform of length H=N/2 (Cooley-Lewis-Welch packing, as
+// fft991 does) with a mixed-radix {8,4,2,3,5} Stockham autosort in shared memory.  One CTA owns R rows.
+//   * the radix plan is a compile-time function of H, so all index arithmetic is strength reduced;
+//   * each pass is done IN PLACE: a thread pulls all its butterflies into registers, the CTA synchronises, the
+//     results go back to the autosort positions -- one buffer per row instead of two;
+//   * rows are stored with one pad element every 8 (index i -> i + i/8) so the stride-RADIX writes of the first
+//     passes do not serialise on shared-memory banks.
+// The c2r kernel gathers its input from the (theta,m)-space matrices written by the Legendre GEMM (zero padding of
+// orders mc >= n_m_max, shtransforms.f90:224-232, is implicit); the r2c kernel scatters its output, already weighted
+// for the quadrature, into the analysis GEMM operands.  Sizes without a compiled plan use the generic kernels below.
 #pragma once
 #include "common.cuh"
 
@@ -18,9 +23,8 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
 __device__ __forceinline__ double2 cscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
-// multiply by sign*i
+// multiply by sg*i
 __device__ __forceinline__ double2 cmuli(double2 a, double sg) { return make_double2(-sg * a.y, sg * a.x); }
-
 // twiddle e^{sg * 2 pi i idx / N}
 __device__ __forceinline__ double2 twid(const double2 *__restrict__ tw, int idx, double sg) {
     double2 w = __ldg(tw + idx);
@@ -28,67 +32,258 @@ __device__ __forceinline__ double2 twid(const double2 *__restrict__ tw, int idx,
     return w;
 }
 
-// One Stockham pass of radix R over `rows` sequences of length H living in src[row*H ..], writing dst.
-// len = current sub-transform length, s = stride (product of radices done).  See oracle fft_stockham.
+// ---- radix butterflies: o_k = sum_j a_j e^{sg 2 pi i jk/R} ------------------------------------------------------
 template <int R>
-__device__ __forceinline__ void stockham_pass(const double2 *__restrict__ src, double2 *__restrict__ dst, int rows, int H,
-                                              int len, int s, const double2 *__restrict__ tw, int N, double sg) {
-    const int m = len / R;
-    const int nb = H / R;  // butterflies per row = m*s
-    const int twstep = N / len;
+__device__ __forceinline__ void butterfly(const double2 *a, double2 *o, double sg);
+
+template <>
+__device__ __forceinline__ void butterfly<2>(const double2 *a, double2 *o, double) {
+    o[0] = cadd(a[0], a[1]);
+    o[1] = csub(a[0], a[1]);
+}
+template <>
+__device__ __forceinline__ void butterfly<4>(const double2 *a, double2 *o, double sg) {
+    double2 t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]), t2 = cadd(a[1], a[3]), t3 = cmuli(csub(a[1], a[3]), sg);
+    o[0] = cadd(t0, t2);
+    o[1] = cadd(t1, t3);
+    o[2] = csub(t0, t2);
+    o[3] = csub(t1, t3);
+}
+template <>
+__device__ __forceinline__ void butterfly<3>(const double2 *a, double2 *o, double sg) {
+    const double s3 = 0.86602540378443864676372317075294;
+    double2 t = cadd(a[1], a[2]);
+    double2 u = cmuli(cscale(csub(a[1], a[2]), s3), sg);
+    double2 c = make_double2(a[0].x - 0.5 * t.x, a[0].y - 0.5 * t.y);
+    o[0] = cadd(a[0], t);
+    o[1] = cadd(c, u);
+    o[2] = csub(c, u);
+}
+template <>
+__device__ __forceinline__ void butterfly<5>(const double2 *a, double2 *o, double sg) {
+    const double c1 = 0.30901699437494742410229341718282, c2 = -0.80901699437494742410229341718282;
+    const double s1 = 0.95105651629515357211643933337938, s2 = 0.58778525229247312916870595463907;
+    double2 t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]), t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
+    o[0] = cadd(a[0], cadd(t1, t2));
+    double2 m1 = make_double2(a[0].x + c1 * t1.x + c2 * t2.x, a[0].y + c1 * t1.y + c2 * t2.y);
+    double2 m2 = make_double2(a[0].x + c2 * t1.x + c1 * t2.x, a[0].y + c2 * t1.y + c1 * t2.y);
+    double2 n1 = cmuli(make_double2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y), sg);
+    double2 n2 = cmuli(make_double2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y), sg);
+    o[1] = cadd(m1, n1);
+    o[4] = csub(m1, n1);
+    o[2] = cadd(m2, n2);
+    o[3] = csub(m2, n2);
+}
+template <>
+__device__ __forceinline__ void butterfly<8>(const double2 *a, double2 *o, double sg) {
+    const double h = 0.70710678118654752440084436210485;
+    double2 t0 = cadd(a[0], a[4]), t4 = csub(a[0], a[4]), t1 = cadd(a[1], a[5]), t5 = csub(a[1], a[5]);
+    double2 t2 = cadd(a[2], a[6]), t6 = csub(a[2], a[6]), t3 = cadd(a[3], a[7]), t7 = csub(a[3], a[7]);
+    // odd branch inputs multiplied by w8^j, w8 = (1 + sg i)/sqrt2
+    double2 u1 = make_double2(h * (t5.x - sg * t5.y), h * (t5.y + sg * t5.x));
+    double2 u2 = cmuli(t6, sg);
+    double2 u3 = make_double2(h * (-t7.x - sg * t7.y), h * (-t7.y + sg * t7.x));
+    double2 e[4] = {t0, t1, t2, t3}, d[4] = {t4, u1, u2, u3}, ye[4], yd[4];
+    butterfly<4>(e, ye, sg);
+    butterfly<4>(d, yd, sg);
+    o[0] = ye[0]; o[2] = ye[1]; o[4] = ye[2]; o[6] = ye[3];
+    o[1] = yd[0]; o[3] = yd[1]; o[5] = yd[2]; o[7] = yd[3];
+}
+
+__host__ __device__ constexpr int fft_pick_radix(int len) {
+    return len % 8 == 0 ? 8 : len % 4 == 0 ? 4 : len % 2 == 0 ? 2 : len % 3 == 0 ? 3 : len % 5 == 0 ? 5 : 1;
+}
+__host__ __device__ constexpr int fft_pad(int i) { return i + (i >> 3); }
+
+// One in-place Stockham pass (compile-time radix RADIX, sub-length LEN, stride S) over R rows of length H.
+template <int H, int R, int NT, int RADIX, int LEN, int S>
+__device__ __forceinline__ void fft_pass(double2 *buf, const double2 *__restrict__ tw, double sg) {
+    constexpr int M = LEN / RADIX, NB = H / RADIX, TOTAL = R * NB, PER = (TOTAL + NT - 1) / NT;
+    constexpr int TWSTEP = 2 * H / LEN, ROWLEN = fft_pad(H);
+    double2 reg[PER][RADIX];
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+        int idx = threadIdx.x + u * NT;
+        if (TOTAL % NT == 0 || idx < TOTAL) {
+            int row = idx / NB, b = idx - row * NB;
+            const double2 *x = buf + row * ROWLEN;
+#pragma unroll
+            for (int j = 0; j < RADIX; j++) reg[u][j] = x[fft_pad(b + NB * j)];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+        int idx = threadIdx.x + u * NT;
+        if (TOTAL % NT == 0 || idx < TOTAL) {
+            int row = idx / NB, b = idx - row * NB;
+            int p = b / S, q = b - p * S;
+            double2 o[RADIX];
+            butterfly<RADIX>(reg[u], o, sg);
+            double2 *y = buf + row * ROWLEN;
+            y[fft_pad(q + S * (RADIX * p))] = o[0];
+#pragma unroll
+            for (int k = 1; k < RADIX; k++) {
+                double2 v = o[k];
+                if (M > 1) v = cmul(v, twid(tw, p * k * TWSTEP, sg));  // p*k < LEN, so the index is < N
+                y[fft_pad(q + S * (RADIX * p + k))] = v;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int H, int R, int NT, int LEN, int S>
+struct FftPasses {
+    static constexpr int RADIX = fft_pick_radix(LEN);
+    static __device__ __forceinline__ void run(double2 *buf, const double2 *__restrict__ tw, double sg) {
+        fft_pass<H, R, NT, RADIX, LEN, S>(buf, tw, sg);
+        FftPasses<H, R, NT, LEN / RADIX, S * RADIX>::run(buf, tw, sg);
+    }
+};
+template <int H, int R, int NT, int S>
+struct FftPasses<H, R, NT, 1, S> {
+    static __device__ __forceinline__ void run(double2 *, const double2 *, double) {}
+};
+
+constexpr int FFT_R = 4;  // rows per CTA of the planned kernels
+// threads per CTA: about 12 complex elements per thread, so the in-place register staging stays below ~64 registers
+__host__ __device__ constexpr int fft_threads(int H) {
+    return ((H / 3 + 31) / 32) * 32 < 32 ? 32 : ((H / 3 + 31) / 32) * 32 > 512 ? 512 : ((H / 3 + 31) / 32) * 32;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// c2r: grid row (row index = colrow[cc]) of parity s and colatitude k from column cc of F.
+//   F element (mc, s, k, col cc) at F[((mc*2+s)*nh + k)*ld + 2*cc].   blockIdx.x = column chunk, blockIdx.y = s*nh + k.
+template <int H>
+__global__ void __launch_bounds__(fft_threads(H)) fft_c2r_plan_kernel(const double2 *__restrict__ tw, const double *__restrict__ F, int ld,
+                                                                     int n_m, int nh, int ncols, const int *__restrict__ colrow,
+                                                                     double *__restrict__ grid) {
+    constexpr int R = FFT_R, NT = fft_threads(H), N = 2 * H, ROWLEN = fft_pad(H);
+    extern __shared__ __align__(16) double2 fsm[];
+    const int cc0 = blockIdx.x * R;
+    const int sk = blockIdx.y, s = sk / nh, k = sk - s * nh;
+    const int rows = min(R, ncols - cc0);
+    // gather the pair (c_kk, c_{H-kk}) and form  Y_k = (c_k + conj c_{H-k}) + i e^{2 pi i k/N} (c_k - conj c_{H-k})
+    const double *Fb = F + ((size_t)s * nh + k) * ld + 2 * cc0;
+    const size_t mstride = (size_t)2 * nh * ld;
+    for (int idx = threadIdx.x; idx < R * (H / 2 + 1); idx += NT) {
+        int kk = idx / R, r = idx - kk * R;
+        double2 a = make_double2(0.0, 0.0), b = a;
+        if (r < rows) {
+            if (kk < n_m) a = *reinterpret_cast<const double2 *>(Fb + kk * mstride + 2 * r);
+            if (kk > 0 && H - kk < n_m) b = *reinterpret_cast<const double2 *>(Fb + (size_t)(H - kk) * mstride + 2 * r);
+        }
+        if (kk == 0) a.y = 0.0;  // c2r ignores Im c_0 (fft.f90:262-268); c_H = 0 because n_m <= H
+        double2 w = twid(tw, kk, 1.0);
+        double2 cb = cconj(b), ca = cconj(a);
+        double2 *row = fsm + r * ROWLEN;
+        row[fft_pad(kk)] = cadd(cadd(a, cb), cmuli(cmul(w, csub(a, cb)), 1.0));
+        if (kk > 0 && 2 * kk < H) {
+            double2 w2 = make_double2(-w.x, w.y);  // e^{2 pi i (H-kk)/N} = -conj(w)
+            row[fft_pad(H - kk)] = cadd(cadd(b, ca), cmuli(cmul(w2, csub(b, ca)), 1.0));
+        }
+    }
+    __syncthreads();
+    FftPasses<H, R, NT, H, 1>::run(fsm, tw, 1.0);
+    // z_j = x_{2j} + i x_{2j+1}: the grid row is the interleaved complex array itself
+    for (int idx = threadIdx.x; idx < R * H; idx += NT) {
+        int r = idx / H, j = idx - r * H;
+        if (r < rows) {
+            int row = colrow[cc0 + r];
+            if (row >= 0) *reinterpret_cast<double2 *>(grid + (((size_t)row * 2 + s) * nh + k) * N + 2 * j) = fsm[r * ROWLEN + fft_pad(j)];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// r2c: one CTA transforms R grid rows (consecutive levels of one field, fixed s,k) and scatters the weighted
+// coefficients of orders mc < n_m into the analysis operands.  blockIdx.x = level chunk, .y = s*nh + k, .z = field.
+struct R2cArgs {
+    const double *grid;
+    int n_lev, nh, n_m, NHP;
+    const double *wgauss;  // 2 pi * gauss(k) / n_phi  (quadrature weight and forward-FFT normalisation)
+    const double *osin2;   // 1/sin^2(theta_k)
+    const R2cField *fields;
+    double *B[2];          // scalar-class / vector-class analysis operands
+    int ldB[2];
+    int minc;
+};
+
+__device__ __forceinline__ void r2c_scatter(const R2cArgs &a, const R2cField &fd, int s, int k, int mc, int lev, double2 zk, double2 zmc,
+                                            double2 w8, double w, double ws) {
+    // X_k = E_k + e^{-2 pi i k/N} O_k, E=(Z_k+conj Z_{H-k})/2, O=-i (Z_k-conj Z_{H-k})/2
+    double2 zm = cconj(zmc);
+    double2 e = cscale(cadd(zk, zm), 0.5), o = cmuli(cscale(csub(zk, zm), 0.5), -1.0);
+    double2 x = cadd(e, cmul(w8, o));
+    const double dm = (double)(mc * a.minc);
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+        const R2cDest ds = fd.d[s][d];
+        if (ds.rtype == R_NONE) continue;
+        double2 v;
+        if (ds.rtype == R_W) v = cscale(x, w);
+        else if (ds.rtype == R_WS) v = cscale(x, ws);
+        else if (ds.rtype == R_NEG_WS) v = cscale(x, -ws);
+        else v = make_double2(dm * ws * x.y, -dm * ws * x.x);  // -i m ws x
+        const int rowsB = (ds.cls == 0) ? a.NHP : 2 * a.NHP;
+        size_t off = ((size_t)(mc * 2 + ds.p) * rowsB + ds.seg * a.NHP + k) * a.ldB[ds.cls] + 2 * ((size_t)ds.col * a.n_lev + lev);
+        *reinterpret_cast<double2 *>(a.B[ds.cls] + off) = v;
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(fft_threads(H)) fft_r2c_plan_kernel(const double2 *__restrict__ tw, R2cArgs a) {
+    constexpr int R = FFT_R, NT = fft_threads(H), N = 2 * H, ROWLEN = fft_pad(H);
+    extern __shared__ __align__(16) double2 fsm[];
+    const int lev0 = blockIdx.x * R;
+    const int sk = blockIdx.y, s = sk / a.nh, k = sk - s * a.nh;
+    const int field = blockIdx.z;
+    const int rows = min(R, a.n_lev - lev0);
+    for (int idx = threadIdx.x; idx < R * H; idx += NT) {
+        int r = idx / H, j = idx - r * H;
+        double2 v = make_double2(0.0, 0.0);
+        if (r < rows) v = *reinterpret_cast<const double2 *>(a.grid + ((((size_t)field * a.n_lev + lev0 + r) * 2 + s) * a.nh + k) * N + 2 * j);
+        fsm[r * ROWLEN + fft_pad(j)] = v;
+    }
+    __syncthreads();
+    FftPasses<H, R, NT, H, 1>::run(fsm, tw, -1.0);
+    const double w = a.wgauss[k], ws = w * a.osin2[k];
+    const R2cField fd = a.fields[field];
+    for (int idx = threadIdx.x; idx < R * a.n_m; idx += NT) {
+        int mc = idx / R, r = idx - mc * R;
+        if (r >= rows) continue;
+        const double2 *z = fsm + r * ROWLEN;
+        r2c_scatter(a, fd, s, k, mc, lev0 + r, z[fft_pad(mc)], z[fft_pad(mc == 0 ? 0 : H - mc)], twid(tw, mc, -1.0), w, ws);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Generic (run-time plan) kernels for lengths without a compiled plan: ping-pong Stockham, radices {4,2,3,5}.
+template <int RX>
+__device__ __forceinline__ void stockham_pass(const double2 *__restrict__ src, double2 *__restrict__ dst, int rows, int H, int len, int s,
+                                              const double2 *__restrict__ tw, int N, double sg) {
+    const int m = len / RX, nb = H / RX, twstep = N / len;
     for (int idx = threadIdx.x; idx < rows * nb; idx += blockDim.x) {
         int row = idx / nb, b = idx - row * nb;
         int p = b / s, q = b - p * s;
         const double2 *x = src + row * H;
         double2 *y = dst + row * H;
-        double2 a[R];
+        double2 a[RX], o[RX];
 #pragma unroll
-        for (int j = 0; j < R; j++) a[j] = x[q + s * (p + m * j)];
-        double2 o[R];
-        if (R == 2) {
-            o[0] = cadd(a[0], a[1]);
-            o[1] = csub(a[0], a[1]);
-        } else if (R == 4) {
-            double2 t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]), t2 = cadd(a[1], a[3]), t3 = cmuli(csub(a[1], a[3]), sg);
-            o[0] = cadd(t0, t2);
-            o[1] = cadd(t1, t3);
-            o[2] = csub(t0, t2);
-            o[3] = csub(t1, t3);
-        } else if (R == 3) {
-            const double s3 = 0.86602540378443864676372317075294;
-            double2 t = cadd(a[1], a[2]);
-            double2 u = cmuli(cscale(csub(a[1], a[2]), s3), sg);
-            double2 c = make_double2(a[0].x - 0.5 * t.x, a[0].y - 0.5 * t.y);
-            o[0] = cadd(a[0], t);
-            o[1] = cadd(c, u);
-            o[2] = csub(c, u);
-        } else {  // R == 5
-            const double c1 = 0.30901699437494742410229341718282, c2 = -0.80901699437494742410229341718282;
-            const double s1 = 0.95105651629515357211643933337938, s2 = 0.58778525229247312916870595463907;
-            double2 t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]), t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
-            o[0] = cadd(a[0], cadd(t1, t2));
-            double2 m1 = make_double2(a[0].x + c1 * t1.x + c2 * t2.x, a[0].y + c1 * t1.y + c2 * t2.y);
-            double2 m2 = make_double2(a[0].x + c2 * t1.x + c1 * t2.x, a[0].y + c2 * t1.y + c1 * t2.y);
-            double2 n1 = cmuli(make_double2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y), sg);
-            double2 n2 = cmuli(make_double2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y), sg);
-            o[1] = cadd(m1, n1);
-            o[4] = csub(m1, n1);
-            o[2] = cadd(m2, n2);
-            o[3] = csub(m2, n2);
-        }
-        y[q + s * (R * p)] = o[0];
+        for (int j = 0; j < RX; j++) a[j] = x[q + s * (p + m * j)];
+        butterfly<RX>(a, o, sg);
+        y[q + s * (RX * p)] = o[0];
 #pragma unroll
-        for (int k = 1; k < R; k++) y[q + s * (R * p + k)] = (p == 0) ? o[k] : cmul(o[k], twid(tw, p * k * twstep, sg));
+        for (int k = 1; k < RX; k++) y[q + s * (RX * p + k)] = (p == 0) ? o[k] : cmul(o[k], twid(tw, p * k * twstep, sg));
     }
 }
 
-// Complex FFT of length H for `rows` rows: data in buf0, scratch buf1; returns pointer holding the result.
 __device__ __forceinline__ double2 *stockham_fft(double2 *buf0, double2 *buf1, int rows, const FftPlan &pl, double sg) {
     int len = pl.H, s = 1;
     double2 *src = buf0, *dst = buf1;
     for (int f = 0; f < pl.nfac; f++) {
         int r = pl.fac[f];
-        // twiddles of the length-`len` sub-transform are tw[(p*k) * (N/len)]; N = 2H so N/len is integral
         if (r == 4) stockham_pass<4>(src, dst, rows, pl.H, len, s, pl.tw, pl.N, sg);
         else if (r == 2) stockham_pass<2>(src, dst, rows, pl.H, len, s, pl.tw, pl.N, sg);
         else if (r == 3) stockham_pass<3>(src, dst, rows, pl.H, len, s, pl.tw, pl.N, sg);
@@ -103,67 +298,41 @@ __device__ __forceinline__ double2 *stockham_fft(double2 *buf0, double2 *buf1, i
 
 constexpr int FFT_THREADS = 256;
 
-// ------------------------------------------------------------------------------------------------------
-// c2r: grid row (row index r = colrow[cc]) of parity s and colatitude k from column cc of F.
-//   F element (mc, s, k, col cc) at F[((mc*2+s)*nh + k)*ld + 2*cc].
-//   blockIdx.x = column chunk, blockIdx.y = s*nh + k.
-__global__ void __launch_bounds__(FFT_THREADS) fft_c2r_kernel(FftPlan pl, const double *__restrict__ F, int ld, int n_m,
-                                                            int nh, int ncols, const int *__restrict__ colrow,
-                                                            double *__restrict__ grid, int R) {
+__global__ void __launch_bounds__(FFT_THREADS) fft_c2r_kernel(FftPlan pl, const double *__restrict__ F, int ld, int n_m, int nh, int ncols,
+                                                            const int *__restrict__ colrow, double *__restrict__ grid, int R) {
     extern __shared__ __align__(16) double2 fsm[];
     const int H = pl.H, N = pl.N;
     double2 *buf0 = fsm, *buf1 = fsm + (size_t)R * H;
     const int cc0 = blockIdx.x * R;
-    const int sk = blockIdx.y;  // s*nh + k
-    const int s = sk / nh, k = sk - s * nh;
+    const int sk = blockIdx.y, s = sk / nh, k = sk - s * nh;
     const int rows = min(R, ncols - cc0);
-    // gather c_mc (zero for mc >= n_m); thread order: column fastest so a warp reads contiguous 16B pieces
     for (int idx = threadIdx.x; idx < R * H; idx += blockDim.x) {
         int mc = idx / R, r = idx - mc * R;
         double2 v = make_double2(0.0, 0.0);
         if (mc < n_m && r < rows) {
             v = *reinterpret_cast<const double2 *>(F + ((size_t)(mc * 2 + s) * nh + k) * ld + 2 * (cc0 + r));
-            if (mc == 0) v.y = 0.0;  // c2r ignores Im c_0 (fft.f90:262-268)
+            if (mc == 0) v.y = 0.0;
         }
         buf1[r * H + mc] = v;
     }
     __syncthreads();
-    // Y_k = (c_k + conj c_{H-k}) + i e^{2 pi i k/N} (c_k - conj c_{H-k}),  c_H = 0 here (n_m <= H)
     for (int idx = threadIdx.x; idx < R * H; idx += blockDim.x) {
         int r = idx / H, kk = idx - r * H;
         const double2 *c = buf1 + r * H;
         double2 ck = c[kk];
         double2 cm = (kk == 0) ? make_double2(0.0, 0.0) : cconj(c[H - kk]);
-        double2 e = cadd(ck, cm), o = cmuli(cmul(twid(pl.tw, kk, 1.0), csub(ck, cm)), 1.0);
-        buf0[r * H + kk] = cadd(e, o);
+        buf0[r * H + kk] = cadd(cadd(ck, cm), cmuli(cmul(twid(pl.tw, kk, 1.0), csub(ck, cm)), 1.0));
     }
     __syncthreads();
     double2 *res = stockham_fft(buf0, buf1, R, pl, 1.0);
-    // z_j = x_{2j} + i x_{2j+1}: the row is the interleaved complex array itself
     for (int idx = threadIdx.x; idx < R * H; idx += blockDim.x) {
         int r = idx / H, j = idx - r * H;
         if (r < rows) {
             int row = colrow[cc0 + r];
-            if (row >= 0)
-                *reinterpret_cast<double2 *>(grid + (((size_t)row * 2 + s) * nh + k) * N + 2 * j) = res[r * H + j];
+            if (row >= 0) *reinterpret_cast<double2 *>(grid + (((size_t)row * 2 + s) * nh + k) * N + 2 * j) = res[r * H + j];
         }
     }
 }
-
-// ------------------------------------------------------------------------------------------------------
-// r2c: one CTA transforms R grid rows (consecutive levels of one field, fixed s,k) and scatters the
-// weighted coefficients of orders mc < n_m into the analysis operands.
-//   blockIdx.x = level chunk, blockIdx.y = s*nh + k, blockIdx.z = field.
-struct R2cArgs {
-    const double *grid;
-    int n_lev, nh, n_m, NHP;
-    const double *wgauss;  // 2 pi * gauss(k) / n_phi  (quadrature weight and forward-FFT normalisation)
-    const double *osin2;   // 1/sin^2(theta_k)
-    const R2cField *fields;
-    double *B[2];          // scalar-class / vector-class analysis operands
-    int ldB[2];
-    int minc;
-};
 
 __global__ void __launch_bounds__(FFT_THREADS) fft_r2c_kernel(FftPlan pl, R2cArgs a, int R) {
     extern __shared__ __align__(16) double2 fsm[];
@@ -176,44 +345,83 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_r2c_kernel(FftPlan pl, R2cArg
     for (int idx = threadIdx.x; idx < R * H; idx += blockDim.x) {
         int r = idx / H, j = idx - r * H;
         double2 v = make_double2(0.0, 0.0);
-        if (r < rows)
-            v = *reinterpret_cast<const double2 *>(a.grid + ((((size_t)field * a.n_lev + lev0 + r) * 2 + s) * a.nh + k) * N + 2 * j);
+        if (r < rows) v = *reinterpret_cast<const double2 *>(a.grid + ((((size_t)field * a.n_lev + lev0 + r) * 2 + s) * a.nh + k) * N + 2 * j);
         buf0[idx] = v;
     }
     __syncthreads();
     double2 *Z = stockham_fft(buf0, buf1, R, pl, -1.0);
     const double w = a.wgauss[k], ws = w * a.osin2[k];
     const R2cField fd = a.fields[field];
-    // X_k = E_k + e^{-2 pi i k/N} O_k, E=(Z_k+conj Z_{H-k})/2, O=-i (Z_k-conj Z_{H-k})/2 ; only k < n_m kept.
     for (int idx = threadIdx.x; idx < rows * a.n_m; idx += blockDim.x) {
         int mc = idx / rows, r = idx - mc * rows;
         const double2 *z = Z + r * H;
-        double2 zk = z[mc], zm = cconj(z[mc == 0 ? 0 : H - mc]);
-        double2 e = cscale(cadd(zk, zm), 0.5), o = cmuli(cscale(csub(zk, zm), 0.5), -1.0);
-        double2 x = cadd(e, cmul(twid(pl.tw, mc, -1.0), o));
-        const double dm = (double)(mc * a.minc);
-#pragma unroll
-        for (int d = 0; d < 2; d++) {
-            const R2cDest ds = fd.d[s][d];
-            if (ds.rtype == R_NONE) continue;
-            double2 v;
-            if (ds.rtype == R_W) v = cscale(x, w);
-            else if (ds.rtype == R_WS) v = cscale(x, ws);
-            else if (ds.rtype == R_NEG_WS) v = cscale(x, -ws);
-            else v = make_double2(dm * ws * x.y, -dm * ws * x.x);  // -i m ws x
-            const int rowsB = (ds.cls == 0) ? a.NHP : 2 * a.NHP;
-            size_t off = ((size_t)(mc * 2 + ds.p) * rowsB + ds.seg * a.NHP + k) * a.ldB[ds.cls] +
-                         2 * ((size_t)ds.col * a.n_lev + lev0 + r);
-            *reinterpret_cast<double2 *>(a.B[ds.cls] + off) = v;
-        }
+        r2c_scatter(a, fd, s, k, mc, lev0 + r, z[mc], z[mc == 0 ? 0 : H - mc], twid(pl.tw, mc, -1.0), w, ws);
     }
 }
 
 inline int fft_rows_per_cta(int H, int want) {
-    // two ping-pong buffers of R*H complex doubles; keep below ~96 KB so two CTAs fit per SM
-    int r = want;
+    int r = want;  // two ping-pong buffers of R*H complex doubles; keep below ~96 KB so two CTAs fit per SM
     while (r > 1 && (size_t)2 * r * H * sizeof(double2) > 96 * 1024) r >>= 1;
     return r;
+}
+
+// ---- dispatch ---------------------------------------------------------------------------------------------
+#define MAGIC_FFT_PLANS(X) X(16) X(24) X(32) X(48) X(64) X(72) X(96) X(128) X(144) X(192) X(256) X(384) X(512) X(768) X(1024) X(1536)
+
+inline bool fft_has_plan(int H) {
+#define X(h) if (H == h) return true;
+    MAGIC_FFT_PLANS(X)
+#undef X
+    return false;
+}
+inline size_t fft_plan_smem(int H) { return (size_t)FFT_R * fft_pad(H) * sizeof(double2); }
+
+inline cudaError_t fft_setup_attributes(int H) {
+    cudaError_t e = cudaFuncSetAttribute(fft_c2r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(fft_r2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+#define X(h)                                                                                                              \
+    if (H == h) {                                                                                                         \
+        e = cudaFuncSetAttribute(fft_c2r_plan_kernel<h>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_plan_smem(h)); \
+        if (e != cudaSuccess) return e;                                                                                   \
+        e = cudaFuncSetAttribute(fft_r2c_plan_kernel<h>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_plan_smem(h)); \
+        if (e != cudaSuccess) return e;                                                                                   \
+    }
+    MAGIC_FFT_PLANS(X)
+#undef X
+    return cudaSuccess;
+}
+
+inline void launch_fft_c2r(const FftPlan &pl, const double *F, int ld, int n_m, int nh, int ncols, const int *colrow, double *grid,
+                           cudaStream_t st) {
+    const int H = pl.H;
+#define X(h)                                                                                                                      \
+    if (H == h) {                                                                                                                 \
+        dim3 g((ncols + FFT_R - 1) / FFT_R, 2 * nh);                                                                              \
+        fft_c2r_plan_kernel<h><<<g, fft_threads(h), fft_plan_smem(h), st>>>(pl.tw, F, ld, n_m, nh, ncols, colrow, grid);          \
+        return;                                                                                                                   \
+    }
+    MAGIC_FFT_PLANS(X)
+#undef X
+    const int R = fft_rows_per_cta(H, 8);
+    dim3 g((ncols + R - 1) / R, 2 * nh);
+    fft_c2r_kernel<<<g, FFT_THREADS, (size_t)2 * R * H * sizeof(double2), st>>>(pl, F, ld, n_m, nh, ncols, colrow, grid, R);
+}
+
+inline void launch_fft_r2c(const FftPlan &pl, const R2cArgs &a, int nfields, cudaStream_t st) {
+    const int H = pl.H;
+#define X(h)                                                                                      \
+    if (H == h) {                                                                                 \
+        dim3 g((a.n_lev + FFT_R - 1) / FFT_R, 2 * a.nh, nfields);                                 \
+        fft_r2c_plan_kernel<h><<<g, fft_threads(h), fft_plan_smem(h), st>>>(pl.tw, a);            \
+        return;                                                                                   \
+    }
+    MAGIC_FFT_PLANS(X)
+#undef X
+    const int R = fft_rows_per_cta(H, 8);
+    dim3 g((a.n_lev + R - 1) / R, 2 * a.nh, nfields);
+    fft_r2c_kernel<<<g, FFT_THREADS, (size_t)2 * R * H * sizeof(double2), st>>>(pl, a, R);
 }
 
 }  // namespace magic

@@ -57,6 +57,9 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    // valid 8-row / 8-column fragments of this warp (ragged M of the analysis, padded N): the rest is skipped
+    const int mfr = min(4, max(0, (pr.M - m0 - wm + 7) >> 3)), nfr = min(4, max(0, (pr.Nvalid - n0 - wn + 7) >> 3));
+    const bool active = mfr > 0 && nfr > 0;
 
     auto load_stage = [&](int kt, int st) {
         double *As = smem + st * STAGE, *Bs = As + A_TILE;
@@ -103,20 +106,30 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
             cp_async_commit();
         }
         const double *As = smem + (kt % STAGES) * STAGE, *Bs = As + A_TILE;
+        if (active) {
 #pragma unroll
-        for (int kk = 0; kk < BK / 4; kk++) {
-            double a[4], b[4];
+            for (int kk = 0; kk < BK / 4; kk++) {
+                double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                int row = wm + i * 8 + g;
-                a[i] = A_KCONTIG ? As[row * LDA_K + kk * 4 + t] : As[(kk * 4 + t) * LDA_M + row];
+                for (int i = 0; i < 4; i++) {
+                    int row = wm + i * 8 + g;
+                    a[i] = A_KCONTIG ? As[row * LDA_K + kk * 4 + t] : As[(kk * 4 + t) * LDA_M + row];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) b[j] = Bs[(kk * 4 + t) * LDB_S + wn + j * 8 + g];
+                if (mfr == 4 && nfr == 4) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (i < mfr && j < nfr) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
             }
-#pragma unroll
-            for (int j = 0; j < 4; j++) b[j] = Bs[(kk * 4 + t) * LDB_S + wn + j * 8 + g];
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
     cp_async_wait<0>();

@@ -42,12 +42,15 @@ struct PointIn { double vr, vt, vp, cvr, cvt, cvp, s, br, bt, bp, cbr, cbt, cbp,
 struct PointOut { double Advr, Advt, Advp, VSr, VSt, VSp, VxBr, VxBt, VxBp, VXir, VXit, VXip, heat; };
 
 // get_nl.f90:213-441 at one grid point.  ct/cn2 carry the hemisphere sign.
+// MAG: magnetic fields present.  EXTRA: anything beyond the Boussinesq curl-form set (u.grad u advection, anelastic
+// heating, composition, precession, centrifuge); when false those branches and their loads are compiled out.
+template <bool MAG, bool EXTRA>
 __device__ __forceinline__ void nl_point(const NlFlags &F, const LevelInfo &L, const PointIn &p, double st, double ct, double os2,
                                          double cn2, double phi, PointOut &o) {
     const int nBc = L.nBc, nR = L.nR;
     const double or1 = L.or1, or2 = L.or2, or4 = L.or4, orho1 = L.orho1, beta = L.beta, r = L.r;
     double LFr = 0, LFt = 0, LFp = 0;
-    const bool lf_on = F.l_mag_LF && nBc == 0 && nR > F.n_r_LCR;
+    const bool lf_on = MAG && F.l_mag_LF && nBc == 0 && nR > F.n_r_LCR;
     if (lf_on) {
         LFr = F.LFfac * os2 * (p.cbt * p.bp - p.cbp * p.bt);
         LFt = F.LFfac * or4 * (p.cbp * p.br - p.cbr * p.bp);
@@ -55,7 +58,7 @@ __device__ __forceinline__ void nl_point(const NlFlags &F, const LevelInfo &L, c
     }
     double Ar = 0, At = 0, Ap = 0;
     if (F.l_conv_nl && nBc == 0) {
-        if (F.l_adv_curl) {
+        if (!EXTRA || F.l_adv_curl) {
             Ar = -os2 * (p.cvt * p.vp - p.cvp * p.vt);
             At = -or4 * (p.cvp * p.vr - p.cvr * p.vp);
             Ap = -or4 * (p.cvr * p.vt - p.cvt * p.vr);
@@ -73,14 +76,14 @@ __device__ __forceinline__ void nl_point(const NlFlags &F, const LevelInfo &L, c
         if (nR > F.n_r_LCR) { Ar = LFr; At = LFt; Ap = LFp; }
         else { Ar = 0; At = 0; Ap = 0; }
     }
-    if (F.l_precession && nBc == 0) {
+    if (EXTRA && F.l_precession && nBc == 0) {
         const double posnalp = -2.0 * F.oek * F.po * sin(F.prec_angle);
         const double ph = F.oek * F.time + phi;
         Ar += posnalp * (1.0 / st) * r * (cos(ph) * p.vp * ct + sin(ph) * p.vt);
         At += -posnalp * st * or2 * (cos(ph) * p.vp + sin(ph) * or1 * p.vr);
         Ap += posnalp * st * cos(ph) * or2 * (p.vt - or1 * p.vr * ct);
     }
-    if (F.l_centrifuge && nBc == 0) {
+    if (EXTRA && F.l_centrifuge && nBc == 0) {
         Ar += -F.dilution_fac * r * (st * st * st * st) * F.ra * F.opr * p.s;
         At += -F.dilution_fac * r * (st * st * st) * ct * F.ra * F.opr * p.s;
     }
@@ -92,13 +95,13 @@ __device__ __forceinline__ void nl_point(const NlFlags &F, const LevelInfo &L, c
         o.VSp = or2 * p.vp * p.s;
     }
     o.VXir = o.VXit = o.VXip = 0;
-    if (F.l_chemical_conv && nBc == 0) {
+    if (EXTRA && F.l_chemical_conv && nBc == 0) {
         o.VXir = p.vr * p.xi;
         o.VXit = or2 * p.vt * p.xi;
         o.VXip = or2 * p.vp * p.xi;
     }
     o.VxBr = o.VxBt = o.VxBp = 0;
-    if (F.l_mag_nl) {
+    if (MAG && F.l_mag_nl) {
         if (nBc == 0 && nR > F.n_r_LCR) {
             o.VxBr = orho1 * os2 * (p.vt * p.bp - p.vp * p.bt);
             o.VxBt = orho1 * or4 * (p.vp * p.br - p.vr * p.bp);
@@ -112,7 +115,7 @@ __device__ __forceinline__ void nl_point(const NlFlags &F, const LevelInfo &L, c
         }
     }
     o.heat = 0;
-    if (F.l_anel && nBc == 0) {
+    if (EXTRA && F.l_anel && nBc == 0) {
         double t1 = p.dvrdr - (2.0 * or1 + beta) * p.vr;
         double t2 = cn2 * p.vt + p.dvpdp + p.dvrdr - or1 * p.vr;
         double t3 = p.dvpdp + cn2 * p.vt + or1 * p.vr;
@@ -129,7 +132,8 @@ __device__ __forceinline__ void nl_point(const NlFlags &F, const LevelInfo &L, c
 
 constexpr int NL_THREADS = 256;
 
-__global__ void __launch_bounds__(NL_THREADS) get_nl_kernel(NlArgs a) {
+template <bool MAG, bool EXTRA>
+__global__ void __launch_bounds__(NL_THREADS, EXTRA ? 1 : 2) get_nl_kernel(NlArgs a) {
     const int lev = blockIdx.y;
     const LevelInfo L = a.lev[lev];
     const NlFlags &F = a.f;
@@ -142,8 +146,8 @@ __global__ void __launch_bounds__(NL_THREADS) get_nl_kernel(NlArgs a) {
         valhi2 = h * h / L.delxh2;
     }
     const double cf2 = F.courfac * F.courfac, af2 = F.alffac * F.alffac;
-    for (size_t pt = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pt < plane; pt += (size_t)gridDim.x * blockDim.x) {
-        const int k = (int)(pt / a.n_phi), j = (int)(pt - (size_t)k * a.n_phi);
+    for (unsigned pt = blockIdx.x * blockDim.x + threadIdx.x; pt < (unsigned)plane; pt += gridDim.x * blockDim.x) {
+        const int k = (int)(pt / (unsigned)a.n_phi), j = (int)(pt - (unsigned)k * (unsigned)a.n_phi);
         const double st = a.sinth[k], ct = a.costh[k];
         const double os2 = 1.0 / (st * st), cn2 = ct / st / st;
         const double phi = (double)j * (6.283185307179586476925286766559 / (double)(a.n_phi * a.minc));
@@ -158,14 +162,23 @@ __global__ void __launch_bounds__(NL_THREADS) get_nl_kernel(NlArgs a) {
         ld(a.gi.vr, pn.vr, ps.vr); ld(a.gi.vt, pn.vt, ps.vt); ld(a.gi.vp, pn.vp, ps.vp);
         ld(a.gi.cvr, pn.cvr, ps.cvr); ld(a.gi.cvt, pn.cvt, ps.cvt); ld(a.gi.cvp, pn.cvp, ps.cvp);
         ld(a.gi.s, pn.s, ps.s);
-        ld(a.gi.br, pn.br, ps.br); ld(a.gi.bt, pn.bt, ps.bt); ld(a.gi.bp, pn.bp, ps.bp);
-        ld(a.gi.cbr, pn.cbr, ps.cbr); ld(a.gi.cbt, pn.cbt, ps.cbt); ld(a.gi.cbp, pn.cbp, ps.cbp);
-        ld(a.gi.xi, pn.xi, ps.xi);
-        ld(a.gi.dvrdr, pn.dvrdr, ps.dvrdr); ld(a.gi.dvtdr, pn.dvtdr, ps.dvtdr); ld(a.gi.dvpdr, pn.dvpdr, ps.dvpdr);
-        ld(a.gi.dvrdt, pn.dvrdt, ps.dvrdt); ld(a.gi.dvrdp, pn.dvrdp, ps.dvrdp);
-        ld(a.gi.dvtdp, pn.dvtdp, ps.dvtdp); ld(a.gi.dvpdp, pn.dvpdp, ps.dvpdp);
-        // torpol_to_dphspat post-scaling by 1/sin^2 (sht_native.f90:263-270)
-        pn.dvtdp *= os2; ps.dvtdp *= os2; pn.dvpdp *= os2; ps.dvpdp *= os2;
+        if (MAG) {
+            ld(a.gi.br, pn.br, ps.br); ld(a.gi.bt, pn.bt, ps.bt); ld(a.gi.bp, pn.bp, ps.bp);
+            ld(a.gi.cbr, pn.cbr, ps.cbr); ld(a.gi.cbt, pn.cbt, ps.cbt); ld(a.gi.cbp, pn.cbp, ps.cbp);
+        } else {
+            pn.br = ps.br = pn.bt = ps.bt = pn.bp = ps.bp = pn.cbr = ps.cbr = pn.cbt = ps.cbt = pn.cbp = ps.cbp = 0.0;
+        }
+        if (EXTRA) {
+            ld(a.gi.xi, pn.xi, ps.xi);
+            ld(a.gi.dvrdr, pn.dvrdr, ps.dvrdr); ld(a.gi.dvtdr, pn.dvtdr, ps.dvtdr); ld(a.gi.dvpdr, pn.dvpdr, ps.dvpdr);
+            ld(a.gi.dvrdt, pn.dvrdt, ps.dvrdt); ld(a.gi.dvrdp, pn.dvrdp, ps.dvrdp);
+            ld(a.gi.dvtdp, pn.dvtdp, ps.dvtdp); ld(a.gi.dvpdp, pn.dvpdp, ps.dvpdp);
+            // torpol_to_dphspat post-scaling by 1/sin^2 (sht_native.f90:263-270)
+            pn.dvtdp *= os2; ps.dvtdp *= os2; pn.dvpdp *= os2; ps.dvpdp *= os2;
+        } else {
+            pn.xi = ps.xi = pn.dvrdr = ps.dvrdr = pn.dvtdr = ps.dvtdr = pn.dvpdr = ps.dvpdr = 0.0;
+            pn.dvrdt = ps.dvrdt = pn.dvrdp = ps.dvrdp = pn.dvtdp = ps.dvtdp = pn.dvpdp = ps.dvpdp = 0.0;
+        }
         // boundary overrides of transform_to_grid_space (rIter.f90:555-602)
         if (L.nBc == 1) { pn.vr = 0.0; ps.vr = 0.0; }
         if (L.nBc == 2) {  // v_rigid_boundary, nonlinear_bcs.f90:120-175 (l_vr_cmb/icb = .false.)
@@ -176,8 +189,8 @@ __global__ void __launch_bounds__(NL_THREADS) get_nl_kernel(NlArgs a) {
         }
         PointOut on, os;
         if (L.nl_on) {
-            nl_point(F, L, pn, st, ct, os2, cn2, phi, on);
-            nl_point(F, L, ps, st, -ct, os2, -cn2, phi, os);
+            nl_point<MAG, EXTRA>(F, L, pn, st, ct, os2, cn2, phi, on);
+            nl_point<MAG, EXTRA>(F, L, ps, st, -ct, os2, -cn2, phi, os);
         } else {
             on = PointOut{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             os = on;
@@ -190,9 +203,11 @@ __global__ void __launch_bounds__(NL_THREADS) get_nl_kernel(NlArgs a) {
         };
         stf(a.go.Advr, on.Advr, os.Advr); stf(a.go.Advt, on.Advt, os.Advt); stf(a.go.Advp, on.Advp, os.Advp);
         stf(a.go.VSr, on.VSr, os.VSr); stf(a.go.VSt, on.VSt, os.VSt); stf(a.go.VSp, on.VSp, os.VSp);
-        stf(a.go.VxBr, on.VxBr, os.VxBr); stf(a.go.VxBt, on.VxBt, os.VxBt); stf(a.go.VxBp, on.VxBp, os.VxBp);
-        stf(a.go.VXir, on.VXir, os.VXir); stf(a.go.VXit, on.VXit, os.VXit); stf(a.go.VXip, on.VXip, os.VXip);
-        stf(a.go.heat, on.heat, os.heat);
+        if (MAG) { stf(a.go.VxBr, on.VxBr, os.VxBr); stf(a.go.VxBt, on.VxBt, os.VxBt); stf(a.go.VxBp, on.VxBp, os.VxBp); }
+        if (EXTRA) {
+            stf(a.go.VXir, on.VXir, os.VXir); stf(a.go.VXit, on.VXit, os.VXit); stf(a.go.VXip, on.VXip, os.VXip);
+            stf(a.go.heat, on.heat, os.heat);
+        }
         // courant.f90:209-275 (XSH_COURANT == 0)
         if (L.cour_on) {
 #pragma unroll
@@ -200,7 +215,7 @@ __global__ void __launch_bounds__(NL_THREADS) get_nl_kernel(NlArgs a) {
                 const PointIn &p = h == 0 ? pn : ps;
                 double vflr2 = L.orho2 * p.vr * p.vr;
                 double vflh2 = (p.vt * p.vt + p.vp * p.vp) * os2 * L.orho2;
-                if (F.l_mag && F.l_mag_LF && !F.l_mag_kin) {
+                if (MAG && F.l_mag && F.l_mag_LF && !F.l_mag_kin) {
                     double valr = p.br * p.br * F.LFfac * L.orho1;
                     double valr2 = valr * valr / (valr + valri2);
                     if (!(valr + valri2 > 0.0)) valr2 = 0.0;
@@ -229,6 +244,17 @@ __global__ void __launch_bounds__(NL_THREADS) get_nl_kernel(NlArgs a) {
             atomic_max_pos(a.courmax + 2 * lev, vr2max);
             atomic_max_pos(a.courmax + 2 * lev + 1, vh2max);
         }
+    }
+}
+
+inline void launch_get_nl(const NlArgs &a, bool mag, bool extra, int gx, int n_lev, cudaStream_t st) {
+    dim3 g(gx, n_lev);
+    if (extra) {
+        if (mag) get_nl_kernel<true, true><<<g, NL_THREADS, 0, st>>>(a);
+        else get_nl_kernel<false, true><<<g, NL_THREADS, 0, st>>>(a);
+    } else {
+        if (mag) get_nl_kernel<true, false><<<g, NL_THREADS, 0, st>>>(a);
+        else get_nl_kernel<false, false><<<g, NL_THREADS, 0, st>>>(a);
     }
 }
 
