@@ -271,16 +271,18 @@ extern "C" int magic_transp_create(magic_sht *h, const char id[128], int rank, i
         size_t maxel = (size_t)std::max(t->lmd1[n_procs], t->rd1[n_procs]) * n_fields;
         MCHECK(cudaMalloc((void **)&t->sendbuf, sizeof(double) * 2 * maxel));
         MCHECK(cudaMalloc((void **)&t->recvbuf, sizeof(double) * 2 * maxel));
-        if (!id) { magic_transp_destroy(t); MFAIL("magic_transp_create: NCCL id required for n_procs > 1"); }
-        if (nccl_load()) { magic_transp_destroy(t); return 1; }
-        ncclUniqueId uid;
-        memcpy(&uid, id, 128);
-        ncclResult_t r = g_nccl.CommInitRank(&t->comm, n_procs, uid, rank);
-        if (r != ncclSuccess) {
-            g_last_error = std::string("ncclCommInitRank -> ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
-            t->comm = nullptr;
-            magic_transp_destroy(t);
-            return 1;
+        // id == NULL: no communicator (pack/unpack halves only -- used to test the permutation kernels in one process)
+        if (id) {
+            if (nccl_load()) { magic_transp_destroy(t); return 1; }
+            ncclUniqueId uid;
+            memcpy(&uid, id, 128);
+            ncclResult_t r = g_nccl.CommInitRank(&t->comm, n_procs, uid, rank);
+            if (r != ncclSuccess) {
+                g_last_error = std::string("ncclCommInitRank -> ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+                t->comm = nullptr;
+                magic_transp_destroy(t);
+                return 1;
+            }
         }
     }
     *out = t;
@@ -346,6 +348,7 @@ static int exchange(magic_transp *t, long long nf, const std::vector<long long> 
                     const std::vector<long long> &rcnt, const std::vector<long long> &rdisp) {
     cudaStream_t st = t->h->stream;
     const int me = t->rank;
+    if (!t->comm) MFAIL("transposer was created without an NCCL id: only the pack/unpack halves are available");
     MCHECK(cudaMemcpyAsync(t->recvbuf + 2 * nf * rdisp[me], t->sendbuf + 2 * nf * sdisp[me], sizeof(double) * 2 * nf * scnt[me],
                            cudaMemcpyDeviceToDevice, st));
     NCHECK(g_nccl.GroupStart());
