@@ -123,7 +123,7 @@ static int synth_call(magic_sht *h, int nsrc, const double *const *srcs, const T
     li.nR = 2; li.lcut = lcut; li.nBc = 0; li.lDeriv = 1; li.nl_on = 1; li.or2 = or2;
     MCHECK(cudaMemcpyAsync(c->d_lev, &li, sizeof(li), cudaMemcpyHostToDevice, h->stream));
     const double *src[MAGIC_MAX_SRC];
-    for (int i = 0; i < MAGIC_MAX_SRC; i++) src[i] = c->d_src + (size_t)(i < 6 ? i : 0) * 2 * h->lm_max;
+    for (int i = 0; i < MAGIC_MAX_SRC; i++) src[i] = i < nsrc ? c->d_src + (size_t)i * 2 * h->lm_max : nullptr;
     if (run_synthesis(h, c->spec, c->L, c->buf, src, c->d_lev, nullptr)) return 1;
     const size_t plane = (size_t)2 * h->nh * h->n_phi, gsz = (size_t)h->n_phi * h->nlat_padded;
     dim3 blk(32, 8), grd((h->n_phi + 31) / 32, (h->nh + 31) / 32);

@@ -109,6 +109,7 @@ int sht_init(magic_sht *h) {
     if (dev_upload_vec(&h->d_tw, tw)) return 1;
     h->fft.tw = h->d_tw;
     MCHECK(gemm_setup_attributes());
+    MCHECK(cudaFuncSetAttribute(synth_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_WARPS * MAGIC_MAX_SRC * 32 * (int)sizeof(double2)));
     MCHECK(fft_setup_attributes(h->fft.H));
     MCHECK(cudaStreamSynchronize(h->stream));
     cudaFree(d_pmm);
@@ -136,7 +137,6 @@ void layout_sizes(const magic_sht *h, const BatchSpec &spec, int n_lev, Layout &
     L.offBs.assign((size_t)n_m * 2, 0); L.offBv.assign((size_t)n_m * 2, 0);
     L.offCas.assign((size_t)n_m * 2, 0); L.offCav.assign((size_t)n_m * 2, 0);
     long long pbs = 0, pbv = 0, pcs = 0, pcv = 0;
-    L.n_kts = L.n_ktv = 0;
     for (int mc = 0; mc < n_m; mc++)
         for (int s = 0; s < 2; s++) {
             int prob = mc * 2 + s;
@@ -146,8 +146,6 @@ void layout_sizes(const magic_sht *h, const BatchSpec &spec, int n_lev, Layout &
             L.offBv[prob] = pbv; pbv += (long long)(kts + kto) * BK * L.Nv;
             L.offCas[prob] = pcs; pcs += (long long)Ks * L.Nas;
             L.offCav[prob] = pcv; pcv += (long long)Ks * L.Nav;
-            if (L.ncol_s) L.n_kts += kts;
-            if (L.npair_v) L.n_ktv += kts + kto;
         }
     L.szBs = pbs; L.szBv = pbv;
     L.szFs = (long long)n_m * 2 * nh * L.Ns; L.szFv = (long long)n_m * 2 * nh * L.Nv;
@@ -182,7 +180,7 @@ void buffers_free(Buffers &b) {
 }
 
 void layout_free(Layout &L) {
-    cudaFree(L.d_offBs); cudaFree(L.d_offBv); cudaFree(L.d_offCas); cudaFree(L.d_offCav); cudaFree(L.d_kts); cudaFree(L.d_ktv);
+    cudaFree(L.d_offBs); cudaFree(L.d_offBv); cudaFree(L.d_offCas); cudaFree(L.d_offCav); cudaFree(L.d_prep_blks);
     cudaFree(L.d_probs_syn); cudaFree(L.d_probs_an); cudaFree(L.d_tiles_syn); cudaFree(L.d_tiles_an);
     cudaFree(L.d_colrow_s); cudaFree(L.d_colrow_v); cudaFree(L.d_scal); cudaFree(L.d_vec); cudaFree(L.d_r2c);
     L = Layout();
@@ -190,7 +188,7 @@ void layout_free(Layout &L) {
 
 int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &buf) {
     const int n_m = h->n_m, nh = h->nh, NHP = h->NHP, n_lev = L.n_lev;
-    std::vector<KTile> kts, ktv;
+    std::vector<int2> blks;
     std::vector<GemmProb> ps, pa;
     std::vector<int2> ts, ta;
     const int mt_syn = (nh + GEMM_BM - 1) / GEMM_BM;
@@ -214,8 +212,6 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
                     g.C = buf.Fv + (size_t)prob * nh * L.Nv;
                     g.ldb = g.ldc = L.Nv;
                     g.Nvalid = 4 * L.npair_v * n_lev;
-                    for (int kt = 0; kt < kt0; kt++) ktv.push_back(KTile{prob, kt, 0, kt});
-                    for (int kt = 0; kt < kt1; kt++) ktv.push_back(KTile{prob, kt0 + kt, 1, kt});
                 } else {
                     g.A1 = g.A0;
                     g.kt0 = kt0; g.kt1 = 0;
@@ -223,7 +219,6 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
                     g.C = buf.Fs + (size_t)prob * nh * L.Ns;
                     g.ldb = g.ldc = L.Ns;
                     g.Nvalid = 2 * L.ncol_s * n_lev;
-                    for (int kt = 0; kt < kt0; kt++) kts.push_back(KTile{prob, kt, 0, kt});
                 }
                 int pid = (int)ps.size();
                 ps.push_back(g);
@@ -267,7 +262,9 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
             }
         }
     }
-    L.n_kts = (int)kts.size(); L.n_ktv = (int)ktv.size();
+    for (int mc = 0; mc < n_m; mc++)
+        for (int jt = 0; jt < (h->l_max - mc * h->minc + 1 + 31) / 32; jt++) blks.push_back(make_int2(mc, jt));
+    L.n_prep_blks = (int)blks.size();
     L.ntiles_syn = (int)ts.size(); L.ntiles_an = (int)ta.size();
     std::vector<int> crs((size_t)L.ncol_s * n_lev), crv((size_t)2 * L.npair_v * n_lev);
     for (int c = 0; c < L.ncol_s; c++)
@@ -293,7 +290,7 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
         r2c[fp].d[1][1] = R2cDest{1, 2 * i + 1, 0, 1, R_NEG_WS};  // A- -> even T, D segment
     }
     if (dev_upload_vec(&L.d_offBs, L.offBs) || dev_upload_vec(&L.d_offBv, L.offBv) || dev_upload_vec(&L.d_offCas, L.offCas) ||
-        dev_upload_vec(&L.d_offCav, L.offCav) || dev_upload_vec(&L.d_kts, kts) || dev_upload_vec(&L.d_ktv, ktv) ||
+        dev_upload_vec(&L.d_offCav, L.offCav) || dev_upload_vec(&L.d_prep_blks, blks) ||
         dev_upload_vec(&L.d_probs_syn, ps) || dev_upload_vec(&L.d_probs_an, pa) || dev_upload_vec(&L.d_tiles_syn, ts) ||
         dev_upload_vec(&L.d_tiles_an, ta) || dev_upload_vec(&L.d_colrow_s, crs) || dev_upload_vec(&L.d_colrow_v, crv) ||
         dev_upload_vec(&L.d_scal, spec.scal) || dev_upload_vec(&L.d_vec, spec.vec) || dev_upload_vec(&L.d_r2c, r2c))
@@ -315,10 +312,17 @@ int run_synthesis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Bu
     a.scal = L.d_scal; a.vec = L.d_vec;
     a.ncol_s = L.ncol_s; a.npair_v = L.npair_v; a.n_lev = L.n_lev; a.lm_max = h->lm_max;
     a.Ns = L.Ns; a.Nv = L.Nv; a.lev = d_lev; a.lstart = h->d_lstart; a.l_max = h->l_max; a.minc = h->minc;
-    a.Bs = buf.Bs; a.Bv = buf.Bv; a.offBs = L.d_offBs; a.offBv = L.d_offBv; a.kts = L.d_kts; a.ktv = L.d_ktv;
+    a.Bs = buf.Bs; a.Bv = buf.Bv; a.offBs = L.d_offBs; a.offBv = L.d_offBv; a.blks = L.d_prep_blks;
+    a.nsrc = 0;
+    for (int i = 0; i < MAGIC_MAX_SRC; i++)
+        if (src[i]) a.nsrc = i + 1;
     if (ev) cudaEventRecord(ev[0], h->stream);
-    if (L.ncol_s && L.n_kts) { synth_prep_scal_kernel<<<L.n_kts, 256, 0, h->stream>>>(a); h->launches++; }
-    if (L.npair_v && L.n_ktv) { synth_prep_vec_kernel<<<L.n_ktv, 256, 0, h->stream>>>(a); h->launches++; }
+    if ((L.ncol_s || L.npair_v) && L.n_prep_blks) {
+        size_t smem = (size_t)PREP_WARPS * a.nsrc * 32 * sizeof(double2);
+        dim3 grid(L.n_prep_blks, (L.n_lev + PREP_WARPS - 1) / PREP_WARPS);
+        synth_prep_kernel<<<grid, PREP_WARPS * 32, smem, h->stream>>>(a);
+        h->launches++;
+    }
     if (ev) cudaEventRecord(ev[1], h->stream);
     launch_legendre_gemm(false, L.d_probs_syn, L.d_tiles_syn, L.ntiles_syn, h->NHP, h->stream);
     h->launches++;

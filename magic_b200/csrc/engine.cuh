@@ -89,9 +89,10 @@ struct Layout {  // descriptors for one chunk size
     int nf_s = 0, npair_a = 0, Nas = 0, Nav = 0;
     std::vector<long long> offBs, offBv, offCas, offCav;
     long long szBs = 0, szBv = 0, szFs = 0, szFv = 0, szBas = 0, szBav = 0, szCas = 0, szCav = 0;
-    int n_kts = 0, n_ktv = 0, ntiles_syn = 0, ntiles_an = 0;
+    int ntiles_syn = 0, ntiles_an = 0;
     long long *d_offBs = nullptr, *d_offBv = nullptr, *d_offCas = nullptr, *d_offCav = nullptr;
-    KTile *d_kts = nullptr, *d_ktv = nullptr;
+    int2 *d_prep_blks = nullptr;
+    int n_prep_blks = 0;
     GemmProb *d_probs_syn = nullptr, *d_probs_an = nullptr;
     int2 *d_tiles_syn = nullptr, *d_tiles_an = nullptr;
     int *d_colrow_s = nullptr, *d_colrow_v = nullptr;

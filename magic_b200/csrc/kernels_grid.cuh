@@ -11,7 +11,7 @@
 namespace magic {
 
 // index of each synthesised field inside the synthesis grid array (-1 = absent)
-struct GridIn { int vr, vt, vp, cvr, cvt, cvp, s, br, bt, bp, cbr, cbt, cbp, xi, dvrdr, dvtdr, dvpdr, dvrdt, dvrdp, dvtdp, dvpdp; };
+struct GridIn { int vr, vt, vp, cvr, cvt, cvp, s, br, bt, bp, cbr, cbt, cbp, xi, dvrdr, dvtdr, dvpdr, dvrdt, dvrdp, dvtdp, dvpdp; };  // same order as PointIn
 // index of each product inside the product grid array (-1 = absent)
 struct GridOut { int Advr, Advt, Advp, VSr, VSt, VSp, VxBr, VxBt, VxBp, VXir, VXit, VXip, heat; };
 
@@ -151,33 +151,30 @@ __global__ void __launch_bounds__(NL_THREADS, EXTRA ? 1 : 2) get_nl_kernel(NlArg
         const double st = a.sinth[k], ct = a.costh[k];
         const double os2 = 1.0 / (st * st), cn2 = ct / st / st;
         const double phi = (double)j * (6.283185307179586476925286766559 / (double)(a.n_phi * a.minc));
-        PointIn pn, ps;
-        auto ld = [&](int fidx, double &n, double &s) {
-            if (fidx < 0) { n = 0.0; s = 0.0; return; }
-            const double *base = a.gin + (((size_t)fidx * a.n_lev + lev) * 2) * plane + pt;
-            double e = base[0], o = base[plane];
-            n = e + o;
-            s = e - o;
-        };
-        ld(a.gi.vr, pn.vr, ps.vr); ld(a.gi.vt, pn.vt, ps.vt); ld(a.gi.vp, pn.vp, ps.vp);
-        ld(a.gi.cvr, pn.cvr, ps.cvr); ld(a.gi.cvt, pn.cvt, ps.cvt); ld(a.gi.cvp, pn.cvp, ps.cvp);
-        ld(a.gi.s, pn.s, ps.s);
-        if (MAG) {
-            ld(a.gi.br, pn.br, ps.br); ld(a.gi.bt, pn.bt, ps.bt); ld(a.gi.bp, pn.bp, ps.bp);
-            ld(a.gi.cbr, pn.cbr, ps.cbr); ld(a.gi.cbt, pn.cbt, ps.cbt); ld(a.gi.cbp, pn.cbp, ps.cbp);
-        } else {
-            pn.br = ps.br = pn.bt = ps.bt = pn.bp = ps.bp = pn.cbr = ps.cbr = pn.cbt = ps.cbt = pn.cbp = ps.cbp = 0.0;
+        // Phase 1: issue every load of this point pair before the first use (the warp scheduler is in-order, so a
+        // load->use->load sequence would leave only two requests in flight per warp).  Slots follow PointIn.
+        const int *fidx = &a.gi.vr;  // GridIn members are declared in PointIn order
+        double re[21], ro[21];
+#pragma unroll
+        for (int f = 0; f < 21; f++) {
+            const bool used = f < 7 || (f < 13 ? MAG : EXTRA);
+            re[f] = 0.0;
+            ro[f] = 0.0;
+            if (used && fidx[f] >= 0) {
+                const double *base = a.gin + (((size_t)fidx[f] * a.n_lev + lev) * 2) * plane + pt;
+                re[f] = __ldg(base);
+                ro[f] = __ldg(base + plane);
+            }
         }
-        if (EXTRA) {
-            ld(a.gi.xi, pn.xi, ps.xi);
-            ld(a.gi.dvrdr, pn.dvrdr, ps.dvrdr); ld(a.gi.dvtdr, pn.dvtdr, ps.dvtdr); ld(a.gi.dvpdr, pn.dvpdr, ps.dvpdr);
-            ld(a.gi.dvrdt, pn.dvrdt, ps.dvrdt); ld(a.gi.dvrdp, pn.dvrdp, ps.dvrdp);
-            ld(a.gi.dvtdp, pn.dvtdp, ps.dvtdp); ld(a.gi.dvpdp, pn.dvpdp, ps.dvpdp);
-            // torpol_to_dphspat post-scaling by 1/sin^2 (sht_native.f90:263-270)
+        PointIn pn, ps;
+        double *pnv = &pn.vr, *psv = &ps.vr;
+#pragma unroll
+        for (int f = 0; f < 21; f++) {
+            pnv[f] = re[f] + ro[f];
+            psv[f] = re[f] - ro[f];
+        }
+        if (EXTRA) {  // torpol_to_dphspat post-scaling by 1/sin^2 (sht_native.f90:263-270)
             pn.dvtdp *= os2; ps.dvtdp *= os2; pn.dvpdp *= os2; ps.dvpdp *= os2;
-        } else {
-            pn.xi = ps.xi = pn.dvrdr = ps.dvrdr = pn.dvtdr = ps.dvtdr = pn.dvpdr = ps.dvpdr = 0.0;
-            pn.dvrdt = ps.dvrdt = pn.dvrdp = ps.dvrdp = pn.dvtdp = ps.dvtdp = pn.dvpdp = ps.dvpdp = 0.0;
         }
         // boundary overrides of transform_to_grid_space (rIter.f90:555-602)
         if (L.nBc == 1) { pn.vr = 0.0; ps.vr = 0.0; }

@@ -48,9 +48,11 @@ __global__ void build_tables_kernel(double *__restrict__ tab, const long long *_
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Synthesis operand assembly.  One CTA per k-tile (16 rows) of one problem.
-struct KTile { int prob; int kt; int seg; int jt; };  // prob = mc*2+s ; seg 0 = P rows, 1 = D rows ; jt = tile in segment
-
+// Synthesis operand assembly (the pre-scalings of the sht_native.f90 wrappers: l(l+1), or2, i*m, l>lcut masks, and
+// the level masks of rIter.f90:466-622).  One CTA per block of 32 consecutive degrees of one order: lane i owns degree
+// l = m + 32*jt + i, so the spectral reads are 512-byte contiguous per (source, level); even/odd lanes feed the two
+// parity problems, and every degree feeds a P row of its own parity problem and a D row of the other one.
+// Warp w of CTA (x, y) takes level y*8 + w.
 struct SynthPrepArgs {
     const double *src[MAGIC_MAX_SRC];  // complex [n_lev][lm_max]
     const ScalCol *scal;
@@ -59,10 +61,10 @@ struct SynthPrepArgs {
     int Ns, Nv;
     const LevelInfo *lev;
     const int *lstart;  // lm index of degree l=m for each mc
-    int l_max, minc;
+    int l_max, minc, nsrc;
     double *Bs, *Bv;
-    const long long *offBs, *offBv;  // per problem, doubles
-    const KTile *kts, *ktv;
+    const long long *offBs, *offBv;  // per problem (mc*2+s), doubles
+    const int2 *blks;                // (mc, jt)
 };
 
 __device__ __forceinline__ bool level_enabled(int lmask, const LevelInfo &L) {
@@ -72,14 +74,16 @@ __device__ __forceinline__ bool level_enabled(int lmask, const LevelInfo &L) {
     return true;
 }
 
-__device__ __forceinline__ double2 eval_terms(const Term *t, const SynthPrepArgs &a, int lm, int l, int m, int lev,
+constexpr int PREP_WARPS = 8;
+
+__device__ __forceinline__ double2 eval_terms(const Term *t, const double2 *xs /* [src][32] of this warp */, int lane, int l, int m,
                                               double or2) {
     double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         int ft = t[i].ftype;
         if (ft == F_NONE) continue;
-        double2 x = *reinterpret_cast<const double2 *>(a.src[t[i].src] + 2 * ((size_t)lev * a.lm_max + lm));
+        double2 x = xs[t[i].src * 32 + lane];
         double dlh = (double)(l * (l + 1));
         if (ft == F_ONE) { acc.x += x.x; acc.y += x.y; }
         else if (ft == F_DLH) { acc.x += dlh * x.x; acc.y += dlh * x.y; }
@@ -90,54 +94,62 @@ __device__ __forceinline__ double2 eval_terms(const Term *t, const SynthPrepArgs
     return acc;
 }
 
-__global__ void __launch_bounds__(256) synth_prep_scal_kernel(SynthPrepArgs a) {
-    const KTile kt = a.kts[blockIdx.x];
-    const int mc = kt.prob >> 1, s = kt.prob & 1, m = mc * a.minc;
-    double *B = a.Bs + a.offBs[kt.prob] + (size_t)kt.kt * BK * a.Ns;
-    const int ncc = a.ncol_s * a.n_lev;
-    for (int idx = threadIdx.x; idx < BK * (a.Ns / 2); idx += blockDim.x) {
-        int r = idx / (a.Ns / 2), cc = idx - r * (a.Ns / 2);
-        double2 v = make_double2(0.0, 0.0);
-        int l = m + 2 * (kt.jt * BK + r) + s;
-        if (cc < ncc && l <= a.l_max) {
-            int col = cc / a.n_lev, lev = cc - col * a.n_lev;
-            const LevelInfo L = a.lev[lev];
-            const ScalCol sc = a.scal[col];
-            if (l <= L.lcut && level_enabled(sc.lmask, L)) v = eval_terms(sc.t, a, a.lstart[mc] + (l - m), l, m, lev, L.or2);
+__global__ void __launch_bounds__(PREP_WARPS * 32) synth_prep_kernel(SynthPrepArgs a) {
+    extern __shared__ __align__(16) double2 prep_sm[];
+    const int2 blk = a.blks[blockIdx.x];
+    const int mc = blk.x, jt = blk.y, m = mc * a.minc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = m + 32 * jt + lane, par = lane & 1, r = lane >> 1;
+    const bool valid_l = l <= a.l_max;
+    const size_t lm = (size_t)a.lstart[mc] + (l - m);
+    const int ne = (a.l_max - m) / 2 + 1, no = (a.l_max - m + 1) / 2;
+    const int K_par = par == 0 ? ne : no, K_oth = par == 0 ? no : ne;
+    const bool tile_ok = jt < (K_par + BK - 1) / BK;  // the k-tile this degree block maps to exists for my parity
+    const int pP = mc * 2 + par, pD = mc * 2 + (1 - par);
+    const int ktD = (K_oth + BK - 1) / BK + jt;       // D rows of problem pD come after its P rows
+    double2 *xs = prep_sm + (size_t)warp * a.nsrc * 32;
+    double *rowS = a.Bs + (a.ncol_s ? a.offBs[pP] : 0) + (size_t)(jt * BK + r) * a.Ns;
+    double *rowVP = a.Bv + (a.npair_v ? a.offBv[pP] : 0) + (size_t)(jt * BK + r) * a.Nv;
+    double *rowVD = a.Bv + (a.npair_v ? a.offBv[pD] : 0) + (size_t)(ktD * BK + r) * a.Nv;
+    const double dm = (double)m;
+    for (int lev = blockIdx.y * PREP_WARPS + warp; lev < a.n_lev; lev += PREP_WARPS * gridDim.y) {
+        const LevelInfo L = a.lev[lev];
+        // stage all sources of this (level, degree block): loads first, then the shared-memory writes
+        double2 x[MAGIC_MAX_SRC];
+#pragma unroll
+        for (int sidx = 0; sidx < MAGIC_MAX_SRC; sidx++) {
+            x[sidx] = make_double2(0.0, 0.0);
+            if (sidx < a.nsrc && a.src[sidx] != nullptr && valid_l)
+                x[sidx] = *reinterpret_cast<const double2 *>(a.src[sidx] + 2 * ((size_t)lev * a.lm_max + lm));
         }
-        *reinterpret_cast<double2 *>(B + (size_t)r * a.Ns + 2 * cc) = v;
-    }
-}
-
-__global__ void __launch_bounds__(256) synth_prep_vec_kernel(SynthPrepArgs a) {
-    const KTile kt = a.ktv[blockIdx.x];
-    const int mc = kt.prob >> 1, s = kt.prob & 1, m = mc * a.minc;
-    double *B = a.Bv + a.offBv[kt.prob] + (size_t)kt.kt * BK * a.Nv;
-    const int ncc = 2 * a.npair_v * a.n_lev;
-    const int par = kt.seg == 0 ? s : 1 - s;  // P rows carry parity s, D rows the other parity
-    for (int idx = threadIdx.x; idx < BK * (a.Nv / 2); idx += blockDim.x) {
-        int r = idx / (a.Nv / 2), cc = idx - r * (a.Nv / 2);
-        double2 v = make_double2(0.0, 0.0);
-        int l = m + 2 * (kt.jt * BK + r) + par;
-        if (cc < ncc && l <= a.l_max) {
-            int col = cc / a.n_lev, lev = cc - col * a.n_lev;
-            int pair = col >> 1, comp = col & 1;  // comp 0 = theta column, 1 = phi column
-            const LevelInfo L = a.lev[lev];
-            const VecPair vp = a.vec[pair];
-            if (l <= L.lcut && l > 0 && level_enabled(vp.lmask, L)) {
-                int lm = a.lstart[mc] + (l - m);
-                // Vtheta = sum (S D + i m T P), Vphi = sum (i m S P - T D)  (SURVEY.md appendix A)
-                if (kt.seg == 0) {
-                    double2 x = eval_terms(comp == 0 ? vp.T : vp.S, a, lm, l, m, lev, L.or2);
-                    double dm = (double)m;
-                    v = make_double2(-dm * x.y, dm * x.x);
-                } else {
-                    if (comp == 0) v = eval_terms(vp.S, a, lm, l, m, lev, L.or2);
-                    else { double2 x = eval_terms(vp.T, a, lm, l, m, lev, L.or2); v = make_double2(-x.x, -x.y); }
+#pragma unroll
+        for (int sidx = 0; sidx < MAGIC_MAX_SRC; sidx++)
+            if (sidx < a.nsrc) xs[sidx * 32 + lane] = x[sidx];
+        __syncwarp();
+        if (tile_ok) {
+            const bool on = valid_l && l <= L.lcut;
+            for (int c = 0; c < a.ncol_s; c++) {
+                const ScalCol sc = a.scal[c];
+                double2 v = make_double2(0.0, 0.0);
+                if (on && level_enabled(sc.lmask, L)) v = eval_terms(sc.t, xs, lane, l, m, L.or2);
+                *reinterpret_cast<double2 *>(rowS + 2 * ((size_t)c * a.n_lev + lev)) = v;
+            }
+            for (int pr = 0; pr < a.npair_v; pr++) {
+                const VecPair vp = a.vec[pr];
+                double2 S = make_double2(0.0, 0.0), T = S;
+                if (on && l > 0 && level_enabled(vp.lmask, L)) {
+                    S = eval_terms(vp.S, xs, lane, l, m, L.or2);
+                    T = eval_terms(vp.T, xs, lane, l, m, L.or2);
                 }
+                // Vtheta = sum (S D + i m T P), Vphi = sum (i m S P - T D)  (SURVEY.md appendix A)
+                const size_t ct = 2 * ((size_t)(2 * pr) * a.n_lev + lev), cp = 2 * ((size_t)(2 * pr + 1) * a.n_lev + lev);
+                *reinterpret_cast<double2 *>(rowVP + ct) = make_double2(-dm * T.y, dm * T.x);
+                *reinterpret_cast<double2 *>(rowVP + cp) = make_double2(-dm * S.y, dm * S.x);
+                *reinterpret_cast<double2 *>(rowVD + ct) = S;
+                *reinterpret_cast<double2 *>(rowVD + cp) = make_double2(-T.x, -T.y);
             }
         }
-        *reinterpret_cast<double2 *>(B + (size_t)r * a.Nv + 2 * cc) = v;
+        __syncwarp();
     }
 }
 
