@@ -240,7 +240,7 @@ def run_magic(args, gs):
     rad = make_radial(n_r_max, gs["l_max"], nRstart=tr.nRstart, nRstop=tr.nRstop)
     chunk = args.level_chunk
     if chunk == 0 and gs["l_max"] >= 1000:
-        chunk = 16
+        chunk = 32 if world == 1 else 0  # N=1 keeps 86 GB of containers resident next to the workspace
     rl = RadialLoop(sht, p, rad, level_chunk=chunk)
 
     fin = {"w": flow_R[0], "dw": flow_R[1], "ddw": flow_R[2], "z": flow_R[3], "dz": flow_R[4], "s": s_R[0],

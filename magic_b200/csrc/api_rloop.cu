@@ -282,7 +282,7 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
         courant_finish_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(rl->buf.courmax, d_lev, nl, out->dtrkc + l0, out->dthkc + l0);
         h->launches += 2;
         cudaEventRecord(rl->ev[4], h->stream);
-        if (run_analysis(h, rl->spec, L, rl->buf, d_lev, rl->ev + 5)) return 1;  // ev[5..7]
+        if (run_analysis(h, rl->spec, L, rl->buf, d_lev, rl->ev + 5, false)) return 1;  // ev[5..7]; extraction is fused below
         cudaEventRecord(rl->ev[8], h->stream);
         // ---- get_td
         TdArgs t{};
@@ -291,20 +291,34 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
         t.f.l_single_matrix = P.l_single_matrix; t.f.l_chemical_conv = P.l_chemical_conv; t.f.l_anelastic_liquid = P.l_anelastic_liquid;
         t.f.CorFac = P.CorFac; t.f.epsc = P.epsc; t.f.epscXi = P.epscXi;
         t.n_lev = nl; t.lm_max = h->lm_max; t.l_max = h->l_max; t.minc = h->minc; t.lm2l = h->d_lm2l; t.lm2m = h->d_lm2m; t.lev = d_lev;
-        const size_t fs = (size_t)nl * lm2;  // one extracted field
-        auto ns = [&](int slot) -> const double * { return slot < 0 ? nullptr : rl->buf.nl_s + (size_t)slot * fs; };
-        auto nv = [&](int pair, int comp) -> const double * { return pair < 0 ? nullptr : rl->buf.nl_v + (size_t)(2 * pair + comp) * fs; };
-        t.AdvrLM = ns(rl->a_Advr); t.AdvtLM = nv(rl->a_Adv, 0); t.AdvpLM = nv(rl->a_Adv, 1);
-        t.VxBrLM = ns(rl->a_VxBr); t.VxBtLM = nv(rl->a_VxB, 0); t.VxBpLM = nv(rl->a_VxB, 1);
-        t.VSrLM = ns(rl->a_VSr); t.VStLM = nv(rl->a_VS, 0);
-        t.VXirLM = ns(rl->a_VXir); t.VXitLM = nv(rl->a_VXi, 0);
-        t.heatLM = ns(rl->a_heat);
+        // tile slots of the nonlinear_lm_t members inside the fused kernel: scalar-class columns first, then vector columns
+        const int nfs = (int)rl->spec.afield_s.size();
+        auto ns = [&](int slot) { return slot; };
+        auto nv = [&](int pair, int comp) { return pair < 0 ? -1 : nfs + 2 * pair + comp; };
+        TdSlots sl;
+        sl.s[0] = ns(rl->a_Advr); sl.s[1] = nv(rl->a_Adv, 0); sl.s[2] = nv(rl->a_Adv, 1);
+        sl.s[3] = ns(rl->a_VxBr); sl.s[4] = nv(rl->a_VxB, 0); sl.s[5] = nv(rl->a_VxB, 1);
+        sl.s[6] = nv(rl->a_VS, 0); sl.s[7] = ns(rl->a_VSr);
+        sl.s[8] = nv(rl->a_VXi, 0); sl.s[9] = ns(rl->a_VXir);
+        sl.s[10] = ns(rl->a_heat);
         t.w = src[S_W]; t.dw = src[S_DW]; t.ddw = src[S_DDW]; t.z = src[S_Z]; t.dz = src[S_DZ];
         auto o = [&](int i) -> double * { return op[i] ? op[i] + (size_t)l0 * lm2 : nullptr; };
         t.dwdt = o(O_DWDT); t.dzdt = o(O_DZDT); t.dpdt = o(O_DPDT); t.dsdt = o(O_DSDT); t.dxidt = o(O_DXIDT); t.dbdt = o(O_DBDT);
         t.djdt = o(O_DJDT); t.dVxVhLM = o(O_DVXVH); t.dVxBhLM = o(O_DVXBH); t.dVSrLM = o(O_DVSR); t.dVXirLM = o(O_DVXIR);
-        get_td_kernel<<<dim3((h->lm_max + 255) / 256, nl), 256, 0, h->stream>>>(t);
-        h->launches++;
+        {
+            ExtractArgs e{};
+            e.Cs = rl->buf.Cas; e.Cv = rl->buf.Cav; e.offCs = L.d_offCas; e.offCv = L.d_offCav; e.Ns = L.Nas; e.Nv = L.Nav;
+            e.n_lev = nl; e.lm_max = h->lm_max; e.nf_s = L.nf_s; e.nf_v = 2 * L.npair_a; e.lm2l = h->d_lm2l; e.lm2m = h->d_lm2m;
+            e.minc = h->minc; e.lev = d_lev; e.out_s = nullptr; e.out_v = nullptr;
+            const int nf = e.nf_s + e.nf_v;
+            // widest tile whose shared-memory footprint still lets several CTAs share an SM
+            auto smem = [&](int tl) { return (size_t)nf * nl * (tl + 1) * sizeof(double2); };
+            if (smem(32) <= 80 * 1024) extract_td_kernel<32><<<(h->lm_max + 31) / 32, 256, smem(32), h->stream>>>(e, t, sl);
+            else if (smem(16) <= 80 * 1024) extract_td_kernel<16><<<(h->lm_max + 15) / 16, 256, smem(16), h->stream>>>(e, t, sl);
+            else if (smem(8) <= 200 * 1024) extract_td_kernel<8><<<(h->lm_max + 7) / 8, 256, smem(8), h->stream>>>(e, t, sl);
+            else MFAIL("magic_rloop: level chunk too large for the fused get_td tile; lower level_chunk");
+            h->launches++;
+        }
         cudaEventRecord(rl->ev[9], h->stream);
         MCHECK(cudaGetLastError());
         if (rl->chunk_start.size() > 1 || true) {

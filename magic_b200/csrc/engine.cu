@@ -109,6 +109,9 @@ int sht_init(magic_sht *h) {
     if (dev_upload_vec(&h->d_tw, tw)) return 1;
     h->fft.tw = h->d_tw;
     MCHECK(gemm_setup_attributes());
+    MCHECK(cudaFuncSetAttribute(extract_td_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MCHECK(cudaFuncSetAttribute(extract_td_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MCHECK(cudaFuncSetAttribute(extract_td_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MCHECK(cudaFuncSetAttribute(synth_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_WARPS * MAGIC_MAX_SRC * 32 * (int)sizeof(double2)));
     MCHECK(fft_setup_attributes(h->fft.H));
     MCHECK(cudaStreamSynchronize(h->stream));
@@ -340,7 +343,8 @@ int run_synthesis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Bu
     return 0;
 }
 
-int run_analysis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buffers &buf, const LevelInfo *d_lev, cudaEvent_t *ev) {
+int run_analysis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buffers &buf, const LevelInfo *d_lev, cudaEvent_t *ev,
+                 bool extract) {
     if (spec.nfield_out == 0) return 0;
     R2cArgs a{};
     a.grid = buf.gout; a.n_lev = L.n_lev; a.nh = h->nh; a.n_m = h->n_m; a.NHP = h->NHP;
@@ -353,6 +357,7 @@ int run_analysis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buf
     launch_legendre_gemm(true, L.d_probs_an, L.d_tiles_an, L.ntiles_an, h->NHP, h->stream);
     h->launches++;
     if (ev) cudaEventRecord(ev[2], h->stream);
+    if (!extract) { MCHECK(cudaGetLastError()); return 0; }
     ExtractArgs e{};
     e.Cs = buf.Cas; e.Cv = buf.Cav; e.offCs = L.d_offCas; e.offCv = L.d_offCav; e.Ns = L.Nas; e.Nv = L.Nav;
     e.n_lev = L.n_lev; e.lm_max = h->lm_max; e.nf_s = L.nf_s; e.nf_v = 2 * L.npair_a; e.lm2l = h->d_lm2l; e.lm2m = h->d_lm2m;

@@ -114,7 +114,8 @@ void buffers_free(Buffers &buf);
 // (start, after FFT, after Legendre).
 int run_synthesis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buffers &buf, const double *const src[MAGIC_MAX_SRC],
                   const LevelInfo *d_lev, cudaEvent_t *ev);
-int run_analysis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buffers &buf, const LevelInfo *d_lev, cudaEvent_t *ev);
+int run_analysis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buffers &buf, const LevelInfo *d_lev, cudaEvent_t *ev,
+                 bool extract = true);
 int sht_init(magic_sht *h);
 void sht_free(magic_sht *h);
 

@@ -218,10 +218,9 @@ __device__ __forceinline__ double2 c_add(double2 a, double2 b) { return make_dou
 __device__ __forceinline__ double2 c_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 c_im(double m, double2 a) { return make_double2(-m * a.y, m * a.x); }  // i*m*a
 
-__global__ void __launch_bounds__(256) get_td_kernel(TdArgs a) {
-    int lm = blockIdx.x * blockDim.x + threadIdx.x;
-    int lev = blockIdx.y;
-    if (lm >= a.lm_max) return;
+// inl = index of this (lm, level) inside the nonlinear_lm_t arrays (== i when they live in global memory in the
+// [lev][lm] layout, a shared-memory tile index in the fused kernel)
+__device__ __forceinline__ void td_compute(const TdArgs &a, int lm, int lev, size_t inl) {
     const LevelInfo L = a.lev[lev];
     const int l = a.lm2l[lm], m = a.lm2m[lm];
     const size_t i = (size_t)lev * a.lm_max + lm;
@@ -249,7 +248,7 @@ __global__ void __launch_bounds__(256) get_td_kernel(TdArgs a) {
                 v = zero;
                 if (F.l_corr) v = c_scale(2.0 * F.CorFac * L.or2, c_add(c_scale(dTheta3A, ldc(a.dw, iA)), c_scale(L.or1 * dTheta4A, ldc(a.w, iA))));
             } else {
-                v = F.l_conv_nl ? c_scale(dLh, ldc(a.AdvpLM, i)) : zero;
+                v = F.l_conv_nl ? c_scale(dLh, ldc(a.AdvpLM, inl)) : zero;
                 if (F.l_corr) {
                     double2 cor = zero;
                     if (l < L.lcut) {
@@ -275,13 +274,13 @@ __global__ void __launch_bounds__(256) get_td_kernel(TdArgs a) {
             if (bulk) {
                 double2 v, vh = zero;
                 if (lm == 0) {
-                    v = F.l_conv_nl ? c_scale(L.or2, ldc(a.AdvrLM, i)) : zero;
+                    v = F.l_conv_nl ? c_scale(L.or2, ldc(a.AdvrLM, inl)) : zero;
                     if (F.l_corr && !F.l_single_matrix) v = c_add(v, c_scale(2.0 * F.CorFac * L.or1 * dTheta2A, ldc(a.z, iA)));
                     stc(a.dwdt, i, v);
                 } else {
                     if (F.l_conv_nl) {
-                        v = c_scale(dLh * L.or4 * L.orho1, ldc(a.AdvrLM, i));
-                        vh = c_scale(-L.orho1 * L.r * L.r * dLh, ldc(a.AdvtLM, i));
+                        v = c_scale(dLh * L.or4 * L.orho1, ldc(a.AdvrLM, inl));
+                        vh = c_scale(-L.orho1 * L.r * L.r * dLh, ldc(a.AdvtLM, inl));
                     } else v = zero;
                     if (F.l_corr) {
                         double2 cor = zero;
@@ -309,7 +308,7 @@ __global__ void __launch_bounds__(256) get_td_kernel(TdArgs a) {
             }
         } else if (bulk) {
             // get_dwdt (get_td.f90:133-197)
-            double2 v = F.l_conv_nl ? c_scale(L.or2, ldc(a.AdvrLM, i)) : zero;
+            double2 v = F.l_conv_nl ? c_scale(L.or2, ldc(a.AdvrLM, inl)) : zero;
             if (lm == 0) {
                 if (F.l_corr && !F.l_single_matrix) v = c_add(v, c_scale(2.0 * F.CorFac * L.or1 * dTheta2A, ldc(a.z, iA)));
             } else if (F.l_corr) {
@@ -330,7 +329,7 @@ __global__ void __launch_bounds__(256) get_td_kernel(TdArgs a) {
     }
     if (!F.l_double_curl && bulk && lm > 0) {
         // get_dpdt (get_td.f90:311-374); lm=0 is never written by the reference
-        double2 v = F.l_conv_nl ? c_scale(-dLh, ldc(a.AdvtLM, i)) : zero;
+        double2 v = F.l_conv_nl ? c_scale(-dLh, ldc(a.AdvtLM, inl)) : zero;
         if (F.l_corr) {
             double2 cor = zero;
             if (l <= L.lcut) {
@@ -350,35 +349,80 @@ __global__ void __launch_bounds__(256) get_td_kernel(TdArgs a) {
             double2 v;
             if (lm == 0) {
                 v = make_double2(F.epsc * L.epscProf, 0.0);
-                if (F.l_anel) v = c_add(v, F.l_anelastic_liquid ? c_scale(L.temp0, ldc(a.heatLM, i)) : ldc(a.heatLM, i));
+                if (F.l_anel) v = c_add(v, F.l_anelastic_liquid ? c_scale(L.temp0, ldc(a.heatLM, inl)) : ldc(a.heatLM, inl));
             } else {
-                v = c_scale(dLh, ldc(a.VStLM, i));
-                if (F.l_anel) v = c_add(v, F.l_anelastic_liquid ? c_scale(L.temp0, ldc(a.heatLM, i)) : ldc(a.heatLM, i));
+                v = c_scale(dLh, ldc(a.VStLM, inl));
+                if (F.l_anel) v = c_add(v, F.l_anelastic_liquid ? c_scale(L.temp0, ldc(a.heatLM, inl)) : ldc(a.heatLM, inl));
             }
             stc(a.dsdt, i, v);
         }
-        stc(a.dVSrLM, i, (bulk && !L.l_bound) ? ldc(a.VSrLM, i) : zero);
+        stc(a.dVSrLM, i, (bulk && !L.l_bound) ? ldc(a.VSrLM, inl) : zero);
     }
     if (F.l_chemical_conv) {
-        if (bulk) stc(a.dxidt, i, lm == 0 ? make_double2(F.epscXi, 0.0) : c_scale(dLh, ldc(a.VXitLM, i)));
-        stc(a.dVXirLM, i, (bulk && !L.l_bound) ? ldc(a.VXirLM, i) : zero);
+        if (bulk) stc(a.dxidt, i, lm == 0 ? make_double2(F.epscXi, 0.0) : c_scale(dLh, ldc(a.VXitLM, inl)));
+        stc(a.dVXirLM, i, (bulk && !L.l_bound) ? ldc(a.VXirLM, inl) : zero);
     }
     if (F.l_mag) {
         // get_dbdt (get_td.f90:557-619)
         if (bulk) {
             if (F.l_mag_nl || F.l_mag_kin) {
-                stc(a.dbdt, i, c_scale(dLh, ldc(a.VxBpLM, i)));
-                stc(a.dVxBhLM, i, c_scale(-dLh * L.r * L.r, ldc(a.VxBtLM, i)));
-                stc(a.djdt, i, c_scale(dLh * L.or4, ldc(a.VxBrLM, i)));
+                stc(a.dbdt, i, c_scale(dLh, ldc(a.VxBpLM, inl)));
+                stc(a.dVxBhLM, i, c_scale(-dLh * L.r * L.r, ldc(a.VxBtLM, inl)));
+                stc(a.djdt, i, c_scale(dLh * L.or4, ldc(a.VxBrLM, inl)));
             } else {
                 stc(a.dbdt, i, zero);
                 stc(a.djdt, i, zero);
                 stc(a.dVxBhLM, i, zero);
             }
         } else {
-            if ((F.l_mag_nl || F.l_mag_kin) && lm > 0) stc(a.dVxBhLM, i, c_scale(-dLh * L.r * L.r, ldc(a.VxBtLM, i)));
+            if ((F.l_mag_nl || F.l_mag_kin) && lm > 0) stc(a.dVxBhLM, i, c_scale(-dLh * L.r * L.r, ldc(a.VxBtLM, inl)));
             else stc(a.dVxBhLM, i, zero);
         }
+    }
+}
+
+__global__ void __launch_bounds__(256) get_td_kernel(TdArgs a) {
+    int lm = blockIdx.x * blockDim.x + threadIdx.x;
+    int lev = blockIdx.y;
+    if (lm >= a.lm_max) return;
+    td_compute(a, lm, lev, (size_t)lev * a.lm_max + lm);
+}
+
+// Fused extraction + get_td: a CTA owns TL consecutive (l,m) modes and all levels of the chunk.  Phase 1 reads the
+// analysis GEMM results with the level index fastest (contiguous in the C matrices) into a shared-memory tile; phase 2
+// runs get_td with the mode index fastest (contiguous in the spectral inputs/outputs).  The nonlinear_lm_t arrays never
+// touch HBM.
+struct TdSlots { int s[11]; };  // tile slot of AdvrLM,AdvtLM,AdvpLM,VxBrLM,VxBtLM,VxBpLM,VStLM,VSrLM,VXitLM,VXirLM,heatLM (-1 absent)
+
+template <int TL>
+__global__ void __launch_bounds__(256) extract_td_kernel(ExtractArgs e, TdArgs t, TdSlots slots) {
+    extern __shared__ __align__(16) double2 td_sm[];
+    constexpr int TLP = TL + 1;
+    const int lm0 = blockIdx.x * TL, n_lev = e.n_lev, nf = e.nf_s + e.nf_v;
+    for (int idx = threadIdx.x; idx < nf * TL * n_lev; idx += blockDim.x) {
+        int lev = idx % n_lev, t2 = idx / n_lev, ll = t2 % TL, f = t2 / TL, lm = lm0 + ll;
+        double2 v = make_double2(0.0, 0.0);
+        if (lm < e.lm_max) {
+            const int l = e.lm2l[lm], m = e.lm2m[lm], mc = m / e.minc, p = (l - m) & 1, j = (l - m) >> 1;
+            if (l <= e.lev[lev].lcut) {
+                if (f < e.nf_s) {
+                    v = *reinterpret_cast<const double2 *>(e.Cs + e.offCs[mc * 2 + p] + (size_t)j * e.Ns + 2 * ((size_t)f * n_lev + lev));
+                } else {
+                    v = *reinterpret_cast<const double2 *>(e.Cv + e.offCv[mc * 2 + p] + (size_t)j * e.Nv + 2 * ((size_t)(f - e.nf_s) * n_lev + lev));
+                    if (lm > 0) { const double ll1 = (double)(l * (l + 1)); v.x = v.x / ll1; v.y = v.y / ll1; }
+                }
+            }
+        }
+        td_sm[((size_t)f * n_lev + lev) * TLP + ll] = v;
+    }
+    __syncthreads();
+    const double *base = reinterpret_cast<const double *>(td_sm);
+    const double **ptrs[11] = {&t.AdvrLM, &t.AdvtLM, &t.AdvpLM, &t.VxBrLM, &t.VxBtLM, &t.VxBpLM, &t.VStLM, &t.VSrLM, &t.VXitLM, &t.VXirLM, &t.heatLM};
+#pragma unroll
+    for (int q = 0; q < 11; q++) *ptrs[q] = slots.s[q] < 0 ? nullptr : base + 2 * (size_t)slots.s[q] * n_lev * TLP;
+    for (int idx = threadIdx.x; idx < TL * n_lev; idx += blockDim.x) {
+        int ll = idx % TL, lev = idx / TL, lm = lm0 + ll;
+        if (lm < e.lm_max) td_compute(t, lm, lev, (size_t)lev * TLP + ll);
     }
 }
 
