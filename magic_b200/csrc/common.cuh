@@ -28,6 +28,8 @@ struct GemmProb {
     int M;         // valid rows of C
     int ldb, ldc;  // leading dimensions of B and C (doubles)
     int Nvalid;    // real (unpadded) column count: DMMA fragments beyond it are skipped
+    int Mlo;       // synthesis: rows (colatitudes) below Mlo hold only negligible table entries and are skipped
+    int klo;       // analysis: leading k-tiles of each segment skipped for the same reason (B rows shift accordingly)
 };
 
 // factor applied to a spectral source when assembling synthesis operands (sht_native.f90 wrappers)

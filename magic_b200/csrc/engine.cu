@@ -97,6 +97,18 @@ int sht_init(magic_sht *h) {
         build_tables_kernel<<<grid, 128, 0, h->stream>>>(h->d_tab, h->d_off, h->d_sinth, h->d_costh, d_pmm, nh, h->NHP, l_max, minc, n_m);
         MCHECK(cudaGetLastError());
     }
+    // polar skipping threshold: MAGIC_POLAR_EPS=0 disables it
+    if (const char *e = getenv("MAGIC_POLAR_EPS")) h->polar_eps = atof(e);
+    h->kmin.assign(n_m, 0);
+    if (h->polar_eps > 0.0) {
+        int *d_kmin = nullptr;
+        MCHECK(cudaMalloc((void **)&d_kmin, sizeof(int) * n_m));
+        table_kmin_kernel<<<n_m, 256, 0, h->stream>>>(h->d_tab, h->d_off, nh, h->NHP, l_max, minc, h->polar_eps, d_kmin);
+        MCHECK(cudaGetLastError());
+        MCHECK(cudaMemcpyAsync(h->kmin.data(), d_kmin, sizeof(int) * n_m, cudaMemcpyDeviceToHost, h->stream));
+        MCHECK(cudaStreamSynchronize(h->stream));
+        cudaFree(d_kmin);
+    }
     // FFT plan
     h->fft.N = h->n_phi;
     h->fft.H = h->n_phi / 2;
@@ -208,6 +220,7 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
                 GemmProb g{};
                 g.A0 = s == 0 ? Pe : Po;
                 g.M = nh;
+                g.Mlo = (h->kmin[mc] / 8) * 8;
                 if (cls == 1) {
                     g.A1 = s == 0 ? Do : De;
                     g.kt0 = kt0; g.kt1 = kt1;
@@ -226,7 +239,7 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
                 int pid = (int)ps.size();
                 ps.push_back(g);
                 int ntn = g.ldb / GEMM_BN;
-                for (int mt = 0; mt < mt_syn; mt++)
+                for (int mt = 0; mt < mt_syn; mt++)  // tiles entirely below Mlo only store zeros (kernel early-out)
                     for (int nt = 0; nt < ntn; nt++) ts.push_back(make_int2(pid, (mt << 16) | nt));
                 L.flops_syn += 2.0 * nh * (double)(g.kt0 + g.kt1) * BK * g.ldb;
             }
@@ -242,9 +255,12 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
                 g.A0 = p == 0 ? Pe : Po;
                 g.A1 = p == 0 ? De : Do;
                 g.M = Kp;
-                g.kt0 = NHP / BK;
+                g.klo = h->kmin[mc] / BK;
+                g.A0 += (size_t)g.klo * BK;
+                g.A1 += (size_t)g.klo * BK;
+                g.kt0 = NHP / BK - g.klo;
                 if (cls == 1) {
-                    g.kt1 = NHP / BK;
+                    g.kt1 = NHP / BK - g.klo;
                     g.B = buf.Bav + (size_t)prob * 2 * NHP * L.Nav;
                     g.C = buf.Cav + L.offCav[prob];
                     g.ldb = g.ldc = L.Nav;

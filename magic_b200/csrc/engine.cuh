@@ -51,6 +51,8 @@ struct magic_sht {
     std::vector<double> theta_ord, gauss;          // gauleg output (monotone north->south)
     std::vector<int> lm2l, lm2m, lstart, ne, no;   // st_map; per-mc first lm and even/odd degree counts
     std::vector<long long> off;                    // [n_m][4] table block offsets: Pe, Do, Po, De
+    std::vector<int> kmin;                         // per mc: first colatitude with non-negligible table entries
+    double polar_eps = 1e-40;
     double *d_tab = nullptr;
     long long *d_off = nullptr;
     double *d_sinth = nullptr, *d_costh = nullptr, *d_wgauss = nullptr, *d_osin2 = nullptr;

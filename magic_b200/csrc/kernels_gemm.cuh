@@ -59,7 +59,17 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
     // valid 8-row / 8-column fragments of this warp (ragged M of the analysis, padded N): the rest is skipped
     const int mfr = min(4, max(0, (pr.M - m0 - wm + 7) >> 3)), nfr = min(4, max(0, (pr.Nvalid - n0 - wn + 7) >> 3));
-    const bool active = mfr > 0 && nfr > 0;
+    const int mlo = min(4, max(0, (pr.Mlo - m0 - wm) >> 3));  // polar skipping: fragments [0, mlo) are all-negligible rows
+    const bool active = mfr > mlo && nfr > 0;
+
+    if (!A_KCONTIG && m0 + GEMM_BM <= pr.Mlo) {
+        // whole tile lies in the negligible polar cap: its rows of F are exact zeros
+        for (int idx = tid; idx < GEMM_BM * (GEMM_BN / 2); idx += G_THREADS) {
+            int row = m0 + idx / (GEMM_BN / 2), c2 = idx % (GEMM_BN / 2);
+            if (row < pr.M) *reinterpret_cast<double2 *>(pr.C + (size_t)row * pr.ldc + n0 + 2 * c2) = make_double2(0.0, 0.0);
+        }
+        return;
+    }
 
     auto load_stage = [&](int kt, int st) {
         double *As = smem + st * STAGE, *Bs = As + A_TILE;
@@ -78,7 +88,8 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
                 cp_async16(As + m * LDA_K + kc * 2, Ab + (size_t)(m0 + m) * lda + kc * 2);
             }
         }
-        const double *Bb = pr.B + (size_t)kt * BK * pr.ldb + n0;
+        const int kb = kt < pr.kt0 ? kt + pr.klo : kt + 2 * pr.klo;  // B row tile (skipped leading tiles of each segment)
+        const double *Bb = pr.B + (size_t)kb * BK * pr.ldb + n0;
 #pragma unroll
         for (int c = 0; c < 2; c++) {  // 16 rows x 32 chunks
             int idx = tid + c * G_THREADS, k = idx >> 5, nc = idx & 31;
@@ -117,7 +128,7 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) b[j] = Bs[(kk * 4 + t) * LDB_S + wn + j * 8 + g];
-                if (mfr == 4 && nfr == 4) {
+                if (mfr == 4 && nfr == 4 && mlo == 0) {
 #pragma unroll
                     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -127,7 +138,7 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
                     for (int i = 0; i < 4; i++)
 #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            if (i < mfr && j < nfr) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                            if (i >= mlo && i < mfr && j < nfr) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                 }
             }
         }

@@ -47,6 +47,27 @@ __global__ void build_tables_kernel(double *__restrict__ tab, const long long *_
     }
 }
 
+// First colatitude index k (north pole = 0) at which any P or D entry of order mc reaches `thr` in magnitude.
+// Rows below it contribute less than thr * |coefficient| to any sum -- with thr = 1e-40 that is 24 orders of magnitude
+// below FP64 rounding of the result -- and are skipped by the Legendre GEMMs ("polar optimisation", cf. the
+// eps_polar of shtns.f90:59, here with a threshold that cannot change a single result bit that matters).
+__global__ void table_kmin_kernel(const double *__restrict__ tab, const long long *__restrict__ off, int nh, int NHP, int l_max,
+                                  int minc, double thr, int *__restrict__ kmin) {
+    __shared__ int best;
+    const int mc = blockIdx.x, m = mc * minc;
+    if (threadIdx.x == 0) best = nh;
+    __syncthreads();
+    const long long rows = 2LL * (l_max - m + 1);  // the four blocks of this order are contiguous
+    const double *base = tab + off[mc * 4];
+    for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+        bool hit = false;
+        for (long long r = 0; r < rows && !hit; r++) hit = fabs(base[r * NHP + k]) >= thr;
+        if (hit) atomicMin(&best, k);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) kmin[mc] = best;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Synthesis operand assembly (the pre-scalings of the sht_native.f90 wrappers: l(l+1), or2, i*m, l>lcut masks, and
 // the level masks of rIter.f90:466-622).  One CTA per block of 32 consecutive degrees of one order: lane i owns degree
