@@ -38,7 +38,14 @@ struct magic_rloop {
     double timing[8] = {0};
     std::vector<float> acc;
     double legendre_flops = 0;
-    std::vector<const void *> registered;
+    std::vector<const void *> registered, seen;
+    // host-pointer path: uploads / downloads of level chunks overlap the compute of neighbouring chunks
+    cudaStream_t s_up = nullptr, s_down = nullptr;
+    std::vector<cudaEvent_t> up_done, comp_done;
+    const double *host_in[S_COUNT] = {nullptr};
+    double *host_out[O_COUNT] = {nullptr};
+    double *host_dtrkc = nullptr, *host_dthkc = nullptr;  // pinned staging (a D2H copy into pageable memory would block the host)
+    bool pipelined = false;
 };
 
 static void add_scal(BatchSpec &s, Term t0, Term t1, int lmask, int &field_counter, int &slot) {
@@ -68,6 +75,12 @@ extern "C" int magic_rloop_destroy(magic_rloop *rl) {
     for (int i = 0; i < O_COUNT; i++) cudaFree(rl->d_out[i]);
     cudaFree(rl->d_dtrkc); cudaFree(rl->d_dthkc); cudaFree(rl->d_lev);
     for (int i = 0; i < 16; i++) cudaEventDestroy(rl->ev[i]);
+    for (auto e : rl->up_done) cudaEventDestroy(e);
+    for (auto e : rl->comp_done) cudaEventDestroy(e);
+    if (rl->host_dtrkc) cudaFreeHost(rl->host_dtrkc);
+    if (rl->host_dthkc) cudaFreeHost(rl->host_dthkc);
+    if (rl->s_up) cudaStreamDestroy(rl->s_up);
+    if (rl->s_down) cudaStreamDestroy(rl->s_down);
     delete rl;
     return 0;
 }
@@ -217,6 +230,16 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
         layout_sizes(h, S, rl->lay_size[1], rl->lay[1]);
         if (layout_bind(h, S, rl->lay[1], rl->buf)) { magic_rloop_destroy(rl); return 1; }
     }
+    MCHECK(cudaStreamCreateWithFlags(&rl->s_up, cudaStreamNonBlocking));
+    MCHECK(cudaStreamCreateWithFlags(&rl->s_down, cudaStreamNonBlocking));
+    rl->up_done.resize(nchunks);
+    rl->comp_done.resize(nchunks);
+    for (int c = 0; c < nchunks; c++) {
+        MCHECK(cudaEventCreateWithFlags(&rl->up_done[c], cudaEventDisableTiming));
+        MCHECK(cudaEventCreateWithFlags(&rl->comp_done[c], cudaEventDisableTiming));
+    }
+    MCHECK(cudaMallocHost((void **)&rl->host_dtrkc, sizeof(double) * n_r_loc));
+    MCHECK(cudaMallocHost((void **)&rl->host_dthkc, sizeof(double) * n_r_loc));
     MCHECK(cudaMalloc((void **)&rl->d_dtrkc, sizeof(double) * n_r_loc));
     MCHECK(cudaMalloc((void **)&rl->d_dthkc, sizeof(double) * n_r_loc));
     *out = rl;
@@ -261,6 +284,7 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
         const LevelInfo *d_lev = rl->d_lev + l0;
         const double *src[MAGIC_MAX_SRC];
         for (int i = 0; i < MAGIC_MAX_SRC; i++) src[i] = (i < S_COUNT && ip[i]) ? ip[i] + (size_t)l0 * lm2 : nullptr;
+        if (rl->pipelined) MCHECK(cudaStreamWaitEvent(h->stream, rl->up_done[c], 0));
         if (run_synthesis(h, rl->spec, L, rl->buf, src, d_lev, rl->ev)) return 1;
         // ---- get_nl + Courant
         MCHECK(cudaMemsetAsync(rl->buf.courmax, 0, sizeof(unsigned long long) * 2 * nl, h->stream));
@@ -321,6 +345,15 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
         }
         cudaEventRecord(rl->ev[9], h->stream);
         MCHECK(cudaGetLastError());
+        if (rl->pipelined) {  // results of this chunk go home while the next chunk computes
+            MCHECK(cudaEventRecord(rl->comp_done[c], h->stream));
+            MCHECK(cudaStreamWaitEvent(rl->s_down, rl->comp_done[c], 0));
+            const size_t off = (size_t)l0 * lm2, bytes = sizeof(double) * (size_t)nl * lm2;
+            for (int i = 0; i < O_COUNT; i++)
+                if (rl->need_out[i]) MCHECK(cudaMemcpyAsync(rl->host_out[i] + off, op[i] + off, bytes, cudaMemcpyDeviceToHost, rl->s_down));
+            MCHECK(cudaMemcpyAsync(rl->host_dtrkc + l0, out->dtrkc + l0, sizeof(double) * nl, cudaMemcpyDeviceToHost, rl->s_down));
+            MCHECK(cudaMemcpyAsync(rl->host_dthkc + l0, out->dthkc + l0, sizeof(double) * nl, cudaMemcpyDeviceToHost, rl->s_down));
+        }
         if (rl->chunk_start.size() > 1 || true) {
             // per-stage device times of this chunk (the sync also bounds the number of in-flight chunks)
             MCHECK(cudaEventSynchronize(rl->ev[9]));
@@ -342,11 +375,15 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
 }
 
 static void try_register(magic_rloop *rl, const void *p, size_t bytes) {
-    if (!p) return;
-    for (const void *q : rl->registered)
-        if (q == p) return;
+    if (!p || bytes < (size_t)8 << 20) return;  // small arrays: staged (pageable) copies are cheaper than pinning
+    for (const void *q : rl->seen)
+        if (q == p) return;  // tried before (registered, or already pinned by the caller)
+    rl->seen.push_back(p);
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return;  // already pinned
+    cudaGetLastError();
     if (cudaHostRegister((void *)p, bytes, cudaHostRegisterDefault) == cudaSuccess) rl->registered.push_back(p);
-    else cudaGetLastError();  // already pinned or not registrable: plain pageable copies still work
+    else cudaGetLastError();  // not registrable: plain pageable copies still work
 }
 
 extern "C" int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const magic_fields_out *out, double time) {
@@ -361,13 +398,21 @@ extern "C" int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const
     magic_fields_in din{};
     magic_fields_out dout{};
     const double *dip[S_COUNT] = {nullptr};
+    const size_t lm2 = 2 * (size_t)h->lm_max;
     for (int i = 0; i < S_COUNT; i++) {
         if (!rl->need_in[i]) continue;
         if (!ip[i]) MFAIL("magic_rloop_run: a required input field is null");
         if (!rl->d_in[i]) MCHECK(cudaMalloc((void **)&rl->d_in[i], fbytes));
         try_register(rl, ip[i], fbytes);
-        MCHECK(cudaMemcpyAsync(rl->d_in[i], ip[i], fbytes, cudaMemcpyHostToDevice, h->stream));
+        rl->host_in[i] = ip[i];
         dip[i] = rl->d_in[i];
+    }
+    // all uploads are queued now, chunk by chunk, on their own stream; the compute stream waits per chunk
+    for (size_t c = 0; c < rl->chunk_start.size(); c++) {
+        const size_t off = (size_t)rl->chunk_start[c] * lm2, bytes = sizeof(double) * (size_t)rl->chunk_size[c] * lm2;
+        for (int i = 0; i < S_COUNT; i++)
+            if (rl->need_in[i]) MCHECK(cudaMemcpyAsync(rl->d_in[i] + off, ip[i] + off, bytes, cudaMemcpyHostToDevice, rl->s_up));
+        MCHECK(cudaEventRecord(rl->up_done[c], rl->s_up));
     }
     din.w = dip[S_W]; din.dw = dip[S_DW]; din.ddw = dip[S_DDW]; din.z = dip[S_Z]; din.dz = dip[S_DZ]; din.s = dip[S_S]; din.ds = dip[S_DS];
     din.p = dip[S_P]; din.xi = dip[S_XI]; din.b = dip[S_B]; din.db = dip[S_DB]; din.ddb = dip[S_DDB]; din.aj = dip[S_AJ]; din.dj = dip[S_DJ];
@@ -380,18 +425,21 @@ extern "C" int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const
             MCHECK(cudaMemsetAsync(rl->d_out[i], 0, fbytes, h->stream));
         }
         try_register(rl, op[i], fbytes);
+        rl->host_out[i] = op[i];
         dop[i] = rl->d_out[i];
     }
     dout.dwdt = dop[O_DWDT]; dout.dzdt = dop[O_DZDT]; dout.dpdt = dop[O_DPDT]; dout.dsdt = dop[O_DSDT]; dout.dxidt = dop[O_DXIDT];
     dout.dbdt = dop[O_DBDT]; dout.djdt = dop[O_DJDT]; dout.dVxVhLM = dop[O_DVXVH]; dout.dVxBhLM = dop[O_DVXBH];
     dout.dVSrLM = dop[O_DVSR]; dout.dVXirLM = dop[O_DVXIR];
     dout.dtrkc = rl->d_dtrkc; dout.dthkc = rl->d_dthkc;
-    if (magic_rloop_run_dev(rl, &din, &dout, time)) return 1;
-    for (int i = 0; i < O_COUNT; i++)
-        if (rl->need_out[i]) MCHECK(cudaMemcpyAsync(op[i], rl->d_out[i], fbytes, cudaMemcpyDeviceToHost, h->stream));
-    MCHECK(cudaMemcpyAsync(out->dtrkc, rl->d_dtrkc, sizeof(double) * rl->n_r_loc, cudaMemcpyDeviceToHost, h->stream));
-    MCHECK(cudaMemcpyAsync(out->dthkc, rl->d_dthkc, sizeof(double) * rl->n_r_loc, cudaMemcpyDeviceToHost, h->stream));
+    rl->pipelined = true;
+    int rc = magic_rloop_run_dev(rl, &din, &dout, time);
+    rl->pipelined = false;
+    if (rc) return 1;
+    MCHECK(cudaStreamSynchronize(rl->s_down));
     MCHECK(cudaStreamSynchronize(h->stream));
+    memcpy(out->dtrkc, rl->host_dtrkc, sizeof(double) * rl->n_r_loc);
+    memcpy(out->dthkc, rl->host_dthkc, sizeof(double) * rl->n_r_loc);
     return 0;
 }
 
