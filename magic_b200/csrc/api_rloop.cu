@@ -95,7 +95,6 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
     if (P.l_precession || P.l_centrifuge) {
         // supported in the kernel; nothing to reject
     }
-    if (P.l_full_sphere) MFAIL("magic_rloop_create: l_full_sphere (v_center_sphere) is not implemented yet");
     magic_rloop *rl = new magic_rloop();
     rl->h = h;
     rl->p = P;
@@ -124,6 +123,7 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
         L.nBc = nBc; L.lDeriv = lDeriv; L.l_bound = l_bound ? 1 : 0;
         L.nl_on = (!loop_bound || lMagNlBc) ? 1 : 0;
         L.cour_on = (!P.l_full_sphere || !is_icb) ? 1 : 0;
+        L.center = (P.l_full_sphere && is_icb) ? 1 : 0;
         L.r = rad->r[i]; L.or1 = rad->or1[i]; L.or2 = rad->or2[i]; L.or4 = rad->or4[i]; L.orho1 = rad->orho1[i];
         L.orho2 = rad->orho2[i]; L.beta = rad->beta[i]; L.rho0 = rad->rho0[i]; L.otemp1 = rad->otemp1[i]; L.temp0 = rad->temp0[i];
         L.visc = rad->visc[i]; L.lambda = rad->lambda[i]; L.epscProf = rad->epscProf[i]; L.delxr2 = rad->delxr2[i];
@@ -143,6 +143,7 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
         if (P.l_heat) { add_scal(S, Term{S_S, F_ONE}, N_, LM_ALL, nf, gi.s); rl->need_in[S_S] = true; units_syn += 1; }
         if (P.l_chemical_conv) { add_scal(S, Term{S_XI, F_ONE}, N_, LM_ALL, nf, gi.xi); rl->need_in[S_XI] = true; units_syn += 1; }
         rl->need_in[S_W] = rl->need_in[S_DW] = rl->need_in[S_Z] = true;
+        if (P.l_full_sphere) rl->need_in[S_DDW] = true;
         add_scal(S, Term{S_W, F_DLH}, N_, LM_VEL, nf, gi.vr);
         add_pair(S, Term{S_DW, F_ONE}, N_, Term{S_Z, F_ONE}, N_, LM_VEL, nf, gi.vt, gi.vp);
         units_syn += 5;
@@ -299,6 +300,9 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
         F.omega_ic = P.omega_ic; F.r_cmb = P.r_cmb; F.r_icb = P.r_icb; F.courfac = P.courfac; F.alffac = P.alffac; F.time = time;
         a.gi = rl->gi; a.go = rl->go; a.gin = rl->buf.gin; a.gout = rl->buf.gout; a.n_lev = nl; a.nh = h->nh; a.n_phi = h->n_phi;
         a.minc = h->minc; a.lev = d_lev; a.sinth = h->d_sinth; a.costh = h->d_costh; a.courmax = rl->buf.courmax;
+        a.ddw = P.l_full_sphere ? src[S_DDW] : nullptr;
+        a.ddb = (P.l_full_sphere && (P.l_mag || P.l_mag_LF)) ? src[S_DDB] : nullptr;
+        a.lm_max = h->lm_max; a.lm10 = 1; a.lm11 = (h->minc == 1 && h->m_max >= 1) ? h->lstart[1] : -1;
         int gx = (int)((plane + NL_THREADS - 1) / NL_THREADS);
         const bool mag = P.l_mag || P.l_mag_LF || P.l_mag_nl;
         const bool extra = !P.l_adv_curl || P.l_anel || P.l_chemical_conv || P.l_precession || P.l_centrifuge;

@@ -41,7 +41,7 @@ struct ScalCol { Term t[2]; int lmask; int pad; };
 struct VecPair { Term S[2]; Term T[2]; int lmask; int pad; };
 
 struct LevelInfo {  // per local level, device resident
-    int nR, lcut, nBc, lDeriv, nl_on, l_bound, cour_on, pad1;
+    int nR, lcut, nBc, lDeriv, nl_on, l_bound, cour_on, center;  // center: full-sphere r=0 level (v_center_sphere)
     double r, or1, or2, or4, orho1, orho2, beta, rho0, otemp1, temp0, visc, lambda, epscProf, delxr2, delxh2;
 };
 

@@ -32,6 +32,8 @@ struct NlArgs {
     const LevelInfo *lev;
     const double *sinth, *costh;  // northern values, [nh]
     unsigned long long *courmax;  // [n_lev][2] bit patterns of the (non-negative) maxima vr2max, vh2max
+    const double *ddw, *ddb;      // spectral inputs of the chunk (complex [n_lev][lm_max]) for v_center_sphere, or null
+    int lm10, lm11, lm_max;       // st_map indices of (l=1,m=0), (l=1,m=1) (-1 when minc /= 1)
 };
 
 __device__ __forceinline__ void atomic_max_pos(unsigned long long *addr, double v) {
@@ -183,6 +185,27 @@ __global__ void __launch_bounds__(NL_THREADS, EXTRA ? 1 : 2) get_nl_kernel(NlArg
             const double om = (L.nR == 1) ? F.omega_ma : F.omega_ic;
             pn.vr = ps.vr = 0.0; pn.vt = ps.vt = 0.0;
             pn.vp = ps.vp = r2 * L.rho0 * (st * st) * om;
+        }
+        if (L.center) {  // v_center_sphere, nonlinear_bcs.f90:177-224 (full sphere, r=0)
+            const double y10 = 0.48860251190291992158638462283835, y11 = 0.34549414947133547925878907835150;
+            const double cph = cos(phi), sph = sin(phi);
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const double *dd = q == 0 ? a.ddw : a.ddb;
+                if (dd == nullptr || (q == 1 && !MAG)) continue;
+                const double d10 = dd[2 * ((size_t)lev * a.lm_max + a.lm10)];
+                double c = 0.0, sn = 0.0;
+                if (a.lm11 >= 0) {
+                    const double re = dd[2 * ((size_t)lev * a.lm_max + a.lm11)], im = dd[2 * ((size_t)lev * a.lm_max + a.lm11) + 1];
+                    c = re * cph - im * sph;
+                    sn = re * sph + im * cph;
+                }
+                const double vrn = y10 * d10 * ct + 2.0 * y11 * st * c, vrs = -y10 * d10 * ct + 2.0 * y11 * st * c;
+                const double vtn = st * (-y10 * d10 * st + 2.0 * y11 * ct * c), vts = st * (-y10 * d10 * st - 2.0 * y11 * ct * c);
+                const double vpb = -2.0 * y11 * st * sn;
+                if (q == 0) { pn.vr = vrn; ps.vr = vrs; pn.vt = vtn; ps.vt = vts; pn.vp = vpb; ps.vp = vpb; }
+                else { pn.br = vrn; ps.br = vrs; pn.bt = vtn; ps.bt = vts; pn.bp = vpb; ps.bp = vpb; }
+            }
         }
         PointOut on, os;
         if (L.nl_on) {

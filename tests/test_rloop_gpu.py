@@ -16,7 +16,8 @@ def oracle_params(p):
     return op
 
 
-def run_both(l_max, n_r_max, physics, levels, level_chunk=0, ktopv=2, kbotv=2, minc=1, n_phi_tot=0, l_R=None, seed=3):
+def run_both(l_max, n_r_max, physics, levels, level_chunk=0, ktopv=2, kbotv=2, minc=1, n_phi_tot=0, l_R=None, seed=3,
+             full_sphere=False):
     from magic_b200 import RadialLoop, Sht, grid_sizes
     from magic_b200.workload import make_fields, make_params, make_radial
     from oracle.oracle import Oracle
@@ -24,6 +25,7 @@ def run_both(l_max, n_r_max, physics, levels, level_chunk=0, ktopv=2, kbotv=2, m
     o = Oracle(gs["l_max"], minc=minc, n_theta=gs["n_theta_max"], n_phi=gs["n_phi_max"], m_max=gs["m_max"])
     s = Sht(gs["l_max"], m_max=gs["m_max"], minc=minc, n_theta_max=gs["n_theta_max"], n_phi_max=gs["n_phi_max"])
     p = make_params(physics, n_r_max, ktopv=ktopv, kbotv=kbotv)
+    p.l_full_sphere = 1 if full_sphere else 0
     rad_full = make_radial(n_r_max, gs["l_max"], l_R=l_R, anel=(physics == "anel"))
     idx = np.array(levels) - 1
     rad = {k: np.ascontiguousarray(v[idx]) for k, v in rad_full.items()}
@@ -114,3 +116,17 @@ def test_run_to_run_bitwise():
     b = run_both(16, 33, "mhd", [5, 6, 7, 8])
     for nm in MHD_OUT + ["dtrkc", "dthkc"]:
         assert np.array_equal(a[3][nm], b[3][nm]), nm
+
+
+@pytest.mark.parametrize("physics,minc,n_phi_tot", [("hydro", 1, 0), ("mhd", 1, 0), ("hydro", 3, 96)])
+def test_full_sphere_centre(physics, minc, n_phi_tot):
+    """samples/full_sphere geometry: the r=0 level takes v_center_sphere (nonlinear_bcs.f90:177-224, l=1 modes of ddw / ddb)
+    and skips the Courant check (rIter.f90:295); l_R varies with radius (radial.f90:291-307)."""
+    n_r = 10
+    l_max = 0 if n_phi_tot else 16
+    lm = 32 if n_phi_tot else 16
+    l_R = np.minimum(lm, (1 + lm * np.sqrt(np.linspace(1.0, 0.05, n_r) / 0.4)).astype(int))
+    o, p, rad, got, ref, ex = run_both(l_max, n_r, physics, list(range(1, n_r + 1)), minc=minc, n_phi_tot=n_phi_tot, l_R=l_R,
+                                       ktopv=1, kbotv=1, full_sphere=True)
+    compare(o, p, rad, got, ref, ex, MHD_OUT if physics == "mhd" else HYDRO_OUT)
+    assert got["dtrkc"][-1] == 1e10 and got["dthkc"][-1] == 1e10
