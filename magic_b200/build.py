@@ -22,10 +22,14 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return OUT
-    cmd = [NVCC] + FLAGS + ["-o", OUT, os.path.join(SRC, "lib.cu"), "-ldl"]
+def build(force=False, verbose=False, out=None, defines=()):
+    """out/defines: build an experimental variant (e.g. defines=["MAGIC_FFT_R_BIG=2"]) next to the default library."""
+    global OUT
+    if out is None:
+        if not force and not needs_build():
+            return OUT
+        out = OUT
+    cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + ["-o", out, os.path.join(SRC, "lib.cu"), "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout)
@@ -33,9 +37,10 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libmagic_b200.so")
     with open(os.path.join(HERE, "ptxas_report.txt"), "w") as f:
         f.write(r.stdout)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
-    print(OUT)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose=True, out=outs[0] if outs else None, defines=defs))

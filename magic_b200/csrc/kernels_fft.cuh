@@ -155,10 +155,18 @@ struct FftPasses<H, R, NT, 1, S> {
     static __device__ __forceinline__ void run(double2 *, const double2 *, double) {}
 };
 
-constexpr int FFT_R = 4;  // rows per CTA of the planned kernels
+// rows per CTA of the planned kernels (experiment knob MAGIC_FFT_R_BIG for H >= 1024)
+#ifndef MAGIC_FFT_R_BIG
+#define MAGIC_FFT_R_BIG 2  // measured at H=1536: 10.3 ms (R=2, two CTAs/SM) vs 11.9 ms (R=4) per 16-level chunk
+#endif
+#ifndef MAGIC_FFT_R_SMALL
+#define MAGIC_FFT_R_SMALL 4
+#endif
+__host__ __device__ constexpr int fft_rows(int H) { return H >= 768 ? MAGIC_FFT_R_BIG : MAGIC_FFT_R_SMALL; }  // H=768: 2.30 vs 2.51 ms; H=384: 1.20 vs 1.15 ms
 // threads per CTA: about 12 complex elements per thread (measured better than 6 at H=1536: 13.3 vs 14.1 ms FFT per chunk)
+__host__ __device__ constexpr int fft_threads_raw(int H, int R) { return ((R * H / 12 + 31) / 32) * 32; }
 __host__ __device__ constexpr int fft_threads(int H) {
-    return ((H / 3 + 31) / 32) * 32 < 32 ? 32 : ((H / 3 + 31) / 32) * 32 > 512 ? 512 : ((H / 3 + 31) / 32) * 32;
+    return fft_threads_raw(H, fft_rows(H)) < 32 ? 32 : fft_threads_raw(H, fft_rows(H)) > 512 ? 512 : fft_threads_raw(H, fft_rows(H));
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -168,7 +176,7 @@ template <int H>
 __global__ void __launch_bounds__(fft_threads(H)) fft_c2r_plan_kernel(const double2 *__restrict__ tw, const double *__restrict__ F, int ld,
                                                                      int n_m, int nh, int ncols, const int *__restrict__ colrow,
                                                                      double *__restrict__ grid) {
-    constexpr int R = FFT_R, NT = fft_threads(H), N = 2 * H, ROWLEN = fft_pad(H);
+    constexpr int R = fft_rows(H), NT = fft_threads(H), N = 2 * H, ROWLEN = fft_pad(H);
     extern __shared__ __align__(16) double2 fsm[];
     const int cc0 = blockIdx.x * R;
     const int sk = blockIdx.y, s = sk / nh, k = sk - s * nh;
@@ -257,7 +265,7 @@ __device__ __forceinline__ void r2c_scatter(const R2cArgs &a, const R2cField &fd
 
 template <int H>
 __global__ void __launch_bounds__(fft_threads(H)) fft_r2c_plan_kernel(const double2 *__restrict__ tw, R2cArgs a) {
-    constexpr int R = FFT_R, NT = fft_threads(H), N = 2 * H, ROWLEN = fft_pad(H);
+    constexpr int R = fft_rows(H), NT = fft_threads(H), N = 2 * H, ROWLEN = fft_pad(H);
     extern __shared__ __align__(16) double2 fsm[];
     const int lev0 = blockIdx.x * R;
     const int sk = blockIdx.y, s = sk / a.nh, k = sk - s * a.nh;
@@ -409,7 +417,7 @@ inline bool fft_has_plan(int H) {
 #undef X
     return false;
 }
-inline size_t fft_plan_smem(int H) { return (size_t)FFT_R * fft_pad(H) * sizeof(double2); }
+inline size_t fft_plan_smem(int H) { return (size_t)fft_rows(H) * fft_pad(H) * sizeof(double2); }
 
 inline cudaError_t fft_setup_attributes(int H) {
     cudaError_t e = cudaFuncSetAttribute(fft_c2r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -433,7 +441,7 @@ inline void launch_fft_c2r(const FftPlan &pl, const double *F, int ld, int n_m, 
     const int H = pl.H;
 #define X(h)                                                                                                                      \
     if (H == h) {                                                                                                                 \
-        dim3 g((ncols + FFT_R - 1) / FFT_R, 2 * nh);                                                                              \
+        dim3 g((ncols + fft_rows(h) - 1) / fft_rows(h), 2 * nh);                                                                              \
         fft_c2r_plan_kernel<h><<<g, fft_threads(h), fft_plan_smem(h), st>>>(pl.tw, F, ld, n_m, nh, ncols, colrow, grid);          \
         return;                                                                                                                   \
     }
@@ -448,7 +456,7 @@ inline void launch_fft_r2c(const FftPlan &pl, const R2cArgs &a, int nfields, cud
     const int H = pl.H;
 #define X(h)                                                                                      \
     if (H == h) {                                                                                 \
-        dim3 g((a.n_lev + FFT_R - 1) / FFT_R, 2 * a.nh, nfields);                                 \
+        dim3 g((a.n_lev + fft_rows(h) - 1) / fft_rows(h), 2 * a.nh, nfields);                                 \
         fft_r2c_plan_kernel<h><<<g, fft_threads(h), fft_plan_smem(h), st>>>(pl.tw, a);            \
         return;                                                                                   \
     }

@@ -4,7 +4,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmagic_b200.so")
+LIB_PATH = os.environ.get("MAGIC_B200_LIB", os.path.join(_HERE, "libmagic_b200.so"))  # env override: experimental builds
 _lib = None
 
 
