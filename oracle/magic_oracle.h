@@ -7,10 +7,16 @@
  * src/nonlinear_bcs.f90, src/rIter.f90 and the alltoallv flavour of src/mpi_transpose.f90.
  * Every function cites the reference file:line it follows.
  *
- * PARITY STATUS: "parity unpinned" by reference golden vectors -- the reference holds no
- * transform-level known-answer tests and cannot be compiled in this image (no Fortran
- * compiler).  The oracle is pinned instead by analytic known answers and an independent scipy
- * evaluation of the associated Legendre functions (tests/test_oracle_analytic.py).
+ * PARITY STATUS: the reference cannot be compiled in this image (Fortran 2008 + MPI, no Fortran compiler) and holds no
+ * transform-level known-answer tests.  The oracle is pinned
+ *   (1) against a GOLDEN VECTOR OF THE REFERENCE for the vector synthesis: the kinetic energy of the reference's own
+ *       checkpoint fixture samples/boussBenchSat/checkpoint_end.start, evaluated in grid space through
+ *       orc_torpol_to_spat, reproduces the e_kin_pol / e_kin_tor / axisymmetric columns of
+ *       samples/boussBenchSat/reference.out to 8e-10 (tests/test_reference_energy.py; 9 printed digits);
+ *   (2) by analytic known answers and an independent scipy evaluation of the associated Legendre functions
+ *       (tests/test_oracle_analytic.py), which also tie the analysis to the synthesis by round trips <= 1e-13.
+ * get_nl / get_td / courant have no reference vectors to be checked against here ("parity unpinned" for those rows):
+ * they are literal restatements, line-cited.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may call
  * into this library.  The product path (magic_b200/) never links or imports it.
