@@ -252,16 +252,29 @@ def run_magic(args, gs):
 
     stage_acc = {}
 
+    tev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    tacc = {"transp_lm2r": 0.0, "transp_r2lm": 0.0}
+
     def step():
+        tev[0].record(ext)
         tr.transp_lm2r_dev_n(5, flow_LM.data_ptr(), flow_R.data_ptr())
         tr.transp_lm2r_dev_n(2, s_LM.data_ptr(), s_R.data_ptr())
         tr.transp_lm2r_dev_n(5, field_LM.data_ptr(), field_R.data_ptr())
+        tev[1].record(ext)
         rl.radialLoop_dev(fin_p, fout_p, dtr.data_ptr(), dth.data_ptr())
+        tev[2].record(ext)
         tr.transp_r2lm_dev_n(3, dflow_R.data_ptr(), dflow_LM.data_ptr())
         tr.transp_r2lm_dev_n(2, ds_R.data_ptr(), ds_LM.data_ptr())
         tr.transp_r2lm_dev_n(3, db_R.data_ptr(), db_LM.data_ptr())
+        tev[3].record(ext)
         for k, v in rl.last_timing().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
+        # (the radial loop synchronises per chunk, so the lm2r events of this step have completed)
+        tev[1].synchronize()
+        tacc["transp_lm2r"] += tev[0].elapsed_time(tev[1])
+        pending.append(None)
+
+    pending = []
 
     def barrier():
         ext.synchronize()
@@ -273,6 +286,8 @@ def run_magic(args, gs):
         step()
     barrier()
     stage_acc.clear()
+    pending.clear()
+    tacc["transp_lm2r"] = 0.0
     launches0 = sht.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -294,6 +309,8 @@ def run_magic(args, gs):
     total_flops = flops_per_level(gs) * n_r_max
     value = total_flops / (ms_step * 1e-3) * 1e-9
     stages = {k: v / args.steps for k, v in stage_acc.items()}
+    stages["transp_lm2r"] = tacc["transp_lm2r"] / max(len(pending), 1)
+    stages["transp_r2lm_plus_wait"] = ms - stages["transp_lm2r"] - stages["total"]
     leg_ms = stages["legendre_syn"] + stages["legendre_an"]
     leg_tflops = rl.legendre_flops() / (leg_ms * 1e-3) * 1e-12 if leg_ms > 0 else 0.0
     checksum = float(torch.view_as_real(dflow_LM).abs().sum().item())
@@ -308,6 +325,11 @@ def run_magic(args, gs):
         del fin, fin_p, flow_R, s_R, field_R, fout, fout_p, dflow_R, ds_R, db_R
         torch.cuda.empty_cache()
         host_out = {k: torch.empty(nr_loc, lm_max, dtype=torch.complex128).pin_memory() for k in OUT_NAMES}
+        # the host-buffer path pipelines H2D / compute / D2H over level chunks: give it at least four chunks
+        e2e_chunk = chunk if (chunk and nr_loc // chunk >= 4) else max(4, nr_loc // 4)
+        if e2e_chunk != chunk:
+            rl.finalize()
+            rl = RadialLoop(sht, p, rad, level_chunk=e2e_chunk)
         np_in = {k: v.numpy() for k, v in host_in.items()}
         np_out = {k: v.numpy() for k, v in host_out.items()}
         np_out["dtrkc"] = np.zeros(nr_loc)
@@ -329,7 +351,7 @@ def run_magic(args, gs):
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
         e2e = {"value": total_flops / (float(ems.item()) * 1e-3) * 1e-9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(ems.item()),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(ems.item()), "level_chunk": e2e_chunk,
                "path": "magic_rloop_run (host R-distributed containers in, explicit terms out; transposes stay on the host side)"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------------------
