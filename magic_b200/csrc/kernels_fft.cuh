@@ -107,8 +107,14 @@ __device__ __forceinline__ void fft_pass(double2 *buf, const double2 *__restrict
         if (TOTAL % NT == 0 || idx < TOTAL) {
             int row = idx / NB, b = idx - row * NB;
             const double2 *x = buf + row * ROWLEN;
+            if constexpr (NB % 8 == 0) {  // padded index is affine in j: pad(b + NB j) = pad(b) + j (NB + NB/8)
+                const double2 *xb = x + fft_pad(b);
 #pragma unroll
-            for (int j = 0; j < RADIX; j++) reg[u][j] = x[fft_pad(b + NB * j)];
+                for (int j = 0; j < RADIX; j++) reg[u][j] = xb[j * (NB + NB / 8)];
+            } else {
+#pragma unroll
+                for (int j = 0; j < RADIX; j++) reg[u][j] = x[fft_pad(b + NB * j)];
+            }
         }
     }
     __syncthreads();
@@ -121,7 +127,13 @@ __device__ __forceinline__ void fft_pass(double2 *buf, const double2 *__restrict
             double2 o[RADIX];
             butterfly<RADIX>(reg[u], o, sg);
             double2 *y = buf + row * ROWLEN;
-            y[fft_pad(q + S * (RADIX * p))] = o[0];
+            // output position of o[k]: pad(q + S (RADIX p + k)) = y0 + k * ystride for the strides that occur
+            int y0, ystride;
+            if constexpr (S % 8 == 0) { y0 = fft_pad(q + S * RADIX * p); ystride = S + S / 8; }
+            else if constexpr (S == 1 && RADIX == 8) { y0 = 9 * p; ystride = 1; }
+            else if constexpr (S == 1 && RADIX == 4) { y0 = 4 * p + (p >> 1); ystride = 1; }
+            else { y0 = 0; ystride = 0; }
+            constexpr bool AFFINE = (S % 8 == 0) || (S == 1 && (RADIX == 8 || RADIX == 4));
             if (M > 1) {
                 // twiddles w^k, w = e^{sg 2 pi i p/LEN}: one table load, the powers by a depth-3 product tree (the
                 // kernel is bound by L1/shared wavefronts, not by the FP64 pipe; each product costs ~1 ulp)
@@ -132,10 +144,12 @@ __device__ __forceinline__ void fft_pass(double2 *buf, const double2 *__restrict
                 if (RADIX > 4) w[4] = cmul(w[2], w[2]);
                 if (RADIX > 5) { w[5] = cmul(w[4], w[1]); w[6] = cmul(w[3], w[3]); w[7 < RADIX ? 7 : 0] = cmul(w[4], w[3]); }
 #pragma unroll
-                for (int k = 1; k < RADIX; k++) y[fft_pad(q + S * (RADIX * p + k))] = cmul(o[k], w[k]);
-            } else {
+                for (int k = 1; k < RADIX; k++) o[k] = cmul(o[k], w[k]);
+            }
 #pragma unroll
-                for (int k = 1; k < RADIX; k++) y[fft_pad(q + S * (RADIX * p + k))] = o[k];
+            for (int k = 0; k < RADIX; k++) {
+                if constexpr (AFFINE) y[y0 + k * ystride] = o[k];
+                else y[fft_pad(q + S * (RADIX * p + k))] = o[k];
             }
         }
     }
