@@ -255,8 +255,8 @@ struct R2cArgs {
     int minc;
 };
 
-__device__ __forceinline__ void r2c_scatter(const R2cArgs &a, const R2cField &fd, int s, int k, int mc, int lev, double2 zk, double2 zmc,
-                                            double2 w8, double w, double ws) {
+__device__ __forceinline__ void r2c_scatter(const R2cArgs &a, const R2cDest *__restrict__ dests /* [2] of (field, s) */, int k, int mc,
+                                            int lev, double2 zk, double2 zmc, double2 w8, double w, double ws) {
     // X_k = E_k + e^{-2 pi i k/N} O_k, E=(Z_k+conj Z_{H-k})/2, O=-i (Z_k-conj Z_{H-k})/2
     double2 zm = cconj(zmc);
     double2 e = cscale(cadd(zk, zm), 0.5), o = cmuli(cscale(csub(zk, zm), 0.5), -1.0);
@@ -264,16 +264,19 @@ __device__ __forceinline__ void r2c_scatter(const R2cArgs &a, const R2cField &fd
     const double dm = (double)(mc * a.minc);
 #pragma unroll
     for (int d = 0; d < 2; d++) {
-        const R2cDest ds = fd.d[s][d];
-        if (ds.rtype == R_NONE) continue;
+        const int rtype = dests[d].rtype;
+        if (rtype == R_NONE) continue;
+        const int cls = dests[d].cls, col = dests[d].col, p = dests[d].p, seg = dests[d].seg;
         double2 v;
-        if (ds.rtype == R_W) v = cscale(x, w);
-        else if (ds.rtype == R_WS) v = cscale(x, ws);
-        else if (ds.rtype == R_NEG_WS) v = cscale(x, -ws);
+        if (rtype == R_W) v = cscale(x, w);
+        else if (rtype == R_WS) v = cscale(x, ws);
+        else if (rtype == R_NEG_WS) v = cscale(x, -ws);
         else v = make_double2(dm * ws * x.y, -dm * ws * x.x);  // -i m ws x
-        const int rowsB = (ds.cls == 0) ? a.NHP : 2 * a.NHP;
-        size_t off = ((size_t)(mc * 2 + ds.p) * rowsB + ds.seg * a.NHP + k) * a.ldB[ds.cls] + 2 * ((size_t)ds.col * a.n_lev + lev);
-        *reinterpret_cast<double2 *>(a.B[ds.cls] + off) = v;
+        const int rowsB = cls == 0 ? a.NHP : 2 * a.NHP;
+        const int ld = cls == 0 ? a.ldB[0] : a.ldB[1];
+        double *B = cls == 0 ? a.B[0] : a.B[1];
+        size_t off = ((size_t)(mc * 2 + p) * rowsB + seg * a.NHP + k) * ld + 2 * ((size_t)col * a.n_lev + lev);
+        *reinterpret_cast<double2 *>(B + off) = v;
     }
 }
 
@@ -306,12 +309,12 @@ __global__ void __launch_bounds__(fft_threads(H)) fft_r2c_plan_kernel(const doub
     __syncthreads();
     FftPasses<H, R, NT, H, 1>::run(fsm, tw, -1.0);
     const double w = a.wgauss[k], ws = w * a.osin2[k];
-    const R2cField fd = a.fields[field];
+    const R2cDest *dests = &a.fields[field].d[s][0];
     for (int idx = threadIdx.x; idx < R * a.n_m; idx += NT) {
         int mc = idx / R, r = idx - mc * R;
         if (r >= rows) continue;
         const double2 *z = fsm + r * ROWLEN;
-        r2c_scatter(a, fd, s, k, mc, lev0 + r, z[fft_pad(mc)], z[fft_pad(mc == 0 ? 0 : H - mc)], twid(tw, mc, -1.0), w, ws);
+        r2c_scatter(a, dests, k, mc, lev0 + r, z[fft_pad(mc)], z[fft_pad(mc == 0 ? 0 : H - mc)], twid(tw, mc, -1.0), w, ws);
     }
 }
 
@@ -408,11 +411,11 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_r2c_kernel(FftPlan pl, R2cArg
     __syncthreads();
     double2 *Z = stockham_fft(buf0, buf1, R, pl, -1.0);
     const double w = a.wgauss[k], ws = w * a.osin2[k];
-    const R2cField fd = a.fields[field];
+    const R2cDest *dests = &a.fields[field].d[s][0];
     for (int idx = threadIdx.x; idx < rows * a.n_m; idx += blockDim.x) {
         int mc = idx / rows, r = idx - mc * rows;
         const double2 *z = Z + r * H;
-        r2c_scatter(a, fd, s, k, mc, lev0 + r, z[mc], z[mc == 0 ? 0 : H - mc], twid(pl.tw, mc, -1.0), w, ws);
+        r2c_scatter(a, dests, k, mc, lev0 + r, z[mc], z[mc == 0 ? 0 : H - mc], twid(pl.tw, mc, -1.0), w, ws);
     }
 }
 
