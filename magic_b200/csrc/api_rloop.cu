@@ -36,7 +36,6 @@ struct magic_rloop {
     bool need_out[O_COUNT] = {false};
     cudaEvent_t ev[16];
     double timing[8] = {0};
-    std::vector<float> acc;
     double legendre_flops = 0;
     std::vector<const void *> registered, seen;
     // host-pointer path: uploads / downloads of level chunks overlap the compute of neighbouring chunks
@@ -92,9 +91,9 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
     *out = nullptr;
     MCHECK(cudaSetDevice(h->dev));
     const magic_params &P = *pp;
-    if (P.l_precession || P.l_centrifuge) {
-        // supported in the kernel; nothing to reject
-    }
+    if (P.l_cond_ma || P.l_cond_ic || P.l_rot_ma || P.l_rot_ic)
+        MFAIL("magic_rloop_create: conducting / rotating boundaries need get_br_v_bcs and the Lorentz torques "
+              "(nonlinear_bcs.f90:24, rIter.f90:267-292), which the batched loop does not produce yet");
     magic_rloop *rl = new magic_rloop();
     rl->h = h;
     rl->p = P;
@@ -211,7 +210,9 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
         double per_level = 8.0 * ((double)probe.szBs + probe.szBv + probe.szFs + probe.szFv + probe.szBas + probe.szBav + probe.szCas + probe.szCav) +
                            8.0 * 2.0 * h->nh * h->n_phi * (S.nfield_in + S.nfield_out);
         level_chunk = (int)std::max(1.0, std::min((double)n_r_loc, 0.6 * (double)free_b / per_level));
-        level_chunk = std::min(level_chunk, 32);  // measured: the analysis GEMM loses 15-20 % at 64-level chunks (N' = 768)
+        // measured: the analysis GEMM loses 15-20 % at 64-level chunks (N' = 768), and a 33-level slab split into 17+16
+        // costs more in tile quantisation than it saves: one chunk up to 48 levels, else chunks of at most 32
+        if (n_r_loc > 48 || level_chunk < n_r_loc) level_chunk = std::min(level_chunk, 32);
     }
     level_chunk = std::min(level_chunk, n_r_loc);
     int nchunks = (n_r_loc + level_chunk - 1) / level_chunk;
@@ -275,8 +276,6 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
     if (!out->dtrkc || !out->dthkc) MFAIL("magic_rloop_run_dev: dtrkc/dthkc are null");
     const size_t lm2 = 2 * (size_t)h->lm_max;
     const size_t plane = (size_t)h->nh * h->n_phi;
-    rl->acc.assign(8, 0.f);
-    struct ChunkEv { int c; };
     std::vector<float> stage(8, 0.f);
     cudaEventRecord(rl->ev[15], h->stream);
     for (size_t c = 0; c < rl->chunk_start.size(); c++) {
@@ -358,7 +357,7 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
             MCHECK(cudaMemcpyAsync(rl->host_dtrkc + l0, out->dtrkc + l0, sizeof(double) * nl, cudaMemcpyDeviceToHost, rl->s_down));
             MCHECK(cudaMemcpyAsync(rl->host_dthkc + l0, out->dthkc + l0, sizeof(double) * nl, cudaMemcpyDeviceToHost, rl->s_down));
         }
-        if (rl->chunk_start.size() > 1 || true) {
+        {
             // per-stage device times of this chunk (the sync also bounds the number of in-flight chunks)
             MCHECK(cudaEventSynchronize(rl->ev[9]));
             float ms;

@@ -130,3 +130,22 @@ def test_full_sphere_centre(physics, minc, n_phi_tot):
                                        ktopv=1, kbotv=1, full_sphere=True)
     compare(o, p, rad, got, ref, ex, MHD_OUT if physics == "mhd" else HYDRO_OUT)
     assert got["dtrkc"][-1] == 1e10 and got["dthkc"][-1] == 1e10
+
+
+def test_hydro_bench_anel_shape():
+    """BASELINE config 2 (samples/hydro_bench_anel as shipped: n_phi_tot=288 -> l_max=96, n_r=97, anelastic hydro with
+    u.grad u advection and viscous heating, stress-free walls): a CMB level, three bulk levels and the ICB level."""
+    o, p, rad, got, ref, ex = run_both(0, 97, "anel", [1, 2, 48, 96, 97], n_phi_tot=288, ktopv=1, kbotv=1)
+    assert o.l_max == 96 and o.lm_max == 4753
+    compare(o, p, rad, got, ref, ex, HYDRO_OUT)
+
+
+def test_unsupported_boundary_physics_fails_loudly():
+    from magic_b200 import MagicError, RadialLoop, Sht
+    from magic_b200.workload import make_params, make_radial
+    s = Sht(16)
+    p = make_params("mhd", 33)
+    p.l_cond_ic = 1
+    with pytest.raises(MagicError, match="get_br_v_bcs"):
+        RadialLoop(s, p, make_radial(33, 16))
+    s.finalize_sht()
