@@ -123,6 +123,11 @@ int magic_rloop_destroy(magic_rloop *rl);
 int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const magic_fields_out *out, double time);
 /* Device-pointer call (inputs/outputs already resident in HBM, e.g. produced by magic_transp_*_dev). */
 int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, const magic_fields_out *out, double time);
+/* omega_ma / omega_ic change every time step when the mantle / inner core rotate (v_rigid_boundary,
+ * nonlinear_bcs.f90:120-175): set them before a run.  After a run, the Lorentz torques of rIter.f90:279-292,461
+ * (zero unless l_mag_LF and the wall is rotating and conducting). */
+int magic_rloop_set_rotation(magic_rloop *rl, double omega_ma, double omega_ic);
+int magic_rloop_get_torques(const magic_rloop *rl, double *lorentz_torque_ic, double *lorentz_torque_ma);
 /* Stream control + kernel accounting for the benchmark. */
 int magic_rloop_sync(magic_rloop *rl);
 long long magic_rloop_launch_count(const magic_rloop *rl);

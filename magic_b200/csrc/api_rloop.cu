@@ -32,6 +32,9 @@ struct magic_rloop {
     double *d_in[S_COUNT] = {nullptr};
     double *d_out[O_COUNT] = {nullptr};
     double *d_dtrkc = nullptr, *d_dthkc = nullptr;
+    double *d_tq_partial = nullptr, *d_torque = nullptr, *h_torque = nullptr;  // Lorentz torques (ic, ma)
+    int tq_parts = 0;
+    double torque[2] = {0.0, 0.0};
     bool need_in[S_COUNT] = {false};
     bool need_out[O_COUNT] = {false};
     cudaEvent_t ev[16];
@@ -72,7 +75,8 @@ extern "C" int magic_rloop_destroy(magic_rloop *rl) {
     buffers_free(rl->buf);
     for (int i = 0; i < S_COUNT; i++) cudaFree(rl->d_in[i]);
     for (int i = 0; i < O_COUNT; i++) cudaFree(rl->d_out[i]);
-    cudaFree(rl->d_dtrkc); cudaFree(rl->d_dthkc); cudaFree(rl->d_lev);
+    cudaFree(rl->d_dtrkc); cudaFree(rl->d_dthkc); cudaFree(rl->d_lev); cudaFree(rl->d_tq_partial); cudaFree(rl->d_torque);
+    if (rl->h_torque) cudaFreeHost(rl->h_torque);
     for (int i = 0; i < 16; i++) cudaEventDestroy(rl->ev[i]);
     for (auto e : rl->up_done) cudaEventDestroy(e);
     for (auto e : rl->comp_done) cudaEventDestroy(e);
@@ -91,9 +95,9 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
     *out = nullptr;
     MCHECK(cudaSetDevice(h->dev));
     const magic_params &P = *pp;
-    if (P.l_cond_ma || P.l_cond_ic || P.l_rot_ma || P.l_rot_ic)
-        MFAIL("magic_rloop_create: conducting / rotating boundaries need get_br_v_bcs and the Lorentz torques "
-              "(nonlinear_bcs.f90:24, rIter.f90:267-292), which the batched loop does not produce yet");
+    if (P.l_mag_nl && ((P.ktopv == 1 && P.l_cond_ma) || (P.kbotv == 1 && P.l_cond_ic)))
+        MFAIL("magic_rloop_create: stress-free + conducting walls need get_br_v_bcs (nonlinear_bcs.f90:24, Namelists.f90:713-729), "
+              "which the batched loop does not produce yet");
     magic_rloop *rl = new magic_rloop();
     rl->h = h;
     rl->p = P;
@@ -123,6 +127,9 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
         L.nl_on = (!loop_bound || lMagNlBc) ? 1 : 0;
         L.cour_on = (!P.l_full_sphere || !is_icb) ? 1 : 0;
         L.center = (P.l_full_sphere && is_icb) ? 1 : 0;
+        L.torque = 0;  // rIter.f90:279-292
+        if (is_icb && P.l_mag_LF && P.l_rot_ic && P.l_cond_ic) L.torque = 1;
+        if (is_cmb && P.l_mag_LF && P.l_rot_ma && P.l_cond_ma) L.torque = 2;
         L.r = rad->r[i]; L.or1 = rad->or1[i]; L.or2 = rad->or2[i]; L.or4 = rad->or4[i]; L.orho1 = rad->orho1[i];
         L.orho2 = rad->orho2[i]; L.beta = rad->beta[i]; L.rho0 = rad->rho0[i]; L.otemp1 = rad->otemp1[i]; L.temp0 = rad->temp0[i];
         L.visc = rad->visc[i]; L.lambda = rad->lambda[i]; L.epscProf = rad->epscProf[i]; L.delxr2 = rad->delxr2[i];
@@ -240,6 +247,10 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
         MCHECK(cudaEventCreateWithFlags(&rl->up_done[c], cudaEventDisableTiming));
         MCHECK(cudaEventCreateWithFlags(&rl->comp_done[c], cudaEventDisableTiming));
     }
+    rl->tq_parts = (int)(((size_t)h->nh * h->n_phi + NL_THREADS - 1) / NL_THREADS);
+    MCHECK(cudaMalloc((void **)&rl->d_tq_partial, sizeof(double) * (size_t)rl->tq_parts * rl->lay_size[0]));
+    MCHECK(cudaMalloc((void **)&rl->d_torque, sizeof(double) * 2));
+    MCHECK(cudaMallocHost((void **)&rl->h_torque, sizeof(double) * 2));
     MCHECK(cudaMallocHost((void **)&rl->host_dtrkc, sizeof(double) * n_r_loc));
     MCHECK(cudaMallocHost((void **)&rl->host_dthkc, sizeof(double) * n_r_loc));
     MCHECK(cudaMalloc((void **)&rl->d_dtrkc, sizeof(double) * n_r_loc));
@@ -278,6 +289,7 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
     const size_t plane = (size_t)h->nh * h->n_phi;
     std::vector<float> stage(8, 0.f);
     cudaEventRecord(rl->ev[15], h->stream);
+    MCHECK(cudaMemsetAsync(rl->d_torque, 0, sizeof(double) * 2, h->stream));  // rIter.f90:177-178
     for (size_t c = 0; c < rl->chunk_start.size(); c++) {
         const int l0 = rl->chunk_start[c], nl = rl->chunk_size[c];
         const Layout &L = (nl == rl->lay_size[0]) ? rl->lay[0] : rl->lay[1];
@@ -301,12 +313,14 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
         a.minc = h->minc; a.lev = d_lev; a.sinth = h->d_sinth; a.costh = h->d_costh; a.courmax = rl->buf.courmax;
         a.ddw = P.l_full_sphere ? src[S_DDW] : nullptr;
         a.ddb = (P.l_full_sphere && (P.l_mag || P.l_mag_LF)) ? src[S_DDB] : nullptr;
+        a.wgauss = h->d_wgauss; a.tq_partial = rl->d_tq_partial;
         a.lm_max = h->lm_max; a.lm10 = 1; a.lm11 = (h->minc == 1 && h->m_max >= 1) ? h->lstart[1] : -1;
         int gx = (int)((plane + NL_THREADS - 1) / NL_THREADS);
         const bool mag = P.l_mag || P.l_mag_LF || P.l_mag_nl;
         const bool extra = !P.l_adv_curl || P.l_anel || P.l_chemical_conv || P.l_precession || P.l_centrifuge;
         launch_get_nl(a, mag, extra, gx, nl, h->stream);
-        courant_finish_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(rl->buf.courmax, d_lev, nl, out->dtrkc + l0, out->dthkc + l0);
+        courant_finish_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(rl->buf.courmax, d_lev, nl, out->dtrkc + l0, out->dthkc + l0,
+                                                                      rl->d_tq_partial, gx, P.LFfac, rl->d_torque);
         h->launches += 2;
         cudaEventRecord(rl->ev[4], h->stream);
         if (run_analysis(h, rl->spec, L, rl->buf, d_lev, rl->ev + 5, false)) return 1;  // ev[5..7]; extraction is fused below
@@ -368,8 +382,11 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
             }
         }
     }
+    MCHECK(cudaMemcpyAsync(rl->h_torque, rl->d_torque, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stream));
     cudaEventRecord(rl->ev[14], h->stream);
     MCHECK(cudaEventSynchronize(rl->ev[14]));
+    rl->torque[0] = rl->h_torque[0];
+    rl->torque[1] = rl->h_torque[1];
     float tot;
     cudaEventElapsedTime(&tot, rl->ev[15], rl->ev[14]);
     stage[0] = tot;
@@ -446,6 +463,18 @@ extern "C" int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const
     return 0;
 }
 
+extern "C" int magic_rloop_set_rotation(magic_rloop *rl, double omega_ma, double omega_ic) {
+    if (!rl) MFAIL("null rloop");
+    rl->p.omega_ma = omega_ma;
+    rl->p.omega_ic = omega_ic;
+    return 0;
+}
+extern "C" int magic_rloop_get_torques(const magic_rloop *rl, double *lorentz_torque_ic, double *lorentz_torque_ma) {
+    if (!rl) MFAIL("null rloop");
+    if (lorentz_torque_ic) *lorentz_torque_ic = rl->torque[0];
+    if (lorentz_torque_ma) *lorentz_torque_ma = rl->torque[1];
+    return 0;
+}
 extern "C" int magic_rloop_sync(magic_rloop *rl) {
     if (!rl) MFAIL("null rloop");
     MCHECK(cudaSetDevice(rl->h->dev));

@@ -42,6 +42,7 @@ struct VecPair { Term S[2]; Term T[2]; int lmask; int pad; };
 
 struct LevelInfo {  // per local level, device resident
     int nR, lcut, nBc, lDeriv, nl_on, l_bound, cour_on, center;  // center: full-sphere r=0 level (v_center_sphere)
+    int torque, pad2;  // torque: 1 = Lorentz torque on the inner core, 2 = on the mantle is taken at this level (rIter.f90:279-292)
     double r, or1, or2, or4, orho1, orho2, beta, rho0, otemp1, temp0, visc, lambda, epscProf, delxr2, delxh2;
 };
 

@@ -34,6 +34,8 @@ struct NlArgs {
     unsigned long long *courmax;  // [n_lev][2] bit patterns of the (non-negative) maxima vr2max, vh2max
     const double *ddw, *ddb;      // spectral inputs of the chunk (complex [n_lev][lm_max]) for v_center_sphere, or null
     int lm10, lm11, lm_max;       // st_map indices of (l=1,m=0), (l=1,m=1) (-1 when minc /= 1)
+    const double *wgauss;         // 2 pi gauss(k) / n_phi
+    double *tq_partial;           // [n_lev][gridDim.x] per-CTA partial sums of gauss * Br * Bp (get_lorentz_torque)
 };
 
 __device__ __forceinline__ void atomic_max_pos(unsigned long long *addr, double v) {
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(NL_THREADS, EXTRA ? 1 : 2) get_nl_kernel(NlArg
     const LevelInfo L = a.lev[lev];
     const NlFlags &F = a.f;
     const size_t plane = (size_t)a.nh * a.n_phi;  // one (field,lev,s) slab
-    double vr2max = 0.0, vh2max = 0.0;
+    double vr2max = 0.0, vh2max = 0.0, tq = 0.0;
     double valri2 = 0.0, valhi2 = 0.0;
     if (F.l_cour_alf_damp) {
         double h = 0.5 * (1.0 + F.opm);
@@ -207,6 +209,7 @@ __global__ void __launch_bounds__(NL_THREADS, EXTRA ? 1 : 2) get_nl_kernel(NlArg
                 else { pn.br = vrn; ps.br = vrs; pn.bt = vtn; ps.bt = vts; pn.bp = vpb; ps.bp = vpb; }
             }
         }
+        if (MAG && L.torque) tq += a.wgauss[k] * (pn.br * pn.bp + ps.br * ps.bp);  // outRot.f90:477-478
         PointOut on, os;
         if (L.nl_on) {
             nl_point<MAG, EXTRA>(F, L, pn, st, ct, os2, cn2, phi, on);
@@ -251,18 +254,23 @@ __global__ void __launch_bounds__(NL_THREADS, EXTRA ? 1 : 2) get_nl_kernel(NlArg
             }
         }
     }
-    if (L.cour_on) {
-        __shared__ double red[2][NL_THREADS / 32];
+    if (L.cour_on || (MAG && L.torque)) {
+        // fixed-shape reductions (xor-shuffle tree, then warps in order): no floating-point atomics, bitwise reproducible
+        __shared__ double red[3][NL_THREADS / 32];
         for (int o = 16; o > 0; o >>= 1) {
             vr2max = fmax(vr2max, __shfl_xor_sync(0xffffffffu, vr2max, o));
             vh2max = fmax(vh2max, __shfl_xor_sync(0xffffffffu, vh2max, o));
+            tq += __shfl_xor_sync(0xffffffffu, tq, o);
         }
-        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = vr2max; red[1][threadIdx.x >> 5] = vh2max; }
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = vr2max; red[1][threadIdx.x >> 5] = vh2max; red[2][threadIdx.x >> 5] = tq; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int w = 1; w < NL_THREADS / 32; w++) { vr2max = fmax(vr2max, red[0][w]); vh2max = fmax(vh2max, red[1][w]); }
-            atomic_max_pos(a.courmax + 2 * lev, vr2max);
-            atomic_max_pos(a.courmax + 2 * lev + 1, vh2max);
+            for (int w = 1; w < NL_THREADS / 32; w++) { vr2max = fmax(vr2max, red[0][w]); vh2max = fmax(vh2max, red[1][w]); tq += red[2][w]; }
+            if (L.cour_on) {
+                atomic_max_pos(a.courmax + 2 * lev, vr2max);
+                atomic_max_pos(a.courmax + 2 * lev + 1, vh2max);
+            }
+            if (MAG && L.torque) a.tq_partial[(size_t)lev * gridDim.x + blockIdx.x] = tq;
         }
     }
 }
@@ -278,8 +286,10 @@ inline void launch_get_nl(const NlArgs &a, bool mag, bool extra, int gx, int n_l
     }
 }
 
-// dtrkc/dthkc from the maxima (courant.f90:272-273, rIter.f90:215-216)
-__global__ void courant_finish_kernel(const unsigned long long *courmax, const LevelInfo *lev, int n_lev, double *dtrkc, double *dthkc) {
+// dtrkc/dthkc from the maxima (courant.f90:272-273, rIter.f90:215-216); Lorentz torques from the per-CTA partial sums,
+// added in CTA order (outRot.f90:423-483; the mantle torque changes sign, rIter.f90:461)
+__global__ void courant_finish_kernel(const unsigned long long *courmax, const LevelInfo *lev, int n_lev, double *dtrkc, double *dthkc,
+                                      const double *tq_partial, int n_part, double LFfac, double *torque /* [0]=ic, [1]=ma */) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_lev) return;
     double vr2max = __longlong_as_double((long long)courmax[2 * i]), vh2max = __longlong_as_double((long long)courmax[2 * i + 1]);
@@ -290,6 +300,12 @@ __global__ void courant_finish_kernel(const unsigned long long *courmax, const L
     }
     dtrkc[i] = a;
     dthkc[i] = b;
+    if (lev[i].torque && tq_partial != nullptr) {
+        double sum = 0.0;
+        for (int j = 0; j < n_part; j++) sum += tq_partial[(size_t)i * n_part + j];
+        if (lev[i].torque == 1) torque[0] = LFfac * sum;
+        else torque[1] = -(LFfac * sum);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------

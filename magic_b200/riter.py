@@ -123,6 +123,16 @@ class RadialLoop:
         fin, fout, keep = self._structs(fields_dev, out_dev, dtrkc_dev, dthkc_dev, device=True)
         check(self.lib.magic_rloop_run_dev(self._h, byref(fin), byref(fout), c_double(time)))
 
+    def set_rotation(self, omega_ma, omega_ic):
+        """Boundary rotation rates of the coming step (omega_ma, omega_ic of v_rigid_boundary)."""
+        check(self.lib.magic_rloop_set_rotation(self._h, c_double(omega_ma), c_double(omega_ic)))
+
+    def torques(self):
+        """(lorentz_torque_ic, lorentz_torque_ma) of the last run (rIter.f90:279-292,461)."""
+        a, b = c_double(), c_double()
+        check(self.lib.magic_rloop_get_torques(self._h, byref(a), byref(b)))
+        return a.value, b.value
+
     def sync(self):
         check(self.lib.magic_rloop_sync(self._h))
 

@@ -148,6 +148,7 @@ typedef struct {
 typedef struct {
     orc_cplx *dwdt, *dzdt, *dpdt, *dsdt, *dxidt, *dbdt, *djdt, *dVxVhLM, *dVxBhLM, *dVSrLM, *dVXirLM;
     double *dtrkc, *dthkc; /* [n_r] */
+    double *lorentz_torque_ic, *lorentz_torque_ma; /* scalars (rIter.f90:279-292, outRot.f90:423-483); may be NULL */
 } orc_fields_out;
 
 /* Executes the body of `do nR=nRstart,nRstop` (rIter.f90:190-444) for n_r levels, with all output

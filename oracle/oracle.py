@@ -55,7 +55,8 @@ class _FieldsIn(C.Structure):
 
 
 class _FieldsOut(C.Structure):
-    _fields_ = [(n, c_void_p) for n in _OUT_NAMES] + [("dtrkc", c_void_p), ("dthkc", c_void_p)]
+    _fields_ = [(n, c_void_p) for n in _OUT_NAMES] + [("dtrkc", c_void_p), ("dthkc", c_void_p),
+                                                       ("lorentz_torque_ic", c_void_p), ("lorentz_torque_ma", c_void_p)]
 
 
 def _load(fast):
@@ -290,8 +291,12 @@ class Oracle:
         out["dthkc"] = np.zeros(n_r)
         fout.dtrkc = _p(out["dtrkc"])
         fout.dthkc = _p(out["dthkc"])
+        tq = np.zeros(2)
+        fout.lorentz_torque_ic = tq.ctypes.data
+        fout.lorentz_torque_ma = tq.ctypes.data + 8
         self.lib.orc_radial_loop(self.h, C.byref(params), C.byref(rad), c_int(n_r), C.byref(fin), C.byref(fout),
                                  c_double(time))
+        out["lorentz_torque_ic"], out["lorentz_torque_ma"] = float(tq[0]), float(tq[1])
         return out
 
     def get_nl_mhd(self, params, nR, nBc, or2, or4, orho1, grids_in):

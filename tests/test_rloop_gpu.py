@@ -17,7 +17,7 @@ def oracle_params(p):
 
 
 def run_both(l_max, n_r_max, physics, levels, level_chunk=0, ktopv=2, kbotv=2, minc=1, n_phi_tot=0, l_R=None, seed=3,
-             full_sphere=False):
+             full_sphere=False, tweak=None):
     from magic_b200 import RadialLoop, Sht, grid_sizes
     from magic_b200.workload import make_fields, make_params, make_radial
     from oracle.oracle import Oracle
@@ -26,12 +26,16 @@ def run_both(l_max, n_r_max, physics, levels, level_chunk=0, ktopv=2, kbotv=2, m
     s = Sht(gs["l_max"], m_max=gs["m_max"], minc=minc, n_theta_max=gs["n_theta_max"], n_phi_max=gs["n_phi_max"])
     p = make_params(physics, n_r_max, ktopv=ktopv, kbotv=kbotv)
     p.l_full_sphere = 1 if full_sphere else 0
+    if tweak:
+        for k, v in tweak.items():
+            setattr(p, k, v)
     rad_full = make_radial(n_r_max, gs["l_max"], l_R=l_R, anel=(physics == "anel"))
     idx = np.array(levels) - 1
     rad = {k: np.ascontiguousarray(v[idx]) for k, v in rad_full.items()}
     fields = make_fields(physics, o.lm2l, o.lm2m, len(levels), seed)
     rl = RadialLoop(s, p, rad, level_chunk=level_chunk)
     got = rl.radialLoop(fields)
+    got["lorentz_torque_ic"], got["lorentz_torque_ma"] = rl.torques()
     ref = o.radial_loop(oracle_params(p), rad, fields)
     # Conditioning probe: the oracle's response to a last-bits (1e-15 relative) perturbation of its inputs.
     # Outputs that are small differences of large sums (e.g. the toroidal part of the nonlinear force,
@@ -146,6 +150,21 @@ def test_unsupported_boundary_physics_fails_loudly():
     s = Sht(16)
     p = make_params("mhd", 33)
     p.l_cond_ic = 1
+    p.kbotv = 1  # stress-free + conducting inner core -> l_b_nl_icb (Namelists.f90:713-720)
     with pytest.raises(MagicError, match="get_br_v_bcs"):
         RadialLoop(s, p, make_radial(33, 16))
     s.finalize_sht()
+
+
+def test_conducting_rotating_walls_and_lorentz_torques():
+    """boussBenchSat physics (conducting, rotating inner core; here also the mantle): rigid walls move with omega
+    (v_rigid_boundary), get_nl runs on the boundary levels (lMagNlBc) and the Lorentz torques are the quadrature of
+    Br*Bp over the wall (rIter.f90:279-292,461, outRot.f90:423-483)."""
+    tw = dict(l_cond_ic=1, l_rot_ic=1, l_cond_ma=1, l_rot_ma=1, omega_ic=0.37, omega_ma=-0.21)
+    o, p, rad, got, ref, ex = run_both(16, 33, "mhd", [1, 2, 3, 31, 32, 33], tweak=tw)
+    compare(o, p, rad, got, ref, ex, MHD_OUT)
+    assert ref["lorentz_torque_ic"] != 0 and ref["lorentz_torque_ma"] != 0
+    assert abs(got["lorentz_torque_ic"] / ref["lorentz_torque_ic"] - 1) < 1e-11
+    assert abs(got["lorentz_torque_ma"] / ref["lorentz_torque_ma"] - 1) < 1e-11
+    # rotation rates can change from step to step
+    assert np.linalg.norm(got["dVxBhLM"][0]) > 0  # moving wall drags field lines: non-zero boundary induction term
