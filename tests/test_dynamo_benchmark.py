@@ -1,0 +1,120 @@
+"""End-to-end golden vectors of the reference: samples/dynamo_benchmark, first 100 time steps.
+
+This is the reference's OWN test of the radial-loop hot path: `samples/dynamo_benchmark/unitTest.py:97-106` runs
+magic.exe (l_max=16, n_r_max=33, Boussinesq MHD, rigid insulating walls, CN/AB2, dt=1e-4) and compares e_kin.TAG and
+e_mag_oc.TAG with reference.out / referenceMag.out at rtol 1e-8, atol 1e-20.  The flow starts from rest, so already
+row 1 is produced entirely by the radial loop (Lorentz force of the start field through torpol_to_spat /
+torpol_to_curl_spat -> get_nl -> spat_to_qst -> get_dwdt/get_dzdt) and every later row by all of it (advection, induction,
+entropy advection, Coriolis couplings, boundary levels, Courant).
+
+The Fortran host cannot be built here, so its LM side is restated in numpy (oracle/lmloop.py, every routine cited);
+the radial loop is either the CPU oracle (CPU test: pins the oracle's get_nl / get_td / analysis rows to the reference)
+or the CUDA library through the C ABI (`-m gpu`: pins the product).  tests/golden/dynamo_benchmark_reference.npz holds
+rows 0..200 of the two reference files (tests/golden/make_dynamo_benchmark_fixture.py).
+
+reference.out prints 9 significant digits (ES16.8), so a correctly rounded value differs from ours by up to 5e-9
+relative; the autotest tolerance 1e-8 is used as is.
+"""
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+RTOL, ATOL = 1e-8, 1e-20          # samples/dynamo_benchmark/unitTest.py:100,106 (magic_wizard.py:423)
+N_STEPS = 100                     # north_star: "dynamo_benchmark energies ... over 100 steps"
+
+
+@pytest.fixture(scope="module")
+def golden():
+    d = np.load(os.path.join(HERE, "golden", "dynamo_benchmark_reference.npz"))
+    return {k: d[k] for k in d.files}
+
+
+def _host(golden, lm2l, lm2m, rloop):
+    from oracle.lmloop import BoussinesqDynamoHost
+    kw = {k: float(golden[k]) for k in ("radratio", "ra", "ek", "pr", "prmag", "dtmax", "alpha", "amp_s1", "amp_b1")}
+    return BoussinesqDynamoHost(lm2l, lm2m, rloop, n_r_max=int(golden["n_r_max"]), init_s1=int(golden["init_s1"]),
+                                init_b1=int(golden["init_b1"]), **kw)
+
+
+def _params(golden):
+    from magic_b200.workload import make_params, make_radial
+    n_r, l_max = int(golden["n_r_max"]), int(golden["l_max"])
+    p = make_params("mhd", n_r, ktopv=2, kbotv=2)     # input.nml: mode=0, ktopv=kbotv=2, ek=1e-3, prmag=5
+    p.courfac, p.alffac = float(golden["courfac"]), float(golden["alffac"])
+    return p, make_radial(n_r, l_max)
+
+
+def _run(golden, host, n_steps):
+    kin = [np.concatenate([[0.0], host.e_kin()])]
+    mag = [np.concatenate([[0.0], host.e_mag_oc()])]
+    for _ in range(n_steps):
+        host.step()
+        kin.append(np.concatenate([[host.time], host.e_kin()]))
+        mag.append(np.concatenate([[host.time], host.e_mag_oc()]))
+    kin, mag = np.array(kin), np.array(mag)
+    np.testing.assert_allclose(kin, golden["e_kin"][: n_steps + 1], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(mag, golden["e_mag_oc"][: n_steps + 1], rtol=RTOL, atol=ATOL)
+    return kin, mag
+
+
+def test_start_fields_reproduce_reference_row0(golden):
+    """initB (init_b1=3, amp_b1=5) and the energy integrals against row 0 of referenceMag.out -- no radial loop."""
+    from oracle.oracle import Oracle
+    o = Oracle(int(golden["l_max"]))
+    h = _host(golden, o.lm2l, o.lm2m, None)
+    np.testing.assert_allclose(h.e_mag_oc(), golden["e_mag_oc"][0, 1:], rtol=RTOL, atol=ATOL)
+    assert np.all(h.e_kin() == 0.0)
+
+
+def test_oracle_radial_loop_reproduces_reference_energies(golden):
+    """CPU oracle inside the reference's time loop: 100 steps of e_kin (8 columns) and e_mag_oc (12 columns)."""
+    from oracle.oracle import Oracle, Params as OParams
+    o = Oracle(int(golden["l_max"]))
+    p, rad = _params(golden)
+    op = OParams()
+    for n, _ in p._fields_:
+        setattr(op, n, getattr(p, n))
+    h = _host(golden, o.lm2l, o.lm2m, lambda f: o.radial_loop(op, rad, f))
+    _run(golden, h, N_STEPS)
+    # the Courant limits of this run stay above dt (no time-step change in the reference's log either)
+    assert min(h.dtrkc_min, h.dthkc_min) > float(golden["dtmax"])
+
+
+@pytest.mark.gpu
+def test_gpu_radial_loop_reproduces_reference_energies(golden):
+    """The CUDA radial loop (magic_rloop_run through the C ABI, host containers) inside the reference's time loop."""
+    from magic_b200 import RadialLoop, Sht
+    s = Sht(int(golden["l_max"]))
+    p, rad = _params(golden)
+    rl = RadialLoop(s, p, rad)
+    h = _host(golden, s.lm2l, s.lm2m, lambda f: rl.radialLoop(f))
+    _run(golden, h, N_STEPS)
+    assert rl.launch_count() > 0
+    rl.finalize()
+    s.finalize_sht()
+
+
+@pytest.mark.gpu
+def test_gpu_and_oracle_trajectories_agree(golden):
+    """Same 20 steps with both radial loops: the states themselves (not just their energies) must agree."""
+    from magic_b200 import RadialLoop, Sht
+    from oracle.oracle import Oracle, Params as OParams
+    from tests.util import rel_l2
+    o = Oracle(int(golden["l_max"]))
+    s = Sht(int(golden["l_max"]))
+    p, rad = _params(golden)
+    op = OParams()
+    for n, _ in p._fields_:
+        setattr(op, n, getattr(p, n))
+    rl = RadialLoop(s, p, rad)
+    ha = _host(golden, o.lm2l, o.lm2m, lambda f: o.radial_loop(op, rad, f))
+    hb = _host(golden, s.lm2l, s.lm2m, lambda f: rl.radialLoop(f))
+    for _ in range(20):
+        ha.step()
+        hb.step()
+    for nm in ("w", "z", "s", "b", "aj"):
+        assert rel_l2(getattr(hb, nm), getattr(ha, nm)) < 1e-11, nm
+    rl.finalize()
+    s.finalize_sht()
