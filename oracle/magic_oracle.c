@@ -1,6 +1,6 @@
 /*
  * magic_oracle.c -- CPU restatement of MagIC's radial-loop hot path.  TEST INFRASTRUCTURE ONLY.
- * See magic_oracle.h for scope, conventions and the "parity unpinned" statement.
+ * See magic_oracle.h for scope, conventions and the parity status (pinned / unpinned rows).
  * All file:line citations are relative to /root/reference/src/.
  */
 #include "magic_oracle.h"

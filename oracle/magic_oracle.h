@@ -15,8 +15,14 @@
  *       samples/boussBenchSat/reference.out to 8e-10 (tests/test_reference_energy.py; 9 printed digits);
  *   (2) by analytic known answers and an independent scipy evaluation of the associated Legendre functions
  *       (tests/test_oracle_analytic.py), which also tie the analysis to the synthesis by round trips <= 1e-13.
- * get_nl / get_td / courant have no reference vectors to be checked against here ("parity unpinned" for those rows):
- * they are literal restatements, line-cited.
+ *   (3) against the GOLDEN VECTORS OF THE REFERENCE'S OWN END-TO-END TEST for the whole radial loop (syntheses, get_nl,
+ *       analyses, get_td, boundary levels, courant): orc_radial_loop, driven by a numpy restatement of the LM-side
+ *       host (oracle/lmloop.py), reproduces the first 100 rows of samples/dynamo_benchmark/reference.out (e_kin.TAG,
+ *       8 columns) and referenceMag.out (e_mag_oc.TAG, 12 columns) at the autotest tolerance rtol 1e-8
+ *       (tests/test_dynamo_benchmark.py; the same test runs the CUDA library through the C ABI under -m gpu).
+ * Still "parity unpinned" (no reference vectors reachable here, literal line-cited restatements only): the anelastic /
+ * u.grad u branch of get_nl with viscous heating (samples/hydro_bench_anel needs the anelastic host), the full-sphere
+ * centre level, rotating conducting walls and the inner-core (_IC) and axisymmetric syntheses.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may call
  * into this library.  The product path (magic_b200/) never links or imports it.

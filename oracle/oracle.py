@@ -1,7 +1,8 @@
 """ctypes front-end to the CPU oracle (oracle/magic_oracle.c).  TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
-this module; magic_b200/ never does.  "parity unpinned": see oracle/magic_oracle.h.
+this module; magic_b200/ never does.  Parity status (what is pinned to reference vectors, what is not): see
+oracle/magic_oracle.h.
 
 Array conventions (numpy, C order):
   spectral  complex128 [lm_max]            st_map order (reference X(lm))

@@ -1,7 +1,8 @@
 """Pins the CPU oracle with analytic known answers and an independent scipy evaluation.
 
-The reference holds no transform-level golden vectors and cannot be compiled here, so
-the oracle is "parity unpinned" with respect to reference outputs; these tests are what anchors it.
+The reference holds no transform-level golden vectors and cannot be compiled here; these tests anchor
+each transform on its own, next to the two golden-vector tests of reference outputs (tests/test_reference_energy.py,
+tests/test_dynamo_benchmark.py).
 """
 import numpy as np
 import pytest
