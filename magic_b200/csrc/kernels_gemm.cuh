@@ -6,7 +6,11 @@
 // with A a slice of the precomputed P/D table, B the (level x field x re/im) batch.  The FP64 pipe is the
 // binding roofline; B200 executes FP64 MMA as DMMA.8x8x4 (measured 37.0 TFLOP/s vs 33.8 for
 // DFMA, profiles/fp64_peak_r01.json), there is no tcgen05 kind for f64, so the tile engine is
-// mma.sync.m8n8k4.f64 fed from shared memory by a multi-stage cp.async pipeline.
+// mma.sync.m8n8k4.f64 fed from shared memory by a multi-stage cp.async pipeline whose stages are handed over with
+// mbarriers (full: the cp.async of all threads have landed; empty: all warps have consumed the stage).  K-tile kt+STAGES-2
+// is loaded at iteration kt into the stage k-tile kt-2 used, so a warp may run up to two k-tiles ahead of the slowest one
+// instead of meeting all others at a CTA barrier every k-tile (measured at l_max=1023, 16 levels: synthesis 16.18 -> 15.10 ms,
+// analysis 12.04 -> 11.76 ms; bit-identical results).
 //
 //   CTA tile 128 x 64, 8 warps as 4(M) x 2(N), warp tile 32 x 32 = 4x4 DMMA tiles, k-tile 16.
 //   A_KCONTIG=false (synthesis): A tile stored As[k][m] (m = colatitude contiguous in the table).
@@ -20,13 +24,20 @@ namespace magic {
 
 constexpr int G_THREADS = 256;
 constexpr int LDA_M = GEMM_BM + 4;  // As[k][m]
-constexpr int LDA_K = BK + 4;       // As[m][k]
+// analysis A tile As[m][k]: padded rows (BK+4) or, with MAGIC_GEMM_SWZ, dense rows whose 4-double groups are XOR-swizzled
+// by (m & 3): the same conflict-free LDS.64 fragment loads in 20 % less shared memory, which buys a 4th pipeline stage
+// (measured 11.68 -> 11.55 ms per 16-level chunk at l_max=1023).  Not worth it / measured worse and removed again: 64x32 warp
+// tiles with 4 warps, interleaved fragment ownership for ragged tiles, register double-buffering of the fragments.
+#ifndef MAGIC_GEMM_SWZ
+#define MAGIC_GEMM_SWZ 1
+#endif
+constexpr int LDA_K = MAGIC_GEMM_SWZ ? BK : BK + 4;  // As[m][k]
 constexpr int LDB_S = GEMM_BN + 4;  // Bs[k][n]
 constexpr int A_TILE_M = BK * LDA_M;
 constexpr int A_TILE_K = GEMM_BM * LDA_K;
 constexpr int B_TILE = BK * LDB_S;
 constexpr int STAGES_M = 4;
-constexpr int STAGES_K = 3;
+constexpr int STAGES_K = MAGIC_GEMM_SWZ ? 4 : 3;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -35,6 +46,33 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ---- mbarrier helpers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// arrival that fires when all prior cp.async of this thread have landed (does not raise the pending count)
+__device__ __forceinline__ void mbar_cp_async_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -85,7 +123,7 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
 #pragma unroll
             for (int c = 0; c < 4; c++) {  // 128 rows x 8 chunks
                 int idx = tid + c * G_THREADS, m = idx >> 3, kc = idx & 7;
-                cp_async16(As + m * LDA_K + kc * 2, Ab + (size_t)(m0 + m) * lda + kc * 2);
+                cp_async16(As + m * LDA_K + (MAGIC_GEMM_SWZ ? kc ^ ((m & 3) << 1) : kc) * 2, Ab + (size_t)(m0 + m) * lda + kc * 2);
             }
         }
         const int kb = kt < pr.kt0 ? kt + pr.klo : kt + 2 * pr.klo;  // B row tile (skipped leading tiles of each segment)
@@ -103,31 +141,46 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    constexpr int DIST = STAGES - 2;  // prefetch distance; the remaining stage is the slack between fastest and slowest warp
+    __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES];
+    if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < KT) load_stage(s, s);
-        cp_async_commit();
-    }
-    for (int kt = 0; kt < KT; kt++) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-            int nk = kt + STAGES - 1;
-            if (nk < KT) load_stage(nk, nk % STAGES);
-            cp_async_commit();
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&bar_full[s], G_THREADS);        // one cp.async arrival per thread
+            mbar_init(&bar_empty[s], G_THREADS / 32);  // one arrival per warp
         }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < DIST; s++)
+        if (s < KT) {
+            load_stage(s, s);
+            mbar_cp_async_arrive(&bar_full[s]);
+        }
+    for (int kt = 0; kt < KT; kt++) {
+        {
+            const int nk = kt + DIST;
+            if (nk < KT) {
+                const int st = nk % STAGES, use = nk / STAGES;
+                if (use > 0) mbar_wait(&bar_empty[st], (use - 1) & 1);  // all warps are done with k-tile nk - STAGES
+                load_stage(nk, st);
+                mbar_cp_async_arrive(&bar_full[st]);
+            }
+        }
+        mbar_wait(&bar_full[kt % STAGES], (kt / STAGES) & 1);
         const double *As = smem + (kt % STAGES) * STAGE, *Bs = As + A_TILE;
         if (active) {
-#pragma unroll
-            for (int kk = 0; kk < BK / 4; kk++) {
-                double a[4], b[4];
+            auto load_frags = [&](int kk, double *a, double *b) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     int row = wm + i * 8 + g;
-                    a[i] = A_KCONTIG ? As[row * LDA_K + kk * 4 + t] : As[(kk * 4 + t) * LDA_M + row];
+                    a[i] = A_KCONTIG ? As[row * LDA_K + (MAGIC_GEMM_SWZ ? ((kk * 4 + t) ^ ((g & 3) << 2)) : kk * 4 + t)]
+                                     : As[(kk * 4 + t) * LDA_M + row];
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) b[j] = Bs[(kk * 4 + t) * LDB_S + wn + j * 8 + g];
+            };
+            auto mma_frags = [&](const double *a, const double *b) {
                 if (mfr == 4 && nfr == 4 && mlo == 0) {
 #pragma unroll
                     for (int i = 0; i < 4; i++)
@@ -140,10 +193,17 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
                         for (int j = 0; j < 4; j++)
                             if (i >= mlo && i < mfr && j < nfr) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                 }
+            };
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; kk++) {
+                double a[4], b[4];
+                load_frags(kk, a, b);
+                mma_frags(a, b);
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[kt % STAGES]);
     }
-    cp_async_wait<0>();
 
 #pragma unroll
     for (int i = 0; i < 4; i++) {

@@ -25,3 +25,9 @@ for it in range(4):
     fl = rl.legendre_flops()
     leg = t["legendre_syn"] + t["legendre_an"]
     print(json.dumps({k: round(v, 3) for k, v in t.items()}), "legendre TF/s", round(fl / leg * 1e-9, 2), "overall TF/s", round(fl / t["total"] * 1e-9, 2))
+import hashlib
+torch.cuda.synchronize()
+h = hashlib.sha256()
+for k in sorted(outs):
+    h.update(outs[k].cpu().numpy().tobytes())
+print("sha256 of outputs", h.hexdigest()[:16], "dtrkc", float(dtr.min()), "dthkc", float(dth.min()))
