@@ -96,10 +96,10 @@ __host__ __device__ constexpr int fft_pick_radix(int len) {
 __host__ __device__ constexpr int fft_pad(int i) { return i + (i >> 3); }
 
 // One in-place Stockham pass (compile-time radix RADIX, sub-length LEN, stride S) over R rows of length H.
-template <int H, int R, int NT, int RADIX, int LEN, int S>
+template <int H, int R, int NT, int RADIX, int LEN, int S, int ROWLEN = fft_pad(H)>
 __device__ __forceinline__ void fft_pass(double2 *buf, const double2 *__restrict__ tw, double sg) {
     constexpr int M = LEN / RADIX, NB = H / RADIX, TOTAL = R * NB, PER = (TOTAL + NT - 1) / NT;
-    constexpr int TWSTEP = 2 * H / LEN, ROWLEN = fft_pad(H);
+    constexpr int TWSTEP = 2 * H / LEN;
     double2 reg[PER][RADIX];
 #pragma unroll
     for (int u = 0; u < PER; u++) {
@@ -156,91 +156,6 @@ __device__ __forceinline__ void fft_pass(double2 *buf, const double2 *__restrict
     __syncthreads();
 }
 
-template <int H, int R, int NT, int LEN, int S>
-struct FftPasses {
-    static constexpr int RADIX = fft_pick_radix(LEN);
-    static __device__ __forceinline__ void run(double2 *buf, const double2 *__restrict__ tw, double sg) {
-        fft_pass<H, R, NT, RADIX, LEN, S>(buf, tw, sg);
-        FftPasses<H, R, NT, LEN / RADIX, S * RADIX>::run(buf, tw, sg);
-    }
-};
-template <int H, int R, int NT, int S>
-struct FftPasses<H, R, NT, 1, S> {
-    static __device__ __forceinline__ void run(double2 *, const double2 *, double) {}
-};
-
-// rows per CTA of the planned kernels (experiment knob MAGIC_FFT_R_BIG for H >= 1024)
-#ifndef MAGIC_FFT_R_BIG
-#define MAGIC_FFT_R_BIG 2  // measured at H=1536: 10.3 ms (R=2, two CTAs/SM) vs 11.9 ms (R=4) per 16-level chunk
-#endif
-#ifndef MAGIC_FFT_R_SMALL
-#define MAGIC_FFT_R_SMALL 4
-#endif
-__host__ __device__ constexpr int fft_rows(int H) { return H >= 768 ? MAGIC_FFT_R_BIG : MAGIC_FFT_R_SMALL; }  // H=768: 2.30 vs 2.51 ms; H=384: 1.20 vs 1.15 ms
-// threads per CTA: about 12 complex elements per thread (measured better than 6 at H=1536: 13.3 vs 14.1 ms FFT per chunk)
-__host__ __device__ constexpr int fft_threads_raw(int H, int R) { return ((R * H / 12 + 31) / 32) * 32; }
-__host__ __device__ constexpr int fft_threads(int H) {
-    return fft_threads_raw(H, fft_rows(H)) < 32 ? 32 : fft_threads_raw(H, fft_rows(H)) > 512 ? 512 : fft_threads_raw(H, fft_rows(H));
-}
-
-// ------------------------------------------------------------------------------------------------------
-// c2r: grid row (row index = colrow[cc]) of parity s and colatitude k from column cc of F.
-//   F element (mc, s, k, col cc) at F[((mc*2+s)*nh + k)*ld + 2*cc].   blockIdx.x = column chunk, blockIdx.y = s*nh + k.
-template <int H>
-__global__ void __launch_bounds__(fft_threads(H)) fft_c2r_plan_kernel(const double2 *__restrict__ tw, const double *__restrict__ F, int ld,
-                                                                     int n_m, int nh, int ncols, const int *__restrict__ colrow,
-                                                                     double *__restrict__ grid) {
-    constexpr int R = fft_rows(H), NT = fft_threads(H), N = 2 * H, ROWLEN = fft_pad(H);
-    extern __shared__ __align__(16) double2 fsm[];
-    const int cc0 = blockIdx.x * R;
-    const int sk = blockIdx.y, s = sk / nh, k = sk - s * nh;
-    const int rows = min(R, ncols - cc0);
-    // gather the pair (c_kk, c_{H-kk}) and form  Y_k = (c_k + conj c_{H-k}) + i e^{2 pi i k/N} (c_k - conj c_{H-k}).
-    // All global loads of a thread are issued before the first use (memory-level parallelism for the strided gather).
-    const double *Fb = F + ((size_t)s * nh + k) * ld + 2 * cc0;
-    const size_t mstride = (size_t)2 * nh * ld;
-    constexpr int NPAIR = R * (H / 2 + 1), PERG = (NPAIR + NT - 1) / NT;
-    double2 ga[PERG], gb[PERG];
-#pragma unroll
-    for (int u = 0; u < PERG; u++) {
-        int idx = threadIdx.x + u * NT;
-        int kk = idx / R, r = idx - kk * R;
-        ga[u] = make_double2(0.0, 0.0);
-        gb[u] = ga[u];
-        if (idx < NPAIR && r < rows) {
-            if (kk < n_m) ga[u] = *reinterpret_cast<const double2 *>(Fb + kk * mstride + 2 * r);
-            if (kk > 0 && H - kk < n_m) gb[u] = *reinterpret_cast<const double2 *>(Fb + (size_t)(H - kk) * mstride + 2 * r);
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < PERG; u++) {
-        int idx = threadIdx.x + u * NT;
-        if (idx < NPAIR) {
-            int kk = idx / R, r = idx - kk * R;
-            double2 a = ga[u], b = gb[u];
-            if (kk == 0) a.y = 0.0;  // c2r ignores Im c_0 (fft.f90:262-268); c_H = 0 because n_m <= H
-            double2 w = twid(tw, kk, 1.0);
-            double2 cb = cconj(b), ca = cconj(a);
-            double2 *row = fsm + r * ROWLEN;
-            row[fft_pad(kk)] = cadd(cadd(a, cb), cmuli(cmul(w, csub(a, cb)), 1.0));
-            if (kk > 0 && 2 * kk < H) {
-                double2 w2 = make_double2(-w.x, w.y);  // e^{2 pi i (H-kk)/N} = -conj(w)
-                row[fft_pad(H - kk)] = cadd(cadd(b, ca), cmuli(cmul(w2, csub(b, ca)), 1.0));
-            }
-        }
-    }
-    __syncthreads();
-    FftPasses<H, R, NT, H, 1>::run(fsm, tw, 1.0);
-    // z_j = x_{2j} + i x_{2j+1}: the grid row is the interleaved complex array itself
-    for (int idx = threadIdx.x; idx < R * H; idx += NT) {
-        int r = idx / H, j = idx - r * H;
-        if (r < rows) {
-            int row = colrow[cc0 + r];
-            if (row >= 0) *reinterpret_cast<double2 *>(grid + (((size_t)row * 2 + s) * nh + k) * N + 2 * j) = fsm[r * ROWLEN + fft_pad(j)];
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------
 // r2c: one CTA transforms R grid rows (consecutive levels of one field, fixed s,k) and scatters the weighted
 // coefficients of orders mc < n_m into the analysis operands.  blockIdx.x = level chunk, .y = s*nh + k, .z = field.
@@ -280,41 +195,225 @@ __device__ __forceinline__ void r2c_scatter(const R2cArgs &a, const R2cDest *__r
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Planned kernels.  The first Stockham pass runs on the registers of the global gather and the last pass feeds the
+// global store, so a row crosses shared memory 2 (passes - 1) times instead of 2 passes + 2 (H = 1536 = 8.8.8.3: 6
+// transfers per element instead of 10; measured per 16-level chunk at l_max=1023: c2r 5.03 -> 4.54 ms, r2c 4.31 -> 4.08 ms
+// against the first-generation kernels that staged the gather in shared memory first).
+//   c2r: the Hermitian pre-processing pairs order kk with H-kk; first-pass butterfly b (inputs kk = b + NB j) pairs with
+//        butterfly NB-b, so one thread gathers the 2 R1 orders of both and produces both butterflies.
+//   r2c: the same pairing at the other end: last-pass butterfly q (outputs mc = q + S k) pairs with butterfly S-q.
+__host__ __device__ constexpr int fft_last_radix(int H) {
+    int len = H;
+    while (len / fft_pick_radix(len) > 1) len /= fft_pick_radix(len);
+    return len;
+}
+__host__ __device__ constexpr int fft2_rows(int H) { return H >= 768 ? 2 : H >= 256 ? 4 : H >= 96 ? 8 : 16; }
+__host__ __device__ constexpr int fft2_rowlen(int H) { return fft_pad(H) + ((fft_pad(H) % 8) == 4 ? 0 : (12 - fft_pad(H) % 8) % 8); }  // == 4 (mod 8): rows r, r+1 on complementary banks
+__host__ __device__ constexpr int fft2_threads(int H) {
+    // one thread per paired first-pass item: R * ceil(NB1 / 2), rounded to warps, at most 256
+    int t = ((fft2_rows(H) * ((H / fft_pick_radix(H) + 1) / 2) + 31) / 32) * 32;
+    return t > 256 ? 256 : t;
+}
+
+// middle passes: everything between the first (LEN = H) and the last (LEN = fft_last_radix(H)) pass
+template <int H, int R, int NT, int ROWLEN_, int LEN, int S>
+struct FftMid {
+    static constexpr int RADIX = fft_pick_radix(LEN);
+    static __device__ __forceinline__ void run(double2 *buf, const double2 *__restrict__ tw, double sg) {
+        if constexpr (LEN / RADIX > 1) {
+            fft_pass<H, R, NT, RADIX, LEN, S, ROWLEN_>(buf, tw, sg);
+            FftMid<H, R, NT, ROWLEN_, LEN / RADIX, S * RADIX>::run(buf, tw, sg);
+        }
+    }
+};
+
+// twiddle powers w^1..w^{RADIX-1} by the same product tree as fft_pass
+template <int RADIX>
+__device__ __forceinline__ void twiddle_powers(double2 *w) {
+    if (RADIX > 2) w[2] = cmul(w[1], w[1]);
+    if (RADIX > 3) w[3] = cmul(w[2], w[1]);
+    if (RADIX > 4) w[4] = cmul(w[2], w[2]);
+    if (RADIX > 5) { w[5] = cmul(w[4], w[1]); w[6] = cmul(w[3], w[3]); w[7 < RADIX ? 7 : 0] = cmul(w[4], w[3]); }
+}
+
+// first-pass butterfly b of a row (S = 1: p = b, outputs at 8b..8b+7 for radix 8) written to shared memory
+template <int H, int R1>
+__device__ __forceinline__ void first_pass_out(double2 *row, const double2 *__restrict__ tw, int b, const double2 *in, double sg) {
+    double2 o[R1];
+    butterfly<R1>(in, o, sg);
+    if (H / R1 > 1) {
+        double2 w[R1];
+        w[1] = twid(tw, b * 2, sg);  // TWSTEP = 2H / LEN = 2
+        twiddle_powers<R1>(w);
+#pragma unroll
+        for (int k = 1; k < R1; k++) o[k] = cmul(o[k], w[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < R1; k++) row[fft_pad(R1 * b + k)] = o[k];
+}
+
 template <int H>
-__global__ void __launch_bounds__(fft_threads(H)) fft_r2c_plan_kernel(const double2 *__restrict__ tw, R2cArgs a) {
-    constexpr int R = fft_rows(H), NT = fft_threads(H), N = 2 * H, ROWLEN = fft_pad(H);
+__global__ void __launch_bounds__(fft2_threads(H)) fft_c2r_plan_kernel(const double2 *__restrict__ tw, const double *__restrict__ F, int ld,
+                                                                    int n_m, int nh, int ncols, const int *__restrict__ colrow,
+                                                                    double *__restrict__ grid) {
+    constexpr int R = fft2_rows(H), NT = fft2_threads(H), N = 2 * H, ROWLEN = fft2_rowlen(H);
+    constexpr int R1 = fft_pick_radix(H), NB1 = H / R1, NI1 = (NB1 + 1) / 2;
+    constexpr int RL = fft_last_radix(H), SL = H / RL;
+    extern __shared__ __align__(16) double2 fsm[];
+    const int cc0 = blockIdx.x * R;
+    const int sk = blockIdx.y, s = sk / nh, k = sk - s * nh;
+    const int rows = min(R, ncols - cc0);
+    const double *Fb = F + ((size_t)s * nh + k) * ld + 2 * cc0;
+    const size_t mstride = (size_t)2 * nh * ld;
+    // ---- gather + Hermitian pre-processing + first pass.  Item t of a row: butterflies (t, NB1 - t); t = 0: butterfly 0 and,
+    //      for even NB1, the self-paired butterfly NB1/2.
+    for (int item = threadIdx.x; item < R * NI1; item += NT) {
+        const int t = item / R, r = item - t * R;
+        const bool has_v = (t > 0) || (NB1 % 2 == 0);
+        const int u = t, v = (t > 0) ? NB1 - t : NB1 / 2;
+        double2 A[R1], B[R1];
+#pragma unroll
+        for (int j = 0; j < R1; j++) {
+            A[j] = make_double2(0.0, 0.0);
+            B[j] = A[j];
+            const int ka = u + NB1 * j, kb = v + NB1 * j;
+            if (r < rows) {
+                if (ka < n_m) A[j] = *reinterpret_cast<const double2 *>(Fb + (size_t)ka * mstride + 2 * r);
+                if (has_v && kb < n_m) B[j] = *reinterpret_cast<const double2 *>(Fb + (size_t)kb * mstride + 2 * r);
+            }
+        }
+        double2 *row = fsm + r * ROWLEN;
+        double2 Yu[R1], Yv[R1];
+        if (t > 0) {
+            // order ka = u + NB1 j pairs with H - ka = v + NB1 (R1-1-j)
+#pragma unroll
+            for (int j = 0; j < R1; j++) {
+                const double2 a = A[j], b = B[R1 - 1 - j];
+                const double2 w = twid(tw, u + NB1 * j, 1.0);
+                const double2 cb = cconj(b), ca = cconj(a);
+                Yu[j] = cadd(cadd(a, cb), cmuli(cmul(w, csub(a, cb)), 1.0));
+                const double2 w2 = make_double2(-w.x, w.y);  // e^{2 pi i (H-ka)/N} = -conj(w)
+                Yv[R1 - 1 - j] = cadd(cadd(b, ca), cmuli(cmul(w2, csub(b, ca)), 1.0));
+            }
+        } else {
+            // butterfly 0: order NB1 j pairs with NB1 (R1 - j) (order H is absent: c_H = 0, Im c_0 ignored, fft.f90:262-268)
+#pragma unroll
+            for (int j = 0; j < R1; j++) {
+                double2 a = A[j];
+                double2 b = (j == 0) ? make_double2(0.0, 0.0) : A[R1 - j];
+                if (j == 0) a.y = 0.0;
+                const double2 w = twid(tw, NB1 * j, 1.0);
+                const double2 cb = cconj(b);
+                Yu[j] = cadd(cadd(a, cb), cmuli(cmul(w, csub(a, cb)), 1.0));
+            }
+            // butterfly NB1/2: order v + NB1 j pairs with v + NB1 (R1-1-j)
+#pragma unroll
+            for (int j = 0; j < R1; j++) {
+                const double2 a = B[j], b = B[R1 - 1 - j];
+                const double2 w = twid(tw, v + NB1 * j, 1.0);
+                const double2 cb = cconj(b);
+                Yv[j] = cadd(cadd(a, cb), cmuli(cmul(w, csub(a, cb)), 1.0));
+            }
+        }
+        first_pass_out<H, R1>(row, tw, u, Yu, 1.0);
+        if (has_v) first_pass_out<H, R1>(row, tw, v, Yv, 1.0);
+    }
+    __syncthreads();
+    FftMid<H, R, NT, ROWLEN, H / R1, R1>::run(fsm, tw, 1.0);
+    // ---- last pass (LEN = RL, p = 0: no twiddles) straight to the grid row: z_j = x_{2j} + i x_{2j+1}
+    for (int idx = threadIdx.x; idx < R * SL; idx += NT) {
+        const int r = idx / SL, q = idx - r * SL;
+        const double2 *x = fsm + r * ROWLEN;
+        double2 in[RL], o[RL];
+#pragma unroll
+        for (int j = 0; j < RL; j++) in[j] = x[fft_pad(q + SL * j)];
+        butterfly<RL>(in, o, 1.0);
+        if (r < rows) {
+            const int row = colrow[cc0 + r];
+            if (row >= 0) {
+                double *g = grid + (((size_t)row * 2 + s) * nh + k) * N;
+#pragma unroll
+                for (int kq = 0; kq < RL; kq++) *reinterpret_cast<double2 *>(g + 2 * (q + SL * kq)) = o[kq];
+            }
+        }
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(fft2_threads(H)) fft_r2c_plan_kernel(const double2 *__restrict__ tw, R2cArgs a) {
+    constexpr int R = fft2_rows(H), NT = fft2_threads(H), N = 2 * H, ROWLEN = fft2_rowlen(H);
+    constexpr int R1 = fft_pick_radix(H), NB1 = H / R1;
+    constexpr int RL = fft_last_radix(H), SL = H / RL, NIL = (SL + 1) / 2;
     extern __shared__ __align__(16) double2 fsm[];
     const int lev0 = blockIdx.x * R;
     const int sk = blockIdx.y, s = sk / a.nh, k = sk - s * a.nh;
     const int field = blockIdx.z;
     const int rows = min(R, a.n_lev - lev0);
+    // ---- first pass on the registers of the (coalesced) row loads
     {
-        constexpr int PERL = (R * H + NT - 1) / NT;
-        double2 gv[PERL];
+        constexpr int PER = (R * NB1 + NT - 1) / NT;
+        double2 reg[PER][R1];
 #pragma unroll
-        for (int u = 0; u < PERL; u++) {
-            int idx = threadIdx.x + u * NT;
-            int r = idx / H, j = idx - r * H;
-            gv[u] = make_double2(0.0, 0.0);
-            if (idx < R * H && r < rows)
-                gv[u] = *reinterpret_cast<const double2 *>(a.grid + ((((size_t)field * a.n_lev + lev0 + r) * 2 + s) * a.nh + k) * N + 2 * j);
+        for (int u = 0; u < PER; u++) {
+            const int idx = threadIdx.x + u * NT, r = idx / NB1, b = idx - r * NB1;
+#pragma unroll
+            for (int j = 0; j < R1; j++) {
+                reg[u][j] = make_double2(0.0, 0.0);
+                if (idx < R * NB1 && r < rows)
+                    reg[u][j] = *reinterpret_cast<const double2 *>(a.grid + ((((size_t)field * a.n_lev + lev0 + r) * 2 + s) * a.nh + k) * N +
+                                                                   2 * (b + NB1 * j));
+            }
         }
 #pragma unroll
-        for (int u = 0; u < PERL; u++) {
-            int idx = threadIdx.x + u * NT;
-            int r = idx / H, j = idx - r * H;
-            if (idx < R * H) fsm[r * ROWLEN + fft_pad(j)] = gv[u];
+        for (int u = 0; u < PER; u++) {
+            const int idx = threadIdx.x + u * NT, r = idx / NB1, b = idx - r * NB1;
+            if (idx < R * NB1) first_pass_out<H, R1>(fsm + r * ROWLEN, tw, b, reg[u], -1.0);
         }
     }
     __syncthreads();
-    FftPasses<H, R, NT, H, 1>::run(fsm, tw, -1.0);
+    FftMid<H, R, NT, ROWLEN, H / R1, R1>::run(fsm, tw, -1.0);
+    // ---- last pass + post-processing + scatter.  Item t of a row: butterflies (t, SL - t); t = 0: butterfly 0 and, for even
+    //      SL, the self-paired butterfly SL/2.  Butterfly q yields orders mc = q + SL kq, whose partners H - mc belong to SL - q.
     const double w = a.wgauss[k], ws = w * a.osin2[k];
     const R2cDest *dests = &a.fields[field].d[s][0];
-    for (int idx = threadIdx.x; idx < R * a.n_m; idx += NT) {
-        int mc = idx / R, r = idx - mc * R;
+    for (int item = threadIdx.x; item < R * NIL; item += NT) {
+        const int t = item / R, r = item - t * R;
         if (r >= rows) continue;
-        const double2 *z = fsm + r * ROWLEN;
-        r2c_scatter(a, dests, k, mc, lev0 + r, z[fft_pad(mc)], z[fft_pad(mc == 0 ? 0 : H - mc)], twid(tw, mc, -1.0), w, ws);
+        const bool has_v = (t > 0) || (SL % 2 == 0);
+        const int u = t, v = (t > 0) ? SL - t : SL / 2;
+        const double2 *x = fsm + r * ROWLEN;
+        double2 in[RL], Zu[RL], Zv[RL];
+#pragma unroll
+        for (int j = 0; j < RL; j++) in[j] = x[fft_pad(u + SL * j)];
+        butterfly<RL>(in, Zu, -1.0);
+        if (has_v) {
+#pragma unroll
+            for (int j = 0; j < RL; j++) in[j] = x[fft_pad(v + SL * j)];
+            butterfly<RL>(in, Zv, -1.0);
+        }
+        const int lev = lev0 + r;
+        if (t > 0) {
+#pragma unroll
+            for (int kq = 0; kq < RL; kq++) {
+                const int mu = u + SL * kq, mv = v + SL * (RL - 1 - kq);  // mu + mv = H
+                if (mu < a.n_m) r2c_scatter(a, dests, k, mu, lev, Zu[kq], Zv[RL - 1 - kq], twid(tw, mu, -1.0), w, ws);
+                if (mv < a.n_m) r2c_scatter(a, dests, k, mv, lev, Zv[RL - 1 - kq], Zu[kq], twid(tw, mv, -1.0), w, ws);
+            }
+        } else {
+#pragma unroll
+            for (int kq = 0; kq < RL; kq++) {
+                const int mu = SL * kq;  // partner H - mu = SL (RL - kq); mu = 0 pairs with itself
+                if (mu < a.n_m) r2c_scatter(a, dests, k, mu, lev, Zu[kq], kq == 0 ? Zu[0] : Zu[RL - kq], twid(tw, mu, -1.0), w, ws);
+            }
+            if (has_v) {
+#pragma unroll
+                for (int kq = 0; kq < RL; kq++) {
+                    const int mv = v + SL * kq;  // partner v + SL (RL-1-kq)
+                    if (mv < a.n_m) r2c_scatter(a, dests, k, mv, lev, Zv[kq], Zv[RL - 1 - kq], twid(tw, mv, -1.0), w, ws);
+                }
+            }
+        }
     }
 }
 
@@ -434,7 +533,7 @@ inline bool fft_has_plan(int H) {
 #undef X
     return false;
 }
-inline size_t fft_plan_smem(int H) { return (size_t)fft_rows(H) * fft_pad(H) * sizeof(double2); }
+inline size_t fft_plan_smem(int H) { return (size_t)fft2_rows(H) * fft2_rowlen(H) * sizeof(double2); }
 
 inline cudaError_t fft_setup_attributes(int H) {
     cudaError_t e = cudaFuncSetAttribute(fft_c2r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -458,8 +557,8 @@ inline void launch_fft_c2r(const FftPlan &pl, const double *F, int ld, int n_m, 
     const int H = pl.H;
 #define X(h)                                                                                                                      \
     if (H == h) {                                                                                                                 \
-        dim3 g((ncols + fft_rows(h) - 1) / fft_rows(h), 2 * nh);                                                                              \
-        fft_c2r_plan_kernel<h><<<g, fft_threads(h), fft_plan_smem(h), st>>>(pl.tw, F, ld, n_m, nh, ncols, colrow, grid);          \
+        dim3 g((ncols + fft2_rows(h) - 1) / fft2_rows(h), 2 * nh);                                                       \
+        fft_c2r_plan_kernel<h><<<g, fft2_threads(h), fft_plan_smem(h), st>>>(pl.tw, F, ld, n_m, nh, ncols, colrow, grid);          \
         return;                                                                                                                   \
     }
     MAGIC_FFT_PLANS(X)
@@ -473,8 +572,8 @@ inline void launch_fft_r2c(const FftPlan &pl, const R2cArgs &a, int nfields, cud
     const int H = pl.H;
 #define X(h)                                                                                      \
     if (H == h) {                                                                                 \
-        dim3 g((a.n_lev + fft_rows(h) - 1) / fft_rows(h), 2 * a.nh, nfields);                                 \
-        fft_r2c_plan_kernel<h><<<g, fft_threads(h), fft_plan_smem(h), st>>>(pl.tw, a);            \
+        dim3 g((a.n_lev + fft2_rows(h) - 1) / fft2_rows(h), 2 * a.nh, nfields);         \
+        fft_r2c_plan_kernel<h><<<g, fft2_threads(h), fft_plan_smem(h), st>>>(pl.tw, a);            \
         return;                                                                                   \
     }
     MAGIC_FFT_PLANS(X)
