@@ -222,16 +222,27 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
         if (n_r_loc > 48 || level_chunk < n_r_loc) level_chunk = std::min(level_chunk, 32);
     }
     level_chunk = std::min(level_chunk, n_r_loc);
-    int nchunks = (n_r_loc + level_chunk - 1) / level_chunk;
-    int base = n_r_loc / nchunks, rem = n_r_loc % nchunks, pos = 0;
-    for (int c = 0; c < nchunks; c++) {
-        int sz = base + (c < rem ? 1 : 0);
-        rl->chunk_start.push_back(pos);
-        rl->chunk_size.push_back(sz);
-        pos += sz;
+    // Chunk sizes: full chunks of `level_chunk` levels (the GEMM column count 4*npair*n_lev is then a multiple of the 64-wide
+    // tile for level_chunk % 4 == 0) and the remainder either folded into the last chunk (small remainder) or as one short
+    // chunk.  (Balanced sizes such as 15/16 for 257 levels waste 6 % of every N-edge tile: measured 1.00 vs 0.94 ms/level.)
+    {
+        const int nfull = n_r_loc / level_chunk, rem = n_r_loc % level_chunk;
+        int big = level_chunk, small = 0, nbig = nfull, nsmall = 0;  // nbig chunks of `big`, then nsmall of `small`
+        if (rem > 0 && rem <= level_chunk / 4 && nfull >= 1) { small = level_chunk + rem; nbig = nfull - 1; nsmall = 1; }
+        else if (rem > 0) { small = rem; nsmall = 1; }
+        int pos = 0;
+        for (int c = 0; c < nbig + nsmall; c++) {
+            const int sz = c < nbig ? big : small;
+            rl->chunk_start.push_back(pos);
+            rl->chunk_size.push_back(sz);
+            pos += sz;
+        }
+        // lay[0] is the larger layout (it sizes the workspace)
+        if (nbig == 0) { rl->lay_size[0] = small; rl->lay_size[1] = 0; }
+        else if (small > big) { rl->lay_size[0] = small; rl->lay_size[1] = big; }
+        else { rl->lay_size[0] = big; rl->lay_size[1] = small; }
     }
-    rl->lay_size[0] = base + (rem ? 1 : 0);
-    rl->lay_size[1] = rem ? base : 0;
+    const int nchunks = (int)rl->chunk_size.size();
     layout_sizes(h, S, rl->lay_size[0], rl->lay[0]);
     if (buffers_alloc(h, S, rl->lay[0], rl->buf)) { magic_rloop_destroy(rl); return 1; }
     if (layout_bind(h, S, rl->lay[0], rl->buf)) { magic_rloop_destroy(rl); return 1; }

@@ -30,6 +30,11 @@ struct GemmProb {
     int Nvalid;    // real (unpadded) column count: DMMA fragments beyond it are skipped
     int Mlo;       // synthesis: rows (colatitudes) below Mlo hold only negligible table entries and are skipped
     int klo;       // analysis: leading k-tiles of each segment skipped for the same reason (B rows shift accordingly)
+    // Triangular polar skipping: ks0/ks1[f] = first k-tile (absolute index inside segment 0/1) that holds a non-negligible
+    // table entry for the 8-row fragment f of the M dimension (255 = none).  Null = no skipping.  A CTA tile starts each
+    // segment at the minimum over its 16 fragments.  (Skipping the DMMAs per fragment as well was measured: the predicate
+    // state costs the 128-register kernel as much as it saves.)
+    const unsigned char *ks0, *ks1;
 };
 
 // factor applied to a spectral source when assembling synthesis operands (sht_native.f90 wrappers)

@@ -108,6 +108,22 @@ int sht_init(magic_sht *h) {
         MCHECK(cudaMemcpyAsync(h->kmin.data(), d_kmin, sizeof(int) * n_m, cudaMemcpyDeviceToHost, h->stream));
         MCHECK(cudaStreamSynchronize(h->stream));
         cudaFree(d_kmin);
+        // fragment-level tables (MAGIC_POLAR_FRAG=0 keeps the per-order rectangle only)
+        const char *fr = getenv("MAGIC_POLAR_FRAG");
+        if (!fr || atoi(fr) != 0) {
+            h->FS = ((h->NHP / 8 + 15) / 16) * 16 + 16;
+            h->FA = (((l_max / 2 + 1 + 7) / 8 + 15) / 16) * 16 + 16;
+            int *d_ne = nullptr, *d_no = nullptr;
+            if (dev_upload_vec(&d_ne, h->ne) || dev_upload_vec(&d_no, h->no)) return 1;
+            MCHECK(cudaMalloc((void **)&h->d_fskip_syn, (size_t)n_m * 4 * h->FS));
+            MCHECK(cudaMalloc((void **)&h->d_fskip_an, (size_t)n_m * 4 * h->FA));
+            table_fskip_kernel<<<dim3(n_m, 4), 128, 0, h->stream>>>(h->d_tab, h->d_off, d_ne, d_no, nh, h->NHP, h->polar_eps, h->FS, h->FA,
+                                                                    h->d_fskip_syn, h->d_fskip_an);
+            MCHECK(cudaGetLastError());
+            MCHECK(cudaStreamSynchronize(h->stream));
+            cudaFree(d_ne);
+            cudaFree(d_no);
+        }
     }
     // FFT plan
     h->fft.N = h->n_phi;
@@ -132,6 +148,7 @@ int sht_init(magic_sht *h) {
 }
 
 void sht_free(magic_sht *h) {
+    cudaFree(h->d_fskip_syn); cudaFree(h->d_fskip_an);
     cudaFree(h->d_tab); cudaFree(h->d_off); cudaFree(h->d_sinth); cudaFree(h->d_costh); cudaFree(h->d_wgauss);
     cudaFree(h->d_osin2); cudaFree(h->d_lm2l); cudaFree(h->d_lm2m); cudaFree(h->d_lstart); cudaFree(h->d_tw);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -221,6 +238,10 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
                 g.A0 = s == 0 ? Pe : Po;
                 g.M = nh;
                 g.Mlo = (h->kmin[mc] / 8) * 8;
+                if (h->d_fskip_syn) {  // table blocks: 0 P_even, 1 D_odd, 2 P_odd, 3 D_even
+                    g.ks0 = h->d_fskip_syn + ((size_t)mc * 4 + (s == 0 ? 0 : 2)) * h->FS;
+                    g.ks1 = cls == 1 ? h->d_fskip_syn + ((size_t)mc * 4 + (s == 0 ? 1 : 3)) * h->FS : nullptr;
+                }
                 if (cls == 1) {
                     g.A1 = s == 0 ? Do : De;
                     g.kt0 = kt0; g.kt1 = kt1;
@@ -256,11 +277,13 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
                 g.A1 = p == 0 ? De : Do;
                 g.M = Kp;
                 g.klo = h->kmin[mc] / BK;
-                g.A0 += (size_t)g.klo * BK;
-                g.A1 += (size_t)g.klo * BK;
-                g.kt0 = NHP / BK - g.klo;
+                g.kt0 = NHP / BK;  // absolute k-tile counts; the kernel starts each segment at max(klo, fragment minimum)
+                if (h->d_fskip_an) {
+                    g.ks0 = h->d_fskip_an + ((size_t)mc * 4 + (p == 0 ? 0 : 2)) * h->FA;
+                    g.ks1 = cls == 1 ? h->d_fskip_an + ((size_t)mc * 4 + (p == 0 ? 3 : 1)) * h->FA : nullptr;
+                }
                 if (cls == 1) {
-                    g.kt1 = NHP / BK - g.klo;
+                    g.kt1 = NHP / BK;
                     g.B = buf.Bav + (size_t)prob * 2 * NHP * L.Nav;
                     g.C = buf.Cav + L.offCav[prob];
                     g.ldb = g.ldc = L.Nav;
@@ -277,7 +300,7 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
                 int ntn = g.ldb / GEMM_BN, ntm = (Kp + GEMM_BM - 1) / GEMM_BM;
                 for (int mt = 0; mt < ntm; mt++)
                     for (int nt = 0; nt < ntn; nt++) ta.push_back(make_int2(pid, (mt << 16) | nt));
-                L.flops_an += 2.0 * Kp * (double)(g.kt0 + g.kt1) * BK * g.ldb;
+                L.flops_an += 2.0 * Kp * (double)(g.kt0 + g.kt1 - (g.kt1 ? 2 : 1) * g.klo) * BK * g.ldb;
             }
         }
     }

@@ -53,6 +53,8 @@ struct magic_sht {
     std::vector<long long> off;                    // [n_m][4] table block offsets: Pe, Do, Po, De
     std::vector<int> kmin;                         // per mc: first colatitude with non-negligible table entries
     double polar_eps = 1e-40;
+    unsigned char *d_fskip_syn = nullptr, *d_fskip_an = nullptr;  // fragment-level skip tables (table_fskip_kernel), or null
+    int FS = 0, FA = 0;                                           // their strides per table block
     double *d_tab = nullptr;
     long long *d_off = nullptr;
     double *d_sinth = nullptr, *d_costh = nullptr, *d_wgauss = nullptr, *d_osin2 = nullptr;

@@ -91,7 +91,6 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
     const int2 tile = tiles[blockIdx.x];
     const GemmProb pr = probs[tile.x];
     const int m0 = (tile.y >> 16) * GEMM_BM, n0 = (tile.y & 0xffff) * GEMM_BN;
-    const int KT = pr.kt0 + pr.kt1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
@@ -109,10 +108,29 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
         return;
     }
 
+    // ---- k range.  Segment s covers absolute k-tiles [st_s, pr.kt_s): st_s = first tile that holds a non-negligible table
+    //      entry for any of the 16 fragments of this CTA tile (the table of order m is negligible polewards of the turning
+    //      point sin(theta) ~ m/l: a triangle in the (degree, colatitude) plane, of which pr.Mlo / pr.klo only remove the
+    //      rectangle common to all degrees).
+    int st0 = pr.klo, st1 = pr.klo;
+    if (pr.ks0 != nullptr) {
+        auto min16 = [](const unsigned char *p) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(p);
+            const unsigned mn = __vminu4(__vminu4(q.x, q.y), __vminu4(q.z, q.w));
+            return (int)min(min(mn & 255u, (mn >> 8) & 255u), min((mn >> 16) & 255u, mn >> 24));
+        };
+        st0 = max(st0, min(min16(pr.ks0 + (m0 >> 3)), pr.kt0));
+        if (pr.ks1 != nullptr) st1 = max(st1, min16(pr.ks1 + (m0 >> 3)));
+    }
+    st1 = min(st1, pr.kt1);
+    const int n0t = pr.kt0 - st0, KT = n0t + (pr.kt1 - st1);
+    const int kb1 = pr.kt0;  // B row tile of segment 1, tile 0 (the segments are stacked in B)
+
     auto load_stage = [&](int kt, int st) {
         double *As = smem + st * STAGE, *Bs = As + A_TILE;
-        const double *Ab = (kt < pr.kt0) ? pr.A0 + (size_t)kt * BK * (A_KCONTIG ? 1 : lda)
-                                         : pr.A1 + (size_t)(kt - pr.kt0) * BK * (A_KCONTIG ? 1 : lda);
+        const bool seg1 = kt >= n0t;
+        const int ka = seg1 ? st1 + (kt - n0t) : st0 + kt;  // absolute k-tile inside the segment
+        const double *Ab = (seg1 ? pr.A1 : pr.A0) + (size_t)ka * BK * (A_KCONTIG ? 1 : lda);
         if (!A_KCONTIG) {
 #pragma unroll
             for (int c = 0; c < 4; c++) {  // 16 rows x 64 chunks of 2 doubles
@@ -126,7 +144,7 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
                 cp_async16(As + m * LDA_K + (MAGIC_GEMM_SWZ ? kc ^ ((m & 3) << 1) : kc) * 2, Ab + (size_t)(m0 + m) * lda + kc * 2);
             }
         }
-        const int kb = kt < pr.kt0 ? kt + pr.klo : kt + 2 * pr.klo;  // B row tile (skipped leading tiles of each segment)
+        const int kb = seg1 ? kb1 + ka : ka;  // B row tile
         const double *Bb = pr.B + (size_t)kb * BK * pr.ldb + n0;
 #pragma unroll
         for (int c = 0; c < 2; c++) {  // 16 rows x 32 chunks

@@ -68,6 +68,49 @@ __global__ void table_kmin_kernel(const double *__restrict__ tab, const long lon
     if (threadIdx.x == 0) kmin[mc] = best;
 }
 
+// Fragment-level refinement of the polar skipping.  The table of order m is negligible for colatitudes polewards of the
+// turning point sin(theta) ~ m/l, i.e. in a triangle of the (degree, colatitude) plane, not a rectangle.  For every block
+// (mc, b) of the table (rows = degrees j, columns = northern colatitudes k):
+//   syn[(mc*4+b)*FS + f]  = first 16-degree tile holding an entry >= thr in colatitudes [8f, 8f+8)   (synthesis: M = theta)
+//   an [(mc*4+b)*FA + jf] = first 16-colatitude tile holding an entry >= thr in degrees [8jf, 8jf+8) (analysis:  M = degree)
+// 255 = none / padding.  blockIdx = (mc, b); threads stride over fragments.
+__global__ void table_fskip_kernel(const double *__restrict__ tab, const long long *__restrict__ off, const int *__restrict__ ne,
+                                   const int *__restrict__ no, int nh, int NHP, double thr, int FS, int FA,
+                                   unsigned char *__restrict__ syn, unsigned char *__restrict__ an) {
+    const int mc = blockIdx.x, b = blockIdx.y;
+    const int rows = (b == 0 || b == 3) ? ne[mc] : no[mc];
+    const double *base = tab + off[mc * 4 + b];
+    unsigned char *so = syn + ((size_t)mc * 4 + b) * FS, *ao = an + ((size_t)mc * 4 + b) * FA;
+    for (int f = threadIdx.x; f < FS; f += blockDim.x) {
+        int first = 255;
+        if (8 * f < nh) {
+            for (int j = 0; j < rows && first == 255; j++) {
+                const double *r = base + (size_t)j * NHP + 8 * f;
+                bool hit = false;
+#pragma unroll
+                for (int c = 0; c < 8; c++) hit |= (8 * f + c < nh) && fabs(r[c]) >= thr;
+                if (hit) first = j / BK;
+            }
+        }
+        so[f] = (unsigned char)first;
+    }
+    for (int jf = threadIdx.x; jf < FA; jf += blockDim.x) {
+        int first = 255;
+        if (8 * jf < rows) {
+            for (int kt = 0; kt < NHP / BK && first == 255; kt++) {
+                bool hit = false;
+                for (int j = 8 * jf; j < min(rows, 8 * jf + 8); j++) {
+                    const double *r = base + (size_t)j * NHP + kt * BK;
+#pragma unroll
+                    for (int c = 0; c < BK; c++) hit |= (kt * BK + c < nh) && fabs(r[c]) >= thr;
+                }
+                if (hit) first = kt;
+            }
+        }
+        ao[jf] = (unsigned char)first;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Synthesis operand assembly (the pre-scalings of the sht_native.f90 wrappers: l(l+1), or2, i*m, l>lcut masks, and
 // the level masks of rIter.f90:466-622).  One CTA per block of 32 consecutive degrees of one order: lane i owns degree
