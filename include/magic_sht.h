@@ -128,6 +128,11 @@ int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, const magic_
  * (zero unless l_mag_LF and the wall is rotating and conducting). */
 int magic_rloop_set_rotation(magic_rloop *rl, double omega_ma, double omega_ic);
 int magic_rloop_get_torques(const magic_rloop *rl, double *lorentz_torque_ic, double *lorentz_torque_ma);
+/* Nonlinear magnetic boundary products of get_br_v_bcs (nonlinear_bcs.f90:24-74, called at rIter.f90:267-277): the arguments
+ * br_vt_lm_cmb, br_vp_lm_cmb (boundary = 0) / br_vt_lm_icb, br_vp_lm_icb (boundary = 1) of radialLoopG (radialLoop.f90:41),
+ * complex [lm_max] HOST arrays, valid after a run on the rank that holds the boundary level.  Only defined for runs with
+ * l_b_nl_cmb / l_b_nl_icb (stress-free wall + conducting mantle / inner core, Namelists.f90:713-729); an error otherwise. */
+int magic_rloop_get_br_v_bcs(const magic_rloop *rl, int boundary, double *br_vt_lm, double *br_vp_lm);
 /* Stream control + kernel accounting for the benchmark. */
 int magic_rloop_sync(magic_rloop *rl);
 long long magic_rloop_launch_count(const magic_rloop *rl);

@@ -35,6 +35,10 @@ struct magic_rloop {
     double *d_tq_partial = nullptr, *d_torque = nullptr, *h_torque = nullptr;  // Lorentz torques (ic, ma)
     int tq_parts = 0;
     double torque[2] = {0.0, 0.0};
+    // get_br_v_bcs (rIter.f90:267-277): local level index of the CMB / ICB when l_b_nl_cmb / l_b_nl_icb, else -1;
+    // results [cmb vt, cmb vp, icb vt, icb vp] x complex [lm_max] on the device and in pinned host memory
+    int bc_lev[2] = {-1, -1};
+    double *d_brv = nullptr, *h_brv = nullptr;
     bool need_in[S_COUNT] = {false};
     bool need_out[O_COUNT] = {false};
     cudaEvent_t ev[16];
@@ -76,6 +80,8 @@ extern "C" int magic_rloop_destroy(magic_rloop *rl) {
     for (int i = 0; i < S_COUNT; i++) cudaFree(rl->d_in[i]);
     for (int i = 0; i < O_COUNT; i++) cudaFree(rl->d_out[i]);
     cudaFree(rl->d_dtrkc); cudaFree(rl->d_dthkc); cudaFree(rl->d_lev); cudaFree(rl->d_tq_partial); cudaFree(rl->d_torque);
+    cudaFree(rl->d_brv);
+    if (rl->h_brv) cudaFreeHost(rl->h_brv);
     if (rl->h_torque) cudaFreeHost(rl->h_torque);
     for (int i = 0; i < 16; i++) cudaEventDestroy(rl->ev[i]);
     for (auto e : rl->up_done) cudaEventDestroy(e);
@@ -95,9 +101,6 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
     *out = nullptr;
     MCHECK(cudaSetDevice(h->dev));
     const magic_params &P = *pp;
-    if (P.l_mag_nl && ((P.ktopv == 1 && P.l_cond_ma) || (P.kbotv == 1 && P.l_cond_ic)))
-        MFAIL("magic_rloop_create: stress-free + conducting walls need get_br_v_bcs (nonlinear_bcs.f90:24, Namelists.f90:713-729), "
-              "which the batched loop does not produce yet");
     magic_rloop *rl = new magic_rloop();
     rl->h = h;
     rl->p = P;
@@ -261,6 +264,19 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
     rl->tq_parts = (int)(((size_t)h->nh * h->n_phi + NL_THREADS - 1) / NL_THREADS);
     MCHECK(cudaMalloc((void **)&rl->d_tq_partial, sizeof(double) * (size_t)rl->tq_parts * rl->lay_size[0]));
     MCHECK(cudaMalloc((void **)&rl->d_torque, sizeof(double) * 2));
+    {   // l_b_nl_cmb / l_b_nl_icb, Namelists.f90:713-729
+        for (int i = 0; i < n_r_loc; i++) {
+            if (rl->lev[i].nR == 1 && P.l_mag_nl && P.ktopv == 1 && P.l_cond_ma) rl->bc_lev[0] = i;
+            if (rl->lev[i].nR == P.n_r_max && P.l_mag_nl && P.kbotv == 1 && P.l_cond_ic) rl->bc_lev[1] = i;
+        }
+        if (rl->bc_lev[0] >= 0 || rl->bc_lev[1] >= 0) {
+            const size_t nb = sizeof(double) * 8 * (size_t)h->lm_max;
+            MCHECK(cudaMalloc((void **)&rl->d_brv, nb));
+            MCHECK(cudaMemset(rl->d_brv, 0, nb));
+            MCHECK(cudaMallocHost((void **)&rl->h_brv, nb));
+            memset(rl->h_brv, 0, nb);
+        }
+    }
     MCHECK(cudaMallocHost((void **)&rl->h_torque, sizeof(double) * 2));
     MCHECK(cudaMallocHost((void **)&rl->host_dtrkc, sizeof(double) * n_r_loc));
     MCHECK(cudaMallocHost((void **)&rl->host_dthkc, sizeof(double) * n_r_loc));
@@ -393,6 +409,17 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
             }
         }
     }
+    for (int w = 0; w < 2; w++) {  // get_br_v_bcs on the boundary levels (rIter.f90:267-277)
+        const int i = rl->bc_lev[w];
+        if (i < 0) continue;
+        if (!in->b || !in->dw || !in->z) MFAIL("magic_rloop_run: get_br_v_bcs needs b, dw and z");
+        const size_t off = (size_t)i * lm2, o2 = (size_t)w * 2 * lm2;
+        const LevelInfo &Lb = rl->lev[i];
+        if (br_v_bcs_dev(h, in->b + off, in->dw + off, in->z + off, Lb.lcut, Lb.or2 * Lb.orho1, w == 0 ? rl->p.omega_ma : rl->p.omega_ic,
+                         rl->d_brv + o2, rl->d_brv + o2 + lm2))
+            return 1;
+    }
+    if (rl->d_brv) MCHECK(cudaMemcpyAsync(rl->h_brv, rl->d_brv, sizeof(double) * 8 * (size_t)h->lm_max, cudaMemcpyDeviceToHost, h->stream));
     MCHECK(cudaMemcpyAsync(rl->h_torque, rl->d_torque, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stream));
     cudaEventRecord(rl->ev[14], h->stream);
     MCHECK(cudaEventSynchronize(rl->ev[14]));
@@ -484,6 +511,15 @@ extern "C" int magic_rloop_get_torques(const magic_rloop *rl, double *lorentz_to
     if (!rl) MFAIL("null rloop");
     if (lorentz_torque_ic) *lorentz_torque_ic = rl->torque[0];
     if (lorentz_torque_ma) *lorentz_torque_ma = rl->torque[1];
+    return 0;
+}
+extern "C" int magic_rloop_get_br_v_bcs(const magic_rloop *rl, int boundary, double *br_vt_lm, double *br_vp_lm) {
+    if (!rl) MFAIL("null rloop");
+    if (boundary < 0 || boundary > 1) MFAIL("magic_rloop_get_br_v_bcs: boundary must be 0 (CMB) or 1 (ICB)");
+    if (rl->bc_lev[boundary] < 0) MFAIL("magic_rloop_get_br_v_bcs: this loop has no nonlinear magnetic boundary condition there");
+    const size_t n = 2 * (size_t)rl->h->lm_max;
+    if (br_vt_lm) memcpy(br_vt_lm, rl->h_brv + (size_t)boundary * 2 * n, sizeof(double) * n);
+    if (br_vp_lm) memcpy(br_vp_lm, rl->h_brv + (size_t)boundary * 2 * n + n, sizeof(double) * n);
     return 0;
 }
 extern "C" int magic_rloop_sync(magic_rloop *rl) {

@@ -171,6 +171,35 @@ static int anal_call(magic_sht *h, const double *const ins[3], double *const out
     return 0;
 }
 
+int magic::br_v_bcs_dev(magic_sht *h, const double *b, const double *dw, const double *z, int lcut, double fac, double omega,
+                        double *br_vt_lm, double *br_vp_lm) {
+    CallCtx *c;
+    if (call_ctx(h, &c)) return 1;
+    // brc = r^2 B_r is the Q part of torpol_to_spat(b, db, aj) (rIter.f90:606); vtc, vpc the horizontal part of
+    // torpol_to_spat(w, dw, z) (rIter.f90:555-559: on a stress-free level only vrc is overwritten)
+    ScalCol sc{}; sc.t[0] = T_(0, F_DLH); sc.t[1] = TNONE; sc.lmask = LM_ALL;
+    VecPair vp{}; vp.S[0] = T_(1, F_ONE); vp.S[1] = TNONE; vp.T[0] = T_(2, F_ONE); vp.T[1] = TNONE; vp.lmask = LM_ALL;
+    MCHECK(cudaMemcpyAsync(c->L.d_scal, &sc, sizeof(sc), cudaMemcpyHostToDevice, h->stream));
+    MCHECK(cudaMemcpyAsync(c->L.d_vec, &vp, sizeof(vp), cudaMemcpyHostToDevice, h->stream));
+    LevelInfo li{};
+    li.nR = 2; li.lcut = lcut; li.nBc = 0; li.lDeriv = 1; li.nl_on = 1;
+    MCHECK(cudaMemcpyAsync(c->d_lev, &li, sizeof(li), cudaMemcpyHostToDevice, h->stream));
+    const double *src[MAGIC_MAX_SRC];
+    for (int i = 0; i < MAGIC_MAX_SRC; i++) src[i] = nullptr;
+    src[0] = b; src[1] = dw; src[2] = z;
+    if (run_synthesis(h, c->spec, c->L, c->buf, src, c->d_lev, nullptr)) return 1;
+    br_v_product_kernel<<<296, 256, 0, h->stream>>>(c->buf.gin, c->buf.gout, h->nh, h->n_phi, h->d_sinth, fac, omega);
+    h->launches++;
+    MCHECK(cudaGetLastError());
+    li.lcut = h->l_max;  // spat_to_sphertor(..., l_max), nonlinear_bcs.f90:72
+    MCHECK(cudaMemcpyAsync(c->d_lev, &li, sizeof(li), cudaMemcpyHostToDevice, h->stream));
+    if (run_analysis(h, c->spec, c->L, c->buf, c->d_lev, nullptr)) return 1;
+    const size_t sb = sizeof(double) * 2 * h->lm_max;
+    MCHECK(cudaMemcpyAsync(br_vt_lm, c->buf.nl_v, sb, cudaMemcpyDeviceToDevice, h->stream));
+    MCHECK(cudaMemcpyAsync(br_vp_lm, c->buf.nl_v + 2 * (size_t)h->lm_max, sb, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
 extern "C" int magic_scal_to_spat(magic_sht *h, const double *Slm, double *fieldc, int lcut) {
     const double *srcs[] = {Slm};
     Term q[2] = {T_(0, F_ONE), TNONE}, z[2] = {TNONE, TNONE};

@@ -140,7 +140,7 @@ int sht_init(magic_sht *h) {
     MCHECK(cudaFuncSetAttribute(extract_td_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MCHECK(cudaFuncSetAttribute(extract_td_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MCHECK(cudaFuncSetAttribute(extract_td_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    MCHECK(cudaFuncSetAttribute(synth_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_WARPS * MAGIC_MAX_SRC * 32 * (int)sizeof(double2)));
+    MCHECK(cudaFuncSetAttribute(synth_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_WARPS * MAGIC_MAX_SRC * PREP_LD * (int)sizeof(double2)));
     MCHECK(fft_setup_attributes(h->fft.H));
     MCHECK(cudaStreamSynchronize(h->stream));
     cudaFree(d_pmm);
@@ -360,7 +360,7 @@ int run_synthesis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Bu
         if (src[i]) a.nsrc = i + 1;
     if (ev) cudaEventRecord(ev[0], h->stream);
     if ((L.ncol_s || L.npair_v) && L.n_prep_blks) {
-        size_t smem = (size_t)PREP_WARPS * a.nsrc * 32 * sizeof(double2);
+        size_t smem = (size_t)PREP_WARPS * a.nsrc * PREP_LD * sizeof(double2);
         dim3 grid(L.n_prep_blks, (L.n_lev + PREP_WARPS - 1) / PREP_WARPS);
         synth_prep_kernel<<<grid, PREP_WARPS * 32, smem, h->stream>>>(a);
         h->launches++;

@@ -120,6 +120,10 @@ int run_synthesis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Bu
                   const LevelInfo *d_lev, cudaEvent_t *ev);
 int run_analysis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buffers &buf, const LevelInfo *d_lev, cudaEvent_t *ev,
                  bool extract = true);
+// get_br_v_bcs (nonlinear_bcs.f90:24-74) for one boundary level, device pointers throughout: b, dw, z are the level's spectra
+// (complex [lm_max]); writes br_vt_lm, br_vp_lm (complex [lm_max]).  Runs on h->stream with the per-call single-level pipeline.
+int br_v_bcs_dev(magic_sht *h, const double *b, const double *dw, const double *z, int lcut, double fac, double omega,
+                 double *br_vt_lm, double *br_vp_lm);
 int sht_init(magic_sht *h);
 void sht_free(magic_sht *h);
 

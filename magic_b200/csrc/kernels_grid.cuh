@@ -334,6 +334,29 @@ __global__ void grid_export_kernel(const double *__restrict__ g /*[2][nh][nphi]*
     }
 }
 
+// get_br_v_bcs products (nonlinear_bcs.f90:58-66) on one boundary level: gin holds br, vt, vp (fields 0,1,2 of a single-level
+// synthesis, E/O layout); gout receives br_vt = fac br vt and br_vp = br (fac vp - omega sin^2 theta) as the (N+S, N-S) rows
+// the r2c FFT expects, fields 1 and 2; field 0 (scalar analysis column, unused) is zeroed.
+__global__ void br_v_product_kernel(const double *__restrict__ gin, double *__restrict__ gout, int nh, int n_phi,
+                                    const double *__restrict__ sinth, double fac, double omega) {
+    const size_t plane = (size_t)nh * n_phi;
+    for (size_t pt = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pt < plane; pt += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(pt / n_phi);
+        const double st2 = sinth[k] * sinth[k];
+        const double bre = gin[pt], bro = gin[plane + pt], vte = gin[2 * plane + pt], vto = gin[3 * plane + pt];
+        const double vpe = gin[4 * plane + pt], vpo = gin[5 * plane + pt];
+        const double brn = bre + bro, brs = bre - bro, vtn = vte + vto, vts = vte - vto, vpn = vpe + vpo, vps = vpe - vpo;
+        const double tn = fac * brn * vtn, ts = fac * brs * vts;
+        const double pn = brn * (fac * vpn - omega * st2), ps = brs * (fac * vps - omega * st2);
+        gout[pt] = 0.0;
+        gout[plane + pt] = 0.0;
+        gout[2 * plane + pt] = tn + ts;
+        gout[3 * plane + pt] = tn - ts;
+        gout[4 * plane + pt] = pn + ps;
+        gout[5 * plane + pt] = pn - ps;
+    }
+}
+
 __global__ void grid_import_kernel(const double *__restrict__ f, double *__restrict__ g, int nh, int n_phi, int nlat_padded) {
     __shared__ double te[32][33], to[32][33];
     int k0 = blockIdx.y * 32, j0 = blockIdx.x * 32;

@@ -138,16 +138,17 @@ __device__ __forceinline__ bool level_enabled(int lmask, const LevelInfo &L) {
     return true;
 }
 
-constexpr int PREP_WARPS = 8;
+constexpr int PREP_WARPS = 8;   // = levels per CTA
+constexpr int PREP_LD = 33;     // padded degree stride of the staging tile
 
-__device__ __forceinline__ double2 eval_terms(const Term *t, const double2 *xs /* [src][32] of this warp */, int lane, int l, int m,
-                                              double or2) {
+__device__ __forceinline__ double2 eval_terms(const Term *t, const double2 *xs /* staging tile of this level */, int d, int src_stride,
+                                              int l, int m, double or2) {
     double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         int ft = t[i].ftype;
         if (ft == F_NONE) continue;
-        double2 x = xs[t[i].src * 32 + lane];
+        double2 x = xs[t[i].src * src_stride + d];
         double dlh = (double)(l * (l + 1));
         if (ft == F_ONE) { acc.x += x.x; acc.y += x.y; }
         else if (ft == F_DLH) { acc.x += dlh * x.x; acc.y += dlh * x.y; }
@@ -158,62 +159,71 @@ __device__ __forceinline__ double2 eval_terms(const Term *t, const double2 *xs /
     return acc;
 }
 
+// CTA (x, y): degree block blks[x] = (mc, jt), levels y*8 .. y*8+7.
+//   phase 1: warp w reads level y*8+w, lane = degree: every source is one 512-byte request; the values go to a shared tile
+//            xs[src][level][degree];
+//   phase 2: thread (degree d = tid/8, level lv = tid%8) evaluates all columns of its (degree, level) and stores them: the 8
+//            lanes of a degree write 128 contiguous bytes of one operand row (the first version let every lane of a warp
+//            write 16 bytes into a different row: 32 half-used sectors per store, 2.4 TB/s).
 __global__ void __launch_bounds__(PREP_WARPS * 32) synth_prep_kernel(SynthPrepArgs a) {
     extern __shared__ __align__(16) double2 prep_sm[];
     const int2 blk = a.blks[blockIdx.x];
     const int mc = blk.x, jt = blk.y, m = mc * a.minc;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int l = m + 32 * jt + lane, par = lane & 1, r = lane >> 1;
-    const bool valid_l = l <= a.l_max;
-    const size_t lm = (size_t)a.lstart[mc] + (l - m);
-    const int ne = (a.l_max - m) / 2 + 1, no = (a.l_max - m + 1) / 2;
-    const int K_par = par == 0 ? ne : no, K_oth = par == 0 ? no : ne;
-    const bool tile_ok = jt < (K_par + BK - 1) / BK;  // the k-tile this degree block maps to exists for my parity
-    const int pP = mc * 2 + par, pD = mc * 2 + (1 - par);
-    const int ktD = (K_oth + BK - 1) / BK + jt;       // D rows of problem pD come after its P rows
-    double2 *xs = prep_sm + (size_t)warp * a.nsrc * 32;
-    double *rowS = a.Bs + (a.ncol_s ? a.offBs[pP] : 0) + (size_t)(jt * BK + r) * a.Ns;
-    double *rowVP = a.Bv + (a.npair_v ? a.offBv[pP] : 0) + (size_t)(jt * BK + r) * a.Nv;
-    double *rowVD = a.Bv + (a.npair_v ? a.offBv[pD] : 0) + (size_t)(ktD * BK + r) * a.Nv;
-    const double dm = (double)m;
-    for (int lev = blockIdx.y * PREP_WARPS + warp; lev < a.n_lev; lev += PREP_WARPS * gridDim.y) {
-        const LevelInfo L = a.lev[lev];
-        // stage all sources of this (level, degree block): loads first, then the shared-memory writes
+    const int lev0 = blockIdx.y * PREP_WARPS;
+    const int src_stride = PREP_WARPS * PREP_LD;
+    {   // ---- phase 1
+        const int lev = lev0 + warp, l = m + 32 * jt + lane;
+        const size_t lm = (size_t)a.lstart[mc] + (l - m);
+        const bool ok = lev < a.n_lev && l <= a.l_max;
         double2 x[MAGIC_MAX_SRC];
 #pragma unroll
         for (int sidx = 0; sidx < MAGIC_MAX_SRC; sidx++) {
             x[sidx] = make_double2(0.0, 0.0);
-            if (sidx < a.nsrc && a.src[sidx] != nullptr && valid_l)
+            if (sidx < a.nsrc && a.src[sidx] != nullptr && ok)
                 x[sidx] = *reinterpret_cast<const double2 *>(a.src[sidx] + 2 * ((size_t)lev * a.lm_max + lm));
         }
 #pragma unroll
         for (int sidx = 0; sidx < MAGIC_MAX_SRC; sidx++)
-            if (sidx < a.nsrc) xs[sidx * 32 + lane] = x[sidx];
-        __syncwarp();
-        if (tile_ok) {
-            const bool on = valid_l && l <= L.lcut;
-            for (int c = 0; c < a.ncol_s; c++) {
-                const ScalCol sc = a.scal[c];
-                double2 v = make_double2(0.0, 0.0);
-                if (on && level_enabled(sc.lmask, L)) v = eval_terms(sc.t, xs, lane, l, m, L.or2);
-                *reinterpret_cast<double2 *>(rowS + 2 * ((size_t)c * a.n_lev + lev)) = v;
-            }
-            for (int pr = 0; pr < a.npair_v; pr++) {
-                const VecPair vp = a.vec[pr];
-                double2 S = make_double2(0.0, 0.0), T = S;
-                if (on && l > 0 && level_enabled(vp.lmask, L)) {
-                    S = eval_terms(vp.S, xs, lane, l, m, L.or2);
-                    T = eval_terms(vp.T, xs, lane, l, m, L.or2);
-                }
-                // Vtheta = sum (S D + i m T P), Vphi = sum (i m S P - T D)  
-                const size_t ct = 2 * ((size_t)(2 * pr) * a.n_lev + lev), cp = 2 * ((size_t)(2 * pr + 1) * a.n_lev + lev);
-                *reinterpret_cast<double2 *>(rowVP + ct) = make_double2(-dm * T.y, dm * T.x);
-                *reinterpret_cast<double2 *>(rowVP + cp) = make_double2(-dm * S.y, dm * S.x);
-                *reinterpret_cast<double2 *>(rowVD + ct) = S;
-                *reinterpret_cast<double2 *>(rowVD + cp) = make_double2(-T.x, -T.y);
-            }
+            if (sidx < a.nsrc) prep_sm[(sidx * PREP_WARPS + warp) * PREP_LD + lane] = x[sidx];
+    }
+    __syncthreads();
+    // ---- phase 2
+    const int lv = threadIdx.x & (PREP_WARPS - 1), d = threadIdx.x >> 3, lev = lev0 + lv;
+    if (lev >= a.n_lev) return;
+    const int l = m + 32 * jt + d, par = d & 1, r = d >> 1;
+    const bool valid_l = l <= a.l_max;
+    const int ne = (a.l_max - m) / 2 + 1, no = (a.l_max - m + 1) / 2;
+    const int K_par = par == 0 ? ne : no, K_oth = par == 0 ? no : ne;
+    if (jt >= (K_par + BK - 1) / BK) return;  // the k-tile this degree block maps to does not exist for my parity
+    const int pP = mc * 2 + par, pD = mc * 2 + (1 - par);
+    const int ktD = (K_oth + BK - 1) / BK + jt;  // D rows of problem pD come after its P rows
+    double *rowS = a.Bs + (a.ncol_s ? a.offBs[pP] : 0) + (size_t)(jt * BK + r) * a.Ns;
+    double *rowVP = a.Bv + (a.npair_v ? a.offBv[pP] : 0) + (size_t)(jt * BK + r) * a.Nv;
+    double *rowVD = a.Bv + (a.npair_v ? a.offBv[pD] : 0) + (size_t)(ktD * BK + r) * a.Nv;
+    const double dm = (double)m;
+    const LevelInfo L = a.lev[lev];
+    const double2 *xs = prep_sm + lv * PREP_LD;
+    const bool on = valid_l && l <= L.lcut;
+    for (int c = 0; c < a.ncol_s; c++) {
+        const ScalCol sc = a.scal[c];
+        double2 v = make_double2(0.0, 0.0);
+        if (on && level_enabled(sc.lmask, L)) v = eval_terms(sc.t, xs, d, src_stride, l, m, L.or2);
+        *reinterpret_cast<double2 *>(rowS + 2 * ((size_t)c * a.n_lev + lev)) = v;
+    }
+    for (int pr = 0; pr < a.npair_v; pr++) {
+        const VecPair vp = a.vec[pr];
+        double2 S = make_double2(0.0, 0.0), T = S;
+        if (on && l > 0 && level_enabled(vp.lmask, L)) {
+            S = eval_terms(vp.S, xs, d, src_stride, l, m, L.or2);
+            T = eval_terms(vp.T, xs, d, src_stride, l, m, L.or2);
         }
-        __syncwarp();
+        // Vtheta = sum (S D + i m T P), Vphi = sum (i m S P - T D)  
+        const size_t ct = 2 * ((size_t)(2 * pr) * a.n_lev + lev), cp = 2 * ((size_t)(2 * pr + 1) * a.n_lev + lev);
+        *reinterpret_cast<double2 *>(rowVP + ct) = make_double2(-dm * T.y, dm * T.x);
+        *reinterpret_cast<double2 *>(rowVP + cp) = make_double2(-dm * S.y, dm * S.x);
+        *reinterpret_cast<double2 *>(rowVD + ct) = S;
+        *reinterpret_cast<double2 *>(rowVD + cp) = make_double2(-T.x, -T.y);
     }
 }
 

@@ -133,6 +133,14 @@ class RadialLoop:
         check(self.lib.magic_rloop_get_torques(self._h, byref(a), byref(b)))
         return a.value, b.value
 
+    def br_v_bcs(self, boundary):
+        """(br_vt_lm, br_vp_lm) of get_br_v_bcs (nonlinear_bcs.f90:24-74) for boundary 'CMB' or 'ICB' after a run."""
+        n = self.sht.lm_max
+        a, b = np.zeros(n, dtype=np.complex128), np.zeros(n, dtype=np.complex128)
+        check(self.lib.magic_rloop_get_br_v_bcs(self._h, c_int({"CMB": 0, "ICB": 1}[boundary]), a.ctypes.data_as(c_void_p),
+                                                b.ctypes.data_as(c_void_p)))
+        return a, b
+
     def sync(self):
         check(self.lib.magic_rloop_sync(self._h))
 

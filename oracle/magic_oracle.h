@@ -155,6 +155,9 @@ typedef struct {
     orc_cplx *dwdt, *dzdt, *dpdt, *dsdt, *dxidt, *dbdt, *djdt, *dVxVhLM, *dVxBhLM, *dVSrLM, *dVXirLM;
     double *dtrkc, *dthkc; /* [n_r] */
     double *lorentz_torque_ic, *lorentz_torque_ma; /* scalars (rIter.f90:279-292, outRot.f90:423-483); may be NULL */
+    /* get_br_v_bcs products [lm_max] (rIter.f90:267-277, nonlinear_bcs.f90:24-74): written when the loop holds the CMB / ICB
+     * level and the run has l_b_nl_cmb / l_b_nl_icb (Namelists.f90:713-729); may be NULL */
+    orc_cplx *br_vt_lm_cmb, *br_vp_lm_cmb, *br_vt_lm_icb, *br_vp_lm_icb;
 } orc_fields_out;
 
 /* Executes the body of `do nR=nRstart,nRstop` (rIter.f90:190-444) for n_r levels, with all output

@@ -57,7 +57,9 @@ class _FieldsIn(C.Structure):
 
 class _FieldsOut(C.Structure):
     _fields_ = [(n, c_void_p) for n in _OUT_NAMES] + [("dtrkc", c_void_p), ("dthkc", c_void_p),
-                                                       ("lorentz_torque_ic", c_void_p), ("lorentz_torque_ma", c_void_p)]
+                                                       ("lorentz_torque_ic", c_void_p), ("lorentz_torque_ma", c_void_p),
+                                                       ("br_vt_lm_cmb", c_void_p), ("br_vp_lm_cmb", c_void_p),
+                                                       ("br_vt_lm_icb", c_void_p), ("br_vp_lm_icb", c_void_p)]
 
 
 def _load(fast):
@@ -295,6 +297,9 @@ class Oracle:
         tq = np.zeros(2)
         fout.lorentz_torque_ic = tq.ctypes.data
         fout.lorentz_torque_ma = tq.ctypes.data + 8
+        for nm in ("br_vt_lm_cmb", "br_vp_lm_cmb", "br_vt_lm_icb", "br_vp_lm_icb"):  # get_br_v_bcs, rIter.f90:267-277
+            out[nm] = np.zeros(self.lm_max, dtype=np.complex128)
+            setattr(fout, nm, _p(out[nm]))
         self.lib.orc_radial_loop(self.h, C.byref(params), C.byref(rad), c_int(n_r), C.byref(fin), C.byref(fout),
                                  c_double(time))
         out["lorentz_torque_ic"], out["lorentz_torque_ma"] = float(tq[0]), float(tq[1])

@@ -144,15 +144,38 @@ def test_hydro_bench_anel_shape():
     compare(o, p, rad, got, ref, ex, HYDRO_OUT)
 
 
-def test_unsupported_boundary_physics_fails_loudly():
-    from magic_b200 import MagicError, RadialLoop, Sht
-    from magic_b200.workload import make_params, make_radial
+def test_stress_free_conducting_walls_get_br_v_bcs():
+    """l_b_nl_cmb / l_b_nl_icb (stress-free walls + conducting mantle / inner core, Namelists.f90:713-729): the boundary
+    levels also deliver get_br_v_bcs (nonlinear_bcs.f90:24-74, rIter.f90:267-277), the products the magnetic boundary
+    conditions of updateB use.  Rotating walls so that the omega * sin^2(theta) term is exercised."""
+    tw = dict(l_cond_ic=1, l_cond_ma=1, l_rot_ic=1, l_rot_ma=1, omega_ic=0.37, omega_ma=-0.21)
+    from magic_b200 import RadialLoop, Sht
+    from magic_b200.workload import make_fields, make_params, make_radial
+    from oracle.oracle import Oracle
+    o = Oracle(16)
     s = Sht(16)
-    p = make_params("mhd", 33)
-    p.l_cond_ic = 1
-    p.kbotv = 1  # stress-free + conducting inner core -> l_b_nl_icb (Namelists.f90:713-720)
-    with pytest.raises(MagicError, match="get_br_v_bcs"):
-        RadialLoop(s, p, make_radial(33, 16))
+    p = make_params("mhd", 33, ktopv=1, kbotv=1)
+    for k, v in tw.items():
+        setattr(p, k, v)
+    levels = np.array([1, 2, 17, 32, 33])
+    rad = {k: np.ascontiguousarray(v[levels - 1]) for k, v in make_radial(33, 16).items()}
+    fields = make_fields("mhd", o.lm2l, o.lm2m, len(levels), 11)
+    rl = RadialLoop(s, p, rad)
+    got = rl.radialLoop(fields)
+    ref = o.radial_loop(oracle_params(p), rad, fields)
+    for bc in ("cmb", "icb"):
+        vt, vp = rl.br_v_bcs(bc.upper())
+        assert np.linalg.norm(ref["br_vt_lm_" + bc]) > 0 and np.linalg.norm(ref["br_vp_lm_" + bc]) > 0
+        assert rel_l2(vt, ref["br_vt_lm_" + bc]) < TOL and rel_l2(vp, ref["br_vp_lm_" + bc]) < TOL, bc
+    for nm in ("dbdt", "djdt", "dVxBhLM"):
+        assert rel_l2(got[nm][1:4], ref[nm][1:4]) < 1e-11, nm
+    # a loop without the boundary level, or without the physics, has no such products
+    rl2 = RadialLoop(s, make_params("mhd", 33), rad)
+    from magic_b200 import MagicError
+    with pytest.raises(MagicError, match="no nonlinear magnetic boundary"):
+        rl2.br_v_bcs("CMB")
+    rl.finalize()
+    rl2.finalize()
     s.finalize_sht()
 
 
