@@ -237,6 +237,17 @@ __device__ __forceinline__ void twiddle_powers(double2 *w) {
     if (RADIX > 5) { w[5] = cmul(w[4], w[1]); w[6] = cmul(w[3], w[3]); w[7 < RADIX ? 7 : 0] = cmul(w[4], w[3]); }
 }
 
+// experiment knobs: minimum resident CTAs per SM handed to __launch_bounds__ (undefined = leave the register choice to ptxas)
+#ifdef MAGIC_FFT_MINB_C
+#define MAGIC_FFT_LB_C(H) __launch_bounds__(fft2_threads(H), MAGIC_FFT_MINB_C)
+#else
+#define MAGIC_FFT_LB_C(H) __launch_bounds__(fft2_threads(H))
+#endif
+#ifdef MAGIC_FFT_MINB_R
+#define MAGIC_FFT_LB_R(H) __launch_bounds__(fft2_threads(H), MAGIC_FFT_MINB_R)
+#else
+#define MAGIC_FFT_LB_R(H) __launch_bounds__(fft2_threads(H))
+#endif
 // first-pass butterfly b of a row (S = 1: p = b, outputs at 8b..8b+7 for radix 8) written to shared memory
 template <int H, int R1>
 __device__ __forceinline__ void first_pass_out(double2 *row, const double2 *__restrict__ tw, int b, const double2 *in, double sg) {
@@ -254,7 +265,7 @@ __device__ __forceinline__ void first_pass_out(double2 *row, const double2 *__re
 }
 
 template <int H>
-__global__ void __launch_bounds__(fft2_threads(H)) fft_c2r_plan_kernel(const double2 *__restrict__ tw, const double *__restrict__ F, int ld,
+__global__ void MAGIC_FFT_LB_C(H) fft_c2r_plan_kernel(const double2 *__restrict__ tw, const double *__restrict__ F, int ld,
                                                                     int n_m, int nh, int ncols, const int *__restrict__ colrow,
                                                                     double *__restrict__ grid) {
     constexpr int R = fft2_rows(H), NT = fft2_threads(H), N = 2 * H, ROWLEN = fft2_rowlen(H);
@@ -341,7 +352,7 @@ __global__ void __launch_bounds__(fft2_threads(H)) fft_c2r_plan_kernel(const dou
 }
 
 template <int H>
-__global__ void __launch_bounds__(fft2_threads(H)) fft_r2c_plan_kernel(const double2 *__restrict__ tw, R2cArgs a) {
+__global__ void MAGIC_FFT_LB_R(H) fft_r2c_plan_kernel(const double2 *__restrict__ tw, R2cArgs a) {
     constexpr int R = fft2_rows(H), NT = fft2_threads(H), N = 2 * H, ROWLEN = fft2_rowlen(H);
     constexpr int R1 = fft_pick_radix(H), NB1 = H / R1;
     constexpr int RL = fft_last_radix(H), SL = H / RL, NIL = (SL + 1) / 2;
