@@ -241,7 +241,7 @@ def run_magic(args, gs):
     rad = make_radial(n_r_max, gs["l_max"], nRstart=tr.nRstart, nRstop=tr.nRstop)
     chunk = args.level_chunk
     if chunk == 0 and gs["l_max"] >= 1000:
-        chunk = 16 if world == 1 else 0  # N=1 keeps 86 GB of containers resident next to the workspace; 16 = the ncu-profiled shape
+        chunk = 16  # the ncu-profiled shape (also what the library's auto rule picks at this truncation)
     rl = RadialLoop(sht, p, rad, level_chunk=chunk)
 
     fin = {"w": flow_R[0], "dw": flow_R[1], "ddw": flow_R[2], "z": flow_R[3], "dz": flow_R[4], "s": s_R[0],
@@ -374,9 +374,10 @@ def run_magic(args, gs):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "legendre_gemm_kernel (FP64 DMMA.8x8x4)", "achieved": leg_tflops,
                          "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": leg_tflops / FP64_PEAK_TFLOPS,
-                         # dram__bytes_read+write of the synthesis launch for a 16-level chunk at l_max=1023
-                         # (profiles/r01/ncu_all_l1023_details_final.csv); null for shapes that were not captured
-                         "traffic": 14.56e9 if (gs["l_max"] == 1023 and chunk == 16) else None,
+                         # dram__bytes_read+write per launch for a 16-level chunk at l_max=1023, mean of the synthesis
+                         # (8.60 + 5.58 GB) and the analysis launch (13.37 + 1.34 GB) of
+                         # profiles/r01/ncu_all_l1023_details_session2.csv; null for shapes that were not captured
+                         "traffic": 14.45e9 if (gs["l_max"] == 1023 and chunk in (0, 16)) else None,
                          "peak_source": "measured DMMA m8n8k4 loop, tools/fp64_peak.cu -> profiles/fp64_peak_r01.json "
                                         "(MEASURED_PEAKS.json carries no FP64 figure)",
                          "share_of_step": leg_ms / ms_step},

@@ -220,9 +220,11 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
         double per_level = 8.0 * ((double)probe.szBs + probe.szBv + probe.szFs + probe.szFv + probe.szBas + probe.szBav + probe.szCas + probe.szCav) +
                            8.0 * 2.0 * h->nh * h->n_phi * (S.nfield_in + S.nfield_out);
         level_chunk = (int)std::max(1.0, std::min((double)n_r_loc, 0.6 * (double)free_b / per_level));
-        // measured: the analysis GEMM loses 15-20 % at 64-level chunks (N' = 768), and a 33-level slab split into 17+16
-        // costs more in tile quantisation than it saves: one chunk up to 48 levels, else chunks of at most 32
-        if (n_r_loc > 48 || level_chunk < n_r_loc) level_chunk = std::min(level_chunk, 32);
+        // measured at l_max=1023 (GEMM ms per level): 16-level chunks 1.65, 32-level chunks 1.78, 64-level chunks > 2.0 --
+        // so 16 levels whenever that still gives the synthesis GEMM >= 20 waves of tiles, else 32 (small truncations are
+        // launch-bound and want the wider batch)
+        const long long tiles16 = (long long)h->n_m * 2 * ((h->nh + GEMM_BM - 1) / GEMM_BM) * ((4LL * std::max(1, (int)S.vec.size()) * 16 + GEMM_BN - 1) / GEMM_BN);
+        level_chunk = std::min(level_chunk, tiles16 >= 20LL * 2 * 148 ? 16 : 32);
     }
     level_chunk = std::min(level_chunk, n_r_loc);
     // Chunk sizes: full chunks of `level_chunk` levels (the GEMM column count 4*npair*n_lev is then a multiple of the 64-wide
