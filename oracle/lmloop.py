@@ -4,30 +4,36 @@ Why it exists: the reference pins the radial-loop hot path (SHT, get_nl, get_td,
 energy time series of its sample runs (samples/*/reference.out, compared at rtol 1e-8 by samples/*/unitTest.py).  The
 Fortran host cannot be built in this image (no Fortran compiler, no MPI), so this module restates the part of the host
 that surrounds the radial loop -- start fields, `finish_explicit_assembly`, the CN/AB2 right-hand sides, the implicit
-solves of `LMLoop` and the energy diagnostics -- for the Boussinesq / Chebyshev / CNAB2 / "WP" path that
-`samples/dynamo_benchmark` runs.  The radial loop itself is a callable handed in by the test: the CPU oracle or the CUDA
-library through the C ABI.  With either, 100 steps must reproduce reference.out / referenceMag.out.
+solves of `LMLoop` and the energy diagnostics -- for the Chebyshev / CNAB2 / "WP" (pressure formulation, separate
+matrices) path that `samples/dynamo_benchmark` (Boussinesq MHD, rigid insulating walls) and `samples/hydro_bench_anel`
+(anelastic polytropic hydro, stress-free walls, angular-momentum correction, n_cheb_max < n_r_max) run.  The radial loop
+itself is a callable handed in by the test: the CPU oracle or the CUDA library through the C ABI.  With either, the
+energy series of reference.out / referenceMag.out must be reproduced at the autotest tolerance.
 
 It is NOT on the product path (magic_b200/ never imports oracle/); the product keeps the Fortran host.
 
 Restated reference routines (file:line relative to /root/reference/src):
   radial grid, Chebyshev matrices      radial.f90 (r, or1, or2, rgrav :628), chebyshev.f90 (rMat, drMat, d2rMat, d3rMat)
+  polytropic reference state           radial.f90:625-729 (adiabatic branch), :759-767 (ViscHeatFac), preCalculations.f90:313-330
   start fields                         startFields.f90:281-330, init_fields.f90:373-560 (initS, init_s1=llmm),
                                        :1129-1188 (initB, init_b1=3), :2211-2497 (ps_cond, entropy diffusion branch)
   time scheme                          multistep_schemes.f90:195-206 (CNAB2 weights), :430-470 (set_imex_rhs),
                                        :558-590 (rotate_imex)
   finish_explicit_assembly             LMLoop.f90:390-453, updateS.f90:543-601, updateB.f90:1005-1041
   updateS / get_sMat / rhs_imp         updateS.f90:156-342, :1065-1212, :658-756
-  updateZ / get_zMat / rhs_imp         updateZ.f90:191-488, :1820-1964, :760-1025
+  updateZ / get_zMat / rhs_imp         updateZ.f90:191-488, :1820-1964, :760-1025 (incl. l_correct_AMz / l_correct_AMe :840-915,
+                                       get_angular_moment outRot.f90:485-543)
   updateWP / get_wpMat / rhs_imp       updateWP.f90:255-634, :1978-2171, :1089-1336
   updateB / get_bMat / rhs_imp         updateB.f90:226-694, :1785-2171, :1520-1652
   dt_courant                           courant.f90:277-346
   get_e_kin / get_e_mag                kinetic_energy.f90:95-230, magnetic_energy.f90:262-470
   step order                           step_time.f90:480-763
 
-The reference solves for Chebyshev coefficients with collocation matrices rMat/drMat/... and transforms back
-(costf1); with n_cheb_max = n_r_max this is algebraically the same as solving for the grid values with the
-differentiation matrices D_k = d^kT . T^-1 used here (differences are rounding only).
+The reference solves for Chebyshev coefficients with collocation matrices rMat/drMat/... and transforms back (costf1).
+Here the operators are written for grid values with the differentiation matrices D_k = d^kT . T^-1 and mapped to
+coefficient space by one product with the basis matrix (M_coef = M_grid . B0), which is algebraically the same matrix;
+the reference's dealiasing -- boundary rows ignore the modes >= n_cheb_max and those modes are zeroed after the solve --
+is applied in coefficient space exactly as in get_sMat / updateS (differences are rounding only).
 """
 import numpy as np
 
@@ -35,9 +41,10 @@ import numpy as np
 class ChebShell:
     """Gauss-Lobatto radial grid of a spherical shell, nR=1 at the CMB (radial.f90, chebyshev.f90, no mapping)."""
 
-    def __init__(self, n_r_max, radratio):
+    def __init__(self, n_r_max, radratio, n_cheb_max=None):
         N = n_r_max
         self.n_r_max = N
+        self.n_cheb_max = N if n_cheb_max is None else n_cheb_max
         self.r_cmb = 1.0 / (1.0 - radratio)
         self.r_icb = self.r_cmb - 1.0
         k = np.arange(N)
@@ -63,6 +70,11 @@ class ChebShell:
         self.D2 = (d2 * drx ** 2) @ Tinv
         self.D3 = (d3 * drx ** 3) @ Tinv
         self.T, self.Tinv = T, Tinv
+        # basis of the reference's coefficient space: f = B0 c with rnorm = sqrt(2/(N-1)) and boundary_fac = 1/2 on the
+        # first and last mode (chebyshev.f90; the same convention as costf1)
+        wts = np.ones(N)
+        wts[0] = wts[-1] = 0.5
+        self.B0 = T * wts[None, :] * np.sqrt(2.0 / (N - 1))
         self.or1 = 1.0 / self.r
         self.or2 = self.or1 ** 2
         # rInt_R (integration.f90): exact integral of the Chebyshev interpolant
@@ -72,7 +84,29 @@ class ChebShell:
         self.w_int = 0.5 * (self.r_cmb - self.r_icb) * (wn @ Tinv)
 
     def rInt_R(self, f):
-        return float(self.w_int @ f)
+        return self.w_int @ f
+
+    def solve(self, M, rhs, bc_rows):
+        """Solve like the reference: unknowns = Chebyshev coefficients, boundary rows blind to modes >= n_cheb_max, those
+        modes zeroed after the solve (e.g. get_sMat updateS.f90:1107-1112 and updateS :311-318); returns grid values.
+        M acts on grid values of nblk stacked fields ([nblk*N, nblk*N])."""
+        N, nc = self.n_r_max, self.n_cheb_max
+        nblk = M.shape[0] // N
+        Mc = np.empty_like(M)
+        for b in range(nblk):
+            Mc[:, b * N:(b + 1) * N] = M[:, b * N:(b + 1) * N] @ self.B0
+        if nc < N:
+            for row in bc_rows:
+                for b in range(nblk):
+                    Mc[row, b * N + nc:(b + 1) * N] = 0.0
+        f = 1.0 / np.max(np.abs(Mc), axis=1)  # row equilibration like WITH_PRECOND_* (conditioning only)
+        c = np.linalg.solve(Mc * f[:, None], rhs * f[:, None])
+        out = np.empty_like(c)
+        for b in range(nblk):
+            cb = c[b * N:(b + 1) * N].copy()
+            cb[nc:] = 0.0
+            out[b * N:(b + 1) * N] = self.B0 @ cb
+        return out
 
 
 def _cc2real(c, m):
@@ -80,23 +114,47 @@ def _cc2real(c, m):
     return np.where(m == 0, 1.0, 2.0) * (c.real ** 2 + c.imag ** 2)
 
 
-class BoussinesqDynamoHost:
-    """The LM-side of MagIC for a Boussinesq MHD shell with rigid walls, fixed entropy, insulating boundaries,
-    Chebyshev collocation and CN/AB2 -- the setup of samples/dynamo_benchmark/input.nml."""
+class ShellHost:
+    """The LM side of MagIC for a spherical shell with fixed-entropy boundaries, Chebyshev collocation, CN/AB2 and the
+    pressure ("WP") formulation with separate matrices.  Options: polytropic anelastic reference state (strat, polind,
+    g0/g1/g2), rigid (2) or stress-free (1) walls, magnetic field with insulating boundaries, n_cheb_max < n_r_max,
+    l_correct_AMz / l_correct_AMe."""
 
-    def __init__(self, lm2l, lm2m, radial_loop, n_r_max=33, radratio=0.35, ra=1e5, ek=1e-3, pr=1.0, prmag=5.0,
-                 dtmax=1e-4, alpha=0.6, init_s1=404, amp_s1=0.1, init_b1=3, amp_b1=5.0):
+    def __init__(self, lm2l, lm2m, radial_loop, n_r_max=33, n_cheb_max=None, radratio=0.35, ra=1e5, ek=1e-3, pr=1.0,
+                 prmag=5.0, dtmax=1e-4, alpha=0.6, init_s1=404, amp_s1=0.1, init_b1=3, amp_b1=5.0, l_mag=True, ktopv=2,
+                 kbotv=2, strat=0.0, polind=2.0, g0=0.0, g1=1.0, g2=0.0, l_correct_AMz=False, l_correct_AMe=False):
         self.lm2l = np.asarray(lm2l)
         self.lm2m = np.asarray(lm2m)
         self.lm_max = len(self.lm2l)
         self.l_max = int(self.lm2l.max())
-        self.g = g = ChebShell(n_r_max, radratio)
+        self.g = g = ChebShell(n_r_max, radratio, n_cheb_max)
         self.N = n_r_max
         self.radial_loop = radial_loop
+        self.l_mag, self.ktopv, self.kbotv = l_mag, ktopv, kbotv
+        self.l_correct_AMz, self.l_correct_AMe = l_correct_AMz, l_correct_AMe
         self.opr, self.opm = 1.0 / pr, 1.0 / prmag
-        self.BuoFac = ra / pr                 # preCalculations.f90:170
+        self.BuoFac = ra / pr                 # preCalculations.f90:170-176 (lScale=1)
         self.LFfac = 1.0 / (ek * prmag)       # preCalculations.f90:158
-        self.rgrav = g.r / g.r_cmb            # radial.f90:628 with g1=1
+        r, or1, or2 = g.r, g.or1, g.or2
+        self.rgrav = g0 + g1 * r / g.r_cmb + g2 * g.r_cmb ** 2 * or2            # radial.f90:628
+        self.l_anel = strat > 0.0
+        if self.l_anel:   # adiabatic polytropic reference state, radial.f90:673-729
+            self.DissNb = (np.exp(strat / polind) - 1.0) / (g.r_cmb - g.r_icb) / (g0 + 0.5 * g1 * (1.0 + radratio) + g2 / radratio)
+            temp0 = -self.DissNb * (g0 * r + 0.5 * g1 * r ** 2 / g.r_cmb - g2 * g.r_cmb ** 2 * or1) + 1.0 + \
+                self.DissNb * g.r_cmb * (g0 + 0.5 * g1 - g2)
+            dg = g1 / g.r_cmb - 2.0 * g2 * g.r_cmb ** 2 * or1 ** 3
+            self.temp0 = temp0
+            self.rho0 = temp0 ** polind
+            self.beta = -polind * self.DissNb * self.rgrav / temp0
+            self.dbeta = -polind * self.DissNb / temp0 ** 2 * (dg * temp0 + self.DissNb * self.rgrav ** 2)
+            self.dLtemp0 = -self.DissNb * self.rgrav / temp0
+            self.ViscHeatFac = self.DissNb * pr / ra                            # radial.f90:762
+        else:
+            one = np.ones(n_r_max)
+            self.DissNb, self.temp0, self.rho0, self.beta, self.dbeta, self.dLtemp0 = 0.0, one, one, 0 * one, 0 * one, 0 * one
+            self.ViscHeatFac = 0.0
+        self.orho1 = 1.0 / self.rho0
+        self.c_moi_oc = 8.0 / 3.0 * np.pi * g.rInt_R(r ** 4 * self.rho0)         # preCalculations.f90:329-330
         self.alpha = alpha
         self.dtmax = dtmax
         self.dt = np.array([dtmax, dtmax])    # startFields.f90:301
@@ -111,26 +169,26 @@ class BoussinesqDynamoHost:
         self.bots = np.zeros(lm_max, dtype=np.complex128)
         lm00 = self._lm(0, 0)
         self.bots[lm00] = sq4pi               # preCalculations.f90:415-418
-        # ---- initS: conductive state (ps_cond, entropy diffusion, epsc=0) + one mode (init_fields.f90:428-541)
-        M = g.D2 + 2.0 * g.or1[:, None] * g.D1
+        # ---- initS: conductive state (ps_cond, entropy diffusion, epsc=0; init_fields.f90:2270-2291) + one mode (:428-541)
+        M = self.opr * (g.D2 + (self.beta + self.dLtemp0 + 2.0 * or1)[:, None] * g.D1)
         M[0] = 0.0
         M[0, 0] = 1.0
         M[-1] = 0.0
         M[-1, -1] = 1.0
-        rhs = np.zeros(N)
-        rhs[0], rhs[-1] = self.tops[lm00].real, self.bots[lm00].real
-        self.s[:, lm00] = np.linalg.solve(M, rhs)
+        rhs = np.zeros((N, 1))
+        rhs[0, 0], rhs[-1, 0] = self.tops[lm00].real, self.bots[lm00].real
+        self.s[:, lm00] = g.solve(M, rhs, (0, N - 1))[:, 0]
         if init_s1 >= 100:
             l, m = init_s1 // 100, init_s1 % 100
-            x = 2.0 * g.r - g.r_cmb - g.r_icb
+            x = 2.0 * r - g.r_cmb - g.r_icb
             s1 = 1.0 - 3.0 * x ** 2 + 3.0 * x ** 4 - x ** 6
             self.s[:, self._lm(l, m)] += amp_s1 * s1
         # ---- initB, init_b1=3, insulating inner core (init_fields.f90:1129-1188)
-        if init_b1 == 3:
+        if l_mag and init_b1 == 3:
             b_pol = amp_b1 * np.sqrt(3.0 * np.pi) / 4.0
             b_tor = -4.0 / 3.0 * amp_b1 * np.sqrt(np.pi / 5.0)
-            self.b[:, self._lm(1, 0)] += b_pol * (g.r ** 3 - 4.0 / 3.0 * g.r_cmb * g.r ** 2 + g.r_icb ** 4 / 3.0 * g.or1)
-            self.aj[:, self._lm(2, 0)] += b_tor * g.r * np.sin(np.pi * (g.r - g.r_icb))
+            self.b[:, self._lm(1, 0)] += b_pol * (r ** 3 - 4.0 / 3.0 * g.r_cmb * r ** 2 + g.r_icb ** 4 / 3.0 * or1)
+            self.aj[:, self._lm(2, 0)] += b_tor * r * np.sin(np.pi * (r - g.r_icb))
         # ---- time arrays (time_array.f90): old, impl (one level each for CNAB2), expl (two levels)
         self.old, self.impl, self.expl = {}, {}, {}
         for nm in ("s", "w", "p", "z", "b", "j"):
@@ -141,38 +199,53 @@ class BoussinesqDynamoHost:
         self._rhs_imp_s()
         self._rhs_imp_wp()
         self._rhs_imp_z()
-        self._rhs_imp_b()
+        if l_mag:
+            self._rhs_imp_b()
 
     # ------------------------------------------------------------------------------------------------
     def _lm(self, l, m):
         return int(np.nonzero((self.lm2l == l) & (self.lm2m == m))[0][0])
 
-    def _d(self, D, f):
-        return D @ f
-
     def _rhs_imp_s(self):
-        """get_entropy_rhs_imp, updateS.f90:658-756 (Boussinesq: beta=dLtemp0=dLkappa=0, kappa=1)."""
+        """get_entropy_rhs_imp, updateS.f90:658-756 (entropy diffusion, kappa=1)."""
         g = self.g
         self.ds = g.D1 @ self.s
         dds = g.D2 @ self.s
         self.old["s"] = self.s.copy()
-        self.impl["s"] = self.opr * (dds + 2.0 * g.or1[:, None] * self.ds - self.dL[None, :] * g.or2[:, None] * self.s)
+        self.impl["s"] = self.opr * (dds + (self.beta + self.dLtemp0 + 2.0 * g.or1)[:, None] * self.ds -
+                                     self.dL[None, :] * g.or2[:, None] * self.s)
 
     def _rhs_imp_z(self):
-        """get_tor_rhs_imp, updateZ.f90:760-1025 (visc=1, beta=0, no rotating walls)."""
+        """get_tor_rhs_imp, updateZ.f90:760-1025 (visc=1, no rotating walls), with the angular-momentum corrections."""
         g = self.g
+        r, beta, dbeta, rho0 = g.r, self.beta, self.dbeta, self.rho0
         self.dz = g.D1 @ self.z
         ddz = g.D2 @ self.z
+        fac3 = 8.0 / 3.0 * np.pi
+        for (l, m, on) in ((1, 0, self.l_correct_AMz), (1, 1, self.l_correct_AMe)):
+            if not on or m > self.lm2m.max():
+                continue
+            lm = self._lm(l, m)
+            # updateZ.f90:840-915 + outRot.f90:485-543 with AMstart=0 and non-rotating walls: remove the rigid rotation
+            # rho0 r^2 corr that carries the angular momentum of z(1,m)
+            corr = fac3 * g.rInt_R(r * r * self.z[:, lm]) / self.c_moi_oc
+            if m == 0:
+                corr = corr.real
+            self.z[:, lm] -= rho0 * r * r * corr
+            self.dz[:, lm] -= rho0 * (2.0 * r + r * r * beta) * corr
+            ddz[:, lm] -= rho0 * (2.0 + 4.0 * beta * r + dbeta * r * r + beta * beta * r * r) * corr
         fac = self.dL[None, :] * g.or2[:, None]
         self.old["z"] = fac * self.z
-        imp = fac * (ddz - fac * self.z)
+        imp = fac * (ddz - beta[:, None] * self.dz -
+                     (fac + (dbeta + 2.0 * beta * g.or1)[:, None]) * self.z)
         imp[0] = 0.0
         imp[-1] = 0.0      # n_r_top=n_r_cmb+1 .. n_r_bot=n_r_icb-1
         self.impl["z"] = imp
 
     def _rhs_imp_wp(self):
-        """get_pol_rhs_imp, updateWP.f90:1089-1336, non double-curl branch."""
+        """get_pol_rhs_imp, updateWP.f90:1089-1336, non double-curl branch (visc=1, dLvisc=0)."""
         g = self.g
+        beta, dbeta, or1 = self.beta[:, None], self.dbeta[:, None], g.or1[:, None]
         self.dw = g.D1 @ self.w
         self.ddw = g.D2 @ self.w
         dddw = g.D3 @ self.w
@@ -180,11 +253,12 @@ class BoussinesqDynamoHost:
         fac = self.dL[None, :] * g.or2[:, None]
         old_w = fac * self.w
         old_p = -fac * self.dw
-        Dif = fac * (self.ddw - fac * self.w)
-        Pre = -self.dp
-        Buo = self.BuoFac * self.rgrav[:, None] * self.s
+        Dif = fac * (self.ddw - beta / 3.0 * self.dw - (fac + 4.0 / 3.0 * (dbeta + beta * or1)) * self.w)
+        Pre = -self.dp + beta * self.p
+        Buo = self.BuoFac * (self.rho0 * self.rgrav)[:, None] * self.s
         imp_w = Pre + Dif + Buo
-        imp_p = fac * self.p + fac * (-dddw + fac * self.dw - fac * 2.0 * g.or1[:, None] * self.w)
+        imp_p = fac * self.p + fac * (-dddw + beta * self.ddw + (fac + dbeta + 2.0 * beta * or1) * self.dw -
+                                      fac * (2.0 * or1 + 2.0 / 3.0 * beta) * self.w)
         l0 = self.lm2l == 0
         for a in (old_w, old_p, imp_w, imp_p):
             a[0] = 0.0
@@ -225,57 +299,59 @@ class BoussinesqDynamoHost:
         return wimp * self.old[nm] + wl2 * self.impl[nm] + we1 * self.expl[nm][0] + we2 * self.expl[nm][1]
 
     def _build_mats(self, wl1):
-        """get_sMat / get_zMat / get_wpMat / get_bMat for every degree (LU by numpy at solve time)."""
+        """get_sMat / get_zMat / get_wpMat / get_bMat for every degree, acting on grid values (ChebShell.solve maps them
+        to coefficient space and applies the dealiasing)."""
         g, N = self.g, self.N
         I = np.eye(N)
+        beta, dbeta = self.beta[:, None], self.dbeta[:, None]
+        or1, or2 = g.or1[:, None], g.or2[:, None]
+        b0, bN = self.beta[0], self.beta[-1]
         mats = {"s": [], "z": [], "wp": [], "b": [], "j": []}
         for l in range(self.l_max + 1):
             dL = float(l * (l + 1))
-            or1, or2 = g.or1[:, None], g.or2[:, None]
             # sMat (updateS.f90:1086-1140), ktops=kbots=1
-            M = I - wl1 * self.opr * (g.D2 + 2.0 * or1 * g.D1 - dL * or2 * I)
+            M = I - wl1 * self.opr * (g.D2 + (beta + self.dLtemp0[:, None] + 2.0 * or1) * g.D1 - dL * or2 * I)
             M[0], M[-1] = I[0], I[-1]
             mats["s"].append(M)
-            # zMat (updateZ.f90:1850-1890), no slip
-            M = dL * or2 * I - wl1 * dL * or2 * (g.D2 - dL * or2 * I)
-            M[0], M[-1] = I[0], I[-1]
+            # zMat (updateZ.f90:1850-1890)
+            M = dL * or2 * I - wl1 * dL * or2 * (g.D2 - beta * g.D1 - (dL * or2 + dbeta + 2.0 * beta * or1) * I)
+            M[0] = I[0] if self.ktopv == 2 else g.D1[0] - (2.0 * g.or1[0] + b0) * I[0]
+            M[-1] = I[-1] if self.kbotv == 2 else g.D1[-1] - (2.0 * g.or1[-1] + bN) * I[-1]
             mats["z"].append(M)
-            # wpMat (updateWP.f90:1999-2090), no slip
+            # wpMat (updateWP.f90:1999-2090)
             W = np.zeros((2 * N, 2 * N))
-            W[:N, :N] = dL * or2 * I - wl1 * dL * or2 * (g.D2 - dL * or2 * I)
-            W[:N, N:] = wl1 * g.D1
-            W[N:, :N] = -dL * or2 * g.D1 - wl1 * dL * or2 * (-g.D3 + dL * or2 * g.D1 - dL * or2 * 2.0 * or1 * I)
+            W[:N, :N] = dL * or2 * I - wl1 * dL * or2 * (g.D2 - beta / 3.0 * g.D1 - (dL * or2 + 4.0 / 3.0 * (beta * or1 + dbeta)) * I)
+            W[:N, N:] = wl1 * (g.D1 - beta * I)
+            W[N:, :N] = -dL * or2 * g.D1 - wl1 * dL * or2 * (-g.D3 + beta * g.D2 + (dL * or2 + dbeta + 2.0 * beta * or1) * g.D1 -
+                                                            dL * or2 * (2.0 * or1 + 2.0 / 3.0 * beta) * I)
             W[N:, N:] = -wl1 * dL * or2 * I
             W[0] = 0.0
             W[0, :N] = I[0]
             W[N - 1] = 0.0
             W[N - 1, :N] = I[-1]
             W[N] = 0.0
-            W[N, :N] = g.D1[0]
+            W[N, :N] = g.D1[0] if self.ktopv == 2 else g.D2[0] - (2.0 * g.or1[0] + b0) * g.D1[0]
             W[2 * N - 1] = 0.0
-            W[2 * N - 1, :N] = g.D1[-1]
+            W[2 * N - 1, :N] = g.D1[-1] if self.kbotv == 2 else g.D2[-1] - (2.0 * g.or1[-1] + bN) * g.D1[-1]
             mats["wp"].append(W)
-            # bMat / jMat (updateB.f90:1824-1905), ktopb=kbotb=1, conductance_ma=0
-            B = dL * or2 * I - wl1 * self.opm * dL * or2 * (g.D2 - dL * or2 * I)
-            J = B.copy()
-            B[0] = g.D1[0] + l * g.or1[0] * I[0]
-            B[-1] = g.D1[-1] - (l + 1.0) * g.or1[-1] * I[-1]
-            J[0], J[-1] = I[0], I[-1]
-            mats["b"].append(B)
-            mats["j"].append(J)
+            if self.l_mag:
+                # bMat / jMat (updateB.f90:1824-1905), ktopb=kbotb=1, conductance_ma=0
+                B = dL * or2 * I - wl1 * self.opm * dL * or2 * (g.D2 - dL * or2 * I)
+                J = B.copy()
+                B[0] = g.D1[0] + l * g.or1[0] * I[0]
+                B[-1] = g.D1[-1] - (l + 1.0) * g.or1[-1] * I[-1]
+                J[0], J[-1] = I[0], I[-1]
+                mats["b"].append(B)
+                mats["j"].append(J)
         self._mats = (wl1, mats)
-
-    @staticmethod
-    def _solve(M, rhs):
-        # row equilibration like WITH_PRECOND_* (conditioning only)
-        f = 1.0 / np.max(np.abs(M), axis=1)
-        return np.linalg.solve(M * f[:, None], rhs * f[:, None])
 
     # ------------------------------------------------------------------------------------------------
     def fields_Rloc(self):
         """What transp_LMloc_to_Rloc hands to the radial loop (step_time.f90:1005-1132)."""
-        return dict(w=self.w, dw=self.dw, ddw=self.ddw, z=self.z, dz=self.dz, s=self.s, b=self.b, db=self.db,
-                    ddb=self.ddb, aj=self.aj, dj=self.dj)
+        f = dict(w=self.w, dw=self.dw, ddw=self.ddw, z=self.z, dz=self.dz, s=self.s)
+        if self.l_mag:
+            f.update(b=self.b, db=self.db, ddb=self.ddb, aj=self.aj, dj=self.dj)
+        return f
 
     def step(self):
         """One pass of the n_time_step loop of step_time.f90:480-763 (CNAB2: one stage)."""
@@ -283,13 +359,14 @@ class BoussinesqDynamoHost:
         out = self.radial_loop({k: np.ascontiguousarray(v) for k, v in self.fields_Rloc().items()})
         or2 = g.or2[:, None]
         l0 = (self.lm2l == 0)[None, :]
-        # finish_explicit_assembly (LMLoop.f90:390-453): orho1=1, dentropy0=0
-        self.expl["s"][0] = out["dsdt"] - or2 * (g.D1 @ out["dVSrLM"])                 # updateS.f90:587-597
+        # finish_explicit_assembly (LMLoop.f90:390-453), dentropy0=0
+        self.expl["s"][0] = self.orho1[:, None] * (out["dsdt"] - or2 * (g.D1 @ out["dVSrLM"]))   # updateS.f90:587-597
         self.expl["w"][0] = np.array(out["dwdt"])
         self.expl["p"][0] = np.array(out["dpdt"])
         self.expl["z"][0] = np.array(out["dzdt"])
-        self.expl["b"][0] = np.array(out["dbdt"])
-        self.expl["j"][0] = out["djdt"] + np.where(l0, 0.0, or2 * (g.D1 @ out["dVxBhLM"]))  # updateB.f90:1030-1037
+        if self.l_mag:
+            self.expl["b"][0] = np.array(out["dbdt"])
+            self.expl["j"][0] = out["djdt"] + np.where(l0, 0.0, or2 * (g.D1 @ out["dVxBhLM"]))  # updateB.f90:1030-1037
         # dt_courant (courant.f90:277-346)
         self.dtrkc_min, self.dthkc_min = float(np.min(out["dtrkc"])), float(np.min(out["dthkc"]))
         dt_min = min(self.dtrkc_min, self.dthkc_min, 1000.0 * self.dtmax)
@@ -317,7 +394,7 @@ class BoussinesqDynamoHost:
         rhs[0], rhs[-1] = self.tops, self.bots
 
         def up_s(l, idx):
-            self.s[:, idx] = self._solve(mats["s"][l], rhs[:, idx])
+            self.s[:, idx] = g.solve(mats["s"][l], rhs[:, idx], (0, N - 1))
         per_degree(up_s)
         self.s[:, m0] = self.s[:, m0].real
         rotate("s")
@@ -330,13 +407,13 @@ class BoussinesqDynamoHost:
             if l == 0:
                 self.z[:, idx] = 0.0
             else:
-                self.z[:, idx] = self._solve(mats["z"][l], rhs[:, idx])
+                self.z[:, idx] = g.solve(mats["z"][l], rhs[:, idx], (0, N - 1))
         per_degree(up_z)
         self.z[:, m0] = self.z[:, m0].real
         rotate("z")
         self._rhs_imp_z()
         # ---- updateWP (updateWP.f90:255-634), buoyancy of the NEW entropy is implicit (:514-524)
-        rw = self._imex_rhs("w", wts) + wl1 * self.BuoFac * self.rgrav[:, None] * self.s
+        rw = self._imex_rhs("w", wts) + wl1 * self.BuoFac * (self.rho0 * self.rgrav)[:, None] * self.s
         rp = self._imex_rhs("p", wts)
         for a in (rw, rp):
             a[0], a[-1] = 0.0, 0.0
@@ -345,7 +422,7 @@ class BoussinesqDynamoHost:
             if l == 0:
                 self.w[:, idx] = 0.0     # p(l=0) (get_p0Mat) does not feed back into the flow; left untouched
                 return
-            sol = self._solve(mats["wp"][l], np.concatenate([rw[:, idx], rp[:, idx]], axis=0))
+            sol = g.solve(mats["wp"][l], np.concatenate([rw[:, idx], rp[:, idx]], axis=0), (0, N - 1, N, 2 * N - 1))
             self.w[:, idx] = sol[:N]
             self.p[:, idx] = sol[N:]
         per_degree(up_wp)
@@ -355,24 +432,25 @@ class BoussinesqDynamoHost:
         rotate("p")
         self._rhs_imp_wp()
         # ---- updateB (updateB.f90:226-694)
-        rb = self._imex_rhs("b", wts)
-        rj = self._imex_rhs("j", wts)
-        for a in (rb, rj):
-            a[0], a[-1] = 0.0, 0.0
+        if self.l_mag:
+            rb = self._imex_rhs("b", wts)
+            rj = self._imex_rhs("j", wts)
+            for a in (rb, rj):
+                a[0], a[-1] = 0.0, 0.0
 
-        def up_b(l, idx):
-            if l == 0:
-                self.b[:, idx] = 0.0
-                self.aj[:, idx] = 0.0
-                return
-            self.b[:, idx] = self._solve(mats["b"][l], rb[:, idx])
-            self.aj[:, idx] = self._solve(mats["j"][l], rj[:, idx])
-        per_degree(up_b)
-        self.b[:, m0] = self.b[:, m0].real
-        self.aj[:, m0] = self.aj[:, m0].real
-        rotate("b")
-        rotate("j")
-        self._rhs_imp_b()
+            def up_b(l, idx):
+                if l == 0:
+                    self.b[:, idx] = 0.0
+                    self.aj[:, idx] = 0.0
+                    return
+                self.b[:, idx] = g.solve(mats["b"][l], rb[:, idx], (0, N - 1))
+                self.aj[:, idx] = g.solve(mats["j"][l], rj[:, idx], (0, N - 1))
+            per_degree(up_b)
+            self.b[:, m0] = self.b[:, m0].real
+            self.aj[:, m0] = self.aj[:, m0].real
+            rotate("b")
+            rotate("j")
+            self._rhs_imp_b()
         self.n_steps += 1
 
     # ------------------------------------------------------------------------------------------------
@@ -380,10 +458,10 @@ class BoussinesqDynamoHost:
         """Columns 2-9 of e_kin.TAG (kinetic_energy.f90:126-196): e_p, e_t, e_p_as, e_t_as, e_p_es, e_t_es, e_p_eas,
         e_t_eas."""
         g = self.g
-        l, m = self.lm2l[None, :], self.lm2m[None, :]
+        m = self.lm2m[None, :]
         dL = self.dL[None, :]
-        e_p = dL * (dL * g.or2[:, None] * _cc2real(self.w, m) + _cc2real(self.dw, m))
-        e_t = dL * _cc2real(self.z, m)
+        e_p = self.orho1[:, None] * dL * (dL * g.or2[:, None] * _cc2real(self.w, m) + _cc2real(self.dw, m))
+        e_t = self.orho1[:, None] * dL * _cc2real(self.z, m)
         return self._energy_columns(e_p, e_t, es_parity=0, eas_parity=0, fac=0.5)
 
     def e_mag_oc(self):
@@ -411,4 +489,8 @@ class BoussinesqDynamoHost:
         I = self.g.rInt_R
         cols = [e_p.sum(1), e_t.sum(1), e_p[:, axi].sum(1), e_t[:, axi].sum(1), e_p[:, es_p].sum(1),
                 e_t[:, ~es_p].sum(1), e_p[:, eas_p].sum(1), e_t[:, eas_t].sum(1)]
-        return np.array([fac * I(c) for c in cols])
+        return np.array([fac * float(I(c)) for c in cols])
+
+
+class BoussinesqDynamoHost(ShellHost):
+    """samples/dynamo_benchmark/input.nml: Boussinesq MHD, rigid insulating walls (the defaults of ShellHost)."""

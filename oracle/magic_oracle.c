@@ -352,18 +352,24 @@ static void fft_stockham(const orc_ctx *c, orc_cplx *x, orc_cplx *y, int sign) {
     orc_cplx *src = x, *dst = y;
     for (int f = 0; f < c->nfac; f++) {
         int r = c->fac[f], m = len / r;
+        orc_cplx wjk[8][8], tw[8]; /* the radix-r DFT matrix and the twiddles of this p: same table entries as before, hoisted */
+        for (int k = 0; k < r; k++)
+            for (int j = 0; j < r; j++) {
+                orc_cplx w = c->trig[(size_t)((long)(j * k % r) * (n / r)) % n];
+                wjk[k][j] = sign > 0 ? w : conj(w);
+            }
         for (int p = 0; p < m; p++) {
+            for (int k = 0; k < r; k++) {
+                orc_cplx t = c->trig[(size_t)((long)p * k * (n / len)) % n];
+                tw[k] = sign > 0 ? t : conj(t);
+            }
             for (int q = 0; q < s; q++) {
                 orc_cplx a[8], b;
                 for (int j = 0; j < r; j++) a[j] = src[q + s * (p + m * j)];
                 for (int k = 0; k < r; k++) {
                     b = 0;
-                    for (int j = 0; j < r; j++) {
-                        orc_cplx w = c->trig[(size_t)((long)(j * k % r) * (n / r)) % n];
-                        b += a[j] * (sign > 0 ? w : conj(w));
-                    }
-                    orc_cplx tw = c->trig[(size_t)((long)p * k * (n / len)) % n];
-                    dst[q + s * (r * p + k)] = b * (sign > 0 ? tw : conj(tw));
+                    for (int j = 0; j < r; j++) b += a[j] * wjk[k][j];
+                    dst[q + s * (r * p + k)] = b * tw[k];
                 }
             }
         }
