@@ -20,9 +20,11 @@
  *       host (oracle/lmloop.py), reproduces the first 100 rows of samples/dynamo_benchmark/reference.out (e_kin.TAG,
  *       8 columns) and referenceMag.out (e_mag_oc.TAG, 12 columns) at the autotest tolerance rtol 1e-8
  *       (tests/test_dynamo_benchmark.py; the same test runs the CUDA library through the C ABI under -m gpu).
- * Still "parity unpinned" (no reference vectors reachable here, literal line-cited restatements only): the anelastic /
- * u.grad u branch of get_nl with viscous heating (samples/hydro_bench_anel needs the anelastic host), the full-sphere
- * centre level, rotating conducting walls and the inner-core (_IC) and axisymmetric syntheses.
+ *   (4) likewise for the anelastic branch (u.grad u advection, viscous heating, stress-free levels): the first logged row
+ *       (10 steps) of samples/hydro_bench_anel/reference.out, whose axisymmetric columns exist only through the quadratic
+ *       terms (tests/test_hydro_bench_anel.py; the CUDA library reproduces all 30 rows under -m gpu).
+ * Still "parity unpinned" (no reference vectors reachable here, literal line-cited restatements only): the full-sphere
+ * centre level, rotating conducting walls, get_br_v_bcs and the inner-core (_IC) and axisymmetric syntheses.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may call
  * into this library.  The product path (magic_b200/) never links or imports it.

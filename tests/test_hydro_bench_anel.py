@@ -9,7 +9,7 @@ spat_to_qst analyses and get_td's anelastic scalings, which samples/dynamo_bench
 
 The Fortran host is restated in numpy (oracle/lmloop.py ShellHost: anelastic background, stress-free boundary rows,
 dealiased Chebyshev solves, l_correct_AMz/AMe); the radial loop is the CPU oracle (CPU test, first logged row = 10 steps)
-or the CUDA library through the C ABI (`-m gpu`, rows 1-5 = 50 steps).  tests/golden/hydro_bench_anel_reference.npz holds
+or the CUDA library through the C ABI (`-m gpu`, all 30 logged rows = the 300 steps of the reference run).  tests/golden/hydro_bench_anel_reference.npz holds
 reference.out (tests/golden/make_hydro_bench_anel_fixture.py).
 """
 import os
@@ -82,14 +82,15 @@ def test_oracle_radial_loop_reproduces_reference_energies(golden):
 
 @pytest.mark.gpu
 def test_gpu_radial_loop_reproduces_reference_energies(golden):
-    """The CUDA radial loop (magic_rloop_run, host containers) inside the reference's time loop: rows 1-5 (50 steps)."""
+    """The CUDA radial loop (magic_rloop_run, host containers) inside the reference's time loop: all 30 rows (300 steps,
+    e_kin grows from 31 to 322 into the nonlinear regime)."""
     from magic_b200 import RadialLoop, Sht, grid_sizes
     gs = grid_sizes(n_phi_tot=int(golden["n_phi_tot"]))
     s = Sht(gs["l_max"], m_max=gs["m_max"], n_theta_max=gs["n_theta_max"], n_phi_max=gs["n_phi_max"])
     h, p, rad = _setup(golden, s.lm2l, s.lm2m)
     rl = RadialLoop(s, p, rad)
     h.radial_loop = lambda f: rl.radialLoop(f)
-    _run(golden, h, 5)
+    _run(golden, h, len(golden["e_kin"]) - 1)
     assert rl.launch_count() > 0
     rl.finalize()
     s.finalize_sht()
