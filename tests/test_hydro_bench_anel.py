@@ -27,13 +27,13 @@ def golden():
     return {k: d[k] for k in d.files}
 
 
-def _setup(golden, lm2l, lm2m):
+def _setup(golden, lm2l, lm2m, l_correct_AM=True):
     from magic_b200.workload import make_params, make_radial
     from oracle.lmloop import ShellHost
     n_r = int(golden["n_r_max"])
     kw = {k: float(golden[k]) for k in ("radratio", "ra", "ek", "pr", "dtmax", "alpha", "amp_s1", "strat", "polind", "g0", "g1", "g2")}
     h = ShellHost(lm2l, lm2m, None, n_r_max=n_r, n_cheb_max=int(golden["n_cheb_max"]), init_s1=int(golden["init_s1"]),
-                  l_mag=False, ktopv=int(golden["ktopv"]), kbotv=int(golden["kbotv"]), l_correct_AMz=True, l_correct_AMe=True, **kw)
+                  l_mag=False, ktopv=int(golden["ktopv"]), kbotv=int(golden["kbotv"]), l_correct_AMz=l_correct_AM, l_correct_AMe=l_correct_AM, **kw)
     p = make_params("anel", n_r, ktopv=int(golden["ktopv"]), kbotv=int(golden["kbotv"]))
     p.ViscHeatFac = h.ViscHeatFac       # DissNb * pr / ra (radial.f90:762)
     p.ra = float(golden["ra"])
