@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--level-chunk", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--overlap", default="auto", choices=["auto", "on", "off"],
+                    help="transposes pipelined chunk-wise against the compute (magic_rloop_run_lm_dev); auto = on for N > 1")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-levels", type=int, default=0)
     return ap.parse_args()
@@ -117,7 +119,8 @@ def config_dict(args, gs, chunk):
             "n_phi": gs["n_phi_max"], "lm_max": gs["lm_max"], "minc": gs["minc"], "fields": gs["physics"],
             "units_per_level": UNITS[gs["physics"]], "level_chunk": chunk, "l2": "inputs_exceed_l2",
             "polar_eps": float(os.environ.get("MAGIC_POLAR_EPS", "1e-40")),
-            "parallelism": f"r-slabs x{args.gpus} (getBlocks) + NCCL all-to-all transposes"}
+            "parallelism": f"r-slabs x{args.gpus} (getBlocks) + NCCL all-to-all transposes" +
+                           (", pipelined chunk-wise under the compute" if (args.overlap == "on" or (args.overlap == "auto" and args.gpus > 1)) else "")}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -256,7 +259,19 @@ def run_magic(args, gs):
     tev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     tacc = {"transp_lm2r": 0.0, "transp_r2lm": 0.0}
 
+    overlap = args.overlap == "on" or (args.overlap == "auto" and world > 1)
+
+    def step_overlapped():
+        # one call: the all-to-alls of level chunk c+1 (in) and c-1 (out) run on a second stream under the compute of chunk c
+        rl.run_lm_dev(tr, flow_LM.data_ptr(), s_LM.data_ptr(), field_LM.data_ptr(), dflow_LM.data_ptr(), ds_LM.data_ptr(),
+                      db_LM.data_ptr(), dtr.data_ptr(), dth.data_ptr())
+        for k, v in rl.last_timing().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+        pending.append(None)
+
     def step():
+        if overlap:
+            return step_overlapped()
         tev[0].record(ext)
         tr.transp_lm2r_dev_n(5, flow_LM.data_ptr(), flow_R.data_ptr())
         tr.transp_lm2r_dev_n(2, s_LM.data_ptr(), s_R.data_ptr())
@@ -310,8 +325,12 @@ def run_magic(args, gs):
     total_flops = flops_per_level(gs) * n_r_max
     value = total_flops / (ms_step * 1e-3) * 1e-9
     stages = {k: v / args.steps for k, v in stage_acc.items()}
-    stages["transp_lm2r"] = tacc["transp_lm2r"] / max(len(pending), 1)
-    stages["transp_r2lm_plus_wait"] = ms - stages["transp_lm2r"] - stages["total"]
+    if overlap:
+        # 'total' spans the chunk loop including its waits for inbound chunks; what is left is the exposed tail of the last r2lm
+        stages["transp_exposed_tail"] = ms - stages["total"]
+    else:
+        stages["transp_lm2r"] = tacc["transp_lm2r"] / max(len(pending), 1)
+        stages["transp_r2lm_plus_wait"] = ms - stages["transp_lm2r"] - stages["total"]
     leg_ms = stages["legendre_syn"] + stages["legendre_an"]
     leg_tflops = rl.legendre_flops() / (leg_ms * 1e-3) * 1e-12 if leg_ms > 0 else 0.0
     checksum = float(torch.view_as_real(dflow_LM).abs().sum().item())

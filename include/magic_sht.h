@@ -157,6 +157,15 @@ int magic_transp_create(magic_sht *h, const char id[128], int rank, int n_procs,
 int magic_transp_destroy(magic_transp *t);
 /* Local extents: llm, ulm (1-based inclusive, lo order), nRstart, nRstop. */
 int magic_transp_extents(const magic_transp *t, int *llm, int *ulm, int *nRstart, int *nRstop);
+/* A part of a transposer: for every rank q it moves only the levels [lev_off[q], lev_off[q] + lev_cnt[q]) of q's radial
+ * slab (offsets relative to the slab; a count may be 0).  arr_LMloc / arr_Rloc keep their full-slab shapes, so the parts
+ * of one level partition together do what the parent does, in smaller all-to-alls that can overlap the compute of other
+ * level chunks (magic_rloop_run_lm_dev does exactly that).  Parts share the parent's buffers and communicator: use them on
+ * one stream and in the same order on every rank; destroy them before the parent. */
+int magic_transp_create_part(magic_transp *parent, const int *lev_off, const int *lev_cnt, magic_transp **out);
+int magic_transp_info(const magic_transp *t, int *rank, int *n_procs, int *n_r_max, int *n_fields);
+/* cudaStream_t on which this object's pack / exchange / unpack work is queued (NULL = the handle's stream). */
+int magic_transp_set_stream(magic_transp *t, void *stream);
 /* arr_LMloc(llm:ulm, 1:n_r_max, n_fields) -> arr_Rloc(1:lm_max, nRstart:nRstop, n_fields), device pointers. */
 int magic_transp_lm2r_dev(magic_transp *t, const double *arr_LMloc, double *arr_Rloc);
 int magic_transp_r2lm_dev(magic_transp *t, const double *arr_Rloc, double *arr_LMloc);
@@ -177,6 +186,24 @@ int magic_transp_unpack_r2lm_dev(magic_transp *t, const double *recvbuf, double 
 /* counts/displacements in complex elements, length n_procs each (create_comm_alltoallv :120-152). */
 int magic_transp_counts(const magic_transp *t, int dir /*0 lm2r, 1 r2lm*/, long long *scounts, long long *sdisp,
                         long long *rcounts, long long *rdisp);
+
+/* ---- the whole hot path of one time step in one call (step_time.f90:485-612): transp_LMloc_to_Rloc -> radialLoopG ->
+ * transp_Rloc_to_LMloc, on LM-distributed DEVICE containers in the reference's packing (fields.f90:211-268,
+ * dt_fieldsLast.f90:125-214).  With more than one rank the transposes run chunk-wise on a second stream: the all-to-all
+ * of level chunk c+1 (in) and of chunk c-1 (out) overlap the compute of chunk c.  Every rank must have created its loop
+ * with the same explicit level_chunk.  Supported field set: heat + flow (+ magnetic field), pressure formulation. */
+typedef struct {
+    const double *flow;  /* complex [5][n_r_max][nlm_loc]: w, dw, ddw, z, dz */
+    const double *s;     /* complex [2][n_r_max][nlm_loc]: s, ds */
+    const double *field; /* complex [5][n_r_max][nlm_loc]: b, db, ddb, aj, dj (NULL without l_mag) */
+} magic_lm_in;
+typedef struct {
+    double *dflowdt;     /* complex [3][n_r_max][nlm_loc]: dwdt, dzdt, dpdt */
+    double *dsdt;        /* complex [2][n_r_max][nlm_loc]: dsdt, dVSrLM */
+    double *dbdt;        /* complex [3][n_r_max][nlm_loc]: dbdt, djdt, dVxBhLM (NULL without l_mag) */
+    double *dtrkc, *dthkc; /* device [n_r_loc] */
+} magic_lm_out;
+int magic_rloop_run_lm_dev(magic_rloop *rl, magic_transp *t, const magic_lm_in *in, const magic_lm_out *out, double time);
 
 /* Pure host helpers (no CUDA device needed): the decomposition the transposer uses.
  * magic_get_blocks: getBlocks (parallel.f90:75-92), 1-based inclusive start/stop per rank.

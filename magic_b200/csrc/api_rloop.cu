@@ -7,6 +7,8 @@
 #include "../../include/magic_sht.h"
 #include "engine.cuh"
 
+#include <functional>
+
 using namespace magic;
 
 enum Src { S_W = 0, S_DW, S_DDW, S_Z, S_DZ, S_S, S_DS, S_P, S_XI, S_B, S_DB, S_DDB, S_AJ, S_DJ, S_COUNT };
@@ -23,6 +25,11 @@ struct magic_rloop {
     GridOut go;
     Buffers buf;
     std::vector<int> chunk_start, chunk_size;
+    int level_chunk = 0;  // the chunk length the sizes above were derived from
+    // hooks of the chunk loop (magic_rloop_run_lm_dev): called on the host right before the first / after the last kernel
+    // of chunk c is queued; they queue the transposes of that chunk on the communication stream
+    std::function<int(int)> hook_before, hook_after;
+    struct LmPipe *lmpipe = nullptr;
     Layout lay[2];  // at most two distinct chunk sizes
     int lay_size[2] = {0, 0};
     // nl_lm slots
@@ -54,6 +61,28 @@ struct magic_rloop {
     bool pipelined = false;
 };
 
+// Level chunks of a slab of n_r_loc levels: full chunks of `level_chunk` levels (the GEMM column count 4*npair*n_lev is then
+// a multiple of the 64-wide tile for level_chunk % 4 == 0), a remainder of at most level_chunk/4 levels folded into the last
+// chunk, a larger one as a short chunk of its own.  A pure function of its arguments: every rank can compute the chunks of
+// every other rank (magic_rloop_run_lm_dev).  (Balanced sizes such as 15/16 for 257 levels leave every N-edge GEMM tile 3/4
+// full: measured 1.00 vs 0.94 ms per level.)
+static void level_chunks(int n_r_loc, int level_chunk, std::vector<int> &start, std::vector<int> &size) {
+    start.clear();
+    size.clear();
+    level_chunk = std::max(1, std::min(level_chunk, n_r_loc));
+    const int nfull = n_r_loc / level_chunk, rem = n_r_loc % level_chunk;
+    int big = level_chunk, small = 0, nbig = nfull, nsmall = 0;  // nbig chunks of `big`, then nsmall of `small`
+    if (rem > 0 && rem <= level_chunk / 4 && nfull >= 1) { small = level_chunk + rem; nbig = nfull - 1; nsmall = 1; }
+    else if (rem > 0) { small = rem; nsmall = 1; }
+    int pos = 0;
+    for (int c = 0; c < nbig + nsmall; c++) {
+        const int sz = c < nbig ? big : small;
+        start.push_back(pos);
+        size.push_back(sz);
+        pos += sz;
+    }
+}
+
 static void add_scal(BatchSpec &s, Term t0, Term t1, int lmask, int &field_counter, int &slot) {
     ScalCol c{};
     c.t[0] = t0; c.t[1] = t1; c.lmask = lmask;
@@ -71,6 +100,8 @@ static void add_pair(BatchSpec &s, Term S0, Term S1, Term T0, Term T1, int lmask
     s.field_v.push_back(slot_p);
 }
 
+static void lmpipe_free(struct LmPipe *p);
+
 extern "C" int magic_rloop_destroy(magic_rloop *rl) {
     if (!rl) return 0;
     cudaSetDevice(rl->h->dev);
@@ -82,6 +113,7 @@ extern "C" int magic_rloop_destroy(magic_rloop *rl) {
     cudaFree(rl->d_dtrkc); cudaFree(rl->d_dthkc); cudaFree(rl->d_lev); cudaFree(rl->d_tq_partial); cudaFree(rl->d_torque);
     cudaFree(rl->d_brv);
     if (rl->h_brv) cudaFreeHost(rl->h_brv);
+    lmpipe_free(rl->lmpipe);
     if (rl->h_torque) cudaFreeHost(rl->h_torque);
     for (int i = 0; i < 16; i++) cudaEventDestroy(rl->ev[i]);
     for (auto e : rl->up_done) cudaEventDestroy(e);
@@ -227,25 +259,12 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
         level_chunk = std::min(level_chunk, tiles16 >= 20LL * 2 * 148 ? 16 : 32);
     }
     level_chunk = std::min(level_chunk, n_r_loc);
-    // Chunk sizes: full chunks of `level_chunk` levels (the GEMM column count 4*npair*n_lev is then a multiple of the 64-wide
-    // tile for level_chunk % 4 == 0) and the remainder either folded into the last chunk (small remainder) or as one short
-    // chunk.  (Balanced sizes such as 15/16 for 257 levels waste 6 % of every N-edge tile: measured 1.00 vs 0.94 ms/level.)
-    {
-        const int nfull = n_r_loc / level_chunk, rem = n_r_loc % level_chunk;
-        int big = level_chunk, small = 0, nbig = nfull, nsmall = 0;  // nbig chunks of `big`, then nsmall of `small`
-        if (rem > 0 && rem <= level_chunk / 4 && nfull >= 1) { small = level_chunk + rem; nbig = nfull - 1; nsmall = 1; }
-        else if (rem > 0) { small = rem; nsmall = 1; }
-        int pos = 0;
-        for (int c = 0; c < nbig + nsmall; c++) {
-            const int sz = c < nbig ? big : small;
-            rl->chunk_start.push_back(pos);
-            rl->chunk_size.push_back(sz);
-            pos += sz;
-        }
-        // lay[0] is the larger layout (it sizes the workspace)
-        if (nbig == 0) { rl->lay_size[0] = small; rl->lay_size[1] = 0; }
-        else if (small > big) { rl->lay_size[0] = small; rl->lay_size[1] = big; }
-        else { rl->lay_size[0] = big; rl->lay_size[1] = small; }
+    rl->level_chunk = level_chunk;
+    level_chunks(n_r_loc, level_chunk, rl->chunk_start, rl->chunk_size);
+    {   // at most two distinct sizes; lay[0] is the larger layout (it sizes the workspace)
+        const int first = rl->chunk_size.front(), last = rl->chunk_size.back();
+        rl->lay_size[0] = std::max(first, last);
+        rl->lay_size[1] = first == last ? 0 : std::min(first, last);
     }
     const int nchunks = (int)rl->chunk_size.size();
     layout_sizes(h, S, rl->lay_size[0], rl->lay[0]);
@@ -326,6 +345,7 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
         const double *src[MAGIC_MAX_SRC];
         for (int i = 0; i < MAGIC_MAX_SRC; i++) src[i] = (i < S_COUNT && ip[i]) ? ip[i] + (size_t)l0 * lm2 : nullptr;
         if (rl->pipelined) MCHECK(cudaStreamWaitEvent(h->stream, rl->up_done[c], 0));
+        if (rl->hook_before && rl->hook_before((int)c)) return 1;
         if (run_synthesis(h, rl->spec, L, rl->buf, src, d_lev, rl->ev)) return 1;
         // ---- get_nl + Courant
         MCHECK(cudaMemsetAsync(rl->buf.courmax, 0, sizeof(unsigned long long) * 2 * nl, h->stream));
@@ -391,6 +411,7 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
         }
         cudaEventRecord(rl->ev[9], h->stream);
         MCHECK(cudaGetLastError());
+        if (rl->hook_after && rl->hook_after((int)c)) return 1;
         if (rl->pipelined) {  // results of this chunk go home while the next chunk computes
             MCHECK(cudaEventRecord(rl->comp_done[c], h->stream));
             MCHECK(cudaStreamWaitEvent(rl->s_down, rl->comp_done[c], 0));
@@ -500,6 +521,150 @@ extern "C" int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const
     MCHECK(cudaStreamSynchronize(h->stream));
     memcpy(out->dtrkc, rl->host_dtrkc, sizeof(double) * rl->n_r_loc);
     memcpy(out->dthkc, rl->host_dthkc, sizeof(double) * rl->n_r_loc);
+    return 0;
+}
+
+// ---- LM containers in, LM containers out: transposes pipelined against the level chunks ---------------------------------
+struct LmPipe {
+    magic_transp *parent = nullptr;
+    std::vector<magic_transp *> parts;  // one per global chunk index
+    cudaStream_t comm = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_out;
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr;
+    double *R[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // flow, s, field, dflowdt, dsdt, dbdt (R-distributed)
+    int C = 0;
+};
+static const int LM_NF[6] = {5, 2, 5, 3, 2, 3};
+
+static void lmpipe_free(LmPipe *p) {
+    if (!p) return;
+    for (auto t : p->parts) magic_transp_destroy(t);
+    for (auto e : p->ev_in) cudaEventDestroy(e);
+    for (auto e : p->ev_out) cudaEventDestroy(e);
+    if (p->ev_start) cudaEventDestroy(p->ev_start);
+    if (p->ev_done) cudaEventDestroy(p->ev_done);
+    if (p->comm) cudaStreamDestroy(p->comm);
+    for (int i = 0; i < 6; i++) cudaFree(p->R[i]);
+    delete p;
+}
+
+static int lmpipe_build(magic_rloop *rl, magic_transp *t) {
+    magic_sht *h = rl->h;
+    int rank, n_procs, n_r_max, nf;
+    if (magic_transp_info(t, &rank, &n_procs, &n_r_max, &nf)) return 1;
+    if (nf < 5) MFAIL("magic_rloop_run_lm_dev: the transposer must serve containers of 5 fields");
+    int llm, ulm, nRstart, nRstop;
+    if (magic_transp_extents(t, &llm, &ulm, &nRstart, &nRstop)) return 1;
+    if (nRstop - nRstart + 1 != rl->n_r_loc) MFAIL("magic_rloop_run_lm_dev: the loop and the transposer disagree on the radial slab");
+    lmpipe_free(rl->lmpipe);
+    LmPipe *p = new LmPipe();
+    rl->lmpipe = p;
+    p->parent = t;
+    const size_t lm2 = 2 * (size_t)h->lm_max;
+    for (int i = 0; i < 6; i++) {
+        if ((i == 2 || i == 5) && !rl->p.l_mag) continue;
+        MCHECK(cudaMalloc((void **)&p->R[i], sizeof(double) * lm2 * rl->n_r_loc * LM_NF[i]));
+        MCHECK(cudaMemsetAsync(p->R[i], 0, sizeof(double) * lm2 * rl->n_r_loc * LM_NF[i], h->stream));
+    }
+    if (n_procs == 1) return 0;
+    // the chunks of every rank (same rule, same level_chunk everywhere); C = the largest chunk count
+    std::vector<int> rs(n_procs), re(n_procs);
+    if (magic_get_blocks(n_r_max, n_procs, rs.data(), re.data())) return 1;
+    std::vector<std::vector<int>> cs(n_procs), cz(n_procs);
+    for (int q = 0; q < n_procs; q++) {
+        level_chunks(re[q] - rs[q] + 1, rl->level_chunk, cs[q], cz[q]);
+        p->C = std::max(p->C, (int)cs[q].size());
+    }
+    if (cs[rank] != rl->chunk_start || cz[rank] != rl->chunk_size) MFAIL("magic_rloop_run_lm_dev: internal chunk mismatch");
+    MCHECK(cudaStreamCreateWithFlags(&p->comm, cudaStreamNonBlocking));
+    MCHECK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+    MCHECK(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
+    for (int c = 0; c < p->C; c++) {
+        std::vector<int> off(n_procs), cnt(n_procs);
+        for (int q = 0; q < n_procs; q++) {
+            const bool has = c < (int)cs[q].size();
+            off[q] = has ? cs[q][c] : re[q] - rs[q] + 1;
+            cnt[q] = has ? cz[q][c] : 0;
+        }
+        magic_transp *part = nullptr;
+        if (magic_transp_create_part(t, off.data(), cnt.data(), &part)) return 1;
+        magic_transp_set_stream(part, (void *)p->comm);
+        p->parts.push_back(part);
+        cudaEvent_t e;
+        MCHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        p->ev_in.push_back(e);
+        MCHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        p->ev_out.push_back(e);
+    }
+    return 0;
+}
+
+extern "C" int magic_rloop_run_lm_dev(magic_rloop *rl, magic_transp *t, const magic_lm_in *in, const magic_lm_out *out, double time) {
+    if (!rl || !t || !in || !out) MFAIL("magic_rloop_run_lm_dev: null argument");
+    magic_sht *h = rl->h;
+    MCHECK(cudaSetDevice(h->dev));
+    const magic_params &P = rl->p;
+    if (P.l_double_curl || P.l_chemical_conv || !P.l_heat || !P.l_conv)
+        MFAIL("magic_rloop_run_lm_dev: supported field set is heat + flow (+ magnetic field) in the pressure formulation; "
+              "use magic_transp_* and magic_rloop_run_dev for other sets");
+    if (!in->flow || !in->s || !out->dflowdt || !out->dsdt || !out->dtrkc || !out->dthkc || (P.l_mag && (!in->field || !out->dbdt)))
+        MFAIL("magic_rloop_run_lm_dev: a required container is null");
+    if (!rl->lmpipe || rl->lmpipe->parent != t)
+        if (lmpipe_build(rl, t)) return 1;
+    LmPipe *p = rl->lmpipe;
+    const size_t fld = 2 * (size_t)h->lm_max * rl->n_r_loc;  // doubles per R-distributed field
+    magic_fields_in fin{};
+    magic_fields_out fout{};
+    fin.w = p->R[0]; fin.dw = p->R[0] + fld; fin.ddw = p->R[0] + 2 * fld; fin.z = p->R[0] + 3 * fld; fin.dz = p->R[0] + 4 * fld;
+    fin.s = p->R[1]; fin.ds = p->R[1] + fld;
+    fout.dwdt = p->R[3]; fout.dzdt = p->R[3] + fld; fout.dpdt = p->R[3] + 2 * fld;
+    fout.dsdt = p->R[4]; fout.dVSrLM = p->R[4] + fld;
+    if (P.l_mag) {
+        fin.b = p->R[2]; fin.db = p->R[2] + fld; fin.ddb = p->R[2] + 2 * fld; fin.aj = p->R[2] + 3 * fld; fin.dj = p->R[2] + 4 * fld;
+        fout.dbdt = p->R[5]; fout.djdt = p->R[5] + fld; fout.dVxBhLM = p->R[5] + 2 * fld;
+    }
+    fout.dtrkc = out->dtrkc; fout.dthkc = out->dthkc;
+    const double *lm_in[3] = {in->flow, in->s, P.l_mag ? in->field : nullptr};
+    double *lm_out[3] = {out->dflowdt, out->dsdt, P.l_mag ? out->dbdt : nullptr};
+    if (p->parts.empty()) {  // one rank: the transposes are the lo <-> st permutation
+        for (int k = 0; k < 3; k++)
+            if (lm_in[k] && magic_transp_lm2r_dev_n(t, LM_NF[k], lm_in[k], p->R[k])) return 1;
+        if (magic_rloop_run_dev(rl, &fin, &fout, time)) return 1;
+        for (int k = 0; k < 3; k++)
+            if (lm_out[k] && magic_transp_r2lm_dev_n(t, LM_NF[3 + k], p->R[3 + k], lm_out[k])) return 1;
+        return 0;
+    }
+    // all inbound transposes are queued now, chunk by chunk, on the communication stream
+    MCHECK(cudaEventRecord(p->ev_start, h->stream));
+    MCHECK(cudaStreamWaitEvent(p->comm, p->ev_start, 0));
+    for (int c = 0; c < p->C; c++) {
+        for (int k = 0; k < 3; k++)
+            if (lm_in[k] && magic_transp_lm2r_dev_n(p->parts[c], LM_NF[k], lm_in[k], p->R[k])) return 1;
+        MCHECK(cudaEventRecord(p->ev_in[c], p->comm));
+    }
+    auto outbound = [&](int c, bool wait) -> int {
+        if (wait) {
+            MCHECK(cudaEventRecord(p->ev_out[c], h->stream));
+            MCHECK(cudaStreamWaitEvent(p->comm, p->ev_out[c], 0));
+        }
+        for (int k = 0; k < 3; k++)
+            if (lm_out[k] && magic_transp_r2lm_dev_n(p->parts[c], LM_NF[3 + k], p->R[3 + k], lm_out[k])) return 1;
+        return 0;
+    };
+    rl->hook_before = [&](int c) -> int {
+        MCHECK(cudaStreamWaitEvent(h->stream, p->ev_in[c], 0));
+        return 0;
+    };
+    rl->hook_after = [&](int c) -> int { return outbound(c, true); };
+    const int rc = magic_rloop_run_dev(rl, &fin, &fout, time);
+    rl->hook_before = nullptr;
+    rl->hook_after = nullptr;
+    if (rc) return 1;
+    // a rank with fewer chunks than C still takes part in the remaining exchanges (it has no levels in them, its peers do)
+    for (int c = (int)rl->chunk_start.size(); c < p->C; c++)
+        if (outbound(c, false)) return 1;
+    MCHECK(cudaEventRecord(p->ev_done, p->comm));
+    MCHECK(cudaStreamWaitEvent(h->stream, p->ev_done, 0));
     return 0;
 }
 

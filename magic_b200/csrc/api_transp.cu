@@ -114,7 +114,8 @@ void build_lo_map(const magic_sht *h, int n_procs, std::vector<int> &lo2st, std:
 struct PackArgs {
     int n_procs, n_fields, n_r_max, lm_max;
     int llm, nlm;          // my lm slab (0-based start in lo order, count)
-    int r0, nr;            // my radial slab (0-based start, count)
+    int r0, nr;            // my radial slab (0-based start, count); for a part: my levels of this part
+    int r_off, nr_arr;     // arr_Rloc holds nr_arr levels per field, of which this object moves [r_off, r_off + nr)
     const int *rstart;     // [n_procs] 0-based first level of each rank
     const int *rcount;     // [n_procs]
     const int *lstart;     // [n_procs] 0-based first lo index of each rank
@@ -158,7 +159,7 @@ __global__ void rside_kernel(PackArgs a, const double2 *__restrict__ arr_R_in, d
     long long t = rel / a.lcount[p];
     int r = (int)(t % a.nr), f = (int)(t / a.nr);
     int lm_st = a.lo2st[a.lstart[p] + lm];
-    size_t pos = (size_t)lm_st + (size_t)a.lm_max * ((size_t)r + (size_t)a.nr * f);
+    size_t pos = (size_t)lm_st + (size_t)a.lm_max * ((size_t)(a.r_off + r) + (size_t)a.nr_arr * f);
     if (buf_out) buf_out[idx] = arr_R_in[pos];    // pack   (mpi_transpose.f90:490-506)
     else arr_R_out[pos] = buf_in[idx];            // unpack (mpi_transpose.f90:341-357)
 }
@@ -195,6 +196,8 @@ __global__ void __launch_bounds__(256) rside_tiled_kernel(PackArgs a, const int 
     const int lB = l0 + jl, mcB = mc0 + jm, mB = mcB * minc;
     const bool vB = lB <= l_max && mcB < n_m && mB <= lB;
     const long long arrB = vB ? (long long)mstart[mcB] + lB - mB : 0;
+    // buffer row (f, r) = f * nr + r; array row = f * nr_arr + r_off + r (a part moves a sub-range of the levels of each field)
+    auto arr_row = [&](int row) { return (long long)(row / a.nr) * a.nr_arr + a.r_off + row % a.nr; };
     for (int rb = row0; rb < min(row0 + RT_ROWS, rows_total); rb += 4) {
         double2 v[4];
 #pragma unroll
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(256) rside_tiled_kernel(PackArgs a, const int 
             v[q] = make_double2(0.0, 0.0);
             if (row < rows_total) {
                 if (UNPACK) { if (vA) v[q] = in[bufA + (long long)row * lcA]; }
-                else { if (vB) v[q] = in[arrB + (long long)row * a.lm_max]; }
+                else { if (vB) v[q] = in[arrB + arr_row(row) * a.lm_max]; }
             }
         }
 #pragma unroll
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(256) rside_tiled_kernel(PackArgs a, const int 
         for (int q = 0; q < 4; q++) {
             const int row = rb + q;
             if (row < rows_total) {
-                if (UNPACK) { if (vB) out[arrB + (long long)row * a.lm_max] = tile[q][jl][jm]; }
+                if (UNPACK) { if (vB) out[arrB + arr_row(row) * a.lm_max] = tile[q][jl][jm]; }
                 else { if (vA) out[bufA + (long long)row * lcA] = tile[q][il][im]; }
             }
         }
@@ -248,6 +251,8 @@ struct magic_transp {
     double *sendbuf = nullptr, *recvbuf = nullptr, *stage_lm = nullptr, *stage_r = nullptr;
     ncclComm_t comm = nullptr;
     PackArgs args;
+    cudaStream_t stream = nullptr;   // stream of the pack / exchange / unpack work (default: the handle's stream)
+    magic_transp *parent = nullptr;  // a part shares maps, buffers and communicator with its parent
 };
 
 extern "C" int magic_get_blocks(int n_points, int n_procs, int *start, int *stop) {
@@ -286,6 +291,11 @@ extern "C" int magic_transp_unique_id(char id[128]) {
 extern "C" int magic_transp_destroy(magic_transp *t) {
     if (!t) return 0;
     cudaSetDevice(t->h->dev);
+    if (t->parent) {  // a part owns only its level tables
+        cudaFree(t->d_rstart); cudaFree(t->d_rcount); cudaFree(t->d_lmdisp); cudaFree(t->d_rdisp);
+        delete t;
+        return 0;
+    }
     if (t->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(t->comm);
     cudaFree(t->d_rstart); cudaFree(t->d_rcount); cudaFree(t->d_lstart); cudaFree(t->d_lcount); cudaFree(t->d_lo2st); cudaFree(t->d_st2lo);
     cudaFree(t->d_lmdisp); cudaFree(t->d_rdisp); cudaFree(t->sendbuf); cudaFree(t->recvbuf); cudaFree(t->stage_lm); cudaFree(t->stage_r);
@@ -328,6 +338,8 @@ extern "C" int magic_transp_create(magic_sht *h, const char id[128], int rank, i
     PackArgs &a = t->args;
     a.n_procs = n_procs; a.n_fields = n_fields; a.n_r_max = n_r_max; a.lm_max = h->lm_max;
     a.llm = t->ls[rank] - 1; a.nlm = nlm; a.r0 = t->rs[rank] - 1; a.nr = nr;
+    a.r_off = 0; a.nr_arr = nr;
+    t->stream = h->stream;
     a.rstart = t->d_rstart; a.rcount = t->d_rcount; a.lstart = t->d_lstart; a.lcount = t->d_lcount; a.lo2st = t->d_lo2st;
     a.disp = nullptr;
     if (n_procs > 1) {
@@ -349,6 +361,66 @@ extern "C" int magic_transp_create(magic_sht *h, const char id[128], int rank, i
         }
     }
     *out = t;
+    return 0;
+}
+
+// A part moves, for every rank q, the level sub-range [lev_off[q], lev_off[q] + lev_cnt[q]) of q's radial slab -- e.g. one
+// level chunk of the radial loop -- with its own (smaller) all-to-all, so that the transposes of one chunk can overlap the
+// compute of another.  It shares the maps, the staging buffers and the communicator of its parent: use the parts of one
+// parent on ONE stream (they serialise on the shared buffers) and issue them in the same order on every rank.
+extern "C" int magic_transp_create_part(magic_transp *parent, const int *lev_off, const int *lev_cnt, magic_transp **out) {
+    if (!parent || !lev_off || !lev_cnt || !out) MFAIL("magic_transp_create_part: null argument");
+    if (parent->parent) MFAIL("magic_transp_create_part: parent is itself a part");
+    *out = nullptr;
+    MCHECK(cudaSetDevice(parent->h->dev));
+    const int n_procs = parent->n_procs, rank = parent->rank;
+    magic_transp *t = new magic_transp(*parent);  // shares every pointer; the level tables are replaced below
+    t->parent = parent;
+    t->d_rstart = t->d_rcount = nullptr;
+    t->d_lmdisp = t->d_rdisp = nullptr;
+    t->stage_lm = t->stage_r = nullptr;
+    const int nlm = t->le[rank] - t->ls[rank] + 1, nr_full = parent->re[rank] - parent->rs[rank] + 1;
+    std::vector<int> rstart(n_procs), rcount(n_procs);
+    for (int q = 0; q < n_procs; q++) {
+        const int nq = parent->re[q] - parent->rs[q] + 1;
+        if (lev_off[q] < 0 || lev_cnt[q] < 0 || lev_off[q] + lev_cnt[q] > nq) { delete t; MFAIL("magic_transp_create_part: level range outside a rank's slab"); }
+        rstart[q] = parent->rs[q] - 1 + lev_off[q];
+        rcount[q] = lev_cnt[q];
+        t->rs[q] = rstart[q] + 1;
+        t->re[q] = rstart[q] + rcount[q];
+    }
+    const int nr = rcount[rank];
+    for (int p = 0; p < n_procs; p++) {
+        const int lcount = t->le[p] - t->ls[p] + 1;
+        t->lm1[p] = (long long)rcount[p] * nlm;
+        t->r1[p] = (long long)nr * lcount;
+        t->lmd1[p + 1] = t->lmd1[p] + t->lm1[p];
+        t->rd1[p + 1] = t->rd1[p] + t->r1[p];
+    }
+    if (dev_upload_vec(&t->d_rstart, rstart) || dev_upload_vec(&t->d_rcount, rcount) || dev_upload_vec(&t->d_lmdisp, t->lmd1) ||
+        dev_upload_vec(&t->d_rdisp, t->rd1)) {
+        magic_transp_destroy(t);
+        return 1;
+    }
+    PackArgs &a = t->args;
+    a.rstart = t->d_rstart; a.rcount = t->d_rcount;
+    a.r0 = rstart[rank]; a.nr = nr; a.r_off = lev_off[rank]; a.nr_arr = nr_full;
+    *out = t;
+    return 0;
+}
+
+extern "C" int magic_transp_info(const magic_transp *t, int *rank, int *n_procs, int *n_r_max, int *n_fields) {
+    if (!t) MFAIL("null transposer");
+    if (rank) *rank = t->rank;
+    if (n_procs) *n_procs = t->n_procs;
+    if (n_r_max) *n_r_max = t->n_r_max;
+    if (n_fields) *n_fields = t->n_fields;
+    return 0;
+}
+
+extern "C" int magic_transp_set_stream(magic_transp *t, void *stream) {
+    if (!t) MFAIL("null transposer");
+    t->stream = stream ? (cudaStream_t)stream : t->h->stream;
     return 0;
 }
 
@@ -376,16 +448,17 @@ static int side_launch(magic_transp *t, int nf, bool lmside, const double *arr_i
     if (total == 0) return 0;
     int blocks = (int)((total + 255) / 256);
     if (lmside)
-        lmside_kernel<<<blocks, 256, 0, t->h->stream>>>(a, (const double2 *)arr_in, (double2 *)arr_out, (const double2 *)buf_in, (double2 *)buf_out, total);
+        lmside_kernel<<<blocks, 256, 0, t->stream>>>(a, (const double2 *)arr_in, (double2 *)arr_out, (const double2 *)buf_in, (double2 *)buf_out, total);
     else {
         const magic_sht *h = t->h;
         const int rows = nf * a.nr;
+        if (rows == 0) return 0;
         dim3 grid((h->l_max + RT_L) / RT_L, (h->n_m + RT_M - 1) / RT_M, (rows + RT_ROWS - 1) / RT_ROWS);
         if (buf_out)
-            rside_tiled_kernel<false><<<grid, 256, 0, h->stream>>>(a, t->d_st2lo, h->d_lstart, (const double2 *)arr_in, (double2 *)buf_out, rows,
+            rside_tiled_kernel<false><<<grid, 256, 0, t->stream>>>(a, t->d_st2lo, h->d_lstart, (const double2 *)arr_in, (double2 *)buf_out, rows,
                                                                   h->minc, h->l_max, h->n_m);
         else
-            rside_tiled_kernel<true><<<grid, 256, 0, h->stream>>>(a, t->d_st2lo, h->d_lstart, (const double2 *)buf_in, (double2 *)arr_out, rows,
+            rside_tiled_kernel<true><<<grid, 256, 0, t->stream>>>(a, t->d_st2lo, h->d_lstart, (const double2 *)buf_in, (double2 *)arr_out, rows,
                                                                  h->minc, h->l_max, h->n_m);
         (void)blocks;
     }
@@ -419,16 +492,17 @@ extern "C" int magic_transp_unpack_r2lm_dev(magic_transp *t, const double *recvb
 // all-to-all(v): segment p of sendbuf goes to rank p, segment p of recvbuf comes from rank p
 static int exchange(magic_transp *t, long long nf, const std::vector<long long> &scnt, const std::vector<long long> &sdisp,
                     const std::vector<long long> &rcnt, const std::vector<long long> &rdisp) {
-    cudaStream_t st = t->h->stream;
+    cudaStream_t st = t->stream;
     const int me = t->rank;
     if (!t->comm) MFAIL("transposer was created without an NCCL id: only the pack/unpack halves are available");
-    MCHECK(cudaMemcpyAsync(t->recvbuf + 2 * nf * rdisp[me], t->sendbuf + 2 * nf * sdisp[me], sizeof(double) * 2 * nf * scnt[me],
-                           cudaMemcpyDeviceToDevice, st));
+    if (scnt[me] > 0)
+        MCHECK(cudaMemcpyAsync(t->recvbuf + 2 * nf * rdisp[me], t->sendbuf + 2 * nf * sdisp[me], sizeof(double) * 2 * nf * scnt[me],
+                               cudaMemcpyDeviceToDevice, st));
     NCHECK(g_nccl.GroupStart());
     for (int p = 0; p < t->n_procs; p++) {
         if (p == me) continue;
-        NCHECK(g_nccl.Send(t->sendbuf + 2 * nf * sdisp[p], (size_t)(2 * nf * scnt[p]), ncclDouble, p, t->comm, st));
-        NCHECK(g_nccl.Recv(t->recvbuf + 2 * nf * rdisp[p], (size_t)(2 * nf * rcnt[p]), ncclDouble, p, t->comm, st));
+        if (scnt[p] > 0) NCHECK(g_nccl.Send(t->sendbuf + 2 * nf * sdisp[p], (size_t)(2 * nf * scnt[p]), ncclDouble, p, t->comm, st));
+        if (rcnt[p] > 0) NCHECK(g_nccl.Recv(t->recvbuf + 2 * nf * rdisp[p], (size_t)(2 * nf * rcnt[p]), ncclDouble, p, t->comm, st));
     }
     NCHECK(g_nccl.GroupEnd());
     return 0;

@@ -22,6 +22,7 @@ SYMBOLS = [
     "magic_rloop_create", "magic_rloop_destroy", "magic_rloop_run", "magic_rloop_run_dev", "magic_rloop_sync",
     "magic_rloop_set_rotation", "magic_rloop_get_torques", "magic_rloop_get_br_v_bcs", "magic_rloop_launch_count", "magic_rloop_last_timing", "magic_rloop_legendre_flops",
     "magic_transp_unique_id", "magic_transp_create", "magic_transp_destroy", "magic_transp_extents",
+    "magic_transp_create_part", "magic_transp_set_stream", "magic_transp_info", "magic_rloop_run_lm_dev",
     "magic_transp_lm2r_dev", "magic_transp_r2lm_dev", "magic_transp_lm2r_dev_n", "magic_transp_r2lm_dev_n", "magic_transp_lm2r", "magic_transp_r2lm",
     "magic_transp_pack_lm2r_dev", "magic_transp_unpack_lm2r_dev", "magic_transp_pack_r2lm_dev",
     "magic_transp_unpack_r2lm_dev", "magic_transp_counts",

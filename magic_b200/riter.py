@@ -45,6 +45,14 @@ class _FieldsOut(C.Structure):
     _fields_ = [(n, c_void_p) for n in OUT_NAMES] + [("dtrkc", c_void_p), ("dthkc", c_void_p)]
 
 
+class _LmIn(C.Structure):
+    _fields_ = [("flow", c_void_p), ("s", c_void_p), ("field", c_void_p)]
+
+
+class _LmOut(C.Structure):
+    _fields_ = [("dflowdt", c_void_p), ("dsdt", c_void_p), ("dbdt", c_void_p), ("dtrkc", c_void_p), ("dthkc", c_void_p)]
+
+
 class RadialLoop:
     """initialize_radialLoop + radialLoopG (radialLoop.f90:26-101) for the levels of one rank."""
 
@@ -122,6 +130,14 @@ class RadialLoop:
         """Device-pointer call: dict name -> int device pointer (e.g. torch tensor .data_ptr())."""
         fin, fout, keep = self._structs(fields_dev, out_dev, dtrkc_dev, dthkc_dev, device=True)
         check(self.lib.magic_rloop_run_dev(self._h, byref(fin), byref(fout), c_double(time)))
+
+    def run_lm_dev(self, transposer, flow_LM, s_LM, field_LM, dflowdt_LM, dsdt_LM, dbdt_LM, dtrkc_dev, dthkc_dev, time=0.0):
+        """The whole hot path of a step on LM-distributed device containers (ints = device pointers; field/dbdt 0 without
+        l_mag): transp_LMloc_to_Rloc -> radialLoopG -> transp_Rloc_to_LMloc (step_time.f90:485-612), the transposes
+        pipelined chunk by chunk against the compute when there is more than one rank."""
+        i = _LmIn(int(flow_LM), int(s_LM), int(field_LM) or None)
+        o = _LmOut(int(dflowdt_LM), int(dsdt_LM), int(dbdt_LM) or None, int(dtrkc_dev), int(dthkc_dev))
+        check(self.lib.magic_rloop_run_lm_dev(self._h, transposer._h, byref(i), byref(o), c_double(time)))
 
     def set_rotation(self, omega_ma, omega_ic):
         """Boundary rotation rates of the coming step (omega_ma, omega_ic of v_rigid_boundary)."""

@@ -56,6 +56,21 @@ class Transposer:
         self.nlm_loc = self.ulm - self.llm + 1
         self.nr_loc = self.nRstop - self.nRstart + 1
 
+    def part(self, lev_off, lev_cnt):
+        """magic_transp_create_part: a transposer that moves, for every rank q, only the levels
+        [lev_off[q], lev_off[q]+lev_cnt[q]) of q's slab (one level chunk).  Array shapes stay those of the parent."""
+        child = object.__new__(Transposer)
+        child.lib, child.sht, child.rank, child.n_procs = self.lib, self.sht, self.rank, self.n_procs
+        child.n_r_max, child.n_fields = self.n_r_max, self.n_fields
+        child.llm, child.ulm, child.nlm_loc, child.nr_loc = self.llm, self.ulm, self.nlm_loc, self.nr_loc
+        off = (c_int * self.n_procs)(*[int(x) for x in lev_off])
+        cnt = (c_int * self.n_procs)(*[int(x) for x in lev_cnt])
+        child._h = c_void_p()
+        check(self.lib.magic_transp_create_part(self._h, off, cnt, byref(child._h)))
+        child.nRstart, child.nRstop = self.nRstart + int(lev_off[self.rank]), self.nRstart + int(lev_off[self.rank]) + int(lev_cnt[self.rank]) - 1
+        child._parent = self  # keep the parent alive
+        return child
+
     def destroy_comm(self):
         if self._h:
             self.lib.magic_transp_destroy(self._h)

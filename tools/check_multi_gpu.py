@@ -61,7 +61,46 @@ def main():
         rl1.finalize()
         for nm in ["dwdt", "dzdt", "dsdt", "dbdt", "djdt", "dVxBhLM"]:
             ok4 = ok4 and np.array_equal(got[nm], ref[nm][rs[0] - 1:re[0]])
-    flags = torch.tensor([ok1, ok2, ok3, ok4], dtype=torch.int32, device=dev)
+    # pipelined LM -> LM path (magic_rloop_run_lm_dev): bit-identical to lm2r -> radial loop -> r2lm done one after the other.
+    # level_chunk=4 gives 2-3 chunks per rank (and, with n_r_max=19, ranks with different chunk counts at some world sizes).
+    def lm_container(names):
+        g = np.stack([gfields[n] for n in names])                     # [nf][n_r_max][lm_max] st order
+        return torch.from_numpy(np.ascontiguousarray(g[:, :, lo2st[ls[rank] - 1:le[rank]]])).to(dev)
+    flow_LM, s_LM, field_LM = lm_container(["w", "dw", "ddw", "z", "dz"]), lm_container(["s", "s"]), lm_container(["b", "db", "ddb", "aj", "dj"])
+    rl = RadialLoop(sht, p, rad, level_chunk=4)
+    zl = lambda n: torch.zeros(n, n_r_max, tr.nlm_loc, dtype=torch.complex128, device=dev)
+    zr = lambda n: torch.zeros(n, tr.nr_loc, sht.lm_max, dtype=torch.complex128, device=dev)
+    dtr, dth = torch.zeros(tr.nr_loc, dtype=torch.float64, device=dev), torch.zeros(tr.nr_loc, dtype=torch.float64, device=dev)
+    # (a) sequential reference
+    fR, sR, bR, dfR, dsR, dbR = zr(5), zr(2), zr(5), zr(3), zr(2), zr(3)
+    torch.cuda.synchronize()
+    tr.transp_lm2r_dev_n(5, flow_LM.data_ptr(), fR.data_ptr()); tr.transp_lm2r_dev_n(2, s_LM.data_ptr(), sR.data_ptr())
+    tr.transp_lm2r_dev_n(5, field_LM.data_ptr(), bR.data_ptr())
+    fin = {"w": fR[0], "dw": fR[1], "ddw": fR[2], "z": fR[3], "dz": fR[4], "s": sR[0], "b": bR[0], "db": bR[1], "ddb": bR[2], "aj": bR[3], "dj": bR[4]}
+    fout = {"dwdt": dfR[0], "dzdt": dfR[1], "dpdt": dfR[2], "dsdt": dsR[0], "dVSrLM": dsR[1], "dbdt": dbR[0], "djdt": dbR[1], "dVxBhLM": dbR[2]}
+    rl.radialLoop_dev({k: v.data_ptr() for k, v in fin.items()}, {k: v.data_ptr() for k, v in fout.items()}, dtr.data_ptr(), dth.data_ptr())
+    ref_LM = [zl(3), zl(2), zl(3)]
+    tr.transp_r2lm_dev_n(3, dfR.data_ptr(), ref_LM[0].data_ptr()); tr.transp_r2lm_dev_n(2, dsR.data_ptr(), ref_LM[1].data_ptr())
+    tr.transp_r2lm_dev_n(3, dbR.data_ptr(), ref_LM[2].data_ptr())
+    ext.synchronize()
+    dtr_ref = dtr.clone()
+    # (b) pipelined, twice (buffers and events are reused from step to step)
+    got_LM = [zl(3), zl(2), zl(3)]
+    ok5 = True
+    for _ in range(2):
+        for g in got_LM:
+            g.zero_()
+        dtr.zero_()
+        torch.cuda.synchronize()
+        rl.run_lm_dev(tr, flow_LM.data_ptr(), s_LM.data_ptr(), field_LM.data_ptr(), got_LM[0].data_ptr(), got_LM[1].data_ptr(),
+                      got_LM[2].data_ptr(), dtr.data_ptr(), dth.data_ptr())
+        ext.synchronize()
+        torch.cuda.synchronize()
+        for a, b in zip(got_LM, ref_LM):
+            ok5 = ok5 and bool(torch.equal(a, b))
+        ok5 = ok5 and bool(torch.equal(dtr, dtr_ref)) and float(ref_LM[0].abs().sum()) > 0
+    rl.finalize()
+    flags = torch.tensor([ok1, ok2, ok3, ok4, ok5], dtype=torch.int32, device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if bool(flags.min().item()) else "FAIL", flags.tolist(), "world", world, flush=True)
