@@ -412,6 +412,9 @@ def run_magic(args, gs):
 
 
 def main():
+    # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO in some images) off it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("BENCH_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse()
     from magic_b200.workload import config_sizes
     gs = config_sizes(args.workload)

@@ -576,7 +576,12 @@ static int lmpipe_build(magic_rloop *rl, magic_transp *t) {
         p->C = std::max(p->C, (int)cs[q].size());
     }
     if (cs[rank] != rl->chunk_start || cz[rank] != rl->chunk_size) MFAIL("magic_rloop_run_lm_dev: internal chunk mismatch");
-    MCHECK(cudaStreamCreateWithFlags(&p->comm, cudaStreamNonBlocking));
+    {   // highest priority: the compute kernels fill every SM with long grids, so the pack / NCCL / unpack CTAs of the
+        // communication stream must be picked first whenever a slot frees up or they trail behind the chunk they serve
+        int lo = 0, hi = 0;
+        MCHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        MCHECK(cudaStreamCreateWithPriority(&p->comm, cudaStreamNonBlocking, hi));
+    }
     MCHECK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
     MCHECK(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
     for (int c = 0; c < p->C; c++) {
