@@ -119,6 +119,10 @@ typedef struct magic_rloop magic_rloop;
 int magic_rloop_create(magic_sht *h, const magic_params *p, const magic_radial *rad, int n_r_loc, int level_chunk,
                        magic_rloop **out);
 int magic_rloop_destroy(magic_rloop *rl);
+/* Host only: the level chunks a loop over n_r_loc levels created with an explicit level_chunk works in (at most
+ * n_r_loc entries): full chunks of level_chunk levels, a remainder <= level_chunk/4 folded into the last chunk, a larger one
+ * as a short last chunk.  Every rank can compute every other rank's chunks from this (magic_rloop_run_lm_dev relies on it). */
+int magic_level_chunks(int n_r_loc, int level_chunk, int *n_chunks, int *start, int *size);
 /* Host-pointer call: H2D of the inputs, the loop, D2H of the outputs (what rIter_cuda_t calls). */
 int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const magic_fields_out *out, double time);
 /* Device-pointer call (inputs/outputs already resident in HBM, e.g. produced by magic_transp_*_dev). */

@@ -83,6 +83,18 @@ static void level_chunks(int n_r_loc, int level_chunk, std::vector<int> &start, 
     }
 }
 
+extern "C" int magic_level_chunks(int n_r_loc, int level_chunk, int *n_chunks, int *start, int *size) {
+    if (n_r_loc < 1 || level_chunk < 1 || !n_chunks) MFAIL("magic_level_chunks: bad arguments");
+    std::vector<int> s, z;
+    level_chunks(n_r_loc, level_chunk, s, z);
+    *n_chunks = (int)s.size();
+    for (size_t i = 0; i < s.size(); i++) {
+        if (start) start[i] = s[i];
+        if (size) size[i] = z[i];
+    }
+    return 0;
+}
+
 static void add_scal(BatchSpec &s, Term t0, Term t1, int lmask, int &field_counter, int &slot) {
     ScalCol c{};
     c.t[0] = t0; c.t[1] = t1; c.lmask = lmask;

@@ -15,8 +15,10 @@
 //   CTA tile 128 x 64, 8 warps as 4(M) x 2(N), warp tile 32 x 32 = 4x4 DMMA tiles, k-tile 16.
 //   A_KCONTIG=false (synthesis): A tile stored As[k][m] (m = colatitude contiguous in the table).
 //   A_KCONTIG=true  (analysis) : A tile stored As[m][k] (m = degree row, k = colatitude contiguous).
-//   Leading dimensions are == 4 (mod 16) doubles so the 16 lanes of each half-warp of an LDS.64 fragment
-//   load hit 16 distinct 8-byte banks.
+//   The [k][m] / [k][n] tiles have leading dimensions == 4 (mod 16) doubles, the [m][k] tile an XOR swizzle (below), so the
+//   16 lanes of each half-warp of an LDS.64 fragment load hit 16 distinct 8-byte banks.
+//   Each K segment of a CTA tile starts at the first k-tile that holds a non-negligible table entry for any of its rows
+//   (triangular polar skipping, GemmProb::ks0/ks1).
 #pragma once
 #include "common.cuh"
 

@@ -45,6 +45,16 @@ class _FieldsOut(C.Structure):
     _fields_ = [(n, c_void_p) for n in OUT_NAMES] + [("dtrkc", c_void_p), ("dthkc", c_void_p)]
 
 
+def level_chunks(n_r_loc, level_chunk):
+    """magic_level_chunks: (start, size) lists of the level chunks of a slab (host only)."""
+    lib = load_library()
+    n = c_int()
+    st = (c_int * n_r_loc)()
+    sz = (c_int * n_r_loc)()
+    check(lib.magic_level_chunks(c_int(n_r_loc), c_int(level_chunk), byref(n), st, sz))
+    return list(st[:n.value]), list(sz[:n.value])
+
+
 class _LmIn(C.Structure):
     _fields_ = [("flow", c_void_p), ("s", c_void_p), ("field", c_void_p)]
 

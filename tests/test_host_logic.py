@@ -57,3 +57,24 @@ def test_workload_shapes_and_seeding():
     assert np.all(f1["w"][:, o.lm2m == 0].imag == 0) and np.all(f1["w"][:, 0] == 0)
     p = make_params("mhd", 33)
     assert p.l_mag == 1 and p.LFfac == pytest.approx(200.0) and p.n_r_max == 33
+
+
+def test_level_chunks_partition_every_slab():
+    """magic_level_chunks (host only): chunks tile the slab, all but the last have exactly level_chunk levels, a small
+    remainder is folded into the last chunk -- and the ranks of a getBlocks decomposition get chunk counts that differ by
+    at most one (magic_rloop_run_lm_dev pads the shorter lists with empty parts)."""
+    from magic_b200.riter import level_chunks
+    from magic_b200.transpose import get_blocks
+    for n in list(range(1, 70)) + [128, 129, 257]:
+        for lc in (1, 4, 16, 32):
+            st, sz = level_chunks(n, lc)
+            assert st[0] == 0 and sum(sz) == n and all(a + b == c for a, b, c in zip(st, sz, st[1:] + [n]))
+            eff = min(lc, n)
+            assert all(z == eff for z in sz[:-1])
+            assert 1 <= sz[-1] <= eff + eff // 4
+    assert level_chunks(257, 16)[1] == [16] * 15 + [17]
+    assert level_chunks(33, 16)[1] == [16, 17] and level_chunks(32, 16)[1] == [16, 16]
+    for n_r, n_procs in ((257, 8), (257, 2), (121, 4), (19, 2)):
+        rs, re = get_blocks(n_r, n_procs)
+        counts = [len(level_chunks(int(e - s + 1), 16 if n_r > 19 else 4)[0]) for s, e in zip(rs, re)]
+        assert max(counts) - min(counts) <= 1, counts
