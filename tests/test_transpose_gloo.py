@@ -84,3 +84,65 @@ def test_two_rank_transpose_matches_oracle(l_max, minc, n_r_max):
     ref_LM = o.transp_r2lm(world, n_r_max, ref_R)
     for p in range(world):
         assert np.array_equal(ref_LM[p], arr_LM[p])
+
+
+def _worker_parts(rank, world, port, l_max, n_r_max, n_fields, level_chunk, ret):
+    """The exchange sequence of magic_rloop_run_lm_dev on the host: all inbound parts in chunk order, then all outbound
+    parts, every part an all-to-all restricted to the c-th level chunk of each rank (empty for ranks with fewer chunks)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from magic_b200.riter import level_chunks
+    from magic_b200.transpose import get_blocks, lo_map
+    lo2st, ls, le = lo_map(l_max, l_max, 1, world)
+    rs, re = get_blocks(n_r_max, world)
+    lm_max = len(lo2st)
+    nlm = le[rank] - ls[rank] + 1
+    nr = re[rank] - rs[rank] + 1
+    chunks = [level_chunks(int(re[q] - rs[q] + 1), level_chunk) for q in range(world)]
+    C = max(len(c[0]) for c in chunks)
+
+    def part(q, c):  # (first global level index, count) of rank q's levels in part c
+        st, sz = chunks[q]
+        return (rs[q] - 1 + st[c], sz[c]) if c < len(st) else (re[q], 0)
+
+    rng = np.random.default_rng(300 + rank)
+    arr_LM = rng.standard_normal((n_fields, n_r_max, nlm)) + 1j * rng.standard_normal((n_fields, n_r_max, nlm))
+    arr_R = np.zeros((n_fields, nr, lm_max), dtype=np.complex128)
+    for c in range(C):  # lm2r parts
+        send = [torch.from_numpy(np.ascontiguousarray(arr_LM[:, part(q, c)[0]:part(q, c)[0] + part(q, c)[1], :]).reshape(-1)) for q in range(world)]
+        g0, n0 = part(rank, c)
+        recv = [torch.empty(n_fields * n0 * (le[p] - ls[p] + 1), dtype=torch.complex128) for p in range(world)]
+        _alltoallv(recv, send, rank, world)
+        for p in range(world):
+            seg = recv[p].numpy().reshape(n_fields, n0, le[p] - ls[p] + 1)
+            arr_R[:, g0 - (rs[rank] - 1):g0 - (rs[rank] - 1) + n0, lo2st[ls[p] - 1:le[p]]] = seg
+    back = np.zeros_like(arr_LM)
+    for c in range(C):  # r2lm parts
+        g0, n0 = part(rank, c)
+        r0 = g0 - (rs[rank] - 1)
+        send = [torch.from_numpy(np.ascontiguousarray(arr_R[:, r0:r0 + n0, lo2st[ls[p] - 1:le[p]]]).reshape(-1)) for p in range(world)]
+        recv = [torch.empty(n_fields * part(q, c)[1] * nlm, dtype=torch.complex128) for q in range(world)]
+        _alltoallv(recv, send, rank, world)
+        for q in range(world):
+            gq, nq = part(q, c)
+            back[:, gq:gq + nq, :] = recv[q].numpy().reshape(n_fields, nq, nlm)
+    ret[rank] = (arr_LM, arr_R, back, C, [len(c[0]) for c in chunks])
+    dist.destroy_process_group()
+
+
+def test_two_rank_chunk_parts_compose_to_the_full_transpose():
+    """n_r_max=19 on 2 ranks with level_chunk=4: slabs of 9 and 10 levels -> 2 and 3 chunks, so rank 0 takes part in a third
+    exchange in which it owns no levels."""
+    from oracle.oracle import Oracle
+    world, n_fields, l_max, n_r_max = 2, 2, 16, 19
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_parts, args=(world, _free_port(), l_max, n_r_max, n_fields, 4, ret), nprocs=world, join=True)
+    assert ret[0][3] == 3 and ret[0][4] == [2, 3]
+    o = Oracle(l_max)
+    arr_LM = [ret[p][0] for p in range(world)]
+    ref_R = o.transp_lm2r(world, n_r_max, arr_LM)
+    for q in range(world):
+        assert np.array_equal(ret[q][1], ref_R[q])
+        assert np.array_equal(ret[q][2], ret[q][0])
