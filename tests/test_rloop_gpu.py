@@ -136,6 +136,26 @@ def test_full_sphere_centre(physics, minc, n_phi_tot):
     assert got["dtrkc"][-1] == 1e10 and got["dthkc"][-1] == 1e10
 
 
+DC_OUT = ["dwdt", "dzdt", "dsdt", "dVSrLM", "dVxVhLM"]
+
+
+@pytest.mark.parametrize("physics,full_sphere", [("hydro", True), ("hydro", False), ("mhd", False)])
+def test_double_curl_form(physics, full_sphere):
+    """l_double_curl (forced by radial_scheme='FD', Namelists.f90:299-304; what samples/full_sphere runs): get_dwdt_double_curl
+    (get_td.f90:199-309) with its Coriolis couplings cut at l_R(nR), and the horizontal advection handed out as dVxVhLM for
+    finish_exp_pol (updateWP.f90:1002-1031); no dpdt.  The oracle's branch is pinned to the reference by
+    tests/test_full_sphere.py."""
+    n_r = 10
+    mhd = physics == "mhd"
+    l_R = None if mhd else np.minimum(32, (1 + 32 * np.sqrt(np.linspace(1.0, 0.05, n_r) / 0.4)).astype(int))
+    o, p, rad, got, ref, ex = run_both(16 if mhd else 0, n_r, physics, list(range(1, n_r + 1)), minc=1 if mhd else 3,
+                                       n_phi_tot=0 if mhd else 96, l_R=l_R, ktopv=1, kbotv=1, full_sphere=full_sphere,
+                                       tweak=dict(l_double_curl=1))
+    assert np.linalg.norm(ref["dVxVhLM"]) > 0 and np.linalg.norm(ref["dpdt"]) == 0
+    compare(o, p, rad, got, ref, ex, DC_OUT + (["dbdt", "djdt", "dVxBhLM"] if mhd else []))
+    assert np.all(got["dpdt"] == 0)
+
+
 def test_hydro_bench_anel_shape():
     """BASELINE config 2 (samples/hydro_bench_anel as shipped: n_phi_tot=288 -> l_max=96, n_r=97, anelastic hydro with
     u.grad u advection and viscous heating, stress-free walls): a CMB level, three bulk levels and the ICB level."""
