@@ -122,7 +122,8 @@ class ShellHost:
 
     def __init__(self, lm2l, lm2m, radial_loop, n_r_max=33, n_cheb_max=None, radratio=0.35, ra=1e5, ek=1e-3, pr=1.0,
                  prmag=5.0, dtmax=1e-4, alpha=0.6, init_s1=404, amp_s1=0.1, init_b1=3, amp_b1=5.0, l_mag=True, ktopv=2,
-                 kbotv=2, strat=0.0, polind=2.0, g0=0.0, g1=1.0, g2=0.0, l_correct_AMz=False, l_correct_AMe=False):
+                 kbotv=2, strat=0.0, polind=2.0, g0=0.0, g1=1.0, g2=0.0, l_correct_AMz=False, l_correct_AMe=False, l_heat=True,
+                 po=0.0, prec_angle=23.5):
         self.lm2l = np.asarray(lm2l)
         self.lm2m = np.asarray(lm2m)
         self.lm_max = len(self.lm2l)
@@ -133,7 +134,11 @@ class ShellHost:
         self.l_mag, self.ktopv, self.kbotv = l_mag, ktopv, kbotv
         self.l_correct_AMz, self.l_correct_AMe = l_correct_AMz, l_correct_AMe
         self.opr, self.opm = 1.0 / pr, 1.0 / prmag
-        self.BuoFac = ra / pr                 # preCalculations.f90:170-176 (lScale=1)
+        self.l_heat = l_heat and ra != 0.0    # Namelists.f90:429
+        self.BuoFac = ra / pr if self.l_heat else 0.0   # preCalculations.f90:170-179 (lScale=1)
+        # precession (Namelists.f90:581-588, preCalculations.f90:164-166, updateZ.f90:231-235): the Poincare force on (1,1)
+        self.oek = 1.0 / ek
+        self.prec_fac = np.sqrt(8.0 * np.pi / 3.0) * po * self.oek ** 2 * np.sin(np.deg2rad(prec_angle)) if po != 0.0 else 0.0
         self.LFfac = 1.0 / (ek * prmag)       # preCalculations.f90:158
         r, or1, or2 = g.r, g.or1, g.or2
         self.rgrav = g0 + g1 * r / g.r_cmb + g2 * g.r_cmb ** 2 * or2            # radial.f90:628
@@ -168,7 +173,8 @@ class ShellHost:
         self.tops = np.zeros(lm_max, dtype=np.complex128)
         self.bots = np.zeros(lm_max, dtype=np.complex128)
         lm00 = self._lm(0, 0)
-        self.bots[lm00] = sq4pi               # preCalculations.f90:415-418
+        if self.l_heat:
+            self.bots[lm00] = sq4pi           # preCalculations.f90:415-418
         # ---- initS: conductive state (ps_cond, entropy diffusion, epsc=0; init_fields.f90:2270-2291) + one mode (:428-541)
         M = self.opr * (g.D2 + (self.beta + self.dLtemp0 + 2.0 * or1)[:, None] * g.D1)
         M[0] = 0.0
@@ -177,8 +183,9 @@ class ShellHost:
         M[-1, -1] = 1.0
         rhs = np.zeros((N, 1))
         rhs[0, 0], rhs[-1, 0] = self.tops[lm00].real, self.bots[lm00].real
-        self.s[:, lm00] = g.solve(M, rhs, (0, N - 1))[:, 0]
-        if init_s1 >= 100:
+        if self.l_heat:
+            self.s[:, lm00] = g.solve(M, rhs, (0, N - 1))[:, 0]
+        if self.l_heat and init_s1 >= 100:
             l, m = init_s1 // 100, init_s1 % 100
             x = 2.0 * r - g.r_cmb - g.r_icb
             s1 = 1.0 - 3.0 * x ** 2 + 3.0 * x ** 4 - x ** 6
@@ -238,6 +245,8 @@ class ShellHost:
         self.old["z"] = fac * self.z
         imp = fac * (ddz - beta[:, None] * self.dz -
                      (fac + (dbeta + 2.0 * beta * g.or1)[:, None]) * self.z)
+        if self.prec_fac != 0.0:   # updateZ.f90:955-958, evaluated at the time the fields belong to
+            imp[:, self._lm(1, 1)] += self.prec_fac * (np.sin(self.oek * self.time) - 1j * np.cos(self.oek * self.time))
         imp[0] = 0.0
         imp[-1] = 0.0      # n_r_top=n_r_cmb+1 .. n_r_bot=n_r_icb-1
         self.impl["z"] = imp
@@ -348,7 +357,9 @@ class ShellHost:
     # ------------------------------------------------------------------------------------------------
     def fields_Rloc(self):
         """What transp_LMloc_to_Rloc hands to the radial loop (step_time.f90:1005-1132)."""
-        f = dict(w=self.w, dw=self.dw, ddw=self.ddw, z=self.z, dz=self.dz, s=self.s)
+        f = dict(w=self.w, dw=self.dw, ddw=self.ddw, z=self.z, dz=self.dz)
+        if self.l_heat:
+            f["s"] = self.s
         if self.l_mag:
             f.update(b=self.b, db=self.db, ddb=self.ddb, aj=self.aj, dj=self.dj)
         return f
@@ -360,7 +371,8 @@ class ShellHost:
         or2 = g.or2[:, None]
         l0 = (self.lm2l == 0)[None, :]
         # finish_explicit_assembly (LMLoop.f90:390-453), dentropy0=0
-        self.expl["s"][0] = self.orho1[:, None] * (out["dsdt"] - or2 * (g.D1 @ out["dVSrLM"]))   # updateS.f90:587-597
+        if self.l_heat:
+            self.expl["s"][0] = self.orho1[:, None] * (out["dsdt"] - or2 * (g.D1 @ out["dVSrLM"]))   # updateS.f90:587-597
         self.expl["w"][0] = np.array(out["dwdt"])
         self.expl["p"][0] = np.array(out["dpdt"])
         self.expl["z"][0] = np.array(out["dzdt"])
@@ -395,12 +407,15 @@ class ShellHost:
 
         def up_s(l, idx):
             self.s[:, idx] = g.solve(mats["s"][l], rhs[:, idx], (0, N - 1))
-        per_degree(up_s)
-        self.s[:, m0] = self.s[:, m0].real
-        rotate("s")
-        self._rhs_imp_s()
+        if self.l_heat:
+            per_degree(up_s)
+            self.s[:, m0] = self.s[:, m0].real
+            rotate("s")
+            self._rhs_imp_s()
         # ---- updateZ (updateZ.f90:191-488)
         rhs = self._imex_rhs("z", wts)
+        if self.prec_fac != 0.0:   # updateZ.f90:385-392: the implicit half of the Poincare force, at the new time
+            rhs[:, self._lm(1, 1)] += wl1 * self.prec_fac * (np.sin(self.oek * self.time) - 1j * np.cos(self.oek * self.time))
         rhs[0], rhs[-1] = 0.0, 0.0
 
         def up_z(l, idx):
