@@ -70,6 +70,10 @@ class ChebShell:
         self.D2 = (d2 * drx ** 2) @ Tinv
         self.D3 = (d3 * drx ** 3) @ Tinv
         self.T, self.Tinv = T, Tinv
+        # get_dr on raw (not dealiased) data, e.g. the explicit terms of finish_exp_*: the reference differentiates the modes
+        # below n_cheb_max only (radial_derivatives.f90 get_dcheb with r_scheme%n_max)
+        keep = (np.arange(N) < self.n_cheb_max).astype(float)
+        self.D1t = ((d1 * drx) * keep[None, :]) @ Tinv
         # basis of the reference's coefficient space: f = B0 c with rnorm = sqrt(2/(N-1)) and boundary_fac = 1/2 on the
         # first and last mode (chebyshev.f90; the same convention as costf1)
         wts = np.ones(N)
@@ -109,6 +113,42 @@ class ChebShell:
         return out
 
 
+class ChebEvenIC:
+    """Inner-core radial grid r_icb .. 0 and the even Chebyshev basis on it (radial.f90:798-822, chebyshev_polynoms.f90
+    `get_chebs_even`): the n_r_ic_max first extrema of T_(2 n_r_ic_max - 2) mapped to [-r_icb, r_icb], basis functions
+    T_0, T_2, ..., derivatives with respect to r."""
+
+    def __init__(self, n_r_ic_max, n_cheb_ic_max, r_icb):
+        Ni = n_r_ic_max
+        self.n_r_ic_max, self.n_cheb_ic_max = Ni, n_cheb_ic_max
+        y = np.cos(np.pi * np.arange(Ni) / (2.0 * Ni - 2.0))
+        self.r = r_icb * y
+        self.r[-1] = 0.0
+        with np.errstate(divide="ignore"):
+            self.O_r = np.where(self.r > 0.0, 1.0 / np.where(self.r > 0.0, self.r, 1.0), 0.0)
+        map_fac = 1.0 / r_icb
+        cheb, dcheb, d2cheb = (np.zeros((Ni, Ni)) for _ in range(3))     # [mode, point]
+        cheb[0] = 1.0
+        last, dlast, d2last = y.copy(), np.full(Ni, map_fac), np.zeros(Ni)   # the odd polynomial in between
+        for n in range(1, Ni):
+            cheb[n] = 2 * y * last - cheb[n - 1]
+            dcheb[n] = 2 * map_fac * last + 2 * y * dlast - dcheb[n - 1]
+            d2cheb[n] = 4 * map_fac * dlast + 2 * y * d2last - d2cheb[n - 1]
+            last, dlast, d2last = (2 * y * cheb[n] - last, 2 * map_fac * cheb[n] + 2 * y * dcheb[n] - dlast,
+                                   4 * map_fac * dcheb[n] + 2 * y * d2cheb[n] - d2last)
+        self.cheb, self.dcheb, self.d2cheb = cheb, dcheb, d2cheb
+        self.cheb_norm = np.sqrt(2.0 / (Ni - 1))
+        w = np.ones(Ni)
+        w[0] = w[-1] = 0.5          # costf1 convention: first and last mode carry 1/2
+        self.w = w
+        self.B0 = (cheb * w[:, None]).T * self.cheb_norm                  # grid values = B0 . coefficients
+        keep = (np.arange(Ni) < n_cheb_ic_max).astype(float)
+        B0inv = np.linalg.inv(self.B0)
+        # get_ddr_even (radial_derivatives_even.f90:16-70): derivatives from the modes below n_cheb_ic_max
+        self.D1 = ((dcheb * (w * keep)[:, None]).T * self.cheb_norm) @ B0inv
+        self.D2 = ((d2cheb * (w * keep)[:, None]).T * self.cheb_norm) @ B0inv
+
+
 def _cc2real(c, m):
     """useful.f90 cc2real: |c|^2 (m=0) or 2|c|^2."""
     return np.where(m == 0, 1.0, 2.0) * (c.real ** 2 + c.imag ** 2)
@@ -123,7 +163,7 @@ class ShellHost:
     def __init__(self, lm2l, lm2m, radial_loop, n_r_max=33, n_cheb_max=None, radratio=0.35, ra=1e5, ek=1e-3, pr=1.0,
                  prmag=5.0, dtmax=1e-4, alpha=0.6, init_s1=404, amp_s1=0.1, init_b1=3, amp_b1=5.0, l_mag=True, ktopv=2,
                  kbotv=2, strat=0.0, polind=2.0, g0=0.0, g1=1.0, g2=0.0, l_correct_AMz=False, l_correct_AMe=False, l_heat=True,
-                 po=0.0, prec_angle=23.5):
+                 po=0.0, prec_angle=23.5, l_cond_ic=False, l_rot_ic=False, sigma_ratio=1.0, n_r_ic_max=17, n_cheb_ic_max=15):
         self.lm2l = np.asarray(lm2l)
         self.lm2m = np.asarray(lm2m)
         self.lm_max = len(self.lm2l)
@@ -170,6 +210,18 @@ class ShellHost:
         N, lm_max = self.N, self.lm_max
         z = lambda: np.zeros((N, lm_max), dtype=np.complex128)
         self.w, self.z, self.p, self.s, self.b, self.aj = z(), z(), z(), z(), z(), z()
+        # conducting and / or freely rotating inner core (kbotb=3, nRotIC=1; Namelists.f90:398-407, :737-739)
+        self.l_cond_ic, self.l_rot_ic, self.O_sr = l_cond_ic and l_mag, l_rot_ic, 1.0 / sigma_ratio
+        self.omega_ic = 0.0
+        self.lorentz_torque_ic = 0.0
+        self.c_z10_omega_ic = 0.5 * np.sqrt(3.0 / np.pi) * or2[-1] / self.rho0[-1]      # preCalculations.f90:313-318
+        self.c_dt_z10_ic = 0.2 * g.r_icb * self.rho0[-1]                                # :336 (rho_ratio_ic = 1)
+        self.c_lorentz_ic = 0.25 * np.sqrt(3.0 / np.pi) * or2[-1]                       # :343
+        self.dom_ic = dict(old=0.0, impl=0.0, expl=[0.0, 0.0])
+        if self.l_cond_ic:
+            self.ic = ChebEvenIC(n_r_ic_max, n_cheb_ic_max, g.r_icb)
+            zi = lambda: np.zeros((n_r_ic_max, lm_max), dtype=np.complex128)
+            self.b_ic, self.aj_ic = zi(), zi()
         self.tops = np.zeros(lm_max, dtype=np.complex128)
         self.bots = np.zeros(lm_max, dtype=np.complex128)
         lm00 = self._lm(0, 0)
@@ -191,7 +243,18 @@ class ShellHost:
             s1 = 1.0 - 3.0 * x ** 2 + 3.0 * x ** 4 - x ** 6
             self.s[:, self._lm(l, m)] += amp_s1 * s1
         # ---- initB, init_b1=3, insulating inner core (init_fields.f90:1129-1188)
-        if l_mag and init_b1 == 3:
+        if l_mag and init_b1 == 3 and self.l_cond_ic:   # init_fields.f90:1140-1176
+            b_pol = amp_b1 * np.sqrt(3.0 * np.pi) / (3.0 + g.r_cmb)
+            b_tor = -4.0 / 3.0 * amp_b1 * np.sqrt(np.pi / 5.0)
+            ri = self.ic.r
+            self.b[:, self._lm(1, 0)] += b_pol * (r ** 3 - 4.0 / 3.0 * g.r_cmb * r ** 2)
+            self.b_ic[:, self._lm(1, 0)] += b_pol * g.r_icb ** 2 * (0.5 * ri ** 2 / g.r_icb + 0.5 * g.r_icb - 4.0 / 3.0 * g.r_cmb)
+            self.aj[:, self._lm(2, 0)] += b_tor * r * np.sin(np.pi * r / g.r_cmb)
+            arg = np.pi * g.r_icb / g.r_cmb
+            aj_ic1 = (arg - 2.0 * np.sin(arg) * np.cos(arg)) / (arg + np.sin(arg) * np.cos(arg))
+            aj_ic2 = (1.0 - aj_ic1) * g.r_icb * np.sin(arg) / np.cos(arg)
+            self.aj_ic[:, self._lm(2, 0)] += b_tor * (aj_ic1 * ri * np.sin(np.pi * ri / g.r_cmb) + aj_ic2 * np.cos(np.pi * ri / g.r_cmb))
+        elif l_mag and init_b1 == 3:
             b_pol = amp_b1 * np.sqrt(3.0 * np.pi) / 4.0
             b_tor = -4.0 / 3.0 * amp_b1 * np.sqrt(np.pi / 5.0)
             self.b[:, self._lm(1, 0)] += b_pol * (r ** 3 - 4.0 / 3.0 * g.r_cmb * r ** 2 + g.r_icb ** 4 / 3.0 * or1)
@@ -201,6 +264,10 @@ class ShellHost:
         for nm in ("s", "w", "p", "z", "b", "j"):
             self.old[nm], self.impl[nm] = z(), z()
             self.expl[nm] = [z(), z()]
+        if self.l_cond_ic:
+            for nm in ("b_ic", "j_ic"):
+                self.old[nm], self.impl[nm] = zi(), zi()
+                self.expl[nm] = [zi(), zi()]
         self._mats = None
         # startFields.f90:373-432: derivatives and old/implicit terms of the start fields
         self._rhs_imp_s()
@@ -250,6 +317,10 @@ class ShellHost:
         imp[0] = 0.0
         imp[-1] = 0.0      # n_r_top=n_r_cmb+1 .. n_r_bot=n_r_icb-1
         self.impl["z"] = imp
+        if self.l_rot_ic:   # updateZ.f90:996-1008: viscous torque on the inner core (kbotv = 2, visc = 1)
+            z10, dz10 = self.z[-1, self._lm(1, 0)].real, self.dz[-1, self._lm(1, 0)].real
+            self.dom_ic["old"] = self.c_dt_z10_ic * z10
+            self.dom_ic["impl"] = -((2.0 * g.or1[-1] + beta[-1]) * z10 - dz10)
 
     def _rhs_imp_wp(self):
         """get_pol_rhs_imp, updateWP.f90:1089-1336, non double-curl branch (visc=1, dLvisc=0)."""
@@ -291,6 +362,19 @@ class ShellHost:
             a[0] = 0.0
             a[-1] = 0.0
         self.impl["b"], self.impl["j"] = ib, ij
+        if self.l_cond_ic:   # get_mag_ic_rhs_imp, updateB.f90:1077-1187
+            ic = self.ic
+            dLN = self.dL[None, :] * g.or2[-1]
+            lp1 = (self.lm2l + 1.0)[None, :]
+            for nm, f in (("b_ic", self.b_ic), ("j_ic", self.aj_ic)):
+                df, ddf = ic.D1 @ f, ic.D2 @ f
+                self.old[nm] = dLN * f
+                imp = self.opm * self.O_sr * dLN * (ddf + 2.0 * lp1 * ic.O_r[:, None] * df)
+                imp[-1] = (self.opm * self.O_sr * dLN * (1.0 + 2.0 * lp1) * ddf)[-1]     # r = 0: 1/r d/dr -> d2/dr2
+                imp[0] = 0.0
+                imp[:, self.lm2l == 0] = 0.0
+                self.old[nm][:, self.lm2l == 0] = 0.0
+                self.impl[nm] = imp
 
     # ------------------------------------------------------------------------------------------------
     def _weights(self):
@@ -352,7 +436,60 @@ class ShellHost:
                 J[0], J[-1] = I[0], I[-1]
                 mats["b"].append(B)
                 mats["j"].append(J)
+        if self.l_rot_ic:
+            # get_z10Mat (updateZ.f90:1719-1800): zMat(l=1) with the torque balance of the inner core in the ICB row
+            M = mats["z"][1].copy()
+            M[-1] = self.c_dt_z10_ic * I[-1] + wl1 * ((2.0 * g.or1[-1] + bN) * I[-1] - g.D1[-1])
+            mats["z10"] = M
+        if self.l_mag and self.l_cond_ic:
+            mats["bic"], mats["jic"] = [None], [None]
+            for l in range(1, self.l_max + 1):
+                for nm, sr in (("bic", 1.0), ("jic", 1.0 / self.O_sr)):
+                    mats[nm].append(self._coupled_mag_matrix(l, wl1, mats["b" if nm == "bic" else "j"][l], sr))
         self._mats = (wl1, mats)
+
+    def _coupled_mag_matrix(self, l, wl1, M_oc, sr):
+        """get_bMat with kbotb = 3 (updateB.f90:1813-2060): outer-core rows as for the insulating case, then continuity of the
+        potential and of its radial derivative (times sigma_ratio for the toroidal part) at the ICB, then the diffusion
+        equation of the inner core for g(r) with potential = (r / r_icb)^(l+1) g(r).  Acts on COEFFICIENTS (outer-core
+        Chebyshev modes, then inner-core even modes); boundary rows are blind to the dealiased modes."""
+        g, ic, N = self.g, self.ic, self.N
+        Ni, nc, nci = ic.n_r_ic_max, g.n_cheb_max, ic.n_cheb_ic_max
+        dL, lp1 = float(l * (l + 1)), l + 1.0
+        A = np.zeros((N + Ni, N + Ni))
+        oc = M_oc.copy()
+        oc[-1] = np.eye(N)[-1]                               # row N: b_oc(r_icb) ...
+        A[:N, :N] = oc @ g.B0
+        A[N, :N] = (sr * g.D1[-1]) @ g.B0                     # row N+1: d/dr of the outer-core potential ...
+        for row in (0, N - 1, N):
+            A[row, nc:N] = 0.0
+        cn = ic.cheb_norm
+        cheb, dcheb, d2cheb = ic.cheb, ic.dcheb, ic.d2cheb    # [mode, point]
+        fac = dL * g.or2[-1]
+        blk = np.zeros((Ni + 1, Ni))                          # rows: N-1 (continuity), N (derivative), N+1 .. (IC points 2 ..)
+        blk[0, :nci] = -cn * cheb[:nci, 0]
+        blk[1, :nci] = -cn * (dcheb[:nci, 0] + lp1 * g.or1[-1] * cheb[:nci, 0])
+        for k in range(1, Ni - 1):
+            blk[1 + k] = cn * fac * (cheb[:, k] - wl1 * self.opm * self.O_sr * (d2cheb[:, k] + 2.0 * lp1 * ic.O_r[k] * dcheb[:, k]))
+        blk[Ni] = cn * fac * (cheb[:, -1] - wl1 * self.opm * self.O_sr * (1.0 + 2.0 * lp1) * d2cheb[:, -1])
+        blk[:, 0] *= 0.5
+        blk[:, -1] *= 0.5
+        A[N - 1:, N:] = blk
+        return A
+
+    def _solve_coupled(self, A, rhs_oc, rhs_ic):
+        """Right-hand side rows as updateB.f90:500-548; returns grid values (outer core, inner core)."""
+        g, ic, N = self.g, self.ic, self.N
+        rhs = np.concatenate([rhs_oc, rhs_ic], axis=0)
+        rhs[0] = 0.0
+        rhs[N - 1] = 0.0
+        rhs[N] = 0.0
+        f = 1.0 / np.max(np.abs(A), axis=1)
+        c = np.linalg.solve(A * f[:, None], rhs * f[:, None])
+        co, ci = c[:N].copy(), c[N:].copy()
+        co[g.n_cheb_max:] = 0.0
+        ci[ic.n_cheb_ic_max:] = 0.0
+        return g.B0 @ co, ic.B0 @ ci
 
     # ------------------------------------------------------------------------------------------------
     def fields_Rloc(self):
@@ -372,13 +509,22 @@ class ShellHost:
         l0 = (self.lm2l == 0)[None, :]
         # finish_explicit_assembly (LMLoop.f90:390-453), dentropy0=0
         if self.l_heat:
-            self.expl["s"][0] = self.orho1[:, None] * (out["dsdt"] - or2 * (g.D1 @ out["dVSrLM"]))   # updateS.f90:587-597
+            self.expl["s"][0] = self.orho1[:, None] * (out["dsdt"] - or2 * (g.D1t @ out["dVSrLM"]))   # updateS.f90:587-597
         self.expl["w"][0] = np.array(out["dwdt"])
         self.expl["p"][0] = np.array(out["dpdt"])
         self.expl["z"][0] = np.array(out["dzdt"])
         if self.l_mag:
             self.expl["b"][0] = np.array(out["dbdt"])
-            self.expl["j"][0] = out["djdt"] + np.where(l0, 0.0, or2 * (g.D1 @ out["dVxBhLM"]))  # updateB.f90:1030-1037
+            self.expl["j"][0] = out["djdt"] + np.where(l0, 0.0, or2 * (g.D1t @ out["dVxBhLM"]))  # updateB.f90:1030-1037
+        if self.l_rot_ic:     # finish_exp_tor (updateZ.f90:1659-1688), gammatau_gravi = 0
+            self.lorentz_torque_ic = float(out["lorentz_torque_ic"])
+            self.dom_ic["expl"][0] = self.c_lorentz_ic * self.lorentz_torque_ic
+        if self.l_cond_ic:    # finish_exp_mag_ic (updateB.f90:955-1003): advection of the inner-core field by its rotation
+            fac = -self.omega_ic * g.or2[-1] * 1j * self.lm2m[None, :] * self.dL[None, :] if self.l_rot_ic else 0.0
+            for nm, f in (("b_ic", self.b_ic), ("j_ic", self.aj_ic)):
+                e = fac * f
+                e[0] = 0.0
+                self.expl[nm][0] = e
         # dt_courant (courant.f90:277-346)
         self.dtrkc_min, self.dthkc_min = float(np.min(out["dtrkc"])), float(np.min(out["dthkc"]))
         dt_min = min(self.dtrkc_min, self.dthkc_min, 1000.0 * self.dtmax)
@@ -424,6 +570,14 @@ class ShellHost:
             else:
                 self.z[:, idx] = g.solve(mats["z"][l], rhs[:, idx], (0, N - 1))
         per_degree(up_z)
+        if self.l_rot_ic:     # updateZ.f90:300-356, :416-420: z(1,0) with the inner-core torque balance, then update_rot_rates
+            lm10 = self._lm(1, 0)
+            d = self.dom_ic
+            r10 = rhs[:, [lm10]].copy()
+            r10[-1] = wimp * d["old"] + wl2 * d["impl"] + we1 * d["expl"][0] + we2 * d["expl"][1]
+            self.z[:, [lm10]] = g.solve(mats["z10"], r10, (0, N - 1)).real
+            d["expl"][1] = d["expl"][0]
+            self.omega_ic = self.c_z10_omega_ic * self.z[-1, lm10].real
         self.z[:, m0] = self.z[:, m0].real
         rotate("z")
         self._rhs_imp_z()
@@ -458,13 +612,26 @@ class ShellHost:
                     self.b[:, idx] = 0.0
                     self.aj[:, idx] = 0.0
                     return
+                if self.l_cond_ic:
+                    self.b[:, idx], self.b_ic[:, idx] = self._solve_coupled(mats["bic"][l], rb[:, idx], rbi[:, idx])
+                    self.aj[:, idx], self.aj_ic[:, idx] = self._solve_coupled(mats["jic"][l], rj[:, idx], rji[:, idx])
+                    return
                 self.b[:, idx] = g.solve(mats["b"][l], rb[:, idx], (0, N - 1))
                 self.aj[:, idx] = g.solve(mats["j"][l], rj[:, idx], (0, N - 1))
+            if self.l_cond_ic:
+                rbi, rji = self._imex_rhs("b_ic", wts), self._imex_rhs("j_ic", wts)
             per_degree(up_b)
             self.b[:, m0] = self.b[:, m0].real
             self.aj[:, m0] = self.aj[:, m0].real
             rotate("b")
             rotate("j")
+            if self.l_cond_ic:
+                self.b_ic[:, self.lm2l == 0] = 0.0
+                self.aj_ic[:, self.lm2l == 0] = 0.0
+                self.b_ic[:, m0] = self.b_ic[:, m0].real
+                self.aj_ic[:, m0] = self.aj_ic[:, m0].real
+                rotate("b_ic")
+                rotate("j_ic")
             self._rhs_imp_b()
         self.n_steps += 1
 
