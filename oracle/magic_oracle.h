@@ -23,8 +23,17 @@
  *   (4) likewise for the anelastic branch (u.grad u advection, viscous heating, stress-free levels): the first logged row
  *       (10 steps) of samples/hydro_bench_anel/reference.out, whose axisymmetric columns exist only through the quadratic
  *       terms (tests/test_hydro_bench_anel.py; the CUDA library reproduces all 30 rows under -m gpu).
- * Still "parity unpinned" (no reference vectors reachable here, literal line-cited restatements only): the full-sphere
- * centre level, rotating conducting walls, get_br_v_bcs and the inner-core (_IC) and axisymmetric syntheses.
+ *   (5) for the double-curl form of get_dwdt, l_R(nR) < l_max and minc = 3 on a grid that ends at r = 0: all 11 rows (100
+ *       steps from the shipped checkpoint) of samples/full_sphere/reference.out, finite-difference host restated in
+ *       oracle/lmloop_fd.py (tests/test_full_sphere.py; the CUDA library reproduces the same rows under -m gpu);
+ *   (6) for the precession branch of get_nl (PCr/PCt/PCp), the `time` argument and m_max < l_max: all 20 rows (200 steps)
+ *       of samples/precession/reference.out (tests/test_precession.py);
+ *   (7) for rotating conducting walls -- get_nl on the boundary levels (lMagNlBc), v_rigid_boundary with omega_ic, the
+ *       Lorentz torque: 300 steps of samples/dynamo_benchmark_condICrotIC/reference.out and referenceMag.out
+ *       (tests/test_condICrotIC.py).
+ * Still "parity unpinned" (no reference vectors reachable here, literal line-cited restatements only): the r = 0 level
+ * itself (v_center_sphere: the energies of (5) are insensitive to it, measured), get_br_v_bcs and the inner-core (_IC) and
+ * axisymmetric syntheses.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may call
  * into this library.  The product path (magic_b200/) never links or imports it.
