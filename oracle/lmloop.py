@@ -70,6 +70,7 @@ class ChebShell:
         self.D2 = (d2 * drx ** 2) @ Tinv
         self.D3 = (d3 * drx ** 3) @ Tinv
         self.T, self.Tinv = T, Tinv
+        self._lu = {}
         # get_dr on raw (not dealiased) data, e.g. the explicit terms of finish_exp_*: the reference differentiates the modes
         # below n_cheb_max only (radial_derivatives.f90 get_dcheb with r_scheme%n_max)
         keep = (np.arange(N) < self.n_cheb_max).astype(float)
@@ -90,21 +91,26 @@ class ChebShell:
     def rInt_R(self, f):
         return self.w_int @ f
 
-    def solve(self, M, rhs, bc_rows):
+    def solve(self, M, rhs, bc_rows, key=None):
         """Solve like the reference: unknowns = Chebyshev coefficients, boundary rows blind to modes >= n_cheb_max, those
         modes zeroed after the solve (e.g. get_sMat updateS.f90:1107-1112 and updateS :311-318); returns grid values.
         M acts on grid values of nblk stacked fields ([nblk*N, nblk*N])."""
         N, nc = self.n_r_max, self.n_cheb_max
         nblk = M.shape[0] // N
-        Mc = np.empty_like(M)
-        for b in range(nblk):
-            Mc[:, b * N:(b + 1) * N] = M[:, b * N:(b + 1) * N] @ self.B0
-        if nc < N:
-            for row in bc_rows:
-                for b in range(nblk):
-                    Mc[row, b * N + nc:(b + 1) * N] = 0.0
-        f = 1.0 / np.max(np.abs(Mc), axis=1)  # row equilibration like WITH_PRECOND_* (conditioning only)
-        c = np.linalg.solve(Mc * f[:, None], rhs * f[:, None])
+        fac = self._lu.get(key) if key is not None else None      # coefficient-space matrix, built once per matrix
+        if fac is None:
+            Mc = np.empty_like(M)
+            for b in range(nblk):
+                Mc[:, b * N:(b + 1) * N] = M[:, b * N:(b + 1) * N] @ self.B0
+            if nc < N:
+                for row in bc_rows:
+                    for b in range(nblk):
+                        Mc[row, b * N + nc:(b + 1) * N] = 0.0
+            f = 1.0 / np.max(np.abs(Mc), axis=1)  # row equilibration like WITH_PRECOND_* (conditioning only)
+            fac = (Mc * f[:, None], f)
+            if key is not None:
+                self._lu[key] = fac
+        c = np.linalg.solve(fac[0], rhs * fac[1][:, None])
         out = np.empty_like(c)
         for b in range(nblk):
             cb = c[b * N:(b + 1) * N].copy()
@@ -217,6 +223,9 @@ class ShellHost:
         self.c_z10_omega_ic = 0.5 * np.sqrt(3.0 / np.pi) * or2[-1] / self.rho0[-1]      # preCalculations.f90:313-318
         self.c_dt_z10_ic = 0.2 * g.r_icb * self.rho0[-1]                                # :336 (rho_ratio_ic = 1)
         self.c_lorentz_ic = 0.25 * np.sqrt(3.0 / np.pi) * or2[-1]                       # :343
+        self.c_moi_ic = 8.0 * np.pi / 15.0 * g.r_icb ** 5 * self.rho0[-1]               # :326
+        self.sigma_ratio, self.prmag = sigma_ratio, prmag
+        self.aj_nl_icb = None
         self.dom_ic = dict(old=0.0, impl=0.0, expl=[0.0, 0.0])
         if self.l_cond_ic:
             self.ic = ChebEvenIC(n_r_ic_max, n_cheb_ic_max, g.r_icb)
@@ -276,6 +285,22 @@ class ShellHost:
         if l_mag:
             self._rhs_imp_b()
 
+    def restart(self, **flags):
+        """A run restarted from its own checkpoint with other switches (samples/*/input_restart.nml): the checkpoint carries
+        the fields, the explicit terms of the previous step and the rotation rates (storeCheckPoints.f90:45-277), all of
+        which this object still holds; startFields.f90:373-432 then rebuilds the old / implicit terms under the new switches
+        (this is where l_correct_AMz / AMe first act on the restart state)."""
+        for k, v in flags.items():
+            if not hasattr(self, k):
+                raise AttributeError(k)
+            setattr(self, k, v)
+        self._mats = None
+        self._rhs_imp_s()
+        self._rhs_imp_wp()
+        self._rhs_imp_z()
+        if self.l_mag:
+            self._rhs_imp_b()
+
     # ------------------------------------------------------------------------------------------------
     def _lm(self, l, m):
         return int(np.nonzero((self.lm2l == l) & (self.lm2m == m))[0][0])
@@ -305,6 +330,8 @@ class ShellHost:
             corr = fac3 * g.rInt_R(r * r * self.z[:, lm]) / self.c_moi_oc
             if m == 0:
                 corr = corr.real
+                if self.l_rot_ic:   # angular_moment_ic(3) = c_moi_ic * omega_ic (outRot.f90:538), nomi = c_moi_oc * y10_norm
+                    corr += self.c_moi_ic * self.omega_ic / (self.c_moi_oc * 0.5 * np.sqrt(3.0 / np.pi))
             self.z[:, lm] -= rho0 * r * r * corr
             self.dz[:, lm] -= rho0 * (2.0 * r + r * r * beta) * corr
             ddz[:, lm] -= rho0 * (2.0 + 4.0 * beta * r + dbeta * r * r + beta * beta * r * r) * corr
@@ -317,10 +344,13 @@ class ShellHost:
         imp[0] = 0.0
         imp[-1] = 0.0      # n_r_top=n_r_cmb+1 .. n_r_bot=n_r_icb-1
         self.impl["z"] = imp
-        if self.l_rot_ic:   # updateZ.f90:996-1008: viscous torque on the inner core (kbotv = 2, visc = 1)
+        if self.l_rot_ic and self.kbotv == 2:   # updateZ.f90:1001-1008: viscous torque on the inner core (visc = 1)
             z10, dz10 = self.z[-1, self._lm(1, 0)].real, self.dz[-1, self._lm(1, 0)].real
             self.dom_ic["old"] = self.c_dt_z10_ic * z10
             self.dom_ic["impl"] = -((2.0 * g.or1[-1] + beta[-1]) * z10 - dz10)
+        elif self.l_rot_ic:                     # updateZ.f90:997-999: stress-free, only the Lorentz torque acts
+            self.dom_ic["old"] = self.c_moi_ic * self.c_lorentz_ic * self.omega_ic
+            self.dom_ic["impl"] = 0.0
 
     def _rhs_imp_wp(self):
         """get_pol_rhs_imp, updateWP.f90:1089-1336, non double-curl branch (visc=1, dLvisc=0)."""
@@ -395,6 +425,7 @@ class ShellHost:
         """get_sMat / get_zMat / get_wpMat / get_bMat for every degree, acting on grid values (ChebShell.solve maps them
         to coefficient space and applies the dealiasing)."""
         g, N = self.g, self.N
+        g._lu = {}
         I = np.eye(N)
         beta, dbeta = self.beta[:, None], self.dbeta[:, None]
         or1, or2 = g.or1[:, None], g.or2[:, None]
@@ -436,7 +467,7 @@ class ShellHost:
                 J[0], J[-1] = I[0], I[-1]
                 mats["b"].append(B)
                 mats["j"].append(J)
-        if self.l_rot_ic:
+        if self.l_rot_ic and self.kbotv == 2:
             # get_z10Mat (updateZ.f90:1719-1800): zMat(l=1) with the torque balance of the inner core in the ICB row
             M = mats["z"][1].copy()
             M[-1] = self.c_dt_z10_ic * I[-1] + wl1 * ((2.0 * g.or1[-1] + bN) * I[-1] - g.D1[-1])
@@ -477,15 +508,20 @@ class ShellHost:
         A[N - 1:, N:] = blk
         return A
 
-    def _solve_coupled(self, A, rhs_oc, rhs_ic):
+    def _solve_coupled(self, A, rhs_oc, rhs_ic, icb_derivative_bc=None, key=None):
         """Right-hand side rows as updateB.f90:500-548; returns grid values (outer core, inner core)."""
         g, ic, N = self.g, self.ic, self.N
         rhs = np.concatenate([rhs_oc, rhs_ic], axis=0)
         rhs[0] = 0.0
         rhs[N - 1] = 0.0
-        rhs[N] = 0.0
-        f = 1.0 / np.max(np.abs(A), axis=1)
-        c = np.linalg.solve(A * f[:, None], rhs * f[:, None])
+        rhs[N] = 0.0 if icb_derivative_bc is None else icb_derivative_bc
+        fac = g._lu.get(key) if key is not None else None
+        if fac is None:
+            f = 1.0 / np.max(np.abs(A), axis=1)
+            fac = (A * f[:, None], f)
+            if key is not None:
+                g._lu[key] = fac
+        c = np.linalg.solve(fac[0], rhs * fac[1][:, None])
         co, ci = c[:N].copy(), c[N:].copy()
         co[g.n_cheb_max:] = 0.0
         ci[ic.n_cheb_ic_max:] = 0.0
@@ -519,6 +555,11 @@ class ShellHost:
         if self.l_rot_ic:     # finish_exp_tor (updateZ.f90:1659-1688), gammatau_gravi = 0
             self.lorentz_torque_ic = float(out["lorentz_torque_ic"])
             self.dom_ic["expl"][0] = self.c_lorentz_ic * self.lorentz_torque_ic
+        if self.l_cond_ic and self.kbotv == 1:   # l_b_nl_icb (Namelists.f90:713-720); get_b_nl_bcs('ICB') nonlinear_bcs.f90:104-111
+            self.aj_nl_icb = -self.sigma_ratio * self.prmag * np.asarray(out["br_vp_lm_icb"])
+            self.aj_nl_icb[0] = 0.0
+        else:
+            self.aj_nl_icb = None
         if self.l_cond_ic:    # finish_exp_mag_ic (updateB.f90:955-1003): advection of the inner-core field by its rotation
             fac = -self.omega_ic * g.or2[-1] * 1j * self.lm2m[None, :] * self.dL[None, :] if self.l_rot_ic else 0.0
             for nm, f in (("b_ic", self.b_ic), ("j_ic", self.aj_ic)):
@@ -552,7 +593,7 @@ class ShellHost:
         rhs[0], rhs[-1] = self.tops, self.bots
 
         def up_s(l, idx):
-            self.s[:, idx] = g.solve(mats["s"][l], rhs[:, idx], (0, N - 1))
+            self.s[:, idx] = g.solve(mats["s"][l], rhs[:, idx], (0, N - 1), ("s", l))
         if self.l_heat:
             per_degree(up_s)
             self.s[:, m0] = self.s[:, m0].real
@@ -568,16 +609,20 @@ class ShellHost:
             if l == 0:
                 self.z[:, idx] = 0.0
             else:
-                self.z[:, idx] = g.solve(mats["z"][l], rhs[:, idx], (0, N - 1))
+                self.z[:, idx] = g.solve(mats["z"][l], rhs[:, idx], (0, N - 1), ("z", l))
         per_degree(up_z)
         if self.l_rot_ic:     # updateZ.f90:300-356, :416-420: z(1,0) with the inner-core torque balance, then update_rot_rates
             lm10 = self._lm(1, 0)
             d = self.dom_ic
-            r10 = rhs[:, [lm10]].copy()
-            r10[-1] = wimp * d["old"] + wl2 * d["impl"] + we1 * d["expl"][0] + we2 * d["expl"][1]
-            self.z[:, [lm10]] = g.solve(mats["z10"], r10, (0, N - 1)).real
+            dom = wimp * d["old"] + wl2 * d["impl"] + we1 * d["expl"][0] + we2 * d["expl"][1]
             d["expl"][1] = d["expl"][0]
-            self.omega_ic = self.c_z10_omega_ic * self.z[-1, lm10].real
+            if self.kbotv == 2:
+                r10 = rhs[:, [lm10]].copy()
+                r10[-1] = dom
+                self.z[:, [lm10]] = g.solve(mats["z10"], r10, (0, N - 1), ("z10",)).real
+                self.omega_ic = self.c_z10_omega_ic * self.z[-1, lm10].real
+            else:             # free slip: explicit time stepping of omega_ic (updateZ.f90:1606-1608, gammatau_gravi = 0)
+                self.omega_ic = dom / (self.c_lorentz_ic * self.c_moi_ic)
         self.z[:, m0] = self.z[:, m0].real
         rotate("z")
         self._rhs_imp_z()
@@ -591,7 +636,7 @@ class ShellHost:
             if l == 0:
                 self.w[:, idx] = 0.0     # p(l=0) (get_p0Mat) does not feed back into the flow; left untouched
                 return
-            sol = g.solve(mats["wp"][l], np.concatenate([rw[:, idx], rp[:, idx]], axis=0), (0, N - 1, N, 2 * N - 1))
+            sol = g.solve(mats["wp"][l], np.concatenate([rw[:, idx], rp[:, idx]], axis=0), (0, N - 1, N, 2 * N - 1), ("wp", l))
             self.w[:, idx] = sol[:N]
             self.p[:, idx] = sol[N:]
         per_degree(up_wp)
@@ -613,11 +658,12 @@ class ShellHost:
                     self.aj[:, idx] = 0.0
                     return
                 if self.l_cond_ic:
-                    self.b[:, idx], self.b_ic[:, idx] = self._solve_coupled(mats["bic"][l], rb[:, idx], rbi[:, idx])
-                    self.aj[:, idx], self.aj_ic[:, idx] = self._solve_coupled(mats["jic"][l], rj[:, idx], rji[:, idx])
+                    self.b[:, idx], self.b_ic[:, idx] = self._solve_coupled(mats["bic"][l], rb[:, idx], rbi[:, idx], key=("bic", l))
+                    bc = None if self.aj_nl_icb is None else self.aj_nl_icb[idx]      # updateB.f90:534-539
+                    self.aj[:, idx], self.aj_ic[:, idx] = self._solve_coupled(mats["jic"][l], rj[:, idx], rji[:, idx], bc, key=("jic", l))
                     return
-                self.b[:, idx] = g.solve(mats["b"][l], rb[:, idx], (0, N - 1))
-                self.aj[:, idx] = g.solve(mats["j"][l], rj[:, idx], (0, N - 1))
+                self.b[:, idx] = g.solve(mats["b"][l], rb[:, idx], (0, N - 1), ("b", l))
+                self.aj[:, idx] = g.solve(mats["j"][l], rj[:, idx], (0, N - 1), ("j", l))
             if self.l_cond_ic:
                 rbi, rji = self._imex_rhs("b_ic", wts), self._imex_rhs("j_ic", wts)
             per_degree(up_b)

@@ -29,11 +29,12 @@
  *   (6) for the precession branch of get_nl (PCr/PCt/PCp), the `time` argument and m_max < l_max: all 20 rows (200 steps)
  *       of samples/precession/reference.out (tests/test_precession.py);
  *   (7) for rotating conducting walls -- get_nl on the boundary levels (lMagNlBc), v_rigid_boundary with omega_ic, the
- *       Lorentz torque: 300 steps of samples/dynamo_benchmark_condICrotIC/reference.out and referenceMag.out
+ *       Lorentz torque: all 1000 steps of samples/dynamo_benchmark_condICrotIC/reference.out and referenceMag.out, and for
+ *       get_br_v_bcs (stress-free walls + conducting inner core) the 100 steps of its restarted stage
  *       (tests/test_condICrotIC.py).
  * Still "parity unpinned" (no reference vectors reachable here, literal line-cited restatements only): the r = 0 level
- * itself (v_center_sphere: the energies of (5) are insensitive to it, measured), get_br_v_bcs and the inner-core (_IC) and
- * axisymmetric syntheses.
+ * itself (v_center_sphere: the energies of (5) are insensitive to it, measured) and the inner-core (_IC) and axisymmetric
+ * syntheses (diagnostics, not called by the radial loop).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may call
  * into this library.  The product path (magic_b200/) never links or imports it.

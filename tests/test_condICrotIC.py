@@ -9,12 +9,16 @@ e_kin.TAG and e_mag_oc.TAG logged every step.  On the radial-loop side this is t
   * the ICB level takes v_rigid_boundary with the current omega_ic (nonlinear_bcs.f90:120-175, rIter.f90:570-591),
   * the loop returns the Lorentz torque on the inner core (rIter.f90:279-292, outRot.f90:423-483), which drives omega_ic
     through the z(1,0) torque balance of updateZ.
-The inner core spins up from rest to omega_ic = 77 within 60 steps, purely through that torque.
+The inner core spins up from rest to omega_ic = 77 within 60 steps, purely through that torque.  The autotest then RESTARTS
+the run from its checkpoint with stress-free walls and l_correct_AMz / AMe (input_restart.nml, 100 more steps): with a
+conducting inner core this switches on the nonlinear magnetic boundary condition at the ICB (l_b_nl_icb,
+Namelists.f90:713-720), i.e. the loop must also deliver get_br_v_bcs (nonlinear_bcs.f90:24-74, rIter.f90:267-277), and the
+inner core is stepped explicitly by the Lorentz torque alone (updateZ.f90:1606-1608).
 
 The Fortran host is restated in numpy (oracle/lmloop.py ShellHost with l_cond_ic / l_rot_ic: coupled outer/inner-core
 matrices of get_bMat, even-Chebyshev inner-core grid, z10Mat, finish_exp_tor, finish_exp_mag_ic); the radial loop is the CPU
-oracle (CPU test, 30 steps) or the CUDA library through the C ABI (300 steps).  tests/golden/condICrotIC_reference.npz
-holds rows 0..300 of reference.out / referenceMag.out (tests/golden/make_condICrotIC_fixture.py).
+oracle or the CUDA library through the C ABI, both over all 1000 + 100 steps.  tests/golden/condICrotIC_reference.npz holds
+the 1102 rows of reference.out / referenceMag.out (tests/golden/make_condICrotIC_fixture.py).
 """
 import os
 
@@ -62,10 +66,14 @@ def _check(golden, h, row):
     np.testing.assert_allclose(gm, golden["e_mag_oc"][row], rtol=RTOL, atol=ATOL, err_msg=f"e_mag_oc row {row}")
 
 
+N_FIRST = 1000       # rows 1..1000: input.nml; row 1001: restart state; rows 1002..1101: input_restart.nml
+RESTART = dict(ktopv=1, kbotv=1, l_correct_AMz=True, l_correct_AMe=True)
+
+
 def _oracle_loop(golden, tweak=None):
     from oracle.oracle import Oracle, Params as OParams
     gs = _sizes(golden)
-    o = Oracle(gs["l_max"], n_theta=gs["n_theta_max"], n_phi=gs["n_phi_max"], m_max=gs["m_max"], threads=min(4, os.cpu_count() or 1))
+    o = Oracle(gs["l_max"], n_theta=gs["n_theta_max"], n_phi=gs["n_phi_max"], m_max=gs["m_max"], threads=min(2, os.cpu_count() or 1))
     h, p, rad = _setup(golden, o.lm2l, o.lm2m)
     op = OParams()
     for n, _ in p._fields_:
@@ -87,14 +95,68 @@ def test_start_fields_carry_the_reference_magnetic_energy(golden):
     _check(golden, h, 0)
 
 
-def test_oracle_radial_loop_reproduces_reference_energies(golden):
-    """CPU oracle inside the reference's time loop: 30 steps, 8 kinetic and 12 magnetic energy columns per step; the inner
-    core is spun up by the Lorentz torque the loop returns."""
+@pytest.fixture(scope="module")
+def first_run(golden):
+    """CPU oracle inside the reference's time loop: the 1000 steps of input.nml, 8 kinetic and 12 magnetic energy columns
+    checked after every step; returns the pickled host at t = 0.1 (what checkpoint_end.start holds)."""
+    import pickle
     h = _oracle_loop(golden)
-    for row in range(1, 31):
+    for row in range(1, N_FIRST + 1):
         h.step()
         _check(golden, h, row)
-    assert 55.0 < h.omega_ic < 65.0 and h.lorentz_torque_ic > 0.0
+        if row == 60:
+            assert 76.0 < h.omega_ic < 78.0 and h.lorentz_torque_ic > 0.0     # spun up by the torque the loop returns
+    loop, h.radial_loop = h.radial_loop, None
+    return pickle.dumps(h)
+
+
+def _restarted(golden, first_run, tweak=None, out_tweak=None):
+    import pickle
+    from oracle.oracle import Oracle, Params as OParams
+    gs = _sizes(golden)
+    o = Oracle(gs["l_max"], n_theta=gs["n_theta_max"], n_phi=gs["n_phi_max"], m_max=gs["m_max"], threads=min(2, os.cpu_count() or 1))
+    h = pickle.loads(first_run)
+    _, p, rad = _setup(golden, o.lm2l, o.lm2m)
+    p.ktopv = p.kbotv = 1
+    op = OParams()
+    for n, _ in p._fields_:
+        setattr(op, n, getattr(p, n))
+
+    def loop(f):
+        op.omega_ic = h.omega_ic
+        if tweak:
+            tweak(op)
+        out = o.radial_loop(op, rad, f)
+        if out_tweak:
+            out_tweak(out)
+        return out
+    h.radial_loop = loop
+    return h
+
+
+def test_oracle_radial_loop_reproduces_reference_energies(golden, first_run):
+    """Rows 1..1000 are checked inside the fixture; here the restart: row 1001 is the checkpoint state AFTER startFields has
+    applied the angular-momentum correction (before it the axisymmetric toroidal energy is off by 0.32), rows 1002..1101 the
+    100 stress-free steps with the nonlinear magnetic boundary condition at the ICB."""
+    h = _restarted(golden, first_run)
+    assert abs(h.e_kin()[3] / golden["e_kin"][N_FIRST + 1][4] - 1.0) > 0.1
+    h.restart(**RESTART)
+    _check(golden, h, N_FIRST + 1)
+    for row in range(N_FIRST + 2, len(golden["e_kin"])):
+        h.step()
+        _check(golden, h, row)
+
+
+def test_the_restart_stage_needs_get_br_v_bcs(golden, first_run):
+    """Negative control: without the br*v products of get_br_v_bcs in the ICB boundary condition the energies are off by
+    2e-3 (kinetic, axisymmetric toroidal) and 5e-5 (magnetic) after ten steps."""
+    h = _restarted(golden, first_run, out_tweak=lambda out: out.__setitem__("br_vp_lm_icb", 0.0 * out["br_vp_lm_icb"]))
+    h.restart(**RESTART)
+    for _ in range(10):
+        h.step()
+    row = golden["e_kin"][N_FIRST + 11], golden["e_mag_oc"][N_FIRST + 11]
+    assert abs(h.e_kin()[3] / row[0][4] - 1.0) > 1e-4
+    assert abs(h.e_mag_oc()[3] / row[1][4] - 1.0) > 1e-6
 
 
 def test_the_energies_see_the_moving_wall(golden):
@@ -110,8 +172,8 @@ def test_the_energies_see_the_moving_wall(golden):
 @pytest.mark.gpu
 @pytest.mark.gpu_unverified
 def test_gpu_radial_loop_reproduces_reference_energies(golden):
-    """The CUDA radial loop (magic_rloop_run + magic_rloop_set_rotation + magic_rloop_get_torques) inside the reference's
-    time loop: 300 steps."""
+    """The CUDA radial loop (magic_rloop_run + magic_rloop_set_rotation + magic_rloop_get_torques, and after the restart
+    magic_rloop_get_br_v_bcs) inside the reference's time loop: all 1000 + 100 steps."""
     from magic_b200 import RadialLoop, Sht
     gs = _sizes(golden)
     s = Sht(gs["l_max"], m_max=gs["m_max"], n_theta_max=gs["n_theta_max"], n_phi_max=gs["n_phi_max"])
@@ -124,7 +186,23 @@ def test_gpu_radial_loop_reproduces_reference_energies(golden):
         out["lorentz_torque_ic"], out["lorentz_torque_ma"] = rl.torques()
         return out
     h.radial_loop = loop
-    for row in range(1, len(golden["e_kin"])):
+    for row in range(1, N_FIRST + 1):
+        h.step()
+        _check(golden, h, row)
+    rl.finalize()
+    p.ktopv = p.kbotv = 1
+    rl = RadialLoop(s, p, rad)
+
+    def loop2(f):
+        rl.set_rotation(0.0, h.omega_ic)
+        out = rl.radialLoop(f)
+        out["lorentz_torque_ic"], out["lorentz_torque_ma"] = rl.torques()
+        out["br_vt_lm_icb"], out["br_vp_lm_icb"] = rl.br_v_bcs("ICB")
+        return out
+    h.radial_loop = loop2
+    h.restart(**RESTART)
+    _check(golden, h, N_FIRST + 1)
+    for row in range(N_FIRST + 2, len(golden["e_kin"])):
         h.step()
         _check(golden, h, row)
     assert rl.launch_count() > 0
