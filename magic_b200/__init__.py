@@ -9,3 +9,4 @@ from .lib import MagicError, load_library  # noqa: F401
 from .sht import Sht, grid_sizes  # noqa: F401
 from .riter import Params, RadialLoop  # noqa: F401
 from .transpose import Transposer, get_blocks  # noqa: F401
+from .checkpoint import Checkpoint, read_checkpoint, write_checkpoint  # noqa: F401
