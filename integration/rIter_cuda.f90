@@ -1,0 +1,260 @@
+module rIter_cuda_mod
+   !
+   ! rIter_cuda_t: a second extension of the abstract rIter_t (rIteration.f90:15-19) next to rIter_single_t
+   ! (rIter.f90:53-63).  One call hands the whole R-local slab (all levels nRstart:nRstop of every field) to
+   ! libmagic_b200.so, which runs transform_to_grid_space, get_nl, transform_to_lm_space, courant and get_td
+   ! (rIter.f90:190-444) for all levels at once on the GPU and returns the same output arrays.
+   !
+   ! Selected in radialLoop.f90:26 instead of `allocate( rIter_single_t :: rIter )`:
+   !      allocate( rIter_cuda_t :: rIter )
+   ! step_time.f90 and LMLoop are untouched.
+   !
+   ! On steps that ask for in-loop diagnostics (graphics, movies, TO, helicity, power, RMS, fluxes, ...:
+   ! rIter.f90:303-404) the call is delegated to an embedded rIter_single_t, whose transforms go through
+   ! `module sht`, i.e. the same library one level at a time.
+   !
+   use iso_c_binding
+   use precision_mod
+   use truncation, only: lm_max, lm_maxMag, n_r_max
+   use radial_data, only: nRstart, nRstop, nRstartMag, nRstopMag, n_r_cmb, n_r_icb
+   use logic, only: l_conv, l_mag, l_heat, l_conv_nl, l_heat_nl, l_mag_nl, l_mag_LF, l_mag_kin, l_anel,    &
+       &            l_adv_curl, l_corr, l_double_curl, l_single_matrix, l_chemical_conv, l_precession,      &
+       &            l_centrifuge, l_anelastic_liquid, l_cour_alf_damp, l_full_sphere, l_parallel_solve,     &
+       &            l_temperature_diff, l_cond_ma, l_cond_ic, l_rot_ma, l_rot_ic, l_b_nl_cmb, l_b_nl_icb,   &
+       &            l_phase_field, l_onset
+   use physical_parameters, only: ktopv, kbotv, n_r_LCR, LFfac, CorFac, epsc, epscXi, opm, ViscHeatFac,     &
+       &                          OhmLossFac, oek, po, prec_angle, dilution_fac, ra, opr
+   use radial_functions, only: r, or1, or2, or4, orho1, orho2, beta, rho0, otemp1, temp0, visc, lambda,     &
+       &                       epscProf, l_R, r_cmb, r_icb
+   use num_param, only: delxr2, delxh2
+   use fields, only: s_Rloc, ds_Rloc, z_Rloc, dz_Rloc, p_Rloc, b_Rloc, db_Rloc, ddb_Rloc, aj_Rloc, dj_Rloc, &
+       &             w_Rloc, dw_Rloc, ddw_Rloc, xi_Rloc, omega_ic, omega_ma
+   use time_schemes, only: type_tscheme
+   use rIteration, only: rIter_t
+   use rIter_mod, only: rIter_single_t
+   use useful, only: abortRun
+   use constants, only: zero
+   use sht, only: sht_h
+   use magic_b200_c
+
+   implicit none
+
+   private
+
+   type, public, extends(rIter_t) :: rIter_cuda_t
+      type(c_ptr) :: rl = c_null_ptr          ! magic_rloop*: plan, device buffers, streams
+      type(rIter_single_t) :: single          ! level-at-a-time loop for the diagnostics steps
+      integer(c_int), allocatable :: nR_loc(:), l_R_loc(:)
+      real(c_double), allocatable :: rad(:,:) ! the 15 radial functions of magic_radial on nRstart:nRstop
+   contains
+      procedure :: initialize
+      procedure :: finalize
+      procedure :: radialLoop
+      procedure, private :: create_plan
+   end type rIter_cuda_t
+
+contains
+
+   subroutine initialize(this)
+
+      class(rIter_cuda_t) :: this
+
+      if ( l_phase_field .or. l_onset ) call abortRun('! rIter_cuda_t: phase field / onset mode are not on the GPU path')
+      call this%single%initialize()
+      !-- the plan needs tscheme%courfac / alffac: it is created by the first radialLoop call
+
+   end subroutine initialize
+!------------------------------------------------------------------------------
+   subroutine finalize(this)
+
+      class(rIter_cuda_t) :: this
+
+      if ( c_associated(this%rl) ) call magic_check( magic_rloop_destroy(this%rl), 'magic_rloop_destroy' )
+      this%rl = c_null_ptr
+      if ( allocated(this%rad) ) deallocate( this%rad, this%nR_loc, this%l_R_loc )
+      call this%single%finalize()
+
+   end subroutine finalize
+!------------------------------------------------------------------------------
+   subroutine create_plan(this, tscheme)
+      !
+      ! Fills magic_params from logic / physical_parameters and magic_radial from radial_functions(nRstart:nRstop)
+      ! (the values get_nl.f90:24-34, get_td.f90:11-21, courant.f90 and rIter.f90:16-40 read) and creates the plan.
+      !
+      class(rIter_cuda_t), target :: this
+      class(type_tscheme), intent(in) :: tscheme
+
+      type(magic_params) :: p
+      type(magic_radial) :: rd
+      integer :: n_r_loc, n, nR
+
+      n_r_loc = nRstop-nRstart+1
+      allocate( this%nR_loc(n_r_loc), this%l_R_loc(n_r_loc), this%rad(n_r_loc,15) )
+      do n=1,n_r_loc
+         nR = nRstart+n-1
+         this%nR_loc(n)  = int(nR,c_int)
+         this%l_R_loc(n) = int(l_R(nR),c_int)
+         this%rad(n,1)  = r(nR);      this%rad(n,2)  = or1(nR);    this%rad(n,3)  = or2(nR)
+         this%rad(n,4)  = or4(nR);    this%rad(n,5)  = orho1(nR);  this%rad(n,6)  = orho2(nR)
+         this%rad(n,7)  = beta(nR);   this%rad(n,8)  = rho0(nR);   this%rad(n,9)  = otemp1(nR)
+         this%rad(n,10) = temp0(nR);  this%rad(n,11) = visc(nR);   this%rad(n,12) = lambda(nR)
+         this%rad(n,13) = epscProf(nR); this%rad(n,14) = delxr2(nR); this%rad(n,15) = delxh2(nR)
+      end do
+      rd%nR  = c_loc(this%nR_loc);   rd%l_R = c_loc(this%l_R_loc)
+      rd%r        = c_loc(this%rad(1,1));  rd%or1    = c_loc(this%rad(1,2));  rd%or2    = c_loc(this%rad(1,3))
+      rd%or4      = c_loc(this%rad(1,4));  rd%orho1  = c_loc(this%rad(1,5));  rd%orho2  = c_loc(this%rad(1,6))
+      rd%beta     = c_loc(this%rad(1,7));  rd%rho0   = c_loc(this%rad(1,8));  rd%otemp1 = c_loc(this%rad(1,9))
+      rd%temp0    = c_loc(this%rad(1,10)); rd%visc   = c_loc(this%rad(1,11)); rd%lambda = c_loc(this%rad(1,12))
+      rd%epscProf = c_loc(this%rad(1,13)); rd%delxr2 = c_loc(this%rad(1,14)); rd%delxh2 = c_loc(this%rad(1,15))
+
+      p%l_conv=l2i(l_conv); p%l_mag=l2i(l_mag); p%l_heat=l2i(l_heat); p%l_conv_nl=l2i(l_conv_nl)
+      p%l_heat_nl=l2i(l_heat_nl); p%l_mag_nl=l2i(l_mag_nl); p%l_mag_LF=l2i(l_mag_LF); p%l_mag_kin=l2i(l_mag_kin)
+      p%l_anel=l2i(l_anel); p%l_adv_curl=l2i(l_adv_curl); p%l_corr=l2i(l_corr); p%l_double_curl=l2i(l_double_curl)
+      p%l_single_matrix=l2i(l_single_matrix); p%l_chemical_conv=l2i(l_chemical_conv)
+      p%l_precession=l2i(l_precession); p%l_centrifuge=l2i(l_centrifuge)
+      p%l_anelastic_liquid=l2i(l_anelastic_liquid); p%l_cour_alf_damp=l2i(l_cour_alf_damp)
+      p%l_full_sphere=l2i(l_full_sphere); p%l_parallel_solve=l2i(l_parallel_solve)
+      p%l_temperature_diff=l2i(l_temperature_diff)
+      p%ktopv=int(ktopv,c_int); p%kbotv=int(kbotv,c_int)
+      p%l_cond_ma=l2i(l_cond_ma); p%l_cond_ic=l2i(l_cond_ic); p%l_rot_ma=l2i(l_rot_ma); p%l_rot_ic=l2i(l_rot_ic)
+      p%n_r_max=int(n_r_max,c_int); p%n_r_LCR=int(n_r_LCR,c_int)
+      p%LFfac=LFfac; p%CorFac=CorFac; p%epsc=epsc; p%epscXi=epscXi; p%opm=opm
+      p%ViscHeatFac=ViscHeatFac; p%OhmLossFac=OhmLossFac
+      p%oek=oek; p%po=po; p%prec_angle=prec_angle; p%dilution_fac=dilution_fac; p%ra=ra; p%opr=opr
+      p%omega_ma=omega_ma; p%omega_ic=omega_ic; p%r_cmb=r_cmb; p%r_icb=r_icb
+      p%courfac=tscheme%courfac; p%alffac=tscheme%alffac
+
+      !-- level_chunk = 0: the library sizes its level batches from the free device memory
+      call magic_check( magic_rloop_create(sht_h, p, rd, int(n_r_loc,c_int), 0_c_int, this%rl), 'magic_rloop_create' )
+
+   contains
+
+      pure integer(c_int) function l2i(l)
+         logical, intent(in) :: l
+         l2i = merge(1_c_int, 0_c_int, l)
+      end function l2i
+
+   end subroutine create_plan
+!------------------------------------------------------------------------------
+   subroutine radialLoop(this,l_graph,l_frame,time,timeStage,tscheme,dtLast,         &
+              &          lTOCalc,lTONext,lTONext2,lHelCalc,lPowerCalc,lRmsCalc,      &
+              &          lPressCalc,lPressNext,lViscBcCalc,lFluxProfCalc,            &
+              &          lPerpParCalc,lGeosCalc,lHemiCalc,lPhaseCalc,l_probe_out,    &
+              &          dsdt,dwdt,dzdt,dpdt,dxidt,dphidt,dbdt,djdt,dVxVhLM,dVxBhLM, &
+              &          dVSrLM,dVXirLM,lorentz_torque_ic,lorentz_torque_ma,         &
+              &          br_vt_lm_cmb,br_vp_lm_cmb,br_vt_lm_icb,br_vp_lm_icb,dtrkc,  &
+              &          dthkc)
+
+      class(rIter_cuda_t) :: this
+
+      !--- Input of variables (rIteration.f90:34-81):
+      logical,             intent(in) :: l_graph,l_frame
+      logical,             intent(in) :: lTOcalc,lTONext,lTONext2,lHelCalc
+      logical,             intent(in) :: lPowerCalc,lHemiCalc
+      logical,             intent(in) :: lViscBcCalc,lFluxProfCalc,lPerpParCalc
+      logical,             intent(in) :: lRmsCalc,lGeosCalc,lPhaseCalc
+      logical,             intent(in) :: l_probe_out
+      logical,             intent(in) :: lPressCalc
+      logical,             intent(in) :: lPressNext
+      real(cp),            intent(in) :: time,timeStage,dtLast
+      class(type_tscheme), intent(in) :: tscheme
+
+      !---- Output of explicit time step:
+      complex(cp), intent(out) :: dwdt(lm_max,nRstart:nRstop)
+      complex(cp), intent(out) :: dzdt(lm_max,nRstart:nRstop)
+      complex(cp), intent(out) :: dpdt(lm_max,nRstart:nRstop)
+      complex(cp), intent(out) :: dsdt(lm_max,nRstart:nRstop)
+      complex(cp), intent(out) :: dxidt(lm_max,nRstart:nRstop)
+      complex(cp), intent(out) :: dphidt(lm_max,nRstart:nRstop)
+      complex(cp), intent(out) :: dVSrLM(lm_max,nRstart:nRstop)
+      complex(cp), intent(out) :: dVXirLM(lm_max,nRstart:nRstop)
+      complex(cp), intent(out) :: dbdt(lm_maxMag,nRstartMag:nRstopMag)
+      complex(cp), intent(out) :: djdt(lm_maxMag,nRstartMag:nRstopMag)
+      complex(cp), intent(out) :: dVxVhLM(lm_max,nRstart:nRstop)
+      complex(cp), intent(out) :: dVxBhLM(lm_maxMag,nRstartMag:nRstopMag)
+      real(cp),    intent(out) :: lorentz_torque_ma,lorentz_torque_ic
+      complex(cp), intent(out) :: br_vt_lm_cmb(:)
+      complex(cp), intent(out) :: br_vp_lm_cmb(:)
+      complex(cp), intent(out) :: br_vt_lm_icb(:)
+      complex(cp), intent(out) :: br_vp_lm_icb(:)
+      real(cp),    intent(out) :: dtrkc(nRstart:nRstop),dthkc(nRstart:nRstop)
+
+      !-- Local variables
+      type(magic_fields_in)  :: fin
+      type(magic_fields_out) :: fout
+
+      !-- Diagnostics steps keep the reference's level-at-a-time loop (its transforms still run on the GPU)
+      if ( l_graph .or. l_frame .or. lTOCalc .or. lTONext .or. lTONext2 .or. lHelCalc .or. lPowerCalc .or.   &
+      &    lRmsCalc .or. lPressCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lGeosCalc .or. &
+      &    lHemiCalc .or. lPhaseCalc .or. l_probe_out ) then
+         call this%single%radialLoop(l_graph,l_frame,time,timeStage,tscheme,dtLast,lTOCalc,lTONext,lTONext2,   &
+              &                      lHelCalc,lPowerCalc,lRmsCalc,lPressCalc,lPressNext,lViscBcCalc,           &
+              &                      lFluxProfCalc,lPerpParCalc,lGeosCalc,lHemiCalc,lPhaseCalc,l_probe_out,    &
+              &                      dsdt,dwdt,dzdt,dpdt,dxidt,dphidt,dbdt,djdt,dVxVhLM,dVxBhLM,dVSrLM,dVXirLM,&
+              &                      lorentz_torque_ic,lorentz_torque_ma,br_vt_lm_cmb,br_vp_lm_cmb,            &
+              &                      br_vt_lm_icb,br_vp_lm_icb,dtrkc,dthkc)
+         return
+      end if
+
+      if ( .not. c_associated(this%rl) ) call this%create_plan(tscheme)
+
+      !-- Inputs: the R-distributed containers of fields.f90:211-268, (lm_max, nRstart:nRstop) each; the library
+      !   ignores the pointers of switched-off physics
+      fin = magic_fields_in(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
+      &                     c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr)
+      if ( l_conv .or. l_mag_kin ) then
+         fin%w = c_loc(w_Rloc);  fin%dw = c_loc(dw_Rloc);  fin%ddw = c_loc(ddw_Rloc)
+         fin%z = c_loc(z_Rloc);  fin%dz = c_loc(dz_Rloc)
+      end if
+      if ( l_heat ) then
+         fin%s = c_loc(s_Rloc);  fin%ds = c_loc(ds_Rloc)
+      end if
+      if ( l_chemical_conv ) fin%xi = c_loc(xi_Rloc)
+      if ( l_mag .or. l_mag_LF ) then
+         fin%b  = c_loc(b_Rloc);   fin%db = c_loc(db_Rloc);  fin%ddb = c_loc(ddb_Rloc)
+         fin%aj = c_loc(aj_Rloc);  fin%dj = c_loc(dj_Rloc)
+      end if
+
+      fout = magic_fields_out(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
+      &                       c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr)
+      fout%dwdt = addr_z(dwdt);  fout%dzdt = addr_z(dzdt)
+      if ( l_double_curl ) then
+         fout%dVxVhLM = addr_z(dVxVhLM)
+      else
+         fout%dpdt = addr_z(dpdt)
+      end if
+      if ( l_heat ) then
+         fout%dsdt = addr_z(dsdt);  fout%dVSrLM = addr_z(dVSrLM)
+      end if
+      if ( l_chemical_conv ) then
+         fout%dxidt = addr_z(dxidt);  fout%dVXirLM = addr_z(dVXirLM)
+      end if
+      if ( l_mag ) then
+         fout%dbdt = addr_z(dbdt);  fout%djdt = addr_z(djdt);  fout%dVxBhLM = addr_z(dVxBhLM)
+      end if
+      fout%dtrkc = addr_r(dtrkc);  fout%dthkc = addr_r(dthkc)
+
+      !-- omega_ma / omega_ic change from step to step when the walls rotate (v_rigid_boundary)
+      call magic_check( magic_rloop_set_rotation(this%rl, omega_ma, omega_ic), 'magic_rloop_set_rotation' )
+
+      !-- The loop: the explicit terms of all local levels (timeStage enters the precession terms, get_nl.f90:346-357)
+      call magic_check( magic_rloop_run(this%rl, fin, fout, timeStage), 'magic_rloop_run' )
+
+      !-- rIter.f90:279-292,461: Lorentz torques on a conducting, rotating inner core / mantle
+      call magic_check( magic_rloop_get_torques(this%rl, lorentz_torque_ic, lorentz_torque_ma), &
+           &            'magic_rloop_get_torques' )
+
+      !-- rIter.f90:267-277: products for the nonlinear magnetic boundary conditions (stress-free + conducting wall)
+      if ( l_b_nl_cmb .and. nRstart == n_r_cmb ) then
+         call magic_check( magic_rloop_get_br_v_bcs(this%rl, 0_c_int, br_vt_lm_cmb, br_vp_lm_cmb), 'get_br_v_bcs CMB' )
+      end if
+      if ( l_b_nl_icb .and. nRstop == n_r_icb ) then
+         call magic_check( magic_rloop_get_br_v_bcs(this%rl, 1_c_int, br_vt_lm_icb, br_vp_lm_icb), 'get_br_v_bcs ICB' )
+      end if
+
+      !-- the phase field is not on this path (initialize aborts when it is switched on)
+      dphidt(:,:) = zero
+
+   end subroutine radialLoop
+!------------------------------------------------------------------------------
+end module rIter_cuda_mod

@@ -1,0 +1,99 @@
+"""integration/*.f90 (the Fortran shim a MagIC maintainer would add) cannot be compiled here -- the image has no Fortran
+compiler -- so its C-facing half is checked textually against include/magic_sht.h and the built library: every
+bind(C, name=...) must be an exported symbol, the bind(C) derived types must list the members of the C structs in the same
+order and with matching types, and module sht must export exactly the public list of sht_native.f90:16-20."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _read(*p):
+    return open(os.path.join(ROOT, *p)).read()
+
+
+def _fortran_type(src, name):
+    """[(kind, member), ...] of `type, bind(C) :: name`, continuation lines joined."""
+    body = re.search(r"type, bind\(C\) :: %s\n(.*?)end type %s" % (name, name), src, re.S).group(1)
+    body = re.sub(r"&\s*\n\s*&", " ", body)
+    out = []
+    for line in body.splitlines():
+        line = line.split("!")[0].strip()
+        if not line:
+            continue
+        decl, names = line.split("::")
+        kind = {"integer(c_int)": "int", "real(c_double)": "double", "type(c_ptr)": "ptr"}[decl.strip()]
+        out += [(kind, n.strip()) for n in names.split(",") if n.strip()]
+    return out
+
+
+def _c_struct(src, name):
+    body = re.search(r"typedef struct \{((?:(?!typedef struct).)*?)\} %s;" % name, src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for stmt in body.split(";"):
+        stmt = " ".join(stmt.split())
+        if not stmt:
+            continue
+        m = re.match(r"(const )?(int|double) (.*)", stmt)
+        base = m.group(2)
+        for item in m.group(3).split(","):
+            item = item.strip()
+            out.append(("ptr" if item.startswith("*") else base, item.lstrip("*").strip()))
+    return out
+
+
+def test_every_bound_name_is_exported_by_the_library():
+    from magic_b200.lib import SYMBOLS
+    src = _read("integration", "magic_b200_c.f90")
+    names = re.findall(r"bind\(C, name='(\w+)'\)", src)
+    assert len(names) >= 30 and len(set(names)) == len(names)
+    for n in names:
+        assert n == "strlen" or n in SYMBOLS, n
+    # what the three shims need is all there: the 17 procedures, the loop, the transposer
+    for n in ("magic_scal_to_spat", "magic_toraxi_to_spat", "magic_torpol_to_curl_spat_IC", "magic_rloop_run",
+              "magic_rloop_get_br_v_bcs", "magic_transp_lm2r", "magic_transp_unique_id"):
+        assert n in names
+
+
+def test_bind_c_types_mirror_the_c_structs():
+    f = _read("integration", "magic_b200_c.f90")
+    h = _read("include", "magic_sht.h")
+    for name in ("magic_params", "magic_radial", "magic_fields_in", "magic_fields_out"):
+        assert _fortran_type(f, name) == _c_struct(h, name), name
+    # and the Python mirror agrees with both
+    from magic_b200.riter import Params
+    assert [n for n, _ in Params._fields_] == [n for _, n in _c_struct(h, "magic_params")]
+
+
+def test_module_sht_has_the_public_list_of_the_reference():
+    src = _read("integration", "sht_cuda.f90")
+    public = re.search(r"public :: (initialize_sht.*?)\n\ncontains", src, re.S).group(1)
+    public = {n.strip() for n in re.sub(r"&", " ", public).split(",") if n.strip()}
+    expected = {"initialize_sht", "finalize_sht", "scal_to_spat", "scal_to_grad_spat", "pol_to_grad_spat", "torpol_to_spat",
+                "sphtor_to_spat", "torpol_to_curl_spat_IC", "torpol_to_spat_IC", "torpol_to_dphspat", "pol_to_curlr_spat",
+                "torpol_to_curl_spat", "scal_to_SH", "spat_to_qst", "spat_to_sphertor", "axi_to_spat", "toraxi_to_spat"}
+    assert public == expected                                            # sht_native.f90:16-20 == shtns.f90:22-26
+    for n in expected:
+        assert len(re.findall(r"^   subroutine %s\(" % n, src, re.M)) == 1, n
+        assert len(re.findall(r"end subroutine %s$" % n, src, re.M)) == 1, n
+    # each wrapper forwards to the C entry point of the same name
+    for n in expected - {"initialize_sht", "finalize_sht"}:
+        assert "magic_%s(sht_h" % n in src, n
+
+
+def test_overriding_procedures_keep_the_reference_argument_lists():
+    """rIteration.f90:34-44 and mpi_transpose.f90:40-52: same dummy names in the same order, no TARGET on dummies."""
+    r = _read("integration", "rIter_cuda.f90")
+    args = re.search(r"subroutine radialLoop\((.*?)\)\n", r, re.S).group(1)
+    args = [a.strip() for a in re.sub(r"&", " ", args).split(",")]
+    assert args == ["this", "l_graph", "l_frame", "time", "timeStage", "tscheme", "dtLast", "lTOCalc", "lTONext", "lTONext2",
+                    "lHelCalc", "lPowerCalc", "lRmsCalc", "lPressCalc", "lPressNext", "lViscBcCalc", "lFluxProfCalc",
+                    "lPerpParCalc", "lGeosCalc", "lHemiCalc", "lPhaseCalc", "l_probe_out", "dsdt", "dwdt", "dzdt", "dpdt",
+                    "dxidt", "dphidt", "dbdt", "djdt", "dVxVhLM", "dVxBhLM", "dVSrLM", "dVXirLM", "lorentz_torque_ic",
+                    "lorentz_torque_ma", "br_vt_lm_cmb", "br_vp_lm_cmb", "br_vt_lm_icb", "br_vp_lm_icb", "dtrkc", "dthkc"]
+    assert "target, intent" not in r
+    t = _read("integration", "mpi_transp_cuda.f90")
+    for proc in ("create_comm", "destroy_comm", "transp_lm2r", "transp_r2lm"):
+        assert re.search(r"procedure :: %s\s+=> %s_cuda" % (proc, proc), t), proc
+    assert "arr_LMloc(llm:ulm,1:n_r_max,*)" in t and "arr_Rloc(1:lm_max,nRstart:nRstop,*)" in t
