@@ -169,7 +169,7 @@ class ShellHost:
     def __init__(self, lm2l, lm2m, radial_loop, n_r_max=33, n_cheb_max=None, radratio=0.35, ra=1e5, ek=1e-3, pr=1.0,
                  prmag=5.0, dtmax=1e-4, alpha=0.6, init_s1=404, amp_s1=0.1, init_b1=3, amp_b1=5.0, l_mag=True, ktopv=2,
                  kbotv=2, strat=0.0, polind=2.0, g0=0.0, g1=1.0, g2=0.0, l_correct_AMz=False, l_correct_AMe=False, l_heat=True,
-                 po=0.0, prec_angle=23.5, l_cond_ic=False, l_rot_ic=False, sigma_ratio=1.0, n_r_ic_max=17, n_cheb_ic_max=15):
+                 po=0.0, prec_angle=23.5, l_cond_ic=False, l_rot_ic=False, sigma_ratio=1.0, n_r_ic_max=17, n_cheb_ic_max=15, var_cond=None):
         self.lm2l = np.asarray(lm2l)
         self.lm2m = np.asarray(lm2m)
         self.lm_max = len(self.lm2l)
@@ -205,6 +205,20 @@ class ShellHost:
             self.DissNb, self.temp0, self.rho0, self.beta, self.dbeta, self.dLtemp0 = 0.0, one, one, 0 * one, 0 * one, 0 * one
             self.ViscHeatFac = 0.0
         self.orho1 = 1.0 / self.rho0
+        # heating prefactors (radial.f90:758-766) and magnetic diffusivity profile (radial.f90:903-916, nVarCond = 2: the
+        # two-branch conductivity of Gomez-Perez et al.; var_cond = dict(con_DecRate, con_RadRatio, con_LambdaMatch))
+        self.OhmLossFac = self.ViscHeatFac / (ek * prmag ** 2) if (self.l_anel and l_mag) else 0.0
+        self.lam, self.dLlam = np.ones(n_r_max), np.zeros(n_r_max)
+        if var_cond is not None and l_mag:
+            r0 = var_cond["con_RadRatio"] * g.r_cmb
+            r0 = r[np.argmin(np.abs(r - r0))]
+            LM, DR = var_cond["con_LambdaMatch"], var_cond["con_DecRate"]
+            ds0 = (LM - 1.0) * DR / (r0 - g.r_icb)
+            x = (r - g.r_icb) / (r0 - g.r_icb)
+            inner = r < r0
+            sigma = np.where(inner, 1.0 + (LM - 1.0) * x ** DR, LM * np.exp(ds0 / LM * (r - r0)))
+            dsigma = np.where(inner, ds0 * x ** (DR - 1.0), ds0 * np.exp(ds0 / LM * (r - r0)))
+            self.lam, self.dLlam = 1.0 / sigma, -dsigma / sigma
         self.c_moi_oc = 8.0 / 3.0 * np.pi * g.rInt_R(r ** 4 * self.rho0)         # preCalculations.f90:329-330
         self.alpha = alpha
         self.dtmax = dtmax
@@ -386,8 +400,9 @@ class ShellHost:
         fac = self.dL[None, :] * g.or2[:, None]
         self.old["b"] = fac * self.b
         self.old["j"] = fac * self.aj
-        ib = self.opm * fac * (self.ddb - fac * self.b)
-        ij = self.opm * fac * (ddj - fac * self.aj)
+        lam, dLlam = self.lam[:, None], self.dLlam[:, None]
+        ib = self.opm * lam * fac * (self.ddb - fac * self.b)
+        ij = self.opm * lam * fac * (ddj + dLlam * self.dj - fac * self.aj)
         for a in (ib, ij):
             a[0] = 0.0
             a[-1] = 0.0
@@ -460,8 +475,9 @@ class ShellHost:
             mats["wp"].append(W)
             if self.l_mag:
                 # bMat / jMat (updateB.f90:1824-1905), ktopb=kbotb=1, conductance_ma=0
-                B = dL * or2 * I - wl1 * self.opm * dL * or2 * (g.D2 - dL * or2 * I)
-                J = B.copy()
+                lam, dLlam = self.lam[:, None], self.dLlam[:, None]
+                B = dL * or2 * I - wl1 * self.opm * lam * dL * or2 * (g.D2 - dL * or2 * I)
+                J = dL * or2 * I - wl1 * self.opm * lam * dL * or2 * (g.D2 + dLlam * g.D1 - dL * or2 * I)
                 B[0] = g.D1[0] + l * g.or1[0] * I[0]
                 B[-1] = g.D1[-1] - (l + 1.0) * g.or1[-1] * I[-1]
                 J[0], J[-1] = I[0], I[-1]

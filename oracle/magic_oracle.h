@@ -31,7 +31,10 @@
  *   (7) for rotating conducting walls -- get_nl on the boundary levels (lMagNlBc), v_rigid_boundary with omega_ic, the
  *       Lorentz torque: all 1000 steps of samples/dynamo_benchmark_condICrotIC/reference.out and referenceMag.out, and for
  *       get_br_v_bcs (stress-free walls + conducting inner core) the 100 steps of its restarted stage
- *       (tests/test_condICrotIC.py).
+ *       (tests/test_condICrotIC.py);
+ *   (8) for a magnetic field in an anelastic background (Lorentz force and induction with orho1, Ohmic heating with
+ *       lambda(r), both kinds of boundary level under lMagNlBc): all 500 steps of samples/varCond/reference.out and
+ *       referenceMag.out (tests/test_varCond.py).
  * Still "parity unpinned" (no reference vectors reachable here, literal line-cited restatements only): the r = 0 level
  * itself (v_center_sphere: the energies of (5) are insensitive to it, measured) and the inner-core (_IC) and axisymmetric
  * syntheses (diagnostics, not called by the radial loop).
