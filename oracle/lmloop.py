@@ -169,7 +169,7 @@ class ShellHost:
     def __init__(self, lm2l, lm2m, radial_loop, n_r_max=33, n_cheb_max=None, radratio=0.35, ra=1e5, ek=1e-3, pr=1.0,
                  prmag=5.0, dtmax=1e-4, alpha=0.6, init_s1=404, amp_s1=0.1, init_b1=3, amp_b1=5.0, l_mag=True, ktopv=2,
                  kbotv=2, strat=0.0, polind=2.0, g0=0.0, g1=1.0, g2=0.0, l_correct_AMz=False, l_correct_AMe=False, l_heat=True,
-                 po=0.0, prec_angle=23.5, l_cond_ic=False, l_rot_ic=False, sigma_ratio=1.0, n_r_ic_max=17, n_cheb_ic_max=15, var_cond=None):
+                 po=0.0, prec_angle=23.5, l_cond_ic=False, l_rot_ic=False, sigma_ratio=1.0, n_r_ic_max=17, n_cheb_ic_max=15, var_cond=None, raxi=0.0, sc=1.0):
         self.lm2l = np.asarray(lm2l)
         self.lm2m = np.asarray(lm2m)
         self.lm_max = len(self.lm2l)
@@ -186,6 +186,8 @@ class ShellHost:
         self.oek = 1.0 / ek
         self.prec_fac = np.sqrt(8.0 * np.pi / 3.0) * po * self.oek ** 2 * np.sin(np.deg2rad(prec_angle)) if po != 0.0 else 0.0
         self.LFfac = 1.0 / (ek * prmag)       # preCalculations.f90:158
+        self.l_chem = raxi != 0.0             # Namelists.f90:421-427: chemical convection (double diffusion)
+        self.ChemFac, self.osc = (raxi / sc if self.l_chem else 0.0), 1.0 / sc           # preCalculations.f90:181-185
         r, or1, or2 = g.r, g.or1, g.or2
         self.rgrav = g0 + g1 * r / g.r_cmb + g2 * g.r_cmb ** 2 * or2            # radial.f90:628
         self.l_anel = strat > 0.0
@@ -230,6 +232,11 @@ class ShellHost:
         N, lm_max = self.N, self.lm_max
         z = lambda: np.zeros((N, lm_max), dtype=np.complex128)
         self.w, self.z, self.p, self.s, self.b, self.aj = z(), z(), z(), z(), z(), z()
+        self.xi = z()
+        self.topxi = np.zeros(lm_max, dtype=np.complex128)
+        self.botxi = np.zeros(lm_max, dtype=np.complex128)
+        if self.l_chem:
+            self.botxi[self._lm(0, 0)] = sq4pi      # ktopxi = kbotxi = 1 (preCalculations.f90:613-617)
         # conducting and / or freely rotating inner core (kbotb=3, nRotIC=1; Namelists.f90:398-407, :737-739)
         self.l_cond_ic, self.l_rot_ic, self.O_sr = l_cond_ic and l_mag, l_rot_ic, 1.0 / sigma_ratio
         self.omega_ic = 0.0
@@ -284,7 +291,7 @@ class ShellHost:
             self.aj[:, self._lm(2, 0)] += b_tor * r * np.sin(np.pi * (r - g.r_icb))
         # ---- time arrays (time_array.f90): old, impl (one level each for CNAB2), expl (two levels)
         self.old, self.impl, self.expl = {}, {}, {}
-        for nm in ("s", "w", "p", "z", "b", "j"):
+        for nm in ("s", "xi", "w", "p", "z", "b", "j"):
             self.old[nm], self.impl[nm] = z(), z()
             self.expl[nm] = [z(), z()]
         if self.l_cond_ic:
@@ -294,10 +301,40 @@ class ShellHost:
         self._mats = None
         # startFields.f90:373-432: derivatives and old/implicit terms of the start fields
         self._rhs_imp_s()
+        self._rhs_imp_xi()
         self._rhs_imp_wp()
         self._rhs_imp_z()
         if l_mag:
             self._rhs_imp_b()
+
+    def load_checkpoint(self, ck):
+        """Start from a MagIC checkpoint (magic_b200.checkpoint.Checkpoint, same grid and truncation -- no remapping):
+        fields, time, rotation rate of the inner core and, for a multistep file, the explicit terms of the previous step
+        (readCheckPoints.f90:767-1468); then startFields.f90:373-432 rebuilds the old / implicit terms."""
+        assert np.abs(ck.r - self.g.r).max() < 1e-13 and ck.lm_max == self.lm_max
+        names = {"w": "w", "z": "z", "p": "p", "s": "s", "xi": "xi", "b": "b", "aj": "aj", "b_ic": "b_ic", "aj_ic": "aj_ic"}
+        tarr = {"w": "w", "z": "z", "p": "p", "s": "s", "xi": "xi", "b": "b", "aj": "j", "b_ic": "b_ic", "aj_ic": "j_ic"}
+        for nm, attr in names.items():
+            if nm in ck.fields and hasattr(self, attr):
+                setattr(self, attr, np.array(ck.fields[nm], dtype=np.complex128))
+                past = ck.past.get(nm, {}).get("expl", [])
+                if past and tarr[nm] in self.expl:
+                    self.expl[tarr[nm]][1] = np.array(past[0], dtype=np.complex128)
+        # startFields.f90:257-279: a file written with the legacy boundary values (-ri^2, ro^2) / (ri^2 + ro^2) * sqrt(4 pi)
+        # of s(0,0) / xi(0,0) is translated to the present convention (0, sqrt(4 pi))
+        g = self.g
+        lm00 = self._lm(0, 0)
+        topval = -g.r_icb ** 2 / (g.r_icb ** 2 + g.r_cmb ** 2) * np.sqrt(4.0 * np.pi)
+        botval = g.r_cmb ** 2 / (g.r_icb ** 2 + g.r_cmb ** 2) * np.sqrt(4.0 * np.pi)
+        for f in (self.s, self.xi):
+            if abs(f[0, lm00] - topval) <= 1e4 * np.finfo(float).eps and abs(f[-1, lm00] - botval) <= 1e4 * np.finfo(float).eps:
+                f[:, lm00] -= topval
+        self.time = float(ck.time)
+        self.omega_ic = float(ck.rotation["omega_ic1"])
+        past = ck.scalars_past.get("domega_ic_dt", {}).get("expl", [])
+        if len(past):
+            self.dom_ic["expl"][1] = float(past[0])
+        self.restart()
 
     def restart(self, **flags):
         """A run restarted from its own checkpoint with other switches (samples/*/input_restart.nml): the checkpoint carries
@@ -310,6 +347,7 @@ class ShellHost:
             setattr(self, k, v)
         self._mats = None
         self._rhs_imp_s()
+        self._rhs_imp_xi()
         self._rhs_imp_wp()
         self._rhs_imp_z()
         if self.l_mag:
@@ -327,6 +365,15 @@ class ShellHost:
         self.old["s"] = self.s.copy()
         self.impl["s"] = self.opr * (dds + (self.beta + self.dLtemp0 + 2.0 * g.or1)[:, None] * self.ds -
                                      self.dL[None, :] * g.or2[:, None] * self.s)
+
+    def _rhs_imp_xi(self):
+        """get_comp_rhs_imp, updateXI.f90:579-650."""
+        g = self.g
+        self.dxi = g.D1 @ self.xi
+        ddxi = g.D2 @ self.xi
+        self.old["xi"] = self.xi.copy()
+        self.impl["xi"] = self.osc * (ddxi + (self.beta + 2.0 * g.or1)[:, None] * self.dxi -
+                                      self.dL[None, :] * g.or2[:, None] * self.xi)
 
     def _rhs_imp_z(self):
         """get_tor_rhs_imp, updateZ.f90:760-1025 (visc=1, no rotating walls), with the angular-momentum corrections."""
@@ -379,7 +426,7 @@ class ShellHost:
         old_p = -fac * self.dw
         Dif = fac * (self.ddw - beta / 3.0 * self.dw - (fac + 4.0 / 3.0 * (dbeta + beta * or1)) * self.w)
         Pre = -self.dp + beta * self.p
-        Buo = self.BuoFac * (self.rho0 * self.rgrav)[:, None] * self.s
+        Buo = (self.rho0 * self.rgrav)[:, None] * (self.BuoFac * self.s + self.ChemFac * self.xi)
         imp_w = Pre + Dif + Buo
         imp_p = fac * self.p + fac * (-dddw + beta * self.ddw + (fac + dbeta + 2.0 * beta * or1) * self.dw -
                                       fac * (2.0 * or1 + 2.0 / 3.0 * beta) * self.w)
@@ -445,13 +492,17 @@ class ShellHost:
         beta, dbeta = self.beta[:, None], self.dbeta[:, None]
         or1, or2 = g.or1[:, None], g.or2[:, None]
         b0, bN = self.beta[0], self.beta[-1]
-        mats = {"s": [], "z": [], "wp": [], "b": [], "j": []}
+        mats = {"s": [], "xi": [], "z": [], "wp": [], "b": [], "j": []}
         for l in range(self.l_max + 1):
             dL = float(l * (l + 1))
             # sMat (updateS.f90:1086-1140), ktops=kbots=1
             M = I - wl1 * self.opr * (g.D2 + (beta + self.dLtemp0[:, None] + 2.0 * or1) * g.D1 - dL * or2 * I)
             M[0], M[-1] = I[0], I[-1]
             mats["s"].append(M)
+            # xiMat (updateXI.f90:924-965), ktopxi = kbotxi = 1
+            M = I - wl1 * self.osc * (g.D2 + (beta + 2.0 * or1) * g.D1 - dL * or2 * I)
+            M[0], M[-1] = I[0], I[-1]
+            mats["xi"].append(M)
             # zMat (updateZ.f90:1850-1890)
             M = dL * or2 * I - wl1 * dL * or2 * (g.D2 - beta * g.D1 - (dL * or2 + dbeta + 2.0 * beta * or1) * I)
             M[0] = I[0] if self.ktopv == 2 else g.D1[0] - (2.0 * g.or1[0] + b0) * I[0]
@@ -549,19 +600,48 @@ class ShellHost:
         f = dict(w=self.w, dw=self.dw, ddw=self.ddw, z=self.z, dz=self.dz)
         if self.l_heat:
             f["s"] = self.s
+        if self.l_chem:
+            f["xi"] = self.xi
         if self.l_mag:
             f.update(b=self.b, db=self.db, ddb=self.ddb, aj=self.aj, dj=self.dj)
         return f
 
     def step(self):
         """One pass of the n_time_step loop of step_time.f90:480-763 (CNAB2: one stage)."""
-        g, N = self.g, self.N
         out = self.radial_loop({k: np.ascontiguousarray(v) for k, v in self.fields_Rloc().items()})
+        self._explicit(out)
+        # dt_courant (courant.f90:277-346)
+        dt_min = min(self.dtrkc_min, self.dthkc_min, 1000.0 * self.dtmax)
+        if self.dt[0] > dt_min:
+            raise RuntimeError("Courant criterion asks for a smaller time step; not expected in this sample")
+        self.dt = np.array([self.dt[0], self.dt[0]])                                    # set_dt_array
+        wts = self._weights()
+        wimp, wl1, wl2, we1, we2 = wts
+        if self._mats is None or self._mats[0] != wl1:
+            self._build_mats(wl1)
+        self.time += self.dt[0]
+        d = self.dom_ic
+
+        def rotate(nm):
+            if nm == "dom_ic":
+                d["expl"][1] = d["expl"][0]
+            else:
+                self.expl[nm][1] = self.expl[nm][0]
+
+        self._lm_loop(lambda nm: self._imex_rhs(nm, wts),
+                      lambda: wimp * d["old"] + wl2 * d["impl"] + we1 * d["expl"][0] + we2 * d["expl"][1], wl1, rotate)
+        self.n_steps += 1
+
+    def _explicit(self, out):
+        """finish_explicit_assembly (LMLoop.f90:390-453, dentropy0 = 0) on the output of one radial loop: the explicit
+        terms of the current stage go to self.expl[*][0] (and self.dom_ic['expl'][0])."""
+        g = self.g
         or2 = g.or2[:, None]
         l0 = (self.lm2l == 0)[None, :]
-        # finish_explicit_assembly (LMLoop.f90:390-453), dentropy0=0
         if self.l_heat:
             self.expl["s"][0] = self.orho1[:, None] * (out["dsdt"] - or2 * (g.D1t @ out["dVSrLM"]))   # updateS.f90:587-597
+        if self.l_chem:
+            self.expl["xi"][0] = self.orho1[:, None] * (out["dxidt"] - or2 * (g.D1t @ out["dVXirLM"]))   # updateXI.f90:495-511
         self.expl["w"][0] = np.array(out["dwdt"])
         self.expl["p"][0] = np.array(out["dpdt"])
         self.expl["z"][0] = np.array(out["dzdt"])
@@ -582,18 +662,14 @@ class ShellHost:
                 e = fac * f
                 e[0] = 0.0
                 self.expl[nm][0] = e
-        # dt_courant (courant.f90:277-346)
         self.dtrkc_min, self.dthkc_min = float(np.min(out["dtrkc"])), float(np.min(out["dthkc"]))
-        dt_min = min(self.dtrkc_min, self.dthkc_min, 1000.0 * self.dtmax)
-        if self.dt[0] > dt_min:
-            raise RuntimeError("Courant criterion asks for a smaller time step; not expected in this sample")
-        self.dt = np.array([self.dt[0], self.dt[0]])                                    # set_dt_array
-        wts = self._weights()
-        wimp, wl1, wl2, we1, we2 = wts
-        if self._mats is None or self._mats[0] != wl1:
-            self._build_mats(wl1)
+
+    def _lm_loop(self, rhs_of, dom_ic_rhs, wl1, rotate):
+        """LMLoop (LMLoop.f90:150-330): updateS, updateZ, updateWP, updateB in the reference's order.  rhs_of(name) is the
+        time scheme's set_imex_rhs for the time array `name`, dom_ic_rhs() its scalar twin for the inner-core rotation,
+        wl1 = wimp_lin(1) the implicit weight the matrices were built with, rotate(name) the scheme's rotate_imex."""
+        g, N = self.g, self.N
         mats = self._mats[1]
-        self.time += self.dt[0]
         m0 = self.lm2m == 0
 
         def per_degree(fn):
@@ -601,11 +677,8 @@ class ShellHost:
                 idx = np.nonzero(self.lm2l == l)[0]
                 fn(l, idx)
 
-        def rotate(nm):
-            self.expl[nm][1] = self.expl[nm][0]
-
         # ---- updateS (updateS.f90:156-342)
-        rhs = self._imex_rhs("s", wts)
+        rhs = rhs_of("s")
         rhs[0], rhs[-1] = self.tops, self.bots
 
         def up_s(l, idx):
@@ -615,8 +688,19 @@ class ShellHost:
             self.s[:, m0] = self.s[:, m0].real
             rotate("s")
             self._rhs_imp_s()
+        # ---- updateXi (updateXI.f90:150-330)
+        if self.l_chem:
+            rhs = rhs_of("xi")
+            rhs[0], rhs[-1] = self.topxi, self.botxi
+
+            def up_xi(l, idx):
+                self.xi[:, idx] = g.solve(mats["xi"][l], rhs[:, idx], (0, N - 1), ("xi", l))
+            per_degree(up_xi)
+            self.xi[:, m0] = self.xi[:, m0].real
+            rotate("xi")
+            self._rhs_imp_xi()
         # ---- updateZ (updateZ.f90:191-488)
-        rhs = self._imex_rhs("z", wts)
+        rhs = rhs_of("z")
         if self.prec_fac != 0.0:   # updateZ.f90:385-392: the implicit half of the Poincare force, at the new time
             rhs[:, self._lm(1, 1)] += wl1 * self.prec_fac * (np.sin(self.oek * self.time) - 1j * np.cos(self.oek * self.time))
         rhs[0], rhs[-1] = 0.0, 0.0
@@ -629,9 +713,8 @@ class ShellHost:
         per_degree(up_z)
         if self.l_rot_ic:     # updateZ.f90:300-356, :416-420: z(1,0) with the inner-core torque balance, then update_rot_rates
             lm10 = self._lm(1, 0)
-            d = self.dom_ic
-            dom = wimp * d["old"] + wl2 * d["impl"] + we1 * d["expl"][0] + we2 * d["expl"][1]
-            d["expl"][1] = d["expl"][0]
+            dom = dom_ic_rhs()
+            rotate("dom_ic")
             if self.kbotv == 2:
                 r10 = rhs[:, [lm10]].copy()
                 r10[-1] = dom
@@ -643,8 +726,8 @@ class ShellHost:
         rotate("z")
         self._rhs_imp_z()
         # ---- updateWP (updateWP.f90:255-634), buoyancy of the NEW entropy is implicit (:514-524)
-        rw = self._imex_rhs("w", wts) + wl1 * self.BuoFac * (self.rho0 * self.rgrav)[:, None] * self.s
-        rp = self._imex_rhs("p", wts)
+        rw = rhs_of("w") + wl1 * (self.rho0 * self.rgrav)[:, None] * (self.BuoFac * self.s + self.ChemFac * self.xi)
+        rp = rhs_of("p")
         for a in (rw, rp):
             a[0], a[-1] = 0.0, 0.0
 
@@ -663,8 +746,8 @@ class ShellHost:
         self._rhs_imp_wp()
         # ---- updateB (updateB.f90:226-694)
         if self.l_mag:
-            rb = self._imex_rhs("b", wts)
-            rj = self._imex_rhs("j", wts)
+            rb = rhs_of("b")
+            rj = rhs_of("j")
             for a in (rb, rj):
                 a[0], a[-1] = 0.0, 0.0
 
@@ -681,7 +764,7 @@ class ShellHost:
                 self.b[:, idx] = g.solve(mats["b"][l], rb[:, idx], (0, N - 1), ("b", l))
                 self.aj[:, idx] = g.solve(mats["j"][l], rj[:, idx], (0, N - 1), ("j", l))
             if self.l_cond_ic:
-                rbi, rji = self._imex_rhs("b_ic", wts), self._imex_rhs("j_ic", wts)
+                rbi, rji = rhs_of("b_ic"), rhs_of("j_ic")
             per_degree(up_b)
             self.b[:, m0] = self.b[:, m0].real
             self.aj[:, m0] = self.aj[:, m0].real
@@ -695,7 +778,6 @@ class ShellHost:
                 rotate("b_ic")
                 rotate("j_ic")
             self._rhs_imp_b()
-        self.n_steps += 1
 
     # ------------------------------------------------------------------------------------------------
     def e_kin(self):
@@ -734,6 +816,77 @@ class ShellHost:
         cols = [e_p.sum(1), e_t.sum(1), e_p[:, axi].sum(1), e_t[:, axi].sum(1), e_p[:, es_p].sum(1),
                 e_t[:, ~es_p].sum(1), e_p[:, eas_p].sum(1), e_t[:, eas_t].sum(1)]
         return np.array([fac * float(I(c)) for c in cols])
+
+
+class DirkShellHost(ShellHost):
+    """ShellHost advanced by a diagonally implicit IMEX Runge-Kutta scheme without assembly stage (dirk_schemes.f90).  Per
+    stage: radial loop on the current fields where the scheme needs an explicit term (l_exp_calc), set_imex_rhs =
+    old(1) + dt sum_j a_exp(i+1,j) expl(j) + dt sum_j a_imp(i+1,j) impl(j) (dirk_schemes.f90:856-895), one LM loop with the
+    constant diagonal weight, then the implicit term of the new stage state (step_time.f90:396-763)."""
+
+    SCHEMES = {
+        # dirk_schemes.f90:723-742
+        "BPR353": dict(imp=[[0, 0, 0, 0, 0], [0.5, 0.5, 0, 0, 0], [5.0 / 18.0, -1.0 / 9.0, 0.5, 0, 0], [0.5, 0, 0, 0.5, 0],
+                            [0.25, 0, 0.75, -0.5, 0.5]],
+                       exp=[[0, 0, 0, 0, 0], [1.0, 0, 0, 0, 0], [4.0 / 9.0, 2.0 / 9.0, 0, 0, 0], [0.25, 0, 0.75, 0, 0],
+                            [0.25, 0, 0.75, 0, 0]],
+                       l_exp_calc=[True, True, True, False], c=[1.0, 2.0 / 3.0, 1.0, 1.0], wimp=0.5),
+    }
+
+    def __init__(self, *a, time_scheme="BPR353", **kw):
+        super().__init__(*a, **kw)
+        sc = self.SCHEMES[time_scheme]
+        self.a_imp, self.a_exp = np.array(sc["imp"], dtype=float), np.array(sc["exp"], dtype=float)
+        self.l_exp_calc, self.c_stage, self.wimp0 = sc["l_exp_calc"], sc["c"], sc["wimp"]
+        self.nstages = len(self.l_exp_calc)
+        self.time_stage = self.time
+
+    def step(self):
+        dt = self.dt[0]
+        names = [nm for nm in self.old]
+        old1 = {nm: self.old[nm].copy() for nm in names}
+        impl = {nm: [self.impl[nm].copy()] for nm in names}
+        expl = {nm: [] for nm in names}
+        d = self.dom_ic
+        dom_old1, dom_impl, dom_expl = d["old"], [d["impl"]], []
+        wl1 = dt * self.wimp0
+        if self._mats is None or self._mats[0] != wl1:
+            self._build_mats(wl1)
+        t_last = self.time
+        for ist in range(1, self.nstages + 1):
+            if self.l_exp_calc[ist - 1]:
+                out = self.radial_loop({k: np.ascontiguousarray(v) for k, v in self.fields_Rloc().items()})
+                self._explicit(out)
+                if self.dt[0] > min(self.dtrkc_min, self.dthkc_min):
+                    raise RuntimeError("Courant criterion asks for a smaller time step; not expected in this sample")
+                for nm in names:
+                    expl[nm].append(np.array(self.expl[nm][0]))
+                dom_expl.append(d["expl"][0])
+            else:
+                for nm in names:
+                    expl[nm].append(None)
+                dom_expl.append(0.0)
+            if ist == 1:
+                self.time = t_last + dt                                   # step_time.f90:721-722
+            self.time_stage = t_last + dt * self.c_stage[ist - 1]         # get_time_stage, dirk_schemes.f90:1075-1085
+
+            def rhs_of(nm, ist=ist):
+                r = old1[nm].copy()
+                for j in range(ist):
+                    if self.a_exp[ist, j] != 0.0:
+                        r += dt * self.a_exp[ist, j] * expl[nm][j]
+                    if self.a_imp[ist, j] != 0.0:
+                        r += dt * self.a_imp[ist, j] * impl[nm][j]
+                return r
+
+            def dom_rhs(ist=ist):
+                return dom_old1 + dt * sum(self.a_exp[ist, j] * dom_expl[j] + self.a_imp[ist, j] * dom_impl[j] for j in range(ist))
+
+            self._lm_loop(rhs_of, dom_rhs, wl1, lambda nm: None)
+            for nm in names:                   # get_*_rhs_imp(..., istage+1): implicit term of the new stage state
+                impl[nm].append(self.impl[nm].copy())
+            dom_impl.append(d["impl"])
+        self.n_steps += 1
 
 
 class BoussinesqDynamoHost(ShellHost):
