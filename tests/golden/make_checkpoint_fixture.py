@@ -39,7 +39,7 @@ def read_checkpoint(path):
     if multistep:
         n = nexp + nimp + nold - 3
         np.fromfile(f, np.float64, 2 * n)
-    np.fromfile(f, np.float64, 12)
+    omega = np.fromfile(f, np.float64, 12)
     l_heat, l_chem, l_phase, l_mag, l_press, l_cond_ic = np.fromfile(f, np.int32, 6)
     extra = (nexp + nimp + nold - 3) if multistep else 0
 
@@ -51,13 +51,18 @@ def read_checkpoint(path):
 
     out = dict(w=field(), z=field())
     if l_press:
-        field()
+        out["p"] = field()
     if l_heat:
         out["s"] = field()
     assert not l_chem and not l_phase
     if l_mag:
         out["b"] = field()
         out["aj"] = field()
+    if l_mag and l_cond_ic:      # inner-core potentials (for tests/test_boussBenchSat.py)
+        for nm in ("b_ic", "aj_ic"):
+            out[nm] = np.fromfile(f, np.complex128, n_r_ic_max * lm_max).reshape(n_r_ic_max, lm_max)
+        assert f.read() == b""
+    out.update(omega_ic1=omega[0], dt=dt, reference_out=np.loadtxt(os.path.join(REF, "reference.out")))
     out.update(radius=radius, l_max=l_max, m_max=m_max, minc=minc, n_r_max=n_r_max, n_theta_max=n_theta_max,
                n_phi_tot=n_phi_tot, ek=ek, prmag=prmag, radratio=radratio, time=time)
     return out
