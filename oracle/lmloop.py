@@ -10,6 +10,13 @@ matrices) path that `samples/dynamo_benchmark` (Boussinesq MHD, rigid insulating
 itself is a callable handed in by the test: the CPU oracle or the CUDA library through the C ABI.  With either, the
 energy series of reference.out / referenceMag.out must be reproduced at the autotest tolerance.
 
+Grown since, one reference sample at a time, and always the same way (a switch of ShellHost, the routines it restates cited
+below): samples/precession (l_heat off, Poincare force), samples/dynamo_benchmark_condICrotIC (conducting inner core on an
+even-Chebyshev grid, coupled outer/inner-core matrices, freely rotating inner core, restart with other boundary conditions,
+nonlinear magnetic boundary condition at the ICB), samples/varCond (anelastic MHD, variable conductivity),
+samples/doubleDiffusion and samples/boussBenchSat (composition equation, start from a checkpoint, IMEX Runge-Kutta scheme
+BPR353 in DirkShellHost).  The finite-difference full sphere of samples/full_sphere lives in oracle/lmloop_fd.py.
+
 It is NOT on the product path (magic_b200/ never imports oracle/); the product keeps the Fortran host.
 
 Restated reference routines (file:line relative to /root/reference/src):
@@ -28,6 +35,18 @@ Restated reference routines (file:line relative to /root/reference/src):
   dt_courant                           courant.f90:277-346
   get_e_kin / get_e_mag                kinetic_energy.f90:95-230, magnetic_energy.f90:262-470
   step order                           step_time.f90:480-763
+  precession                           updateZ.f90:231-235, :385-392, :955-958; preCalculations.f90:164-166
+  conducting inner core                radial.f90:798-868, chebyshev_polynoms.f90 get_chebs_even, radial_derivatives_even.f90:16-70,
+                                       init_fields.f90:1140-1176, updateB.f90:529-548 (rhs), :1955-2060 (get_bMat), :1077-1187
+                                       (get_mag_ic_rhs_imp), :955-1003 (finish_exp_mag_ic)
+  rotating inner core                  updateZ.f90:300-356 (z10 rhs), :1719-1800 (get_z10Mat), :996-1008, :1563-1619
+                                       (update_rot_rates), :1659-1688 (finish_exp_tor); preCalculations.f90:313-345
+  nonlinear magnetic BC at the ICB     Namelists.f90:713-720, nonlinear_bcs.f90:71-118 (get_b_nl_bcs), updateB.f90:534-539
+  variable conductivity                radial.f90:903-916 (nVarCond = 2), updateB.f90:1633-1637, :1826-1837
+  composition                          updateXI.f90:495-511, :579-650, :924-965; preCalculations.f90:181-185, :613-617
+  restart                              readCheckPoints.f90:767-1468, startFields.f90:257-279, :373-432
+  IMEX Runge-Kutta (BPR353)            dirk_schemes.f90:723-742, :764-788, :856-895, :1075-1085; step_time.f90:396-763
+  get_dr of raw explicit terms         radial_derivatives.f90 get_dcheb (modes below n_cheb_max only)
 
 The reference solves for Chebyshev coefficients with collocation matrices rMat/drMat/... and transforms back (costf1).
 Here the operators are written for grid values with the differentiation matrices D_k = d^kT . T^-1 and mapped to
