@@ -355,6 +355,31 @@ class ShellHost:
             self.dom_ic["expl"][1] = float(past[0])
         self.restart()
 
+    _STATE_FIELDS = ("w", "z", "p", "s", "xi", "b", "aj", "b_ic", "aj_ic")
+
+    def state_dict(self):
+        """What a checkpoint of a multistep run holds (storeCheckPoints.f90:45-277): fields, the explicit terms of the
+        previous step, rotation rate and its explicit term, time and time step -- as a flat dict of arrays (np.savez)."""
+        d = {"time": self.time, "dt": self.dt, "omega_ic": self.omega_ic, "dom_ic_expl2": self.dom_ic["expl"][1]}
+        for nm in self._STATE_FIELDS:
+            if hasattr(self, nm):
+                d["field_" + nm] = getattr(self, nm)
+        for nm, e in self.expl.items():
+            d["expl2_" + nm] = e[1]
+        return d
+
+    def load_state_dict(self, d):
+        for nm in self._STATE_FIELDS:
+            if "field_" + nm in d and hasattr(self, nm):
+                setattr(self, nm, np.array(d["field_" + nm], dtype=np.complex128))
+        for nm in self.expl:
+            if "expl2_" + nm in d:
+                self.expl[nm][1] = np.array(d["expl2_" + nm], dtype=np.complex128)
+        self.time, self.dt = float(d["time"]), np.array(d["dt"], dtype=float)
+        self.omega_ic = float(d["omega_ic"])
+        self.dom_ic["expl"][1] = float(d["dom_ic_expl2"])
+        self.restart()
+
     def restart(self, **flags):
         """A run restarted from its own checkpoint with other switches (samples/*/input_restart.nml): the checkpoint carries
         the fields, the explicit terms of the previous step and the rotation rates (storeCheckPoints.f90:45-277), all of

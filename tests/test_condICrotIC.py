@@ -95,30 +95,33 @@ def test_start_fields_carry_the_reference_magnetic_energy(golden):
     _check(golden, h, 0)
 
 
+def test_oracle_radial_loop_reproduces_the_first_steps(golden):
+    """CPU oracle inside the reference's time loop: the first 30 steps of input.nml, 8 kinetic and 12 magnetic energy columns
+    after every step; the inner core is spun up from rest by the Lorentz torque the loop returns.  (All 1000 steps of this
+    stage are checked the same way by tests/golden/make_condICrotIC_state.py when it builds the restart state, and by the
+    GPU leg below.)"""
+    h = _oracle_loop(golden)
+    for row in range(1, 31):
+        h.step()
+        _check(golden, h, row)
+    assert 55.0 < h.omega_ic < 65.0 and h.lorentz_torque_ic > 0.0
+
+
 @pytest.fixture(scope="module")
 def first_run(golden):
-    """CPU oracle inside the reference's time loop: the 1000 steps of input.nml, 8 kinetic and 12 magnetic energy columns
-    checked after every step; returns the pickled host at t = 0.1 (what checkpoint_end.start holds)."""
-    import pickle
-    from threadpoolctl import threadpool_limits
-    h = _oracle_loop(golden)
-    with threadpool_limits(limits=1, user_api="blas"):   # 33 x 33 systems: BLAS threads only cost time here
-        for row in range(1, N_FIRST + 1):
-            h.step()
-            _check(golden, h, row)
-            if row == 60:
-                assert 76.0 < h.omega_ic < 78.0 and h.lorentz_torque_ic > 0.0     # spun up by the torque the loop returns
-    loop, h.radial_loop = h.radial_loop, None
-    return pickle.dumps(h)
+    """The state after the 1000 steps of input.nml (what checkpoint_end.start holds): tests/golden/condICrotIC_state_1000.npz,
+    produced by this host with the CPU oracle, every step checked against reference.out on the way
+    (tests/golden/make_condICrotIC_state.py)."""
+    d = np.load(os.path.join(HERE, "golden", "condICrotIC_state_1000.npz"))
+    return {k: d[k] for k in d.files}
 
 
 def _restarted(golden, first_run, tweak=None, out_tweak=None):
-    import pickle
     from oracle.oracle import Oracle, Params as OParams
     gs = _sizes(golden)
     o = Oracle(gs["l_max"], n_theta=gs["n_theta_max"], n_phi=gs["n_phi_max"], m_max=gs["m_max"], threads=1)
-    h = pickle.loads(first_run)
-    _, p, rad = _setup(golden, o.lm2l, o.lm2m)
+    h, p, rad = _setup(golden, o.lm2l, o.lm2m)
+    h.load_state_dict(first_run)
     p.ktopv = p.kbotv = 1
     op = OParams()
     for n, _ in p._fields_:
@@ -137,7 +140,7 @@ def _restarted(golden, first_run, tweak=None, out_tweak=None):
 
 
 def test_oracle_radial_loop_reproduces_reference_energies(golden, first_run):
-    """Rows 1..1000 are checked inside the fixture; here the restart: row 1001 is the checkpoint state AFTER startFields has
+    """The restart from the state after 1000 steps: row 1001 is the checkpoint state AFTER startFields has
     applied the angular-momentum correction (before it the axisymmetric toroidal energy is off by 0.32), rows 1002..1101 the
     100 stress-free steps with the nonlinear magnetic boundary condition at the ICB."""
     h = _restarted(golden, first_run)
