@@ -97,3 +97,47 @@ def test_overriding_procedures_keep_the_reference_argument_lists():
     for proc in ("create_comm", "destroy_comm", "transp_lm2r", "transp_r2lm"):
         assert re.search(r"procedure :: %s\s+=> %s_cuda" % (proc, proc), t), proc
     assert "arr_LMloc(llm:ulm,1:n_r_max,*)" in t and "arr_Rloc(1:lm_max,nRstart:nRstop,*)" in t
+
+
+def _crack(path):
+    """numpy.f2py's Fortran parser: good enough for modules without type-bound procedures (it returns nothing for the
+    reference's own rIter.f90 either), i.e. for magic_b200_c.f90 and sht_cuda.f90."""
+    import contextlib
+    import io
+    import numpy.f2py.crackfortran as cf
+    cf.verbose = 0
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(buf):
+        blocks = cf.crackfortran([path])
+    out = {}
+
+    def walk(bs):
+        for b in bs:
+            if b.get("block") in ("subroutine", "function"):
+                out[b["name"]] = list(b.get("args", []))
+            walk(b.get("body", []))
+    walk(blocks)
+    return out
+
+
+def test_a_fortran_parser_accepts_the_two_plain_modules():
+    """Parsed with numpy.f2py.crackfortran: every interface of magic_b200_c.f90 takes as many arguments as the C prototype of
+    the same name in include/magic_sht.h, and the 17 procedures of sht_cuda.f90 have the reference's argument counts."""
+    h = _read("include", "magic_sht.h")
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|double|void \*|const char \*|long long)\s*\*?\s*(magic_\w+)\(([^;{]*?)\);", h, re.S):
+        args = " ".join(m.group(2).split())
+        protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    procs = _crack(os.path.join(ROOT, "integration", "magic_b200_c.f90"))
+    bound = [n for n in procs if n.startswith("magic_") and n != "magic_check"]
+    assert len(bound) >= 30
+    for n in bound:
+        cname = [k for k in protos if k.lower() == n][0]
+        assert len(procs[n]) == protos[cname], (n, procs[n], protos[cname])
+    sht = _crack(os.path.join(ROOT, "integration", "sht_cuda.f90"))
+    expected = {"initialize_sht": 1, "finalize_sht": 0, "scal_to_spat": 3, "scal_to_grad_spat": 4, "pol_to_grad_spat": 4,
+                "torpol_to_spat": 7, "sphtor_to_spat": 5, "torpol_to_curl_spat_ic": 9, "torpol_to_spat_ic": 8,
+                "torpol_to_dphspat": 5, "pol_to_curlr_spat": 3, "torpol_to_curl_spat": 9, "scal_to_sh": 3, "spat_to_qst": 7,
+                "spat_to_sphertor": 5, "axi_to_spat": 2, "toraxi_to_spat": 4}        # sht_native.f90:24-405
+    assert {k: len(v) for k, v in sht.items()} == expected
