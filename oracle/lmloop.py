@@ -188,7 +188,7 @@ class ShellHost:
     def __init__(self, lm2l, lm2m, radial_loop, n_r_max=33, n_cheb_max=None, radratio=0.35, ra=1e5, ek=1e-3, pr=1.0,
                  prmag=5.0, dtmax=1e-4, alpha=0.6, init_s1=404, amp_s1=0.1, init_b1=3, amp_b1=5.0, l_mag=True, ktopv=2,
                  kbotv=2, strat=0.0, polind=2.0, g0=0.0, g1=1.0, g2=0.0, l_correct_AMz=False, l_correct_AMe=False, l_heat=True,
-                 po=0.0, prec_angle=23.5, l_cond_ic=False, l_rot_ic=False, sigma_ratio=1.0, n_r_ic_max=17, n_cheb_ic_max=15, var_cond=None, raxi=0.0, sc=1.0):
+                 po=0.0, prec_angle=23.5, l_cond_ic=False, l_rot_ic=False, sigma_ratio=1.0, n_r_ic_max=17, n_cheb_ic_max=15, var_cond=None, raxi=0.0, sc=1.0, dif_exp=None):
         self.lm2l = np.asarray(lm2l)
         self.lm2m = np.asarray(lm2m)
         self.lm_max = len(self.lm2l)
@@ -226,6 +226,16 @@ class ShellHost:
             self.DissNb, self.temp0, self.rho0, self.beta, self.dbeta, self.dLtemp0 = 0.0, one, one, 0 * one, 0 * one, 0 * one
             self.ViscHeatFac = 0.0
         self.orho1 = 1.0 / self.rho0
+        # transport properties (radial.f90 transportProperties): nVarVisc = nVarDiff = 2, visc = kappa = (rho0 / rho0(icb))^difExp,
+        # logarithmic derivatives through get_dr as in the reference
+        one_r = np.ones(n_r_max)
+        self.visc, self.dLvisc, self.ddLvisc, self.kappa, self.dLkappa = one_r, 0 * one_r, 0 * one_r, one_r, 0 * one_r
+        if dif_exp is not None:
+            self.visc = (self.rho0 / self.rho0[-1]) ** dif_exp
+            self.dLvisc = (g.D1t @ self.visc) / self.visc
+            self.ddLvisc = g.D1t @ self.dLvisc
+            self.kappa = self.visc.copy()
+            self.dLkappa = self.dLvisc.copy()
         # heating prefactors (radial.f90:758-766) and magnetic diffusivity profile (radial.f90:903-916, nVarCond = 2: the
         # two-branch conductivity of Gomez-Perez et al.; var_cond = dict(con_DecRate, con_RadRatio, con_LambdaMatch))
         self.OhmLossFac = self.ViscHeatFac / (ek * prmag ** 2) if (self.l_anel and l_mag) else 0.0
@@ -277,7 +287,7 @@ class ShellHost:
         if self.l_heat:
             self.bots[lm00] = sq4pi           # preCalculations.f90:415-418
         # ---- initS: conductive state (ps_cond, entropy diffusion, epsc=0; init_fields.f90:2270-2291) + one mode (:428-541)
-        M = self.opr * (g.D2 + (self.beta + self.dLtemp0 + 2.0 * or1)[:, None] * g.D1)
+        M = self.opr * self.kappa[:, None] * (g.D2 + (self.beta + self.dLtemp0 + 2.0 * or1 + self.dLkappa)[:, None] * g.D1)
         M[0] = 0.0
         M[0, 0] = 1.0
         M[-1] = 0.0
@@ -407,8 +417,9 @@ class ShellHost:
         self.ds = g.D1 @ self.s
         dds = g.D2 @ self.s
         self.old["s"] = self.s.copy()
-        self.impl["s"] = self.opr * (dds + (self.beta + self.dLtemp0 + 2.0 * g.or1)[:, None] * self.ds -
-                                     self.dL[None, :] * g.or2[:, None] * self.s)
+        self.impl["s"] = self.opr * self.kappa[:, None] * (
+            dds + (self.beta + self.dLtemp0 + 2.0 * g.or1 + self.dLkappa)[:, None] * self.ds -
+            self.dL[None, :] * g.or2[:, None] * self.s)
 
     def _rhs_imp_xi(self):
         """get_comp_rhs_imp, updateXI.f90:579-650."""
@@ -442,8 +453,9 @@ class ShellHost:
             ddz[:, lm] -= rho0 * (2.0 + 4.0 * beta * r + dbeta * r * r + beta * beta * r * r) * corr
         fac = self.dL[None, :] * g.or2[:, None]
         self.old["z"] = fac * self.z
-        imp = fac * (ddz - beta[:, None] * self.dz -
-                     (fac + (dbeta + 2.0 * beta * g.or1)[:, None]) * self.z)
+        dLv = self.dLvisc
+        imp = fac * self.visc[:, None] * (ddz + (dLv - beta)[:, None] * self.dz -
+                                          (fac + (dLv * beta + 2.0 * dLv * g.or1 + dbeta + 2.0 * beta * g.or1)[:, None]) * self.z)
         if self.prec_fac != 0.0:   # updateZ.f90:955-958, evaluated at the time the fields belong to
             imp[:, self._lm(1, 1)] += self.prec_fac * (np.sin(self.oek * self.time) - 1j * np.cos(self.oek * self.time))
         imp[0] = 0.0
@@ -468,12 +480,15 @@ class ShellHost:
         fac = self.dL[None, :] * g.or2[:, None]
         old_w = fac * self.w
         old_p = -fac * self.dw
-        Dif = fac * (self.ddw - beta / 3.0 * self.dw - (fac + 4.0 / 3.0 * (dbeta + beta * or1)) * self.w)
+        visc, dLv = self.visc[:, None], self.dLvisc[:, None]
+        Dif = fac * visc * (self.ddw + (2.0 * dLv - beta / 3.0) * self.dw -
+                            (fac + 4.0 / 3.0 * (dbeta + dLv * beta + (3.0 * dLv + beta) * or1)) * self.w)
         Pre = -self.dp + beta * self.p
         Buo = (self.rho0 * self.rgrav)[:, None] * (self.BuoFac * self.s + self.ChemFac * self.xi)
         imp_w = Pre + Dif + Buo
-        imp_p = fac * self.p + fac * (-dddw + beta * self.ddw + (fac + dbeta + 2.0 * beta * or1) * self.dw -
-                                      fac * (2.0 * or1 + 2.0 / 3.0 * beta) * self.w)
+        imp_p = fac * self.p + fac * visc * (-dddw + (beta - dLv) * self.ddw +
+                                             (fac + dLv * beta + dbeta + 2.0 * (dLv + beta) * or1) * self.dw -
+                                             fac * (2.0 * or1 + 2.0 / 3.0 * beta + dLv) * self.w)
         l0 = self.lm2l == 0
         for a in (old_w, old_p, imp_w, imp_p):
             a[0] = 0.0
@@ -540,7 +555,8 @@ class ShellHost:
         for l in range(self.l_max + 1):
             dL = float(l * (l + 1))
             # sMat (updateS.f90:1086-1140), ktops=kbots=1
-            M = I - wl1 * self.opr * (g.D2 + (beta + self.dLtemp0[:, None] + 2.0 * or1) * g.D1 - dL * or2 * I)
+            M = I - wl1 * self.opr * self.kappa[:, None] * (
+                g.D2 + (beta + self.dLtemp0[:, None] + 2.0 * or1 + self.dLkappa[:, None]) * g.D1 - dL * or2 * I)
             M[0], M[-1] = I[0], I[-1]
             mats["s"].append(M)
             # xiMat (updateXI.f90:924-965), ktopxi = kbotxi = 1
@@ -548,16 +564,21 @@ class ShellHost:
             M[0], M[-1] = I[0], I[-1]
             mats["xi"].append(M)
             # zMat (updateZ.f90:1850-1890)
-            M = dL * or2 * I - wl1 * dL * or2 * (g.D2 - beta * g.D1 - (dL * or2 + dbeta + 2.0 * beta * or1) * I)
+            visc, dLv = self.visc[:, None], self.dLvisc[:, None]
+            M = dL * or2 * I - wl1 * dL * or2 * visc * (
+                g.D2 + (dLv - beta) * g.D1 - (dLv * beta + 2.0 * dLv * or1 + dL * or2 + dbeta + 2.0 * beta * or1) * I)
             M[0] = I[0] if self.ktopv == 2 else g.D1[0] - (2.0 * g.or1[0] + b0) * I[0]
             M[-1] = I[-1] if self.kbotv == 2 else g.D1[-1] - (2.0 * g.or1[-1] + bN) * I[-1]
             mats["z"].append(M)
             # wpMat (updateWP.f90:1999-2090)
             W = np.zeros((2 * N, 2 * N))
-            W[:N, :N] = dL * or2 * I - wl1 * dL * or2 * (g.D2 - beta / 3.0 * g.D1 - (dL * or2 + 4.0 / 3.0 * (beta * or1 + dbeta)) * I)
+            W[:N, :N] = dL * or2 * I - wl1 * dL * or2 * visc * (
+                g.D2 + (2.0 * dLv - beta / 3.0) * g.D1 -
+                (dL * or2 + 4.0 / 3.0 * (dLv * beta + (3.0 * dLv + beta) * or1 + dbeta)) * I)
             W[:N, N:] = wl1 * (g.D1 - beta * I)
-            W[N:, :N] = -dL * or2 * g.D1 - wl1 * dL * or2 * (-g.D3 + beta * g.D2 + (dL * or2 + dbeta + 2.0 * beta * or1) * g.D1 -
-                                                            dL * or2 * (2.0 * or1 + 2.0 / 3.0 * beta) * I)
+            W[N:, :N] = -dL * or2 * g.D1 - wl1 * dL * or2 * visc * (
+                -g.D3 + (beta - dLv) * g.D2 + (dL * or2 + dbeta + dLv * beta + 2.0 * (dLv + beta) * or1) * g.D1 -
+                dL * or2 * (2.0 * or1 + dLv + 2.0 / 3.0 * beta) * I)
             W[N:, N:] = -wl1 * dL * or2 * I
             W[0] = 0.0
             W[0, :N] = I[0]

@@ -37,7 +37,8 @@
  *       referenceMag.out (tests/test_varCond.py);
  *   (9) for chemical convection (xi, dxidt, dVXirLM) and for a loop called three times per step on Runge-Kutta stage states:
  *       the 25 BPR353 steps of samples/doubleDiffusion and of samples/boussBenchSat (saturated dynamo, conducting rotating
- *       inner core) from their shipped checkpoints (tests/test_doubleDiffusion.py, tests/test_boussBenchSat.py).
+ *       inner core) from their shipped checkpoints (tests/test_doubleDiffusion.py, tests/test_boussBenchSat.py);
+ *   (10) for a radially varying viscosity in the viscous heating: the 250 steps of samples/varProps (tests/test_varProps.py).
  * Still "parity unpinned" (no reference vectors reachable here, literal line-cited restatements only): the r = 0 level
  * itself (v_center_sphere: the energies of (5) are insensitive to it, measured) and the inner-core (_IC) and axisymmetric
  * syntheses (diagnostics, not called by the radial loop).

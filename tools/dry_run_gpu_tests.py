@@ -85,6 +85,7 @@ def main(names):
         "precession": ("tests.test_precession", "test_gpu_radial_loop_reproduces_reference_energies"),
         "full_sphere": ("tests.test_full_sphere", "test_gpu_radial_loop_reproduces_reference_energies"),
         "varCond": ("tests.test_varCond", "test_gpu_radial_loop_reproduces_reference_energies"),
+        "varProps": ("tests.test_varProps", "test_gpu_radial_loop_reproduces_reference_energies"),
         "doubleDiffusion": ("tests.test_doubleDiffusion", "test_gpu_radial_loop_reproduces_reference_energies"),
         "boussBenchSat": ("tests.test_boussBenchSat", "test_gpu_radial_loop_reproduces_reference_energies"),
         "condICrotIC": ("tests.test_condICrotIC", "test_gpu_radial_loop_reproduces_reference_energies"),

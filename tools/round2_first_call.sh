@@ -5,7 +5,7 @@
 set -u
 mkdir -p gpurun_out
 export MAGIC_UNVERIFIED_GPU=1
-timeout 900 python -m pytest tests -m gpu -q -k "precession or condICrotIC or varCond or doubleDiffusion or boussBenchSat or full_size" -x --durations=15 > gpurun_out/pytest_unverified.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -k "precession or condICrotIC or varCond or varProps or doubleDiffusion or boussBenchSat or full_size" -x --durations=15 > gpurun_out/pytest_unverified.log 2>&1
 echo "unverified rc=$?" | tee -a gpurun_out/pytest_unverified.log
 tail -25 gpurun_out/pytest_unverified.log
 unset MAGIC_UNVERIFIED_GPU
