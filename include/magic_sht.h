@@ -146,6 +146,11 @@ long long magic_rloop_launch_count(const magic_rloop *rl);
 int magic_rloop_last_timing(const magic_rloop *rl, double out[8]);
 /* Algorithmic FP64 flops of the Legendre stage of one run (U * 2*n_theta*lm_max per level). */
 double magic_rloop_legendre_flops(const magic_rloop *rl);
+/* Scalar-equivalent Legendre passes per bulk level: out[0] = the reference's count (native_qst_to_spat / native_spat_to_sph_tor
+ * sum against Plm AND dPlm: 5 per q/s/t transform, 36 for the MHD set), out[1] = the passes this library
+ * executes (dPlm is a 3-point combination of Plm, plms.f90:117-187, so a vector component is ONE pass against Plm: 3 per
+ * q/s/t transform, 22 for the MHD set). */
+int magic_rloop_legendre_units(const magic_rloop *rl, double out[2]);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* r <-> LM redistribution: a 5th type_mpitransp (mpi_transpose.f90:18-54), alltoallv semantics of   */

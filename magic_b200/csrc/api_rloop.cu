@@ -51,6 +51,7 @@ struct magic_rloop {
     cudaEvent_t ev[16];
     double timing[8] = {0};
     double legendre_flops = 0;
+    double units_ref = 0, units_exec = 0;  // scalar-equivalent Legendre passes per bulk level: reference count / executed here
     std::vector<const void *> registered, seen;
     // host-pointer path: uploads / downloads of level chunks overlap the compute of neighbouring chunks
     cudaStream_t s_up = nullptr, s_down = nullptr;
@@ -247,6 +248,8 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
     if (P.l_mag_nl) add_qst(go.VxBr, go.VxBt, go.VxBp, rl->a_VxBr, rl->a_VxB);
     S.nfield_out = no;
     rl->legendre_flops = (units_syn + units_an) * 2.0 * (double)h->n_theta * (double)h->lm_max * (double)n_r_loc;
+    rl->units_ref = units_syn + units_an;
+    rl->units_exec = (double)(S.scal.size() + 2 * S.vec.size() + S.afield_s.size() + 2 * S.afield_vt.size());
 
     // ---- outputs needed
     if (P.l_conv) { rl->need_out[O_DZDT] = rl->need_out[O_DWDT] = true; if (P.l_double_curl) rl->need_out[O_DVXVH] = true; }
@@ -261,13 +264,14 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
         cudaMemGetInfo(&free_b, &total_b);
         Layout probe;
         layout_sizes(h, S, 1, probe);
-        double per_level = 8.0 * ((double)probe.szBs + probe.szBv + probe.szFs + probe.szFv + probe.szBas + probe.szBav + probe.szCas + probe.szCav) +
+        double per_level = 8.0 * ((double)probe.szB + probe.szF + probe.szBa + probe.szCa) +
                            8.0 * 2.0 * h->nh * h->n_phi * (S.nfield_in + S.nfield_out);
         level_chunk = (int)std::max(1.0, std::min((double)n_r_loc, 0.6 * (double)free_b / per_level));
         // measured at l_max=1023 (GEMM ms per level): 16-level chunks 1.65, 32-level chunks 1.78, 64-level chunks > 2.0 --
         // so 16 levels whenever that still gives the synthesis GEMM >= 20 waves of tiles, else 32 (small truncations are
         // launch-bound and want the wider batch)
-        const long long tiles16 = (long long)h->n_m * 2 * ((h->nh + GEMM_BM - 1) / GEMM_BM) * ((4LL * std::max(1, (int)S.vec.size()) * 16 + GEMM_BN - 1) / GEMM_BN);
+        const long long tiles16 = (long long)h->n_m * 2 * ((h->nh + GEMM_BM - 1) / GEMM_BM) *
+                                  ((2LL * std::max(1, (int)(S.scal.size() + 2 * S.vec.size())) * 16 + GEMM_BN - 1) / GEMM_BN);
         level_chunk = std::min(level_chunk, tiles16 >= 20LL * 2 * 148 ? 16 : 32);
     }
     level_chunk = std::min(level_chunk, n_r_loc);
@@ -408,11 +412,9 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
         t.dwdt = o(O_DWDT); t.dzdt = o(O_DZDT); t.dpdt = o(O_DPDT); t.dsdt = o(O_DSDT); t.dxidt = o(O_DXIDT); t.dbdt = o(O_DBDT);
         t.djdt = o(O_DJDT); t.dVxVhLM = o(O_DVXVH); t.dVxBhLM = o(O_DVXBH); t.dVSrLM = o(O_DVSR); t.dVXirLM = o(O_DVXIR);
         {
-            ExtractArgs e{};
-            e.Cs = rl->buf.Cas; e.Cv = rl->buf.Cav; e.offCs = L.d_offCas; e.offCv = L.d_offCav; e.Ns = L.Nas; e.Nv = L.Nav;
-            e.n_lev = nl; e.lm_max = h->lm_max; e.nf_s = L.nf_s; e.nf_v = 2 * L.npair_a; e.lm2l = h->d_lm2l; e.lm2m = h->d_lm2m;
-            e.minc = h->minc; e.lev = d_lev; e.out_s = nullptr; e.out_v = nullptr;
-            const int nf = e.nf_s + e.nf_v;
+            ExtractArgs e = make_extract_args(h, L, rl->buf, d_lev);
+            e.out_s = nullptr; e.out_v = nullptr;
+            const int nf = e.nf_s + 2 * e.npair;
             // widest tile whose shared-memory footprint still lets several CTAs share an SM
             auto smem = [&](int tl) { return (size_t)nf * nl * (tl + 1) * sizeof(double2); };
             if (smem(32) <= 80 * 1024) extract_td_kernel<32><<<(h->lm_max + 31) / 32, 256, smem(32), h->stream>>>(e, t, sl);
@@ -719,3 +721,9 @@ extern "C" int magic_rloop_last_timing(const magic_rloop *rl, double out[8]) {
     return 0;
 }
 extern "C" double magic_rloop_legendre_flops(const magic_rloop *rl) { return rl ? rl->legendre_flops : 0.0; }
+extern "C" int magic_rloop_legendre_units(const magic_rloop *rl, double out[2]) {
+    if (!rl || !out) MFAIL("magic_rloop_legendre_units: null argument");
+    out[0] = rl->units_ref;
+    out[1] = rl->units_exec;
+    return 0;
+}

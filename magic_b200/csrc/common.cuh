@@ -1,9 +1,12 @@
 // common.cuh -- shared structures of magic_b200 (device + host).  Layouts are described in DESIGN.md.
 //
-//   table   per order mc four row blocks [P_even][D_odd][P_odd][D_even]; one row per degree l, NHP doubles
-//           per row (northern colatitudes k=0..nh-1, zero padded to a multiple of 16).  P = Plm,
-//           D = dPlm = sin(theta) dP/dtheta of shtransforms.f90:38-91 / plms.f90:14-189.
-//   B       Legendre-GEMM right operand, [K_pad][N] row-major per problem, N a multiple of 64,
+//   table   per order mc two row blocks [P_even][P_odd]; one row per degree l = m .. l_max+1, NHP doubles
+//           per row (northern colatitudes k=0..nh-1, zero padded to a multiple of 16).  P = Plm of
+//           shtransforms.f90:38-91 / plms.f90:14-189.  The reference's dPlm = sin(theta) dP/dtheta is by construction
+//           l c(l+1) P(l+1) - (l+1) c(l) P(l-1) (plms.f90:117-187), so every sum against dPlm is a sum against P with
+//           3-point-combined coefficients: the vector transforms need no D table and cost 2 (synthesis) or 2 (analysis)
+//           scalar-equivalent passes instead of 4.
+//   B       Legendre-GEMM right operand, [K_pad][N] row-major per problem (mc, parity), N a multiple of 64,
 //           column n = (col*n_lev + lev)*2 + reim.
 //   F       (theta,m)-space, per problem (mc, s) a [nh][N] matrix with the same columns as B.
 //   grid    g[field][lev][s][k][phi]: phi fastest; s=0 holds the equatorially symmetric part E, s=1 the
@@ -57,15 +60,10 @@ struct FftPlan {
     const double2 *tw;  // device: exp(+2 pi i k/N), k=0..N-1
 };
 
-// r2c destination: the FFT of a grid row (field,lev,s,k) is scaled and written into an analysis operand
-enum RType : int { R_NONE = 0, R_W = 1, R_WS = 2, R_NEG_WS = 3, R_MIM_WS = 4 };
-struct R2cDest {
-    int cls;    // 0 scalar-class operand, 1 vector-class operand
-    int col;    // complex column index (before *n_lev)
-    int p;      // parity problem receiving the row
-    int seg;    // 0: P segment rows [0,NHP), 1: D segment rows [NHP,2NHP)
-    int rtype;  // RType
-};
-struct R2cField { R2cDest d[2][2]; };  // [s][dest]
+// r2c destination: the FFT of a grid row (field,lev,s,k) is scaled by the quadrature weight (R_W) or by weight / sin^2 theta
+// (R_WS, vector components: shtransforms.f90:787-794) and written into row k, column `col` of the analysis operand of the
+// parity problem s (the symmetric part E = N+S meets the even-parity P rows, O = N-S the odd ones).
+enum RType : int { R_NONE = 0, R_W = 1, R_WS = 2 };
+struct R2cField { int col; int rtype; };
 
 }  // namespace magic

@@ -51,27 +51,29 @@ int sht_init(magic_sht *h) {
     MCHECK(cudaSetDevice(h->dev));
     MCHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     // st_map (blocking.f90:309-317)
-    h->lm2l.clear(); h->lm2m.clear(); h->lstart.assign(n_m, 0); h->ne.assign(n_m, 0); h->no.assign(n_m, 0);
+    h->lm2l.clear(); h->lm2m.clear(); h->lstart.assign(n_m, 0); h->ne1.assign(n_m, 0); h->no1.assign(n_m, 0);
+    std::vector<double> clm;  // c(l), l = m .. l_max+2 per order (the dTheta coefficients of plms.f90:117-187 / horizontal.f90:202-229)
     for (int mc = 0; mc < n_m; mc++) {
         int m = mc * minc;
         h->lstart[mc] = (int)h->lm2l.size();
         for (int l = m; l <= l_max; l++) { h->lm2l.push_back(l); h->lm2m.push_back(m); }
-        h->ne[mc] = (l_max - m) / 2 + 1;
-        h->no[mc] = (l_max - m + 1) / 2;
+        h->ne1[mc] = (l_max + 1 - m) / 2 + 1;  // degrees m, m+2, ... <= l_max+1
+        h->no1[mc] = (l_max + 1 - m + 1) / 2;  // degrees m+1, m+3, ... <= l_max+1
+        for (int l = m; l <= l_max + 2; l++) clm.push_back(sqrt((double)((l + m) * (l - m)) / (double)((2 * l - 1) * (2 * l + 1))));
     }
     if ((int)h->lm2l.size() != h->lm_max) MFAIL("internal: lm_max mismatch");
     gauleg_host(h->n_theta, h->theta_ord, h->gauss);
     // table block offsets
-    h->off.assign((size_t)n_m * 4, 0);
+    h->off.assign((size_t)n_m * 2, 0);
     long long pos = 0;
     for (int mc = 0; mc < n_m; mc++) {
-        int rows[4] = {h->ne[mc], h->no[mc], h->no[mc], h->ne[mc]};
-        for (int b = 0; b < 4; b++) { h->off[(size_t)mc * 4 + b] = pos; pos += (long long)rows[b] * h->NHP; }
+        int rows[2] = {h->ne1[mc], h->no1[mc]};
+        for (int b = 0; b < 2; b++) { h->off[(size_t)mc * 2 + b] = pos; pos += (long long)rows[b] * h->NHP; }
     }
     long long tab_doubles = pos + (long long)(GEMM_BM + 2 * BK) * std::max(h->NHP, GEMM_BM) + 1024;
     MCHECK(cudaMalloc((void **)&h->d_tab, sizeof(double) * tab_doubles));
     MCHECK(cudaMemsetAsync(h->d_tab, 0, sizeof(double) * tab_doubles, h->stream));
-    if (dev_upload_vec(&h->d_off, h->off)) return 1;
+    if (dev_upload_vec(&h->d_off, h->off) || dev_upload_vec(&h->d_clm, clm)) return 1;
     std::vector<double> sinth(nh), costh(nh), wg(nh), os2(nh), pmm(n_m);
     const double pi = 3.14159265358979323846264338327950288;
     for (int k = 0; k < nh; k++) {
@@ -112,12 +114,12 @@ int sht_init(magic_sht *h) {
         const char *fr = getenv("MAGIC_POLAR_FRAG");
         if (!fr || atoi(fr) != 0) {
             h->FS = ((h->NHP / 8 + 15) / 16) * 16 + 16;
-            h->FA = (((l_max / 2 + 1 + 7) / 8 + 15) / 16) * 16 + 16;
+            h->FA = ((((l_max + 1) / 2 + 1 + 7) / 8 + 15) / 16) * 16 + 16;
             int *d_ne = nullptr, *d_no = nullptr;
-            if (dev_upload_vec(&d_ne, h->ne) || dev_upload_vec(&d_no, h->no)) return 1;
-            MCHECK(cudaMalloc((void **)&h->d_fskip_syn, (size_t)n_m * 4 * h->FS));
-            MCHECK(cudaMalloc((void **)&h->d_fskip_an, (size_t)n_m * 4 * h->FA));
-            table_fskip_kernel<<<dim3(n_m, 4), 128, 0, h->stream>>>(h->d_tab, h->d_off, d_ne, d_no, nh, h->NHP, h->polar_eps, h->FS, h->FA,
+            if (dev_upload_vec(&d_ne, h->ne1) || dev_upload_vec(&d_no, h->no1)) return 1;
+            MCHECK(cudaMalloc((void **)&h->d_fskip_syn, (size_t)n_m * 2 * h->FS));
+            MCHECK(cudaMalloc((void **)&h->d_fskip_an, (size_t)n_m * 2 * h->FA));
+            table_fskip_kernel<<<dim3(n_m, 2), 128, 0, h->stream>>>(h->d_tab, h->d_off, d_ne, d_no, nh, h->NHP, h->polar_eps, h->FS, h->FA,
                                                                     h->d_fskip_syn, h->d_fskip_an);
             MCHECK(cudaGetLastError());
             MCHECK(cudaStreamSynchronize(h->stream));
@@ -149,7 +151,7 @@ int sht_init(magic_sht *h) {
 
 void sht_free(magic_sht *h) {
     cudaFree(h->d_fskip_syn); cudaFree(h->d_fskip_an);
-    cudaFree(h->d_tab); cudaFree(h->d_off); cudaFree(h->d_sinth); cudaFree(h->d_costh); cudaFree(h->d_wgauss);
+    cudaFree(h->d_tab); cudaFree(h->d_off); cudaFree(h->d_clm); cudaFree(h->d_sinth); cudaFree(h->d_costh); cudaFree(h->d_wgauss);
     cudaFree(h->d_osin2); cudaFree(h->d_lm2l); cudaFree(h->d_lm2m); cudaFree(h->d_lstart); cudaFree(h->d_tw);
     if (h->stream) cudaStreamDestroy(h->stream);
 }
@@ -160,37 +162,33 @@ void layout_sizes(const magic_sht *h, const BatchSpec &spec, int n_lev, Layout &
     L.n_lev = n_lev;
     L.ncol_s = (int)spec.scal.size();
     L.npair_v = (int)spec.vec.size();
-    L.Ns = L.ncol_s ? pad_up(2 * L.ncol_s * n_lev, GEMM_BN) : 0;
-    L.Nv = L.npair_v ? pad_up(4 * L.npair_v * n_lev, GEMM_BN) : 0;
+    L.ncol = L.ncol_s + 2 * L.npair_v;
+    L.N = L.ncol ? pad_up(2 * L.ncol * n_lev, GEMM_BN) : 0;
     L.nf_s = (int)spec.afield_s.size();
     L.npair_a = (int)spec.afield_vt.size();
-    L.Nas = L.nf_s ? pad_up(2 * L.nf_s * n_lev, GEMM_BN) : 0;
-    L.Nav = L.npair_a ? pad_up(4 * L.npair_a * n_lev, GEMM_BN) : 0;
-    L.offBs.assign((size_t)n_m * 2, 0); L.offBv.assign((size_t)n_m * 2, 0);
-    L.offCas.assign((size_t)n_m * 2, 0); L.offCav.assign((size_t)n_m * 2, 0);
-    long long pbs = 0, pbv = 0, pcs = 0, pcv = 0;
+    L.nfa = L.nf_s + 2 * L.npair_a;
+    L.Na = L.nfa ? pad_up(2 * L.nfa * n_lev, GEMM_BN) : 0;
+    L.offB.assign((size_t)n_m * 2, 0);
+    L.offC.assign((size_t)n_m * 2, 0);
+    long long pb = 0, pc = 0;
     for (int mc = 0; mc < n_m; mc++)
         for (int s = 0; s < 2; s++) {
-            int prob = mc * 2 + s;
-            int Ks = s == 0 ? h->ne[mc] : h->no[mc], Ko = s == 0 ? h->no[mc] : h->ne[mc];
-            int kts = (Ks + BK - 1) / BK, kto = (Ko + BK - 1) / BK;
-            L.offBs[prob] = pbs; pbs += (long long)kts * BK * L.Ns;
-            L.offBv[prob] = pbv; pbv += (long long)(kts + kto) * BK * L.Nv;
-            L.offCas[prob] = pcs; pcs += (long long)Ks * L.Nas;
-            L.offCav[prob] = pcv; pcv += (long long)Ks * L.Nav;
+            const int prob = mc * 2 + s, K = s == 0 ? h->ne1[mc] : h->no1[mc], kt = (K + BK - 1) / BK;
+            L.offB[prob] = pb; pb += (long long)kt * BK * L.N;
+            L.offC[prob] = pc; pc += (long long)K * L.Na;
         }
-    L.szBs = pbs; L.szBv = pbv;
-    L.szFs = (long long)n_m * 2 * nh * L.Ns; L.szFv = (long long)n_m * 2 * nh * L.Nv;
-    L.szBas = (long long)n_m * 2 * NHP * L.Nas; L.szBav = (long long)n_m * 2 * 2 * NHP * L.Nav;
-    L.szCas = pcs + (long long)GEMM_BM * L.Nas; L.szCav = pcv + (long long)GEMM_BM * L.Nav;
+    L.szB = pb;
+    L.szF = (long long)n_m * 2 * nh * L.N;
+    L.szBa = (long long)n_m * 2 * NHP * L.Na;
+    L.szCa = pc + (long long)GEMM_BM * L.Na;
 }
 
 int buffers_alloc(magic_sht *h, const BatchSpec &spec, const Layout &L, Buffers &b) {
     size_t plane = (size_t)2 * h->nh * h->n_phi;
     struct { double **p; long long n; } items[] = {
-        {&b.Bs, L.szBs}, {&b.Bv, L.szBv}, {&b.Fs, L.szFs}, {&b.Fv, L.szFv},
+        {&b.B, L.szB}, {&b.F, L.szF},
         {&b.gin, (long long)(plane * spec.nfield_in * L.n_lev)}, {&b.gout, (long long)(plane * spec.nfield_out * L.n_lev)},
-        {&b.Bas, L.szBas}, {&b.Bav, L.szBav}, {&b.Cas, L.szCas}, {&b.Cav, L.szCav},
+        {&b.Ba, L.szBa}, {&b.Ca, L.szCa},
         {&b.nl_s, (long long)2 * L.nf_s * L.n_lev * h->lm_max}, {&b.nl_v, (long long)4 * L.npair_a * L.n_lev * h->lm_max}};
     b.bytes = 0;
     for (auto &it : items) {
@@ -205,16 +203,16 @@ int buffers_alloc(magic_sht *h, const BatchSpec &spec, const Layout &L, Buffers 
 }
 
 void buffers_free(Buffers &b) {
-    double *ps[] = {b.Bs, b.Bv, b.Fs, b.Fv, b.gin, b.gout, b.Bas, b.Bav, b.Cas, b.Cav, b.nl_s, b.nl_v};
+    double *ps[] = {b.B, b.F, b.gin, b.gout, b.Ba, b.Ca, b.nl_s, b.nl_v};
     for (double *p : ps) cudaFree(p);
     cudaFree(b.courmax);
     b = Buffers();
 }
 
 void layout_free(Layout &L) {
-    cudaFree(L.d_offBs); cudaFree(L.d_offBv); cudaFree(L.d_offCas); cudaFree(L.d_offCav); cudaFree(L.d_prep_blks);
+    cudaFree(L.d_offB); cudaFree(L.d_offC); cudaFree(L.d_prep_blks);
     cudaFree(L.d_probs_syn); cudaFree(L.d_probs_an); cudaFree(L.d_tiles_syn); cudaFree(L.d_tiles_an);
-    cudaFree(L.d_colrow_s); cudaFree(L.d_colrow_v); cudaFree(L.d_scal); cudaFree(L.d_vec); cudaFree(L.d_r2c);
+    cudaFree(L.d_colrow); cudaFree(L.d_scal); cudaFree(L.d_vec); cudaFree(L.d_r2c);
     L = Layout();
 }
 
@@ -225,116 +223,66 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
     std::vector<int2> ts, ta;
     const int mt_syn = (nh + GEMM_BM - 1) / GEMM_BM;
     for (int mc = 0; mc < n_m; mc++) {
-        const double *Pe = h->d_tab + h->off[(size_t)mc * 4 + 0], *Do = h->d_tab + h->off[(size_t)mc * 4 + 1];
-        const double *Po = h->d_tab + h->off[(size_t)mc * 4 + 2], *De = h->d_tab + h->off[(size_t)mc * 4 + 3];
-        // ---- synthesis problems: vector class first (largest K), then scalar class
-        for (int cls = 1; cls >= 0; cls--) {
-            if ((cls == 1 && !L.npair_v) || (cls == 0 && !L.ncol_s)) continue;
-            for (int s = 0; s < 2; s++) {
-                int prob = mc * 2 + s;
-                int Ks = s == 0 ? h->ne[mc] : h->no[mc], Ko = s == 0 ? h->no[mc] : h->ne[mc];
-                int kt0 = (Ks + BK - 1) / BK, kt1 = (Ko + BK - 1) / BK;
+        for (int s = 0; s < 2; s++) {
+            const int prob = mc * 2 + s, K = s == 0 ? h->ne1[mc] : h->no1[mc], kt = (K + BK - 1) / BK;
+            const double *P = h->d_tab + h->off[(size_t)mc * 2 + s];
+            if (L.ncol) {  // ---- synthesis: F[theta_k, n] = sum_l P(l, theta_k) B[l, n]
                 GemmProb g{};
-                g.A0 = s == 0 ? Pe : Po;
+                g.A0 = g.A1 = P;
+                g.kt0 = kt; g.kt1 = 0;
                 g.M = nh;
                 g.Mlo = (h->kmin[mc] / 8) * 8;
-                if (h->d_fskip_syn) {  // table blocks: 0 P_even, 1 D_odd, 2 P_odd, 3 D_even
-                    g.ks0 = h->d_fskip_syn + ((size_t)mc * 4 + (s == 0 ? 0 : 2)) * h->FS;
-                    g.ks1 = cls == 1 ? h->d_fskip_syn + ((size_t)mc * 4 + (s == 0 ? 1 : 3)) * h->FS : nullptr;
-                }
-                if (cls == 1) {
-                    g.A1 = s == 0 ? Do : De;
-                    g.kt0 = kt0; g.kt1 = kt1;
-                    g.B = buf.Bv + L.offBv[prob];
-                    g.C = buf.Fv + (size_t)prob * nh * L.Nv;
-                    g.ldb = g.ldc = L.Nv;
-                    g.Nvalid = 4 * L.npair_v * n_lev;
-                } else {
-                    g.A1 = g.A0;
-                    g.kt0 = kt0; g.kt1 = 0;
-                    g.B = buf.Bs + L.offBs[prob];
-                    g.C = buf.Fs + (size_t)prob * nh * L.Ns;
-                    g.ldb = g.ldc = L.Ns;
-                    g.Nvalid = 2 * L.ncol_s * n_lev;
-                }
-                int pid = (int)ps.size();
+                if (h->d_fskip_syn) g.ks0 = h->d_fskip_syn + ((size_t)mc * 2 + s) * h->FS;
+                g.B = buf.B + L.offB[prob];
+                g.C = buf.F + (size_t)prob * nh * L.N;
+                g.ldb = g.ldc = L.N;
+                g.Nvalid = 2 * L.ncol * n_lev;
+                const int pid = (int)ps.size();
                 ps.push_back(g);
-                int ntn = g.ldb / GEMM_BN;
                 for (int mt = 0; mt < mt_syn; mt++)  // tiles entirely below Mlo only store zeros (kernel early-out)
-                    for (int nt = 0; nt < ntn; nt++) ts.push_back(make_int2(pid, (mt << 16) | nt));
-                L.flops_syn += 2.0 * nh * (double)(g.kt0 + g.kt1) * BK * g.ldb;
+                    for (int nt = 0; nt < L.N / GEMM_BN; nt++) ts.push_back(make_int2(pid, (mt << 16) | nt));
+                L.flops_syn += 2.0 * nh * (double)kt * BK * L.N;
             }
-        }
-        // ---- analysis problems
-        for (int cls = 1; cls >= 0; cls--) {
-            if ((cls == 1 && !L.npair_a) || (cls == 0 && !L.nf_s)) continue;
-            for (int p = 0; p < 2; p++) {
-                int prob = mc * 2 + p;
-                int Kp = p == 0 ? h->ne[mc] : h->no[mc];
-                if (Kp == 0) continue;
+            if (L.nfa) {   // ---- analysis: C[l, n] = sum_k P(l, theta_k) Ba[k, n]
                 GemmProb g{};
-                g.A0 = p == 0 ? Pe : Po;
-                g.A1 = p == 0 ? De : Do;
-                g.M = Kp;
+                g.A0 = g.A1 = P;
+                g.M = K;
                 g.klo = h->kmin[mc] / BK;
-                g.kt0 = NHP / BK;  // absolute k-tile counts; the kernel starts each segment at max(klo, fragment minimum)
-                if (h->d_fskip_an) {
-                    g.ks0 = h->d_fskip_an + ((size_t)mc * 4 + (p == 0 ? 0 : 2)) * h->FA;
-                    g.ks1 = cls == 1 ? h->d_fskip_an + ((size_t)mc * 4 + (p == 0 ? 3 : 1)) * h->FA : nullptr;
-                }
-                if (cls == 1) {
-                    g.kt1 = NHP / BK;
-                    g.B = buf.Bav + (size_t)prob * 2 * NHP * L.Nav;
-                    g.C = buf.Cav + L.offCav[prob];
-                    g.ldb = g.ldc = L.Nav;
-                    g.Nvalid = 4 * L.npair_a * n_lev;
-                } else {
-                    g.kt1 = 0;
-                    g.B = buf.Bas + (size_t)prob * NHP * L.Nas;
-                    g.C = buf.Cas + L.offCas[prob];
-                    g.ldb = g.ldc = L.Nas;
-                    g.Nvalid = 2 * L.nf_s * n_lev;
-                }
-                int pid = (int)pa.size();
+                g.kt0 = NHP / BK;  // absolute k-tile count; the kernel starts at max(klo, fragment minimum)
+                g.kt1 = 0;
+                if (h->d_fskip_an) g.ks0 = h->d_fskip_an + ((size_t)mc * 2 + s) * h->FA;
+                g.B = buf.Ba + (size_t)prob * NHP * L.Na;
+                g.C = buf.Ca + L.offC[prob];
+                g.ldb = g.ldc = L.Na;
+                g.Nvalid = 2 * L.nfa * n_lev;
+                const int pid = (int)pa.size();
                 pa.push_back(g);
-                int ntn = g.ldb / GEMM_BN, ntm = (Kp + GEMM_BM - 1) / GEMM_BM;
-                for (int mt = 0; mt < ntm; mt++)
-                    for (int nt = 0; nt < ntn; nt++) ta.push_back(make_int2(pid, (mt << 16) | nt));
-                L.flops_an += 2.0 * Kp * (double)(g.kt0 + g.kt1 - (g.kt1 ? 2 : 1) * g.klo) * BK * g.ldb;
+                for (int mt = 0; mt < (K + GEMM_BM - 1) / GEMM_BM; mt++)
+                    for (int nt = 0; nt < L.Na / GEMM_BN; nt++) ta.push_back(make_int2(pid, (mt << 16) | nt));
+                L.flops_an += 2.0 * K * (double)(g.kt0 - g.klo) * BK * L.Na;
             }
         }
     }
-    for (int mc = 0; mc < n_m; mc++)
-        for (int jt = 0; jt < (h->l_max - mc * h->minc + 1 + 31) / 32; jt++) blks.push_back(make_int2(mc, jt));
+    for (int mc = 0; mc < n_m; mc++)  // operand assembly: blocks of 32 degrees m .. l_max+1
+        for (int jt = 0; jt < (h->l_max + 1 - mc * h->minc + 1 + 31) / 32; jt++) blks.push_back(make_int2(mc, jt));
     L.n_prep_blks = (int)blks.size();
     L.ntiles_syn = (int)ts.size(); L.ntiles_an = (int)ta.size();
-    std::vector<int> crs((size_t)L.ncol_s * n_lev), crv((size_t)2 * L.npair_v * n_lev);
-    for (int c = 0; c < L.ncol_s; c++)
-        for (int lev = 0; lev < n_lev; lev++) crs[(size_t)c * n_lev + lev] = spec.field_s[c] < 0 ? -1 : spec.field_s[c] * n_lev + lev;
-    for (int c = 0; c < 2 * L.npair_v; c++)
-        for (int lev = 0; lev < n_lev; lev++) crv[(size_t)c * n_lev + lev] = spec.field_v[c] < 0 ? -1 : spec.field_v[c] * n_lev + lev;
-    std::vector<R2cField> r2c(std::max(spec.nfield_out, 1));
-    for (auto &f : r2c)
-        for (int s = 0; s < 2; s++)
-            for (int d = 0; d < 2; d++) f.d[s][d] = R2cDest{0, 0, 0, 0, R_NONE};
-    for (int i = 0; i < L.nf_s; i++)
-        for (int s = 0; s < 2; s++) r2c[spec.afield_s[i]].d[s][0] = R2cDest{0, i, s, 0, R_W};
-    for (int i = 0; i < L.npair_a; i++) {
-        int ft = spec.afield_vt[i], fp = spec.afield_vp[i];
-        // SURVEY.md appendix A / shtransforms.f90:821-860: A=fft(vp)/sin^2, B=fft(vt)/sin^2
-        r2c[ft].d[0][0] = R2cDest{1, 2 * i, 1, 1, R_WS};          // B+ -> odd  S, D segment
-        r2c[ft].d[0][1] = R2cDest{1, 2 * i + 1, 0, 0, R_MIM_WS};  // B+ -> even T, P segment
-        r2c[ft].d[1][0] = R2cDest{1, 2 * i, 0, 1, R_WS};          // B- -> even S, D segment
-        r2c[ft].d[1][1] = R2cDest{1, 2 * i + 1, 1, 0, R_MIM_WS};  // B- -> odd  T, P segment
-        r2c[fp].d[0][0] = R2cDest{1, 2 * i, 0, 0, R_MIM_WS};      // A+ -> even S, P segment
-        r2c[fp].d[0][1] = R2cDest{1, 2 * i + 1, 1, 1, R_NEG_WS};  // A+ -> odd  T, D segment
-        r2c[fp].d[1][0] = R2cDest{1, 2 * i, 1, 0, R_MIM_WS};      // A- -> odd  S, P segment
-        r2c[fp].d[1][1] = R2cDest{1, 2 * i + 1, 0, 1, R_NEG_WS};  // A- -> even T, D segment
+    // grid field written by every synthesis column (scalar columns first, then the theta / phi columns of every pair)
+    std::vector<int> cr((size_t)std::max(L.ncol, 1) * n_lev, -1);
+    for (int c = 0; c < L.ncol; c++) {
+        const int fld = c < L.ncol_s ? spec.field_s[c] : spec.field_v[c - L.ncol_s];
+        for (int lev = 0; lev < n_lev; lev++) cr[(size_t)c * n_lev + lev] = fld < 0 ? -1 : fld * n_lev + lev;
     }
-    if (dev_upload_vec(&L.d_offBs, L.offBs) || dev_upload_vec(&L.d_offBv, L.offBv) || dev_upload_vec(&L.d_offCas, L.offCas) ||
-        dev_upload_vec(&L.d_offCav, L.offCav) || dev_upload_vec(&L.d_prep_blks, blks) ||
+    // analysis column of every product field: scalar fields first, then (theta-type = B, phi-type = A) of every pair
+    std::vector<R2cField> r2c(std::max(spec.nfield_out, 1), R2cField{0, R_NONE});
+    for (int i = 0; i < L.nf_s; i++) r2c[spec.afield_s[i]] = R2cField{i, R_W};
+    for (int i = 0; i < L.npair_a; i++) {
+        r2c[spec.afield_vt[i]] = R2cField{L.nf_s + 2 * i, R_WS};
+        r2c[spec.afield_vp[i]] = R2cField{L.nf_s + 2 * i + 1, R_WS};
+    }
+    if (dev_upload_vec(&L.d_offB, L.offB) || dev_upload_vec(&L.d_offC, L.offC) || dev_upload_vec(&L.d_prep_blks, blks) ||
         dev_upload_vec(&L.d_probs_syn, ps) || dev_upload_vec(&L.d_probs_an, pa) || dev_upload_vec(&L.d_tiles_syn, ts) ||
-        dev_upload_vec(&L.d_tiles_an, ta) || dev_upload_vec(&L.d_colrow_s, crs) || dev_upload_vec(&L.d_colrow_v, crv) ||
+        dev_upload_vec(&L.d_tiles_an, ta) || dev_upload_vec(&L.d_colrow, cr) ||
         dev_upload_vec(&L.d_scal, spec.scal) || dev_upload_vec(&L.d_vec, spec.vec) || dev_upload_vec(&L.d_r2c, r2c))
         return 1;
     return 0;
@@ -353,13 +301,13 @@ int run_synthesis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Bu
     for (int i = 0; i < MAGIC_MAX_SRC; i++) a.src[i] = src[i];
     a.scal = L.d_scal; a.vec = L.d_vec;
     a.ncol_s = L.ncol_s; a.npair_v = L.npair_v; a.n_lev = L.n_lev; a.lm_max = h->lm_max;
-    a.Ns = L.Ns; a.Nv = L.Nv; a.lev = d_lev; a.lstart = h->d_lstart; a.l_max = h->l_max; a.minc = h->minc;
-    a.Bs = buf.Bs; a.Bv = buf.Bv; a.offBs = L.d_offBs; a.offBv = L.d_offBv; a.blks = L.d_prep_blks;
+    a.N = L.N; a.lev = d_lev; a.lstart = h->d_lstart; a.clm = h->d_clm; a.l_max = h->l_max; a.minc = h->minc;
+    a.B = buf.B; a.offB = L.d_offB; a.blks = L.d_prep_blks;
     a.nsrc = 0;
     for (int i = 0; i < MAGIC_MAX_SRC; i++)
         if (src[i]) a.nsrc = i + 1;
     if (ev) cudaEventRecord(ev[0], h->stream);
-    if ((L.ncol_s || L.npair_v) && L.n_prep_blks) {
+    if (L.ncol && L.n_prep_blks) {
         size_t smem = (size_t)PREP_WARPS * a.nsrc * PREP_LD * sizeof(double2);
         dim3 grid(L.n_prep_blks, (L.n_lev + PREP_WARPS - 1) / PREP_WARPS);
         synth_prep_kernel<<<grid, PREP_WARPS * 32, smem, h->stream>>>(a);
@@ -369,17 +317,24 @@ int run_synthesis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Bu
     launch_legendre_gemm(false, L.d_probs_syn, L.d_tiles_syn, L.ntiles_syn, h->NHP, h->stream);
     h->launches++;
     if (ev) cudaEventRecord(ev[2], h->stream);
-    if (L.ncol_s) {
-        launch_fft_c2r(h->fft, buf.Fs, L.Ns, h->n_m, h->nh, L.ncol_s * L.n_lev, L.d_colrow_s, buf.gin, h->stream);
-        h->launches++;
-    }
-    if (L.npair_v) {
-        launch_fft_c2r(h->fft, buf.Fv, L.Nv, h->n_m, h->nh, 2 * L.npair_v * L.n_lev, L.d_colrow_v, buf.gin, h->stream);
+    if (L.ncol) {
+        launch_fft_c2r(h->fft, buf.F, L.N, h->n_m, h->nh, L.ncol * L.n_lev, L.d_colrow, buf.gin, h->stream);
         h->launches++;
     }
     if (ev) cudaEventRecord(ev[3], h->stream);
     MCHECK(cudaGetLastError());
     return 0;
+}
+
+static ExtractArgs extract_args(const magic_sht *h, const Layout &L, const Buffers &buf, const LevelInfo *d_lev) {
+    ExtractArgs e{};
+    e.C = buf.Ca; e.offC = L.d_offC; e.N = L.Na; e.n_lev = L.n_lev; e.lm_max = h->lm_max; e.nf_s = L.nf_s; e.npair = L.npair_a;
+    e.lm2l = h->d_lm2l; e.lm2m = h->d_lm2m; e.lstart = h->d_lstart; e.clm = h->d_clm; e.minc = h->minc; e.lev = d_lev;
+    e.out_s = buf.nl_s; e.out_v = buf.nl_v;
+    return e;
+}
+ExtractArgs make_extract_args(const magic_sht *h, const Layout &L, const Buffers &buf, const LevelInfo *d_lev) {
+    return extract_args(h, L, buf, d_lev);
 }
 
 int run_analysis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buffers &buf, const LevelInfo *d_lev, cudaEvent_t *ev,
@@ -388,7 +343,7 @@ int run_analysis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buf
     R2cArgs a{};
     a.grid = buf.gout; a.n_lev = L.n_lev; a.nh = h->nh; a.n_m = h->n_m; a.NHP = h->NHP;
     a.wgauss = h->d_wgauss; a.osin2 = h->d_osin2; a.fields = L.d_r2c;
-    a.B[0] = buf.Bas; a.B[1] = buf.Bav; a.ldB[0] = L.Nas; a.ldB[1] = L.Nav; a.minc = h->minc;
+    a.B = buf.Ba; a.ldB = L.Na; a.minc = h->minc;
     if (ev) cudaEventRecord(ev[0], h->stream);
     launch_fft_r2c(h->fft, a, spec.nfield_out, h->stream);
     h->launches++;
@@ -397,10 +352,7 @@ int run_analysis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buf
     h->launches++;
     if (ev) cudaEventRecord(ev[2], h->stream);
     if (!extract) { MCHECK(cudaGetLastError()); return 0; }
-    ExtractArgs e{};
-    e.Cs = buf.Cas; e.Cv = buf.Cav; e.offCs = L.d_offCas; e.offCv = L.d_offCav; e.Ns = L.Nas; e.Nv = L.Nav;
-    e.n_lev = L.n_lev; e.lm_max = h->lm_max; e.nf_s = L.nf_s; e.nf_v = 2 * L.npair_a; e.lm2l = h->d_lm2l; e.lm2m = h->d_lm2m;
-    e.minc = h->minc; e.lev = d_lev; e.out_s = buf.nl_s; e.out_v = buf.nl_v;
+    const ExtractArgs e = extract_args(h, L, buf, d_lev);
     dim3 g2((h->lm_max + 255) / 256, L.n_lev);
     anal_extract_kernel<<<g2, 256, 0, h->stream>>>(e);
     h->launches++;

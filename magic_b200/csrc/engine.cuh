@@ -49,8 +49,9 @@ inline int pad_up(int x, int m) { return (x + m - 1) / m * m; }
 struct magic_sht {
     int l_max, m_max, minc, n_theta, n_phi, nlat_padded, n_m, lm_max, nh, NHP, dev;
     std::vector<double> theta_ord, gauss;          // gauleg output (monotone north->south)
-    std::vector<int> lm2l, lm2m, lstart, ne, no;   // st_map; per-mc first lm and even/odd degree counts
-    std::vector<long long> off;                    // [n_m][4] table block offsets: Pe, Do, Po, De
+    std::vector<int> lm2l, lm2m, lstart, ne1, no1; // st_map; per-mc first lm and even/odd-parity degree counts of m .. l_max+1
+    std::vector<long long> off;                    // [n_m][2] table block offsets: P_even, P_odd
+    double *d_clm = nullptr;                       // c(l) = sqrt((l+m)(l-m)/((2l-1)(2l+1))), l = m .. l_max+2, at lstart[mc] + 2 mc + (l-m)
     std::vector<int> kmin;                         // per mc: first colatitude with non-negligible table entries
     double polar_eps = 1e-40;
     unsigned char *d_fskip_syn = nullptr, *d_fskip_an = nullptr;  // fragment-level skip tables (table_fskip_kernel), or null
@@ -81,25 +82,25 @@ struct BatchSpec {
 };
 
 struct Buffers {  // big device arrays, sized for the largest chunk
-    double *Bs = nullptr, *Bv = nullptr, *Fs = nullptr, *Fv = nullptr, *gin = nullptr, *gout = nullptr;
-    double *Bas = nullptr, *Bav = nullptr, *Cas = nullptr, *Cav = nullptr, *nl_s = nullptr, *nl_v = nullptr;
+    double *B = nullptr, *F = nullptr, *gin = nullptr, *gout = nullptr;   // synthesis operand, (theta,m) space, grids
+    double *Ba = nullptr, *Ca = nullptr, *nl_s = nullptr, *nl_v = nullptr;  // analysis operand / result, per-call spectra
     unsigned long long *courmax = nullptr;
     size_t bytes = 0;
 };
 
 struct Layout {  // descriptors for one chunk size
     int n_lev = 0;
-    int ncol_s = 0, npair_v = 0, Ns = 0, Nv = 0;
-    int nf_s = 0, npair_a = 0, Nas = 0, Nav = 0;
-    std::vector<long long> offBs, offBv, offCas, offCav;
-    long long szBs = 0, szBv = 0, szFs = 0, szFv = 0, szBas = 0, szBav = 0, szCas = 0, szCav = 0;
+    int ncol_s = 0, npair_v = 0, ncol = 0, N = 0;    // synthesis: complex columns = ncol_s + 2 npair_v, N = pad64(2 ncol n_lev)
+    int nf_s = 0, npair_a = 0, nfa = 0, Na = 0;      // analysis:  complex columns = nf_s + 2 npair_a
+    std::vector<long long> offB, offC;
+    long long szB = 0, szF = 0, szBa = 0, szCa = 0;
     int ntiles_syn = 0, ntiles_an = 0;
-    long long *d_offBs = nullptr, *d_offBv = nullptr, *d_offCas = nullptr, *d_offCav = nullptr;
+    long long *d_offB = nullptr, *d_offC = nullptr;
     int2 *d_prep_blks = nullptr;
     int n_prep_blks = 0;
     GemmProb *d_probs_syn = nullptr, *d_probs_an = nullptr;
     int2 *d_tiles_syn = nullptr, *d_tiles_an = nullptr;
-    int *d_colrow_s = nullptr, *d_colrow_v = nullptr;
+    int *d_colrow = nullptr;
     ScalCol *d_scal = nullptr;
     VecPair *d_vec = nullptr;
     R2cField *d_r2c = nullptr;
@@ -124,6 +125,7 @@ int run_analysis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buf
 // (complex [lm_max]); writes br_vt_lm, br_vp_lm (complex [lm_max]).  Runs on h->stream with the per-call single-level pipeline.
 int br_v_bcs_dev(magic_sht *h, const double *b, const double *dw, const double *z, int lcut, double fac, double omega,
                  double *br_vt_lm, double *br_vp_lm);
+ExtractArgs make_extract_args(const magic_sht *h, const Layout &L, const Buffers &buf, const LevelInfo *d_lev);
 int sht_init(magic_sht *h);
 void sht_free(magic_sht *h);
 

@@ -165,34 +165,21 @@ struct R2cArgs {
     const double *wgauss;  // 2 pi * gauss(k) / n_phi  (quadrature weight and forward-FFT normalisation)
     const double *osin2;   // 1/sin^2(theta_k)
     const R2cField *fields;
-    double *B[2];          // scalar-class / vector-class analysis operands
-    int ldB[2];
+    double *B;             // analysis operands: per parity problem (mc, s) a [NHP][ldB] matrix
+    int ldB;
     int minc;
 };
 
-__device__ __forceinline__ void r2c_scatter(const R2cArgs &a, const R2cDest *__restrict__ dests /* [2] of (field, s) */, int k, int mc,
-                                            int lev, double2 zk, double2 zmc, double2 w8, double w, double ws) {
+__device__ __forceinline__ void r2c_scatter(const R2cArgs &a, const R2cField fd, int s, int k, int mc, int lev, double2 zk, double2 zmc,
+                                            double2 w8, double w, double ws) {
     // X_k = E_k + e^{-2 pi i k/N} O_k, E=(Z_k+conj Z_{H-k})/2, O=-i (Z_k-conj Z_{H-k})/2
+    if (fd.rtype == R_NONE) return;
     double2 zm = cconj(zmc);
     double2 e = cscale(cadd(zk, zm), 0.5), o = cmuli(cscale(csub(zk, zm), 0.5), -1.0);
     double2 x = cadd(e, cmul(w8, o));
-    const double dm = (double)(mc * a.minc);
-#pragma unroll
-    for (int d = 0; d < 2; d++) {
-        const int rtype = dests[d].rtype;
-        if (rtype == R_NONE) continue;
-        const int cls = dests[d].cls, col = dests[d].col, p = dests[d].p, seg = dests[d].seg;
-        double2 v;
-        if (rtype == R_W) v = cscale(x, w);
-        else if (rtype == R_WS) v = cscale(x, ws);
-        else if (rtype == R_NEG_WS) v = cscale(x, -ws);
-        else v = make_double2(dm * ws * x.y, -dm * ws * x.x);  // -i m ws x
-        const int rowsB = cls == 0 ? a.NHP : 2 * a.NHP;
-        const int ld = cls == 0 ? a.ldB[0] : a.ldB[1];
-        double *B = cls == 0 ? a.B[0] : a.B[1];
-        size_t off = ((size_t)(mc * 2 + p) * rowsB + seg * a.NHP + k) * ld + 2 * ((size_t)col * a.n_lev + lev);
-        *reinterpret_cast<double2 *>(B + off) = v;
-    }
+    const double2 v = cscale(x, fd.rtype == R_W ? w : ws);
+    const size_t off = ((size_t)(mc * 2 + s) * a.NHP + k) * a.ldB + 2 * ((size_t)fd.col * a.n_lev + lev);
+    *reinterpret_cast<double2 *>(a.B + off) = v;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -387,7 +374,7 @@ __global__ void MAGIC_FFT_LB_R(H) fft_r2c_plan_kernel(const double2 *__restrict_
     // ---- last pass + post-processing + scatter.  Item t of a row: butterflies (t, SL - t); t = 0: butterfly 0 and, for even
     //      SL, the self-paired butterfly SL/2.  Butterfly q yields orders mc = q + SL kq, whose partners H - mc belong to SL - q.
     const double w = a.wgauss[k], ws = w * a.osin2[k];
-    const R2cDest *dests = &a.fields[field].d[s][0];
+    const R2cField dests = a.fields[field];
     for (int item = threadIdx.x; item < R * NIL; item += NT) {
         const int t = item / R, r = item - t * R;
         if (r >= rows) continue;
@@ -408,20 +395,20 @@ __global__ void MAGIC_FFT_LB_R(H) fft_r2c_plan_kernel(const double2 *__restrict_
 #pragma unroll
             for (int kq = 0; kq < RL; kq++) {
                 const int mu = u + SL * kq, mv = v + SL * (RL - 1 - kq);  // mu + mv = H
-                if (mu < a.n_m) r2c_scatter(a, dests, k, mu, lev, Zu[kq], Zv[RL - 1 - kq], twid(tw, mu, -1.0), w, ws);
-                if (mv < a.n_m) r2c_scatter(a, dests, k, mv, lev, Zv[RL - 1 - kq], Zu[kq], twid(tw, mv, -1.0), w, ws);
+                if (mu < a.n_m) r2c_scatter(a, dests, s, k, mu, lev, Zu[kq], Zv[RL - 1 - kq], twid(tw, mu, -1.0), w, ws);
+                if (mv < a.n_m) r2c_scatter(a, dests, s, k, mv, lev, Zv[RL - 1 - kq], Zu[kq], twid(tw, mv, -1.0), w, ws);
             }
         } else {
 #pragma unroll
             for (int kq = 0; kq < RL; kq++) {
                 const int mu = SL * kq;  // partner H - mu = SL (RL - kq); mu = 0 pairs with itself
-                if (mu < a.n_m) r2c_scatter(a, dests, k, mu, lev, Zu[kq], kq == 0 ? Zu[0] : Zu[RL - kq], twid(tw, mu, -1.0), w, ws);
+                if (mu < a.n_m) r2c_scatter(a, dests, s, k, mu, lev, Zu[kq], kq == 0 ? Zu[0] : Zu[RL - kq], twid(tw, mu, -1.0), w, ws);
             }
             if (has_v) {
 #pragma unroll
                 for (int kq = 0; kq < RL; kq++) {
                     const int mv = v + SL * kq;  // partner v + SL (RL-1-kq)
-                    if (mv < a.n_m) r2c_scatter(a, dests, k, mv, lev, Zv[kq], Zv[RL - 1 - kq], twid(tw, mv, -1.0), w, ws);
+                    if (mv < a.n_m) r2c_scatter(a, dests, s, k, mv, lev, Zv[kq], Zv[RL - 1 - kq], twid(tw, mv, -1.0), w, ws);
                 }
             }
         }
@@ -521,11 +508,11 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_r2c_kernel(FftPlan pl, R2cArg
     __syncthreads();
     double2 *Z = stockham_fft(buf0, buf1, R, pl, -1.0);
     const double w = a.wgauss[k], ws = w * a.osin2[k];
-    const R2cDest *dests = &a.fields[field].d[s][0];
+    const R2cField dests = a.fields[field];
     for (int idx = threadIdx.x; idx < rows * a.n_m; idx += blockDim.x) {
         int mc = idx / rows, r = idx - mc * rows;
         const double2 *z = Z + r * H;
-        r2c_scatter(a, dests, k, mc, lev0 + r, z[mc], z[mc == 0 ? 0 : H - mc], twid(pl.tw, mc, -1.0), w, ws);
+        r2c_scatter(a, dests, s, k, mc, lev0 + r, z[mc], z[mc == 0 ? 0 : H - mc], twid(pl.tw, mc, -1.0), w, ws);
     }
 }
 

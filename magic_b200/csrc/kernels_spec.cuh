@@ -6,8 +6,9 @@
 namespace magic {
 
 // ------------------------------------------------------------------------------------------------------
-// Table build: plm_theta (plms.f90:14-189, norm=2) evaluated per (order mc, northern colatitude k), written in
-// the blocked layout of common.cuh.  off[mc*4 + {0,1,2,3}] = offsets (doubles) of P_even, D_odd, P_odd, D_even.
+// Table build: plm_theta (plms.f90:14-189, norm=2) evaluated per (order mc, northern colatitude k) for the degrees
+// l = m .. l_max+1 (the reference runs the same recurrence to l_max+1 for its derivative table), written in the blocked
+// layout of common.cuh.  off[mc*2 + {0,1}] = offsets (doubles) of P_even, P_odd.
 __global__ void build_tables_kernel(double *__restrict__ tab, const long long *__restrict__ off,
                                     const double *__restrict__ sinth, const double *__restrict__ costh,
                                     const double *__restrict__ pmm_fac, int nh, int NHP, int l_max, int minc, int n_m) {
@@ -17,48 +18,37 @@ __global__ void build_tables_kernel(double *__restrict__ tab, const long long *_
     const int m = mc * minc;
     const double dnorm = 0.28209479177387814347403972578039;  // 1/sqrt(4 pi)
     const double st = sinth[k], ct = costh[k];
-    double *Pe = tab + off[mc * 4 + 0], *Do = tab + off[mc * 4 + 1], *Po = tab + off[mc * 4 + 2], *De = tab + off[mc * 4 + 3];
+    double *Pe = tab + off[mc * 2 + 0], *Po = tab + off[mc * 2 + 1];
     double plm = pmm_fac[mc];
     if (st != 0.0) plm = plm * pow(st, (double)m);
     else if (m != 0) plm = 0.0;
-    // sliding window of normalised values: pm1 = P_{l-1}, p0 = P_l, pp1 = P_{l+1}
     double plm1 = 0.0, plm2;
-    double pm1 = 0.0, p0 = dnorm * plm;
-    for (int l = m; l <= l_max; l++) {
-        // advance recurrence to degree l+1 (plms.f90:79-113)
-        int ln = l + 1;
+    for (int l = m; l <= l_max + 1; l++) {
+        const int j = (l - m) >> 1;
+        if (((l - m) & 1) == 0) Pe[(size_t)j * NHP + k] = dnorm * plm;
+        else Po[(size_t)j * NHP + k] = dnorm * plm;
+        // advance the recurrence to degree l+1 (plms.f90:79-113)
+        const int ln = l + 1;
         plm2 = plm1;
         plm1 = plm;
         plm = ct * sqrt((double)((2 * ln - 1) * (2 * ln + 1)) / (double)((ln - m) * (ln + m))) * plm1 -
               sqrt(((double)(2 * ln + 1) * (double)(ln + m - 1) * (double)(ln - m - 1)) /
                    ((double)(2 * ln - 3) * (double)(ln - m) * (double)(ln + m))) * plm2;
-        double pp1 = dnorm * plm;
-        // sin(theta) dP/dtheta (plms.f90:117-187)
-        double d;
-        if (l == m) d = l / sqrt((double)(2 * l + 3)) * pp1;
-        else
-            d = l * sqrt((double)((l + m + 1) * (l - m + 1)) / (double)((2 * l + 1) * (2 * l + 3))) * pp1 -
-                (l + 1) * sqrt((double)((l + m) * (l - m)) / (double)((2 * l - 1) * (2 * l + 1))) * pm1;
-        int j = (l - m) >> 1;
-        if (((l - m) & 1) == 0) { Pe[(size_t)j * NHP + k] = p0; De[(size_t)j * NHP + k] = d; }
-        else { Po[(size_t)j * NHP + k] = p0; Do[(size_t)j * NHP + k] = d; }
-        pm1 = p0;
-        p0 = pp1;
     }
 }
 
-// First colatitude index k (north pole = 0) at which any P or D entry of order mc reaches `thr` in magnitude.
-// Rows below it contribute less than thr * |coefficient| to any sum -- with thr = 1e-40 that is 24 orders of magnitude
-// below FP64 rounding of the result -- and are skipped by the Legendre GEMMs ("polar optimisation", cf. the
-// eps_polar of shtns.f90:59, here with a threshold that cannot change a single result bit that matters).
+// First colatitude index k (north pole = 0) at which any P entry of order mc (degrees m .. l_max+1) reaches `thr` in
+// magnitude.  Rows below it contribute less than thr * l * |coefficient| to any sum -- with thr = 1e-40 that is more than 20
+// orders of magnitude below FP64 rounding of the result -- and are skipped by the Legendre GEMMs ("polar optimisation", cf.
+// the eps_polar of shtns.f90:59, here with a threshold that cannot change a single result bit that matters).
 __global__ void table_kmin_kernel(const double *__restrict__ tab, const long long *__restrict__ off, int nh, int NHP, int l_max,
                                   int minc, double thr, int *__restrict__ kmin) {
     __shared__ int best;
     const int mc = blockIdx.x, m = mc * minc;
     if (threadIdx.x == 0) best = nh;
     __syncthreads();
-    const long long rows = 2LL * (l_max - m + 1);  // the four blocks of this order are contiguous
-    const double *base = tab + off[mc * 4];
+    const long long rows = (long long)(l_max + 1 - m + 1);  // the two blocks of this order are contiguous
+    const double *base = tab + off[mc * 2];
     for (int k = threadIdx.x; k < nh; k += blockDim.x) {
         bool hit = false;
         for (long long r = 0; r < rows && !hit; r++) hit = fabs(base[r * NHP + k]) >= thr;
@@ -71,16 +61,16 @@ __global__ void table_kmin_kernel(const double *__restrict__ tab, const long lon
 // Fragment-level refinement of the polar skipping.  The table of order m is negligible for colatitudes polewards of the
 // turning point sin(theta) ~ m/l, i.e. in a triangle of the (degree, colatitude) plane, not a rectangle.  For every block
 // (mc, b) of the table (rows = degrees j, columns = northern colatitudes k):
-//   syn[(mc*4+b)*FS + f]  = first 16-degree tile holding an entry >= thr in colatitudes [8f, 8f+8)   (synthesis: M = theta)
-//   an [(mc*4+b)*FA + jf] = first 16-colatitude tile holding an entry >= thr in degrees [8jf, 8jf+8) (analysis:  M = degree)
+//   syn[(mc*2+b)*FS + f]  = first 16-degree tile holding an entry >= thr in colatitudes [8f, 8f+8)   (synthesis: M = theta)
+//   an [(mc*2+b)*FA + jf] = first 16-colatitude tile holding an entry >= thr in degrees [8jf, 8jf+8) (analysis:  M = degree)
 // 255 = none / padding.  blockIdx = (mc, b); threads stride over fragments.
 __global__ void table_fskip_kernel(const double *__restrict__ tab, const long long *__restrict__ off, const int *__restrict__ ne,
                                    const int *__restrict__ no, int nh, int NHP, double thr, int FS, int FA,
                                    unsigned char *__restrict__ syn, unsigned char *__restrict__ an) {
     const int mc = blockIdx.x, b = blockIdx.y;
-    const int rows = (b == 0 || b == 3) ? ne[mc] : no[mc];
-    const double *base = tab + off[mc * 4 + b];
-    unsigned char *so = syn + ((size_t)mc * 4 + b) * FS, *ao = an + ((size_t)mc * 4 + b) * FA;
+    const int rows = b == 0 ? ne[mc] : no[mc];
+    const double *base = tab + off[mc * 2 + b];
+    unsigned char *so = syn + ((size_t)mc * 2 + b) * FS, *ao = an + ((size_t)mc * 2 + b) * FA;
     for (int f = threadIdx.x; f < FS; f += blockDim.x) {
         int first = 255;
         if (8 * f < nh) {
@@ -112,23 +102,26 @@ __global__ void table_fskip_kernel(const double *__restrict__ tab, const long lo
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Synthesis operand assembly (the pre-scalings of the sht_native.f90 wrappers: l(l+1), or2, i*m, l>lcut masks, and
-// the level masks of rIter.f90:466-622).  One CTA per block of 32 consecutive degrees of one order: lane i owns degree
-// l = m + 32*jt + i, so the spectral reads are 512-byte contiguous per (source, level); even/odd lanes feed the two
-// parity problems, and every degree feeds a P row of its own parity problem and a D row of the other one.
-// Warp w of CTA (x, y) takes level y*8 + w.
+// Synthesis operand assembly: the pre-scalings of the sht_native.f90 wrappers (l(l+1), or2, i*m, l>lcut masks), the level
+// masks of rIter.f90:466-622, and the 3-point combination that turns the reference's sums against dPlm into sums against
+// Plm (plms.f90:117-187: dPlm(l) = l c(l+1) Plm(l+1) - (l+1) c(l) Plm(l-1), so
+//      sum_l S(l) dPlm(l) = sum_l' Plm(l') [ (l'-1) c(l') S(l'-1) - (l'+2) c(l'+1) S(l'+1) ],   l' = m .. lcut+1).
+// One CTA per block of 32 consecutive degrees l' of one order (plus one halo degree on either side): lane i owns degree
+// m + 32*jt + i, so the spectral reads are 512-byte contiguous per (source, level); even/odd degrees feed the two parity
+// problems.  Warp w of CTA (x, y) takes level y*8 + w.
 struct SynthPrepArgs {
     const double *src[MAGIC_MAX_SRC];  // complex [n_lev][lm_max]
     const ScalCol *scal;
     const VecPair *vec;
     int ncol_s, npair_v, n_lev, lm_max;
-    int Ns, Nv;
+    int N;
     const LevelInfo *lev;
-    const int *lstart;  // lm index of degree l=m for each mc
+    const int *lstart;   // lm index of degree l=m for each mc
+    const double *clm;   // c(l), l = m .. l_max+2, at lstart[mc] + 2 mc + (l - m)
     int l_max, minc, nsrc;
-    double *Bs, *Bv;
-    const long long *offBs, *offBv;  // per problem (mc*2+s), doubles
-    const int2 *blks;                // (mc, jt)
+    double *B;
+    const long long *offB;  // per problem (mc*2+s), doubles
+    const int2 *blks;       // (mc, jt)
 };
 
 __device__ __forceinline__ bool level_enabled(int lmask, const LevelInfo &L) {
@@ -139,16 +132,16 @@ __device__ __forceinline__ bool level_enabled(int lmask, const LevelInfo &L) {
 }
 
 constexpr int PREP_WARPS = 8;   // = levels per CTA
-constexpr int PREP_LD = 33;     // padded degree stride of the staging tile
+constexpr int PREP_LD = 35;     // staging tile: positions 0..33 = degrees l0-1 .. l0+32, odd stride against bank conflicts
 
-__device__ __forceinline__ double2 eval_terms(const Term *t, const double2 *xs /* staging tile of this level */, int d, int src_stride,
+__device__ __forceinline__ double2 eval_terms(const Term *t, const double2 *xs /* staging tile of this level */, int pos, int src_stride,
                                               int l, int m, double or2) {
     double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         int ft = t[i].ftype;
         if (ft == F_NONE) continue;
-        double2 x = xs[t[i].src * src_stride + d];
+        double2 x = xs[t[i].src * src_stride + pos];
         double dlh = (double)(l * (l + 1));
         if (ft == F_ONE) { acc.x += x.x; acc.y += x.y; }
         else if (ft == F_DLH) { acc.x += dlh * x.x; acc.y += dlh * x.y; }
@@ -160,11 +153,10 @@ __device__ __forceinline__ double2 eval_terms(const Term *t, const double2 *xs /
 }
 
 // CTA (x, y): degree block blks[x] = (mc, jt), levels y*8 .. y*8+7.
-//   phase 1: warp w reads level y*8+w, lane = degree: every source is one 512-byte request; the values go to a shared tile
-//            xs[src][level][degree];
+//   phase 1: warp w reads level y*8+w, lane = degree: every source is one 512-byte request (plus the two halo degrees); the
+//            values go to a shared tile xs[src][level][position];
 //   phase 2: thread (degree d = tid/8, level lv = tid%8) evaluates all columns of its (degree, level) and stores them: the 8
-//            lanes of a degree write 128 contiguous bytes of one operand row (the first version let every lane of a warp
-//            write 16 bytes into a different row: 32 half-used sectors per store, 2.4 TB/s).
+//            lanes of a degree write 128 contiguous bytes of one operand row.
 __global__ void __launch_bounds__(PREP_WARPS * 32) synth_prep_kernel(SynthPrepArgs a) {
     extern __shared__ __align__(16) double2 prep_sm[];
     const int2 blk = a.blks[blockIdx.x];
@@ -172,96 +164,147 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) synth_prep_kernel(SynthPrepAr
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lev0 = blockIdx.y * PREP_WARPS;
     const int src_stride = PREP_WARPS * PREP_LD;
-    {   // ---- phase 1
-        const int lev = lev0 + warp, l = m + 32 * jt + lane;
-        const size_t lm = (size_t)a.lstart[mc] + (l - m);
-        const bool ok = lev < a.n_lev && l <= a.l_max;
-        double2 x[MAGIC_MAX_SRC];
+    const int l0 = m + 32 * jt;
+    {   // ---- phase 1: positions p = 0..33 hold degrees l0-1+p
+        const int lev = lev0 + warp;
 #pragma unroll
-        for (int sidx = 0; sidx < MAGIC_MAX_SRC; sidx++) {
-            x[sidx] = make_double2(0.0, 0.0);
-            if (sidx < a.nsrc && a.src[sidx] != nullptr && ok)
-                x[sidx] = *reinterpret_cast<const double2 *>(a.src[sidx] + 2 * ((size_t)lev * a.lm_max + lm));
+        for (int round = 0; round < 2; round++) {
+            const int pos = round == 0 ? lane : 32 + lane;
+            if (round == 1 && lane >= 2) break;
+            const int l = l0 - 1 + pos;
+            const bool ok = lev < a.n_lev && l >= m && l <= a.l_max;
+            const size_t lm = (size_t)a.lstart[mc] + (l - m);
+#pragma unroll
+            for (int sidx = 0; sidx < MAGIC_MAX_SRC; sidx++) {
+                if (sidx < a.nsrc) {
+                    double2 x = make_double2(0.0, 0.0);
+                    if (a.src[sidx] != nullptr && ok) x = *reinterpret_cast<const double2 *>(a.src[sidx] + 2 * ((size_t)lev * a.lm_max + lm));
+                    prep_sm[(sidx * PREP_WARPS + warp) * PREP_LD + pos] = x;
+                }
+            }
         }
-#pragma unroll
-        for (int sidx = 0; sidx < MAGIC_MAX_SRC; sidx++)
-            if (sidx < a.nsrc) prep_sm[(sidx * PREP_WARPS + warp) * PREP_LD + lane] = x[sidx];
     }
     __syncthreads();
     // ---- phase 2
     const int lv = threadIdx.x & (PREP_WARPS - 1), d = threadIdx.x >> 3, lev = lev0 + lv;
     if (lev >= a.n_lev) return;
-    const int l = m + 32 * jt + d, par = d & 1, r = d >> 1;
-    const bool valid_l = l <= a.l_max;
-    const int ne = (a.l_max - m) / 2 + 1, no = (a.l_max - m + 1) / 2;
-    const int K_par = par == 0 ? ne : no, K_oth = par == 0 ? no : ne;
+    const int l = l0 + d, par = d & 1, r = d >> 1, L1 = a.l_max + 1;
+    const int K_par = par == 0 ? (L1 - m) / 2 + 1 : (L1 - m + 1) / 2;
     if (jt >= (K_par + BK - 1) / BK) return;  // the k-tile this degree block maps to does not exist for my parity
-    const int pP = mc * 2 + par, pD = mc * 2 + (1 - par);
-    const int ktD = (K_oth + BK - 1) / BK + jt;  // D rows of problem pD come after its P rows
-    double *rowS = a.Bs + (a.ncol_s ? a.offBs[pP] : 0) + (size_t)(jt * BK + r) * a.Ns;
-    double *rowVP = a.Bv + (a.npair_v ? a.offBv[pP] : 0) + (size_t)(jt * BK + r) * a.Nv;
-    double *rowVD = a.Bv + (a.npair_v ? a.offBv[pD] : 0) + (size_t)(ktD * BK + r) * a.Nv;
+    double *row = a.B + a.offB[mc * 2 + par] + (size_t)(jt * BK + r) * a.N;
     const double dm = (double)m;
     const LevelInfo L = a.lev[lev];
     const double2 *xs = prep_sm + lv * PREP_LD;
-    const bool on = valid_l && l <= L.lcut;
+    const int pos = d + 1;
+    const bool on = l <= a.l_max && l <= L.lcut;
     for (int c = 0; c < a.ncol_s; c++) {
         const ScalCol sc = a.scal[c];
         double2 v = make_double2(0.0, 0.0);
-        if (on && level_enabled(sc.lmask, L)) v = eval_terms(sc.t, xs, d, src_stride, l, m, L.or2);
-        *reinterpret_cast<double2 *>(rowS + 2 * ((size_t)c * a.n_lev + lev)) = v;
+        if (on && level_enabled(sc.lmask, L)) v = eval_terms(sc.t, xs, pos, src_stride, l, m, L.or2);
+        *reinterpret_cast<double2 *>(row + 2 * ((size_t)c * a.n_lev + lev)) = v;
+    }
+    if (a.npair_v == 0) return;
+    // degrees l-1, l, l+1 of the (S, T) pair; entry l = 0 is ignored (shtransforms.f90:137-138), degrees above lcut are zero
+    const bool on_m = l - 1 >= m && l - 1 >= 1 && l - 1 <= L.lcut;
+    const bool on_0 = on && l >= 1;
+    const bool on_p = l + 1 <= a.l_max && l + 1 <= L.lcut;
+    double cm = 0.0, cp = 0.0;
+    if (l <= L1) {
+        const double *cl = a.clm + a.lstart[mc] + 2 * mc + (l - m);
+        cm = (double)(l - 1) * cl[0];   // dTheta2S-like coefficient of S(l-1)
+        cp = (double)(l + 2) * cl[1];   // coefficient of S(l+1)
     }
     for (int pr = 0; pr < a.npair_v; pr++) {
         const VecPair vp = a.vec[pr];
-        double2 S = make_double2(0.0, 0.0), T = S;
-        if (on && l > 0 && level_enabled(vp.lmask, L)) {
-            S = eval_terms(vp.S, xs, d, src_stride, l, m, L.or2);
-            T = eval_terms(vp.T, xs, d, src_stride, l, m, L.or2);
+        const double2 z = make_double2(0.0, 0.0);
+        double2 S0 = z, T0 = z, Sm = z, Tm = z, Sp = z, Tp = z;
+        if (l <= L1 && level_enabled(vp.lmask, L)) {
+            if (on_0) { S0 = eval_terms(vp.S, xs, pos, src_stride, l, m, L.or2); T0 = eval_terms(vp.T, xs, pos, src_stride, l, m, L.or2); }
+            if (on_m) { Sm = eval_terms(vp.S, xs, pos - 1, src_stride, l - 1, m, L.or2); Tm = eval_terms(vp.T, xs, pos - 1, src_stride, l - 1, m, L.or2); }
+            if (on_p) { Sp = eval_terms(vp.S, xs, pos + 1, src_stride, l + 1, m, L.or2); Tp = eval_terms(vp.T, xs, pos + 1, src_stride, l + 1, m, L.or2); }
         }
-        // Vtheta = sum (S D + i m T P), Vphi = sum (i m S P - T D)  
-        const size_t ct = 2 * ((size_t)(2 * pr) * a.n_lev + lev), cp = 2 * ((size_t)(2 * pr + 1) * a.n_lev + lev);
-        *reinterpret_cast<double2 *>(rowVP + ct) = make_double2(-dm * T.y, dm * T.x);
-        *reinterpret_cast<double2 *>(rowVP + cp) = make_double2(-dm * S.y, dm * S.x);
-        *reinterpret_cast<double2 *>(rowVD + ct) = S;
-        *reinterpret_cast<double2 *>(rowVD + cp) = make_double2(-T.x, -T.y);
+        // Vtheta = sum_l' P(l') [S'(l') + i m T(l')],  Vphi = sum_l' P(l') [i m S(l') - T'(l')]   (SURVEY.md appendix A with
+        // X'(l') = (l'-1) c(l') X(l'-1) - (l'+2) c(l'+1) X(l'+1))
+        const double2 Sd = make_double2(cm * Sm.x - cp * Sp.x, cm * Sm.y - cp * Sp.y);
+        const double2 Td = make_double2(cm * Tm.x - cp * Tp.x, cm * Tm.y - cp * Tp.y);
+        const size_t ct = 2 * ((size_t)(a.ncol_s + 2 * pr) * a.n_lev + lev), cph = 2 * ((size_t)(a.ncol_s + 2 * pr + 1) * a.n_lev + lev);
+        *reinterpret_cast<double2 *>(row + ct) = make_double2(Sd.x - dm * T0.y, Sd.y + dm * T0.x);
+        *reinterpret_cast<double2 *>(row + cph) = make_double2(-dm * S0.y - Td.x, dm * S0.x - Td.y);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Analysis extraction: C matrices of the analysis GEMM -> spectral arrays nl[field][lev][lm]
-// (the nonlinear_lm_t members of get_td.f90:27-45).  Vector outputs are divided by l(l+1)
-// (shtransforms.f90:866-870); degrees above lcut are exact zeros (shtransforms.f90:680,693).
+// Analysis extraction: C matrices of the analysis GEMM -> spectral arrays (the nonlinear_lm_t members of
+// get_td.f90:27-45).  Scalar columns are copied.  A vector pair arrives as the projections a(l') = sum_k w A P(l'),
+// b(l') = sum_k w B P(l') (A = fft(vp)/sin^2, B = fft(vt)/sin^2; l' = m .. l_max+1) and is combined to the reference's
+//     S(l) = [ -i m a(l) + l c(l+1) b(l+1) - (l+1) c(l) b(l-1) ] / l(l+1)
+//     T(l) = [ -( l c(l+1) a(l+1) - (l+1) c(l) a(l-1) ) - i m b(l) ] / l(l+1)
+// (shtransforms.f90:821-870 with dPlm(l) = l c(l+1) Plm(l+1) - (l+1) c(l) Plm(l-1), plms.f90:117-187).  Degrees above
+// lcut are exact zeros (shtransforms.f90:680,693).
 struct ExtractArgs {
-    const double *Cs, *Cv;
-    const long long *offCs, *offCv;  // per problem (mc*2+p), doubles
-    int Ns, Nv, n_lev, lm_max, nf_s, nf_v;  // nf_v = number of vector output columns (2 per pair)
-    const int *lm2l, *lm2m;
+    const double *C;
+    const long long *offC;  // per problem (mc*2+p), doubles
+    int N, n_lev, lm_max, nf_s, npair;
+    const int *lm2l, *lm2m, *lstart;
+    const double *clm;
     int minc;
     const LevelInfo *lev;
     double *out_s;  // [nf_s][n_lev][lm_max] complex
-    double *out_v;  // [nf_v][n_lev][lm_max] complex
+    double *out_v;  // [2*npair][n_lev][lm_max] complex: S, T per pair
 };
+
+struct ModeRef {  // where the analysis results of one (l, m) mode live
+    const double *own, *up, *dn;  // rows of degrees l, l+1, l-1 (column 0 of the level; dn valid only when has_dn)
+    bool has_dn;
+    double e, f, dm, ll1;         // l c(l+1), (l+1) c(l), m, l(l+1) (1 for l = 0)
+};
+
+__device__ __forceinline__ ModeRef mode_ref(const ExtractArgs &e, int lm, int lev) {
+    ModeRef r;
+    const int l = e.lm2l[lm], m = e.lm2m[lm], mc = m / e.minc, p = (l - m) & 1, j = (l - m) >> 1;
+    const double *cp = e.C + e.offC[mc * 2 + p] + 2 * (size_t)lev, *cq = e.C + e.offC[mc * 2 + 1 - p] + 2 * (size_t)lev;
+    r.own = cp + (size_t)j * e.N;
+    r.up = cq + (size_t)(j + p) * e.N;
+    r.has_dn = l > m;
+    r.dn = cq + (size_t)(r.has_dn ? j - 1 + p : 0) * e.N;
+    const double *cl = e.clm + e.lstart[mc] + 2 * mc + (l - m);
+    r.e = (double)l * cl[1];
+    r.f = (double)(l + 1) * cl[0];
+    r.dm = (double)m;
+    r.ll1 = lm > 0 ? (double)(l * (l + 1)) : 1.0;
+    return r;
+}
+
+// pair i: column of B (theta-type field) = nf_s + 2 i, column of A (phi-type field) = nf_s + 2 i + 1
+__device__ __forceinline__ void pair_combine(const ExtractArgs &e, const ModeRef &r, int i, double2 &S, double2 &T) {
+    const size_t cb = 2 * (size_t)(e.nf_s + 2 * i) * e.n_lev, ca = cb + 2 * (size_t)e.n_lev;
+    const double2 z = make_double2(0.0, 0.0);
+    const double2 a0 = *reinterpret_cast<const double2 *>(r.own + ca), b0 = *reinterpret_cast<const double2 *>(r.own + cb);
+    const double2 au = *reinterpret_cast<const double2 *>(r.up + ca), bu = *reinterpret_cast<const double2 *>(r.up + cb);
+    const double2 ad = r.has_dn ? *reinterpret_cast<const double2 *>(r.dn + ca) : z;
+    const double2 bd = r.has_dn ? *reinterpret_cast<const double2 *>(r.dn + cb) : z;
+    S.x = (r.dm * a0.y + (r.e * bu.x - r.f * bd.x)) / r.ll1;
+    S.y = (-r.dm * a0.x + (r.e * bu.y - r.f * bd.y)) / r.ll1;
+    T.x = (-(r.e * au.x - r.f * ad.x) + r.dm * b0.y) / r.ll1;
+    T.y = (-(r.e * au.y - r.f * ad.y) - r.dm * b0.x) / r.ll1;
+}
 
 __global__ void __launch_bounds__(256) anal_extract_kernel(ExtractArgs a) {
     int lm = blockIdx.x * blockDim.x + threadIdx.x;
     int lev = blockIdx.y;
     if (lm >= a.lm_max) return;
-    const int l = a.lm2l[lm], m = a.lm2m[lm], mc = m / a.minc;
-    const int p = (l - m) & 1, j = (l - m) >> 1;
-    const bool on = l <= a.lev[lev].lcut;
+    const bool on = a.lm2l[lm] <= a.lev[lev].lcut;
+    const ModeRef r = mode_ref(a, lm, lev);
+    const double2 z = make_double2(0.0, 0.0);
     for (int f = 0; f < a.nf_s; f++) {
-        double2 v = make_double2(0.0, 0.0);
-        if (on) v = *reinterpret_cast<const double2 *>(a.Cs + a.offCs[mc * 2 + p] + (size_t)j * a.Ns + 2 * ((size_t)f * a.n_lev + lev));
+        double2 v = on ? *reinterpret_cast<const double2 *>(r.own + 2 * (size_t)f * a.n_lev) : z;
         *reinterpret_cast<double2 *>(a.out_s + 2 * (((size_t)f * a.n_lev + lev) * a.lm_max + lm)) = v;
     }
-    const double ll1 = (double)(l * (l + 1));
-    for (int f = 0; f < a.nf_v; f++) {
-        double2 v = make_double2(0.0, 0.0);
-        if (on) {
-            v = *reinterpret_cast<const double2 *>(a.Cv + a.offCv[mc * 2 + p] + (size_t)j * a.Nv + 2 * ((size_t)f * a.n_lev + lev));
-            if (lm > 0) { v.x = v.x / ll1; v.y = v.y / ll1; }
-        }
-        *reinterpret_cast<double2 *>(a.out_v + 2 * (((size_t)f * a.n_lev + lev) * a.lm_max + lm)) = v;
+    for (int i = 0; i < a.npair; i++) {
+        double2 S = z, T = z;
+        if (on) pair_combine(a, r, i, S, T);
+        *reinterpret_cast<double2 *>(a.out_v + 2 * (((size_t)(2 * i) * a.n_lev + lev) * a.lm_max + lm)) = S;
+        *reinterpret_cast<double2 *>(a.out_v + 2 * (((size_t)(2 * i + 1) * a.n_lev + lev) * a.lm_max + lm)) = T;
     }
 }
 
@@ -472,37 +515,25 @@ template <int TL>
 __global__ void __launch_bounds__(256) extract_td_kernel(ExtractArgs e, TdArgs t, TdSlots slots) {
     extern __shared__ __align__(16) double2 td_sm[];
     constexpr int TLP = TL + 1;
-    const int lm0 = blockIdx.x * TL, n_lev = e.n_lev, nf = e.nf_s + e.nf_v;
-    // a thread owns (mode, level) pairs and reads all nf fields of a pair back to back: the loads are independent and
-    // issued before the first use (one load in flight per thread left this kernel at 1.9 TB/s)
-    constexpr int NF_MAX = 12;  // nonlinear_lm_t has 11 members
+    const int lm0 = blockIdx.x * TL, n_lev = e.n_lev;
+    // a thread owns (mode, level) pairs; tile slot f of a pair: scalar columns first, then (S, T) of every vector pair
     for (int pidx = threadIdx.x; pidx < TL * n_lev; pidx += blockDim.x) {
         const int lev = pidx % n_lev, ll = pidx / n_lev, lm = lm0 + ll;
+        const double2 z = make_double2(0.0, 0.0);
         bool on = false;
-        const double *ps = e.Cs, *pv = e.Cv;
-        double ll1 = 1.0;
+        ModeRef r;
         if (lm < e.lm_max) {
-            const int l = e.lm2l[lm], m = e.lm2m[lm], mc = m / e.minc, p = (l - m) & 1, j = (l - m) >> 1;
-            on = l <= e.lev[lev].lcut;
-            if (e.nf_s) ps = e.Cs + e.offCs[mc * 2 + p] + (size_t)j * e.Ns + 2 * (size_t)lev;
-            if (e.nf_v) pv = e.Cv + e.offCv[mc * 2 + p] + (size_t)j * e.Nv + 2 * (size_t)lev;
-            if (lm > 0) ll1 = (double)(l * (l + 1));
+            on = e.lm2l[lm] <= e.lev[lev].lcut;
+            r = mode_ref(e, lm, lev);
         }
-        double2 v[NF_MAX];
-#pragma unroll
-        for (int f = 0; f < NF_MAX; f++) {
-            v[f] = make_double2(0.0, 0.0);
-            if (on && f < nf)
-                v[f] = f < e.nf_s ? *reinterpret_cast<const double2 *>(ps + 2 * (size_t)f * n_lev)
-                                  : *reinterpret_cast<const double2 *>(pv + 2 * (size_t)(f - e.nf_s) * n_lev);
+        for (int f = 0; f < e.nf_s; f++)
+            td_sm[((size_t)f * n_lev + lev) * TLP + ll] = on ? *reinterpret_cast<const double2 *>(r.own + 2 * (size_t)f * n_lev) : z;
+        for (int i = 0; i < e.npair; i++) {
+            double2 S = z, T = z;
+            if (on) pair_combine(e, r, i, S, T);
+            td_sm[((size_t)(e.nf_s + 2 * i) * n_lev + lev) * TLP + ll] = S;
+            td_sm[((size_t)(e.nf_s + 2 * i + 1) * n_lev + lev) * TLP + ll] = T;
         }
-#pragma unroll
-        for (int f = 0; f < NF_MAX; f++)
-            if (f < nf) {
-                double2 x = v[f];
-                if (f >= e.nf_s && lm > 0) { x.x = x.x / ll1; x.y = x.y / ll1; }
-                td_sm[((size_t)f * n_lev + lev) * TLP + ll] = x;
-            }
     }
     __syncthreads();
     const double *base = reinterpret_cast<const double *>(td_sm);

@@ -181,3 +181,9 @@ class RadialLoop:
 
     def legendre_flops(self):
         return float(self.lib.magic_rloop_legendre_flops(self._h))
+
+    def legendre_units(self):
+        """(reference count, executed) scalar-equivalent Legendre passes per bulk level."""
+        u = (c_double * 2)()
+        check(self.lib.magic_rloop_legendre_units(self._h, u))
+        return float(u[0]), float(u[1])

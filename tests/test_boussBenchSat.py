@@ -106,7 +106,6 @@ def test_the_saturated_state_needs_every_term(golden):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 def test_gpu_radial_loop_reproduces_reference_energies(golden):
     """The CUDA radial loop inside the reference's Runge-Kutta loop: all five logged rows (25 steps, 75 loops)."""
     from magic_b200 import RadialLoop, Sht

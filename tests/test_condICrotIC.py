@@ -175,7 +175,6 @@ def test_the_energies_see_the_moving_wall(golden):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 def test_gpu_radial_loop_reproduces_reference_energies(golden):
     """The CUDA radial loop (magic_rloop_run + magic_rloop_set_rotation + magic_rloop_get_torques, and after the restart
     magic_rloop_get_br_v_bcs) inside the reference's time loop: all 1000 + 100 steps."""

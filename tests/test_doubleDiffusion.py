@@ -101,7 +101,6 @@ def test_the_energies_see_the_composition_advection(golden):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 def test_gpu_radial_loop_reproduces_reference_energies(golden):
     """The CUDA radial loop (magic_rloop_run, host containers, xi / dxidt / dVXirLM) inside the reference's Runge-Kutta loop:
     all five logged rows (25 steps, 75 loops)."""

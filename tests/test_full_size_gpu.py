@@ -13,14 +13,18 @@ Direct oracle comparisons: the whole radial loop on three levels at l_max = 255 
 shape), and on ONE bulk level at l_max = 1023 (config 5; the oracle's four Legendre tables take 12.9 GB of host memory there,
 the same footprint bench.py's cpu_baseline leg has).
 
-Written after the GPU budget of round 1 was spent: marked gpu_unverified until it has run on a device once.
+Tolerance of the direct comparisons: relative L2 <= 1e-12, or 10x the oracle's own response to a 1e-15 relative perturbation
+of its inputs where that is larger (the same rule as tests/test_rloop_gpu.py).  Only dzdt needs it: for the rough synthetic
+spectra the toroidal part of the nonlinear force is a small difference of large sums and is then weighted by l(l+1), so two
+correctly rounded evaluation orders of the reference's own formula differ by more than 1e-12 on it (measured on the B200 in
+round 2: l_max=255 5e-11, 511 4e-11, 1023 2e-9, every other output <= 1e-12).  Both numbers are printed (pytest -s / -rP).
 """
 import numpy as np
 import pytest
 
 from tests.util import random_spectrum, rel_l2
 
-pytestmark = [pytest.mark.gpu, pytest.mark.gpu_unverified]
+pytestmark = pytest.mark.gpu
 
 SIZES = [255, 511, 1023]
 
@@ -44,6 +48,11 @@ def _weights(s):
     """Quadrature weights per grid row (theta rows are N/S interleaved: rows 2k and 2k+1 share the k-th Gauss weight)."""
     th, g = s.get_grid()
     return np.repeat(np.asarray(g)[: len(th) // 2], 2)
+
+
+def _pc(a, b):
+    """largest deviation of any coefficient relative to the largest coefficient of the output"""
+    return np.abs(a - b).max() / np.abs(b).max()
 
 
 def test_scalar_round_trip_and_parseval(sht):
@@ -86,6 +95,26 @@ def test_lcut_zeros_and_linearity(sht):
     assert np.all(S[m.lm2l > lcut] == 0) and rel_l2(S[m.lm2l <= lcut], A[m.lm2l <= lcut]) < 1e-12
 
 
+def test_transforms_against_the_oracle(sht):
+    """north_star bar at full size: the vector synthesis and the q/s/t analysis of the per-call API against the oracle's
+    loops, relative L2 and worst single coefficient / grid value <= 1e-12."""
+    from oracle.oracle import Oracle
+    o = Oracle(sht.l_max, threads=16)
+    rng = np.random.default_rng(14)
+    m = _Maps(sht)
+    W, dW, Z = (random_spectrum(m, rng, zero_l0=True) for _ in range(3))
+    got = sht.torpol_to_spat(W, dW, Z, sht.l_max)
+    ref = o.torpol_to_spat(W, dW, Z, sht.l_max)
+    for nm, g, r in zip(("vr", "vt", "vp"), got, ref):
+        print(f"  l_max={sht.l_max} torpol_to_spat {nm}: rel_l2 {rel_l2(g, r):.3e} worst point {_pc(g, r):.3e}")
+        assert rel_l2(g, r) < 1e-12 and _pc(g, r) < 1e-12
+    gq = sht.spat_to_qst(ref[0].copy(), ref[1].copy(), ref[2].copy(), sht.l_max)
+    rq = o.spat_to_qst(ref[0].copy(), ref[1].copy(), ref[2].copy(), sht.l_max)
+    for nm, g, r in zip(("q", "s", "t"), gq, rq):
+        print(f"  l_max={sht.l_max} spat_to_qst {nm}: rel_l2 {rel_l2(g, r):.3e} worst coefficient {_pc(g, r):.3e}")
+        assert rel_l2(g, r) < 1e-12 and _pc(g, r) < 1e-12
+
+
 def _loop_setup(l_max, n_r_max, physics, levels, level_chunk=0, **flags):
     from magic_b200 import RadialLoop, Sht
     from magic_b200.workload import make_fields, make_params, make_radial
@@ -101,6 +130,32 @@ def _loop_setup(l_max, n_r_max, physics, levels, level_chunk=0, **flags):
 
 
 MHD_OUT = ["dwdt", "dzdt", "dpdt", "dsdt", "dbdt", "djdt", "dVxBhLM", "dVSrLM"]
+TOL = 1e-12
+
+
+def _compare_with_floor(make_oracle, op, rad, fields, got, names, sel_of):
+    """Per output: rel. L2 and worst single coefficient against the strict oracle.  The floor is what two evaluations of the
+    reference's OWN formula differ by: (a) the oracle's response to a last-bits (1e-15 relative) perturbation of its inputs,
+    (b) the oracle built with -O3 -mavx2 -mfma against the strict IEEE build (same loops, other rounding order)."""
+    o = make_oracle(False)
+    ref = o.radial_loop(op, rad, fields)
+    prng = np.random.default_rng(12345)
+    pert = {k: v * (1.0 + 1e-15 * prng.standard_normal(v.shape)) for k, v in fields.items()}
+    noise = o.radial_loop(op, rad, pert)
+    del o
+    fast = make_oracle(True).radial_loop(op, rad, fields)
+    for nm in names:
+        sel = sel_of(nm)
+        lo = 1 if nm == "dpdt" else 0
+        g, r, n, f = (x[nm][sel][:, lo:] for x in (got, ref, noise, fast))
+        err, pc = rel_l2(g, r), _pc(g, r)
+        floor, floor_pc = max(rel_l2(n, r), rel_l2(f, r)), max(_pc(n, r), _pc(f, r))
+        print(f"  {nm:8s} rel_l2 {err:.3e} (input-noise {rel_l2(n, r):.3e}, fma-build {rel_l2(f, r):.3e})   "
+              f"worst coefficient {pc:.3e} (input-noise {_pc(n, r):.3e}, fma-build {_pc(f, r):.3e})"
+              f"  {'<- floor rule' if max(err, pc) >= TOL else ''}")
+        assert err < max(TOL, 10.0 * floor), (nm, err, floor)
+        assert pc < max(TOL, 10.0 * floor_pc), (nm, pc, floor_pc)
+    return ref
 
 
 @pytest.mark.parametrize("l_max,n_r_max,physics", [(255, 121, "mhd"), (511, 161, "hydro")])
@@ -109,15 +164,13 @@ def test_radial_loop_against_the_oracle(l_max, n_r_max, physics):
     from oracle.oracle import Oracle, Params as OParams
     s, p, rad, fields, rl = _loop_setup(l_max, n_r_max, physics, [1, 2, n_r_max // 2])
     got = rl.radialLoop(fields)
-    o = Oracle(l_max, threads=8)
     op = OParams()
     for n, _ in p._fields_:
         setattr(op, n, getattr(p, n))
-    ref = o.radial_loop(op, rad, fields)
-    for nm in (MHD_OUT if physics == "mhd" else ["dwdt", "dzdt", "dpdt", "dsdt", "dVSrLM"]):
-        sel = slice(None) if nm.startswith("dV") else slice(1, None)
-        lo = 1 if nm == "dpdt" else 0
-        assert rel_l2(got[nm][sel][:, lo:], ref[nm][sel][:, lo:]) < 1e-11, nm
+    print(f"radial loop vs oracle, l_max={l_max} {physics}")
+    ref = _compare_with_floor(lambda fast: Oracle(l_max, threads=8, fast=fast), op, rad, fields, got,
+                              MHD_OUT if physics == "mhd" else ["dwdt", "dzdt", "dpdt", "dsdt", "dVSrLM"],
+                              lambda nm: slice(None) if nm.startswith("dV") else slice(1, None))
     assert np.allclose(got["dtrkc"], ref["dtrkc"], rtol=1e-12) and np.allclose(got["dthkc"], ref["dthkc"], rtol=1e-12)
     rl.finalize()
     s.finalize_sht()
@@ -128,14 +181,11 @@ def test_l1023_one_level_against_the_oracle():
     from oracle.oracle import Oracle, Params as OParams
     s, p, rad, fields, rl = _loop_setup(1023, 257, "mhd", [129])
     got = rl.radialLoop(fields)
-    o = Oracle(1023, threads=16)
     op = OParams()
     for n, _ in p._fields_:
         setattr(op, n, getattr(p, n))
-    ref = o.radial_loop(op, rad, fields)
-    for nm in MHD_OUT:
-        lo = 1 if nm == "dpdt" else 0
-        assert rel_l2(got[nm][:, lo:], ref[nm][:, lo:]) < 1e-10, nm     # conditioning of dzdt at this size: see DESIGN 5
+    print("radial loop vs oracle, l_max=1023 mhd, one bulk level (polar_eps = 1e-40)")
+    _compare_with_floor(lambda fast: Oracle(1023, threads=16, fast=fast), op, rad, fields, got, MHD_OUT, lambda nm: slice(None))
     rl.finalize()
     s.finalize_sht()
 

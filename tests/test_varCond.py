@@ -119,7 +119,6 @@ def test_the_energies_see_the_anelastic_magnetic_terms(golden):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 def test_gpu_radial_loop_reproduces_reference_energies(golden):
     """The CUDA radial loop (magic_rloop_run, host containers) inside the reference's time loop: all 50 logged rows."""
     from magic_b200 import RadialLoop, Sht
