@@ -137,6 +137,13 @@ int magic_rloop_get_torques(const magic_rloop *rl, double *lorentz_torque_ic, do
  * complex [lm_max] HOST arrays, valid after a run on the rank that holds the boundary level.  Only defined for runs with
  * l_b_nl_cmb / l_b_nl_icb (stress-free wall + conducting mantle / inner core, Namelists.f90:713-729); an error otherwise. */
 int magic_rloop_get_br_v_bcs(const magic_rloop *rl, int boundary, double *br_vt_lm, double *br_vp_lm);
+/* Page-locks a PERSISTENT host array of the caller (a field container that lives as long as the run) so that magic_rloop_run
+ * can overlap its transfers with the compute; unpin before the array is freed.  The run calls never pin on their own: without
+ * this call the transfers are staged through pageable memory (correct, slower).  Already page-locked memory is accepted. */
+int magic_rloop_pin_host(magic_rloop *rl, const void *ptr, size_t bytes);
+int magic_rloop_unpin_host(magic_rloop *rl, const void *ptr);
+/* The level chunk in use (magic_rloop_create's level_chunk, or its automatic choice, clamped to n_r_loc). */
+int magic_rloop_level_chunk(const magic_rloop *rl);
 /* Stream control + kernel accounting for the benchmark. */
 int magic_rloop_sync(magic_rloop *rl);
 long long magic_rloop_launch_count(const magic_rloop *rl);
@@ -144,6 +151,10 @@ long long magic_rloop_launch_count(const magic_rloop *rl);
  * out[0]=total, [1]=synthesis prep, [2]=Legendre synthesis, [3]=c2r FFT, [4]=get_nl, [5]=r2c FFT,
  * [6]=Legendre analysis, [7]=get_td epilogue. */
 int magic_rloop_last_timing(const magic_rloop *rl, double out[8]);
+/* Device time (ms) of the last run that lay outside the chunk loop: out[0] = start of the run -> first kernel of the first
+ * chunk (the inbound transposes / transfers of the first chunk that nothing could hide), out[1] = last kernel of the last
+ * chunk -> end of the run (outbound transposes / transfers of the last chunk, boundary products). */
+int magic_rloop_last_exposed(const magic_rloop *rl, double out[2]);
 /* Algorithmic FP64 flops of the Legendre stage of one run (U * 2*n_theta*lm_max per level). */
 double magic_rloop_legendre_flops(const magic_rloop *rl);
 /* Scalar-equivalent Legendre passes per bulk level: out[0] = the reference's count (native_qst_to_spat / native_spat_to_sph_tor
@@ -197,22 +208,33 @@ int magic_transp_counts(const magic_transp *t, int dir /*0 lm2r, 1 r2lm*/, long 
                         long long *rcounts, long long *rdisp);
 
 /* ---- the whole hot path of one time step in one call (step_time.f90:485-612): transp_LMloc_to_Rloc -> radialLoopG ->
- * transp_Rloc_to_LMloc, on LM-distributed DEVICE containers in the reference's packing (fields.f90:211-268,
- * dt_fieldsLast.f90:125-214).  With more than one rank the transposes run chunk-wise on a second stream: the all-to-all
- * of level chunk c+1 (in) and of chunk c-1 (out) overlap the compute of chunk c.  Every rank must have created its loop
- * with the same explicit level_chunk.  Supported field set: heat + flow (+ magnetic field), pressure formulation. */
+ * transp_Rloc_to_LMloc, on LM-distributed containers in the reference's packing (fields.f90:211-268,
+ * dt_fieldsLast.f90:125-214).  The work is pipelined level chunk by level chunk: while chunk c computes, the transposes of
+ * chunk c+1 (in) and c-1 (out) run on a high-priority second stream and -- for the host-pointer call -- the PCIe transfers
+ * of chunks c+2 (up) and c-1 (down) on two more.  With several ranks the first and the last chunk of every slab are short
+ * (4 levels; MAGIC_LM_TAPER), because their transposes are the only ones that cannot hide.  Every rank derives every rank's
+ * chunks from the same pure function of (slab, level_chunk): create all loops of a run with the same level_chunk (or 0).
+ * Field sets: flow (+ heat) (+ magnetic field) (+ composition), pressure or double-curl formulation.
+ * Containers of switched-off physics are NULL.  ds / dxi (second field of the s / xi containers) are not read. */
 typedef struct {
     const double *flow;  /* complex [5][n_r_max][nlm_loc]: w, dw, ddw, z, dz */
     const double *s;     /* complex [2][n_r_max][nlm_loc]: s, ds */
     const double *field; /* complex [5][n_r_max][nlm_loc]: b, db, ddb, aj, dj (NULL without l_mag) */
+    const double *xi;    /* complex [2][n_r_max][nlm_loc]: xi, dxi (NULL without l_chemical_conv) */
 } magic_lm_in;
 typedef struct {
-    double *dflowdt;     /* complex [3][n_r_max][nlm_loc]: dwdt, dzdt, dpdt */
+    double *dflowdt;     /* complex [3 or 4][n_r_max][nlm_loc]: dwdt, dzdt, dpdt (, dVxVhLM with l_double_curl) */
     double *dsdt;        /* complex [2][n_r_max][nlm_loc]: dsdt, dVSrLM */
     double *dbdt;        /* complex [3][n_r_max][nlm_loc]: dbdt, djdt, dVxBhLM (NULL without l_mag) */
-    double *dtrkc, *dthkc; /* device [n_r_loc] */
+    double *dtrkc, *dthkc; /* [n_r_loc]: device for _dev, host otherwise */
+    double *dxidt;       /* complex [2][n_r_max][nlm_loc]: dxidt, dVXirLM (NULL without l_chemical_conv) */
 } magic_lm_out;
+/* DEVICE containers (the LM-side solver lives on the GPU, or a benchmark). */
 int magic_rloop_run_lm_dev(magic_rloop *rl, magic_transp *t, const magic_lm_in *in, const magic_lm_out *out, double time);
+/* HOST containers: the drop-in call of a Fortran host whose LM loop stays on the CPU -- replaces the three calls
+ * transp_LMloc_to_Rloc (step_time.f90:485), radialLoopG (:530) and transp_Rloc_to_LMloc (:612) without intermediate host
+ * R-containers.  Page-lock the containers once with magic_rloop_pin_host for asynchronous transfers. */
+int magic_rloop_run_lm(magic_rloop *rl, magic_transp *t, const magic_lm_in *in, const magic_lm_out *out, double time);
 
 /* Pure host helpers (no CUDA device needed): the decomposition the transposer uses.
  * magic_get_blocks: getBlocks (parallel.f90:75-92), 1-based inclusive start/stop per rank.

@@ -243,6 +243,19 @@ module magic_b200_c
          integer(c_int) :: ierr
       end function magic_rloop_run
 
+      function magic_rloop_pin_host(rl, ptr, bytes) bind(C, name='magic_rloop_pin_host') result(ierr)
+         import :: c_int, c_ptr, c_size_t
+         type(c_ptr), value :: rl, ptr
+         integer(c_size_t), value :: bytes
+         integer(c_int) :: ierr
+      end function magic_rloop_pin_host
+
+      function magic_rloop_unpin_host(rl, ptr) bind(C, name='magic_rloop_unpin_host') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: rl, ptr
+         integer(c_int) :: ierr
+      end function magic_rloop_unpin_host
+
       function magic_rloop_set_rotation(rl, omega_ma, omega_ic) bind(C, name='magic_rloop_set_rotation') result(ierr)
          import :: c_int, c_ptr, c_double
          type(c_ptr), value :: rl

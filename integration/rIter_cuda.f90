@@ -22,6 +22,7 @@ module rIter_cuda_mod
        &            l_centrifuge, l_anelastic_liquid, l_cour_alf_damp, l_full_sphere, l_parallel_solve,     &
        &            l_temperature_diff, l_cond_ma, l_cond_ic, l_rot_ma, l_rot_ic, l_b_nl_cmb, l_b_nl_icb,   &
        &            l_phase_field, l_onset
+   use special, only: lGrenoble
    use physical_parameters, only: ktopv, kbotv, n_r_LCR, LFfac, CorFac, epsc, epscXi, opm, ViscHeatFac,     &
        &                          OhmLossFac, oek, po, prec_angle, dilution_fac, ra, opr
    use radial_functions, only: r, or1, or2, or4, orho1, orho2, beta, rho0, otemp1, temp0, visc, lambda,     &
@@ -60,6 +61,8 @@ contains
       class(rIter_cuda_t) :: this
 
       if ( l_phase_field .or. l_onset ) call abortRun('! rIter_cuda_t: phase field / onset mode are not on the GPU path')
+      !-- get_lorentz_torque adds the imposed-field term b0r with lGrenoble (outRot.f90:465-478): not on the GPU path
+      if ( lGrenoble ) call abortRun('! rIter_cuda_t: lGrenoble (imposed b0 in the Lorentz torque) is not on the GPU path')
       call this%single%initialize()
       !-- the plan needs tscheme%courfac / alffac: it is created by the first radialLoop call
 
@@ -124,8 +127,21 @@ contains
       p%omega_ma=omega_ma; p%omega_ic=omega_ic; p%r_cmb=r_cmb; p%r_icb=r_icb
       p%courfac=tscheme%courfac; p%alffac=tscheme%alffac
 
-      !-- level_chunk = 0: the library sizes its level batches from the free device memory
+      !-- level_chunk = 0: the library picks its level batch from the truncation and the field set (the same on every rank)
       call magic_check( magic_rloop_create(sht_h, p, rd, int(n_r_loc,c_int), 0_c_int, this%rl), 'magic_rloop_create' )
+
+      !-- page-lock the persistent R-distributed input containers of fields.f90 once, so that the uploads of one level chunk
+      !   overlap the compute of another (the library never pins caller memory on its own); finalize unpins them
+      if ( l_conv .or. l_mag_kin ) then
+         call pin(c_loc(w_Rloc), size(w_Rloc));  call pin(c_loc(dw_Rloc), size(dw_Rloc));  call pin(c_loc(ddw_Rloc), size(ddw_Rloc))
+         call pin(c_loc(z_Rloc), size(z_Rloc));  call pin(c_loc(dz_Rloc), size(dz_Rloc))
+      end if
+      if ( l_heat ) call pin(c_loc(s_Rloc), size(s_Rloc))
+      if ( l_chemical_conv ) call pin(c_loc(xi_Rloc), size(xi_Rloc))
+      if ( l_mag .or. l_mag_LF ) then
+         call pin(c_loc(b_Rloc), size(b_Rloc));   call pin(c_loc(db_Rloc), size(db_Rloc));  call pin(c_loc(ddb_Rloc), size(ddb_Rloc))
+         call pin(c_loc(aj_Rloc), size(aj_Rloc)); call pin(c_loc(dj_Rloc), size(dj_Rloc))
+      end if
 
    contains
 
@@ -133,6 +149,12 @@ contains
          logical, intent(in) :: l
          l2i = merge(1_c_int, 0_c_int, l)
       end function l2i
+
+      subroutine pin(ptr, n_complex)
+         type(c_ptr), intent(in) :: ptr
+         integer,     intent(in) :: n_complex
+         call magic_check( magic_rloop_pin_host(this%rl, ptr, int(16,c_size_t)*int(n_complex,c_size_t)), 'magic_rloop_pin_host' )
+      end subroutine pin
 
    end subroutine create_plan
 !------------------------------------------------------------------------------
@@ -186,7 +208,9 @@ contains
       !-- Diagnostics steps keep the reference's level-at-a-time loop (its transforms still run on the GPU)
       if ( l_graph .or. l_frame .or. lTOCalc .or. lTONext .or. lTONext2 .or. lHelCalc .or. lPowerCalc .or.   &
       &    lRmsCalc .or. lPressCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lGeosCalc .or. &
-      &    lHemiCalc .or. lPhaseCalc .or. l_probe_out ) then
+      &    lHemiCalc .or. lPhaseCalc .or. l_probe_out .or. ( lPressNext .and. l_double_curl ) ) then
+         !-- ( lPressNext with the double-curl equation: the reference also calls get_dpdt then (rIter.f90:420); the batched
+         !   loop only produces dpdt in the pressure formulation, so that step takes the level-at-a-time loop )
          call this%single%radialLoop(l_graph,l_frame,time,timeStage,tscheme,dtLast,lTOCalc,lTONext,lTONext2,   &
               &                      lHelCalc,lPowerCalc,lRmsCalc,lPressCalc,lPressNext,lViscBcCalc,           &
               &                      lFluxProfCalc,lPerpParCalc,lGeosCalc,lHemiCalc,lPhaseCalc,l_probe_out,    &

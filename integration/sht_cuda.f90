@@ -14,7 +14,8 @@ module sht
    !
    use iso_c_binding
    use precision_mod, only: cp
-   use truncation, only: l_max, m_max, minc, n_theta_max, n_phi_max, nlat_padded
+   use truncation, only: l_max, m_max, m_min, minc, n_theta_max, n_phi_max, nlat_padded
+   use useful, only: abortRun
    use parallel_mod, only: rank
    use magic_b200_c
 
@@ -40,6 +41,8 @@ contains
 
       integer(c_int) :: scr, n_dev
 
+      !-- the library builds lm_max, st_map and lo_map from m = 0 (blocking.f90 loops from m_min): refuse anything else loudly
+      if ( m_min /= 0 ) call abortRun('! sht (magic_b200): m_min /= 0 is not supported by the GPU backend')
       n_dev = magic_device_count()
       if ( n_dev < 1 ) call magic_check(1_c_int, 'initialize_sht (no CUDA device; this backend has no CPU path)')
       !-- one rank <-> one GPU of its node

@@ -25,13 +25,15 @@ struct magic_rloop {
     GridOut go;
     Buffers buf;
     std::vector<int> chunk_start, chunk_size;
-    int level_chunk = 0;  // the chunk length the sizes above were derived from
+    int level_chunk = 0;      // the chunk length the sizes above were derived from (clamped to this rank's slab)
+    int level_chunk_req = 0;  // the same before clamping: a pure function of the truncation and the field set, equal on every rank
     // hooks of the chunk loop (magic_rloop_run_lm_dev): called on the host right before the first / after the last kernel
     // of chunk c is queued; they queue the transposes of that chunk on the communication stream
     std::function<int(int)> hook_before, hook_after;
     struct LmPipe *lmpipe = nullptr;
-    Layout lay[2];  // at most two distinct chunk sizes
-    int lay_size[2] = {0, 0};
+    std::vector<Layout> lays;    // one layout per distinct chunk size; lays[0] belongs to the largest chunk (it sizes the workspace)
+    std::vector<int> lay_sizes;
+    int buf_levels = 0;          // number of levels the workspace `buf` was allocated for
     // nl_lm slots
     int a_Advr = -1, a_VSr = -1, a_VxBr = -1, a_VXir = -1, a_heat = -1;  // scalar-class analysis columns
     int a_Adv = -1, a_VS = -1, a_VxB = -1, a_VXi = -1;                    // vector pairs
@@ -49,10 +51,12 @@ struct magic_rloop {
     bool need_in[S_COUNT] = {false};
     bool need_out[O_COUNT] = {false};
     cudaEvent_t ev[16];
+    std::vector<cudaEvent_t> cev;  // 10 timing events per chunk (stage boundaries), read once per run
     double timing[8] = {0};
+    double exposed[2] = {0, 0};
     double legendre_flops = 0;
     double units_ref = 0, units_exec = 0;  // scalar-equivalent Legendre passes per bulk level: reference count / executed here
-    std::vector<const void *> registered, seen;
+    std::vector<std::pair<const void *, size_t>> registered;  // magic_rloop_pin_host
     // host-pointer path: uploads / downloads of level chunks overlap the compute of neighbouring chunks
     cudaStream_t s_up = nullptr, s_down = nullptr;
     std::vector<cudaEvent_t> up_done, comp_done;
@@ -115,11 +119,70 @@ static void add_pair(BatchSpec &s, Term S0, Term S1, Term T0, Term T1, int lmask
 
 static void lmpipe_free(struct LmPipe *p);
 
+// Tapered variant for the pipelined multi-rank call: a short first and last chunk (`taper` levels each) so that the inbound
+// transpose of the first chunk and the outbound transpose of the last one -- the two that cannot hide under any compute --
+// are small; the levels in between are chunked as above.  Pure function as well.
+static void level_chunks_tapered(int n_r_loc, int level_chunk, int taper, std::vector<int> &start, std::vector<int> &size) {
+    level_chunk = std::max(1, std::min(level_chunk, n_r_loc));
+    if (taper <= 0 || taper >= level_chunk || n_r_loc < 2 * taper + std::max(4, level_chunk / 2)) {
+        level_chunks(n_r_loc, level_chunk, start, size);
+        return;
+    }
+    std::vector<int> ms, mz;
+    level_chunks(n_r_loc - 2 * taper, level_chunk, ms, mz);
+    start.assign(1, 0);
+    size.assign(1, taper);
+    for (size_t i = 0; i < ms.size(); i++) { start.push_back(taper + ms[i]); size.push_back(mz[i]); }
+    start.push_back(n_r_loc - taper);
+    size.push_back(taper);
+}
+
+// (Re)partitions the slab into the given level chunks: one layout per distinct size, the workspace sized for the largest.
+static int rloop_set_chunks(magic_rloop *rl, const std::vector<int> &start, const std::vector<int> &size) {
+    magic_sht *h = rl->h;
+    rl->chunk_start = start;
+    rl->chunk_size = size;
+    std::vector<int> sizes(size);
+    std::sort(sizes.begin(), sizes.end(), std::greater<int>());
+    sizes.erase(std::unique(sizes.begin(), sizes.end()), sizes.end());
+    for (auto &L : rl->lays) layout_free(L);
+    rl->lays.assign(sizes.size(), Layout());
+    rl->lay_sizes = sizes;
+    layout_sizes(h, rl->spec, sizes[0], rl->lays[0]);
+    if (sizes[0] > rl->buf_levels) {
+        buffers_free(rl->buf);
+        if (buffers_alloc(h, rl->spec, rl->lays[0], rl->buf)) return 1;
+        rl->buf_levels = sizes[0];
+        cudaFree(rl->d_tq_partial);
+        rl->tq_parts = (int)(((size_t)h->nh * h->n_phi + NL_THREADS - 1) / NL_THREADS);
+        MCHECK(cudaMalloc((void **)&rl->d_tq_partial, sizeof(double) * (size_t)rl->tq_parts * sizes[0]));
+    }
+    for (size_t i = 0; i < sizes.size(); i++) {
+        if (i) layout_sizes(h, rl->spec, sizes[i], rl->lays[i]);
+        if (layout_bind(h, rl->spec, rl->lays[i], rl->buf)) return 1;
+    }
+    const size_t nchunks = size.size();
+    while (rl->up_done.size() < nchunks) {
+        cudaEvent_t e;
+        MCHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        rl->up_done.push_back(e);
+        MCHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        rl->comp_done.push_back(e);
+    }
+    while (rl->cev.size() < 10 * nchunks) {
+        cudaEvent_t e;
+        MCHECK(cudaEventCreate(&e));
+        rl->cev.push_back(e);
+    }
+    return 0;
+}
+
 extern "C" int magic_rloop_destroy(magic_rloop *rl) {
     if (!rl) return 0;
     cudaSetDevice(rl->h->dev);
-    for (const void *p : rl->registered) cudaHostUnregister((void *)p);
-    for (int i = 0; i < 2; i++) layout_free(rl->lay[i]);
+    for (const auto &r : rl->registered) cudaHostUnregister((void *)r.first);
+    for (auto &L : rl->lays) layout_free(L);
+    for (auto e : rl->cev) cudaEventDestroy(e);
     buffers_free(rl->buf);
     for (int i = 0; i < S_COUNT; i++) cudaFree(rl->d_in[i]);
     for (int i = 0; i < O_COUNT; i++) cudaFree(rl->d_out[i]);
@@ -146,6 +209,9 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
     *out = nullptr;
     MCHECK(cudaSetDevice(h->dev));
     const magic_params &P = *pp;
+    // the reference forces l_adv_curl = .false. for anelastic runs (Namelists.f90:540); with both set the viscous heating would
+    // read velocity derivatives that the curl-form column program never synthesises
+    if (P.l_anel && P.l_adv_curl) MFAIL("magic_rloop_create: l_anel with l_adv_curl is not a configuration of the reference (Namelists.f90:540)");
     magic_rloop *rl = new magic_rloop();
     rl->h = h;
     rl->p = P;
@@ -260,46 +326,26 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
 
     // ---- chunking
     if (level_chunk <= 0) {
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        Layout probe;
-        layout_sizes(h, S, 1, probe);
-        double per_level = 8.0 * ((double)probe.szB + probe.szF + probe.szBa + probe.szCa) +
-                           8.0 * 2.0 * h->nh * h->n_phi * (S.nfield_in + S.nfield_out);
-        level_chunk = (int)std::max(1.0, std::min((double)n_r_loc, 0.6 * (double)free_b / per_level));
+        // The automatic choice depends on the truncation and the field set only -- never on this rank's slab or its free
+        // memory -- so every rank of a run derives the same value (magic_rloop_run_lm_dev computes the chunks of its peers
+        // from it).  A workspace that does not fit fails loudly in buffers_alloc below.
         // measured at l_max=1023 (GEMM ms per level): 16-level chunks 1.65, 32-level chunks 1.78, 64-level chunks > 2.0 --
         // so 16 levels whenever that still gives the synthesis GEMM >= 20 waves of tiles, else 32 (small truncations are
         // launch-bound and want the wider batch)
         const long long tiles16 = (long long)h->n_m * 2 * ((h->nh + GEMM_BM - 1) / GEMM_BM) *
                                   ((2LL * std::max(1, (int)(S.scal.size() + 2 * S.vec.size())) * 16 + GEMM_BN - 1) / GEMM_BN);
-        level_chunk = std::min(level_chunk, tiles16 >= 20LL * 2 * 148 ? 16 : 32);
+        level_chunk = tiles16 >= 20LL * 2 * 148 ? 16 : 32;
     }
+    rl->level_chunk_req = level_chunk;
     level_chunk = std::min(level_chunk, n_r_loc);
     rl->level_chunk = level_chunk;
-    level_chunks(n_r_loc, level_chunk, rl->chunk_start, rl->chunk_size);
-    {   // at most two distinct sizes; lay[0] is the larger layout (it sizes the workspace)
-        const int first = rl->chunk_size.front(), last = rl->chunk_size.back();
-        rl->lay_size[0] = std::max(first, last);
-        rl->lay_size[1] = first == last ? 0 : std::min(first, last);
-    }
-    const int nchunks = (int)rl->chunk_size.size();
-    layout_sizes(h, S, rl->lay_size[0], rl->lay[0]);
-    if (buffers_alloc(h, S, rl->lay[0], rl->buf)) { magic_rloop_destroy(rl); return 1; }
-    if (layout_bind(h, S, rl->lay[0], rl->buf)) { magic_rloop_destroy(rl); return 1; }
-    if (rl->lay_size[1]) {
-        layout_sizes(h, S, rl->lay_size[1], rl->lay[1]);
-        if (layout_bind(h, S, rl->lay[1], rl->buf)) { magic_rloop_destroy(rl); return 1; }
+    {
+        std::vector<int> cs, cz;
+        level_chunks(n_r_loc, level_chunk, cs, cz);
+        if (rloop_set_chunks(rl, cs, cz)) { magic_rloop_destroy(rl); return 1; }
     }
     MCHECK(cudaStreamCreateWithFlags(&rl->s_up, cudaStreamNonBlocking));
     MCHECK(cudaStreamCreateWithFlags(&rl->s_down, cudaStreamNonBlocking));
-    rl->up_done.resize(nchunks);
-    rl->comp_done.resize(nchunks);
-    for (int c = 0; c < nchunks; c++) {
-        MCHECK(cudaEventCreateWithFlags(&rl->up_done[c], cudaEventDisableTiming));
-        MCHECK(cudaEventCreateWithFlags(&rl->comp_done[c], cudaEventDisableTiming));
-    }
-    rl->tq_parts = (int)(((size_t)h->nh * h->n_phi + NL_THREADS - 1) / NL_THREADS);
-    MCHECK(cudaMalloc((void **)&rl->d_tq_partial, sizeof(double) * (size_t)rl->tq_parts * rl->lay_size[0]));
     MCHECK(cudaMalloc((void **)&rl->d_torque, sizeof(double) * 2));
     {   // l_b_nl_cmb / l_b_nl_icb, Namelists.f90:713-729
         for (int i = 0; i < n_r_loc; i++) {
@@ -335,117 +381,114 @@ static void out_ptrs(const magic_fields_out *o, double *tmp[O_COUNT]) {
     tmp[O_DVXIR] = o->dVXirLM;
 }
 
-extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, const magic_fields_out *out, double time) {
-    if (!rl || !in || !out) MFAIL("magic_rloop_run_dev: null argument");
-    magic_sht *h = rl->h;
-    MCHECK(cudaSetDevice(h->dev));
-    const magic_params &P = rl->p;
+// ---- the chunk loop in three pieces: begin (checks, start event), chunk c (all kernels of one level chunk, queued on the
+//      handle's stream), end (boundary products, torques, the one host synchronisation of the run, stage timings) --------
+struct RunCtx {
     const double *ip[S_COUNT];
     double *op[O_COUNT];
-    in_ptrs(in, ip);
-    out_ptrs(out, op);
+    double *dtrkc, *dthkc;
+    double time;
+};
+
+static int rloop_begin(magic_rloop *rl, const magic_fields_in *in, const magic_fields_out *out, double time, RunCtx &x) {
+    magic_sht *h = rl->h;
+    MCHECK(cudaSetDevice(h->dev));
+    in_ptrs(in, x.ip);
+    out_ptrs(out, x.op);
     for (int i = 0; i < S_COUNT; i++)
-        if (rl->need_in[i] && !ip[i]) MFAIL("magic_rloop_run_dev: a required input field is null");
+        if (rl->need_in[i] && !x.ip[i]) MFAIL("magic_rloop: a required input field is null");
     for (int i = 0; i < O_COUNT; i++)
-        if (rl->need_out[i] && !op[i]) MFAIL("magic_rloop_run_dev: a required output field is null");
-    if (!out->dtrkc || !out->dthkc) MFAIL("magic_rloop_run_dev: dtrkc/dthkc are null");
-    const size_t lm2 = 2 * (size_t)h->lm_max;
-    const size_t plane = (size_t)h->nh * h->n_phi;
-    std::vector<float> stage(8, 0.f);
+        if (rl->need_out[i] && !x.op[i]) MFAIL("magic_rloop: a required output field is null");
+    if (!out->dtrkc || !out->dthkc) MFAIL("magic_rloop: dtrkc/dthkc are null");
+    x.dtrkc = out->dtrkc; x.dthkc = out->dthkc; x.time = time;
     cudaEventRecord(rl->ev[15], h->stream);
     MCHECK(cudaMemsetAsync(rl->d_torque, 0, sizeof(double) * 2, h->stream));  // rIter.f90:177-178
-    for (size_t c = 0; c < rl->chunk_start.size(); c++) {
-        const int l0 = rl->chunk_start[c], nl = rl->chunk_size[c];
-        const Layout &L = (nl == rl->lay_size[0]) ? rl->lay[0] : rl->lay[1];
-        const LevelInfo *d_lev = rl->d_lev + l0;
-        const double *src[MAGIC_MAX_SRC];
-        for (int i = 0; i < MAGIC_MAX_SRC; i++) src[i] = (i < S_COUNT && ip[i]) ? ip[i] + (size_t)l0 * lm2 : nullptr;
-        if (rl->pipelined) MCHECK(cudaStreamWaitEvent(h->stream, rl->up_done[c], 0));
-        if (rl->hook_before && rl->hook_before((int)c)) return 1;
-        if (run_synthesis(h, rl->spec, L, rl->buf, src, d_lev, rl->ev)) return 1;
-        // ---- get_nl + Courant
-        MCHECK(cudaMemsetAsync(rl->buf.courmax, 0, sizeof(unsigned long long) * 2 * nl, h->stream));
-        NlArgs a{};
-        NlFlags &F = a.f;
-        F.l_conv_nl = P.l_conv_nl; F.l_heat_nl = P.l_heat_nl; F.l_mag_nl = P.l_mag_nl; F.l_mag_LF = P.l_mag_LF; F.l_mag = P.l_mag;
-        F.l_mag_kin = P.l_mag_kin; F.l_adv_curl = P.l_adv_curl; F.l_anel = P.l_anel; F.l_chemical_conv = P.l_chemical_conv;
-        F.l_precession = P.l_precession; F.l_centrifuge = P.l_centrifuge; F.l_cour_alf_damp = P.l_cour_alf_damp;
-        F.l_full_sphere = P.l_full_sphere; F.n_r_LCR = P.n_r_LCR;
-        F.LFfac = P.LFfac; F.opm = P.opm; F.ViscHeatFac = P.ViscHeatFac; F.OhmLossFac = P.OhmLossFac; F.oek = P.oek; F.po = P.po;
-        F.prec_angle = P.prec_angle; F.dilution_fac = P.dilution_fac; F.ra = P.ra; F.opr = P.opr; F.omega_ma = P.omega_ma;
-        F.omega_ic = P.omega_ic; F.r_cmb = P.r_cmb; F.r_icb = P.r_icb; F.courfac = P.courfac; F.alffac = P.alffac; F.time = time;
-        a.gi = rl->gi; a.go = rl->go; a.gin = rl->buf.gin; a.gout = rl->buf.gout; a.n_lev = nl; a.nh = h->nh; a.n_phi = h->n_phi;
-        a.minc = h->minc; a.lev = d_lev; a.sinth = h->d_sinth; a.costh = h->d_costh; a.courmax = rl->buf.courmax;
-        a.ddw = P.l_full_sphere ? src[S_DDW] : nullptr;
-        a.ddb = (P.l_full_sphere && (P.l_mag || P.l_mag_LF)) ? src[S_DDB] : nullptr;
-        a.wgauss = h->d_wgauss; a.tq_partial = rl->d_tq_partial;
-        a.lm_max = h->lm_max; a.lm10 = 1; a.lm11 = (h->minc == 1 && h->m_max >= 1) ? h->lstart[1] : -1;
-        int gx = (int)((plane + NL_THREADS - 1) / NL_THREADS);
-        const bool mag = P.l_mag || P.l_mag_LF || P.l_mag_nl;
-        const bool extra = !P.l_adv_curl || P.l_anel || P.l_chemical_conv || P.l_precession || P.l_centrifuge;
-        launch_get_nl(a, mag, extra, gx, nl, h->stream);
-        courant_finish_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(rl->buf.courmax, d_lev, nl, out->dtrkc + l0, out->dthkc + l0,
-                                                                      rl->d_tq_partial, gx, P.LFfac, rl->d_torque);
-        h->launches += 2;
-        cudaEventRecord(rl->ev[4], h->stream);
-        if (run_analysis(h, rl->spec, L, rl->buf, d_lev, rl->ev + 5, false)) return 1;  // ev[5..7]; extraction is fused below
-        cudaEventRecord(rl->ev[8], h->stream);
-        // ---- get_td
-        TdArgs t{};
-        t.f.l_conv = P.l_conv; t.f.l_mag = P.l_mag; t.f.l_heat = P.l_heat; t.f.l_conv_nl = P.l_conv_nl; t.f.l_mag_nl = P.l_mag_nl;
-        t.f.l_mag_kin = P.l_mag_kin; t.f.l_anel = P.l_anel; t.f.l_corr = P.l_corr; t.f.l_double_curl = P.l_double_curl;
-        t.f.l_single_matrix = P.l_single_matrix; t.f.l_chemical_conv = P.l_chemical_conv; t.f.l_anelastic_liquid = P.l_anelastic_liquid;
-        t.f.CorFac = P.CorFac; t.f.epsc = P.epsc; t.f.epscXi = P.epscXi;
-        t.n_lev = nl; t.lm_max = h->lm_max; t.l_max = h->l_max; t.minc = h->minc; t.lm2l = h->d_lm2l; t.lm2m = h->d_lm2m; t.lev = d_lev;
-        // tile slots of the nonlinear_lm_t members inside the fused kernel: scalar-class columns first, then vector columns
-        const int nfs = (int)rl->spec.afield_s.size();
-        auto ns = [&](int slot) { return slot; };
-        auto nv = [&](int pair, int comp) { return pair < 0 ? -1 : nfs + 2 * pair + comp; };
-        TdSlots sl;
-        sl.s[0] = ns(rl->a_Advr); sl.s[1] = nv(rl->a_Adv, 0); sl.s[2] = nv(rl->a_Adv, 1);
-        sl.s[3] = ns(rl->a_VxBr); sl.s[4] = nv(rl->a_VxB, 0); sl.s[5] = nv(rl->a_VxB, 1);
-        sl.s[6] = nv(rl->a_VS, 0); sl.s[7] = ns(rl->a_VSr);
-        sl.s[8] = nv(rl->a_VXi, 0); sl.s[9] = ns(rl->a_VXir);
-        sl.s[10] = ns(rl->a_heat);
-        t.w = src[S_W]; t.dw = src[S_DW]; t.ddw = src[S_DDW]; t.z = src[S_Z]; t.dz = src[S_DZ];
-        auto o = [&](int i) -> double * { return op[i] ? op[i] + (size_t)l0 * lm2 : nullptr; };
-        t.dwdt = o(O_DWDT); t.dzdt = o(O_DZDT); t.dpdt = o(O_DPDT); t.dsdt = o(O_DSDT); t.dxidt = o(O_DXIDT); t.dbdt = o(O_DBDT);
-        t.djdt = o(O_DJDT); t.dVxVhLM = o(O_DVXVH); t.dVxBhLM = o(O_DVXBH); t.dVSrLM = o(O_DVSR); t.dVXirLM = o(O_DVXIR);
-        {
-            ExtractArgs e = make_extract_args(h, L, rl->buf, d_lev);
-            e.out_s = nullptr; e.out_v = nullptr;
-            const int nf = e.nf_s + 2 * e.npair;
-            // widest tile whose shared-memory footprint still lets several CTAs share an SM
-            auto smem = [&](int tl) { return (size_t)nf * nl * (tl + 1) * sizeof(double2); };
-            if (smem(32) <= 80 * 1024) extract_td_kernel<32><<<(h->lm_max + 31) / 32, 256, smem(32), h->stream>>>(e, t, sl);
-            else if (smem(16) <= 80 * 1024) extract_td_kernel<16><<<(h->lm_max + 15) / 16, 256, smem(16), h->stream>>>(e, t, sl);
-            else if (smem(8) <= 200 * 1024) extract_td_kernel<8><<<(h->lm_max + 7) / 8, 256, smem(8), h->stream>>>(e, t, sl);
-            else MFAIL("magic_rloop: level chunk too large for the fused get_td tile; lower level_chunk");
-            h->launches++;
-        }
-        cudaEventRecord(rl->ev[9], h->stream);
-        MCHECK(cudaGetLastError());
-        if (rl->hook_after && rl->hook_after((int)c)) return 1;
-        if (rl->pipelined) {  // results of this chunk go home while the next chunk computes
-            MCHECK(cudaEventRecord(rl->comp_done[c], h->stream));
-            MCHECK(cudaStreamWaitEvent(rl->s_down, rl->comp_done[c], 0));
-            const size_t off = (size_t)l0 * lm2, bytes = sizeof(double) * (size_t)nl * lm2;
-            for (int i = 0; i < O_COUNT; i++)
-                if (rl->need_out[i]) MCHECK(cudaMemcpyAsync(rl->host_out[i] + off, op[i] + off, bytes, cudaMemcpyDeviceToHost, rl->s_down));
-            MCHECK(cudaMemcpyAsync(rl->host_dtrkc + l0, out->dtrkc + l0, sizeof(double) * nl, cudaMemcpyDeviceToHost, rl->s_down));
-            MCHECK(cudaMemcpyAsync(rl->host_dthkc + l0, out->dthkc + l0, sizeof(double) * nl, cudaMemcpyDeviceToHost, rl->s_down));
-        }
-        {
-            // per-stage device times of this chunk (the sync also bounds the number of in-flight chunks)
-            MCHECK(cudaEventSynchronize(rl->ev[9]));
-            float ms;
-            const int pairs[7][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {5, 6}, {6, 7}, {7, 9}};
-            for (int s = 0; s < 7; s++) {
-                cudaEventElapsedTime(&ms, rl->ev[pairs[s][0]], rl->ev[pairs[s][1]]);
-                stage[s + 1] += ms;
-            }
-        }
+    return 0;
+}
+
+static int rloop_chunk(magic_rloop *rl, int c, const RunCtx &x) {
+    magic_sht *h = rl->h;
+    const magic_params &P = rl->p;
+    const size_t lm2 = 2 * (size_t)h->lm_max;
+    const size_t plane = (size_t)h->nh * h->n_phi;
+    const int l0 = rl->chunk_start[c], nl = rl->chunk_size[c];
+    const Layout *Lp = nullptr;
+    for (size_t i = 0; i < rl->lay_sizes.size(); i++)
+        if (rl->lay_sizes[i] == nl) Lp = &rl->lays[i];
+    if (!Lp) MFAIL("magic_rloop: internal: no layout for this chunk size");
+    const Layout &L = *Lp;
+    cudaEvent_t *ev = rl->cev.data() + 10 * (size_t)c;
+    const LevelInfo *d_lev = rl->d_lev + l0;
+    const double *src[MAGIC_MAX_SRC];
+    for (int i = 0; i < MAGIC_MAX_SRC; i++) src[i] = (i < S_COUNT && x.ip[i]) ? x.ip[i] + (size_t)l0 * lm2 : nullptr;
+    if (run_synthesis(h, rl->spec, L, rl->buf, src, d_lev, ev)) return 1;  // ev[0..3]
+    // ---- get_nl + Courant
+    MCHECK(cudaMemsetAsync(rl->buf.courmax, 0, sizeof(unsigned long long) * 2 * nl, h->stream));
+    NlArgs a{};
+    NlFlags &F = a.f;
+    F.l_conv_nl = P.l_conv_nl; F.l_heat_nl = P.l_heat_nl; F.l_mag_nl = P.l_mag_nl; F.l_mag_LF = P.l_mag_LF; F.l_mag = P.l_mag;
+    F.l_mag_kin = P.l_mag_kin; F.l_adv_curl = P.l_adv_curl; F.l_anel = P.l_anel; F.l_chemical_conv = P.l_chemical_conv;
+    F.l_precession = P.l_precession; F.l_centrifuge = P.l_centrifuge; F.l_cour_alf_damp = P.l_cour_alf_damp;
+    F.l_full_sphere = P.l_full_sphere; F.n_r_LCR = P.n_r_LCR;
+    F.LFfac = P.LFfac; F.opm = P.opm; F.ViscHeatFac = P.ViscHeatFac; F.OhmLossFac = P.OhmLossFac; F.oek = P.oek; F.po = P.po;
+    F.prec_angle = P.prec_angle; F.dilution_fac = P.dilution_fac; F.ra = P.ra; F.opr = P.opr; F.omega_ma = P.omega_ma;
+    F.omega_ic = P.omega_ic; F.r_cmb = P.r_cmb; F.r_icb = P.r_icb; F.courfac = P.courfac; F.alffac = P.alffac; F.time = x.time;
+    a.gi = rl->gi; a.go = rl->go; a.gin = rl->buf.gin; a.gout = rl->buf.gout; a.n_lev = nl; a.nh = h->nh; a.n_phi = h->n_phi;
+    a.minc = h->minc; a.lev = d_lev; a.sinth = h->d_sinth; a.costh = h->d_costh; a.courmax = rl->buf.courmax;
+    a.ddw = P.l_full_sphere ? src[S_DDW] : nullptr;
+    a.ddb = (P.l_full_sphere && (P.l_mag || P.l_mag_LF)) ? src[S_DDB] : nullptr;
+    a.wgauss = h->d_wgauss; a.tq_partial = rl->d_tq_partial;
+    a.lm_max = h->lm_max; a.lm10 = 1; a.lm11 = (h->minc == 1 && h->m_max >= 1) ? h->lstart[1] : -1;
+    int gx = (int)((plane + NL_THREADS - 1) / NL_THREADS);
+    const bool mag = P.l_mag || P.l_mag_LF || P.l_mag_nl;
+    const bool extra = !P.l_adv_curl || P.l_anel || P.l_chemical_conv || P.l_precession || P.l_centrifuge;
+    launch_get_nl(a, mag, extra, gx, nl, h->stream);
+    courant_finish_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(rl->buf.courmax, d_lev, nl, x.dtrkc + l0, x.dthkc + l0,
+                                                                  rl->d_tq_partial, gx, P.LFfac, rl->d_torque);
+    h->launches += 2;
+    cudaEventRecord(ev[4], h->stream);
+    if (run_analysis(h, rl->spec, L, rl->buf, d_lev, ev + 5, false)) return 1;  // ev[5..7]; extraction is fused below
+    // ---- get_td
+    TdArgs t{};
+    t.f.l_conv = P.l_conv; t.f.l_mag = P.l_mag; t.f.l_heat = P.l_heat; t.f.l_conv_nl = P.l_conv_nl; t.f.l_mag_nl = P.l_mag_nl;
+    t.f.l_mag_kin = P.l_mag_kin; t.f.l_anel = P.l_anel; t.f.l_corr = P.l_corr; t.f.l_double_curl = P.l_double_curl;
+    t.f.l_single_matrix = P.l_single_matrix; t.f.l_chemical_conv = P.l_chemical_conv; t.f.l_anelastic_liquid = P.l_anelastic_liquid;
+    t.f.CorFac = P.CorFac; t.f.epsc = P.epsc; t.f.epscXi = P.epscXi;
+    t.n_lev = nl; t.lm_max = h->lm_max; t.l_max = h->l_max; t.minc = h->minc; t.lm2l = h->d_lm2l; t.lm2m = h->d_lm2m; t.lev = d_lev;
+    // tile slots of the nonlinear_lm_t members inside the fused kernel: scalar-class columns first, then vector columns
+    const int nfs = (int)rl->spec.afield_s.size();
+    auto ns = [&](int slot) { return slot; };
+    auto nv = [&](int pair, int comp) { return pair < 0 ? -1 : nfs + 2 * pair + comp; };
+    TdSlots sl;
+    sl.s[0] = ns(rl->a_Advr); sl.s[1] = nv(rl->a_Adv, 0); sl.s[2] = nv(rl->a_Adv, 1);
+    sl.s[3] = ns(rl->a_VxBr); sl.s[4] = nv(rl->a_VxB, 0); sl.s[5] = nv(rl->a_VxB, 1);
+    sl.s[6] = nv(rl->a_VS, 0); sl.s[7] = ns(rl->a_VSr);
+    sl.s[8] = nv(rl->a_VXi, 0); sl.s[9] = ns(rl->a_VXir);
+    sl.s[10] = ns(rl->a_heat);
+    t.w = src[S_W]; t.dw = src[S_DW]; t.ddw = src[S_DDW]; t.z = src[S_Z]; t.dz = src[S_DZ];
+    auto o = [&](int i) -> double * { return x.op[i] ? x.op[i] + (size_t)l0 * lm2 : nullptr; };
+    t.dwdt = o(O_DWDT); t.dzdt = o(O_DZDT); t.dpdt = o(O_DPDT); t.dsdt = o(O_DSDT); t.dxidt = o(O_DXIDT); t.dbdt = o(O_DBDT);
+    t.djdt = o(O_DJDT); t.dVxVhLM = o(O_DVXVH); t.dVxBhLM = o(O_DVXBH); t.dVSrLM = o(O_DVSR); t.dVXirLM = o(O_DVXIR);
+    {
+        ExtractArgs e = make_extract_args(h, L, rl->buf, d_lev);
+        e.out_s = nullptr; e.out_v = nullptr;
+        const int nf = e.nf_s + 2 * e.npair;
+        // widest tile whose shared-memory footprint still lets several CTAs share an SM
+        auto smem = [&](int tl) { return (size_t)nf * nl * (tl + 1) * sizeof(double2); };
+        if (smem(32) <= 80 * 1024) extract_td_kernel<32><<<(h->lm_max + 31) / 32, 256, smem(32), h->stream>>>(e, t, sl);
+        else if (smem(16) <= 80 * 1024) extract_td_kernel<16><<<(h->lm_max + 15) / 16, 256, smem(16), h->stream>>>(e, t, sl);
+        else if (smem(8) <= 200 * 1024) extract_td_kernel<8><<<(h->lm_max + 7) / 8, 256, smem(8), h->stream>>>(e, t, sl);
+        else MFAIL("magic_rloop: level chunk too large for the fused get_td tile; lower level_chunk");
+        h->launches++;
     }
+    cudaEventRecord(ev[9], h->stream);
+    MCHECK(cudaGetLastError());
+    return 0;
+}
+
+static int rloop_end(magic_rloop *rl, const magic_fields_in *in) {
+    magic_sht *h = rl->h;
+    const size_t lm2 = 2 * (size_t)h->lm_max;
     for (int w = 0; w < 2; w++) {  // get_br_v_bcs on the boundary levels (rIter.f90:267-277)
         const int i = rl->bc_lev[w];
         if (i < 0) continue;
@@ -462,23 +505,48 @@ extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, c
     MCHECK(cudaEventSynchronize(rl->ev[14]));
     rl->torque[0] = rl->h_torque[0];
     rl->torque[1] = rl->h_torque[1];
-    float tot;
-    cudaEventElapsedTime(&tot, rl->ev[15], rl->ev[14]);
-    stage[0] = tot;
+    // per-stage device times of the run: 0 total, 1 prep, 2 Legendre synthesis, 3 c2r, 4 get_nl, 5 r2c, 6 Legendre analysis, 7 get_td
+    double stage[8] = {0};
+    float ms;
+    const int pairs[7][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {5, 6}, {6, 7}, {7, 9}};
+    for (size_t c = 0; c < rl->chunk_start.size(); c++)
+        for (int s = 0; s < 7; s++) {
+            cudaEventElapsedTime(&ms, rl->cev[10 * c + pairs[s][0]], rl->cev[10 * c + pairs[s][1]]);
+            stage[s + 1] += ms;
+        }
+    cudaEventElapsedTime(&ms, rl->ev[15], rl->ev[14]);
+    stage[0] = ms;
     for (int i = 0; i < 8; i++) rl->timing[i] = stage[i];
+    // what the pipelined calls could not hide: run start -> first kernel of the first chunk, last kernel of the last chunk -> end
+    const size_t nc = rl->chunk_start.size();
+    cudaEventElapsedTime(&ms, rl->ev[15], rl->cev[0]);
+    rl->exposed[0] = ms;
+    cudaEventElapsedTime(&ms, rl->cev[10 * (nc - 1) + 9], rl->ev[14]);
+    rl->exposed[1] = ms;
     return 0;
 }
 
-static void try_register(magic_rloop *rl, const void *p, size_t bytes) {
-    if (!p || bytes < (size_t)8 << 20) return;  // small arrays: staged (pageable) copies are cheaper than pinning
-    for (const void *q : rl->seen)
-        if (q == p) return;  // tried before (registered, or already pinned by the caller)
-    rl->seen.push_back(p);
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return;  // already pinned
-    cudaGetLastError();
-    if (cudaHostRegister((void *)p, bytes, cudaHostRegisterDefault) == cudaSuccess) rl->registered.push_back(p);
-    else cudaGetLastError();  // not registrable: plain pageable copies still work
+extern "C" int magic_rloop_run_dev(magic_rloop *rl, const magic_fields_in *in, const magic_fields_out *out, double time) {
+    if (!rl || !in || !out) MFAIL("magic_rloop_run_dev: null argument");
+    magic_sht *h = rl->h;
+    RunCtx x;
+    if (rloop_begin(rl, in, out, time, x)) return 1;
+    const size_t lm2 = 2 * (size_t)h->lm_max;
+    for (size_t c = 0; c < rl->chunk_start.size(); c++) {
+        const int l0 = rl->chunk_start[c], nl = rl->chunk_size[c];
+        if (rl->pipelined) MCHECK(cudaStreamWaitEvent(h->stream, rl->up_done[c], 0));
+        if (rloop_chunk(rl, (int)c, x)) return 1;
+        if (rl->pipelined) {  // results of this chunk go home while the next chunk computes
+            MCHECK(cudaEventRecord(rl->comp_done[c], h->stream));
+            MCHECK(cudaStreamWaitEvent(rl->s_down, rl->comp_done[c], 0));
+            const size_t off = (size_t)l0 * lm2, bytes = sizeof(double) * (size_t)nl * lm2;
+            for (int i = 0; i < O_COUNT; i++)
+                if (rl->need_out[i]) MCHECK(cudaMemcpyAsync(rl->host_out[i] + off, x.op[i] + off, bytes, cudaMemcpyDeviceToHost, rl->s_down));
+            MCHECK(cudaMemcpyAsync(rl->host_dtrkc + l0, x.dtrkc + l0, sizeof(double) * nl, cudaMemcpyDeviceToHost, rl->s_down));
+            MCHECK(cudaMemcpyAsync(rl->host_dthkc + l0, x.dthkc + l0, sizeof(double) * nl, cudaMemcpyDeviceToHost, rl->s_down));
+        }
+    }
+    return rloop_end(rl, in);
 }
 
 extern "C" int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const magic_fields_out *out, double time) {
@@ -498,7 +566,6 @@ extern "C" int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const
         if (!rl->need_in[i]) continue;
         if (!ip[i]) MFAIL("magic_rloop_run: a required input field is null");
         if (!rl->d_in[i]) MCHECK(cudaMalloc((void **)&rl->d_in[i], fbytes));
-        try_register(rl, ip[i], fbytes);
         rl->host_in[i] = ip[i];
         dip[i] = rl->d_in[i];
     }
@@ -519,7 +586,6 @@ extern "C" int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const
             MCHECK(cudaMalloc((void **)&rl->d_out[i], fbytes));
             MCHECK(cudaMemsetAsync(rl->d_out[i], 0, fbytes, h->stream));
         }
-        try_register(rl, op[i], fbytes);
         rl->host_out[i] = op[i];
         dop[i] = rl->d_out[i];
     }
@@ -538,152 +604,313 @@ extern "C" int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const
     return 0;
 }
 
-// ---- LM containers in, LM containers out: transposes pipelined against the level chunks ---------------------------------
+// Page-locking of caller-owned host arrays is explicit (opt in, opt out): the host registers its PERSISTENT containers once
+// (the Fortran shim does so for the arrays of fields.f90 / dt_fieldsLast.f90) and must unpin them before freeing them.  The
+// run calls never pin anything themselves: a temporary that is freed while still registered would leave a stale
+// registration behind, and a later allocation at the same address would be treated as pinned against the old pages.
+extern "C" int magic_rloop_pin_host(magic_rloop *rl, const void *ptr, size_t bytes) {
+    if (!rl || !ptr || bytes == 0) MFAIL("magic_rloop_pin_host: null argument");
+    MCHECK(cudaSetDevice(rl->h->dev));
+    for (const auto &r : rl->registered)
+        if (r.first == ptr) {
+            if (r.second == bytes) return 0;
+            MFAIL("magic_rloop_pin_host: this address is already pinned with another size; unpin it first");
+        }
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost) return 0;  // pinned by its owner
+    cudaGetLastError();
+    MCHECK(cudaHostRegister((void *)ptr, bytes, cudaHostRegisterDefault));
+    rl->registered.emplace_back(ptr, bytes);
+    return 0;
+}
+extern "C" int magic_rloop_unpin_host(magic_rloop *rl, const void *ptr) {
+    if (!rl || !ptr) MFAIL("magic_rloop_unpin_host: null argument");
+    MCHECK(cudaSetDevice(rl->h->dev));
+    for (size_t i = 0; i < rl->registered.size(); i++)
+        if (rl->registered[i].first == ptr) {
+            MCHECK(cudaHostUnregister((void *)ptr));
+            rl->registered.erase(rl->registered.begin() + i);
+            return 0;
+        }
+    MFAIL("magic_rloop_unpin_host: this address was not pinned through magic_rloop_pin_host");
+}
+
+
+// ---- LM-distributed containers in, LM-distributed explicit terms out: the whole of step_time.f90:485-612 in one call,
+//      the transposes (and, for host containers, the PCIe transfers) pipelined level chunk by level chunk ----------------
+// Containers (fields.f90:211-268, dt_fieldsLast.f90:125-214), k = 0..3:
+//   in : flow(w,dw,ddw,z,dz)  s(s,ds)  field(b,db,ddb,aj,dj)  xi(xi,dxi)
+//   out: dflowdt(dwdt,dzdt,dpdt[,dVxVhLM])  dsdt(dsdt,dVSrLM)  dbdt(dbdt,djdt,dVxBhLM)  dxidt(dxidt,dVXirLM)
 struct LmPipe {
     magic_transp *parent = nullptr;
     std::vector<magic_transp *> parts;  // one per global chunk index
-    cudaStream_t comm = nullptr;
-    std::vector<cudaEvent_t> ev_in, ev_out;
-    cudaEvent_t ev_start = nullptr, ev_done = nullptr;
-    double *R[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // flow, s, field, dflowdt, dsdt, dbdt (R-distributed)
-    int C = 0;
+    cudaStream_t comm = nullptr, s_up = nullptr, s_down = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_out, ev_up, ev_lmout;
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_ready = nullptr;
+    int nf_in[4] = {0, 0, 0, 0}, nf_out[4] = {0, 0, 0, 0};   // container widths as the host declares them (0 = absent)
+    int nt_in[4] = {0, 0, 0, 0};                             // leading fields of each inbound container the loop really reads
+    double *R_in[4] = {nullptr, nullptr, nullptr, nullptr}, *R_out[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *LM_in[4] = {nullptr, nullptr, nullptr, nullptr}, *LM_out[4] = {nullptr, nullptr, nullptr, nullptr};  // host-pointer entry only
+    int C = 0, n_procs = 1, rank = 0, n_r_max = 0, nlm = 0;
+    std::vector<int> rs;                   // 0-based first level of every rank
+    std::vector<std::vector<int>> cs, cz;  // level chunks of every rank (start inside the slab, size)
+    // radial matrices of the host's radial scheme (magic_rloop_set_radial_matrices) for the LM-side prologue / epilogue
+    double *d_D1 = nullptr, *d_D2 = nullptr;
+    int ldD = 0;
+    GemmProb *d_dprobs = nullptr;
+    int2 *d_dtiles = nullptr;
+    int n_dtiles = 0;
+    double *d_work = nullptr;              // [3][n_r_max][nlm] radial derivatives of dVSrLM, dVxBhLM, dVxVhLM
+    double *d_lmrad = nullptr;             // [4][n_r_max]: or2, orho1, dentropy0, l_R (as doubles)
+    int *d_lo2l = nullptr;                 // degree of every local mode (lo order)
 };
-static const int LM_NF[6] = {5, 2, 5, 3, 2, 3};
 
 static void lmpipe_free(LmPipe *p) {
     if (!p) return;
     for (auto t : p->parts) magic_transp_destroy(t);
-    for (auto e : p->ev_in) cudaEventDestroy(e);
-    for (auto e : p->ev_out) cudaEventDestroy(e);
-    if (p->ev_start) cudaEventDestroy(p->ev_start);
-    if (p->ev_done) cudaEventDestroy(p->ev_done);
-    if (p->comm) cudaStreamDestroy(p->comm);
-    for (int i = 0; i < 6; i++) cudaFree(p->R[i]);
+    for (auto *v : {&p->ev_in, &p->ev_out, &p->ev_up, &p->ev_lmout})
+        for (auto e : *v) cudaEventDestroy(e);
+    for (cudaEvent_t e : {p->ev_start, p->ev_done, p->ev_ready})
+        if (e) cudaEventDestroy(e);
+    for (cudaStream_t s : {p->comm, p->s_up, p->s_down})
+        if (s) cudaStreamDestroy(s);
+    for (int i = 0; i < 4; i++) { cudaFree(p->R_in[i]); cudaFree(p->R_out[i]); cudaFree(p->LM_in[i]); cudaFree(p->LM_out[i]); }
+    cudaFree(p->d_D1); cudaFree(p->d_D2); cudaFree(p->d_dprobs); cudaFree(p->d_dtiles); cudaFree(p->d_work); cudaFree(p->d_lmrad);
+    cudaFree(p->d_lo2l);
     delete p;
 }
 
 static int lmpipe_build(magic_rloop *rl, magic_transp *t) {
     magic_sht *h = rl->h;
+    const magic_params &P = rl->p;
     int rank, n_procs, n_r_max, nf;
     if (magic_transp_info(t, &rank, &n_procs, &n_r_max, &nf)) return 1;
-    if (nf < 5) MFAIL("magic_rloop_run_lm_dev: the transposer must serve containers of 5 fields");
+    if (nf < 5) MFAIL("magic_rloop_run_lm: the transposer must serve containers of 5 fields");
     int llm, ulm, nRstart, nRstop;
     if (magic_transp_extents(t, &llm, &ulm, &nRstart, &nRstop)) return 1;
-    if (nRstop - nRstart + 1 != rl->n_r_loc) MFAIL("magic_rloop_run_lm_dev: the loop and the transposer disagree on the radial slab");
-    lmpipe_free(rl->lmpipe);
+    if (nRstop - nRstart + 1 != rl->n_r_loc) MFAIL("magic_rloop_run_lm: the loop and the transposer disagree on the radial slab");
+    LmPipe *old = rl->lmpipe;
     LmPipe *p = new LmPipe();
-    rl->lmpipe = p;
-    p->parent = t;
-    const size_t lm2 = 2 * (size_t)h->lm_max;
-    for (int i = 0; i < 6; i++) {
-        if ((i == 2 || i == 5) && !rl->p.l_mag) continue;
-        MCHECK(cudaMalloc((void **)&p->R[i], sizeof(double) * lm2 * rl->n_r_loc * LM_NF[i]));
-        MCHECK(cudaMemsetAsync(p->R[i], 0, sizeof(double) * lm2 * rl->n_r_loc * LM_NF[i], h->stream));
+    if (old) {  // keep the radial matrices across a rebuild
+        p->d_D1 = old->d_D1; p->d_D2 = old->d_D2; p->ldD = old->ldD; p->d_lmrad = old->d_lmrad;
+        old->d_D1 = old->d_D2 = old->d_lmrad = nullptr;
+        lmpipe_free(old);
     }
-    if (n_procs == 1) return 0;
-    // the chunks of every rank (same rule, same level_chunk everywhere); C = the largest chunk count
+    rl->lmpipe = p;
+    p->parent = t; p->n_procs = n_procs; p->rank = rank; p->n_r_max = n_r_max; p->nlm = ulm - llm + 1;
+    const bool flow = P.l_conv || P.l_mag_kin, mag = P.l_mag || P.l_mag_LF;
+    if (!flow) MFAIL("magic_rloop_run_lm: a run without the flow containers is not supported");
+    p->nf_in[0] = 5; p->nt_in[0] = 5;
+    if (P.l_heat) { p->nf_in[1] = 2; p->nt_in[1] = 1; }           // ds is not read by the radial loop
+    if (mag) { p->nf_in[2] = 5; p->nt_in[2] = 5; }
+    if (P.l_chemical_conv) { p->nf_in[3] = 2; p->nt_in[3] = 1; }
+    if (P.l_conv) p->nf_out[0] = P.l_double_curl ? 4 : 3;
+    if (P.l_heat) p->nf_out[1] = 2;
+    if (P.l_mag) p->nf_out[2] = 3;
+    if (P.l_chemical_conv) p->nf_out[3] = 2;
+    const size_t fld = 2 * (size_t)h->lm_max * rl->n_r_loc;
+    for (int k = 0; k < 4; k++) {
+        if (p->nf_in[k]) {
+            MCHECK(cudaMalloc((void **)&p->R_in[k], sizeof(double) * fld * p->nf_in[k]));
+            MCHECK(cudaMemsetAsync(p->R_in[k], 0, sizeof(double) * fld * p->nf_in[k], h->stream));
+        }
+        if (p->nf_out[k]) {
+            MCHECK(cudaMalloc((void **)&p->R_out[k], sizeof(double) * fld * p->nf_out[k]));
+            MCHECK(cudaMemsetAsync(p->R_out[k], 0, sizeof(double) * fld * p->nf_out[k], h->stream));
+        }
+    }
+    // the level chunks of every rank: same rule and same (unclamped) level_chunk everywhere, tapered when the transposes
+    // cross NVLink (MAGIC_LM_TAPER, default 4 levels; 0 = off)
     std::vector<int> rs(n_procs), re(n_procs);
     if (magic_get_blocks(n_r_max, n_procs, rs.data(), re.data())) return 1;
-    std::vector<std::vector<int>> cs(n_procs), cz(n_procs);
+    int taper = n_procs > 1 ? 4 : 0;
+    if (const char *e = getenv("MAGIC_LM_TAPER")) taper = atoi(e);
+    p->rs.resize(n_procs);
+    p->cs.assign(n_procs, {});
+    p->cz.assign(n_procs, {});
     for (int q = 0; q < n_procs; q++) {
-        level_chunks(re[q] - rs[q] + 1, rl->level_chunk, cs[q], cz[q]);
-        p->C = std::max(p->C, (int)cs[q].size());
+        p->rs[q] = rs[q] - 1;
+        level_chunks_tapered(re[q] - rs[q] + 1, rl->level_chunk_req, taper, p->cs[q], p->cz[q]);
+        p->C = std::max(p->C, (int)p->cs[q].size());
     }
-    if (cs[rank] != rl->chunk_start || cz[rank] != rl->chunk_size) MFAIL("magic_rloop_run_lm_dev: internal chunk mismatch");
-    {   // highest priority: the compute kernels fill every SM with long grids, so the pack / NCCL / unpack CTAs of the
+    if (p->cs[rank] != rl->chunk_start || p->cz[rank] != rl->chunk_size)
+        if (rloop_set_chunks(rl, p->cs[rank], p->cz[rank])) return 1;
+    {   // highest priority: the compute kernels fill every SM with long grids, so the pack / exchange / unpack CTAs of the
         // communication stream must be picked first whenever a slot frees up or they trail behind the chunk they serve
         int lo = 0, hi = 0;
         MCHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         MCHECK(cudaStreamCreateWithPriority(&p->comm, cudaStreamNonBlocking, hi));
+        MCHECK(cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking));
+        MCHECK(cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking));
     }
     MCHECK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
     MCHECK(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
+    MCHECK(cudaEventCreateWithFlags(&p->ev_ready, cudaEventDisableTiming));
     for (int c = 0; c < p->C; c++) {
         std::vector<int> off(n_procs), cnt(n_procs);
         for (int q = 0; q < n_procs; q++) {
-            const bool has = c < (int)cs[q].size();
-            off[q] = has ? cs[q][c] : re[q] - rs[q] + 1;
-            cnt[q] = has ? cz[q][c] : 0;
+            const bool has = c < (int)p->cs[q].size();
+            off[q] = has ? p->cs[q][c] : re[q] - rs[q] + 1;
+            cnt[q] = has ? p->cz[q][c] : 0;
         }
         magic_transp *part = nullptr;
         if (magic_transp_create_part(t, off.data(), cnt.data(), &part)) return 1;
         magic_transp_set_stream(part, (void *)p->comm);
         p->parts.push_back(part);
-        cudaEvent_t e;
-        MCHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        p->ev_in.push_back(e);
-        MCHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        p->ev_out.push_back(e);
+        for (auto *v : {&p->ev_in, &p->ev_out, &p->ev_up, &p->ev_lmout}) {
+            cudaEvent_t e;
+            MCHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            v->push_back(e);
+        }
     }
+    return 0;
+}
+
+// host <-> device rows of part c of an LM-distributed container ([nf][n_r_max][nlm] complex): for every rank q the levels of
+// q's c-th chunk, all nf fields of one rank in one strided copy
+static int lm_rows_copy(LmPipe *p, int c, int nf, double *dst, const double *src, cudaMemcpyKind kind, cudaStream_t st) {
+    const size_t row = sizeof(double) * 2 * (size_t)p->nlm, pitch = row * p->n_r_max;
+    for (int q = 0; q < p->n_procs; q++) {
+        if (c >= (int)p->cs[q].size() || p->cz[q][c] == 0) continue;
+        const size_t off = (size_t)(p->rs[q] + p->cs[q][c]) * 2 * (size_t)p->nlm;
+        MCHECK(cudaMemcpy2DAsync(dst + off, pitch, src + off, pitch, row * p->cz[q][c], nf, kind, st));
+    }
+    return 0;
+}
+
+struct LmHostIO {  // host containers of magic_rloop_run_lm (null for the device-pointer call)
+    const double *in[4];
+    double *out[4];
+};
+
+static int lm_run(magic_rloop *rl, magic_transp *t, const double *const lm_in[4], double *const lm_out[4], double *dtrkc, double *dthkc,
+                  double time, const LmHostIO *io) {
+    magic_sht *h = rl->h;
+    MCHECK(cudaSetDevice(h->dev));
+    if (!rl->lmpipe || rl->lmpipe->parent != t)
+        if (lmpipe_build(rl, t)) return 1;
+    LmPipe *p = rl->lmpipe;
+    const magic_params &P = rl->p;
+    for (int k = 0; k < 4; k++) {
+        if (p->nf_in[k] && !lm_in[k]) MFAIL("magic_rloop_run_lm: a required inbound container is null");
+        if (p->nf_out[k] && !lm_out[k]) MFAIL("magic_rloop_run_lm: a required outbound container is null");
+    }
+    const size_t fld = 2 * (size_t)h->lm_max * rl->n_r_loc;  // doubles per R-distributed field
+    magic_fields_in fin{};
+    magic_fields_out fout{};
+    fin.w = p->R_in[0]; fin.dw = p->R_in[0] + fld; fin.ddw = p->R_in[0] + 2 * fld; fin.z = p->R_in[0] + 3 * fld; fin.dz = p->R_in[0] + 4 * fld;
+    if (p->nf_in[1]) { fin.s = p->R_in[1]; fin.ds = p->R_in[1] + fld; }
+    if (p->nf_in[2]) { fin.b = p->R_in[2]; fin.db = p->R_in[2] + fld; fin.ddb = p->R_in[2] + 2 * fld; fin.aj = p->R_in[2] + 3 * fld; fin.dj = p->R_in[2] + 4 * fld; }
+    if (p->nf_in[3]) fin.xi = p->R_in[3];
+    if (p->nf_out[0]) {
+        fout.dwdt = p->R_out[0]; fout.dzdt = p->R_out[0] + fld; fout.dpdt = p->R_out[0] + 2 * fld;
+        if (P.l_double_curl) fout.dVxVhLM = p->R_out[0] + 3 * fld;
+    }
+    if (p->nf_out[1]) { fout.dsdt = p->R_out[1]; fout.dVSrLM = p->R_out[1] + fld; }
+    if (p->nf_out[2]) { fout.dbdt = p->R_out[2]; fout.djdt = p->R_out[2] + fld; fout.dVxBhLM = p->R_out[2] + 2 * fld; }
+    if (p->nf_out[3]) { fout.dxidt = p->R_out[3]; fout.dVXirLM = p->R_out[3] + fld; }
+    fout.dtrkc = dtrkc; fout.dthkc = dthkc;
+    RunCtx x;
+    if (rloop_begin(rl, &fin, &fout, time, x)) return 1;
+    // the transposes start once everything queued on the compute stream so far (the previous step) is done
+    MCHECK(cudaEventRecord(p->ev_start, h->stream));
+    MCHECK(cudaStreamWaitEvent(p->comm, p->ev_start, 0));
+    if (io) {
+        MCHECK(cudaStreamWaitEvent(p->s_up, p->ev_start, 0));
+        MCHECK(cudaStreamWaitEvent(p->s_down, p->ev_start, 0));
+    }
+    auto inbound = [&](int c) -> int {
+        if (io) {  // PCIe: the rows of this part, only the fields the loop reads
+            for (int k = 0; k < 4; k++)
+                if (p->nf_in[k] && lm_rows_copy(p, c, p->nt_in[k], p->LM_in[k], io->in[k], cudaMemcpyHostToDevice, p->s_up)) return 1;
+            MCHECK(cudaEventRecord(p->ev_up[c], p->s_up));
+            MCHECK(cudaStreamWaitEvent(p->comm, p->ev_up[c], 0));
+        }
+        for (int k = 0; k < 4; k++)
+            if (p->nf_in[k] && magic_transp_lm2r_dev_n(p->parts[c], p->nt_in[k], lm_in[k], p->R_in[k])) return 1;
+        MCHECK(cudaEventRecord(p->ev_in[c], p->comm));
+        return 0;
+    };
+    auto outbound = [&](int c, bool computed) -> int {
+        if (computed) {
+            MCHECK(cudaEventRecord(p->ev_out[c], h->stream));
+            MCHECK(cudaStreamWaitEvent(p->comm, p->ev_out[c], 0));
+        }
+        for (int k = 0; k < 4; k++)
+            if (p->nf_out[k] && magic_transp_r2lm_dev_n(p->parts[c], p->nf_out[k], p->R_out[k], lm_out[k])) return 1;
+        if (io) {
+            MCHECK(cudaEventRecord(p->ev_lmout[c], p->comm));
+            MCHECK(cudaStreamWaitEvent(p->s_down, p->ev_lmout[c], 0));
+            for (int k = 0; k < 4; k++)
+                if (p->nf_out[k] && lm_rows_copy(p, c, p->nf_out[k], io->out[k], p->LM_out[k], cudaMemcpyDeviceToHost, p->s_down)) return 1;
+        }
+        return 0;
+    };
+    // Queue order on the communication stream -- identical on every rank, also for ranks with fewer chunks than C (they have
+    // no levels in the late parts, their peers do): in(0) .. in(DIST-1), then per chunk c: in(c+DIST), [compute c], out(c).
+    const int DIST = 2, nloc = (int)rl->chunk_start.size();
+    for (int c = 0; c < std::min(DIST, p->C); c++)
+        if (inbound(c)) return 1;
+    for (int c = 0; c < p->C; c++) {
+        if (c + DIST < p->C && inbound(c + DIST)) return 1;
+        if (c < nloc) {
+            MCHECK(cudaStreamWaitEvent(h->stream, p->ev_in[c], 0));
+            if (rloop_chunk(rl, c, x)) return 1;
+        }
+        if (outbound(c, c < nloc)) return 1;
+    }
+    MCHECK(cudaEventRecord(p->ev_done, p->comm));
+    MCHECK(cudaStreamWaitEvent(h->stream, p->ev_done, 0));
+    if (rloop_end(rl, &fin)) return 1;
     return 0;
 }
 
 extern "C" int magic_rloop_run_lm_dev(magic_rloop *rl, magic_transp *t, const magic_lm_in *in, const magic_lm_out *out, double time) {
     if (!rl || !t || !in || !out) MFAIL("magic_rloop_run_lm_dev: null argument");
+    if (!out->dtrkc || !out->dthkc) MFAIL("magic_rloop_run_lm_dev: dtrkc/dthkc are null");
+    const double *li[4] = {in->flow, in->s, in->field, in->xi};
+    double *lo[4] = {out->dflowdt, out->dsdt, out->dbdt, out->dxidt};
+    return lm_run(rl, t, li, lo, out->dtrkc, out->dthkc, time, nullptr);
+}
+
+// Host containers in, host containers out: what a type_mpicuda + rIter_cuda_t pair of the Fortran host calls instead of
+// transp_LMloc_to_Rloc / radialLoopG / transp_Rloc_to_LMloc (step_time.f90:485-612).  Inside: H2D of the rows of level chunk
+// c+2, NVLink transposes of chunk c+1, compute of chunk c, transposes and D2H of chunk c-1 all overlap.
+extern "C" int magic_rloop_run_lm(magic_rloop *rl, magic_transp *t, const magic_lm_in *in, const magic_lm_out *out, double time) {
+    if (!rl || !t || !in || !out) MFAIL("magic_rloop_run_lm: null argument");
+    if (!out->dtrkc || !out->dthkc) MFAIL("magic_rloop_run_lm: dtrkc/dthkc are null");
     magic_sht *h = rl->h;
     MCHECK(cudaSetDevice(h->dev));
-    const magic_params &P = rl->p;
-    if (P.l_double_curl || P.l_chemical_conv || !P.l_heat || !P.l_conv)
-        MFAIL("magic_rloop_run_lm_dev: supported field set is heat + flow (+ magnetic field) in the pressure formulation; "
-              "use magic_transp_* and magic_rloop_run_dev for other sets");
-    if (!in->flow || !in->s || !out->dflowdt || !out->dsdt || !out->dtrkc || !out->dthkc || (P.l_mag && (!in->field || !out->dbdt)))
-        MFAIL("magic_rloop_run_lm_dev: a required container is null");
     if (!rl->lmpipe || rl->lmpipe->parent != t)
         if (lmpipe_build(rl, t)) return 1;
     LmPipe *p = rl->lmpipe;
-    const size_t fld = 2 * (size_t)h->lm_max * rl->n_r_loc;  // doubles per R-distributed field
-    magic_fields_in fin{};
-    magic_fields_out fout{};
-    fin.w = p->R[0]; fin.dw = p->R[0] + fld; fin.ddw = p->R[0] + 2 * fld; fin.z = p->R[0] + 3 * fld; fin.dz = p->R[0] + 4 * fld;
-    fin.s = p->R[1]; fin.ds = p->R[1] + fld;
-    fout.dwdt = p->R[3]; fout.dzdt = p->R[3] + fld; fout.dpdt = p->R[3] + 2 * fld;
-    fout.dsdt = p->R[4]; fout.dVSrLM = p->R[4] + fld;
-    if (P.l_mag) {
-        fin.b = p->R[2]; fin.db = p->R[2] + fld; fin.ddb = p->R[2] + 2 * fld; fin.aj = p->R[2] + 3 * fld; fin.dj = p->R[2] + 4 * fld;
-        fout.dbdt = p->R[5]; fout.djdt = p->R[5] + fld; fout.dVxBhLM = p->R[5] + 2 * fld;
-    }
-    fout.dtrkc = out->dtrkc; fout.dthkc = out->dthkc;
-    const double *lm_in[3] = {in->flow, in->s, P.l_mag ? in->field : nullptr};
-    double *lm_out[3] = {out->dflowdt, out->dsdt, P.l_mag ? out->dbdt : nullptr};
-    if (p->parts.empty()) {  // one rank: the transposes are the lo <-> st permutation
-        for (int k = 0; k < 3; k++)
-            if (lm_in[k] && magic_transp_lm2r_dev_n(t, LM_NF[k], lm_in[k], p->R[k])) return 1;
-        if (magic_rloop_run_dev(rl, &fin, &fout, time)) return 1;
-        for (int k = 0; k < 3; k++)
-            if (lm_out[k] && magic_transp_r2lm_dev_n(t, LM_NF[3 + k], p->R[3 + k], lm_out[k])) return 1;
-        return 0;
-    }
-    // all inbound transposes are queued now, chunk by chunk, on the communication stream
-    MCHECK(cudaEventRecord(p->ev_start, h->stream));
-    MCHECK(cudaStreamWaitEvent(p->comm, p->ev_start, 0));
-    for (int c = 0; c < p->C; c++) {
-        for (int k = 0; k < 3; k++)
-            if (lm_in[k] && magic_transp_lm2r_dev_n(p->parts[c], LM_NF[k], lm_in[k], p->R[k])) return 1;
-        MCHECK(cudaEventRecord(p->ev_in[c], p->comm));
-    }
-    auto outbound = [&](int c, bool wait) -> int {
-        if (wait) {
-            MCHECK(cudaEventRecord(p->ev_out[c], h->stream));
-            MCHECK(cudaStreamWaitEvent(p->comm, p->ev_out[c], 0));
+    const size_t lmf = 2 * (size_t)p->nlm * p->n_r_max;  // doubles per LM-distributed field
+    for (int k = 0; k < 4; k++) {
+        if (p->nf_in[k] && !p->LM_in[k]) {
+            MCHECK(cudaMalloc((void **)&p->LM_in[k], sizeof(double) * (lmf * p->nf_in[k] + 64 * (size_t)p->nlm + 256)));
+            MCHECK(cudaMemsetAsync(p->LM_in[k], 0, sizeof(double) * (lmf * p->nf_in[k] + 64 * (size_t)p->nlm + 256), h->stream));
         }
-        for (int k = 0; k < 3; k++)
-            if (lm_out[k] && magic_transp_r2lm_dev_n(p->parts[c], LM_NF[3 + k], p->R[3 + k], lm_out[k])) return 1;
-        return 0;
-    };
-    rl->hook_before = [&](int c) -> int {
-        MCHECK(cudaStreamWaitEvent(h->stream, p->ev_in[c], 0));
-        return 0;
-    };
-    rl->hook_after = [&](int c) -> int { return outbound(c, true); };
-    const int rc = magic_rloop_run_dev(rl, &fin, &fout, time);
-    rl->hook_before = nullptr;
-    rl->hook_after = nullptr;
-    if (rc) return 1;
-    // a rank with fewer chunks than C still takes part in the remaining exchanges (it has no levels in them, its peers do)
-    for (int c = (int)rl->chunk_start.size(); c < p->C; c++)
-        if (outbound(c, false)) return 1;
-    MCHECK(cudaEventRecord(p->ev_done, p->comm));
-    MCHECK(cudaStreamWaitEvent(h->stream, p->ev_done, 0));
+        if (p->nf_out[k] && !p->LM_out[k]) {
+            MCHECK(cudaMalloc((void **)&p->LM_out[k], sizeof(double) * (lmf * p->nf_out[k] + 64 * (size_t)p->nlm + 256)));
+            MCHECK(cudaMemsetAsync(p->LM_out[k], 0, sizeof(double) * (lmf * p->nf_out[k] + 64 * (size_t)p->nlm + 256), h->stream));
+        }
+    }
+    LmHostIO io;
+    io.in[0] = in->flow; io.in[1] = in->s; io.in[2] = in->field; io.in[3] = in->xi;
+    io.out[0] = out->dflowdt; io.out[1] = out->dsdt; io.out[2] = out->dbdt; io.out[3] = out->dxidt;
+    for (int k = 0; k < 4; k++) {
+        if (p->nf_in[k] && !io.in[k]) MFAIL("magic_rloop_run_lm: a required inbound container is null");
+        if (p->nf_out[k] && !io.out[k]) MFAIL("magic_rloop_run_lm: a required outbound container is null");
+    }
+    const double *li[4] = {p->LM_in[0], p->LM_in[1], p->LM_in[2], p->LM_in[3]};
+    double *lo[4] = {p->LM_out[0], p->LM_out[1], p->LM_out[2], p->LM_out[3]};
+    if (lm_run(rl, t, li, lo, rl->d_dtrkc, rl->d_dthkc, time, &io)) return 1;
+    MCHECK(cudaMemcpyAsync(rl->host_dtrkc, rl->d_dtrkc, sizeof(double) * rl->n_r_loc, cudaMemcpyDeviceToHost, h->stream));
+    MCHECK(cudaMemcpyAsync(rl->host_dthkc, rl->d_dthkc, sizeof(double) * rl->n_r_loc, cudaMemcpyDeviceToHost, h->stream));
+    MCHECK(cudaStreamSynchronize(p->s_down));
+    MCHECK(cudaStreamSynchronize(h->stream));
+    memcpy(out->dtrkc, rl->host_dtrkc, sizeof(double) * rl->n_r_loc);
+    memcpy(out->dthkc, rl->host_dthkc, sizeof(double) * rl->n_r_loc);
     return 0;
 }
 
@@ -715,9 +942,16 @@ extern "C" int magic_rloop_sync(magic_rloop *rl) {
     return 0;
 }
 extern "C" long long magic_rloop_launch_count(const magic_rloop *rl) { return rl ? rl->h->launches : 0; }
+extern "C" int magic_rloop_level_chunk(const magic_rloop *rl) { return rl ? rl->level_chunk : 0; }
 extern "C" int magic_rloop_last_timing(const magic_rloop *rl, double out[8]) {
     if (!rl) MFAIL("null rloop");
     for (int i = 0; i < 8; i++) out[i] = rl->timing[i];
+    return 0;
+}
+extern "C" int magic_rloop_last_exposed(const magic_rloop *rl, double out[2]) {
+    if (!rl || !out) MFAIL("null argument");
+    out[0] = rl->exposed[0];
+    out[1] = rl->exposed[1];
     return 0;
 }
 extern "C" double magic_rloop_legendre_flops(const magic_rloop *rl) { return rl ? rl->legendre_flops : 0.0; }

@@ -122,6 +122,8 @@ struct PackArgs {
     const int *lcount;     // [n_procs]
     const long long *disp; // [n_procs+1] element displacement of each peer segment, PER FIELD
     const int *lo2st;
+    int direct;            // single rank: the "buffer" of the R-side kernels is arr_LMloc itself ([f][n_r_max][lm_lo]); a part
+                           // then addresses row (f, r) at f * n_r_max + r0 + r instead of f * nr + r
 };
 
 __device__ __forceinline__ int find_seg(const long long *disp, int n, long long idx, int nf) {
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(256) rside_tiled_kernel(PackArgs a, const int 
     const long long arrB = vB ? (long long)mstart[mcB] + lB - mB : 0;
     // buffer row (f, r) = f * nr + r; array row = f * nr_arr + r_off + r (a part moves a sub-range of the levels of each field)
     auto arr_row = [&](int row) { return (long long)(row / a.nr) * a.nr_arr + a.r_off + row % a.nr; };
+    auto buf_row = [&](int row) { return a.direct ? (long long)(row / a.nr) * a.n_r_max + a.r0 + row % a.nr : (long long)row; };
     for (int rb = row0; rb < min(row0 + RT_ROWS, rows_total); rb += 4) {
         double2 v[4];
 #pragma unroll
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(256) rside_tiled_kernel(PackArgs a, const int 
             const int row = rb + q;
             v[q] = make_double2(0.0, 0.0);
             if (row < rows_total) {
-                if (UNPACK) { if (vA) v[q] = in[bufA + (long long)row * lcA]; }
+                if (UNPACK) { if (vA) v[q] = in[bufA + buf_row(row) * lcA]; }
                 else { if (vB) v[q] = in[arrB + arr_row(row) * a.lm_max]; }
             }
         }
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(256) rside_tiled_kernel(PackArgs a, const int 
             const int row = rb + q;
             if (row < rows_total) {
                 if (UNPACK) { if (vB) out[arrB + arr_row(row) * a.lm_max] = tile[q][jl][jm]; }
-                else { if (vA) out[bufA + (long long)row * lcA] = tile[q][il][im]; }
+                else { if (vA) out[bufA + buf_row(row) * lcA] = tile[q][il][im]; }
             }
         }
         __syncthreads();
@@ -342,6 +345,7 @@ extern "C" int magic_transp_create(magic_sht *h, const char id[128], int rank, i
     t->stream = h->stream;
     a.rstart = t->d_rstart; a.rcount = t->d_rcount; a.lstart = t->d_lstart; a.lcount = t->d_lcount; a.lo2st = t->d_lo2st;
     a.disp = nullptr;
+    a.direct = n_procs == 1 ? 1 : 0;
     if (n_procs > 1) {
         size_t maxel = (size_t)std::max(t->lmd1[n_procs], t->rd1[n_procs]) * n_fields;
         MCHECK(cudaMalloc((void **)&t->sendbuf, sizeof(double) * 2 * maxel));
@@ -541,6 +545,7 @@ extern "C" int magic_transp_r2lm_dev(magic_transp *t, const double *arr_Rloc, do
 }
 
 static int ensure_stage(magic_transp *t) {
+    if (t->parent) MFAIL("the host-pointer transposes are not available on a part (use the parent, or the device-pointer calls)");
     if (t->stage_lm) return 0;
     MCHECK(cudaMalloc((void **)&t->stage_lm, sizeof(double) * 2 * (size_t)t->lmd1[t->n_procs] * t->n_fields));
     MCHECK(cudaMalloc((void **)&t->stage_r, sizeof(double) * 2 * (size_t)t->rd1[t->n_procs] * t->n_fields));
@@ -551,10 +556,10 @@ extern "C" int magic_transp_lm2r(magic_transp *t, const double *arr_LMloc, doubl
     TCHK(t, t->n_fields);
     if (ensure_stage(t)) return 1;
     size_t blm = sizeof(double) * 2 * (size_t)t->lmd1[t->n_procs] * t->n_fields, br = sizeof(double) * 2 * (size_t)t->rd1[t->n_procs] * t->n_fields;
-    MCHECK(cudaMemcpyAsync(t->stage_lm, arr_LMloc, blm, cudaMemcpyHostToDevice, t->h->stream));
+    MCHECK(cudaMemcpyAsync(t->stage_lm, arr_LMloc, blm, cudaMemcpyHostToDevice, t->stream));  // same stream as pack / exchange / unpack
     if (magic_transp_lm2r_dev(t, t->stage_lm, t->stage_r)) return 1;
-    MCHECK(cudaMemcpyAsync(arr_Rloc, t->stage_r, br, cudaMemcpyDeviceToHost, t->h->stream));
-    MCHECK(cudaStreamSynchronize(t->h->stream));
+    MCHECK(cudaMemcpyAsync(arr_Rloc, t->stage_r, br, cudaMemcpyDeviceToHost, t->stream));
+    MCHECK(cudaStreamSynchronize(t->stream));
     return 0;
 }
 
@@ -562,9 +567,9 @@ extern "C" int magic_transp_r2lm(magic_transp *t, const double *arr_Rloc, double
     TCHK(t, t->n_fields);
     if (ensure_stage(t)) return 1;
     size_t blm = sizeof(double) * 2 * (size_t)t->lmd1[t->n_procs] * t->n_fields, br = sizeof(double) * 2 * (size_t)t->rd1[t->n_procs] * t->n_fields;
-    MCHECK(cudaMemcpyAsync(t->stage_r, arr_Rloc, br, cudaMemcpyHostToDevice, t->h->stream));
+    MCHECK(cudaMemcpyAsync(t->stage_r, arr_Rloc, br, cudaMemcpyHostToDevice, t->stream));
     if (magic_transp_r2lm_dev(t, t->stage_r, t->stage_lm)) return 1;
-    MCHECK(cudaMemcpyAsync(arr_LMloc, t->stage_lm, blm, cudaMemcpyDeviceToHost, t->h->stream));
-    MCHECK(cudaStreamSynchronize(t->h->stream));
+    MCHECK(cudaMemcpyAsync(arr_LMloc, t->stage_lm, blm, cudaMemcpyDeviceToHost, t->stream));
+    MCHECK(cudaStreamSynchronize(t->stream));
     return 0;
 }

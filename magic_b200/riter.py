@@ -56,11 +56,12 @@ def level_chunks(n_r_loc, level_chunk):
 
 
 class _LmIn(C.Structure):
-    _fields_ = [("flow", c_void_p), ("s", c_void_p), ("field", c_void_p)]
+    _fields_ = [("flow", c_void_p), ("s", c_void_p), ("field", c_void_p), ("xi", c_void_p)]
 
 
 class _LmOut(C.Structure):
-    _fields_ = [("dflowdt", c_void_p), ("dsdt", c_void_p), ("dbdt", c_void_p), ("dtrkc", c_void_p), ("dthkc", c_void_p)]
+    _fields_ = [("dflowdt", c_void_p), ("dsdt", c_void_p), ("dbdt", c_void_p), ("dtrkc", c_void_p), ("dthkc", c_void_p),
+                ("dxidt", c_void_p)]
 
 
 class RadialLoop:
@@ -145,9 +146,19 @@ class RadialLoop:
         """The whole hot path of a step on LM-distributed device containers (ints = device pointers; field/dbdt 0 without
         l_mag): transp_LMloc_to_Rloc -> radialLoopG -> transp_Rloc_to_LMloc (step_time.f90:485-612), the transposes
         pipelined chunk by chunk against the compute when there is more than one rank."""
-        i = _LmIn(int(flow_LM), int(s_LM), int(field_LM) or None)
-        o = _LmOut(int(dflowdt_LM), int(dsdt_LM), int(dbdt_LM) or None, int(dtrkc_dev), int(dthkc_dev))
+        i = _LmIn(int(flow_LM), int(s_LM) or None, int(field_LM) or None, None)
+        o = _LmOut(int(dflowdt_LM), int(dsdt_LM) or None, int(dbdt_LM) or None, int(dtrkc_dev), int(dthkc_dev), None)
         check(self.lib.magic_rloop_run_lm_dev(self._h, transposer._h, byref(i), byref(o), c_double(time)))
+
+    def run_lm(self, transposer, lm_in, lm_out, dtrkc, dthkc, time=0.0):
+        """magic_rloop_run_lm: the same on HOST LM-distributed containers (numpy complex128 arrays [nf, n_r_max, nlm_loc];
+        dict keys flow, s, field, xi / dflowdt, dsdt, dbdt, dxidt; dtrkc, dthkc float64 [n_r_loc])."""
+        def a(d, k):
+            v = d.get(k)
+            return None if v is None else v.ctypes.data
+        i = _LmIn(a(lm_in, "flow"), a(lm_in, "s"), a(lm_in, "field"), a(lm_in, "xi"))
+        o = _LmOut(a(lm_out, "dflowdt"), a(lm_out, "dsdt"), a(lm_out, "dbdt"), dtrkc.ctypes.data, dthkc.ctypes.data, a(lm_out, "dxidt"))
+        check(self.lib.magic_rloop_run_lm(self._h, transposer._h, byref(i), byref(o), c_double(time)))
 
     def set_rotation(self, omega_ma, omega_ic):
         """Boundary rotation rates of the coming step (omega_ma, omega_ic of v_rigid_boundary)."""
@@ -179,8 +190,24 @@ class RadialLoop:
         keys = ["total", "prep", "legendre_syn", "fft_c2r", "get_nl", "fft_r2c", "legendre_an", "get_td"]
         return dict(zip(keys, list(t)))
 
+    def last_exposed(self):
+        """(ms before the first chunk's first kernel, ms after the last chunk's last kernel) of the last run."""
+        t = (c_double * 2)()
+        check(self.lib.magic_rloop_last_exposed(self._h, t))
+        return float(t[0]), float(t[1])
+
     def legendre_flops(self):
         return float(self.lib.magic_rloop_legendre_flops(self._h))
+
+    def level_chunk(self):
+        return int(self.lib.magic_rloop_level_chunk(self._h))
+
+    def pin_host(self, array):
+        """magic_rloop_pin_host: page-lock a persistent numpy array of the caller (unpin_host before it is freed)."""
+        check(self.lib.magic_rloop_pin_host(self._h, c_void_p(array.ctypes.data), array.nbytes))
+
+    def unpin_host(self, array):
+        check(self.lib.magic_rloop_unpin_host(self._h, c_void_p(array.ctypes.data)))
 
     def legendre_units(self):
         """(reference count, executed) scalar-equivalent Legendre passes per bulk level."""

@@ -13,8 +13,13 @@ CONFIGS = {
     # name: (l_max, minc, n_r_max, n_phi_tot or None, physics)
     "dynamo_benchmark": dict(l_max=16, minc=1, n_r_max=33, physics="mhd", config_id=0),
     "hydro_bench_anel": dict(l_max=0, n_phi_tot=288, minc=1, n_r_max=97, physics="anel", config_id=1),
+    # BASELINE.json quotes this case at "l_max=85": the grid when l_max is imposed instead of n_phi_tot
+    "hydro_bench_anel_l85": dict(l_max=85, minc=1, n_r_max=97, physics="anel", config_id=1),
     "bouss_dynamo_l255": dict(l_max=255, minc=1, n_r_max=121, physics="mhd", config_id=2),
-    "full_sphere_l511": dict(l_max=511, minc=1, n_r_max=161, physics="hydro", config_id=3),
+    # samples/full_sphere scaled up: FD radial scheme => double-curl poloidal equation, r = 0 level (v_center_sphere),
+    # l_R(r) falling towards the centre (l_var_l, radial.f90:291-307 with rcut_l = 0.1)
+    "full_sphere_l511": dict(l_max=511, minc=1, n_r_max=161, physics="hydro", config_id=3,
+                             flags=dict(l_full_sphere=1, l_double_curl=1), l_var_l=True),
     "dynamo_l1023": dict(l_max=1023, minc=1, n_r_max=257, physics="mhd", config_id=4),
 }
 
@@ -112,8 +117,31 @@ def make_fields(physics, lm2l, lm2m, n_r_loc, seed, out=None):
 def config_sizes(name):
     c = CONFIGS[name]
     gs = grid_sizes(l_max=c["l_max"], n_phi_tot=c.get("n_phi_tot", 0), minc=c["minc"])
-    gs.update(n_r_max=c["n_r_max"], minc=c["minc"], physics=c["physics"], config_id=c["config_id"])
+    gs.update(n_r_max=c["n_r_max"], minc=c["minc"], physics=c["physics"], config_id=c["config_id"], flags=c.get("flags", {}),
+              l_var_l=c.get("l_var_l", False))
     return gs
+
+
+def config_params(gs):
+    """make_params + the configuration's extra switches."""
+    p = make_params(gs["physics"], gs["n_r_max"])
+    for k, v in gs.get("flags", {}).items():
+        setattr(p, k, v)
+    return p
+
+
+def config_l_R(gs):
+    """l_R(nR) = min(l_max, int(1 + l_max sqrt(x / rcut_l))) of radial.f90:291-296 (l_var_l, rcut_l = 0.1), with x the distance
+    from the innermost level as a fraction of the shell depth (the full sphere's r / r_cmb), or None for l_R = l_max."""
+    if not gs.get("l_var_l"):
+        return None
+    n_r_max, l_max = gs["n_r_max"], gs["l_max"]
+    r = make_radial(n_r_max, l_max)["r"]
+    r_cmb = r[0]
+    l_R = np.full(n_r_max, l_max, dtype=np.int32)
+    for n in range(n_r_max):
+        l_R[n] = min(l_max, int(1.0 + l_max * np.sqrt((r[n] - r[-1]) / (r_cmb - r[-1]) / 0.1)))
+    return l_R
 
 
 def seed_for(config_id, rank):

@@ -99,8 +99,40 @@ def main():
         for a, b in zip(got_LM, ref_LM):
             ok5 = ok5 and bool(torch.equal(a, b))
         ok5 = ok5 and bool(torch.equal(dtr, dtr_ref)) and float(ref_LM[0].abs().sum()) > 0
+    # (c) the host-pointer call magic_rloop_run_lm: host LM containers in, host LM explicit terms out (PCIe transfers pipelined
+    #     with the transposes and the compute), twice; bit-identical to (a)
+    h_in = {"flow": flow_LM.cpu().numpy(), "s": s_LM.cpu().numpy(), "field": field_LM.cpu().numpy()}
+    ok6 = True
+    for _ in range(2):
+        h_out = {"dflowdt": np.zeros((3, n_r_max, tr.nlm_loc), dtype=np.complex128), "dsdt": np.zeros((2, n_r_max, tr.nlm_loc), dtype=np.complex128),
+                 "dbdt": np.zeros((3, n_r_max, tr.nlm_loc), dtype=np.complex128)}
+        h_dtr, h_dth = np.zeros(tr.nr_loc), np.zeros(tr.nr_loc)
+        rl.run_lm(tr, h_in, h_out, h_dtr, h_dth)
+        for a, b in zip([h_out["dflowdt"], h_out["dsdt"], h_out["dbdt"]], ref_LM):
+            ok6 = ok6 and np.array_equal(a, b.cpu().numpy())
+        ok6 = ok6 and np.array_equal(h_dtr, dtr_ref.cpu().numpy())
     rl.finalize()
-    flags = torch.tensor([ok1, ok2, ok3, ok4, ok5], dtype=torch.int32, device=dev)
+    # (d) another field set through the same pipeline: Boussinesq hydro in the double-curl formulation (4-field dflowdt, no magnetic
+    #     containers), device containers, against the sequential calls
+    p2 = make_params("hydro", n_r_max)
+    p2.l_double_curl = 1
+    rl = RadialLoop(sht, p2, rad, level_chunk=4)
+    dfR4, dsR2 = zr(4), zr(2)
+    torch.cuda.synchronize()
+    fout2 = {"dwdt": dfR4[0], "dzdt": dfR4[1], "dVxVhLM": dfR4[3], "dsdt": dsR2[0], "dVSrLM": dsR2[1]}
+    fin2 = {k: fin[k] for k in ["w", "dw", "ddw", "z", "dz", "s"]}
+    rl.radialLoop_dev({k: v.data_ptr() for k, v in fin2.items()}, {k: v.data_ptr() for k, v in fout2.items()}, dtr.data_ptr(), dth.data_ptr())
+    ref2 = [zl(4), zl(2)]
+    tr.transp_r2lm_dev_n(4, dfR4.data_ptr(), ref2[0].data_ptr()); tr.transp_r2lm_dev_n(2, dsR2.data_ptr(), ref2[1].data_ptr())
+    ext.synchronize()
+    got2 = [zl(4), zl(2)]
+    torch.cuda.synchronize()
+    rl.run_lm_dev(tr, flow_LM.data_ptr(), s_LM.data_ptr(), 0, got2[0].data_ptr(), got2[1].data_ptr(), 0, dtr.data_ptr(), dth.data_ptr())
+    ext.synchronize()
+    torch.cuda.synchronize()
+    ok7 = all(bool(torch.equal(a, b)) for a, b in zip(got2, ref2)) and float(ref2[0][3].abs().sum()) > 0
+    rl.finalize()
+    flags = torch.tensor([ok1, ok2, ok3, ok4, ok5, ok6, ok7], dtype=torch.int32, device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if bool(flags.min().item()) else "FAIL", flags.tolist(), "world", world, flush=True)
