@@ -236,6 +236,24 @@ int magic_rloop_run_lm_dev(magic_rloop *rl, magic_transp *t, const magic_lm_in *
  * R-containers.  Page-lock the containers once with magic_rloop_pin_host for asynchronous transfers. */
 int magic_rloop_run_lm(magic_rloop *rl, magic_transp *t, const magic_lm_in *in, const magic_lm_out *out, double time);
 
+/* ---- LM-side prologue and epilogue of the host-container call.  In the LM distribution a rank holds ALL
+ * radial levels of its modes, so radial derivatives are local: a small FP64 GEMM with the radial scheme's matrix.
+ *   magic_rloop_set_radial_matrices: D1, D2 row-major [n_r_max][n_r_max], (D f)(r_i) = sum_j D[i][j] f(r_j) -- what get_dr /
+ *     get_ddr (radial_derivatives.f90:714-912) compute on this grid INCLUDING the n_cheb_max truncation; the shim builds them
+ *     once by applying get_dr / get_ddr to the unit vectors.
+ *   magic_rloop_set_lm_radial: or2, orho1, dentropy0, l_R on all n_r_max levels (finish_exp_entropy, updateS.f90:543-601).
+ *   magic_rloop_lm_options(derivs_on_device, finish_on_device):
+ *     derivs_on_device: dw, ddw, dz (db, ddb, dj) are computed on the device from w, z (b, aj); only fields 0 and 3 of the flow
+ *       and field containers cross PCIe (5 instead of 11 arrays for the MHD set).  The upload of w, z, b, aj then precedes all
+ *       compute instead of being pipelined with it.
+ *     finish_on_device: finish_explicit_assembly (LMLoop.f90:390-453: finish_exp_entropy, _comp, _pol, _mag) runs on the device
+ *       after the outbound transposes; dVSrLM, dVxBhLM, dVxVhLM, dVXirLM stay on the device (6 instead of 8 arrays come down),
+ *       and the host must then NOT call finish_explicit_assembly itself (step_time.f90:647). */
+int magic_rloop_set_radial_matrices(magic_rloop *rl, int n_r_max, const double *D1, const double *D2);
+int magic_rloop_set_lm_radial(magic_rloop *rl, int n_r_max, const double *or2, const double *orho1, const double *dentropy0,
+                              const int *l_R);
+int magic_rloop_lm_options(magic_rloop *rl, int derivs_on_device, int finish_on_device);
+
 /* Pure host helpers (no CUDA device needed): the decomposition the transposer uses.
  * magic_get_blocks: getBlocks (parallel.f90:75-92), 1-based inclusive start/stop per rank.
  * magic_lo_map: lo2st[lm_lo] = 0-based st_map index of the lm_lo-th entry of lo_map (snake ordering when

@@ -31,6 +31,9 @@ struct magic_rloop {
     // of chunk c is queued; they queue the transposes of that chunk on the communication stream
     std::function<int(int)> hook_before, hook_after;
     struct LmPipe *lmpipe = nullptr;
+    // LM-side prologue / epilogue: the host's radial scheme as dense matrices, radial functions on all levels
+    std::vector<double> D1h, D2h, lmrad_h;  // [n_r][n_r] row-major x2; [4][n_r]: or2, orho1, dentropy0, l_R
+    int n_r_mat = 0, lm_derivs = 0, lm_finish = 0;
     std::vector<Layout> lays;    // one layout per distinct chunk size; lays[0] belongs to the largest chunk (it sizes the workspace)
     std::vector<int> lay_sizes;
     int buf_levels = 0;          // number of levels the workspace `buf` was allocated for
@@ -329,12 +332,9 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
         // The automatic choice depends on the truncation and the field set only -- never on this rank's slab or its free
         // memory -- so every rank of a run derives the same value (magic_rloop_run_lm_dev computes the chunks of its peers
         // from it).  A workspace that does not fit fails loudly in buffers_alloc below.
-        // measured at l_max=1023 (GEMM ms per level): 16-level chunks 1.65, 32-level chunks 1.78, 64-level chunks > 2.0 --
-        // so 16 levels whenever that still gives the synthesis GEMM >= 20 waves of tiles, else 32 (small truncations are
-        // launch-bound and want the wider batch)
-        const long long tiles16 = (long long)h->n_m * 2 * ((h->nh + GEMM_BM - 1) / GEMM_BM) *
-                                  ((2LL * std::max(1, (int)(S.scal.size() + 2 * S.vec.size())) * 16 + GEMM_BN - 1) / GEMM_BN);
-        level_chunk = tiles16 >= 20LL * 2 * 148 ? 16 : 32;
+        // measured at l_max=1023 (whole loop, ms per level): 16-level chunks 1.79, 32-level chunks 1.75, 64-level chunks 1.74: with
+        // 13 + 9 complex columns per level the GEMM tile counts 26 n_lev / 64 and 18 n_lev / 64 are whole numbers at 32 levels
+        level_chunk = 32;
     }
     rl->level_chunk_req = level_chunk;
     level_chunk = std::min(level_chunk, n_r_loc);
@@ -657,9 +657,9 @@ struct LmPipe {
     // radial matrices of the host's radial scheme (magic_rloop_set_radial_matrices) for the LM-side prologue / epilogue
     double *d_D1 = nullptr, *d_D2 = nullptr;
     int ldD = 0;
-    GemmProb *d_dprobs = nullptr;
-    int2 *d_dtiles = nullptr;
-    int n_dtiles = 0;
+    GemmProb *d_dprobs[2] = {nullptr, nullptr};  // cached tile lists of the prologue (0) and epilogue (1) matrix products
+    int2 *d_dtiles[2] = {nullptr, nullptr};
+    int n_dtiles[2] = {0, 0};
     double *d_work = nullptr;              // [3][n_r_max][nlm] radial derivatives of dVSrLM, dVxBhLM, dVxVhLM
     double *d_lmrad = nullptr;             // [4][n_r_max]: or2, orho1, dentropy0, l_R (as doubles)
     int *d_lo2l = nullptr;                 // degree of every local mode (lo order)
@@ -675,7 +675,8 @@ static void lmpipe_free(LmPipe *p) {
     for (cudaStream_t s : {p->comm, p->s_up, p->s_down})
         if (s) cudaStreamDestroy(s);
     for (int i = 0; i < 4; i++) { cudaFree(p->R_in[i]); cudaFree(p->R_out[i]); cudaFree(p->LM_in[i]); cudaFree(p->LM_out[i]); }
-    cudaFree(p->d_D1); cudaFree(p->d_D2); cudaFree(p->d_dprobs); cudaFree(p->d_dtiles); cudaFree(p->d_work); cudaFree(p->d_lmrad);
+    cudaFree(p->d_D1); cudaFree(p->d_D2); cudaFree(p->d_work); cudaFree(p->d_lmrad);
+    for (int i = 0; i < 2; i++) { cudaFree(p->d_dprobs[i]); cudaFree(p->d_dtiles[i]); }
     cudaFree(p->d_lo2l);
     delete p;
 }
@@ -691,11 +692,7 @@ static int lmpipe_build(magic_rloop *rl, magic_transp *t) {
     if (nRstop - nRstart + 1 != rl->n_r_loc) MFAIL("magic_rloop_run_lm: the loop and the transposer disagree on the radial slab");
     LmPipe *old = rl->lmpipe;
     LmPipe *p = new LmPipe();
-    if (old) {  // keep the radial matrices across a rebuild
-        p->d_D1 = old->d_D1; p->d_D2 = old->d_D2; p->ldD = old->ldD; p->d_lmrad = old->d_lmrad;
-        old->d_D1 = old->d_D2 = old->d_lmrad = nullptr;
-        lmpipe_free(old);
-    }
+    if (old) lmpipe_free(old);
     rl->lmpipe = p;
     p->parent = t; p->n_procs = n_procs; p->rank = rank; p->n_r_max = n_r_max; p->nlm = ulm - llm + 1;
     const bool flow = P.l_conv || P.l_mag_kin, mag = P.l_mag || P.l_mag_LF;
@@ -767,15 +764,84 @@ static int lmpipe_build(magic_rloop *rl, magic_transp *t) {
 }
 
 // host <-> device rows of part c of an LM-distributed container ([nf][n_r_max][nlm] complex): for every rank q the levels of
-// q's c-th chunk, all nf fields of one rank in one strided copy
-static int lm_rows_copy(LmPipe *p, int c, int nf, double *dst, const double *src, cudaMemcpyKind kind, cudaStream_t st) {
+// q's c-th chunk, for the fields in `mask` (runs of consecutive fields of one rank go in one strided copy)
+static int lm_rows_copy(LmPipe *p, int c, int nf, unsigned mask, double *dst, const double *src, cudaMemcpyKind kind, cudaStream_t st) {
     const size_t row = sizeof(double) * 2 * (size_t)p->nlm, pitch = row * p->n_r_max;
     for (int q = 0; q < p->n_procs; q++) {
         if (c >= (int)p->cs[q].size() || p->cz[q][c] == 0) continue;
         const size_t off = (size_t)(p->rs[q] + p->cs[q][c]) * 2 * (size_t)p->nlm;
-        MCHECK(cudaMemcpy2DAsync(dst + off, pitch, src + off, pitch, row * p->cz[q][c], nf, kind, st));
+        for (int f = 0; f < nf;) {
+            if (!(mask >> f & 1u)) { f++; continue; }
+            int f1 = f;
+            while (f1 < nf && (mask >> f1 & 1u)) f1++;
+            const size_t fo = off + (size_t)f * 2 * (size_t)p->nlm * p->n_r_max;
+            MCHECK(cudaMemcpy2DAsync(dst + fo, pitch, src + fo, pitch, row * p->cz[q][c], f1 - f, kind, st));
+            f = f1;
+        }
     }
     return 0;
+}
+
+// ---- radial-matrix products on LM-distributed device arrays: Y[n_r x 2 nlm] = D[n_r x n_r] X[n_r x 2 nlm] with the Legendre
+//      GEMM kernel (D zero-padded to whole tiles; X must be followed by >= 15 readable rows: the containers this file
+//      allocates carry that slack).  get_dr / get_ddr of radial_derivatives.f90 for whatever radial scheme the host runs.
+struct DerivJob { const double *X; double *Y; int which; };
+
+static int lm_matrix_upload(magic_rloop *rl, LmPipe *p) {
+    if (p->d_D1 || rl->n_r_mat == 0) return 0;
+    const int n = rl->n_r_mat;
+    if (n != p->n_r_max) MFAIL("magic_rloop: the radial matrices were given for another n_r_max than the transposer's");
+    p->ldD = pad_up(n, BK);
+    const int rows = pad_up(n, GEMM_BM) + GEMM_BM;
+    std::vector<double> pad((size_t)rows * p->ldD, 0.0);
+    for (int which = 0; which < 2; which++) {
+        const std::vector<double> &D = which == 0 ? rl->D1h : rl->D2h;
+        std::fill(pad.begin(), pad.end(), 0.0);
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) pad[(size_t)i * p->ldD + j] = D[(size_t)i * n + j];
+        if (dev_upload_vec(which == 0 ? &p->d_D1 : &p->d_D2, pad)) return 1;
+    }
+    if (!rl->lmrad_h.empty() && dev_upload_vec(&p->d_lmrad, rl->lmrad_h)) return 1;
+    // degree and order of every local mode (lo order)
+    std::vector<int> lo2st(rl->h->lm_max), ls(p->n_procs), le(p->n_procs);
+    if (magic_lo_map(rl->h->l_max, rl->h->m_max, rl->h->minc, p->n_procs, lo2st.data(), ls.data(), le.data())) return 1;
+    std::vector<int> ll(2 * (size_t)p->nlm);
+    for (int i = 0; i < p->nlm; i++) {
+        const int st = lo2st[ls[p->rank] - 1 + i];
+        ll[i] = rl->h->lm2l[st];
+        ll[(size_t)p->nlm + i] = rl->h->lm2m[st];
+    }
+    if (dev_upload_vec(&p->d_lo2l, ll)) return 1;
+    MCHECK(cudaMalloc((void **)&p->d_work, sizeof(double) * (2 * (size_t)p->nlm * p->n_r_max * 4 + 64 * (size_t)p->nlm + 256)));
+    MCHECK(cudaMemset(p->d_work, 0, sizeof(double) * (2 * (size_t)p->nlm * p->n_r_max * 4 + 64 * (size_t)p->nlm + 256)));
+    return 0;
+}
+
+static int lm_matrix_products(magic_rloop *rl, LmPipe *p, int slot, const std::vector<DerivJob> &jobs, cudaStream_t st) {
+    if (jobs.empty()) return 0;
+    if (p->d_dprobs[slot]) {  // the arrays of a slot never move: its tile list is built once
+        launch_legendre_gemm(true, p->d_dprobs[slot], p->d_dtiles[slot], p->n_dtiles[slot], p->ldD, st);
+        rl->h->launches++;
+        MCHECK(cudaGetLastError());
+        return 0;
+    }
+    const int n = p->n_r_max, N = 2 * p->nlm;
+    std::vector<GemmProb> probs;
+    std::vector<int2> tiles;
+    for (const DerivJob &j : jobs) {
+        GemmProb g{};
+        g.A0 = j.which == 1 ? p->d_D1 : p->d_D2;
+        g.B = j.X; g.C = j.Y;
+        g.kt0 = p->ldD / BK; g.M = n; g.ldb = g.ldc = N; g.Nvalid = g.Nstore = N; g.Mlo = 0; g.klo = 0; g.ks0 = nullptr;
+        probs.push_back(g);
+    }
+    for (int mt = 0; mt < (n + GEMM_BM - 1) / GEMM_BM; mt++)
+        for (int nt = 0; nt < (N + GEMM_BN - 1) / GEMM_BN; nt++)
+            for (size_t pid = 0; pid < probs.size(); pid++) tiles.push_back(make_int2((int)pid, (mt << 16) | nt));
+    if ((N + GEMM_BN - 1) / GEMM_BN > 0xffff) MFAIL("magic_rloop: too many local modes for the radial-matrix GEMM tile index");
+    if (dev_upload_vec(&p->d_dprobs[slot], probs) || dev_upload_vec(&p->d_dtiles[slot], tiles)) return 1;
+    p->n_dtiles[slot] = (int)tiles.size();
+    return lm_matrix_products(rl, p, slot, jobs, st);
 }
 
 struct LmHostIO {  // host containers of magic_rloop_run_lm (null for the device-pointer call)
@@ -819,10 +885,50 @@ static int lm_run(magic_rloop *rl, magic_transp *t, const double *const lm_in[4]
         MCHECK(cudaStreamWaitEvent(p->s_up, p->ev_start, 0));
         MCHECK(cudaStreamWaitEvent(p->s_down, p->ev_start, 0));
     }
+    // ---- options of the host-container call
+    const bool derivs = io && rl->lm_derivs, finish = io && rl->lm_finish;
+    if ((rl->lm_derivs || rl->lm_finish) && !io) MFAIL("magic_rloop_run_lm_dev: the LM-side prologue / epilogue options belong to the host-container call magic_rloop_run_lm");
+    if (derivs || finish) {
+        if (rl->n_r_mat == 0) MFAIL("magic_rloop_run_lm: set the radial matrices first (magic_rloop_set_radial_matrices)");
+        if (finish && rl->lmrad_h.empty()) MFAIL("magic_rloop_run_lm: set the LM-side radial functions first (magic_rloop_set_lm_radial)");
+        if (lm_matrix_upload(rl, p)) return 1;
+    }
+    const size_t lmf = 2 * (size_t)p->nlm * p->n_r_max;  // doubles per LM-distributed field
+    // fields that cross PCIe part by part: up = what the loop reads (ds / dxi never; with the prologue on the device only s / xi),
+    // down = every explicit term (with the epilogue on the device not the arrays it consumes or finishes)
+    unsigned up_mask[4] = {0x1fu, 0x1u, 0x1fu, 0x1u}, down_mask[4] = {0xfu, 0x3u, 0x7u, 0x3u}, late_mask[4] = {0, 0, 0, 0};
+    if (derivs) up_mask[0] = up_mask[2] = 0;
+    if (finish) {
+        if (P.l_heat) { down_mask[1] = 0; late_mask[1] = 0x1u; }                       // dsdt finished, dVSrLM consumed
+        if (P.l_chemical_conv) { down_mask[3] = 0; late_mask[3] = 0x1u; }              // dxidt, dVXirLM
+        if (P.l_mag) { down_mask[2] = 0x1u; late_mask[2] = 0x2u; }                     // dbdt as is; djdt finished, dVxBhLM consumed
+        if (P.l_double_curl) { down_mask[0] = 0x6u; late_mask[0] = 0x1u; }            // dzdt, dpdt as is; dwdt finished, dVxVhLM consumed
+    }
+    if (derivs) {
+        // prologue: w, z (b, aj) of ALL levels go up first; dw, ddw, dz (db, ddb, dj) are radial-matrix products on the device
+        for (int k = 0; k < 4; k += 2) {
+            if (!p->nf_in[k]) continue;
+            for (int f = 0; f < 4; f += 3)
+                MCHECK(cudaMemcpyAsync(p->LM_in[k] + f * lmf, io->in[k] + f * lmf, sizeof(double) * lmf, cudaMemcpyHostToDevice, p->s_up));
+        }
+        MCHECK(cudaEventRecord(p->ev_ready, p->s_up));
+        MCHECK(cudaStreamWaitEvent(h->stream, p->ev_ready, 0));
+        std::vector<DerivJob> jobs;
+        for (int k = 0; k < 4; k += 2) {
+            if (!p->nf_in[k]) continue;
+            double *b = p->LM_in[k];
+            jobs.push_back({b, b + lmf, 1});
+            jobs.push_back({b, b + 2 * lmf, 2});
+            jobs.push_back({b + 3 * lmf, b + 4 * lmf, 1});
+        }
+        if (lm_matrix_products(rl, p, 0, jobs, h->stream)) return 1;
+        MCHECK(cudaEventRecord(p->ev_ready, h->stream));
+        MCHECK(cudaStreamWaitEvent(p->comm, p->ev_ready, 0));
+    }
     auto inbound = [&](int c) -> int {
         if (io) {  // PCIe: the rows of this part, only the fields the loop reads
             for (int k = 0; k < 4; k++)
-                if (p->nf_in[k] && lm_rows_copy(p, c, p->nt_in[k], p->LM_in[k], io->in[k], cudaMemcpyHostToDevice, p->s_up)) return 1;
+                if (p->nf_in[k] && up_mask[k] && lm_rows_copy(p, c, p->nf_in[k], up_mask[k], p->LM_in[k], io->in[k], cudaMemcpyHostToDevice, p->s_up)) return 1;
             MCHECK(cudaEventRecord(p->ev_up[c], p->s_up));
             MCHECK(cudaStreamWaitEvent(p->comm, p->ev_up[c], 0));
         }
@@ -842,7 +948,7 @@ static int lm_run(magic_rloop *rl, magic_transp *t, const double *const lm_in[4]
             MCHECK(cudaEventRecord(p->ev_lmout[c], p->comm));
             MCHECK(cudaStreamWaitEvent(p->s_down, p->ev_lmout[c], 0));
             for (int k = 0; k < 4; k++)
-                if (p->nf_out[k] && lm_rows_copy(p, c, p->nf_out[k], io->out[k], p->LM_out[k], cudaMemcpyDeviceToHost, p->s_down)) return 1;
+                if (p->nf_out[k] && down_mask[k] && lm_rows_copy(p, c, p->nf_out[k], down_mask[k], io->out[k], p->LM_out[k], cudaMemcpyDeviceToHost, p->s_down)) return 1;
         }
         return 0;
     };
@@ -861,6 +967,30 @@ static int lm_run(magic_rloop *rl, magic_transp *t, const double *const lm_in[4]
     }
     MCHECK(cudaEventRecord(p->ev_done, p->comm));
     MCHECK(cudaStreamWaitEvent(h->stream, p->ev_done, 0));
+    if (finish) {
+        // epilogue = finish_explicit_assembly (LMLoop.f90:390-453): radial derivatives of dVSrLM, dVxBhLM, dVxVhLM, dVXirLM by
+        // the radial matrix, then the point-wise completion of dsdt, djdt, dwdt, dxidt -- all levels of the local modes are here
+        std::vector<DerivJob> jobs;
+        double *wk = p->d_work;
+        FinishArgs fa{};
+        fa.n_r_max = p->n_r_max; fa.nlm = p->nlm; fa.lo2l = p->d_lo2l; fa.lo2m = p->d_lo2l + p->nlm;
+        fa.or2 = p->d_lmrad; fa.orho1 = p->d_lmrad + p->n_r_max; fa.dentropy0 = p->d_lmrad + 2 * p->n_r_max; fa.l_R = p->d_lmrad + 3 * p->n_r_max;
+        fa.w = p->LM_in[0];
+        if (P.l_heat) { jobs.push_back({p->LM_out[1] + lmf, wk, 1}); fa.dsdt = p->LM_out[1]; fa.work_s = wk; }
+        if (P.l_mag) { jobs.push_back({p->LM_out[2] + 2 * lmf, wk + lmf, 1}); fa.djdt = p->LM_out[2] + lmf; fa.work_b = wk + lmf; }
+        if (P.l_double_curl) { jobs.push_back({p->LM_out[0] + 3 * lmf, wk + 2 * lmf, 1}); fa.dwdt = p->LM_out[0]; fa.work_v = wk + 2 * lmf; }
+        if (P.l_chemical_conv) { jobs.push_back({p->LM_out[3] + lmf, wk + 3 * lmf, 1}); fa.dxidt = p->LM_out[3]; fa.work_xi = wk + 3 * lmf; }
+        if (lm_matrix_products(rl, p, 1, jobs, h->stream)) return 1;
+        finish_explicit_kernel<<<dim3((p->nlm + 255) / 256, p->n_r_max), 256, 0, h->stream>>>(fa);
+        h->launches++;
+        MCHECK(cudaGetLastError());
+        MCHECK(cudaEventRecord(p->ev_ready, h->stream));
+        MCHECK(cudaStreamWaitEvent(p->s_down, p->ev_ready, 0));
+        for (int k = 0; k < 4; k++)
+            for (int f = 0; f < p->nf_out[k]; f++)
+                if (late_mask[k] >> f & 1u)
+                    MCHECK(cudaMemcpyAsync(io->out[k] + f * lmf, p->LM_out[k] + f * lmf, sizeof(double) * lmf, cudaMemcpyDeviceToHost, p->s_down));
+    }
     if (rloop_end(rl, &fin)) return 1;
     return 0;
 }
@@ -911,6 +1041,36 @@ extern "C" int magic_rloop_run_lm(magic_rloop *rl, magic_transp *t, const magic_
     MCHECK(cudaStreamSynchronize(h->stream));
     memcpy(out->dtrkc, rl->host_dtrkc, sizeof(double) * rl->n_r_loc);
     memcpy(out->dthkc, rl->host_dthkc, sizeof(double) * rl->n_r_loc);
+    return 0;
+}
+
+extern "C" int magic_rloop_set_radial_matrices(magic_rloop *rl, int n_r_max, const double *D1, const double *D2) {
+    if (!rl || !D1 || !D2 || n_r_max < 2) MFAIL("magic_rloop_set_radial_matrices: bad arguments");
+    rl->n_r_mat = n_r_max;
+    rl->D1h.assign(D1, D1 + (size_t)n_r_max * n_r_max);
+    rl->D2h.assign(D2, D2 + (size_t)n_r_max * n_r_max);
+    if (rl->lmpipe) { lmpipe_free(rl->lmpipe); rl->lmpipe = nullptr; }  // device copies are rebuilt with the next run
+    return 0;
+}
+extern "C" int magic_rloop_set_lm_radial(magic_rloop *rl, int n_r_max, const double *or2, const double *orho1, const double *dentropy0,
+                                         const int *l_R) {
+    if (!rl || !or2 || !orho1 || !dentropy0 || !l_R || n_r_max < 2) MFAIL("magic_rloop_set_lm_radial: bad arguments");
+    rl->lmrad_h.assign(4 * (size_t)n_r_max, 0.0);
+    for (int i = 0; i < n_r_max; i++) {
+        rl->lmrad_h[i] = or2[i];
+        rl->lmrad_h[(size_t)n_r_max + i] = orho1[i];
+        rl->lmrad_h[2 * (size_t)n_r_max + i] = dentropy0[i];
+        rl->lmrad_h[3 * (size_t)n_r_max + i] = (double)l_R[i];
+    }
+    if (rl->lmpipe) { lmpipe_free(rl->lmpipe); rl->lmpipe = nullptr; }
+    return 0;
+}
+extern "C" int magic_rloop_lm_options(magic_rloop *rl, int derivs_on_device, int finish_on_device) {
+    if (!rl) MFAIL("null rloop");
+    if (finish_on_device && (rl->p.l_anelastic_liquid || rl->p.l_single_matrix))
+        MFAIL("magic_rloop_lm_options: the device epilogue covers finish_exp_entropy / _comp / _pol / _mag, not the anelastic-liquid or single-matrix variants");
+    rl->lm_derivs = derivs_on_device ? 1 : 0;
+    rl->lm_finish = finish_on_device ? 1 : 0;
     return 0;
 }
 

@@ -1,6 +1,7 @@
 // api_transp.cu -- C ABI: r <-> LM redistribution (a 5th `type_mpitransp`, mpi_transpose.f90:18-54) with
 // the alltoallv semantics of type_mpiatoav: pack (:320-333 / :490-506), exchange, permuting unpack
-// (:341-357 / :515-528).  The exchange is a grouped ncclSend/ncclRecv all-to-all over NVLink; NCCL is
+// (:341-357 / :515-528).  The exchange is a grouped ncclSend/ncclRecv all-to-all over NVLink that reads / writes the
+// LM-distributed array in place (its blocks are contiguous per peer and field), so only the R side packs; NCCL is
 // resolved at run time (dlopen) so the library loads on machines without it and single-rank use needs none.
 #include <dlfcn.h>
 #include <nccl.h>
@@ -493,25 +494,6 @@ extern "C" int magic_transp_unpack_r2lm_dev(magic_transp *t, const double *recvb
     return side_launch(t, t->n_fields, true, nullptr, arr_LMloc, recvbuf, nullptr);
 }
 
-// all-to-all(v): segment p of sendbuf goes to rank p, segment p of recvbuf comes from rank p
-static int exchange(magic_transp *t, long long nf, const std::vector<long long> &scnt, const std::vector<long long> &sdisp,
-                    const std::vector<long long> &rcnt, const std::vector<long long> &rdisp) {
-    cudaStream_t st = t->stream;
-    const int me = t->rank;
-    if (!t->comm) MFAIL("transposer was created without an NCCL id: only the pack/unpack halves are available");
-    if (scnt[me] > 0)
-        MCHECK(cudaMemcpyAsync(t->recvbuf + 2 * nf * rdisp[me], t->sendbuf + 2 * nf * sdisp[me], sizeof(double) * 2 * nf * scnt[me],
-                               cudaMemcpyDeviceToDevice, st));
-    NCHECK(g_nccl.GroupStart());
-    for (int p = 0; p < t->n_procs; p++) {
-        if (p == me) continue;
-        if (scnt[p] > 0) NCHECK(g_nccl.Send(t->sendbuf + 2 * nf * sdisp[p], (size_t)(2 * nf * scnt[p]), ncclDouble, p, t->comm, st));
-        if (rcnt[p] > 0) NCHECK(g_nccl.Recv(t->recvbuf + 2 * nf * rdisp[p], (size_t)(2 * nf * rcnt[p]), ncclDouble, p, t->comm, st));
-    }
-    NCHECK(g_nccl.GroupEnd());
-    return 0;
-}
-
 // single rank: the packed buffer of the one segment IS arr_LMloc ([f][n_r][lm_lo]), so lm2r / r2lm are one tiled
 // lo<->st permutation without staging
 static int permute_launch(magic_transp *t, int nf, const double *in, double *out, int to_st) {
@@ -519,11 +501,46 @@ static int permute_launch(magic_transp *t, int nf, const double *in, double *out
     return side_launch(t, nf, false, in, nullptr, nullptr, out);              // pack:   arr_R(st) -> buffer(lo)
 }
 
+// The LM side needs no packing: in arr_LMloc ([f][n_r_max][nlm]) the levels of rank q's slab (or of q's part of it) are
+// contiguous rows of every field, and the R-side buffers keep a rank's segment field-major ([f][levels][modes]).  So every
+// (peer, field) block is sent from / received into arr_LMloc directly -- the packing copy of mpi_transpose.f90:320-333 and
+// the unpacking copy of :515-528 (2 x the container through HBM per transpose) do not exist here.
+static int exchange_lm_direct(magic_transp *t, int nf, const double *arr_LM_send, double *arr_LM_recv) {
+    cudaStream_t st = t->stream;
+    const int me = t->rank, n = t->n_procs;
+    if (!t->comm) MFAIL("transposer was created without an NCCL id: only the pack/unpack halves are available");
+    const size_t nlm = (size_t)(t->le[me] - t->ls[me] + 1), frow = nlm * t->n_r_max;  // complex elements per field
+    auto lm_block = [&](int q, int f) { return 2 * ((size_t)f * frow + (size_t)(t->rs[q] - 1) * nlm); };  // doubles
+    // own segment: a strided device copy
+    if (t->lm1[me] > 0) {
+        if (arr_LM_send)
+            MCHECK(cudaMemcpy2DAsync(t->recvbuf + 2 * (size_t)nf * t->rd1[me], sizeof(double) * 2 * t->r1[me], arr_LM_send + lm_block(me, 0),
+                                     sizeof(double) * 2 * frow, sizeof(double) * 2 * t->lm1[me], nf, cudaMemcpyDeviceToDevice, st));
+        else
+            MCHECK(cudaMemcpy2DAsync(arr_LM_recv + lm_block(me, 0), sizeof(double) * 2 * frow, t->sendbuf + 2 * (size_t)nf * t->rd1[me],
+                                     sizeof(double) * 2 * t->r1[me], sizeof(double) * 2 * t->lm1[me], nf, cudaMemcpyDeviceToDevice, st));
+    }
+    NCHECK(g_nccl.GroupStart());
+    for (int p = 0; p < n; p++) {
+        if (p == me) continue;
+        for (int f = 0; f < nf; f++) {
+            if (arr_LM_send) {  // lm2r: my modes of p's levels go out, p's modes of my levels come in
+                if (t->lm1[p] > 0) NCHECK(g_nccl.Send(arr_LM_send + lm_block(p, f), (size_t)(2 * t->lm1[p]), ncclDouble, p, t->comm, st));
+                if (t->r1[p] > 0) NCHECK(g_nccl.Recv(t->recvbuf + 2 * ((size_t)nf * t->rd1[p] + (size_t)f * t->r1[p]), (size_t)(2 * t->r1[p]), ncclDouble, p, t->comm, st));
+            } else {            // r2lm: the mirror image
+                if (t->r1[p] > 0) NCHECK(g_nccl.Send(t->sendbuf + 2 * ((size_t)nf * t->rd1[p] + (size_t)f * t->r1[p]), (size_t)(2 * t->r1[p]), ncclDouble, p, t->comm, st));
+                if (t->lm1[p] > 0) NCHECK(g_nccl.Recv(arr_LM_recv + lm_block(p, f), (size_t)(2 * t->lm1[p]), ncclDouble, p, t->comm, st));
+            }
+        }
+    }
+    NCHECK(g_nccl.GroupEnd());
+    return 0;
+}
+
 extern "C" int magic_transp_lm2r_dev_n(magic_transp *t, int nf, const double *arr_LMloc, double *arr_Rloc) {
     TCHK(t, nf);
     if (t->n_procs == 1) return permute_launch(t, nf, arr_LMloc, arr_Rloc, 1);
-    if (side_launch(t, nf, true, arr_LMloc, nullptr, nullptr, t->sendbuf)) return 1;
-    if (exchange(t, nf, t->lm1, t->lmd1, t->r1, t->rd1)) return 1;
+    if (exchange_lm_direct(t, nf, arr_LMloc, nullptr)) return 1;
     return side_launch(t, nf, false, nullptr, arr_Rloc, t->recvbuf, nullptr);
 }
 
@@ -531,8 +548,7 @@ extern "C" int magic_transp_r2lm_dev_n(magic_transp *t, int nf, const double *ar
     TCHK(t, nf);
     if (t->n_procs == 1) return permute_launch(t, nf, arr_Rloc, arr_LMloc, 0);
     if (side_launch(t, nf, false, arr_Rloc, nullptr, nullptr, t->sendbuf)) return 1;
-    if (exchange(t, nf, t->r1, t->rd1, t->lm1, t->lmd1)) return 1;
-    return side_launch(t, nf, true, nullptr, arr_LMloc, t->recvbuf, nullptr);
+    return exchange_lm_direct(t, nf, nullptr, arr_LMloc);
 }
 
 extern "C" int magic_transp_lm2r_dev(magic_transp *t, const double *arr_LMloc, double *arr_Rloc) {

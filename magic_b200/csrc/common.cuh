@@ -24,20 +24,20 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 64;
 
 struct GemmProb {
-    const double *A0, *A1;  // two K segments of the table operand
+    const double *A0;  // the table operand (P block of one order and parity)
     const double *B;
     double *C;
-    int kt0, kt1;  // k-tiles per segment
-    int M;         // valid rows of C
-    int ldb, ldc;  // leading dimensions of B and C (doubles)
-    int Nvalid;    // real (unpadded) column count: DMMA fragments beyond it are skipped
-    int Mlo;       // synthesis: rows (colatitudes) below Mlo hold only negligible table entries and are skipped
-    int klo;       // analysis: leading k-tiles of each segment skipped for the same reason (B rows shift accordingly)
-    // Triangular polar skipping: ks0/ks1[f] = first k-tile (absolute index inside segment 0/1) that holds a non-negligible
-    // table entry for the 8-row fragment f of the M dimension (255 = none).  Null = no skipping.  A CTA tile starts each
-    // segment at the minimum over its 16 fragments.  (Skipping the DMMAs per fragment as well was measured: the predicate
-    // state costs the 128-register kernel as much as it saves.)
-    const unsigned char *ks0, *ks1;
+    int kt0;           // k-tiles
+    int M;             // valid rows of C
+    int ldb, ldc;      // leading dimensions of B and C (doubles)
+    int Nvalid;        // real (unpadded) column count: DMMA fragments beyond it are skipped
+    int Nstore;        // columns >= Nstore are not stored (= ldc when C is padded to whole tiles)
+    int Mlo;           // synthesis: rows (colatitudes) below Mlo hold only negligible table entries and are skipped
+    int klo;           // analysis: leading k-tiles skipped for the same reason
+    // Triangular polar skipping: ks0[f] = first k-tile that holds a non-negligible table entry for the 8-row fragment f of the
+    // M dimension (255 = none).  Null = no skipping.  A CTA tile starts at the minimum over its 16 fragments.  (Skipping the
+    // DMMAs per fragment as well was measured: the predicate state costs the 128-register kernel as much as it saves.)
+    const unsigned char *ks0;
 };
 
 // factor applied to a spectral source when assembling synthesis operands (sht_native.f90 wrappers)
@@ -65,5 +65,55 @@ struct FftPlan {
 // parity problem s (the symmetric part E = N+S meets the even-parity P rows, O = N-S the odd ones).
 enum RType : int { R_NONE = 0, R_W = 1, R_WS = 2 };
 struct R2cField { int col; int rtype; };
+
+
+// ---- asynchronous-copy and mbarrier helpers (Legendre GEMM pipeline, FFT row prefetch) ---------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+
+// ---- mbarrier helpers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// arrival that fires when all prior cp.async of this thread have landed (does not raise the pending count)
+__device__ __forceinline__ void mbar_cp_async_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// makes the mbarrier initialisation visible to the asynchronous proxy (bulk copies complete on it)
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+// TMA 1-D bulk copy global -> shared (bytes: multiple of 16, both addresses 16-byte aligned); completes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
 
 }  // namespace magic

@@ -228,14 +228,14 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
             const double *P = h->d_tab + h->off[(size_t)mc * 2 + s];
             if (L.ncol) {  // ---- synthesis: F[theta_k, n] = sum_l P(l, theta_k) B[l, n]
                 GemmProb g{};
-                g.A0 = g.A1 = P;
-                g.kt0 = kt; g.kt1 = 0;
+                g.A0 = P;
+                g.kt0 = kt;
                 g.M = nh;
                 g.Mlo = (h->kmin[mc] / 8) * 8;
                 if (h->d_fskip_syn) g.ks0 = h->d_fskip_syn + ((size_t)mc * 2 + s) * h->FS;
                 g.B = buf.B + L.offB[prob];
                 g.C = buf.F + (size_t)prob * nh * L.N;
-                g.ldb = g.ldc = L.N;
+                g.ldb = g.ldc = g.Nstore = L.N;
                 g.Nvalid = 2 * L.ncol * n_lev;
                 const int pid = (int)ps.size();
                 ps.push_back(g);
@@ -245,15 +245,14 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
             }
             if (L.nfa) {   // ---- analysis: C[l, n] = sum_k P(l, theta_k) Ba[k, n]
                 GemmProb g{};
-                g.A0 = g.A1 = P;
+                g.A0 = P;
                 g.M = K;
                 g.klo = h->kmin[mc] / BK;
                 g.kt0 = NHP / BK;  // absolute k-tile count; the kernel starts at max(klo, fragment minimum)
-                g.kt1 = 0;
                 if (h->d_fskip_an) g.ks0 = h->d_fskip_an + ((size_t)mc * 2 + s) * h->FA;
                 g.B = buf.Ba + (size_t)prob * NHP * L.Na;
                 g.C = buf.Ca + L.offC[prob];
-                g.ldb = g.ldc = L.Na;
+                g.ldb = g.ldc = g.Nstore = L.Na;
                 g.Nvalid = 2 * L.nfa * n_lev;
                 const int pid = (int)pa.size();
                 pa.push_back(g);

@@ -225,12 +225,16 @@ __device__ __forceinline__ void twiddle_powers(double2 *w) {
 }
 
 // experiment knobs: minimum resident CTAs per SM handed to __launch_bounds__ (undefined = leave the register choice to ptxas)
-#ifdef MAGIC_FFT_MINB_C
+#ifdef MAGIC_FFT_MAXREG
+#define MAGIC_FFT_LB_C(H) __maxnreg__(MAGIC_FFT_MAXREG)
+#elif defined(MAGIC_FFT_MINB_C)
 #define MAGIC_FFT_LB_C(H) __launch_bounds__(fft2_threads(H), MAGIC_FFT_MINB_C)
 #else
 #define MAGIC_FFT_LB_C(H) __launch_bounds__(fft2_threads(H))
 #endif
-#ifdef MAGIC_FFT_MINB_R
+#ifdef MAGIC_FFT_MAXREG
+#define MAGIC_FFT_LB_R(H) __maxnreg__(MAGIC_FFT_MAXREG)
+#elif defined(MAGIC_FFT_MINB_R)
 #define MAGIC_FFT_LB_R(H) __launch_bounds__(fft2_threads(H), MAGIC_FFT_MINB_R)
 #else
 #define MAGIC_FFT_LB_R(H) __launch_bounds__(fft2_threads(H))
@@ -416,6 +420,204 @@ __global__ void MAGIC_FFT_LB_R(H) fft_r2c_plan_kernel(const double2 *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Prefetching variants of the planned kernels.  A CTA works through `tpc` consecutive row tiles; while tile t runs its
+// barrier-separated Stockham passes, the input of tile t+1 is already on its way into a staging buffer in shared memory:
+//   c2r: the gather of the (theta,m)-space rows (32-byte pieces, one per order) with cp.async (LDGSTS);
+//   r2c: the grid rows (contiguous, 8 n_phi bytes each) with one TMA bulk copy per row (cp.async.bulk, completion on an
+//        mbarrier).
+// The first pass then reads its operands from the staging buffer instead of from global memory, so no warp ever waits a DRAM
+// round trip inside the transform (ncu on the non-prefetching kernels: 40 % of all warp stalls were long-scoreboard stalls at
+// 2 CTAs = 12 warps per SM; the register file, not shared memory, limits the CTA count, so the staging buffer costs no
+// occupancy).  Arithmetic and results are identical to the kernels above.
+// (128 registers: the register file is split over the four SM sub-partitions, a CTA of 6 warps puts 2 warps on two of them,
+//  and two CTAs per SM need 4 warps x 32 lanes x 128 registers = one sub-partition's 16 K registers)
+template <int H>
+__global__ void __maxnreg__(128) fft_c2r_pf_kernel(const double2 *__restrict__ tw, const double *__restrict__ F, int ld, int n_m,
+                                                                  int nh, int ncols, const int *__restrict__ colrow,
+                                                                  double *__restrict__ grid, int tpc) {
+    constexpr int R = fft2_rows(H), NT = fft2_threads(H), N = 2 * H, ROWLEN = fft2_rowlen(H);
+    constexpr int R1 = fft_pick_radix(H), NB1 = H / R1, NI1 = (NB1 + 1) / 2;
+    constexpr int RL = fft_last_radix(H), SL = H / RL;
+    extern __shared__ __align__(16) double2 fsm[];
+    double2 *stage = fsm + R * ROWLEN;  // [n_m][R]
+    const int sk = blockIdx.y, s = sk / nh, k = sk - s * nh;
+    const int ntile = (ncols + R - 1) / R;
+    const int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, ntile);
+    const double *Frow = F + ((size_t)s * nh + k) * ld;
+    const size_t mstride = (size_t)2 * nh * ld;
+    auto gather = [&](int t) {
+        const int cc0 = t * R, rows = min(R, ncols - cc0);
+        for (int idx = threadIdx.x; idx < n_m * R; idx += NT) {
+            const int mc = idx / R, r = idx - mc * R;
+            if (r < rows) cp_async16(stage + idx, Frow + (size_t)mc * mstride + 2 * (cc0 + r));
+            else stage[idx] = make_double2(0.0, 0.0);
+        }
+        cp_async_commit();
+    };
+    if (t0 < t1) gather(t0);
+    for (int t = t0; t < t1; t++) {
+        const int cc0 = t * R, rows = min(R, ncols - cc0);
+        cp_async_wait_all();
+        __syncthreads();  // staging buffer complete; every thread is past the last pass of the previous tile
+        // ---- Hermitian pre-processing + first pass (see fft_c2r_plan_kernel)
+        for (int item = threadIdx.x; item < R * NI1; item += NT) {
+            const int tt = item / R, r = item - tt * R;
+            const bool has_v = (tt > 0) || (NB1 % 2 == 0);
+            const int u = tt, v = (tt > 0) ? NB1 - tt : NB1 / 2;
+            double2 A[R1], B[R1];
+#pragma unroll
+            for (int j = 0; j < R1; j++) {
+                A[j] = make_double2(0.0, 0.0);
+                B[j] = A[j];
+                const int ka = u + NB1 * j, kb = v + NB1 * j;
+                if (ka < n_m) A[j] = stage[ka * R + r];
+                if (has_v && kb < n_m) B[j] = stage[kb * R + r];
+            }
+            double2 *row = fsm + r * ROWLEN;
+            double2 Yu[R1], Yv[R1];
+            if (tt > 0) {
+#pragma unroll
+                for (int j = 0; j < R1; j++) {
+                    const double2 a = A[j], b = B[R1 - 1 - j];
+                    const double2 w = twid(tw, u + NB1 * j, 1.0);
+                    const double2 cb = cconj(b), ca = cconj(a);
+                    Yu[j] = cadd(cadd(a, cb), cmuli(cmul(w, csub(a, cb)), 1.0));
+                    const double2 w2 = make_double2(-w.x, w.y);
+                    Yv[R1 - 1 - j] = cadd(cadd(b, ca), cmuli(cmul(w2, csub(b, ca)), 1.0));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < R1; j++) {
+                    double2 a = A[j];
+                    double2 b = (j == 0) ? make_double2(0.0, 0.0) : A[R1 - j];
+                    if (j == 0) a.y = 0.0;
+                    const double2 w = twid(tw, NB1 * j, 1.0);
+                    const double2 cb = cconj(b);
+                    Yu[j] = cadd(cadd(a, cb), cmuli(cmul(w, csub(a, cb)), 1.0));
+                }
+#pragma unroll
+                for (int j = 0; j < R1; j++) {
+                    const double2 a = B[j], b = B[R1 - 1 - j];
+                    const double2 w = twid(tw, v + NB1 * j, 1.0);
+                    const double2 cb = cconj(b);
+                    Yv[j] = cadd(cadd(a, cb), cmuli(cmul(w, csub(a, cb)), 1.0));
+                }
+            }
+            first_pass_out<H, R1>(row, tw, u, Yu, 1.0);
+            if (has_v) first_pass_out<H, R1>(row, tw, v, Yv, 1.0);
+        }
+        __syncthreads();  // the staging buffer has been consumed
+        if (t + 1 < t1) gather(t + 1);
+        FftMid<H, R, NT, ROWLEN, H / R1, R1>::run(fsm, tw, 1.0);
+        for (int idx = threadIdx.x; idx < R * SL; idx += NT) {
+            const int r = idx / SL, q = idx - r * SL;
+            const double2 *x = fsm + r * ROWLEN;
+            double2 in[RL], o[RL];
+#pragma unroll
+            for (int j = 0; j < RL; j++) in[j] = x[fft_pad(q + SL * j)];
+            butterfly<RL>(in, o, 1.0);
+            if (r < rows) {
+                const int row = colrow[cc0 + r];
+                if (row >= 0) {
+                    double *g = grid + (((size_t)row * 2 + s) * nh + k) * N;
+#pragma unroll
+                    for (int kq = 0; kq < RL; kq++) *reinterpret_cast<double2 *>(g + 2 * (q + SL * kq)) = o[kq];
+                }
+            }
+        }
+    }
+}
+
+template <int H>
+__global__ void __maxnreg__(128) fft_r2c_pf_kernel(const double2 *__restrict__ tw, R2cArgs a, int tpc) {
+    constexpr int R = fft2_rows(H), NT = fft2_threads(H), N = 2 * H, ROWLEN = fft2_rowlen(H);
+    constexpr int R1 = fft_pick_radix(H), NB1 = H / R1;
+    constexpr int RL = fft_last_radix(H), SL = H / RL, NIL = (SL + 1) / 2;
+    extern __shared__ __align__(16) double2 fsm[];
+    double2 *stage = fsm + R * ROWLEN;  // [R][H]
+    __shared__ uint64_t bar;
+    const int sk = blockIdx.y, s = sk / a.nh, k = sk - s * a.nh;
+    const int field = blockIdx.z;
+    const int ntile = (a.n_lev + R - 1) / R;
+    const int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, ntile);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    auto fetch = [&](int t) {  // one thread: arm the barrier with the byte count, then one bulk copy per grid row
+        const int lev0 = t * R, rows = min(R, a.n_lev - lev0);
+        mbar_expect_tx(&bar, (unsigned)(rows * N * sizeof(double)));
+        for (int r = 0; r < rows; r++)
+            bulk_g2s(stage + r * H, a.grid + ((((size_t)field * a.n_lev + lev0 + r) * 2 + s) * a.nh + k) * N, (unsigned)(N * sizeof(double)), &bar);
+    };
+    if (threadIdx.x == 0 && t0 < t1) fetch(t0);
+    const double w = a.wgauss[k], ws = w * a.osin2[k];
+    const R2cField dests = a.fields[field];
+    for (int t = t0; t < t1; t++) {
+        const int lev0 = t * R, rows = min(R, a.n_lev - lev0);
+        mbar_wait(&bar, (t - t0) & 1);
+        // ---- first pass on the staged rows
+        {
+            constexpr int PER = (R * NB1 + NT - 1) / NT;
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const int idx = threadIdx.x + u * NT, r = idx / NB1, b = idx - r * NB1;
+                if (idx < R * NB1) {
+                    double2 reg[R1];
+#pragma unroll
+                    for (int j = 0; j < R1; j++) reg[j] = r < rows ? stage[r * H + b + NB1 * j] : make_double2(0.0, 0.0);
+                    first_pass_out<H, R1>(fsm + r * ROWLEN, tw, b, reg, -1.0);
+                }
+            }
+        }
+        __syncthreads();  // the staged rows have been consumed, the first-pass results are in place
+        if (threadIdx.x == 0 && t + 1 < t1) fetch(t + 1);
+        FftMid<H, R, NT, ROWLEN, H / R1, R1>::run(fsm, tw, -1.0);
+        // ---- last pass + post-processing + scatter (see fft_r2c_plan_kernel)
+        for (int item = threadIdx.x; item < R * NIL; item += NT) {
+            const int tt = item / R, r = item - tt * R;
+            if (r >= rows) continue;
+            const bool has_v = (tt > 0) || (SL % 2 == 0);
+            const int u = tt, v = (tt > 0) ? SL - tt : SL / 2;
+            const double2 *x = fsm + r * ROWLEN;
+            double2 in[RL], Zu[RL], Zv[RL];
+#pragma unroll
+            for (int j = 0; j < RL; j++) in[j] = x[fft_pad(u + SL * j)];
+            butterfly<RL>(in, Zu, -1.0);
+            if (has_v) {
+#pragma unroll
+                for (int j = 0; j < RL; j++) in[j] = x[fft_pad(v + SL * j)];
+                butterfly<RL>(in, Zv, -1.0);
+            }
+            const int lev = lev0 + r;
+            if (tt > 0) {
+#pragma unroll
+                for (int kq = 0; kq < RL; kq++) {
+                    const int mu = u + SL * kq, mv = v + SL * (RL - 1 - kq);  // mu + mv = H
+                    if (mu < a.n_m) r2c_scatter(a, dests, s, k, mu, lev, Zu[kq], Zv[RL - 1 - kq], twid(tw, mu, -1.0), w, ws);
+                    if (mv < a.n_m) r2c_scatter(a, dests, s, k, mv, lev, Zv[RL - 1 - kq], Zu[kq], twid(tw, mv, -1.0), w, ws);
+                }
+            } else {
+#pragma unroll
+                for (int kq = 0; kq < RL; kq++) {
+                    const int mu = SL * kq;
+                    if (mu < a.n_m) r2c_scatter(a, dests, s, k, mu, lev, Zu[kq], kq == 0 ? Zu[0] : Zu[RL - kq], twid(tw, mu, -1.0), w, ws);
+                }
+                if (has_v) {
+#pragma unroll
+                    for (int kq = 0; kq < RL; kq++) {
+                        const int mv = v + SL * kq;
+                        if (mv < a.n_m) r2c_scatter(a, dests, s, k, mv, lev, Zv[kq], Zv[RL - 1 - kq], twid(tw, mv, -1.0), w, ws);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // the last pass has read fsm: the next tile's first pass may overwrite it
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Generic (run-time plan) kernels for lengths without a compiled plan: ping-pong Stockham, radices {4,2,3,5}.
 template <int RX>
 __device__ __forceinline__ void stockham_pass(const double2 *__restrict__ src, double2 *__restrict__ dst, int rows, int H, int len, int s,
@@ -532,6 +734,24 @@ inline bool fft_has_plan(int H) {
     return false;
 }
 inline size_t fft_plan_smem(int H) { return (size_t)fft2_rows(H) * fft2_rowlen(H) * sizeof(double2); }
+inline size_t fft_pf_smem_c2r(int H, int n_m) { return fft_plan_smem(H) + (size_t)n_m * fft2_rows(H) * sizeof(double2); }
+inline size_t fft_pf_smem_r2c(int H) { return fft_plan_smem(H) + (size_t)H * fft2_rows(H) * sizeof(double2); }
+// MAGIC_FFT_PF=0 selects the non-prefetching planned kernels (A/B measurements); tiles per CTA: MAGIC_FFT_TPC (default 8)
+inline bool fft_use_pf() { static int v = -1; if (v < 0) { const char *e = getenv("MAGIC_FFT_PF"); v = (e && atoi(e) == 0) ? 0 : 1; } return v == 1; }
+inline int fft_tpc() { static int v = -1; if (v < 0) { const char *e = getenv("MAGIC_FFT_TPC"); v = e ? max(1, atoi(e)) : 8; } return v; }
+
+// percentage of the 228 KB shared-memory maximum that `ctas` resident CTAs of `bytes` dynamic shared memory (+ 1 KB each) need
+#ifndef MAGIC_FFT_PF_CTAS
+#define MAGIC_FFT_PF_CTAS 2
+#endif
+#ifndef MAGIC_FFT_PLAN_CTAS
+#define MAGIC_FFT_PLAN_CTAS 2
+#endif
+inline int fft_carveout(size_t bytes, int ctas) {
+    const double need = (double)ctas * (double)(bytes + 1024) / (228.0 * 1024.0) * 100.0;
+    int pct = (int)need + 2;
+    return pct > 100 ? 100 : pct;
+}
 
 inline cudaError_t fft_setup_attributes(int H) {
     cudaError_t e = cudaFuncSetAttribute(fft_c2r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -544,6 +764,16 @@ inline cudaError_t fft_setup_attributes(int H) {
         if (e != cudaSuccess) return e;                                                                                   \
         e = cudaFuncSetAttribute(fft_r2c_plan_kernel<h>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_plan_smem(h)); \
         if (e != cudaSuccess) return e;                                                                                   \
+        e = cudaFuncSetAttribute(fft_c2r_pf_kernel<h>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_pf_smem_c2r(h, h)); \
+        if (e != cudaSuccess) return e;                                                                                   \
+        e = cudaFuncSetAttribute(fft_r2c_pf_kernel<h>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_pf_smem_r2c(h)); \
+        if (e != cudaSuccess) return e;                                                                                   \
+        /* shared-memory carve-out: exactly what the resident CTAs need -- the rest of the 256 KB array stays L1, which    \
+           holds the twiddle table (measured: with the whole array carved out as shared memory the c2r kernel loses 50 %) */ \
+        cudaFuncSetAttribute(fft_c2r_pf_kernel<h>, cudaFuncAttributePreferredSharedMemoryCarveout, fft_carveout(fft_pf_smem_c2r(h, h), MAGIC_FFT_PF_CTAS)); \
+        cudaFuncSetAttribute(fft_r2c_pf_kernel<h>, cudaFuncAttributePreferredSharedMemoryCarveout, fft_carveout(fft_pf_smem_r2c(h), MAGIC_FFT_PF_CTAS)); \
+        cudaFuncSetAttribute(fft_c2r_plan_kernel<h>, cudaFuncAttributePreferredSharedMemoryCarveout, fft_carveout(fft_plan_smem(h), MAGIC_FFT_PLAN_CTAS)); \
+        cudaFuncSetAttribute(fft_r2c_plan_kernel<h>, cudaFuncAttributePreferredSharedMemoryCarveout, fft_carveout(fft_plan_smem(h), MAGIC_FFT_PLAN_CTAS)); \
     }
     MAGIC_FFT_PLANS(X)
 #undef X
@@ -555,7 +785,14 @@ inline void launch_fft_c2r(const FftPlan &pl, const double *F, int ld, int n_m, 
     const int H = pl.H;
 #define X(h)                                                                                                                      \
     if (H == h) {                                                                                                                 \
-        dim3 g((ncols + fft2_rows(h) - 1) / fft2_rows(h), 2 * nh);                                                       \
+        const int ntile = (ncols + fft2_rows(h) - 1) / fft2_rows(h);                                                              \
+        if (fft_use_pf() && fft_pf_smem_c2r(h, n_m) <= 110 * 1024) {                                                              \
+            const int tpc = fft_tpc();                                                                                            \
+            dim3 g((ntile + tpc - 1) / tpc, 2 * nh);                                                                              \
+            fft_c2r_pf_kernel<h><<<g, fft2_threads(h), fft_pf_smem_c2r(h, n_m), st>>>(pl.tw, F, ld, n_m, nh, ncols, colrow, grid, tpc); \
+            return;                                                                                                               \
+        }                                                                                                                         \
+        dim3 g(ntile, 2 * nh);                                                                                                    \
         fft_c2r_plan_kernel<h><<<g, fft2_threads(h), fft_plan_smem(h), st>>>(pl.tw, F, ld, n_m, nh, ncols, colrow, grid);          \
         return;                                                                                                                   \
     }
@@ -570,7 +807,14 @@ inline void launch_fft_r2c(const FftPlan &pl, const R2cArgs &a, int nfields, cud
     const int H = pl.H;
 #define X(h)                                                                                      \
     if (H == h) {                                                                                 \
-        dim3 g((a.n_lev + fft2_rows(h) - 1) / fft2_rows(h), 2 * a.nh, nfields);         \
+        const int ntile = (a.n_lev + fft2_rows(h) - 1) / fft2_rows(h);                            \
+        if (fft_use_pf() && fft_pf_smem_r2c(h) <= 110 * 1024) {                                   \
+            const int tpc = fft_tpc();                                                            \
+            dim3 g((ntile + tpc - 1) / tpc, 2 * a.nh, nfields);                                   \
+            fft_r2c_pf_kernel<h><<<g, fft2_threads(h), fft_pf_smem_r2c(h), st>>>(pl.tw, a, tpc);   \
+            return;                                                                               \
+        }                                                                                         \
+        dim3 g(ntile, 2 * a.nh, nfields);                                                         \
         fft_r2c_plan_kernel<h><<<g, fft2_threads(h), fft_plan_smem(h), st>>>(pl.tw, a);            \
         return;                                                                                   \
     }

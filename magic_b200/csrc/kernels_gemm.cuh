@@ -41,124 +41,31 @@ constexpr int B_TILE = BK * LDB_S;
 constexpr int STAGES_M = 4;
 constexpr int STAGES_K = MAGIC_GEMM_SWZ ? 4 : 3;
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-
-// ---- mbarrier helpers ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-// arrival that fires when all prior cp.async of this thread have landed (does not raise the pending count)
-__device__ __forceinline__ void mbar_cp_async_arrive(uint64_t *bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-    unsigned ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    }
-}
-
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
 }
 
+// A CTA works through tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the k-tiles of all its tiles form ONE stream through the
+// stage ring, so with a persistent grid (two CTAs per SM, MAGIC_GEMM_PERSIST=1) the first k-tiles of the next tile are loaded
+// while the last ones of the current tile are multiplied.  MEASURED at l_max=1023, 32-level chunks: persistent 38.1 + 28.1 ms per
+// 64 levels, one tile per CTA (gridDim.x = ntiles, the default) 36.1 + 26.7 ms, bit-identical: the hardware block scheduler
+// balances the very unequal tiles (polar skipping, ragged edges) better than a static round-robin, and the descriptor chain of
+// the next tile (tile -> problem -> skip table) stalls all warps of the persistent CTA at every tile change.
 template <bool A_KCONTIG>
 __global__ void __launch_bounds__(G_THREADS, 2)
-legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict__ tiles, int lda) {
+legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict__ tiles, int ntiles, int lda) {
     extern __shared__ __align__(16) double smem[];
     constexpr int STAGES = A_KCONTIG ? STAGES_K : STAGES_M;
     constexpr int A_TILE = A_KCONTIG ? A_TILE_K : A_TILE_M;
     constexpr int STAGE = A_TILE + B_TILE;
+    constexpr int DIST = STAGES - 2;  // prefetch distance; the remaining stage is the slack between fastest and slowest warp
 
-    const int2 tile = tiles[blockIdx.x];
-    const GemmProb pr = probs[tile.x];
-    const int m0 = (tile.y >> 16) * GEMM_BM, n0 = (tile.y & 0xffff) * GEMM_BN;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
-    // valid 8-row / 8-column fragments of this warp (ragged M of the analysis, padded N): the rest is skipped
-    const int mfr = min(4, max(0, (pr.M - m0 - wm + 7) >> 3)), nfr = min(4, max(0, (pr.Nvalid - n0 - wn + 7) >> 3));
-    const int mlo = min(4, max(0, (pr.Mlo - m0 - wm) >> 3));  // polar skipping: fragments [0, mlo) are all-negligible rows
-    const bool active = mfr > mlo && nfr > 0;
 
-    if (!A_KCONTIG && m0 + GEMM_BM <= pr.Mlo) {
-        // whole tile lies in the negligible polar cap: its rows of F are exact zeros
-        for (int idx = tid; idx < GEMM_BM * (GEMM_BN / 2); idx += G_THREADS) {
-            int row = m0 + idx / (GEMM_BN / 2), c2 = idx % (GEMM_BN / 2);
-            if (row < pr.M) *reinterpret_cast<double2 *>(pr.C + (size_t)row * pr.ldc + n0 + 2 * c2) = make_double2(0.0, 0.0);
-        }
-        return;
-    }
-
-    // ---- k range.  Segment s covers absolute k-tiles [st_s, pr.kt_s): st_s = first tile that holds a non-negligible table
-    //      entry for any of the 16 fragments of this CTA tile (the table of order m is negligible polewards of the turning
-    //      point sin(theta) ~ m/l: a triangle in the (degree, colatitude) plane, of which pr.Mlo / pr.klo only remove the
-    //      rectangle common to all degrees).
-    int st0 = pr.klo, st1 = pr.klo;
-    if (pr.ks0 != nullptr) {
-        auto min16 = [](const unsigned char *p) {
-            const uint4 q = *reinterpret_cast<const uint4 *>(p);
-            const unsigned mn = __vminu4(__vminu4(q.x, q.y), __vminu4(q.z, q.w));
-            return (int)min(min(mn & 255u, (mn >> 8) & 255u), min((mn >> 16) & 255u, mn >> 24));
-        };
-        st0 = max(st0, min(min16(pr.ks0 + (m0 >> 3)), pr.kt0));
-        if (pr.ks1 != nullptr) st1 = max(st1, min16(pr.ks1 + (m0 >> 3)));
-    }
-    st1 = min(st1, pr.kt1);
-    const int n0t = pr.kt0 - st0, KT = n0t + (pr.kt1 - st1);
-    const int kb1 = pr.kt0;  // B row tile of segment 1, tile 0 (the segments are stacked in B)
-
-    auto load_stage = [&](int kt, int st) {
-        double *As = smem + st * STAGE, *Bs = As + A_TILE;
-        const bool seg1 = kt >= n0t;
-        const int ka = seg1 ? st1 + (kt - n0t) : st0 + kt;  // absolute k-tile inside the segment
-        const double *Ab = (seg1 ? pr.A1 : pr.A0) + (size_t)ka * BK * (A_KCONTIG ? 1 : lda);
-        if (!A_KCONTIG) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {  // 16 rows x 64 chunks of 2 doubles
-                int idx = tid + c * G_THREADS, k = idx >> 6, mc = idx & 63;
-                cp_async16(As + k * LDA_M + mc * 2, Ab + (size_t)k * lda + m0 + mc * 2);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {  // 128 rows x 8 chunks
-                int idx = tid + c * G_THREADS, m = idx >> 3, kc = idx & 7;
-                cp_async16(As + m * LDA_K + (MAGIC_GEMM_SWZ ? kc ^ ((m & 3) << 1) : kc) * 2, Ab + (size_t)(m0 + m) * lda + kc * 2);
-            }
-        }
-        const int kb = seg1 ? kb1 + ka : ka;  // B row tile
-        const double *Bb = pr.B + (size_t)kb * BK * pr.ldb + n0;
-#pragma unroll
-        for (int c = 0; c < 2; c++) {  // 16 rows x 32 chunks
-            int idx = tid + c * G_THREADS, k = idx >> 5, nc = idx & 31;
-            cp_async16(Bs + k * LDB_S + nc * 2, Bb + (size_t)k * pr.ldb + nc * 2);
-        }
-    };
-
-    double acc[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    constexpr int DIST = STAGES - 2;  // prefetch distance; the remaining stage is the slack between fastest and slowest warp
     __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES];
     if (tid == 0) {
 #pragma unroll
@@ -168,67 +75,146 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int s = 0; s < DIST; s++)
-        if (s < KT) {
-            load_stage(s, s);
-            mbar_cp_async_arrive(&bar_full[s]);
+
+    // first k-tile of a CTA tile: the first one that holds a non-negligible table entry for any of its 16 row fragments (the
+    // table of order m is negligible polewards of the turning point sin(theta) ~ m/l: a triangle in the (degree, colatitude)
+    // plane, of which Mlo / klo only remove the rectangle common to all degrees); -1: the whole tile lies in the polar cap
+    auto first_ktile = [&](const GemmProb &pr, int m0) -> int {
+        if (!A_KCONTIG && m0 + GEMM_BM <= pr.Mlo) return -1;
+        int st0 = pr.klo;
+        if (pr.ks0 != nullptr) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(pr.ks0 + (m0 >> 3));
+            const unsigned mn = __vminu4(__vminu4(q.x, q.y), __vminu4(q.z, q.w));
+            const int f = (int)min(min(mn & 255u, (mn >> 8) & 255u), min((mn >> 16) & 255u, mn >> 24));
+            st0 = max(st0, min(f, pr.kt0));
         }
-    for (int kt = 0; kt < KT; kt++) {
-        {
-            const int nk = kt + DIST;
-            if (nk < KT) {
-                const int st = nk % STAGES, use = nk / STAGES;
-                if (use > 0) mbar_wait(&bar_empty[st], (use - 1) & 1);  // all warps are done with k-tile nk - STAGES
-                load_stage(nk, st);
-                mbar_cp_async_arrive(&bar_full[st]);
+        return st0;
+    };
+
+    // ---- load cursor: k-tile lkt of lKT of tile lt goes into stage slot gl % STAGES
+    int lt = blockIdx.x - gridDim.x, lkt = 0, lKT = 0, lldb = 0, gl = 0;
+    const double *lA = nullptr, *lB = nullptr;
+    auto load_next = [&]() {
+        while (lkt >= lKT) {  // next tile with work
+            lt += gridDim.x;
+            if (lt >= ntiles) return;
+            const int2 tile = tiles[lt];
+            const GemmProb &pr = probs[tile.x];
+            const int m0 = (tile.y >> 16) * GEMM_BM, n0 = (tile.y & 0xffff) * GEMM_BN;
+            const int st0 = first_ktile(pr, m0);
+            lkt = 0;
+            lKT = st0 < 0 ? 0 : pr.kt0 - st0;
+            if (lKT > 0) {
+                lA = pr.A0 + (A_KCONTIG ? (size_t)m0 * lda + (size_t)st0 * BK : (size_t)st0 * BK * lda + m0);
+                lB = pr.B + (size_t)st0 * BK * pr.ldb + n0;
+                lldb = pr.ldb;
             }
         }
-        mbar_wait(&bar_full[kt % STAGES], (kt / STAGES) & 1);
-        const double *As = smem + (kt % STAGES) * STAGE, *Bs = As + A_TILE;
-        if (active) {
-            auto load_frags = [&](int kk, double *a, double *b) {
+        const int st = gl % STAGES, use = gl / STAGES;
+        if (use > 0) mbar_wait(&bar_empty[st], (use - 1) & 1);  // all warps are done with the k-tile that used this slot
+        double *As = smem + st * STAGE, *Bs = As + A_TILE;
+        if (!A_KCONTIG) {
+            const double *Ab = lA + (size_t)lkt * BK * lda;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    int row = wm + i * 8 + g;
-                    a[i] = A_KCONTIG ? As[row * LDA_K + (MAGIC_GEMM_SWZ ? ((kk * 4 + t) ^ ((g & 3) << 2)) : kk * 4 + t)]
-                                     : As[(kk * 4 + t) * LDA_M + row];
-                }
+            for (int c = 0; c < 4; c++) {  // 16 rows x 64 chunks of 2 doubles
+                int idx = tid + c * G_THREADS, k = idx >> 6, mc = idx & 63;
+                cp_async16(As + k * LDA_M + mc * 2, Ab + (size_t)k * lda + mc * 2);
+            }
+        } else {
+            const double *Ab = lA + (size_t)lkt * BK;
 #pragma unroll
-                for (int j = 0; j < 4; j++) b[j] = Bs[(kk * 4 + t) * LDB_S + wn + j * 8 + g];
-            };
-            auto mma_frags = [&](const double *a, const double *b) {
-                if (mfr == 4 && nfr == 4 && mlo == 0) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            if (i >= mlo && i < mfr && j < nfr) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                }
-            };
-#pragma unroll
-            for (int kk = 0; kk < BK / 4; kk++) {
-                double a[4], b[4];
-                load_frags(kk, a, b);
-                mma_frags(a, b);
+            for (int c = 0; c < 4; c++) {  // 128 rows x 8 chunks
+                int idx = tid + c * G_THREADS, m = idx >> 3, kc = idx & 7;
+                cp_async16(As + m * LDA_K + (MAGIC_GEMM_SWZ ? kc ^ ((m & 3) << 1) : kc) * 2, Ab + (size_t)m * lda + kc * 2);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_empty[kt % STAGES]);
-    }
+        const double *Bb = lB + (size_t)lkt * BK * lldb;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {  // 16 rows x 32 chunks
+            int idx = tid + c * G_THREADS, k = idx >> 5, nc = idx & 31;
+            cp_async16(Bs + k * LDB_S + nc * 2, Bb + (size_t)k * lldb + nc * 2);
+        }
+        mbar_cp_async_arrive(&bar_full[st]);
+        lkt++;
+        gl++;
+    };
 
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        int row = m0 + wm + i * 8 + g;
-        if (row < pr.M) {
-            double *crow = pr.C + (size_t)row * pr.ldc + n0 + wn + 2 * t;
+    for (int s = 0; s < DIST; s++) load_next();
+
+    int gc = 0;  // k-tiles consumed so far
+    for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const int2 tile = tiles[ti];
+        const GemmProb &pr = probs[tile.x];
+        const int m0 = (tile.y >> 16) * GEMM_BM, n0 = (tile.y & 0xffff) * GEMM_BN;
+        const int M = pr.M, ldc = pr.ldc, Nstore = pr.Nstore;
+        double *const C = pr.C;
+        const int st0 = first_ktile(pr, m0);
+        if (st0 < 0) {
+            // whole tile lies in the negligible polar cap: its rows of F are exact zeros
+            for (int idx = tid; idx < GEMM_BM * (GEMM_BN / 2); idx += G_THREADS) {
+                int row = m0 + idx / (GEMM_BN / 2), c2 = idx % (GEMM_BN / 2);
+                if (row < M && n0 + 2 * c2 < Nstore) *reinterpret_cast<double2 *>(C + (size_t)row * ldc + n0 + 2 * c2) = make_double2(0.0, 0.0);
+            }
+            continue;
+        }
+        const int KT = pr.kt0 - st0;
+        // valid 8-row / 8-column fragments of this warp (ragged M of the analysis, padded N): the rest is skipped
+        const int mfr = min(4, max(0, (M - m0 - wm + 7) >> 3)), nfr = min(4, max(0, (pr.Nvalid - n0 - wn + 7) >> 3));
+        const int mlo = min(4, max(0, (pr.Mlo - m0 - wm) >> 3));  // polar skipping: fragments [0, mlo) are all-negligible rows
+        const bool active = mfr > mlo && nfr > 0;
+        const bool full = mfr == 4 && nfr == 4 && mlo == 0;
+
+        double acc[4][4][2];
 #pragma unroll
-            for (int j = 0; j < 4; j++) *reinterpret_cast<double2 *>(crow + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int kt = 0; kt < KT; kt++, gc++) {
+            load_next();  // k-tile gc + DIST of this CTA's stream (it may belong to the next tile)
+            const int st = gc % STAGES;
+            mbar_wait(&bar_full[st], (gc / STAGES) & 1);
+            const double *As = smem + st * STAGE, *Bs = As + A_TILE;
+            if (active) {
+#pragma unroll
+                for (int kk = 0; kk < BK / 4; kk++) {
+                    double a[4], b[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        int row = wm + i * 8 + g;
+                        a[i] = A_KCONTIG ? As[row * LDA_K + (MAGIC_GEMM_SWZ ? ((kk * 4 + t) ^ ((g & 3) << 2)) : kk * 4 + t)]
+                                         : As[(kk * 4 + t) * LDA_M + row];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) b[j] = Bs[(kk * 4 + t) * LDB_S + wn + j * 8 + g];
+                    if (full) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                if (i >= mlo && i < mfr && j < nfr) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[st]);
+        }
+
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int row = m0 + wm + i * 8 + g;
+            if (row < M) {
+                double *crow = C + (size_t)row * ldc + n0 + wn + 2 * t;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (n0 + wn + 2 * t + j * 8 < Nstore) *reinterpret_cast<double2 *>(crow + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
         }
     }
 }
@@ -241,17 +227,29 @@ inline cudaError_t gemm_setup_attributes() {
     cudaError_t e = cudaFuncSetAttribute(legendre_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)gemm_smem_bytes(false));
     if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(legendre_gemm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(legendre_gemm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return cudaFuncSetAttribute(legendre_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)gemm_smem_bytes(true));
 }
 
+// grid: one CTA per tile (MAGIC_GEMM_PERSIST=1: two persistent CTAs per SM, see the kernel's header comment)
 inline void launch_legendre_gemm(bool a_kcontig, const GemmProb *probs, const int2 *tiles, int ntiles, int lda,
                                  cudaStream_t st) {
     if (ntiles <= 0) return;
+    static int ctas = 0;
+    if (ctas == 0) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const char *e = getenv("MAGIC_GEMM_PERSIST");
+        ctas = (e && atoi(e) == 1) ? 2 * sms : (1 << 30);
+    }
+    const int grid = ntiles < ctas ? ntiles : ctas;
     if (a_kcontig)
-        legendre_gemm_kernel<true><<<ntiles, G_THREADS, gemm_smem_bytes(true), st>>>(probs, tiles, lda);
+        legendre_gemm_kernel<true><<<grid, G_THREADS, gemm_smem_bytes(true), st>>>(probs, tiles, ntiles, lda);
     else
-        legendre_gemm_kernel<false><<<ntiles, G_THREADS, gemm_smem_bytes(false), st>>>(probs, tiles, lda);
+        legendre_gemm_kernel<false><<<grid, G_THREADS, gemm_smem_bytes(false), st>>>(probs, tiles, ntiles, lda);
 }
 
 }  // namespace magic

@@ -546,4 +546,48 @@ __global__ void __launch_bounds__(256) extract_td_kernel(ExtractArgs e, TdArgs t
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// finish_explicit_assembly (LMLoop.f90:390-453) on LM-distributed device arrays ([n_r_max][nlm] complex, lo order): the radial
+// derivatives `work` of dVSrLM / dVXirLM / dVxVhLM / dVxBhLM come from the radial-matrix GEMM; this kernel applies
+//   finish_exp_entropy (updateS.f90:543-601):  dsdt  = orho1 (dsdt  - or2 work_s  - l(l+1) or2 dentropy0 w)
+//   finish_exp_comp    (updateXI.f90:478-512): dxidt = orho1 (dxidt - or2 work_xi)
+//   finish_exp_pol     (updateWP.f90:1002-1031): dwdt += or2 work_v   (l > 0)
+//   finish_exp_mag     (updateB.f90:1005-1041):  djdt += or2 work_b   (not the (0,0) mode)
+// each only for l <= l_R(n_r).  Null pointers switch a term off.
+struct FinishArgs {
+    int n_r_max, nlm;
+    const int *lo2l;          // degree of local mode i (lo order)
+    const int *lo2m;
+    const double *or2, *orho1, *dentropy0, *l_R;  // [n_r_max]
+    const double *w;          // LM-distributed w (flow container, field 0)
+    double *dsdt, *dxidt, *dwdt, *djdt;
+    const double *work_s, *work_xi, *work_v, *work_b;
+};
+
+__global__ void __launch_bounds__(256) finish_explicit_kernel(FinishArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, n_r = blockIdx.y;
+    if (i >= a.nlm) return;
+    const int l = a.lo2l[i], m = a.lo2m[i];
+    if ((double)l > a.l_R[n_r]) return;
+    const size_t idx = (size_t)n_r * a.nlm + i;
+    const double or2 = a.or2[n_r], orho1 = a.orho1[n_r];
+    if (a.dsdt) {
+        const double2 d = ldc(a.dsdt, idx), wk = ldc(a.work_s, idx), w = ldc(a.w, idx);
+        const double f = (double)(l * (l + 1)) * or2 * a.dentropy0[n_r];
+        stc(a.dsdt, idx, make_double2(orho1 * (d.x - or2 * wk.x - f * w.x), orho1 * (d.y - or2 * wk.y - f * w.y)));
+    }
+    if (a.dxidt) {
+        const double2 d = ldc(a.dxidt, idx), wk = ldc(a.work_xi, idx);
+        stc(a.dxidt, idx, make_double2(orho1 * (d.x - or2 * wk.x), orho1 * (d.y - or2 * wk.y)));
+    }
+    if (a.dwdt && l > 0) {
+        const double2 d = ldc(a.dwdt, idx), wk = ldc(a.work_v, idx);
+        stc(a.dwdt, idx, make_double2(d.x + or2 * wk.x, d.y + or2 * wk.y));
+    }
+    if (a.djdt && !(l == 0 && m == 0)) {
+        const double2 d = ldc(a.djdt, idx), wk = ldc(a.work_b, idx);
+        stc(a.djdt, idx, make_double2(d.x + or2 * wk.x, d.y + or2 * wk.y));
+    }
+}
+
 }  // namespace magic

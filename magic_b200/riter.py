@@ -160,6 +160,20 @@ class RadialLoop:
         o = _LmOut(a(lm_out, "dflowdt"), a(lm_out, "dsdt"), a(lm_out, "dbdt"), dtrkc.ctypes.data, dthkc.ctypes.data, a(lm_out, "dxidt"))
         check(self.lib.magic_rloop_run_lm(self._h, transposer._h, byref(i), byref(o), c_double(time)))
 
+    def set_radial_matrices(self, D1, D2):
+        """Dense matrices of the host's radial scheme (get_dr / get_ddr incl. the n_cheb_max truncation), [n_r_max, n_r_max]."""
+        D1 = np.ascontiguousarray(D1, dtype=np.float64)
+        D2 = np.ascontiguousarray(D2, dtype=np.float64)
+        check(self.lib.magic_rloop_set_radial_matrices(self._h, c_int(D1.shape[0]), c_void_p(D1.ctypes.data), c_void_p(D2.ctypes.data)))
+
+    def set_lm_radial(self, or2, orho1, dentropy0, l_R):
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (or2, orho1, dentropy0)]
+        lr = np.ascontiguousarray(l_R, dtype=np.int32)
+        check(self.lib.magic_rloop_set_lm_radial(self._h, c_int(len(lr)), *[c_void_p(x.ctypes.data) for x in a], c_void_p(lr.ctypes.data)))
+
+    def lm_options(self, derivs_on_device=False, finish_on_device=False):
+        check(self.lib.magic_rloop_lm_options(self._h, c_int(int(derivs_on_device)), c_int(int(finish_on_device))))
+
     def set_rotation(self, omega_ma, omega_ic):
         """Boundary rotation rates of the coming step (omega_ma, omega_ic of v_rigid_boundary)."""
         check(self.lib.magic_rloop_set_rotation(self._h, c_double(omega_ma), c_double(omega_ic)))
