@@ -43,6 +43,17 @@ module magic_b200_c
       type(c_ptr) :: dtrkc, dthkc
    end type magic_fields_out
 
+   !-- LM-distributed containers of magic_rloop_run_lm (fields.f90:211-268, dt_fieldsLast.f90:125-214)
+   type, bind(C) :: magic_lm_in
+      type(c_ptr) :: flow, s, field, xi
+   end type magic_lm_in
+
+   type, bind(C) :: magic_lm_out
+      type(c_ptr) :: dflowdt, dsdt, dbdt
+      type(c_ptr) :: dtrkc, dthkc
+      type(c_ptr) :: dxidt
+   end type magic_lm_out
+
    interface
 
       !---------------------------------------------------------------- C library
@@ -242,6 +253,15 @@ module magic_b200_c
          real(c_double), value :: time
          integer(c_int) :: ierr
       end function magic_rloop_run
+
+      function magic_rloop_run_lm(rl, t, lin, lout, time) bind(C, name='magic_rloop_run_lm') result(ierr)
+         import :: c_int, c_ptr, c_double, magic_lm_in, magic_lm_out
+         type(c_ptr), value :: rl, t
+         type(magic_lm_in),  intent(in) :: lin
+         type(magic_lm_out), intent(in) :: lout
+         real(c_double), value :: time
+         integer(c_int) :: ierr
+      end function magic_rloop_run_lm
 
       function magic_rloop_pin_host(rl, ptr, bytes) bind(C, name='magic_rloop_pin_host') result(ierr)
          import :: c_int, c_ptr, c_size_t

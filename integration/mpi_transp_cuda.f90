@@ -30,6 +30,23 @@ module mpi_transp_cuda_mod
 
    private
 
+   !-- Fused mode (l_fused_lm): MagIC's step is transp_LMloc_to_Rloc -> radialLoopG -> transp_Rloc_to_LMloc
+   !   (step_time.f90:485-612).  With the CPU-resident LM loop all three cross PCIe; magic_rloop_run_lm does them in ONE call
+   !   on the LM-distributed host containers, chunk-pipelined, without intermediate host R-containers.  step_time.f90 stays
+   !   untouched: in fused mode transp_lm2r only RECORDS its request (the loop of the same stage picks the LM containers up
+   !   itself), and transp_r2lm returns at once when the loop has already delivered the LM-distributed explicit terms.  On
+   !   steps with in-loop diagnostics rIter_cuda_t falls back to the level-at-a-time loop: it first executes the recorded
+   !   requests (run_pending_lm2r) so that the R-distributed host arrays exist, and clears l_outputs_in_lm so that the
+   !   transposes back are real.
+   logical, public :: l_fused_lm = .true.
+   logical, public :: l_outputs_in_lm = .false.
+   integer, parameter :: n_pending_max = 8
+   integer, public :: n_pending = 0
+   type(c_ptr) :: pending_t(n_pending_max), pending_lm(n_pending_max), pending_r(n_pending_max)
+   type(c_ptr), public :: transp5 = c_null_ptr   ! a transposer that serves containers of up to 5 fields (the loop needs one)
+
+   public :: run_pending_lm2r
+
    type, public, extends(type_mpitransp) :: type_mpicuda
       type(c_ptr) :: t = c_null_ptr
    contains
@@ -66,6 +83,7 @@ contains
       if ( llm_c /= llm .or. ulm_c /= ulm .or. nRstart_c /= nRstart .or. nRstop_c /= nRstop ) then
          call abortRun('! type_mpicuda: the library and MagIC disagree on llm:ulm / nRstart:nRstop')
       end if
+      if ( n_fields >= 5 .and. .not. c_associated(transp5) ) transp5 = this%t
 
    end subroutine create_comm_cuda
 !------------------------------------------------------------------------------
@@ -84,6 +102,14 @@ contains
       complex(cp), intent(in)  :: arr_LMloc(llm:ulm,1:n_r_max,*)
       complex(cp), intent(out) :: arr_Rloc(1:lm_max,nRstart:nRstop,*)
 
+      if ( l_fused_lm ) then   ! record only: the radial loop of this stage either fuses it or executes it
+         if ( n_pending == n_pending_max ) call abortRun('! type_mpicuda: too many pending transposes')
+         n_pending = n_pending+1
+         pending_t(n_pending)  = this%t
+         pending_lm(n_pending) = c_loc(arr_LMloc)
+         pending_r(n_pending)  = c_loc(arr_Rloc)
+         return
+      end if
       call magic_check( magic_transp_lm2r(this%t, arr_LMloc, arr_Rloc), 'magic_transp_lm2r' )
 
    end subroutine transp_lm2r_cuda
@@ -94,8 +120,26 @@ contains
       complex(cp), intent(in)  :: arr_Rloc(1:lm_max,nRstart:nRstop,*)
       complex(cp), intent(out) :: arr_LMloc(llm:ulm,1:n_r_max,*)
 
+      if ( l_fused_lm .and. l_outputs_in_lm ) return   ! magic_rloop_run_lm has written arr_LMloc already
       call magic_check( magic_transp_r2lm(this%t, arr_Rloc, arr_LMloc), 'magic_transp_r2lm' )
 
    end subroutine transp_r2lm_cuda
+!------------------------------------------------------------------------------
+   subroutine run_pending_lm2r()
+      !
+      ! Executes the transposes recorded in fused mode (host pointers: H2D, exchange, D2H), e.g. before a diagnostics step
+      ! that needs the R-distributed host arrays.
+      !
+      integer :: n
+      complex(cp), pointer :: a_lm(:), a_r(:)
+
+      do n=1,n_pending
+         call c_f_pointer(pending_lm(n), a_lm, [1])
+         call c_f_pointer(pending_r(n), a_r, [1])
+         call magic_check( magic_transp_lm2r(pending_t(n), a_lm, a_r), 'magic_transp_lm2r (pending)' )
+      end do
+      n_pending = 0
+
+   end subroutine run_pending_lm2r
 !------------------------------------------------------------------------------
 end module mpi_transp_cuda_mod

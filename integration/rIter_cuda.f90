@@ -29,7 +29,12 @@ module rIter_cuda_mod
        &                       epscProf, l_R, r_cmb, r_icb
    use num_param, only: delxr2, delxh2
    use fields, only: s_Rloc, ds_Rloc, z_Rloc, dz_Rloc, p_Rloc, b_Rloc, db_Rloc, ddb_Rloc, aj_Rloc, dj_Rloc, &
-       &             w_Rloc, dw_Rloc, ddw_Rloc, xi_Rloc, omega_ic, omega_ma
+       &             w_Rloc, dw_Rloc, ddw_Rloc, xi_Rloc, omega_ic, omega_ma,                                &
+       &             flow_LMloc_container, s_LMloc_container, field_LMloc_container, xi_LMloc_container
+   use dt_fieldsLast, only: dflowdt_LMloc_container, dsdt_LMloc_container, dbdt_LMloc_container,            &
+       &                    dxidt_LMloc_container
+   use blocking, only: llm
+   use mpi_transp_cuda_mod, only: l_fused_lm, l_outputs_in_lm, n_pending, transp5, run_pending_lm2r
    use time_schemes, only: type_tscheme
    use rIteration, only: rIter_t
    use rIter_mod, only: rIter_single_t
@@ -204,6 +209,9 @@ contains
       !-- Local variables
       type(magic_fields_in)  :: fin
       type(magic_fields_out) :: fout
+      type(magic_lm_in)      :: lin
+      type(magic_lm_out)     :: lout
+      integer :: ist
 
       !-- Diagnostics steps keep the reference's level-at-a-time loop (its transforms still run on the GPU)
       if ( l_graph .or. l_frame .or. lTOCalc .or. lTONext .or. lTONext2 .or. lHelCalc .or. lPowerCalc .or.   &
@@ -211,6 +219,10 @@ contains
       &    lHemiCalc .or. lPhaseCalc .or. l_probe_out .or. ( lPressNext .and. l_double_curl ) ) then
          !-- ( lPressNext with the double-curl equation: the reference also calls get_dpdt then (rIter.f90:420); the batched
          !   loop only produces dpdt in the pressure formulation, so that step takes the level-at-a-time loop )
+         if ( l_fused_lm ) then   ! the recorded transposes become real: the level-at-a-time loop reads the host R arrays
+            call run_pending_lm2r()
+            l_outputs_in_lm = .false.
+         end if
          call this%single%radialLoop(l_graph,l_frame,time,timeStage,tscheme,dtLast,lTOCalc,lTONext,lTONext2,   &
               &                      lHelCalc,lPowerCalc,lRmsCalc,lPressCalc,lPressNext,lViscBcCalc,           &
               &                      lFluxProfCalc,lPerpParCalc,lGeosCalc,lHemiCalc,lPhaseCalc,l_probe_out,    &
@@ -221,6 +233,35 @@ contains
       end if
 
       if ( .not. c_associated(this%rl) ) call this%create_plan(tscheme)
+
+      !-- Fused mode: LM-distributed host containers in, LM-distributed explicit terms out -- the transposes on either side of
+      !   this call (step_time.f90:485, :612) are part of it (mpi_transp_cuda_mod); the explicit terms go into the slice
+      !   tscheme%istage of the time-array containers, which is where transp_Rloc_to_LMloc would put them (step_time.f90:1134-1245)
+      if ( l_fused_lm .and. n_pending > 0 .and. .not. ( l_b_nl_cmb .or. l_b_nl_icb ) ) then
+         ist = tscheme%istage
+         lin  = magic_lm_in(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr)
+         lout = magic_lm_out(c_null_ptr, c_null_ptr, c_null_ptr, addr_r(dtrkc), addr_r(dthkc), c_null_ptr)
+         if ( l_conv .or. l_mag_kin ) lin%flow = c_loc(flow_LMloc_container)
+         if ( l_heat ) lin%s = c_loc(s_LMloc_container)
+         if ( l_mag .or. l_mag_LF ) lin%field = c_loc(field_LMloc_container)
+         if ( l_chemical_conv ) lin%xi = c_loc(xi_LMloc_container)
+         if ( l_conv ) lout%dflowdt = c_loc(dflowdt_LMloc_container(llm,1,1,ist))
+         if ( l_heat ) lout%dsdt = c_loc(dsdt_LMloc_container(llm,1,1,ist))
+         if ( l_mag ) lout%dbdt = c_loc(dbdt_LMloc_container(llm,1,1,ist))
+         if ( l_chemical_conv ) lout%dxidt = c_loc(dxidt_LMloc_container(llm,1,1,ist))
+         call magic_check( magic_rloop_set_rotation(this%rl, omega_ma, omega_ic), 'magic_rloop_set_rotation' )
+         call magic_check( magic_rloop_run_lm(this%rl, transp5, lin, lout, timeStage), 'magic_rloop_run_lm' )
+         call magic_check( magic_rloop_get_torques(this%rl, lorentz_torque_ic, lorentz_torque_ma), &
+              &            'magic_rloop_get_torques' )
+         n_pending = 0
+         l_outputs_in_lm = .true.
+         dphidt(:,:) = zero
+         return
+      end if
+      if ( l_fused_lm ) then   ! (nonlinear magnetic boundary products need the R-distributed path: rIter.f90:267-277)
+         call run_pending_lm2r()
+         l_outputs_in_lm = .false.
+      end if
 
       !-- Inputs: the R-distributed containers of fields.f90:211-268, (lm_max, nRstart:nRstop) each; the library
       !   ignores the pointers of switched-off physics

@@ -59,7 +59,7 @@ def test_every_bound_name_is_exported_by_the_library():
 def test_bind_c_types_mirror_the_c_structs():
     f = _read("integration", "magic_b200_c.f90")
     h = _read("include", "magic_sht.h")
-    for name in ("magic_params", "magic_radial", "magic_fields_in", "magic_fields_out"):
+    for name in ("magic_params", "magic_radial", "magic_fields_in", "magic_fields_out", "magic_lm_in", "magic_lm_out"):
         assert _fortran_type(f, name) == _c_struct(h, name), name
     # and the Python mirror agrees with both
     from magic_b200.riter import Params
