@@ -954,16 +954,39 @@ static int lm_run(magic_rloop *rl, magic_transp *t, const double *const lm_in[4]
     };
     // Queue order on the communication stream -- identical on every rank, also for ranks with fewer chunks than C (they have
     // no levels in the late parts, their peers do): in(0) .. in(DIST-1), then per chunk c: in(c+DIST), [compute c], out(c).
+    // MAGIC_LM_ALIGN=1: the transposes of an iteration (in(c+DIST), out(c-1)) start when chunk c enters its synthesis GEMM --
+    // HBM-bound pack / unpack kernels then share the machine with a tensor-bound kernel instead of with the HBM-bound
+    // operand assembly and FFTs.
+    static int align = -1;
+    if (align < 0) { const char *e = getenv("MAGIC_LM_ALIGN"); align = e ? atoi(e) : 0; }
     const int DIST = 2, nloc = (int)rl->chunk_start.size();
     for (int c = 0; c < std::min(DIST, p->C); c++)
         if (inbound(c)) return 1;
-    for (int c = 0; c < p->C; c++) {
-        if (c + DIST < p->C && inbound(c + DIST)) return 1;
-        if (c < nloc) {
-            MCHECK(cudaStreamWaitEvent(h->stream, p->ev_in[c], 0));
-            if (rloop_chunk(rl, c, x)) return 1;
+    if (!align) {
+        for (int c = 0; c < p->C; c++) {
+            if (c + DIST < p->C && inbound(c + DIST)) return 1;
+            if (c < nloc) {
+                MCHECK(cudaStreamWaitEvent(h->stream, p->ev_in[c], 0));
+                if (rloop_chunk(rl, c, x)) return 1;
+            }
+            if (outbound(c, c < nloc)) return 1;
         }
-        if (outbound(c, c < nloc)) return 1;
+    } else {
+        for (int c = 0; c < p->C; c++) {
+            if (c < nloc) {
+                MCHECK(cudaStreamWaitEvent(h->stream, p->ev_in[c], 0));
+                if (rloop_chunk(rl, c, x)) return 1;
+                MCHECK(cudaEventRecord(p->ev_out[c], h->stream));
+                MCHECK(cudaStreamWaitEvent(p->comm, rl->cev[10 * (size_t)c + 1], 0));  // chunk c has finished its operand assembly
+            }
+            if (c + DIST < p->C && inbound(c + DIST)) return 1;
+            if (c > 0) {
+                if (c - 1 < nloc) MCHECK(cudaStreamWaitEvent(p->comm, p->ev_out[c - 1], 0));
+                if (outbound(c - 1, false)) return 1;
+            }
+        }
+        if (p->C - 1 < nloc) MCHECK(cudaStreamWaitEvent(p->comm, p->ev_out[p->C - 1], 0));
+        if (outbound(p->C - 1, false)) return 1;
     }
     MCHECK(cudaEventRecord(p->ev_done, p->comm));
     MCHECK(cudaStreamWaitEvent(h->stream, p->ev_done, 0));

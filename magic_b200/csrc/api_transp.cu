@@ -243,6 +243,28 @@ __global__ void permute_kernel(const double2 *__restrict__ in, double2 *__restri
     else out[idx] = in[st];
 }
 
+// ---- copy-engine exchange: cross-process flags in IPC-shared device memory -----------------------------------------------
+// slot[q] points at MY entry of peer q's flag array (mapped through CUDA IPC); the store is ordered after everything this
+// stream did before (the peer copies) and made visible system-wide
+__global__ void ce_signal_kernel(unsigned long long *const *slot, int n, int me, unsigned long long seq) {
+    const int q = threadIdx.x;
+    if (q < n && q != me) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(slot[q]) = seq;
+    }
+}
+// spins until every peer's flag has reached seq; traps instead of hanging when a peer never arrives (20 s)
+__global__ void ce_wait_kernel(const volatile unsigned long long *flags, int n, int me, unsigned long long seq) {
+    const int p = threadIdx.x;
+    if (p < n && p != me) {
+        const long long t0 = clock64();
+        while (flags[p] < seq) {
+            if (clock64() - t0 > 40000000000LL) __trap();
+        }
+        __threadfence_system();
+    }
+}
+
 }  // namespace
 
 struct magic_transp {
@@ -254,6 +276,15 @@ struct magic_transp {
     long long *d_lmdisp = nullptr, *d_rdisp = nullptr;
     double *sendbuf = nullptr, *recvbuf = nullptr, *stage_lm = nullptr, *stage_r = nullptr;
     ncclComm_t comm = nullptr;
+    // copy-engine exchange (MAGIC_TRANSP_CE=1; measured equal to the NCCL exchange at N = 2, so NCCL stays the default): peers'
+    // receive buffers mapped into this process;
+    // the payload moves with cudaMemcpy2DAsync (DMA engines over NVLink, no SM), arrival / release are flagged in IPC memory
+    bool ce = false;
+    size_t half = 0;                                   // doubles per half of the double-buffered receive buffer
+    std::vector<double *> peer_base;                   // [n_procs] peer q's receive buffer in my address space (own: recvbuf)
+    unsigned long long *my_flags = nullptr;            // [2][n_procs] in my receive allocation: arrival flags, release flags
+    unsigned long long **d_slot_data = nullptr, **d_slot_ack = nullptr;  // my entries in the peers' flag arrays
+    unsigned long long *seq = nullptr;                 // host counter of exchanges, shared by a parent and its parts
     PackArgs args;
     cudaStream_t stream = nullptr;   // stream of the pack / exchange / unpack work (default: the handle's stream)
     magic_transp *parent = nullptr;  // a part shares maps, buffers and communicator with its parent
@@ -300,10 +331,100 @@ extern "C" int magic_transp_destroy(magic_transp *t) {
         delete t;
         return 0;
     }
+    if (t->ce) {
+        for (int p = 0; p < t->n_procs; p++)
+            if (p != t->rank && t->peer_base[p]) cudaIpcCloseMemHandle(t->peer_base[p]);
+        cudaFree(t->d_slot_data); cudaFree(t->d_slot_ack);
+    }
+    delete t->seq;
     if (t->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(t->comm);
     cudaFree(t->d_rstart); cudaFree(t->d_rcount); cudaFree(t->d_lstart); cudaFree(t->d_lcount); cudaFree(t->d_lo2st); cudaFree(t->d_st2lo);
     cudaFree(t->d_lmdisp); cudaFree(t->d_rdisp); cudaFree(t->sendbuf); cudaFree(t->recvbuf); cudaFree(t->stage_lm); cudaFree(t->stage_r);
     delete t;
+    return 0;
+}
+
+// Maps every peer's receive buffer into this process: the IPC handles travel through the NCCL communicator (one 64-byte
+// message per peer pair).  Leaves t->ce false (NCCL send/recv stays the exchange) when the devices cannot do peer access.
+static int ce_setup(magic_transp *t) {
+    const int n = t->n_procs, me = t->rank;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, t->recvbuf) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (getenv("MAGIC_TRANSP_DEBUG")) {  // a recognisable word behind the flag arrays
+        unsigned long long tag = 1000 + me;
+        cudaMemcpy(reinterpret_cast<unsigned long long *>(t->recvbuf + 2 * t->half) + 2 * n, &tag, 8, cudaMemcpyHostToDevice);
+    }
+    std::vector<cudaIpcMemHandle_t> all(n);
+    double *d_h = nullptr;
+    MCHECK(cudaMalloc((void **)&d_h, 64 * (size_t)n));
+    MCHECK(cudaMemcpyAsync(d_h + 8 * me, &mine, 64, cudaMemcpyHostToDevice, t->stream));
+    NCHECK(g_nccl.GroupStart());
+    for (int p = 0; p < n; p++) {
+        if (p == me) continue;
+        NCHECK(g_nccl.Send(d_h + 8 * me, 8, ncclDouble, p, t->comm, t->stream));
+        NCHECK(g_nccl.Recv(d_h + 8 * p, 8, ncclDouble, p, t->comm, t->stream));
+    }
+    NCHECK(g_nccl.GroupEnd());
+    MCHECK(cudaMemcpyAsync(all.data(), d_h, 64 * (size_t)n, cudaMemcpyDeviceToHost, t->stream));
+    MCHECK(cudaStreamSynchronize(t->stream));
+    cudaFree(d_h);
+    t->peer_base.assign(n, nullptr);
+    t->peer_base[me] = t->recvbuf;
+    bool ok = true;
+    for (int p = 0; p < n && ok; p++) {
+        if (p == me) continue;
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        t->peer_base[p] = (double *)ptr;
+    }
+    // every rank must take the same path: agree through one more tiny exchange (1.0 = mapped all peers)
+    {
+        double *d_ok = nullptr;
+        MCHECK(cudaMalloc((void **)&d_ok, sizeof(double) * (size_t)n));
+        std::vector<double> oks(n, 0.0);
+        oks[me] = ok ? 1.0 : 0.0;
+        MCHECK(cudaMemcpyAsync(d_ok, oks.data(), sizeof(double) * n, cudaMemcpyHostToDevice, t->stream));
+        NCHECK(g_nccl.GroupStart());
+        for (int p = 0; p < n; p++) {
+            if (p == me) continue;
+            NCHECK(g_nccl.Send(d_ok + me, 1, ncclDouble, p, t->comm, t->stream));
+            NCHECK(g_nccl.Recv(d_ok + p, 1, ncclDouble, p, t->comm, t->stream));
+        }
+        NCHECK(g_nccl.GroupEnd());
+        MCHECK(cudaMemcpyAsync(oks.data(), d_ok, sizeof(double) * n, cudaMemcpyDeviceToHost, t->stream));
+        MCHECK(cudaStreamSynchronize(t->stream));
+        cudaFree(d_ok);
+        for (int p = 0; p < n; p++) ok = ok && oks[p] == 1.0;
+    }
+    if (!ok) {
+        for (int p = 0; p < n; p++)
+            if (p != me && t->peer_base[p]) cudaIpcCloseMemHandle(t->peer_base[p]);
+        t->peer_base.clear();
+        return 0;
+    }
+    if (getenv("MAGIC_TRANSP_DEBUG")) {
+        for (int p = 0; p < n; p++) {
+            cudaPointerAttributes at{};
+            cudaError_t e = cudaPointerGetAttributes(&at, t->peer_base[p]);
+            int can = -1;
+            if (at.device >= 0 && at.device != t->h->dev) cudaDeviceCanAccessPeer(&can, t->h->dev, at.device);
+            unsigned long long probe = 0, hh[2];
+            memcpy(hh, &all[p], 16);
+            cudaError_t e2 = cudaMemcpy(&probe, reinterpret_cast<unsigned long long *>(t->peer_base[p] + 2 * t->half) + 2 * n, 8, cudaMemcpyDefault);
+            fprintf(stderr, "[magic_transp rank %d dev %d] peer %d base %p attr rc=%d type=%d device=%d canAccessPeer=%d half=%zu handle=%016llx%016llx probe rc=%d val=%llu\n",
+                    me, t->h->dev, p, (void *)t->peer_base[p], (int)e, (int)at.type, at.device, can, t->half, hh[0], hh[1], (int)e2, probe);
+        }
+        cudaGetLastError();
+    }
+    std::vector<unsigned long long *> sd(n, nullptr), sa(n, nullptr);
+    for (int p = 0; p < n; p++) {
+        unsigned long long *pf = reinterpret_cast<unsigned long long *>(t->peer_base[p] + 2 * t->half);
+        sd[p] = pf + me;        // arrival flag "from me" at peer p
+        sa[p] = pf + n + me;    // release flag "by me" at peer p
+    }
+    if (dev_upload_vec(&t->d_slot_data, sd) || dev_upload_vec(&t->d_slot_ack, sa)) return 1;
+    t->ce = true;
     return 0;
 }
 
@@ -350,7 +471,16 @@ extern "C" int magic_transp_create(magic_sht *h, const char id[128], int rank, i
     if (n_procs > 1) {
         size_t maxel = (size_t)std::max(t->lmd1[n_procs], t->rd1[n_procs]) * n_fields;
         MCHECK(cudaMalloc((void **)&t->sendbuf, sizeof(double) * 2 * maxel));
-        MCHECK(cudaMalloc((void **)&t->recvbuf, sizeof(double) * 2 * maxel));
+        // receive buffer: two halves (exchange k lands in half k & 1) + the flag words of the copy-engine exchange.  The half
+        // size is the same on every rank (the largest need of any rank): peers address my halves and flags with their own copy
+        size_t gmax = 0;
+        for (int p = 0; p < n_procs; p++)
+            gmax = std::max(gmax, std::max((size_t)n_r_max * (size_t)lcount[p], (size_t)rcount[p] * (size_t)h->lm_max));
+        t->half = (2 * gmax * n_fields + 31) / 32 * 32;
+        MCHECK(cudaMalloc((void **)&t->recvbuf, sizeof(double) * 2 * t->half + 4096));
+        MCHECK(cudaMemset(t->recvbuf + 2 * t->half, 0, 4096));
+        t->my_flags = reinterpret_cast<unsigned long long *>(t->recvbuf + 2 * t->half);
+        t->seq = new unsigned long long(0);
         // id == NULL: no communicator (pack/unpack halves only -- used to test the permutation kernels in one process)
         if (id) {
             if (nccl_load()) { magic_transp_destroy(t); return 1; }
@@ -362,6 +492,10 @@ extern "C" int magic_transp_create(magic_sht *h, const char id[128], int rank, i
                 t->comm = nullptr;
                 magic_transp_destroy(t);
                 return 1;
+            }
+            const char *e = getenv("MAGIC_TRANSP_CE");
+            if (e && atoi(e) == 1 && 2 * n_procs * sizeof(unsigned long long) <= 4096) {
+                if (ce_setup(t)) { magic_transp_destroy(t); return 1; }
             }
         }
     }
@@ -505,6 +639,51 @@ static int permute_launch(magic_transp *t, int nf, const double *in, double *out
 // contiguous rows of every field, and the R-side buffers keep a rank's segment field-major ([f][levels][modes]).  So every
 // (peer, field) block is sent from / received into arr_LMloc directly -- the packing copy of mpi_transpose.f90:320-333 and
 // the unpacking copy of :515-528 (2 x the container through HBM per transpose) do not exist here.
+// Copy-engine form of the exchange.  Exchange number k of this communicator lands in half k & 1 of the receivers' buffers:
+//   wait until every peer has released what exchange k-2 put there -> peer copies (2-D DMA, one per peer) -> raise my arrival
+//   flag at every peer -> wait for all arrival flags -> [caller unpacks] -> ce_release raises my release flag at every peer.
+// Returns the half that holds the received data.
+static int ce_exchange(magic_transp *t, int nf, const double *arr_LM_send, bool r2lm, double **recv_half) {
+    cudaStream_t st = t->stream;
+    const int me = t->rank, n = t->n_procs;
+    const unsigned long long seq = ++(*t->seq);
+    const size_t hoff = (seq & 1ULL) * t->half;
+    *recv_half = t->recvbuf + hoff;
+    const size_t nlm = (size_t)(t->le[me] - t->ls[me] + 1), frow = nlm * t->n_r_max;
+    if (seq > 2) ce_wait_kernel<<<1, n, 0, st>>>(t->my_flags + n, n, me, seq - 2);
+    const size_t c16 = sizeof(double) * 2;
+    if (!r2lm) {
+        // my modes of q's levels -> q's buffer, segment "from me": [f][levels of q][my modes], contiguous
+        for (int q = 0; q < n; q++) {
+            if (t->lm1[q] == 0) continue;
+            const size_t nr_q = (size_t)(t->re[q] - t->rs[q] + 1);
+            const size_t dst = 2 * (size_t)nf * nr_q * (size_t)(t->ls[me] - t->ls[0]);  // nf * rd1 as rank q computes it
+            MCHECK(cudaMemcpy2DAsync(t->peer_base[q] + hoff + dst, c16 * t->lm1[q], arr_LM_send + 2 * (size_t)(t->rs[q] - 1) * nlm, c16 * frow,
+                                     c16 * t->lm1[q], nf, cudaMemcpyDefault, st));
+        }
+    } else {
+        // my levels of p's modes (packed in sendbuf, segment p: [f][my levels][modes of p]) -> p's buffer, segment "from me"
+        size_t lev_before = 0;  // levels of the ranks before me (of this part)
+        for (int q = 0; q < me; q++) lev_before += (size_t)(t->re[q] - t->rs[q] + 1);
+        for (int p = 0; p < n; p++) {
+            if (t->r1[p] == 0) continue;
+            const size_t nlm_p = (size_t)(t->le[p] - t->ls[p] + 1);
+            const size_t dst = 2 * (size_t)nf * lev_before * nlm_p;  // nf * lmd1 as rank p computes it
+            MCHECK(cudaMemcpyAsync(t->peer_base[p] + hoff + dst, t->sendbuf + 2 * (size_t)nf * t->rd1[p], c16 * (size_t)nf * t->r1[p],
+                                   cudaMemcpyDefault, st));
+        }
+    }
+    ce_signal_kernel<<<1, n, 0, st>>>(t->d_slot_data, n, me, seq);
+    ce_wait_kernel<<<1, n, 0, st>>>(t->my_flags, n, me, seq);
+    MCHECK(cudaGetLastError());
+    return 0;
+}
+static int ce_release(magic_transp *t) {
+    ce_signal_kernel<<<1, t->n_procs, 0, t->stream>>>(t->d_slot_ack, t->n_procs, t->rank, *t->seq);
+    MCHECK(cudaGetLastError());
+    return 0;
+}
+
 static int exchange_lm_direct(magic_transp *t, int nf, const double *arr_LM_send, double *arr_LM_recv) {
     cudaStream_t st = t->stream;
     const int me = t->rank, n = t->n_procs;
@@ -540,6 +719,12 @@ static int exchange_lm_direct(magic_transp *t, int nf, const double *arr_LM_send
 extern "C" int magic_transp_lm2r_dev_n(magic_transp *t, int nf, const double *arr_LMloc, double *arr_Rloc) {
     TCHK(t, nf);
     if (t->n_procs == 1) return permute_launch(t, nf, arr_LMloc, arr_Rloc, 1);
+    if (t->ce) {
+        double *rh = nullptr;
+        if (ce_exchange(t, nf, arr_LMloc, false, &rh)) return 1;
+        if (side_launch(t, nf, false, nullptr, arr_Rloc, rh, nullptr)) return 1;
+        return ce_release(t);
+    }
     if (exchange_lm_direct(t, nf, arr_LMloc, nullptr)) return 1;
     return side_launch(t, nf, false, nullptr, arr_Rloc, t->recvbuf, nullptr);
 }
@@ -548,6 +733,19 @@ extern "C" int magic_transp_r2lm_dev_n(magic_transp *t, int nf, const double *ar
     TCHK(t, nf);
     if (t->n_procs == 1) return permute_launch(t, nf, arr_Rloc, arr_LMloc, 0);
     if (side_launch(t, nf, false, arr_Rloc, nullptr, nullptr, t->sendbuf)) return 1;
+    if (t->ce) {
+        double *rh = nullptr;
+        if (ce_exchange(t, nf, nullptr, true, &rh)) return 1;
+        // LM side: segment q of the buffer ([f][levels of q][my modes]) goes to the rows of q's levels of every field
+        const int me = t->rank;
+        const size_t nlm = (size_t)(t->le[me] - t->ls[me] + 1), frow = nlm * t->n_r_max, c16 = sizeof(double) * 2;
+        for (int q = 0; q < t->n_procs; q++) {
+            if (t->lm1[q] == 0) continue;
+            MCHECK(cudaMemcpy2DAsync(arr_LMloc + 2 * (size_t)(t->rs[q] - 1) * nlm, c16 * frow, rh + 2 * (size_t)nf * t->lmd1[q], c16 * t->lm1[q],
+                                     c16 * t->lm1[q], nf, cudaMemcpyDeviceToDevice, t->stream));
+        }
+        return ce_release(t);
+    }
     return exchange_lm_direct(t, nf, nullptr, arr_LMloc);
 }
 

@@ -118,3 +118,48 @@ def test_gpu_and_oracle_trajectories_agree(golden):
         assert rel_l2(getattr(hb, nm), getattr(ha, nm)) < 1e-11, nm
     rl.finalize()
     s.finalize_sht()
+
+
+@pytest.mark.gpu
+def test_gpu_fused_lm_call_with_device_prologue_and_epilogue(golden):
+    """The drop-in call of a host whose LM loop stays on the CPU -- magic_rloop_run_lm: LM-distributed host containers in,
+    LM-distributed explicit terms out -- inside the reference's time loop, with SURVEY 8(f)1 on the device: dw, ddw, dz, db,
+    ddb, dj are radial-matrix products computed from w, z, b, aj (the derivative slots of the host containers are poisoned
+    with NaN), and finish_explicit_assembly (finish_exp_entropy, finish_exp_mag) runs after the outbound transposes, so
+    dVSrLM / dVxBhLM never reach the host.  All 100 rows of both golden files at the autotest tolerance."""
+    from magic_b200 import RadialLoop, Sht, Transposer
+    from magic_b200.transpose import lo_map
+    l_max, n_r = int(golden["l_max"]), int(golden["n_r_max"])
+    s = Sht(l_max)
+    tr = Transposer(s, n_r, 5)
+    p, rad = _params(golden)
+    rl = RadialLoop(s, p, rad, level_chunk=8)
+    lo2st, _, _ = lo_map(l_max, l_max, 1, 1)
+    st2lo = np.argsort(lo2st)
+    nlm = len(lo2st)
+    state = {}
+
+    def loop(f):
+        lm = lambda a: np.ascontiguousarray(a[:, lo2st])
+        nan = np.full((n_r, nlm), np.nan + 0j)
+        h_in = {"flow": np.stack([lm(f["w"]), nan, nan, lm(f["z"]), nan]), "s": np.stack([lm(f["s"]), nan]),
+                "field": np.stack([lm(f["b"]), nan, nan, lm(f["aj"]), nan])}
+        out = {"dflowdt": np.zeros((3, n_r, nlm), dtype=np.complex128), "dsdt": np.zeros((2, n_r, nlm), dtype=np.complex128),
+               "dbdt": np.zeros((3, n_r, nlm), dtype=np.complex128)}
+        dtr, dth = np.zeros(n_r), np.zeros(n_r)
+        rl.run_lm(tr, h_in, out, dtr, dth)
+        st = lambda a: np.ascontiguousarray(a[:, st2lo])
+        # dsdt and djdt arrive finished; the arrays finish_explicit_assembly would differentiate stayed on the device (zeros
+        # here make the host's own finish step of this Boussinesq case, orho1 = 1, the identity)
+        return {"dwdt": st(out["dflowdt"][0]), "dzdt": st(out["dflowdt"][1]), "dpdt": st(out["dflowdt"][2]), "dsdt": st(out["dsdt"][0]),
+                "dVSrLM": st(out["dsdt"][1]), "dbdt": st(out["dbdt"][0]), "djdt": st(out["dbdt"][1]), "dVxBhLM": st(out["dbdt"][2]),
+                "dtrkc": dtr, "dthkc": dth}
+
+    h = _host(golden, s.lm2l, s.lm2m, loop)
+    rl.set_radial_matrices(h.g.D1t, h.g.D2)
+    rl.set_lm_radial(h.g.or2, np.ones(n_r), np.zeros(n_r), np.full(n_r, l_max, dtype=np.int32))   # dentropy0 = 0 in this sample
+    rl.lm_options(derivs_on_device=True, finish_on_device=True)
+    _run(golden, h, N_STEPS)
+    rl.finalize()
+    tr.destroy_comm()
+    s.finalize_sht()
