@@ -26,8 +26,56 @@ __device__ __forceinline__ double2 cscale(double2 a, double s) { return make_dou
 // multiply by sg*i
 __device__ __forceinline__ double2 cmuli(double2 a, double sg) { return make_double2(-sg * a.y, sg * a.x); }
 // twiddle e^{sg * 2 pi i idx / N}
+// Cache hints (MAGIC_FFT_HINTS=0 turns them off for A/B runs): the twiddle table (H entries in use, 24 KB at n_phi = 3072) is
+// the only data of these kernels that is re-read, but it shares L1 with the streaming rows -- ncu on the unhinted kernels:
+// 27-37 % of the twiddle sectors missed L1 and every miss is an L2 round trip in the middle of a barrier-separated pass
+// (long-scoreboard stalls on the DMULs that consume them: a quarter of all samples).  Twiddle loads ask for evict_last, the
+// streaming loads and stores do not allocate in L1.
+#ifndef MAGIC_FFT_HINTS
+#define MAGIC_FFT_HINTS 1
+#endif
+#ifndef MAGIC_FFT_TWHOIST
+#define MAGIC_FFT_TWHOIST 0
+#endif
+// measured at l_max = 1023 (ms per 16-level chunk): cache hints 4.51 -> 3.95 (c2r), 3.04 -> 2.60 (r2c); twiddle load hoisted above the
+// pass barrier: 3.95 vs 3.94 (off); table copy in shared memory for c2r: 3.92 vs 3.91 (off); r2c post-processing twiddles requested
+// before the last butterflies: 2.56 vs 2.60 (off: changes FMA contraction, i.e. result bits, for 1.5 %)
+#ifndef MAGIC_FFT_C2R_STW
+#define MAGIC_FFT_C2R_STW 0
+#endif
+#ifndef MAGIC_FFT_R2C_TWHOIST
+#define MAGIC_FFT_R2C_TWHOIST 0
+#endif
+__device__ __forceinline__ double2 ld_keep(const double2 *p) {
+#if MAGIC_FFT_HINTS
+    double2 v;
+    asm("ld.global.nc.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ double2 ld_stream(const double *p) {
+#if MAGIC_FFT_HINTS
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+#else
+    return *reinterpret_cast<const double2 *>(p);
+#endif
+}
+__device__ __forceinline__ void st_stream(double *p, double2 v) {
+#if MAGIC_FFT_HINTS
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+#else
+    *reinterpret_cast<double2 *>(p) = v;
+#endif
+}
+// TWS: `tw` is a copy of the table in shared memory (the c2r prefetch kernel keeps one: its L1 is too small to hold the table
+// next to two CTAs' row and staging buffers -- ncu: 53 % twiddle hit rate even with evict_last)
+template <bool TWS = false>
 __device__ __forceinline__ double2 twid(const double2 *__restrict__ tw, int idx, double sg) {
-    double2 w = __ldg(tw + idx);
+    double2 w = TWS ? tw[idx] : ld_keep(tw + idx);
     w.y *= sg;
     return w;
 }
@@ -96,11 +144,12 @@ __host__ __device__ constexpr int fft_pick_radix(int len) {
 __host__ __device__ constexpr int fft_pad(int i) { return i + (i >> 3); }
 
 // One in-place Stockham pass (compile-time radix RADIX, sub-length LEN, stride S) over R rows of length H.
-template <int H, int R, int NT, int RADIX, int LEN, int S, int ROWLEN = fft_pad(H)>
+template <int H, int R, int NT, int RADIX, int LEN, int S, int ROWLEN = fft_pad(H), bool TWS = false>
 __device__ __forceinline__ void fft_pass(double2 *buf, const double2 *__restrict__ tw, double sg) {
     constexpr int M = LEN / RADIX, NB = H / RADIX, TOTAL = R * NB, PER = (TOTAL + NT - 1) / NT;
     constexpr int TWSTEP = 2 * H / LEN;
     double2 reg[PER][RADIX];
+    double2 w1[PER];
 #pragma unroll
     for (int u = 0; u < PER; u++) {
         int idx = threadIdx.x + u * NT;
@@ -115,6 +164,11 @@ __device__ __forceinline__ void fft_pass(double2 *buf, const double2 *__restrict
 #pragma unroll
                 for (int j = 0; j < RADIX; j++) reg[u][j] = x[fft_pad(b + NB * j)];
             }
+            // the pass's one twiddle load is issued before the barrier, so its latency hides behind the shared-memory loads
+            // and the barrier wait instead of heading the dependent chain of the butterfly outputs
+#if MAGIC_FFT_TWHOIST
+            if (M > 1) w1[u] = twid<TWS>(tw, (b / S) * TWSTEP, sg);
+#endif
         }
     }
     __syncthreads();
@@ -138,7 +192,11 @@ __device__ __forceinline__ void fft_pass(double2 *buf, const double2 *__restrict
                 // twiddles w^k, w = e^{sg 2 pi i p/LEN}: one table load, the powers by a depth-3 product tree (the
                 // kernel is bound by L1/shared wavefronts, not by the FP64 pipe; each product costs ~1 ulp)
                 double2 w[RADIX];
-                w[1] = twid(tw, p * TWSTEP, sg);
+#if MAGIC_FFT_TWHOIST
+                w[1] = w1[u];
+#else
+                w[1] = twid<TWS>(tw, p * TWSTEP, sg);
+#endif
                 if (RADIX > 2) w[2] = cmul(w[1], w[1]);
                 if (RADIX > 3) w[3] = cmul(w[2], w[1]);
                 if (RADIX > 4) w[4] = cmul(w[2], w[2]);
@@ -179,7 +237,7 @@ __device__ __forceinline__ void r2c_scatter(const R2cArgs &a, const R2cField fd,
     double2 x = cadd(e, cmul(w8, o));
     const double2 v = cscale(x, fd.rtype == R_W ? w : ws);
     const size_t off = ((size_t)(mc * 2 + s) * a.NHP + k) * a.ldB + 2 * ((size_t)fd.col * a.n_lev + lev);
-    *reinterpret_cast<double2 *>(a.B + off) = v;
+    st_stream(a.B + off, v);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -204,13 +262,13 @@ __host__ __device__ constexpr int fft2_threads(int H) {
 }
 
 // middle passes: everything between the first (LEN = H) and the last (LEN = fft_last_radix(H)) pass
-template <int H, int R, int NT, int ROWLEN_, int LEN, int S>
+template <int H, int R, int NT, int ROWLEN_, int LEN, int S, bool TWS = false>
 struct FftMid {
     static constexpr int RADIX = fft_pick_radix(LEN);
     static __device__ __forceinline__ void run(double2 *buf, const double2 *__restrict__ tw, double sg) {
         if constexpr (LEN / RADIX > 1) {
-            fft_pass<H, R, NT, RADIX, LEN, S, ROWLEN_>(buf, tw, sg);
-            FftMid<H, R, NT, ROWLEN_, LEN / RADIX, S * RADIX>::run(buf, tw, sg);
+            fft_pass<H, R, NT, RADIX, LEN, S, ROWLEN_, TWS>(buf, tw, sg);
+            FftMid<H, R, NT, ROWLEN_, LEN / RADIX, S * RADIX, TWS>::run(buf, tw, sg);
         }
     }
 };
@@ -240,13 +298,13 @@ __device__ __forceinline__ void twiddle_powers(double2 *w) {
 #define MAGIC_FFT_LB_R(H) __launch_bounds__(fft2_threads(H))
 #endif
 // first-pass butterfly b of a row (S = 1: p = b, outputs at 8b..8b+7 for radix 8) written to shared memory
-template <int H, int R1>
+template <int H, int R1, bool TWS = false>
 __device__ __forceinline__ void first_pass_out(double2 *row, const double2 *__restrict__ tw, int b, const double2 *in, double sg) {
     double2 o[R1];
     butterfly<R1>(in, o, sg);
     if (H / R1 > 1) {
         double2 w[R1];
-        w[1] = twid(tw, b * 2, sg);  // TWSTEP = 2H / LEN = 2
+        w[1] = twid<TWS>(tw, b * 2, sg);  // TWSTEP = 2H / LEN = 2
         twiddle_powers<R1>(w);
 #pragma unroll
         for (int k = 1; k < R1; k++) o[k] = cmul(o[k], w[k]);
@@ -268,6 +326,10 @@ __global__ void MAGIC_FFT_LB_C(H) fft_c2r_plan_kernel(const double2 *__restrict_
     const int rows = min(R, ncols - cc0);
     const double *Fb = F + ((size_t)s * nh + k) * ld + 2 * cc0;
     const size_t mstride = (size_t)2 * nh * ld;
+    // destination rows of this tile, fetched now (the store phase used to start with a dependent global load: 5 % of all stall
+    // samples sat on its first use)
+    __shared__ int s_row[R];
+    if (threadIdx.x < R) s_row[threadIdx.x] = threadIdx.x < rows ? colrow[cc0 + threadIdx.x] : -1;
     // ---- gather + Hermitian pre-processing + first pass.  Item t of a row: butterflies (t, NB1 - t); t = 0: butterfly 0 and,
     //      for even NB1, the self-paired butterfly NB1/2.
     for (int item = threadIdx.x; item < R * NI1; item += NT) {
@@ -281,8 +343,8 @@ __global__ void MAGIC_FFT_LB_C(H) fft_c2r_plan_kernel(const double2 *__restrict_
             B[j] = A[j];
             const int ka = u + NB1 * j, kb = v + NB1 * j;
             if (r < rows) {
-                if (ka < n_m) A[j] = *reinterpret_cast<const double2 *>(Fb + (size_t)ka * mstride + 2 * r);
-                if (has_v && kb < n_m) B[j] = *reinterpret_cast<const double2 *>(Fb + (size_t)kb * mstride + 2 * r);
+                if (ka < n_m) A[j] = ld_stream(Fb + (size_t)ka * mstride + 2 * r);
+                if (has_v && kb < n_m) B[j] = ld_stream(Fb + (size_t)kb * mstride + 2 * r);
             }
         }
         double2 *row = fsm + r * ROWLEN;
@@ -331,12 +393,12 @@ __global__ void MAGIC_FFT_LB_C(H) fft_c2r_plan_kernel(const double2 *__restrict_
 #pragma unroll
         for (int j = 0; j < RL; j++) in[j] = x[fft_pad(q + SL * j)];
         butterfly<RL>(in, o, 1.0);
-        if (r < rows) {
-            const int row = colrow[cc0 + r];
+        {
+            const int row = s_row[r];
             if (row >= 0) {
                 double *g = grid + (((size_t)row * 2 + s) * nh + k) * N;
 #pragma unroll
-                for (int kq = 0; kq < RL; kq++) *reinterpret_cast<double2 *>(g + 2 * (q + SL * kq)) = o[kq];
+                for (int kq = 0; kq < RL; kq++) st_stream(g + 2 * (q + SL * kq), o[kq]);
             }
         }
     }
@@ -363,8 +425,7 @@ __global__ void MAGIC_FFT_LB_R(H) fft_r2c_plan_kernel(const double2 *__restrict_
             for (int j = 0; j < R1; j++) {
                 reg[u][j] = make_double2(0.0, 0.0);
                 if (idx < R * NB1 && r < rows)
-                    reg[u][j] = *reinterpret_cast<const double2 *>(a.grid + ((((size_t)field * a.n_lev + lev0 + r) * 2 + s) * a.nh + k) * N +
-                                                                   2 * (b + NB1 * j));
+                    reg[u][j] = ld_stream(a.grid + ((((size_t)field * a.n_lev + lev0 + r) * 2 + s) * a.nh + k) * N + 2 * (b + NB1 * j));
             }
         }
 #pragma unroll
@@ -432,7 +493,7 @@ __global__ void MAGIC_FFT_LB_R(H) fft_r2c_plan_kernel(const double2 *__restrict_
 // (128 registers: the register file is split over the four SM sub-partitions, a CTA of 6 warps puts 2 warps on two of them,
 //  and two CTAs per SM need 4 warps x 32 lanes x 128 registers = one sub-partition's 16 K registers)
 template <int H>
-__global__ void __maxnreg__(128) fft_c2r_pf_kernel(const double2 *__restrict__ tw, const double *__restrict__ F, int ld, int n_m,
+__global__ void __maxnreg__(128) fft_c2r_pf_kernel(const double2 *__restrict__ tw_g, const double *__restrict__ F, int ld, int n_m,
                                                                   int nh, int ncols, const int *__restrict__ colrow,
                                                                   double *__restrict__ grid, int tpc) {
     constexpr int R = fft2_rows(H), NT = fft2_threads(H), N = 2 * H, ROWLEN = fft2_rowlen(H);
@@ -440,6 +501,16 @@ __global__ void __maxnreg__(128) fft_c2r_pf_kernel(const double2 *__restrict__ t
     constexpr int RL = fft_last_radix(H), SL = H / RL;
     extern __shared__ __align__(16) double2 fsm[];
     double2 *stage = fsm + R * ROWLEN;  // [n_m][R]
+    __shared__ int s_row[R];
+#if MAGIC_FFT_C2R_STW
+    constexpr bool TWS = true;
+    double2 *stw = stage + n_m * R;     // tw[0 .. H): every index these passes and the Hermitian pre-processing use
+    for (int i = threadIdx.x; i < H; i += NT) stw[i] = __ldg(tw_g + i);
+    const double2 *tw = stw;            // visible after the first barrier of the tile loop
+#else
+    constexpr bool TWS = false;
+    const double2 *tw = tw_g;
+#endif
     const int sk = blockIdx.y, s = sk / nh, k = sk - s * nh;
     const int ntile = (ncols + R - 1) / R;
     const int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, ntile);
@@ -459,6 +530,7 @@ __global__ void __maxnreg__(128) fft_c2r_pf_kernel(const double2 *__restrict__ t
         const int cc0 = t * R, rows = min(R, ncols - cc0);
         cp_async_wait_all();
         __syncthreads();  // staging buffer complete; every thread is past the last pass of the previous tile
+        if (threadIdx.x < R) s_row[threadIdx.x] = threadIdx.x < rows ? colrow[cc0 + threadIdx.x] : -1;  // read after the next barriers
         // ---- Hermitian pre-processing + first pass (see fft_c2r_plan_kernel)
         for (int item = threadIdx.x; item < R * NI1; item += NT) {
             const int tt = item / R, r = item - tt * R;
@@ -479,7 +551,7 @@ __global__ void __maxnreg__(128) fft_c2r_pf_kernel(const double2 *__restrict__ t
 #pragma unroll
                 for (int j = 0; j < R1; j++) {
                     const double2 a = A[j], b = B[R1 - 1 - j];
-                    const double2 w = twid(tw, u + NB1 * j, 1.0);
+                    const double2 w = twid<TWS>(tw, u + NB1 * j, 1.0);
                     const double2 cb = cconj(b), ca = cconj(a);
                     Yu[j] = cadd(cadd(a, cb), cmuli(cmul(w, csub(a, cb)), 1.0));
                     const double2 w2 = make_double2(-w.x, w.y);
@@ -491,24 +563,24 @@ __global__ void __maxnreg__(128) fft_c2r_pf_kernel(const double2 *__restrict__ t
                     double2 a = A[j];
                     double2 b = (j == 0) ? make_double2(0.0, 0.0) : A[R1 - j];
                     if (j == 0) a.y = 0.0;
-                    const double2 w = twid(tw, NB1 * j, 1.0);
+                    const double2 w = twid<TWS>(tw, NB1 * j, 1.0);
                     const double2 cb = cconj(b);
                     Yu[j] = cadd(cadd(a, cb), cmuli(cmul(w, csub(a, cb)), 1.0));
                 }
 #pragma unroll
                 for (int j = 0; j < R1; j++) {
                     const double2 a = B[j], b = B[R1 - 1 - j];
-                    const double2 w = twid(tw, v + NB1 * j, 1.0);
+                    const double2 w = twid<TWS>(tw, v + NB1 * j, 1.0);
                     const double2 cb = cconj(b);
                     Yv[j] = cadd(cadd(a, cb), cmuli(cmul(w, csub(a, cb)), 1.0));
                 }
             }
-            first_pass_out<H, R1>(row, tw, u, Yu, 1.0);
-            if (has_v) first_pass_out<H, R1>(row, tw, v, Yv, 1.0);
+            first_pass_out<H, R1, TWS>(row, tw, u, Yu, 1.0);
+            if (has_v) first_pass_out<H, R1, TWS>(row, tw, v, Yv, 1.0);
         }
         __syncthreads();  // the staging buffer has been consumed
         if (t + 1 < t1) gather(t + 1);
-        FftMid<H, R, NT, ROWLEN, H / R1, R1>::run(fsm, tw, 1.0);
+        FftMid<H, R, NT, ROWLEN, H / R1, R1, TWS>::run(fsm, tw, 1.0);
         for (int idx = threadIdx.x; idx < R * SL; idx += NT) {
             const int r = idx / SL, q = idx - r * SL;
             const double2 *x = fsm + r * ROWLEN;
@@ -516,12 +588,12 @@ __global__ void __maxnreg__(128) fft_c2r_pf_kernel(const double2 *__restrict__ t
 #pragma unroll
             for (int j = 0; j < RL; j++) in[j] = x[fft_pad(q + SL * j)];
             butterfly<RL>(in, o, 1.0);
-            if (r < rows) {
-                const int row = colrow[cc0 + r];
+            {
+                const int row = s_row[r];
                 if (row >= 0) {
                     double *g = grid + (((size_t)row * 2 + s) * nh + k) * N;
 #pragma unroll
-                    for (int kq = 0; kq < RL; kq++) *reinterpret_cast<double2 *>(g + 2 * (q + SL * kq)) = o[kq];
+                    for (int kq = 0; kq < RL; kq++) st_stream(g + 2 * (q + SL * kq), o[kq]);
                 }
             }
         }
@@ -582,6 +654,20 @@ __global__ void __maxnreg__(128) fft_r2c_pf_kernel(const double2 *__restrict__ t
             const int u = tt, v = (tt > 0) ? SL - tt : SL / 2;
             const double2 *x = fsm + r * ROWLEN;
             double2 in[RL], Zu[RL], Zv[RL];
+            // post-processing twiddles of the paired orders, requested before the butterflies (all indices are < H, so the loads
+            // need no predicate): their L1 latency used to sit between the butterfly and the scatter (ncu: the DMULs consuming
+            // them held 20 % of the stall samples)
+            constexpr bool HOIST = MAGIC_FFT_R2C_TWHOIST && RL <= 4;
+            double2 wu[HOIST ? RL : 1], wv[HOIST ? RL : 1];
+            if constexpr (HOIST) {
+                if (tt > 0) {
+#pragma unroll
+                    for (int kq = 0; kq < RL; kq++) {
+                        wu[kq] = twid(tw, u + SL * kq, -1.0);
+                        wv[kq] = twid(tw, v + SL * (RL - 1 - kq), -1.0);
+                    }
+                }
+            }
 #pragma unroll
             for (int j = 0; j < RL; j++) in[j] = x[fft_pad(u + SL * j)];
             butterfly<RL>(in, Zu, -1.0);
@@ -595,8 +681,8 @@ __global__ void __maxnreg__(128) fft_r2c_pf_kernel(const double2 *__restrict__ t
 #pragma unroll
                 for (int kq = 0; kq < RL; kq++) {
                     const int mu = u + SL * kq, mv = v + SL * (RL - 1 - kq);  // mu + mv = H
-                    if (mu < a.n_m) r2c_scatter(a, dests, s, k, mu, lev, Zu[kq], Zv[RL - 1 - kq], twid(tw, mu, -1.0), w, ws);
-                    if (mv < a.n_m) r2c_scatter(a, dests, s, k, mv, lev, Zv[RL - 1 - kq], Zu[kq], twid(tw, mv, -1.0), w, ws);
+                    if (mu < a.n_m) r2c_scatter(a, dests, s, k, mu, lev, Zu[kq], Zv[RL - 1 - kq], HOIST ? wu[HOIST ? kq : 0] : twid(tw, mu, -1.0), w, ws);
+                    if (mv < a.n_m) r2c_scatter(a, dests, s, k, mv, lev, Zv[RL - 1 - kq], Zu[kq], HOIST ? wv[HOIST ? kq : 0] : twid(tw, mv, -1.0), w, ws);
                 }
             } else {
 #pragma unroll
@@ -734,7 +820,7 @@ inline bool fft_has_plan(int H) {
     return false;
 }
 inline size_t fft_plan_smem(int H) { return (size_t)fft2_rows(H) * fft2_rowlen(H) * sizeof(double2); }
-inline size_t fft_pf_smem_c2r(int H, int n_m) { return fft_plan_smem(H) + (size_t)n_m * fft2_rows(H) * sizeof(double2); }
+inline size_t fft_pf_smem_c2r(int H, int n_m) { return fft_plan_smem(H) + (size_t)n_m * fft2_rows(H) * sizeof(double2) + (MAGIC_FFT_C2R_STW ? (size_t)H * sizeof(double2) : 0); }
 inline size_t fft_pf_smem_r2c(int H) { return fft_plan_smem(H) + (size_t)H * fft2_rows(H) * sizeof(double2); }
 // MAGIC_FFT_PF=0 selects the non-prefetching planned kernels (A/B measurements); tiles per CTA: MAGIC_FFT_TPC (default 8)
 inline bool fft_use_pf() { static int v = -1; if (v < 0) { const char *e = getenv("MAGIC_FFT_PF"); v = (e && atoi(e) == 0) ? 0 : 1; } return v == 1; }
@@ -786,7 +872,7 @@ inline void launch_fft_c2r(const FftPlan &pl, const double *F, int ld, int n_m, 
 #define X(h)                                                                                                                      \
     if (H == h) {                                                                                                                 \
         const int ntile = (ncols + fft2_rows(h) - 1) / fft2_rows(h);                                                              \
-        if (fft_use_pf() && fft_pf_smem_c2r(h, n_m) <= 110 * 1024) {                                                              \
+        if (fft_use_pf() && fft_pf_smem_c2r(h, n_m) <= 113 * 1024) {                                                              \
             const int tpc = fft_tpc();                                                                                            \
             dim3 g((ntile + tpc - 1) / tpc, 2 * nh);                                                                              \
             fft_c2r_pf_kernel<h><<<g, fft2_threads(h), fft_pf_smem_c2r(h, n_m), st>>>(pl.tw, F, ld, n_m, nh, ncols, colrow, grid, tpc); \
