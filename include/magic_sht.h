@@ -137,6 +137,39 @@ int magic_rloop_get_torques(const magic_rloop *rl, double *lorentz_torque_ic, do
  * complex [lm_max] HOST arrays, valid after a run on the rank that holds the boundary level.  Only defined for runs with
  * l_b_nl_cmb / l_b_nl_icb (stress-free wall + conducting mantle / inner core, Namelists.f90:713-729); an error otherwise. */
 int magic_rloop_get_br_v_bcs(const magic_rloop *rl, int boundary, double *br_vt_lm, double *br_vp_lm);
+
+/* ---- In-loop diagnostics of log steps (rIter.f90:303-373) ------------------------------------------------
+ * The reference calls get_helicity (outMisc.f90:1052), get_hemi (:991), get_visc_heat (power.f90:384), get_perpPar
+ * (outPar.f90:646), get_fluxes (:470) and get_nlBLayers (:584) on the grid arrays of every level when lHelCalc, lHemiCalc,
+ * lPowerCalc, lPerpParCalc, lFluxProfCalc, lViscBcCalc are set.  One call here returns all requested per-level sums: the
+ * fields they read are synthesised on the device (lDeriv = .true. on the boundary levels, as rIter.f90:193-205 sets it when
+ * an output flag is on) and reduced by one fused kernel; out is a HOST array [n_r_loc][MAGIC_NDIAG].
+ *   mask   MAGIC_DIAG_* bits; MAGIC_DIAG_RMSBULK = lRmsCalc is on, so boundary levels are treated as bulk (rIter.f90:215)
+ *   ktops / kbots  thermal boundary types (1 = fixed entropy: horizontal entropy gradient zeroed there, rIter.f90:488-495)
+ * Slot s of level i is out[i * MAGIC_NDIAG + s]:
+ *   HelASr(nR,1:2) 0,1   Hel2ASr 2,3   HelnaASr 4,5   Helna2ASr 6,7   HelEAASr 8
+ *   hemi_ekin_r(nR,1:2) 9,10   hemi_vrabs_r 11,12   hemi_emag_r 13,14   hemi_brabs_r 15,16        viscASr 17
+ *   EperpASr 18   EparASr 19   EperpaxiASr 20   EparaxiASr 21
+ *   fkinASr 22   sum(vr*sr) 23   sum(vr*pr) 24   fviscASr 25   fresASr 26   fpoynASr 27
+ *       (fconvASr = temp0*[23] + ViscHeatFac*ThExpNb*alpha0*temp0*orho1*[24], or [23] alone with l_anelastic_liquid:
+ *        outPar.f90:511-517 -- radial functions the host holds)
+ *   uhASr 28   duhASr 29   gradT2ASr 30
+ * magic_rloop_diagnostics takes HOST field pointers (the *_Rloc arrays rIter_cuda_t already holds), the _dev form device
+ * pointers.  Not available for full-sphere runs. */
+#define MAGIC_DIAG_HEL 1
+#define MAGIC_DIAG_HEMI 2
+#define MAGIC_DIAG_POWER 4
+#define MAGIC_DIAG_PERPPAR 8
+#define MAGIC_DIAG_FLUX 16
+#define MAGIC_DIAG_VISCBC 32
+#define MAGIC_DIAG_RMSBULK 256
+#define MAGIC_NDIAG 32
+int magic_rloop_diagnostics(magic_rloop *rl, const magic_fields_in *in, int mask, int ktops, int kbots, double *out);
+int magic_rloop_diagnostics_dev(magic_rloop *rl, const magic_fields_in *in, int mask, int ktops, int kbots, double *out);
+/* The grid fields graphOut_mpi writes (rIter.f90:303-314, out_graph_file.f90:337) for one local level (0-based), HOST arrays
+ * f(nlat_padded, n_phi) in the layout of the per-call transforms; NULL outputs are skipped (vr/vt/vp and br/bt/bp as triples). */
+int magic_rloop_graph_fields(magic_rloop *rl, const magic_fields_in *in, int level, double *vr, double *vt, double *vp, double *br,
+                             double *bt, double *bp, double *sr, double *pr);
 /* Page-locks a PERSISTENT host array of the caller (a field container that lives as long as the run) so that magic_rloop_run
  * can overlap its transfers with the compute; unpin before the array is freed.  The run calls never pin on their own: without
  * this call the transfers are staged through pageable memory (correct, slower).  Already page-locked memory is accepted. */

@@ -1,0 +1,205 @@
+// api_diag.cu -- C ABI: the in-loop diagnostics of log steps (rIter.f90:303-373) and the grid fields
+// graphOut_mpi reads (rIter.f90:303-314).
+//
+// The reference evaluates get_helicity / get_hemi / get_visc_heat / get_nlBLayers / get_fluxes / get_perpPar level by level on the
+// grid arrays the loop has just synthesised, and synthesises extra fields for them (the velocity gradients in curl-form runs,
+// pressure, entropy gradient: rIter.f90:483-527).  Here a log step runs a second, synthesis-only column program over the same
+// spectral inputs -- exactly the fields the requested diagnostics read, with lDeriv = .true. on the boundary levels as the
+// reference sets it (rIter.f90:193-205) -- followed by one fused reduction kernel per level chunk.  The hot path of ordinary
+// steps is untouched; nothing but [n_r_loc][32] doubles crosses PCIe (instead of 20+ grid fields per level).
+// Included by lib.cu after api_rloop.cu (it uses magic_rloop).
+#include "kernels_diag.cuh"
+
+struct DiagPipe {
+    int mask = -1, chunk = 0, gx = 0;
+    BatchSpec spec;
+    DiagIn di;
+    Layout lay;
+    Buffers buf;
+    LevelInfo *d_lev = nullptr;
+    double *d_gauss = nullptr, *d_means = nullptr, *d_partial = nullptr, *d_out = nullptr, *h_out = nullptr;
+    double *d_src[S_COUNT] = {nullptr};  // staging of the host-pointer call: complex [chunk][lm_max] per source
+    bool need[S_COUNT] = {false};
+};
+
+static void diag_free(DiagPipe *d) {
+    if (!d) return;
+    layout_free(d->lay);
+    buffers_free(d->buf);
+    cudaFree(d->d_lev); cudaFree(d->d_gauss); cudaFree(d->d_means); cudaFree(d->d_partial); cudaFree(d->d_out);
+    if (d->h_out) cudaFreeHost(d->h_out);
+    for (int i = 0; i < S_COUNT; i++) cudaFree(d->d_src[i]);
+    delete d;
+}
+
+// column program of transform_to_grid_space with the output branches taken (rIter.f90:483-622)
+static int diag_build(magic_rloop *rl, int mask) {
+    magic_sht *h = rl->h;
+    const magic_params &P = rl->p;
+    if (P.l_full_sphere) MFAIL("magic_rloop_diagnostics: full-sphere runs (v_center_sphere on the r = 0 level) are not supported");
+    if (!(P.l_conv || P.l_mag_kin)) MFAIL("magic_rloop_diagnostics: needs a flow (l_conv or l_mag_kin)");
+    diag_free(rl->diag);
+    rl->diag = nullptr;
+    DiagPipe *d = new DiagPipe();
+    rl->diag = d;
+    d->mask = mask;
+    BatchSpec &S = d->spec;
+    int *dip = (int *)&d->di;
+    for (int i = 0; i < DIAG_NF; i++) dip[i] = -1;
+    DiagIn &di = d->di;
+    const Term N_ = {0, F_NONE};
+    const bool flux = mask & DM_FLUX, viscbc = mask & DM_VISCBC;
+    const bool mag = (P.l_mag || P.l_mag_LF) && ((mask & DM_HEMI) || flux);
+    int nf = 0;
+    auto need = [&](std::initializer_list<int> s) { for (int i : s) d->need[i] = true; };
+    if (P.l_heat && (flux || viscbc)) {
+        add_scal(S, Term{S_S, F_ONE}, N_, LM_ALL, nf, di.s); need({S_S});
+        if (viscbc) {
+            add_pair(S, Term{S_S, F_ONE}, N_, N_, N_, LM_ALL, nf, di.dsdt, di.dsdp);   // scal_to_grad_spat, rIter.f90:487
+            add_scal(S, Term{S_DS, F_ONE}, N_, LM_ALL, nf, di.drs); need({S_DS});       // rIter.f90:511-513
+        }
+    }
+    if (flux && !P.l_anelastic_liquid) { add_scal(S, Term{S_P, F_ONE}, N_, LM_ALL, nf, di.p); need({S_P}); }  // lPressCalc, rIter.f90:503
+    need({S_W, S_DW, S_DDW, S_Z, S_DZ});
+    add_scal(S, Term{S_W, F_DLH}, N_, LM_VEL, nf, di.vr);
+    add_pair(S, Term{S_DW, F_ONE}, N_, Term{S_Z, F_ONE}, N_, LM_VEL, nf, di.vt, di.vp);
+    add_scal(S, Term{S_DW, F_DLH}, N_, LM_ALL, nf, di.dvrdr);
+    add_pair(S, Term{S_DDW, F_ONE}, N_, Term{S_DZ, F_ONE}, N_, LM_ALL, nf, di.dvtdr, di.dvpdr);
+    add_scal(S, Term{S_Z, F_DLH}, N_, LM_VEL, nf, di.cvr);
+    add_pair(S, Term{S_W, F_DLH}, N_, N_, N_, LM_VELBULK, nf, di.dvrdt, di.dvrdp);
+    add_pair(S, Term{S_DW, F_IM}, N_, Term{S_Z, F_IM}, N_, LM_VEL, nf, di.dvtdp, di.dvpdp);
+    if (mag) {
+        need({S_B, S_DB, S_AJ});
+        add_scal(S, Term{S_B, F_DLH}, N_, LM_ALL, nf, di.br);
+        add_pair(S, Term{S_DB, F_ONE}, N_, Term{S_AJ, F_ONE}, N_, LM_ALL, nf, di.bt, di.bp);
+        if (flux && P.l_mag_nl) {
+            need({S_DDB, S_DJ});
+            add_pair(S, Term{S_DJ, F_ONE}, N_, Term{S_B, F_OR2DLH}, Term{S_DDB, F_NEG}, LM_ALL, nf, di.cbt, di.cbp);
+        }
+    }
+    S.nfield_in = nf;
+    S.nfield_out = 0;
+    // level chunk: bounded by free memory (grid + (theta,m) space + operands are about 2.2 grid fields per synthesised field)
+    size_t free_b = 0, total_b = 0;
+    MCHECK(cudaMemGetInfo(&free_b, &total_b));
+    const double per_level = 2.2 * 8.0 * (double)h->n_theta * h->n_phi * nf + 64.0 * h->lm_max * S_COUNT;
+    int chunk = (int)std::min<double>(32.0, 0.5 * (double)free_b / per_level);
+    chunk = std::max(1, std::min(chunk, rl->n_r_loc));
+    d->chunk = chunk;
+    layout_sizes(h, S, chunk, d->lay);
+    if (buffers_alloc(h, S, d->lay, d->buf)) return 1;
+    if (layout_bind(h, S, d->lay, d->buf)) return 1;
+    // the diagnostics' levels: lDeriv = .true. everywhere (rIter.f90:193-205), boundary levels bulk with lRmsCalc (:215)
+    std::vector<LevelInfo> lev = rl->lev;
+    for (auto &L : lev) {
+        L.lDeriv = 1;
+        if (mask & 256) L.nBc = 0;
+    }
+    if (dev_upload_vec(&d->d_lev, lev)) return 1;
+    std::vector<double> ga(h->nh);
+    for (int k = 0; k < h->nh; k++) ga[k] = h->gauss[k];
+    if (dev_upload_vec(&d->d_gauss, ga)) return 1;
+    const size_t plane = (size_t)h->nh * h->n_phi;
+    d->gx = (int)std::min<size_t>((plane + DIAG_THREADS - 1) / DIAG_THREADS, 4 * 148);
+    MCHECK(cudaMalloc((void **)&d->d_means, sizeof(double) * DIAG_NMEAN * chunk * 2 * h->nh));
+    MCHECK(cudaMalloc((void **)&d->d_partial, sizeof(double) * (size_t)chunk * d->gx * DIAG_NSLOT));
+    MCHECK(cudaMalloc((void **)&d->d_out, sizeof(double) * (size_t)rl->n_r_loc * DIAG_NSLOT));
+    MCHECK(cudaMallocHost((void **)&d->h_out, sizeof(double) * (size_t)rl->n_r_loc * DIAG_NSLOT));
+    return 0;
+}
+
+static int diag_run(magic_rloop *rl, const magic_fields_in *in, int mask, int ktops, int kbots, double *out, bool host_in) {
+    if (!rl || !in || !out) MFAIL("magic_rloop_diagnostics: null argument");
+    magic_sht *h = rl->h;
+    MCHECK(cudaSetDevice(h->dev));
+    if (!rl->diag || rl->diag->mask != mask)
+        if (diag_build(rl, mask)) return 1;
+    DiagPipe *d = rl->diag;
+    const magic_params &P = rl->p;
+    const double *ip[S_COUNT];
+    in_ptrs(in, ip);
+    for (int i = 0; i < S_COUNT; i++)
+        if (d->need[i] && !ip[i]) MFAIL("magic_rloop_diagnostics: a required input field is null");
+    const size_t lm2 = 2 * (size_t)h->lm_max;
+    const int nl = d->chunk, n_r = rl->n_r_loc;
+    if (host_in)
+        for (int i = 0; i < S_COUNT; i++)
+            if (d->need[i] && !d->d_src[i]) MCHECK(cudaMalloc((void **)&d->d_src[i], sizeof(double) * lm2 * nl));
+    DiagArgs a{};
+    a.di = d->di; a.gin = d->buf.gin; a.n_lev = nl; a.nh = h->nh; a.n_phi = h->n_phi; a.mask = mask & 63;
+    a.l_mag = (P.l_mag && d->di.br >= 0) ? 1 : 0; a.l_mag_nl = (P.l_mag_nl && d->di.cbt >= 0) ? 1 : 0;
+    a.n_r_max = P.n_r_max; a.ktops = ktops; a.kbots = kbots;
+    a.omega_ma = P.omega_ma; a.omega_ic = P.omega_ic; a.r_cmb = P.r_cmb; a.r_icb = P.r_icb;
+    a.sinth = h->d_sinth; a.costh = h->d_costh; a.gauss = d->d_gauss;
+    const int mf[DIAG_NMEAN] = {d->di.vr, d->di.cvr, d->di.vt, d->di.vp, d->di.dvrdp, d->di.dvpdr, d->di.dvtdr, d->di.dvrdt};
+    for (int i = 0; i < DIAG_NMEAN; i++) a.mean_field[i] = mf[i];
+    a.means = d->d_means; a.partial = d->d_partial;
+    // chunks of exactly `nl` levels; the last one is shifted back so that it ends on the last level (its overlap is recomputed)
+    for (int l0 = 0; l0 < n_r; l0 += nl) {
+        const int s0 = std::min(l0, n_r - nl);
+        const double *src[MAGIC_MAX_SRC];
+        for (int i = 0; i < MAGIC_MAX_SRC; i++) src[i] = nullptr;
+        for (int i = 0; i < S_COUNT; i++) {
+            if (!d->need[i]) continue;
+            if (host_in) {
+                MCHECK(cudaMemcpyAsync(d->d_src[i], ip[i] + (size_t)s0 * lm2, sizeof(double) * lm2 * nl, cudaMemcpyHostToDevice, h->stream));
+                src[i] = d->d_src[i];
+            } else {
+                src[i] = ip[i] + (size_t)s0 * lm2;
+            }
+        }
+        if (run_synthesis(h, d->spec, d->lay, d->buf, src, d->d_lev + s0, nullptr)) return 1;
+        a.lev = d->d_lev + s0;
+        if (mask & (DM_HEL | DM_PERPPAR)) {
+            const size_t nrow = (size_t)DIAG_NMEAN * nl * 2 * h->nh;
+            diag_mean_kernel<<<(unsigned)((nrow + DIAG_THREADS / 32 - 1) / (DIAG_THREADS / 32)), DIAG_THREADS, 0, h->stream>>>(a);
+            h->launches++;
+        }
+        diag_kernel<<<dim3(d->gx, nl), DIAG_THREADS, 0, h->stream>>>(a);
+        diag_finish_kernel<<<(nl * DIAG_NSLOT + 127) / 128, 128, 0, h->stream>>>(d->d_partial, d->gx, nl, d->d_out + (size_t)s0 * DIAG_NSLOT);
+        h->launches += 2;
+        MCHECK(cudaGetLastError());
+    }
+    MCHECK(cudaMemcpyAsync(d->h_out, d->d_out, sizeof(double) * (size_t)n_r * DIAG_NSLOT, cudaMemcpyDeviceToHost, h->stream));
+    MCHECK(cudaStreamSynchronize(h->stream));
+    memcpy(out, d->h_out, sizeof(double) * (size_t)n_r * DIAG_NSLOT);
+    return 0;
+}
+
+extern "C" int magic_rloop_diagnostics(magic_rloop *rl, const magic_fields_in *in, int mask, int ktops, int kbots, double *out) {
+    return diag_run(rl, in, mask, ktops, kbots, out, true);
+}
+extern "C" int magic_rloop_diagnostics_dev(magic_rloop *rl, const magic_fields_in *in, int mask, int ktops, int kbots, double *out) {
+    return diag_run(rl, in, mask, ktops, kbots, out, false);
+}
+
+// ---- graphOut_mpi's inputs (rIter.f90:303-314): vr, vt, vp, [br, bt, bp,] sr, [pr] of one local level on the grid, in the
+// reference layout f(nlat_padded, n_phi) with N/S-interleaved rows; the host writes them to the graphic file as it does today
+// (out_graph_file.f90:337).  Uses the per-call transforms, so boundary levels get the values transform_to_grid_space produces
+// for bulk levels (graphOut is called before the boundary overrides matter: rigid walls hold v = wall motion, which the host
+// fills in as before).
+extern "C" int magic_rloop_graph_fields(magic_rloop *rl, const magic_fields_in *in, int level, double *vr, double *vt, double *vp, double *br,
+                                        double *bt, double *bp, double *sr, double *pr) {
+    if (!rl || !in) MFAIL("magic_rloop_graph_fields: null argument");
+    if (level < 0 || level >= rl->n_r_loc) MFAIL("magic_rloop_graph_fields: level out of range");
+    magic_sht *h = rl->h;
+    const size_t off = 2 * (size_t)h->lm_max * level;
+    const int lcut = rl->lev[level].lcut;
+    if (vr && vt && vp) {
+        if (!in->w || !in->dw || !in->z) MFAIL("magic_rloop_graph_fields: w, dw, z needed");
+        if (magic_torpol_to_spat(h, in->w + off, in->dw + off, in->z + off, vr, vt, vp, lcut)) return 1;
+    }
+    if (br && bt && bp) {
+        if (!in->b || !in->db || !in->aj) MFAIL("magic_rloop_graph_fields: b, db, aj needed");
+        if (magic_torpol_to_spat(h, in->b + off, in->db + off, in->aj + off, br, bt, bp, lcut)) return 1;
+    }
+    if (sr) {
+        if (!in->s) MFAIL("magic_rloop_graph_fields: s needed");
+        if (magic_scal_to_spat(h, in->s + off, sr, lcut)) return 1;
+    }
+    if (pr) {
+        if (!in->p) MFAIL("magic_rloop_graph_fields: p needed");
+        if (magic_scal_to_spat(h, in->p + off, pr, lcut)) return 1;
+    }
+    return 0;
+}

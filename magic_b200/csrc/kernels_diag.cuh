@@ -1,0 +1,232 @@
+// kernels_diag.cuh -- the grid-space diagnostics the reference evaluates inside the radial loop on log steps
+// (rIter.f90:303-373), fused into one pass over the synthesised grid fields of a level chunk:
+//   get_helicity   outMisc.f90:1052-1167      get_hemi      outMisc.f90:991-1050
+//   get_visc_heat  power.f90:384-441          get_perpPar   outPar.f90:646-726
+//   get_fluxes     outPar.f90:470-582         get_nlBLayers outPar.f90:584-644
+// The reference calls them one after the other, each sweeping the (theta, phi) arrays of one level on the host; here one kernel
+// reads every field of a (k, phi) point pair once (E/O layout of kernels_grid.cuh: north = E+O, south = E-O) and accumulates
+// all requested sums.  Reductions are fixed-shape (per thread -> xor-shuffle tree -> warps in order -> CTAs in order): no
+// floating-point atomics, bitwise reproducible.  HBM-bound: 8 n_theta n_phi bytes per field and level, read once.
+#pragma once
+#include "common.cuh"
+
+namespace magic {
+
+// grid field index of every field the diagnostics read (-1 = absent); same order as the loader below
+struct DiagIn { int vr, vt, vp, cvr, dvrdr, dvtdr, dvpdr, dvrdt, dvrdp, dvtdp, dvpdp, s, p, drs, dsdt, dsdp, br, bt, bp, cbt, cbp; };
+constexpr int DIAG_NF = 21;
+constexpr int DIAG_NSLOT = 32;   // = MAGIC_NDIAG
+constexpr int DIAG_NMEAN = 8;    // phi means of vr, cvr, vt, vp, dvrdp, dvpdr, dvtdr, dvrdt (outMisc.f90:1091-1108)
+constexpr int DIAG_THREADS = 256;
+
+enum DiagSlot {
+    DG_HEL_N = 0, DG_HEL_S, DG_HEL2_N, DG_HEL2_S, DG_HELNA_N, DG_HELNA_S, DG_HELNA2_N, DG_HELNA2_S, DG_HELEA,
+    DG_EKIN_N, DG_EKIN_S, DG_VRABS_N, DG_VRABS_S, DG_EMAG_N, DG_EMAG_S, DG_BRABS_N, DG_BRABS_S,
+    DG_VISC,
+    DG_EPERP, DG_EPAR, DG_EPERPAXI, DG_EPARAXI,
+    DG_FKIN, DG_FCONV_S, DG_FCONV_P, DG_FVISC, DG_FRES, DG_FPOYN,
+    DG_UH, DG_DUH, DG_GRADT2
+};
+enum DiagMask { DM_HEL = 1, DM_HEMI = 2, DM_POWER = 4, DM_PERPPAR = 8, DM_FLUX = 16, DM_VISCBC = 32 };
+
+struct DiagArgs {
+    DiagIn di;
+    const double *gin;
+    int n_lev, nh, n_phi, mask;
+    int l_mag, l_mag_nl, n_r_max, ktops, kbots;
+    double omega_ma, omega_ic, r_cmb, r_icb;
+    const LevelInfo *lev;         // the diagnostics' own copy: lDeriv = 1 everywhere, nBc = 0 with lRmsCalc (rIter.f90:190-215)
+    const double *sinth, *costh;  // northern values [nh]
+    const double *gauss;          // Gauss weight of colatitude pair k [nh]
+    int mean_field[DIAG_NMEAN];   // grid field index of each averaged field
+    double *means;                // [DIAG_NMEAN][n_lev][2 (E, O)][nh]
+    double *partial;              // [n_lev][gridDim.x][DIAG_NSLOT]
+};
+
+// phi means of the E and O rows: one warp per row, lane-strided partial sums, xor-shuffle tree
+__global__ void __launch_bounds__(DIAG_THREADS) diag_mean_kernel(DiagArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t nrow = (size_t)DIAG_NMEAN * a.n_lev * 2 * a.nh;
+    const size_t row = (size_t)blockIdx.x * (DIAG_THREADS / 32) + warp;
+    if (row >= nrow) return;
+    const int k = (int)(row % a.nh);
+    const size_t t = row / a.nh;
+    const int s = (int)(t % 2), lev = (int)((t / 2) % a.n_lev), f = (int)(t / 2 / a.n_lev);
+    double sum = 0.0;
+    if (a.mean_field[f] >= 0) {
+        const double *g = a.gin + ((((size_t)a.mean_field[f] * a.n_lev + lev) * 2 + s) * a.nh + k) * a.n_phi;
+        for (int j = lane; j < a.n_phi; j += 32) sum += g[j];
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) a.means[row] = sum * (1.0 / (double)a.n_phi);
+}
+
+struct DiagPoint { double vr, vt, vp, cvr, dvrdr, dvtdr, dvpdr, dvrdt, dvrdp, dvtdp, dvpdp, s, p, drs, dsdt, dsdp, br, bt, bp, cbt, cbp; };
+
+// boundary values of transform_to_grid_space with lDeriv = .true. (rIter.f90:555-602, v_rigid_boundary nonlinear_bcs.f90:120-175);
+// applies to point values and to phi means alike (the overrides do not depend on phi)
+__device__ __forceinline__ void diag_override(const DiagArgs &a, const LevelInfo &L, double st, double ct, double &vr, double &vt, double &vp,
+                                              double &cvr) {
+    if (L.nBc == 1) vr = 0.0;
+    if (L.nBc == 2) {
+        const double r2 = (L.nR == 1) ? a.r_cmb * a.r_cmb : a.r_icb * a.r_icb;
+        const double om = (L.nR == 1) ? a.omega_ma : a.omega_ic;
+        vr = 0.0;
+        vt = 0.0;
+        vp = r2 * L.rho0 * (st * st) * om;
+        cvr = r2 * L.rho0 * 2.0 * ct * om;
+    }
+}
+
+// the sums of one grid point; h = 0 north, 1 south; ct carries the hemisphere sign; m[] = phi means of this hemisphere
+__device__ __forceinline__ void diag_point(const DiagArgs &a, const LevelInfo &L, const DiagPoint &p, const double *m, int h, double st, double ct,
+                                           double ga, double *acc) {
+    const double or1 = L.or1, or2 = L.or2, or4 = L.or4, orho1 = L.orho1, orho2 = L.orho2, beta = L.beta, r = L.r, visc = L.visc;
+    const double os2 = 1.0 / (st * st), st2 = st * st, cn2 = ct / st / st;
+    const double pn1 = 1.0 / (double)a.n_phi, pn2 = 6.283185307179586476925286766559 / (double)a.n_phi;
+    const double w1 = pn1 * ga, w2 = pn2 * ga;
+    if (a.mask & DM_HEL) {
+        const double vras = m[0], cvras = m[1], vtas = m[2], vpas = m[3], dvrdpas = m[4], dvpdras = m[5], dvtdras = m[6], dvrdtas = m[7];
+        const double vrna = p.vr - vras, cvrna = p.cvr - cvras, vtna = p.vt - vtas, vpna = p.vp - vpas;
+        const double dvrdpna = p.dvrdp - dvrdpas;
+        const double dvpdrna = p.dvpdr - beta * p.vp - dvpdras + beta * vpas;
+        const double dvtdrna = p.dvtdr - beta * p.vt - dvtdras + beta * vtas;
+        const double dvrdtna = p.dvrdt - dvrdtas;
+        const double Hel = or4 * orho2 * p.vr * p.cvr +
+                           or2 * orho2 * os2 * (p.vt * (or2 * p.dvrdp - p.dvpdr + beta * p.vp) + p.vp * (p.dvtdr - beta * p.vt - or2 * p.dvrdt));
+        const double Helna = or4 * orho2 * vrna * cvrna + or2 * orho2 * os2 * (vtna * (or2 * dvrdpna - dvpdrna) + vpna * (dvtdrna - or2 * dvrdtna));
+        acc[DG_HEL_N + h] += w1 * Hel;
+        acc[DG_HEL2_N + h] += w1 * Hel * Hel;
+        acc[DG_HELNA_N + h] += w1 * Helna;
+        acc[DG_HELNA2_N + h] += w1 * Helna * Helna;
+        acc[DG_HELEA] += (h ? -1.0 : 1.0) * w1 * Hel;
+    }
+    if (a.mask & DM_HEMI) {
+        acc[DG_EKIN_N + h] += w2 * (0.5 * orho1 * (or2 * p.vr * p.vr + os2 * p.vt * p.vt + os2 * p.vp * p.vp));
+        acc[DG_VRABS_N + h] += w2 * (orho1 * fabs(p.vr));
+        if (a.l_mag) {
+            acc[DG_EMAG_N + h] += w2 * (0.5 * (or2 * p.br * p.br + os2 * p.bt * p.bt + os2 * p.bp * p.bp));
+            acc[DG_BRABS_N + h] += w2 * fabs(p.br);
+        }
+    }
+    if (a.mask & DM_POWER) {
+        const double t1 = p.dvrdr - (2.0 * or1 + beta) * p.vr;
+        const double t2 = cn2 * p.vt + p.dvpdp + p.dvrdr - or1 * p.vr;
+        const double t3 = p.dvpdp + cn2 * p.vt + or1 * p.vr;
+        const double t6 = 2.0 * p.dvtdp + p.cvr - 2.0 * cn2 * p.vp;
+        const double t4 = r * p.dvtdr - (2.0 + beta * r) * p.vt + or1 * p.dvrdt;
+        const double t5 = r * p.dvpdr - (2.0 + beta * r) * p.vp + or1 * p.dvrdp;
+        const double t7 = beta * p.vr;
+        acc[DG_VISC] += w2 * (or2 * orho1 * visc *
+                              (2.0 * t1 * t1 + 2.0 * t2 * t2 + 2.0 * t3 * t3 + t6 * t6 + os2 * (t4 * t4 + t5 * t5) - 2.0 * (1.0 / 3.0) * t7 * t7));
+    }
+    if (a.mask & DM_PERPPAR) {
+        const double f = 0.5 * or2 * orho2, vras = m[0], vtas = m[2], vpas = m[3];
+        acc[DG_EPERP] += w1 * (f * (or2 * st2 * p.vr * p.vr + (os2 - 1.0) * p.vt * p.vt + 2.0 * or1 * ct * p.vr * p.vt + os2 * p.vp * p.vp));
+        acc[DG_EPAR] += w1 * (f * (or2 * (1.0 - st2) * p.vr * p.vr + p.vt * p.vt - 2.0 * or1 * ct * p.vr * p.vt));
+        acc[DG_EPERPAXI] += w1 * (f * (or2 * st2 * vras * vras + (os2 - 1.0) * vtas * vtas + 2.0 * or1 * ct * vras * vtas + os2 * vpas * vpas));
+        acc[DG_EPARAXI] += w1 * (f * (or2 * (1.0 - st2) * vras * vras + vtas * vtas - 2.0 * or1 * ct * vras * vtas));
+    }
+    if (a.mask & DM_FLUX) {
+        const bool bulk = L.nR != 1 && L.nR != a.n_r_max;
+        double fvisc = 0.0;
+        if (bulk)
+            fvisc = -2.0 * visc * orho1 * p.vr * or2 * (p.dvrdr - (2.0 * or1 + 2.0 * (1.0 / 3.0) * beta) * p.vr) -
+                    visc * orho1 * p.vt * os2 * (or2 * p.dvrdt + p.dvtdr - (2.0 * or1 + beta) * p.vt) -
+                    visc * orho1 * p.vp * os2 * (or2 * p.dvrdp + p.dvpdr - (2.0 * or1 + beta) * p.vp);
+        acc[DG_FKIN] += w2 * (0.5 * or2 * orho2 * (os2 * (p.vt * p.vt + p.vp * p.vp) + or2 * p.vr * p.vr) * p.vr);
+        acc[DG_FCONV_S] += w2 * (p.vr * p.s);
+        acc[DG_FCONV_P] += w2 * (p.vr * p.p);
+        acc[DG_FVISC] += w2 * fvisc;
+        if (a.l_mag_nl) {
+            acc[DG_FRES] += w2 * (os2 * (p.cbt * p.bp - p.cbp * p.bt));
+            acc[DG_FPOYN] += w2 * (-orho1 * or2 * os2 * (p.vp * p.br * p.bp - p.vr * p.bp * p.bp - p.vr * p.bt * p.bt + p.vt * p.br * p.bt));
+        }
+    }
+    if (a.mask & DM_VISCBC) {
+        const double uh = or2 * orho2 * os2 * (p.vt * p.vt + p.vp * p.vp);
+        const double duh = or2 * orho2 * os2 * (p.dvtdr * p.vt - (or1 + beta) * p.vt * p.vt + p.dvpdr * p.vp - (or1 + beta) * p.vp * p.vp);
+        const double grads = p.drs * p.drs + or2 * os2 * (p.dsdt * p.dsdt + p.dsdp * p.dsdp);
+        acc[DG_UH] += w1 * sqrt(uh);
+        if (uh != 0.0) acc[DG_DUH] += w1 * fabs(duh) / sqrt(uh);
+        acc[DG_GRADT2] += w1 * grads;
+    }
+}
+
+__global__ void __launch_bounds__(DIAG_THREADS) diag_kernel(DiagArgs a) {
+    const int lev = blockIdx.y;
+    const LevelInfo L = a.lev[lev];
+    const size_t plane = (size_t)a.nh * a.n_phi;
+    const size_t mstride = (size_t)a.n_lev * 2 * a.nh;  // one averaged field
+    double acc[DIAG_NSLOT];
+#pragma unroll
+    for (int i = 0; i < DIAG_NSLOT; i++) acc[i] = 0.0;
+    const bool zero_grad_s = (L.nR == 1 && a.ktops == 1) || (L.nR == a.n_r_max && a.kbots == 1);  // rIter.f90:488-495
+    for (unsigned pt = blockIdx.x * blockDim.x + threadIdx.x; pt < (unsigned)plane; pt += gridDim.x * blockDim.x) {
+        const int k = (int)(pt / (unsigned)a.n_phi);
+        const double st = a.sinth[k], ct = a.costh[k], ga = a.gauss[k];
+        const int *fidx = &a.di.vr;
+        double re[DIAG_NF], ro[DIAG_NF];
+#pragma unroll
+        for (int f = 0; f < DIAG_NF; f++) {  // every load before the first use (in-order issue)
+            re[f] = 0.0;
+            ro[f] = 0.0;
+            if (fidx[f] >= 0) {
+                const double *base = a.gin + (((size_t)fidx[f] * a.n_lev + lev) * 2) * plane + pt;
+                re[f] = __ldg(base);
+                ro[f] = __ldg(base + plane);
+            }
+        }
+        DiagPoint pn, ps;
+        double *pnv = &pn.vr, *psv = &ps.vr;
+#pragma unroll
+        for (int f = 0; f < DIAG_NF; f++) {
+            pnv[f] = re[f] + ro[f];
+            psv[f] = re[f] - ro[f];
+        }
+        const double os2 = 1.0 / (st * st);  // torpol_to_dphspat post-scaling, sht_native.f90:263-270
+        pn.dvtdp *= os2; ps.dvtdp *= os2; pn.dvpdp *= os2; ps.dvpdp *= os2;
+        if (zero_grad_s) { pn.dsdt = ps.dsdt = 0.0; pn.dsdp = ps.dsdp = 0.0; }
+        diag_override(a, L, st, ct, pn.vr, pn.vt, pn.vp, pn.cvr);
+        diag_override(a, L, st, -ct, ps.vr, ps.vt, ps.vp, ps.cvr);
+        double mn[DIAG_NMEAN], ms[DIAG_NMEAN];
+        if (a.mask & (DM_HEL | DM_PERPPAR)) {
+#pragma unroll
+            for (int f = 0; f < DIAG_NMEAN; f++) {
+                const double e = a.means[(size_t)f * mstride + ((size_t)lev * 2 + 0) * a.nh + k];
+                const double o = a.means[(size_t)f * mstride + ((size_t)lev * 2 + 1) * a.nh + k];
+                mn[f] = e + o;
+                ms[f] = e - o;
+            }
+            diag_override(a, L, st, ct, mn[0], mn[2], mn[3], mn[1]);
+            diag_override(a, L, st, -ct, ms[0], ms[2], ms[3], ms[1]);
+        }
+        diag_point(a, L, pn, mn, 0, st, ct, ga, acc);
+        diag_point(a, L, ps, ms, 1, st, -ct, ga, acc);
+    }
+    __shared__ double red[DIAG_THREADS / 32][DIAG_NSLOT];
+#pragma unroll
+    for (int i = 0; i < DIAG_NSLOT; i++) {
+        double v = acc[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < DIAG_NSLOT) {
+        double v = 0.0;
+        for (int w = 0; w < DIAG_THREADS / 32; w++) v += red[w][threadIdx.x];
+        a.partial[((size_t)lev * gridDim.x + blockIdx.x) * DIAG_NSLOT + threadIdx.x] = v;
+    }
+}
+
+// CTA partials added in CTA order -> out[lev][slot]
+__global__ void diag_finish_kernel(const double *partial, int n_part, int n_lev, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lev * DIAG_NSLOT) return;
+    const int lev = i / DIAG_NSLOT, slot = i - lev * DIAG_NSLOT;
+    double v = 0.0;
+    for (int j = 0; j < n_part; j++) v += partial[((size_t)lev * n_part + j) * DIAG_NSLOT + slot];
+    out[i] = v;
+}
+
+}  // namespace magic

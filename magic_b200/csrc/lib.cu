@@ -3,4 +3,5 @@
 #include "engine.cu"
 #include "api_sht.cu"
 #include "api_rloop.cu"
+#include "api_diag.cu"
 #include "api_transp.cu"

@@ -29,6 +29,9 @@ class Params(C.Structure):
 
 RADIAL_NAMES = ["r", "or1", "or2", "or4", "orho1", "orho2", "beta", "rho0", "otemp1", "temp0", "visc", "lambda",
                 "epscProf", "delxr2", "delxh2"]
+# magic_rloop_diagnostics: mask bits and slots (include/magic_sht.h)
+DIAG_HEL, DIAG_HEMI, DIAG_POWER, DIAG_PERPPAR, DIAG_FLUX, DIAG_VISCBC, DIAG_RMSBULK = 1, 2, 4, 8, 16, 32, 256
+NDIAG = 32
 IN_NAMES = ["w", "dw", "ddw", "z", "dz", "s", "ds", "p", "xi", "b", "db", "ddb", "aj", "dj"]
 OUT_NAMES = ["dwdt", "dzdt", "dpdt", "dsdt", "dxidt", "dbdt", "djdt", "dVxVhLM", "dVxBhLM", "dVSrLM", "dVXirLM"]
 
@@ -135,6 +138,27 @@ class RadialLoop:
             out["dthkc"] = np.zeros(self.n_r_loc)
         fin, fout, keep = self._structs(fields, out, out["dtrkc"], out["dthkc"], device=False)
         check(self.lib.magic_rloop_run(self._h, byref(fin), byref(fout), c_double(time)))
+        return out
+
+    def diagnostics(self, fields, mask, ktops=1, kbots=1, device=False):
+        """The in-loop diagnostics of a log step (rIter.f90:303-373: get_helicity, get_hemi, get_visc_heat, get_perpPar,
+        get_fluxes, get_nlBLayers) for this rank's levels: float64 [n_r_loc, NDIAG], slots as documented in
+        include/magic_sht.h.  fields as for radialLoop (host arrays), or device pointers with device=True."""
+        fin, _, keep = self._structs(fields, {}, 0 if device else np.zeros(1), 0 if device else np.zeros(1), device=device)
+        out = np.zeros((self.n_r_loc, NDIAG))
+        fn = self.lib.magic_rloop_diagnostics_dev if device else self.lib.magic_rloop_diagnostics
+        check(fn(self._h, byref(fin), c_int(mask), c_int(ktops), c_int(kbots), out.ctypes.data_as(c_void_p)))
+        return out
+
+    def graph_fields(self, fields, level, mag=False, pressure=False):
+        """The grid fields graphOut_mpi reads (rIter.f90:303-314) for local level `level`: dict of float64
+        [n_phi, nlat_padded] arrays (Fortran f(nlat_padded, n_phi))."""
+        fin, _, keep = self._structs(fields, {}, np.zeros(1), np.zeros(1), device=False)
+        shp = (self.sht.n_phi_max, self.sht.nlat_padded)
+        names = ["vr", "vt", "vp"] + (["br", "bt", "bp"] if mag else []) + ["sr"] + (["pr"] if pressure else [])
+        out = {n: np.zeros(shp) for n in names}
+        ptrs = [out[n].ctypes.data_as(c_void_p) if n in out else c_void_p(None) for n in ("vr", "vt", "vp", "br", "bt", "bp", "sr", "pr")]
+        check(self.lib.magic_rloop_graph_fields(self._h, byref(fin), c_int(level), *ptrs))
         return out
 
     def radialLoop_dev(self, fields_dev, out_dev, dtrkc_dev, dthkc_dev, time=0.0):

@@ -418,3 +418,4 @@ void orc_fft_many(const orc_ctx *c, const double *g, orc_cplx *f) {
 
 #include "magic_oracle_sht.inc"
 #include "magic_oracle_rloop.inc"
+#include "magic_oracle_diag.inc"

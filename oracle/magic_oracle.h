@@ -184,6 +184,13 @@ typedef struct {
 void orc_radial_loop(const orc_ctx *c, const orc_params *p, const orc_radial *rad, int n_r,
                      const orc_fields_in *in, const orc_fields_out *out, double time);
 
+/* The grid-space diagnostics of rIter.f90:303-373 (get_helicity, get_hemi, get_visc_heat, get_perpPar, get_fluxes,
+ * get_nlBLayers) for n_r levels: out[n_r][32], slots as MAGIC_DG_* of include/magic_sht.h; mask = MAGIC_DIAG_* bits;
+ * ktops / kbots: thermal boundary condition types (fixed temperature = 1 zeroes the horizontal entropy gradient on that
+ * boundary, rIter.f90:488-495). */
+void orc_radial_diagnostics(const orc_ctx *c, const orc_params *p, const orc_radial *rad, int n_r, const orc_fields_in *in,
+                            int mask, int ktops, int kbots, double *out);
+
 /* get_nl only, on caller-provided grids (get_nl.f90:213-441): in/out arrays are [nphi][nlat] each.
  * in: vr vt vp cvr cvt cvp s br bt bp cbr cbt cbp (13) ; out: Advr Advt Advp LFr LFt LFp VSr VSt VSp
  * VxBr VxBt VxBp (12).  Provided so tests can check the grid-space kernel in isolation. */

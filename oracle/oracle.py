@@ -305,6 +305,33 @@ class Oracle:
         out["lorentz_torque_ic"], out["lorentz_torque_ma"] = float(tq[0]), float(tq[1])
         return out
 
+    def radial_diagnostics(self, params, radial, fields, mask, ktops=1, kbots=1):
+        """rIter.f90:303-373 (get_helicity, get_hemi, get_visc_heat, get_perpPar, get_fluxes, get_nlBLayers) for the levels in
+        `radial`: float64 [n_r, 32], slots as MAGIC_DG_* of include/magic_sht.h."""
+        n_r = len(radial["nR"])
+        keep = []
+        rad = _Radial()
+        for nm in ["nR", "l_R"]:
+            a = np.ascontiguousarray(radial[nm], dtype=np.int32)
+            keep.append(a)
+            setattr(rad, nm, _p(a))
+        for nm in _RAD_NAMES:
+            key = "lambda" if nm == "lambda_" else nm
+            a = np.ascontiguousarray(radial.get(key, np.ones(n_r)), dtype=np.float64)
+            keep.append(a)
+            setattr(rad, nm, _p(a))
+        fin = _FieldsIn()
+        for nm in _IN_NAMES:
+            if nm in fields and fields[nm] is not None:
+                a = self._c(fields[nm])
+                assert a.shape == (n_r, self.lm_max)
+                keep.append(a)
+                setattr(fin, nm, _p(a))
+        out = np.zeros((n_r, 32))
+        self.lib.orc_radial_diagnostics(self.h, C.byref(params), C.byref(rad), c_int(n_r), C.byref(fin), c_int(mask), c_int(ktops),
+                                        c_int(kbots), _p(out))
+        return out
+
     def get_nl_mhd(self, params, nR, nBc, or2, or4, orho1, grids_in):
         """get_nl.f90:213-441 on 13 caller grids -> 12 product grids."""
         ins = [self._r(g) for g in grids_in]

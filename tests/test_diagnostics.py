@@ -1,0 +1,164 @@
+"""In-loop diagnostics of log steps (rIter.f90:303-373): get_helicity, get_hemi (outMisc.f90:991-1167),
+get_visc_heat (power.f90:384-441), get_perpPar, get_fluxes, get_nlBLayers (outPar.f90:470-726).
+
+CPU: the oracle's restatement (oracle/magic_oracle_diag.inc) against closed forms that do not go through the grid --
+Parseval for the hemispheric energies, solid-body rotation for helicity / viscous heating / E_perp.
+GPU (-m gpu): magic_rloop_diagnostics through the C ABI against the oracle on the same seeded spectra: Boussinesq MHD with
+rigid walls, anelastic hydro with stress-free walls, rotating rigid walls, lRmsCalc (boundaries as bulk), device pointers.
+The golden pin of these routines (helicity.TAG / hemi.TAG / power.TAG of samples/testOutputs) is tests/test_testOutputs.py.
+"""
+import numpy as np
+import pytest
+
+from magic_b200.riter import (DIAG_FLUX, DIAG_HEL, DIAG_HEMI, DIAG_PERPPAR, DIAG_POWER, DIAG_RMSBULK, DIAG_VISCBC, NDIAG)
+from magic_b200.workload import make_fields, make_params, make_radial
+
+ALL = DIAG_HEL | DIAG_HEMI | DIAG_POWER | DIAG_PERPPAR | DIAG_FLUX | DIAG_VISCBC
+TOL = 1e-12   # relative to the largest entry of a slot over the levels (sums of ~1e4 positive and negative terms)
+
+
+def _oracle(l_max, minc=1):
+    from oracle.oracle import Oracle
+    return Oracle(l_max, minc=minc)
+
+
+def _oparams(p):
+    from oracle.oracle import Params as OParams
+    op = OParams()
+    for n, _ in p._fields_:
+        setattr(op, n, getattr(p, n))
+    return op
+
+
+def _case(physics, l_max, n_r_max, lm2l, lm2m, seed, ktopv=2, kbotv=2, anel=False):
+    p = make_params(physics, n_r_max, ktopv=ktopv, kbotv=kbotv)
+    rad = make_radial(n_r_max, l_max, anel=anel)
+    f = make_fields(physics, lm2l, lm2m, n_r_max, seed)
+    rng = np.random.default_rng(seed + 7)
+    for nm, src in (("p", "s"), ("ds", "s")):   # pressure and the radial entropy derivative: any smooth spectra will do
+        f[nm] = f[src] * (0.3 + rng.random()) + 0.1 * f["w"]
+    return p, rad, f
+
+
+def test_oracle_hemispheric_energies_obey_parseval():
+    """get_hemi against the spectral energy: north + south of 1/2 int (vr^2/r^2 + (vt^2 + vp^2)/sin^2) dOmega (the grid fields
+    are r^2 u_r and r sin(theta) u_h) equals 1/2 sum_lm (2 - delta_m0) [ l^2(l+1)^2/r^2 |w|^2 + l(l+1) (|dw|^2 + |z|^2) ] for
+    an orthonormal basis."""
+    l_max, n_r = 12, 5
+    o = _oracle(l_max)
+    p, rad, f = _case("mhd", l_max, n_r, o.lm2l, o.lm2m, 3)
+    d = o.radial_diagnostics(_oparams(p), rad, f, DIAG_HEMI | DIAG_RMSBULK)
+    l, m = o.lm2l.astype(float), o.lm2m
+    fac = np.where(m == 0, 1.0, 2.0)
+    dLh = l * (l + 1.0)
+    for i in range(n_r):
+        or2 = rad["or2"][i]
+        for (q, s, t, n0) in (("w", "dw", "z", 9), ("b", "db", "aj", 13)):
+            e = 0.5 * np.sum(fac * (dLh ** 2 * or2 * abs(f[q][i]) ** 2 + dLh * (abs(f[s][i]) ** 2 + abs(f[t][i]) ** 2)))
+            assert abs(d[i, n0] + d[i, n0 + 1] - e) < 1e-12 * e
+
+
+def test_oracle_solid_body_rotation_closed_forms():
+    """A rigid rotation about z (toroidal l=1, m=0: z = c r^2) has no helicity, no viscous heating, and all its kinetic
+    energy perpendicular to the axis: E_perp = E_perp_axi = the hemi energies (up to the 2 pi / r^2 factors of the
+    routines), E_par = 0."""
+    l_max, n_r = 8, 4
+    o = _oracle(l_max)
+    p = make_params("hydro", n_r)
+    rad = make_radial(n_r, l_max)
+    lm10 = int(np.where((o.lm2l == 1) & (o.lm2m == 0))[0][0])
+    f = {k: np.zeros((n_r, o.lm_max), dtype=complex) for k in ("w", "dw", "ddw", "z", "dz", "s", "ds", "p")}
+    c = 0.7
+    f["z"][:, lm10] = c * rad["r"] ** 2
+    f["dz"][:, lm10] = 2 * c * rad["r"]
+    d = o.radial_diagnostics(_oparams(p), rad, f, ALL | DIAG_RMSBULK)
+    scale = np.abs(d).max()
+    assert np.abs(d[:, 0:9]).max() < 1e-13 * scale          # helicity
+    assert np.abs(d[:, 17]).max() < 1e-10 * scale           # viscous heating of a rigid rotation
+    assert np.abs(d[:, 19]).max() < 1e-13 * scale and np.abs(d[:, 21]).max() < 1e-13 * scale   # E_par
+    np.testing.assert_allclose(d[:, 18], d[:, 20], rtol=1e-12)                                    # axisymmetric flow
+    np.testing.assert_allclose(2 * np.pi * d[:, 18], (d[:, 9] + d[:, 10]) * rad["or2"], rtol=1e-12)   # orho = 1
+
+
+def _compare(got, ref, mask, label):
+    worst = 0.0
+    for s in range(NDIAG):
+        scale = np.abs(ref[:, s]).max()
+        if scale == 0.0:
+            assert np.abs(got[:, s]).max() == 0.0, f"{label}: slot {s} should be zero"
+            continue
+        err = np.abs(got[:, s] - ref[:, s]).max() / scale
+        worst = max(worst, err)
+        assert err < TOL, f"{label}: slot {s} deviates by {err:.2e}"
+    print(f"{label}: worst slot error {worst:.2e}")
+
+
+CASES = [
+    # physics, l_max, n_r, ktopv, kbotv, anel, extra mask, omega_ic
+    ("mhd", 21, 7, 2, 2, False, 0, 0.0),
+    ("mhd", 16, 6, 1, 1, False, 0, 0.0),
+    ("anel", 32, 6, 1, 2, True, 0, 0.0),
+    ("mhd", 16, 5, 2, 2, False, 0, 3.5),
+    ("mhd", 16, 5, 2, 1, False, DIAG_RMSBULK, 0.0),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("physics,l_max,n_r,ktopv,kbotv,anel,extra,omega_ic", CASES)
+def test_gpu_diagnostics_against_the_oracle(physics, l_max, n_r, ktopv, kbotv, anel, extra, omega_ic):
+    from magic_b200 import RadialLoop, Sht
+    s = Sht(l_max)
+    o = _oracle(l_max)
+    p, rad, f = _case(physics, l_max, n_r, s.lm2l, s.lm2m, 11 + l_max, ktopv, kbotv, anel)
+    if omega_ic:
+        p.omega_ic, p.l_rot_ic = omega_ic, 1
+    rl = RadialLoop(s, p, rad)
+    for mask in (ALL | extra, DIAG_HEL | extra, DIAG_HEMI | DIAG_POWER | extra):
+        got = rl.diagnostics(f, mask, ktops=1, kbots=2)
+        ref = o.radial_diagnostics(_oparams(p), rad, f, mask, ktops=1, kbots=2)
+        _compare(got, ref, mask, f"{physics} l{l_max} ktopv{ktopv} kbotv{kbotv} mask {mask}")
+    again = rl.diagnostics(f, ALL | extra, ktops=1, kbots=2)
+    assert np.array_equal(again, rl.diagnostics(f, ALL | extra, ktops=1, kbots=2)), "diagnostics are not bitwise repeatable"
+    rl.finalize()
+    s.finalize_sht()
+
+
+@pytest.mark.gpu
+def test_gpu_diagnostics_device_pointers_and_level_chunks():
+    """Device-resident inputs give the bits of the host-pointer call; a radial loop run before and after is unaffected."""
+    import torch
+    from magic_b200 import RadialLoop, Sht
+    l_max, n_r = 32, 40          # more levels than one diagnostics chunk (32): exercises the shifted last chunk
+    s = Sht(l_max)
+    p, rad, f = _case("mhd", l_max, n_r, s.lm2l, s.lm2m, 5)
+    rl = RadialLoop(s, p, rad)
+    before = rl.radialLoop(f)
+    host = rl.diagnostics(f, ALL)
+    dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in f.items()}
+    got = rl.diagnostics({k: v.data_ptr() for k, v in dev.items()}, ALL, device=True)
+    assert np.array_equal(host, got)
+    after = rl.radialLoop(f)
+    for k in before:
+        assert np.array_equal(before[k], after[k]), k
+    o = _oracle(l_max)
+    _compare(host, o.radial_diagnostics(_oparams(p), rad, f, ALL), ALL, "mhd l32, 40 levels")
+    rl.finalize()
+    s.finalize_sht()
+
+
+@pytest.mark.gpu
+def test_gpu_graph_fields_are_the_per_call_transforms():
+    from magic_b200 import RadialLoop, Sht
+    l_max, n_r = 16, 4
+    s = Sht(l_max)
+    o = _oracle(l_max)
+    p, rad, f = _case("mhd", l_max, n_r, s.lm2l, s.lm2m, 9)
+    rl = RadialLoop(s, p, rad)
+    g = rl.graph_fields(f, 2, mag=True, pressure=True)
+    vr, vt, vp = o.torpol_to_spat(f["w"][2], f["dw"][2], f["z"][2], l_max)
+    br, bt, bp = o.torpol_to_spat(f["b"][2], f["db"][2], f["aj"][2], l_max)
+    for got, ref in ((g["vr"], vr), (g["vt"], vt), (g["vp"], vp), (g["br"], br), (g["bt"], bt), (g["bp"], bp),
+                     (g["sr"], o.scal_to_spat(f["s"][2], l_max)), (g["pr"], o.scal_to_spat(f["p"][2], l_max))):
+        assert np.linalg.norm(got - ref) < 1e-12 * np.linalg.norm(ref)
+    rl.finalize()
+    s.finalize_sht()
