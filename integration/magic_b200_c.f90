@@ -54,6 +54,10 @@ module magic_b200_c
       type(c_ptr) :: dxidt
    end type magic_lm_out
 
+   !-- magic_rloop_diagnostics: mask bits (include/magic_sht.h)
+   integer(c_int), parameter :: MAGIC_DIAG_HEL = 1, MAGIC_DIAG_HEMI = 2, MAGIC_DIAG_POWER = 4, MAGIC_DIAG_PERPPAR = 8, &
+   &                            MAGIC_DIAG_FLUX = 16, MAGIC_DIAG_VISCBC = 32, MAGIC_DIAG_RMSBULK = 256
+
    interface
 
       !---------------------------------------------------------------- C library
@@ -298,6 +302,16 @@ module magic_b200_c
          complex(c_double_complex), intent(out) :: br_vt_lm(*), br_vp_lm(*)
          integer(c_int) :: ierr
       end function magic_rloop_get_br_v_bcs
+
+      !-- in-loop diagnostics of log steps (rIter.f90:303-373): out(MAGIC_NDIAG, n_r_loc), slots as in include/magic_sht.h
+      function magic_rloop_diagnostics(rl, fin, mask, ktops, kbots, out) bind(C, name='magic_rloop_diagnostics') result(ierr)
+         import :: c_int, c_ptr, c_double, magic_fields_in
+         type(c_ptr), value :: rl
+         type(magic_fields_in), intent(in) :: fin
+         integer(c_int), value :: mask, ktops, kbots
+         real(c_double), intent(out) :: out(32,*)
+         integer(c_int) :: ierr
+      end function magic_rloop_diagnostics
 
       !---------------------------------------------------------------- r <-> LM transposer
       function magic_transp_unique_id(id) bind(C, name='magic_transp_unique_id') result(ierr)

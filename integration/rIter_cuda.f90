@@ -24,9 +24,16 @@ module rIter_cuda_mod
        &            l_phase_field, l_onset
    use special, only: lGrenoble
    use physical_parameters, only: ktopv, kbotv, n_r_LCR, LFfac, CorFac, epsc, epscXi, opm, ViscHeatFac,     &
-       &                          OhmLossFac, oek, po, prec_angle, dilution_fac, ra, opr
+       &                          OhmLossFac, oek, po, prec_angle, dilution_fac, ra, opr, ktops, kbots,     &
+       &                          ThExpNb
    use radial_functions, only: r, or1, or2, or4, orho1, orho2, beta, rho0, otemp1, temp0, visc, lambda,     &
-       &                       epscProf, l_R, r_cmb, r_icb
+       &                       epscProf, l_R, r_cmb, r_icb, alpha0
+   !-- per-level sums of the in-loop diagnostics (module variables of the reference, to be made public there)
+   use outMisc_mod, only: HelASr, Hel2ASr, HelnaASr, Helna2ASr, HelEAASr, hemi_ekin_r, hemi_vrabs_r,        &
+       &                  hemi_emag_r, hemi_brabs_r
+   use power, only: viscASr
+   use outPar_mod, only: EperpASr, EparASr, EperpaxiASr, EparaxiASr, fkinASr, fconvASr, fviscASr, fresASr,  &
+       &                 fpoynASr, uhASr, duhASr, gradT2ASr
    use num_param, only: delxr2, delxh2
    use fields, only: s_Rloc, ds_Rloc, z_Rloc, dz_Rloc, p_Rloc, b_Rloc, db_Rloc, ddb_Rloc, aj_Rloc, dj_Rloc, &
        &             w_Rloc, dw_Rloc, ddw_Rloc, xi_Rloc, omega_ic, omega_ma,                                &
@@ -211,12 +218,17 @@ contains
       type(magic_fields_out) :: fout
       type(magic_lm_in)      :: lin
       type(magic_lm_out)     :: lout
-      integer :: ist
+      integer :: ist, mask, nR
+      logical :: l_diag
+      real(c_double), allocatable :: dg(:,:)
 
-      !-- Diagnostics steps keep the reference's level-at-a-time loop (its transforms still run on the GPU)
-      if ( l_graph .or. l_frame .or. lTOCalc .or. lTONext .or. lTONext2 .or. lHelCalc .or. lPowerCalc .or.   &
-      &    lRmsCalc .or. lPressCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lGeosCalc .or. &
-      &    lHemiCalc .or. lPhaseCalc .or. l_probe_out .or. ( lPressNext .and. l_double_curl ) ) then
+      !-- Log steps: get_helicity, get_hemi, get_visc_heat, get_perpPar, get_fluxes and get_nlBLayers (rIter.f90:320-367) are
+      !   evaluated on the device after the batched loop (diagnostics_on_device below).  The remaining output hooks keep the
+      !   reference's level-at-a-time loop (its transforms still run on the GPU)
+      if ( l_graph .or. l_frame .or. lTOCalc .or. lTONext .or. lTONext2 .or. lRmsCalc .or. lPressCalc .or.   &
+      &    lGeosCalc .or. lPhaseCalc .or. l_probe_out .or. ( lPressNext .and. l_double_curl ) .or.           &
+      &    ( l_full_sphere .and. ( lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or.        &
+      &                            lPerpParCalc .or. lHemiCalc ) ) ) then
          !-- ( lPressNext with the double-curl equation: the reference also calls get_dpdt then (rIter.f90:420); the batched
          !   loop only produces dpdt in the pressure formulation, so that step takes the level-at-a-time loop )
          if ( l_fused_lm ) then   ! the recorded transposes become real: the level-at-a-time loop reads the host R arrays
@@ -237,7 +249,8 @@ contains
       !-- Fused mode: LM-distributed host containers in, LM-distributed explicit terms out -- the transposes on either side of
       !   this call (step_time.f90:485, :612) are part of it (mpi_transp_cuda_mod); the explicit terms go into the slice
       !   tscheme%istage of the time-array containers, which is where transp_Rloc_to_LMloc would put them (step_time.f90:1134-1245)
-      if ( l_fused_lm .and. n_pending > 0 .and. .not. ( l_b_nl_cmb .or. l_b_nl_icb ) ) then
+      l_diag = lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lHemiCalc
+      if ( l_fused_lm .and. n_pending > 0 .and. .not. ( l_b_nl_cmb .or. l_b_nl_icb .or. l_diag ) ) then
          ist = tscheme%istage
          lin  = magic_lm_in(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr)
          lout = magic_lm_out(c_null_ptr, c_null_ptr, c_null_ptr, addr_r(dtrkc), addr_r(dthkc), c_null_ptr)
@@ -319,6 +332,54 @@ contains
 
       !-- the phase field is not on this path (initialize aborts when it is switched on)
       dphidt(:,:) = zero
+
+      !-- rIter.f90:320-367 on log steps: one call returns the per-level sums of all requested routines; they go where the
+      !   reference's routines store them (the arrays below are module variables of outMisc_mod, power and outPar_mod, to be
+      !   made public there: HelASr .. HelEAASr, hemi_*_r, viscASr, EperpASr .. EparaxiASr, fkinASr .. fpoynASr, uhASr ..)
+      if ( l_diag ) then
+         mask = 0
+         if ( lHelCalc )      mask = mask + MAGIC_DIAG_HEL
+         if ( lHemiCalc )     mask = mask + MAGIC_DIAG_HEMI
+         if ( lPowerCalc )    mask = mask + MAGIC_DIAG_POWER
+         if ( lPerpParCalc )  mask = mask + MAGIC_DIAG_PERPPAR
+         if ( lFluxProfCalc ) mask = mask + MAGIC_DIAG_FLUX
+         if ( lViscBcCalc )   mask = mask + MAGIC_DIAG_VISCBC
+         if ( lFluxProfCalc ) fin%p = c_loc(p_Rloc)    ! lPressCalc is set with lFluxProfCalc (step_time.f90:399)
+         allocate( dg(32,nRstart:nRstop) )
+         call magic_check( magic_rloop_diagnostics(this%rl, fin, int(mask,c_int), int(ktops,c_int), int(kbots,c_int), dg), &
+              &            'magic_rloop_diagnostics' )
+         do nR=nRstart,nRstop
+            if ( lHelCalc ) then
+               HelASr(nR,:)=dg(1:2,nR);  Hel2ASr(nR,:)=dg(3:4,nR);  HelnaASr(nR,:)=dg(5:6,nR)
+               Helna2ASr(nR,:)=dg(7:8,nR);  HelEAASr(nR)=dg(9,nR)
+            end if
+            if ( lHemiCalc ) then
+               hemi_ekin_r(nR,:)=dg(10:11,nR);  hemi_vrabs_r(nR,:)=dg(12:13,nR)
+               if ( l_mag ) then
+                  hemi_emag_r(nR,:)=dg(14:15,nR);  hemi_brabs_r(nR,:)=dg(16:17,nR)
+               end if
+            end if
+            if ( lPowerCalc ) viscASr(nR)=dg(18,nR)
+            if ( lPerpParCalc ) then
+               EperpASr(nR)=dg(19,nR);  EparASr(nR)=dg(20,nR);  EperpaxiASr(nR)=dg(21,nR);  EparaxiASr(nR)=dg(22,nR)
+            end if
+            if ( lFluxProfCalc ) then
+               fkinASr(nR)=dg(23,nR);  fviscASr(nR)=dg(26,nR)
+               if ( l_anelastic_liquid ) then                                       ! outPar.f90:511-517
+                  fconvASr(nR)=dg(24,nR)
+               else
+                  fconvASr(nR)=temp0(nR)*dg(24,nR)+ViscHeatFac*ThExpNb*alpha0(nR)*temp0(nR)*orho1(nR)*dg(25,nR)
+               end if
+               if ( l_mag_nl ) then
+                  fresASr(nR)=dg(27,nR);  fpoynASr(nR)=dg(28,nR)
+               end if
+            end if
+            if ( lViscBcCalc ) then
+               uhASr(nR)=dg(29,nR);  duhASr(nR)=dg(30,nR);  gradT2ASr(nR)=dg(31,nR)
+            end if
+         end do
+         deallocate( dg )
+      end if
 
    end subroutine radialLoop
 !------------------------------------------------------------------------------
