@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--level-chunk", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-f1", default="on", choices=["on", "off"],
+                    help="also time the end-to-end call with the LM-side prologue / epilogue on the device (SURVEY 8(f)1); e2e = the faster")
     ap.add_argument("--overlap", default="auto", choices=["auto", "on", "off"],
                     help="transposes pipelined chunk-wise against the compute (magic_rloop_run_lm_dev); auto = on for N > 1")
     ap.add_argument("--no-cpu", action="store_true")
@@ -446,28 +448,65 @@ def run_magic(args, gs):
         # bytes that cross PCIe per step: the fields the loop reads (ds is not) / every explicit term
         h2d = sum(v[:(1 if k == "s" else v.shape[0])].nbytes for k, v in np_in.items())
         d2h = sum(v.nbytes for v in np_out.values()) + h_dtr.nbytes + h_dth.nbytes
-        for _ in range(max(1, min(args.warmup, 2))):
-            rl.run_lm(tr, np_in, np_out, h_dtr, h_dth)
-        same = local_bits(h_out.values()) == ref_bits
-        barrier()
-        t0 = time.perf_counter()
-        with torch.cuda.stream(ext):
-            e0.record(ext)
-            for _ in range(args.steps):
+        def time_e2e():
+            for _ in range(max(1, min(args.warmup, 2))):
                 rl.run_lm(tr, np_in, np_out, h_dtr, h_dth)
-            e1.record(ext)
-        barrier()
-        wall = (time.perf_counter() - t0) / args.steps * 1e3
-        ems = torch.tensor([max(e0.elapsed_time(e1) / args.steps, wall)], dtype=torch.float64, device=dev)
-        sm = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+            bits = local_bits(h_out.values())
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(ext):
+                e0.record(ext)
+                for _ in range(args.steps):
+                    rl.run_lm(tr, np_in, np_out, h_dtr, h_dth)
+                e1.record(ext)
+            barrier()
+            wall = (time.perf_counter() - t0) / args.steps * 1e3
+            ems = torch.tensor([max(e0.elapsed_time(e1) / args.steps, wall)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+            return float(ems.item()), bits
+
+        def record(ms_e2e, h2d_b, d2h_b, path, extra):
+            r = {"value": total_flops / (ms_e2e * 1e-3) * 1e-9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
+                 "ms_per_step": ms_e2e, "bytes_are": "per rank", "path": path}
+            r.update(extra)
+            return r
+
+        # (A) every container crosses PCIe: 11 field arrays up (ds is not read), 8 explicit terms down
+        ms_a, bits_a = time_e2e()
+        sm = torch.tensor([1 if bits_a == ref_bits else 0], dtype=torch.int32, device=dev)
         if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
             dist.all_reduce(sm, op=dist.ReduceOp.MIN)
-        e2e = {"value": total_flops / (float(ems.item()) * 1e-3) * 1e-9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(ems.item()), "bytes_are": "per rank",
-               "bit_identical_to_device_path": bool(sm.item()),
-               "path": "magic_rloop_run_lm (host LM-distributed containers in, host LM-distributed explicit terms out: PCIe up, "
-                       "lm2r, radial loop, r2lm, PCIe down, pipelined level chunk by level chunk)"}
+        variants = {"full_containers": record(
+            ms_a, h2d, d2h, "magic_rloop_run_lm (host LM-distributed containers in, host LM-distributed explicit terms out: PCIe up, "
+            "lm2r, radial loop, r2lm, PCIe down, pipelined level chunk by level chunk)", {"bit_identical_to_device_path": bool(sm.item())})}
+        # (B) SURVEY 8(f)1 on the device (magic_rloop_lm_options): dw, ddw, dz, db, ddb, dj come from w, z, b, aj by the radial-matrix
+        #     GEMM in the LM distribution, finish_explicit_assembly runs after the outbound transposes -- only w, z, s, b, aj go
+        #     up and dVSrLM, dVxBhLM (dVxVhLM) stay down.  Same kernels and level count; the derivative inputs of the loop are then
+        #     D w instead of independent random spectra, so the results are not comparable bit for bit (parity of this path:
+        #     tests/test_lm_side_gpu.py).
+        if args.e2e_f1 == "on":
+            from magic_b200.workload import cheb_matrices
+            D1, D2 = cheb_matrices(n_r_max)
+            full = make_radial(n_r_max, gs["l_max"], l_R=config_l_R(gs), anel=gs["physics"] == "anel")
+            rl.set_radial_matrices(D1, D2)
+            rl.set_lm_radial(full["or2"], full["orho1"], np.zeros(n_r_max), full["l_R"])
+            rl.lm_options(derivs_on_device=True, finish_on_device=True)
+            fld = lambda v: v[0].nbytes
+            h2d_b = 2 * fld(np_in["flow"]) + fld(np_in["s"]) + (2 * fld(np_in["field"]) if "field" in np_in else 0)
+            d2h_b = 3 * fld(np_out["dflowdt"]) + fld(np_out["dsdt"]) + (2 * fld(np_out["dbdt"]) if "dbdt" in np_out else 0) \
+                + h_dtr.nbytes + h_dth.nbytes
+            ms_b, _ = time_e2e()
+            rl.lm_options(derivs_on_device=False, finish_on_device=False)
+            variants["derivatives_and_finish_on_device"] = record(
+                ms_b, h2d_b, d2h_b, "magic_rloop_run_lm with magic_rloop_lm_options(1, 1): only w, z, s, b, aj cross PCIe upwards (radial "
+                "derivatives by a radial-matrix GEMM on the device), finish_explicit_assembly on the device after the outbound "
+                "transposes (dVSrLM, dVxBhLM stay on the device)", {"parity": "tests/test_lm_side_gpu.py"})
+        best = min(variants, key=lambda k: variants[k]["ms_per_step"])
+        e2e = dict(variants[best])
+        e2e["variant"] = best
+        e2e["variants"] = {k: {kk: vv for kk, vv in v.items() if kk in ("ms_per_step", "value", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+                           for k, v in variants.items()}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------------------
     cpu = None

@@ -166,6 +166,13 @@ int magic_rloop_get_br_v_bcs(const magic_rloop *rl, int boundary, double *br_vt_
 #define MAGIC_NDIAG 32
 int magic_rloop_diagnostics(magic_rloop *rl, const magic_fields_in *in, int mask, int ktops, int kbots, double *out);
 int magic_rloop_diagnostics_dev(magic_rloop *rl, const magic_fields_in *in, int mask, int ktops, int kbots, double *out);
+/* get_dtBLM (rIter.f90:392-395, dtB.f90:144-223), what the loop contributes when l_dtB is on: the eleven grid
+ * products of (vr, vt, vp, br, bt, bp) and their analyses (2 spat_to_sphertor + 7 scal_to_SH with lcut = l_max) for all local
+ * levels, as one more batch on the Legendre GEMM / FFT kernels.  out: HOST complex [11][n_r_loc][lm_max] = BtVrLM, BpVrLM,
+ * BrVtLM, BrVpLM, BtVpLM, BpVtLM, BpVtBtVpCotLM, BpVtBtVpSn2LM, BrVZLM, BtVZLM, BtVZsn2LM (the module arrays of dtB.f90:52-56,
+ * which get_dH_dtBLM then combines level by level).  in: HOST pointers (w, dw, z, b, db, aj are read); _dev: device pointers. */
+int magic_rloop_dtb(magic_rloop *rl, const magic_fields_in *in, double *out);
+int magic_rloop_dtb_dev(magic_rloop *rl, const magic_fields_in *in, double *out);
 /* The grid fields graphOut_mpi writes (rIter.f90:303-314, out_graph_file.f90:337) for one local level (0-based), HOST arrays
  * f(nlat_padded, n_phi) in the layout of the per-call transforms; NULL outputs are skipped (vr/vt/vp and br/bt/bp as triples). */
 int magic_rloop_graph_fields(magic_rloop *rl, const magic_fields_in *in, int level, double *vr, double *vt, double *vp, double *br,

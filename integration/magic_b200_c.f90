@@ -313,6 +313,15 @@ module magic_b200_c
          integer(c_int) :: ierr
       end function magic_rloop_diagnostics
 
+      !-- get_dtBLM (dtB.f90:144-223) for all local levels: out(lm_max, n_r_loc, 11)
+      function magic_rloop_dtb(rl, fin, out) bind(C, name='magic_rloop_dtb') result(ierr)
+         import :: c_int, c_ptr, c_double_complex, magic_fields_in
+         type(c_ptr), value :: rl
+         type(magic_fields_in), intent(in) :: fin
+         complex(c_double_complex), intent(out) :: out(*)
+         integer(c_int) :: ierr
+      end function magic_rloop_dtb
+
       !---------------------------------------------------------------- r <-> LM transposer
       function magic_transp_unique_id(id) bind(C, name='magic_transp_unique_id') result(ierr)
          import :: c_int, c_char

@@ -21,7 +21,7 @@ module rIter_cuda_mod
        &            l_adv_curl, l_corr, l_double_curl, l_single_matrix, l_chemical_conv, l_precession,      &
        &            l_centrifuge, l_anelastic_liquid, l_cour_alf_damp, l_full_sphere, l_parallel_solve,     &
        &            l_temperature_diff, l_cond_ma, l_cond_ic, l_rot_ma, l_rot_ic, l_b_nl_cmb, l_b_nl_icb,   &
-       &            l_phase_field, l_onset
+       &            l_phase_field, l_onset, l_dtB
    use special, only: lGrenoble
    use physical_parameters, only: ktopv, kbotv, n_r_LCR, LFfac, CorFac, epsc, epscXi, opm, ViscHeatFac,     &
        &                          OhmLossFac, oek, po, prec_angle, dilution_fac, ra, opr, ktops, kbots,     &
@@ -32,6 +32,9 @@ module rIter_cuda_mod
    use outMisc_mod, only: HelASr, Hel2ASr, HelnaASr, Helna2ASr, HelEAASr, hemi_ekin_r, hemi_vrabs_r,        &
        &                  hemi_emag_r, hemi_brabs_r
    use power, only: viscASr
+   !-- get_dtBLM's per-level results (module variables of dtB_mod, to be made public there) and the routine that consumes them
+   use dtB_mod, only: BtVrLM, BpVrLM, BrVtLM, BrVpLM, BtVpLM, BpVtLM, BpVtBtVpCotLM, BpVtBtVpSn2LM, BrVZLM, BtVZLM,   &
+       &              BtVZsn2LM, get_dH_dtBLM
    use outPar_mod, only: EperpASr, EparASr, EperpaxiASr, EparaxiASr, fkinASr, fconvASr, fviscASr, fresASr,  &
        &                 fpoynASr, uhASr, duhASr, gradT2ASr
    use num_param, only: delxr2, delxh2
@@ -221,6 +224,7 @@ contains
       integer :: ist, mask, nR
       logical :: l_diag
       real(c_double), allocatable :: dg(:,:)
+      complex(c_double_complex), allocatable :: dtb(:,:,:)
 
       !-- Log steps: get_helicity, get_hemi, get_visc_heat, get_perpPar, get_fluxes and get_nlBLayers (rIter.f90:320-367) are
       !   evaluated on the device after the batched loop (diagnostics_on_device below).  The remaining output hooks keep the
@@ -250,7 +254,7 @@ contains
       !   this call (step_time.f90:485, :612) are part of it (mpi_transp_cuda_mod); the explicit terms go into the slice
       !   tscheme%istage of the time-array containers, which is where transp_Rloc_to_LMloc would put them (step_time.f90:1134-1245)
       l_diag = lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lHemiCalc
-      if ( l_fused_lm .and. n_pending > 0 .and. .not. ( l_b_nl_cmb .or. l_b_nl_icb .or. l_diag ) ) then
+      if ( l_fused_lm .and. n_pending > 0 .and. .not. ( l_b_nl_cmb .or. l_b_nl_icb .or. l_diag .or. l_dtB ) ) then
          ist = tscheme%istage
          lin  = magic_lm_in(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr)
          lout = magic_lm_out(c_null_ptr, c_null_ptr, c_null_ptr, addr_r(dtrkc), addr_r(dthkc), c_null_ptr)
@@ -332,6 +336,20 @@ contains
 
       !-- the phase field is not on this path (initialize aborts when it is switched on)
       dphidt(:,:) = zero
+
+      !-- rIter.f90:388-395, 442 with l_dtB: the eleven products of get_dtBLM and their analyses for all local levels as one
+      !   batch on the device; get_dH_dtBLM then combines them level by level as in the reference
+      if ( l_dtB ) then
+         allocate( dtb(lm_max,nRstart:nRstop,11) )
+         call magic_check( magic_rloop_dtb(this%rl, fin, dtb), 'magic_rloop_dtb' )
+         do nR=nRstart,nRstop
+            BtVrLM(:)=dtb(:,nR,1);  BpVrLM(:)=dtb(:,nR,2);  BrVtLM(:)=dtb(:,nR,3);  BrVpLM(:)=dtb(:,nR,4)
+            BtVpLM(:)=dtb(:,nR,5);  BpVtLM(:)=dtb(:,nR,6);  BpVtBtVpCotLM(:)=dtb(:,nR,7);  BpVtBtVpSn2LM(:)=dtb(:,nR,8)
+            BrVZLM(:)=dtb(:,nR,9);  BtVZLM(:)=dtb(:,nR,10);  BtVZsn2LM(:)=dtb(:,nR,11)
+            call get_dH_dtBLM(nR)
+         end do
+         deallocate( dtb )
+      end if
 
       !-- rIter.f90:320-367 on log steps: one call returns the per-level sums of all requested routines; they go where the
       !   reference's routines store them (the arrays below are module variables of outMisc_mod, power and outPar_mod, to be

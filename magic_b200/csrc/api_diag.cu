@@ -203,3 +203,124 @@ extern "C" int magic_rloop_graph_fields(magic_rloop *rl, const magic_fields_in *
     }
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// get_dtBLM (rIter.f90:392-395, dtB.f90:144-223): with l_dtB the reference forms eleven grid products of
+// (vr, vt, vp, br, bt, bp) on every level and analyses them (2 spat_to_sphertor + 7 scal_to_SH, lcut = l_max).  Here: one more
+// column program on the batched pipeline -- 6 synthesised fields, dtb_product_kernel, 11 analysed fields -- so the extra
+// transforms ride on the Legendre GEMM / FFT kernels of the hot path.  out: HOST complex [11][n_r_loc][lm_max] in the order
+// BtVrLM, BpVrLM, BrVtLM, BrVpLM, BtVpLM, BpVtLM, BpVtBtVpCotLM, BpVtBtVpSn2LM, BrVZLM, BtVZLM, BtVZsn2LM.
+struct DtbPipe {
+    int chunk = 0, gx = 0;
+    BatchSpec spec;
+    Layout lay;
+    Buffers buf;
+    LevelInfo *d_lev_an = nullptr;  // lcut = l_max for the analysis (dtB.f90:210-221)
+    double *d_means = nullptr;
+    double *d_src[S_COUNT] = {nullptr};
+};
+
+static void dtb_free(DtbPipe *d) {
+    if (!d) return;
+    layout_free(d->lay);
+    buffers_free(d->buf);
+    cudaFree(d->d_lev_an); cudaFree(d->d_means);
+    for (int i = 0; i < S_COUNT; i++) cudaFree(d->d_src[i]);
+    delete d;
+}
+
+static int dtb_build(magic_rloop *rl) {
+    magic_sht *h = rl->h;
+    const magic_params &P = rl->p;
+    if (P.l_full_sphere) MFAIL("magic_rloop_dtb: full-sphere runs are not supported");
+    if (!(P.l_mag || P.l_mag_LF)) MFAIL("magic_rloop_dtb: needs a magnetic field");
+    DtbPipe *d = new DtbPipe();
+    rl->dtb = d;
+    BatchSpec &S = d->spec;
+    const Term N_ = {0, F_NONE};
+    int nf = 0, f0, f1, f2;
+    add_scal(S, Term{S_W, F_DLH}, N_, LM_VEL, nf, f0);
+    add_pair(S, Term{S_DW, F_ONE}, N_, Term{S_Z, F_ONE}, N_, LM_VEL, nf, f1, f2);
+    add_scal(S, Term{S_B, F_DLH}, N_, LM_ALL, nf, f0);
+    add_pair(S, Term{S_DB, F_ONE}, N_, Term{S_AJ, F_ONE}, N_, LM_ALL, nf, f1, f2);
+    S.nfield_in = nf;  // vr, vt, vp, br, bt, bp = grid fields 0..5
+    S.afield_vt = {0, 2};
+    S.afield_vp = {1, 3};
+    S.afield_s = {4, 5, 6, 7, 8, 9, 10};
+    S.nfield_out = 11;
+    size_t free_b = 0, total_b = 0;
+    MCHECK(cudaMemGetInfo(&free_b, &total_b));
+    const double per_level = 2.2 * 8.0 * (double)h->n_theta * h->n_phi * (6 + 11) + 64.0 * h->lm_max * 17;
+    int chunk = (int)std::min<double>(32.0, 0.5 * (double)free_b / per_level);
+    chunk = std::max(1, std::min(chunk, rl->n_r_loc));
+    d->chunk = chunk;
+    layout_sizes(h, S, chunk, d->lay);
+    if (buffers_alloc(h, S, d->lay, d->buf)) return 1;
+    if (layout_bind(h, S, d->lay, d->buf)) return 1;
+    std::vector<LevelInfo> lev = rl->lev;
+    for (auto &L : lev) L.lcut = h->l_max;
+    if (dev_upload_vec(&d->d_lev_an, lev)) return 1;
+    const size_t plane = (size_t)h->nh * h->n_phi;
+    d->gx = (int)std::min<size_t>((plane + DIAG_THREADS - 1) / DIAG_THREADS, 8 * 148);
+    MCHECK(cudaMalloc((void **)&d->d_means, sizeof(double) * DIAG_NMEAN * chunk * 2 * h->nh));
+    return 0;
+}
+
+static int dtb_run(magic_rloop *rl, const magic_fields_in *in, double *out, bool host_in) {
+    if (!rl || !in || !out) MFAIL("magic_rloop_dtb: null argument");
+    magic_sht *h = rl->h;
+    MCHECK(cudaSetDevice(h->dev));
+    if (!rl->dtb)
+        if (dtb_build(rl)) return 1;
+    DtbPipe *d = rl->dtb;
+    const magic_params &P = rl->p;
+    const double *ip[S_COUNT];
+    in_ptrs(in, ip);
+    const int needed[6] = {S_W, S_DW, S_Z, S_B, S_DB, S_AJ};
+    for (int i : needed)
+        if (!ip[i]) MFAIL("magic_rloop_dtb: w, dw, z, b, db, aj are needed");
+    const size_t lm2 = 2 * (size_t)h->lm_max;
+    const int nl = d->chunk, n_r = rl->n_r_loc;
+    if (host_in)
+        for (int i : needed)
+            if (!d->d_src[i]) MCHECK(cudaMalloc((void **)&d->d_src[i], sizeof(double) * lm2 * nl));
+    DiagArgs ma{};   // phi mean of vp through the diagnostics' mean kernel
+    ma.gin = d->buf.gin; ma.n_lev = nl; ma.nh = h->nh; ma.n_phi = h->n_phi;
+    for (int i = 0; i < DIAG_NMEAN; i++) ma.mean_field[i] = -1;
+    ma.mean_field[0] = 2;
+    ma.means = d->d_means;
+    DtbArgs a{};
+    a.gin = d->buf.gin; a.gout = d->buf.gout; a.n_lev = nl; a.nh = h->nh; a.n_phi = h->n_phi;
+    a.omega_ma = P.omega_ma; a.omega_ic = P.omega_ic; a.r_cmb = P.r_cmb; a.r_icb = P.r_icb;
+    a.sinth = h->d_sinth; a.costh = h->d_costh; a.means = d->d_means;
+    for (int l0 = 0; l0 < n_r; l0 += nl) {
+        const int s0 = std::min(l0, n_r - nl);
+        const double *src[MAGIC_MAX_SRC];
+        for (int i = 0; i < MAGIC_MAX_SRC; i++) src[i] = nullptr;
+        for (int i : needed) {
+            if (host_in) {
+                MCHECK(cudaMemcpyAsync(d->d_src[i], ip[i] + (size_t)s0 * lm2, sizeof(double) * lm2 * nl, cudaMemcpyHostToDevice, h->stream));
+                src[i] = d->d_src[i];
+            } else {
+                src[i] = ip[i] + (size_t)s0 * lm2;
+            }
+        }
+        if (run_synthesis(h, d->spec, d->lay, d->buf, src, rl->d_lev + s0, nullptr)) return 1;
+        a.lev = rl->d_lev + s0;
+        const size_t nrow = (size_t)DIAG_NMEAN * nl * 2 * h->nh;
+        diag_mean_kernel<<<(unsigned)((nrow + DIAG_THREADS / 32 - 1) / (DIAG_THREADS / 32)), DIAG_THREADS, 0, h->stream>>>(ma);
+        dtb_product_kernel<<<dim3(d->gx, nl), DIAG_THREADS, 0, h->stream>>>(a);
+        h->launches += 2;
+        if (run_analysis(h, d->spec, d->lay, d->buf, d->d_lev_an + s0, nullptr, true)) return 1;
+        // nl_v: [S0, T0, S1, T1][nl][lm_max] -> out 0..3; nl_s: [7][nl][lm_max] -> out 4..10
+        for (int q = 0; q < 11; q++) {
+            const double *srcq = q < 4 ? d->buf.nl_v + (size_t)q * nl * lm2 : d->buf.nl_s + (size_t)(q - 4) * nl * lm2;
+            MCHECK(cudaMemcpyAsync(out + ((size_t)q * n_r + s0) * lm2, srcq, sizeof(double) * lm2 * nl, cudaMemcpyDeviceToHost, h->stream));
+        }
+        MCHECK(cudaStreamSynchronize(h->stream));  // the staging buffers are reused by the next chunk
+    }
+    return 0;
+}
+
+extern "C" int magic_rloop_dtb(magic_rloop *rl, const magic_fields_in *in, double *out) { return dtb_run(rl, in, out, true); }
+extern "C" int magic_rloop_dtb_dev(magic_rloop *rl, const magic_fields_in *in, double *out) { return dtb_run(rl, in, out, false); }

@@ -230,3 +230,75 @@ __global__ void diag_finish_kernel(const double *partial, int n_part, int n_lev,
 }
 
 }  // namespace magic
+
+// ------------------------------------------------------------------------------------------------------
+// get_dtBLM (dtB.f90:144-223): the eleven grid products of the magnetic-field production diagnostics, written as the (N+S, N-S)
+// rows the r2c FFT expects (product field k of gout): BtVr, BpVr, BrVt, BrVp, BtVp, BpVt, BpVtBtVpCot, BpVtBtVpSn2, BrVZ, BtVZ,
+// BtVZsn2.  gin holds vr, vt, vp, br, bt, bp (fields 0..5); means[0] = phi mean of vp (E/O rows).
+namespace magic {
+
+struct DtbArgs {
+    const double *gin;
+    double *gout;
+    int n_lev, nh, n_phi;
+    double omega_ma, omega_ic, r_cmb, r_icb;
+    const LevelInfo *lev;
+    const double *sinth, *costh;
+    const double *means;  // [n_lev][2][nh]
+};
+
+__global__ void __launch_bounds__(DIAG_THREADS) dtb_product_kernel(DtbArgs a) {
+    const int lev = blockIdx.y;
+    const LevelInfo L = a.lev[lev];
+    const size_t plane = (size_t)a.nh * a.n_phi;
+    for (unsigned pt = blockIdx.x * blockDim.x + threadIdx.x; pt < (unsigned)plane; pt += gridDim.x * blockDim.x) {
+        const int k = (int)(pt / (unsigned)a.n_phi);
+        const double st = a.sinth[k], ct = a.costh[k];
+        double n[6], s[6];
+#pragma unroll
+        for (int f = 0; f < 6; f++) {
+            const double *base = a.gin + (((size_t)f * a.n_lev + lev) * 2) * plane + pt;
+            const double e = __ldg(base), o = __ldg(base + plane);
+            n[f] = e + o;
+            s[f] = e - o;
+        }
+        const double me = a.means[((size_t)lev * 2 + 0) * a.nh + k], mo = a.means[((size_t)lev * 2 + 1) * a.nh + k];
+        double vpn = me + mo, vps = me - mo;
+        if (L.nBc == 1) { n[0] = 0.0; s[0] = 0.0; }
+        if (L.nBc == 2) {  // v_rigid_boundary, nonlinear_bcs.f90:120-175
+            const double r2 = (L.nR == 1) ? a.r_cmb * a.r_cmb : a.r_icb * a.r_icb;
+            const double om = (L.nR == 1) ? a.omega_ma : a.omega_ic;
+            n[0] = s[0] = 0.0; n[1] = s[1] = 0.0;
+            n[2] = s[2] = vpn = vps = r2 * L.rho0 * (st * st) * om;
+        }
+        const double fac = 1.0 / (st * st), cot = ct / st / st / st, orho1 = L.orho1;
+        const double vpASn = orho1 * vpn, vpASs = orho1 * vps;
+        double pn[11], ps[11];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const double *v = h == 0 ? n : s;
+            double *p = h == 0 ? pn : ps;
+            const double fc = h == 0 ? cot : -cot, vz = h == 0 ? vpASn : vpASs;
+            const double vr = v[0], vt = v[1], vp = v[2], br = v[3], bt = v[4], bp = v[5];
+            p[0] = orho1 * bt * vr;
+            p[1] = orho1 * bp * vr;
+            p[2] = orho1 * vt * br;
+            p[3] = orho1 * vp * br;
+            p[4] = fac * orho1 * bt * vp;
+            p[5] = fac * orho1 * bp * vt;
+            p[6] = fc * orho1 * (bp * vt + bt * vp);
+            p[7] = fac * fac * orho1 * (bp * vt + bt * vp);
+            p[8] = fac * br * vz;
+            p[9] = fac * bt * vz;
+            p[10] = fac * fac * bt * vz;
+        }
+#pragma unroll
+        for (int q = 0; q < 11; q++) {
+            double *base = a.gout + (((size_t)q * a.n_lev + lev) * 2) * plane + pt;
+            base[0] = pn[q] + ps[q];
+            base[plane] = pn[q] - ps[q];
+        }
+    }
+}
+
+}  // namespace magic

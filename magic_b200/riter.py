@@ -150,6 +150,15 @@ class RadialLoop:
         check(fn(self._h, byref(fin), c_int(mask), c_int(ktops), c_int(kbots), out.ctypes.data_as(c_void_p)))
         return out
 
+    def dtb(self, fields, device=False):
+        """get_dtBLM (dtB.f90:144-223) for this rank's levels: complex128 [11, n_r_loc, lm_max] (BtVrLM, BpVrLM, BrVtLM, BrVpLM,
+        BtVpLM, BpVtLM, BpVtBtVpCotLM, BpVtBtVpSn2LM, BrVZLM, BtVZLM, BtVZsn2LM)."""
+        fin, _, keep = self._structs(fields, {}, 0 if device else np.zeros(1), 0 if device else np.zeros(1), device=device)
+        out = np.zeros((11, self.n_r_loc, self.sht.lm_max), dtype=np.complex128)
+        fn = self.lib.magic_rloop_dtb_dev if device else self.lib.magic_rloop_dtb
+        check(fn(self._h, byref(fin), out.ctypes.data_as(c_void_p)))
+        return out
+
     def graph_fields(self, fields, level, mag=False, pressure=False):
         """The grid fields graphOut_mpi reads (rIter.f90:303-314) for local level `level`: dict of float64
         [n_phi, nlat_padded] arrays (Fortran f(nlat_padded, n_phi))."""

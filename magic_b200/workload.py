@@ -86,6 +86,23 @@ def make_radial(n_r_max, l_max, nRstart=1, nRstop=None, l_R=None, anel=False):
     return {k: np.ascontiguousarray(v[sl]) for k, v in full.items()}
 
 
+def cheb_matrices(n_r_max, r_icb=7.0 / 13.0, r_cmb=20.0 / 13.0):
+    """First and second derivative collocation matrices on the Gauss-Lobatto radii of make_radial (nR = 1 is the CMB): what
+    get_dr / get_ddr (radial_derivatives.f90:714-912) compute on this grid, as the dense matrices
+    magic_rloop_set_radial_matrices takes."""
+    N = n_r_max - 1
+    x = np.cos(np.pi * np.arange(n_r_max) / N)
+    c = np.ones(n_r_max)
+    c[0] = c[-1] = 2.0
+    c *= (-1.0) ** np.arange(n_r_max)
+    X = np.tile(x, (n_r_max, 1)).T
+    dX = X - X.T
+    D = np.outer(c, 1.0 / c) / (dX + np.eye(n_r_max))
+    D -= np.diag(D.sum(axis=1))
+    D *= 2.0 / (r_cmb - r_icb)
+    return D, D @ D
+
+
 FIELD_SETS = {
     "mhd": ["w", "dw", "ddw", "z", "dz", "s", "b", "db", "ddb", "aj", "dj"],
     "hydro": ["w", "dw", "ddw", "z", "dz", "s"],

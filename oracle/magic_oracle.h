@@ -191,6 +191,10 @@ void orc_radial_loop(const orc_ctx *c, const orc_params *p, const orc_radial *ra
 void orc_radial_diagnostics(const orc_ctx *c, const orc_params *p, const orc_radial *rad, int n_r, const orc_fields_in *in,
                             int mask, int ktops, int kbots, double *out);
 
+/* get_dtBLM (dtB.f90:144-223) for n_r levels: out[11][n_r][lm_max] = BtVrLM, BpVrLM, BrVtLM, BrVpLM, BtVpLM, BpVtLM,
+ * BpVtBtVpCotLM, BpVtBtVpSn2LM, BrVZLM, BtVZLM, BtVZsn2LM. */
+void orc_radial_dtB(const orc_ctx *c, const orc_params *p, const orc_radial *rad, int n_r, const orc_fields_in *in, orc_cplx *out);
+
 /* get_nl only, on caller-provided grids (get_nl.f90:213-441): in/out arrays are [nphi][nlat] each.
  * in: vr vt vp cvr cvt cvp s br bt bp cbr cbt cbp (13) ; out: Advr Advt Advp LFr LFt LFp VSr VSt VSp
  * VxBr VxBt VxBp (12).  Provided so tests can check the grid-space kernel in isolation. */

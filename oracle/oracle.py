@@ -332,6 +332,31 @@ class Oracle:
                                         c_int(kbots), _p(out))
         return out
 
+    def radial_dtB(self, params, radial, fields):
+        """get_dtBLM (dtB.f90:144-223) for the levels in `radial`: complex128 [11, n_r, lm_max] (BtVrLM, BpVrLM, BrVtLM, BrVpLM,
+        BtVpLM, BpVtLM, BpVtBtVpCotLM, BpVtBtVpSn2LM, BrVZLM, BtVZLM, BtVZsn2LM)."""
+        n_r = len(radial["nR"])
+        keep = []
+        rad = _Radial()
+        for nm in ["nR", "l_R"]:
+            a = np.ascontiguousarray(radial[nm], dtype=np.int32)
+            keep.append(a)
+            setattr(rad, nm, _p(a))
+        for nm in _RAD_NAMES:
+            key = "lambda" if nm == "lambda_" else nm
+            a = np.ascontiguousarray(radial.get(key, np.ones(n_r)), dtype=np.float64)
+            keep.append(a)
+            setattr(rad, nm, _p(a))
+        fin = _FieldsIn()
+        for nm in _IN_NAMES:
+            if nm in fields and fields[nm] is not None:
+                a = self._c(fields[nm])
+                keep.append(a)
+                setattr(fin, nm, _p(a))
+        out = np.zeros((11, n_r, self.lm_max), dtype=np.complex128)
+        self.lib.orc_radial_dtB(self.h, C.byref(params), C.byref(rad), c_int(n_r), C.byref(fin), _p(out))
+        return out
+
     def get_nl_mhd(self, params, nR, nBc, or2, or4, orho1, grids_in):
         """get_nl.f90:213-441 on 13 caller grids -> 12 product grids."""
         ins = [self._r(g) for g in grids_in]

@@ -146,6 +146,55 @@ def test_gpu_diagnostics_device_pointers_and_level_chunks():
     s.finalize_sht()
 
 
+def test_oracle_dtB_products_against_the_per_call_transforms():
+    """orc_radial_dtB (get_dtBLM, dtB.f90:144-223) on a bulk level against the same products formed in numpy from the oracle's
+    own syntheses and analysed with its per-call transforms."""
+    l_max, n_r = 12, 3
+    o = _oracle(l_max)
+    p, rad, f = _case("mhd", l_max, n_r, o.lm2l, o.lm2m, 21, anel=True)
+    out = o.radial_dtB(_oparams(p), rad, f)
+    i = 1
+    vr, vt, vp = o.torpol_to_spat(f["w"][i], f["dw"][i], f["z"][i], l_max)
+    br, bt, bp = o.torpol_to_spat(f["b"][i], f["db"][i], f["aj"][i], l_max)
+    n_t = len(o.theta_ord)             # N/S-interleaved colatitudes of the grid rows (row 2k = k-th northern node, 2k+1 its mirror)
+    theta = np.empty(n_t)
+    theta[0::2], theta[1::2] = o.theta_ord[:n_t // 2], o.theta_ord[::-1][:n_t // 2]
+    os2, cot = 1.0 / np.sin(theta) ** 2, np.cos(theta) / np.sin(theta) ** 3
+    rho = rad["orho1"][i]
+    vpAS = rho * vp.mean(axis=0)
+    s1, t1 = o.spat_to_sphertor(rho * bt * vr, rho * bp * vr, l_max)
+    s2, t2 = o.spat_to_sphertor(rho * vt * br, rho * vp * br, l_max)
+    want = [s1, t1, s2, t2, o.scal_to_SH(os2 * rho * bt * vp, l_max), o.scal_to_SH(os2 * rho * bp * vt, l_max),
+            o.scal_to_SH(cot * rho * (bp * vt + bt * vp), l_max), o.scal_to_SH(os2 ** 2 * rho * (bp * vt + bt * vp), l_max),
+            o.scal_to_SH(os2 * br * vpAS, l_max), o.scal_to_SH(os2 * bt * vpAS, l_max), o.scal_to_SH(os2 ** 2 * bt * vpAS, l_max)]
+    for q in range(11):
+        assert np.linalg.norm(out[q, i] - want[q]) < 1e-13 * np.linalg.norm(want[q]), q
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("l_max,n_r,ktopv,kbotv,anel,omega_ic", [(21, 6, 2, 2, False, 0.0), (16, 5, 1, 2, True, 2.5), (32, 40, 2, 1, False, 0.0)])
+def test_gpu_dtB_batch_against_the_oracle(l_max, n_r, ktopv, kbotv, anel, omega_ic):
+    """magic_rloop_dtb (get_dtBLM as one more batch on the Legendre / FFT kernels) against the oracle: rigid and
+    stress-free walls, a rotating inner core, an anelastic background, more levels than one chunk."""
+    from magic_b200 import RadialLoop, Sht
+    s = Sht(l_max)
+    o = _oracle(l_max)
+    p, rad, f = _case("mhd", l_max, n_r, s.lm2l, s.lm2m, 31 + l_max, ktopv, kbotv, anel)
+    if omega_ic:
+        p.omega_ic, p.l_rot_ic = omega_ic, 1
+    rl = RadialLoop(s, p, rad)
+    got = rl.dtb(f)
+    ref = o.radial_dtB(_oparams(p), rad, f)
+    names = ["BtVrLM", "BpVrLM", "BrVtLM", "BrVpLM", "BtVpLM", "BpVtLM", "BpVtBtVpCotLM", "BpVtBtVpSn2LM", "BrVZLM", "BtVZLM", "BtVZsn2LM"]
+    for q, nm in enumerate(names):
+        err = np.linalg.norm(got[q] - ref[q]) / np.linalg.norm(ref[q])
+        print(f"  dtB l{l_max} {nm}: rel_l2 {err:.2e}")
+        assert err < 1e-12, (nm, err)
+    assert np.array_equal(got, rl.dtb(f)), "dtB batch is not bitwise repeatable"
+    rl.finalize()
+    s.finalize_sht()
+
+
 @pytest.mark.gpu
 def test_gpu_graph_fields_are_the_per_call_transforms():
     from magic_b200 import RadialLoop, Sht
