@@ -90,6 +90,9 @@ typedef struct {
     double oek, po, prec_angle, dilution_fac, ra, opr;
     double omega_ma, omega_ic, r_cmb, r_icb;
     double courfac, alffac;
+    /* phase field (get_nl.f90:333-344; physical_parameters.f90 epsPhase, phaseDiffFac, penaltyFac, tmelt); appended in round 2 */
+    double epsPhase, phaseDiffFac, penaltyFac, tmelt;
+    int l_phase_field;
 } magic_params;
 
 /* radial_functions the loop reads, one entry per LOCAL level (radial.f90:283-307, num_param.f90:30-31). */
@@ -104,12 +107,14 @@ typedef struct {
  * NULL where the switch is off. */
 typedef struct {
     const double *w, *dw, *ddw, *z, *dz, *s, *ds, *p, *xi, *b, *db, *ddb, *aj, *dj;
+    const double *phi; /* phi_Rloc (l_phase_field) */
 } magic_fields_in;
 
 /* Outputs of radialLoop (rIter.f90:125-147), same layout; dtrkc/dthkc are [n_r_loc] reals. */
 typedef struct {
     double *dwdt, *dzdt, *dpdt, *dsdt, *dxidt, *dbdt, *djdt, *dVxVhLM, *dVxBhLM, *dVSrLM, *dVXirLM;
     double *dtrkc, *dthkc;
+    double *dphidt;    /* l_phase_field: scal_to_SH(phiTerms), rIter.f90:698 */
 } magic_fields_out;
 
 typedef struct magic_rloop magic_rloop;

@@ -24,6 +24,8 @@ module magic_b200_c
       real(c_double) :: oek, po, prec_angle, dilution_fac, ra, opr
       real(c_double) :: omega_ma, omega_ic, r_cmb, r_icb
       real(c_double) :: courfac, alffac
+      real(c_double) :: epsPhase, phaseDiffFac, penaltyFac, tmelt
+      integer(c_int) :: l_phase_field
    end type magic_params
 
    !-- magic_radial: radial functions, one entry per LOCAL level
@@ -36,11 +38,13 @@ module magic_b200_c
    !-- magic_fields_in / magic_fields_out: R-distributed containers (lm_max, nRstart:nRstop); c_null_ptr where unused
    type, bind(C) :: magic_fields_in
       type(c_ptr) :: w, dw, ddw, z, dz, s, ds, p, xi, b, db, ddb, aj, dj
+      type(c_ptr) :: phi
    end type magic_fields_in
 
    type, bind(C) :: magic_fields_out
       type(c_ptr) :: dwdt, dzdt, dpdt, dsdt, dxidt, dbdt, djdt, dVxVhLM, dVxBhLM, dVSrLM, dVXirLM
       type(c_ptr) :: dtrkc, dthkc
+      type(c_ptr) :: dphidt
    end type magic_fields_out
 
    !-- LM-distributed containers of magic_rloop_run_lm (fields.f90:211-268, dt_fieldsLast.f90:125-214)

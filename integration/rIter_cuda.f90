@@ -25,7 +25,7 @@ module rIter_cuda_mod
    use special, only: lGrenoble
    use physical_parameters, only: ktopv, kbotv, n_r_LCR, LFfac, CorFac, epsc, epscXi, opm, ViscHeatFac,     &
        &                          OhmLossFac, oek, po, prec_angle, dilution_fac, ra, opr, ktops, kbots,     &
-       &                          ThExpNb
+       &                          ThExpNb, epsPhase, phaseDiffFac, penaltyFac, tmelt
    use radial_functions, only: r, or1, or2, or4, orho1, orho2, beta, rho0, otemp1, temp0, visc, lambda,     &
        &                       epscProf, l_R, r_cmb, r_icb, alpha0
    !-- per-level sums of the in-loop diagnostics (module variables of the reference, to be made public there)
@@ -38,7 +38,7 @@ module rIter_cuda_mod
    use outPar_mod, only: EperpASr, EparASr, EperpaxiASr, EparaxiASr, fkinASr, fconvASr, fviscASr, fresASr,  &
        &                 fpoynASr, uhASr, duhASr, gradT2ASr
    use num_param, only: delxr2, delxh2
-   use fields, only: s_Rloc, ds_Rloc, z_Rloc, dz_Rloc, p_Rloc, b_Rloc, db_Rloc, ddb_Rloc, aj_Rloc, dj_Rloc, &
+   use fields, only: s_Rloc, ds_Rloc, z_Rloc, dz_Rloc, p_Rloc, b_Rloc, db_Rloc, ddb_Rloc, aj_Rloc, dj_Rloc, phi_Rloc, &
        &             w_Rloc, dw_Rloc, ddw_Rloc, xi_Rloc, omega_ic, omega_ma,                                &
        &             flow_LMloc_container, s_LMloc_container, field_LMloc_container, xi_LMloc_container
    use dt_fieldsLast, only: dflowdt_LMloc_container, dsdt_LMloc_container, dbdt_LMloc_container,            &
@@ -75,7 +75,7 @@ contains
 
       class(rIter_cuda_t) :: this
 
-      if ( l_phase_field .or. l_onset ) call abortRun('! rIter_cuda_t: phase field / onset mode are not on the GPU path')
+      if ( l_onset ) call abortRun('! rIter_cuda_t: onset mode is not on the GPU path')
       !-- get_lorentz_torque adds the imposed-field term b0r with lGrenoble (outRot.f90:465-478): not on the GPU path
       if ( lGrenoble ) call abortRun('! rIter_cuda_t: lGrenoble (imposed b0 in the Lorentz torque) is not on the GPU path')
       call this%single%initialize()
@@ -141,6 +141,8 @@ contains
       p%oek=oek; p%po=po; p%prec_angle=prec_angle; p%dilution_fac=dilution_fac; p%ra=ra; p%opr=opr
       p%omega_ma=omega_ma; p%omega_ic=omega_ic; p%r_cmb=r_cmb; p%r_icb=r_icb
       p%courfac=tscheme%courfac; p%alffac=tscheme%alffac
+      p%epsPhase=epsPhase; p%phaseDiffFac=phaseDiffFac; p%penaltyFac=penaltyFac; p%tmelt=tmelt
+      p%l_phase_field=l2i(l_phase_field)
 
       !-- level_chunk = 0: the library picks its level batch from the truncation and the field set (the same on every rank)
       call magic_check( magic_rloop_create(sht_h, p, rd, int(n_r_loc,c_int), 0_c_int, this%rl), 'magic_rloop_create' )
@@ -254,7 +256,7 @@ contains
       !   this call (step_time.f90:485, :612) are part of it (mpi_transp_cuda_mod); the explicit terms go into the slice
       !   tscheme%istage of the time-array containers, which is where transp_Rloc_to_LMloc would put them (step_time.f90:1134-1245)
       l_diag = lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lHemiCalc
-      if ( l_fused_lm .and. n_pending > 0 .and. .not. ( l_b_nl_cmb .or. l_b_nl_icb .or. l_diag .or. l_dtB ) ) then
+      if ( l_fused_lm .and. n_pending > 0 .and. .not. ( l_b_nl_cmb .or. l_b_nl_icb .or. l_diag .or. l_dtB .or. l_phase_field ) ) then
          ist = tscheme%istage
          lin  = magic_lm_in(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr)
          lout = magic_lm_out(c_null_ptr, c_null_ptr, c_null_ptr, addr_r(dtrkc), addr_r(dthkc), c_null_ptr)
@@ -283,7 +285,9 @@ contains
       !-- Inputs: the R-distributed containers of fields.f90:211-268, (lm_max, nRstart:nRstop) each; the library
       !   ignores the pointers of switched-off physics
       fin = magic_fields_in(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
-      &                     c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr)
+      &                     c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
+      &                     c_null_ptr)
+      if ( l_phase_field ) fin%phi = c_loc(phi_Rloc)
       if ( l_conv .or. l_mag_kin ) then
          fin%w = c_loc(w_Rloc);  fin%dw = c_loc(dw_Rloc);  fin%ddw = c_loc(ddw_Rloc)
          fin%z = c_loc(z_Rloc);  fin%dz = c_loc(dz_Rloc)
@@ -298,7 +302,8 @@ contains
       end if
 
       fout = magic_fields_out(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
-      &                       c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr)
+      &                       c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr)
+      if ( l_phase_field ) fout%dphidt = addr_z(dphidt)
       fout%dwdt = addr_z(dwdt);  fout%dzdt = addr_z(dzdt)
       if ( l_double_curl ) then
          fout%dVxVhLM = addr_z(dVxVhLM)
@@ -334,8 +339,7 @@ contains
          call magic_check( magic_rloop_get_br_v_bcs(this%rl, 1_c_int, br_vt_lm_icb, br_vp_lm_icb), 'get_br_v_bcs ICB' )
       end if
 
-      !-- the phase field is not on this path (initialize aborts when it is switched on)
-      dphidt(:,:) = zero
+      if ( .not. l_phase_field ) dphidt(:,:) = zero
 
       !-- rIter.f90:388-395, 442 with l_dtB: the eleven products of get_dtBLM and their analyses for all local levels as one
       !   batch on the device; get_dH_dtBLM then combines them level by level as in the reference

@@ -11,8 +11,8 @@
 
 using namespace magic;
 
-enum Src { S_W = 0, S_DW, S_DDW, S_Z, S_DZ, S_S, S_DS, S_P, S_XI, S_B, S_DB, S_DDB, S_AJ, S_DJ, S_COUNT };
-enum OutIdx { O_DWDT = 0, O_DZDT, O_DPDT, O_DSDT, O_DXIDT, O_DBDT, O_DJDT, O_DVXVH, O_DVXBH, O_DVSR, O_DVXIR, O_COUNT };
+enum Src { S_W = 0, S_DW, S_DDW, S_Z, S_DZ, S_S, S_DS, S_P, S_XI, S_B, S_DB, S_DDB, S_AJ, S_DJ, S_PHI, S_COUNT };
+enum OutIdx { O_DWDT = 0, O_DZDT, O_DPDT, O_DSDT, O_DXIDT, O_DBDT, O_DJDT, O_DVXVH, O_DVXBH, O_DVSR, O_DVXIR, O_DPHIDT, O_COUNT };
 
 struct magic_rloop {
     magic_sht *h = nullptr;
@@ -40,7 +40,7 @@ struct magic_rloop {
     std::vector<int> lay_sizes;
     int buf_levels = 0;          // number of levels the workspace `buf` was allocated for
     // nl_lm slots
-    int a_Advr = -1, a_VSr = -1, a_VxBr = -1, a_VXir = -1, a_heat = -1;  // scalar-class analysis columns
+    int a_Advr = -1, a_VSr = -1, a_VxBr = -1, a_VXir = -1, a_heat = -1, a_phi = -1;  // scalar-class analysis columns
     int a_Adv = -1, a_VS = -1, a_VxB = -1, a_VXi = -1;                    // vector pairs
     // resident device copies for the host-pointer entry point
     double *d_in[S_COUNT] = {nullptr};
@@ -271,6 +271,7 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
     if (P.l_conv || P.l_mag_kin) {
         if (P.l_heat) { add_scal(S, Term{S_S, F_ONE}, N_, LM_ALL, nf, gi.s); rl->need_in[S_S] = true; units_syn += 1; }
         if (P.l_chemical_conv) { add_scal(S, Term{S_XI, F_ONE}, N_, LM_ALL, nf, gi.xi); rl->need_in[S_XI] = true; units_syn += 1; }
+        if (P.l_phase_field) { add_scal(S, Term{S_PHI, F_ONE}, N_, LM_ALL, nf, gi.phi); rl->need_in[S_PHI] = true; units_syn += 1; }  // rIter.f90:509
         rl->need_in[S_W] = rl->need_in[S_DW] = rl->need_in[S_Z] = true;
         if (P.l_full_sphere) rl->need_in[S_DDW] = true;
         add_scal(S, Term{S_W, F_DLH}, N_, LM_VEL, nf, gi.vr);
@@ -320,6 +321,7 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
         if (P.l_anel) { go.heat = no++; rl->a_heat = (int)S.afield_s.size(); S.afield_s.push_back(go.heat); units_an += 1; }
     }
     if (P.l_chemical_conv) add_qst(go.VXir, go.VXit, go.VXip, rl->a_VXir, rl->a_VXi);
+    if (P.l_phase_field) { go.phiTerms = no++; rl->a_phi = (int)S.afield_s.size(); S.afield_s.push_back(go.phiTerms); units_an += 1; }  // rIter.f90:698
     if (P.l_mag_nl) add_qst(go.VxBr, go.VxBt, go.VxBp, rl->a_VxBr, rl->a_VxB);
     S.nfield_out = no;
     rl->legendre_flops = (units_syn + units_an) * 2.0 * (double)h->n_theta * (double)h->lm_max * (double)n_r_loc;
@@ -331,6 +333,7 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
     if (!P.l_double_curl) rl->need_out[O_DPDT] = true;
     if (P.l_heat) rl->need_out[O_DSDT] = rl->need_out[O_DVSR] = true;
     if (P.l_chemical_conv) rl->need_out[O_DXIDT] = rl->need_out[O_DVXIR] = true;
+    if (P.l_phase_field) rl->need_out[O_DPHIDT] = true;
     if (P.l_mag) rl->need_out[O_DBDT] = rl->need_out[O_DJDT] = rl->need_out[O_DVXBH] = true;
 
     // ---- chunking
@@ -378,13 +381,13 @@ extern "C" int magic_rloop_create(magic_sht *h, const magic_params *pp, const ma
 static const double *const *in_ptrs(const magic_fields_in *in, const double *tmp[S_COUNT]) {
     tmp[S_W] = in->w; tmp[S_DW] = in->dw; tmp[S_DDW] = in->ddw; tmp[S_Z] = in->z; tmp[S_DZ] = in->dz; tmp[S_S] = in->s;
     tmp[S_DS] = in->ds; tmp[S_P] = in->p; tmp[S_XI] = in->xi; tmp[S_B] = in->b; tmp[S_DB] = in->db; tmp[S_DDB] = in->ddb;
-    tmp[S_AJ] = in->aj; tmp[S_DJ] = in->dj;
+    tmp[S_AJ] = in->aj; tmp[S_DJ] = in->dj; tmp[S_PHI] = in->phi;
     return tmp;
 }
 static void out_ptrs(const magic_fields_out *o, double *tmp[O_COUNT]) {
     tmp[O_DWDT] = o->dwdt; tmp[O_DZDT] = o->dzdt; tmp[O_DPDT] = o->dpdt; tmp[O_DSDT] = o->dsdt; tmp[O_DXIDT] = o->dxidt;
     tmp[O_DBDT] = o->dbdt; tmp[O_DJDT] = o->djdt; tmp[O_DVXVH] = o->dVxVhLM; tmp[O_DVXBH] = o->dVxBhLM; tmp[O_DVSR] = o->dVSrLM;
-    tmp[O_DVXIR] = o->dVXirLM;
+    tmp[O_DVXIR] = o->dVXirLM; tmp[O_DPHIDT] = o->dphidt;
 }
 
 // ---- the chunk loop in three pieces: begin (checks, start event), chunk c (all kernels of one level chunk, queued on the
@@ -435,7 +438,8 @@ static int rloop_chunk(magic_rloop *rl, int c, const RunCtx &x) {
     F.l_conv_nl = P.l_conv_nl; F.l_heat_nl = P.l_heat_nl; F.l_mag_nl = P.l_mag_nl; F.l_mag_LF = P.l_mag_LF; F.l_mag = P.l_mag;
     F.l_mag_kin = P.l_mag_kin; F.l_adv_curl = P.l_adv_curl; F.l_anel = P.l_anel; F.l_chemical_conv = P.l_chemical_conv;
     F.l_precession = P.l_precession; F.l_centrifuge = P.l_centrifuge; F.l_cour_alf_damp = P.l_cour_alf_damp;
-    F.l_full_sphere = P.l_full_sphere; F.n_r_LCR = P.n_r_LCR;
+    F.l_full_sphere = P.l_full_sphere; F.n_r_LCR = P.n_r_LCR; F.l_phase_field = P.l_phase_field;
+    F.epsPhase = P.epsPhase; F.phaseDiffFac = P.phaseDiffFac; F.penaltyFac = P.penaltyFac; F.tmelt = P.tmelt;
     F.LFfac = P.LFfac; F.opm = P.opm; F.ViscHeatFac = P.ViscHeatFac; F.OhmLossFac = P.OhmLossFac; F.oek = P.oek; F.po = P.po;
     F.prec_angle = P.prec_angle; F.dilution_fac = P.dilution_fac; F.ra = P.ra; F.opr = P.opr; F.omega_ma = P.omega_ma;
     F.omega_ic = P.omega_ic; F.r_cmb = P.r_cmb; F.r_icb = P.r_icb; F.courfac = P.courfac; F.alffac = P.alffac; F.time = x.time;
@@ -447,7 +451,7 @@ static int rloop_chunk(magic_rloop *rl, int c, const RunCtx &x) {
     a.lm_max = h->lm_max; a.lm10 = 1; a.lm11 = (h->minc == 1 && h->m_max >= 1) ? h->lstart[1] : -1;
     int gx = (int)((plane + NL_THREADS - 1) / NL_THREADS);
     const bool mag = P.l_mag || P.l_mag_LF || P.l_mag_nl;
-    const bool extra = !P.l_adv_curl || P.l_anel || P.l_chemical_conv || P.l_precession || P.l_centrifuge;
+    const bool extra = !P.l_adv_curl || P.l_anel || P.l_chemical_conv || P.l_precession || P.l_centrifuge || P.l_phase_field;
     launch_get_nl(a, mag, extra, gx, nl, h->stream);
     courant_finish_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(rl->buf.courmax, d_lev, nl, x.dtrkc + l0, x.dthkc + l0,
                                                                   rl->d_tq_partial, gx, P.LFfac, rl->d_torque);
@@ -458,7 +462,7 @@ static int rloop_chunk(magic_rloop *rl, int c, const RunCtx &x) {
     TdArgs t{};
     t.f.l_conv = P.l_conv; t.f.l_mag = P.l_mag; t.f.l_heat = P.l_heat; t.f.l_conv_nl = P.l_conv_nl; t.f.l_mag_nl = P.l_mag_nl;
     t.f.l_mag_kin = P.l_mag_kin; t.f.l_anel = P.l_anel; t.f.l_corr = P.l_corr; t.f.l_double_curl = P.l_double_curl;
-    t.f.l_single_matrix = P.l_single_matrix; t.f.l_chemical_conv = P.l_chemical_conv; t.f.l_anelastic_liquid = P.l_anelastic_liquid;
+    t.f.l_single_matrix = P.l_single_matrix; t.f.l_chemical_conv = P.l_chemical_conv; t.f.l_anelastic_liquid = P.l_anelastic_liquid; t.f.l_phase_field = P.l_phase_field;
     t.f.CorFac = P.CorFac; t.f.epsc = P.epsc; t.f.epscXi = P.epscXi;
     t.n_lev = nl; t.lm_max = h->lm_max; t.l_max = h->l_max; t.minc = h->minc; t.lm2l = h->d_lm2l; t.lm2m = h->d_lm2m; t.lev = d_lev;
     // tile slots of the nonlinear_lm_t members inside the fused kernel: scalar-class columns first, then vector columns
@@ -471,10 +475,11 @@ static int rloop_chunk(magic_rloop *rl, int c, const RunCtx &x) {
     sl.s[6] = nv(rl->a_VS, 0); sl.s[7] = ns(rl->a_VSr);
     sl.s[8] = nv(rl->a_VXi, 0); sl.s[9] = ns(rl->a_VXir);
     sl.s[10] = ns(rl->a_heat);
+    sl.s[11] = ns(rl->a_phi);
     t.w = src[S_W]; t.dw = src[S_DW]; t.ddw = src[S_DDW]; t.z = src[S_Z]; t.dz = src[S_DZ];
     auto o = [&](int i) -> double * { return x.op[i] ? x.op[i] + (size_t)l0 * lm2 : nullptr; };
     t.dwdt = o(O_DWDT); t.dzdt = o(O_DZDT); t.dpdt = o(O_DPDT); t.dsdt = o(O_DSDT); t.dxidt = o(O_DXIDT); t.dbdt = o(O_DBDT);
-    t.djdt = o(O_DJDT); t.dVxVhLM = o(O_DVXVH); t.dVxBhLM = o(O_DVXBH); t.dVSrLM = o(O_DVSR); t.dVXirLM = o(O_DVXIR);
+    t.djdt = o(O_DJDT); t.dVxVhLM = o(O_DVXVH); t.dVxBhLM = o(O_DVXBH); t.dVSrLM = o(O_DVSR); t.dVXirLM = o(O_DVXIR); t.dphidt = o(O_DPHIDT);
     {
         ExtractArgs e = make_extract_args(h, L, rl->buf, d_lev);
         e.out_s = nullptr; e.out_v = nullptr;
@@ -583,7 +588,7 @@ extern "C" int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const
         MCHECK(cudaEventRecord(rl->up_done[c], rl->s_up));
     }
     din.w = dip[S_W]; din.dw = dip[S_DW]; din.ddw = dip[S_DDW]; din.z = dip[S_Z]; din.dz = dip[S_DZ]; din.s = dip[S_S]; din.ds = dip[S_DS];
-    din.p = dip[S_P]; din.xi = dip[S_XI]; din.b = dip[S_B]; din.db = dip[S_DB]; din.ddb = dip[S_DDB]; din.aj = dip[S_AJ]; din.dj = dip[S_DJ];
+    din.p = dip[S_P]; din.xi = dip[S_XI]; din.b = dip[S_B]; din.db = dip[S_DB]; din.ddb = dip[S_DDB]; din.aj = dip[S_AJ]; din.dj = dip[S_DJ]; din.phi = dip[S_PHI];
     double *dop[O_COUNT] = {nullptr};
     for (int i = 0; i < O_COUNT; i++) {
         if (!rl->need_out[i]) continue;
@@ -597,7 +602,7 @@ extern "C" int magic_rloop_run(magic_rloop *rl, const magic_fields_in *in, const
     }
     dout.dwdt = dop[O_DWDT]; dout.dzdt = dop[O_DZDT]; dout.dpdt = dop[O_DPDT]; dout.dsdt = dop[O_DSDT]; dout.dxidt = dop[O_DXIDT];
     dout.dbdt = dop[O_DBDT]; dout.djdt = dop[O_DJDT]; dout.dVxVhLM = dop[O_DVXVH]; dout.dVxBhLM = dop[O_DVXBH];
-    dout.dVSrLM = dop[O_DVSR]; dout.dVXirLM = dop[O_DVXIR];
+    dout.dVSrLM = dop[O_DVSR]; dout.dVXirLM = dop[O_DVXIR]; dout.dphidt = dop[O_DPHIDT];
     dout.dtrkc = rl->d_dtrkc; dout.dthkc = rl->d_dthkc;
     rl->pipelined = true;
     int rc = magic_rloop_run_dev(rl, &din, &dout, time);
@@ -863,6 +868,7 @@ static int lm_run(magic_rloop *rl, magic_transp *t, const double *const lm_in[4]
         if (lmpipe_build(rl, t)) return 1;
     LmPipe *p = rl->lmpipe;
     const magic_params &P = rl->p;
+    if (P.l_phase_field) MFAIL("magic_rloop_run_lm: the phase field has no LM-distributed container here; use the R-distributed calls");
     for (int k = 0; k < 4; k++) {
         if (p->nf_in[k] && !lm_in[k]) MFAIL("magic_rloop_run_lm: a required inbound container is null");
         if (p->nf_out[k] && !lm_out[k]) MFAIL("magic_rloop_run_lm: a required outbound container is null");

@@ -11,15 +11,15 @@
 namespace magic {
 
 // index of each synthesised field inside the synthesis grid array (-1 = absent)
-struct GridIn { int vr, vt, vp, cvr, cvt, cvp, s, br, bt, bp, cbr, cbt, cbp, xi, dvrdr, dvtdr, dvpdr, dvrdt, dvrdp, dvtdp, dvpdp; };  // same order as PointIn
+struct GridIn { int vr, vt, vp, cvr, cvt, cvp, s, br, bt, bp, cbr, cbt, cbp, xi, dvrdr, dvtdr, dvpdr, dvrdt, dvrdp, dvtdp, dvpdp, phi; };  // same order as PointIn
 // index of each product inside the product grid array (-1 = absent)
-struct GridOut { int Advr, Advt, Advp, VSr, VSt, VSp, VxBr, VxBt, VxBp, VXir, VXit, VXip, heat; };
+struct GridOut { int Advr, Advt, Advp, VSr, VSt, VSp, VxBr, VxBt, VxBp, VXir, VXit, VXip, heat, phiTerms; };
 
 struct NlFlags {
     int l_conv_nl, l_heat_nl, l_mag_nl, l_mag_LF, l_mag, l_mag_kin, l_adv_curl, l_anel, l_chemical_conv, l_precession,
-        l_centrifuge, l_cour_alf_damp, l_full_sphere, n_r_LCR;
+        l_centrifuge, l_cour_alf_damp, l_full_sphere, n_r_LCR, l_phase_field;
     double LFfac, opm, ViscHeatFac, OhmLossFac, oek, po, prec_angle, dilution_fac, ra, opr, omega_ma, omega_ic, r_cmb, r_icb,
-        courfac, alffac, time;
+        courfac, alffac, time, epsPhase, phaseDiffFac, penaltyFac, tmelt;
 };
 
 struct NlArgs {
@@ -42,8 +42,8 @@ __device__ __forceinline__ void atomic_max_pos(unsigned long long *addr, double 
     atomicMax(addr, (unsigned long long)__double_as_longlong(v));  // valid for v >= 0
 }
 
-struct PointIn { double vr, vt, vp, cvr, cvt, cvp, s, br, bt, bp, cbr, cbt, cbp, xi, dvrdr, dvtdr, dvpdr, dvrdt, dvrdp, dvtdp, dvpdp; };
-struct PointOut { double Advr, Advt, Advp, VSr, VSt, VSp, VxBr, VxBt, VxBp, VXir, VXit, VXip, heat; };
+struct PointIn { double vr, vt, vp, cvr, cvt, cvp, s, br, bt, bp, cbr, cbt, cbp, xi, dvrdr, dvtdr, dvpdr, dvrdt, dvrdp, dvtdp, dvpdp, phi; };
+struct PointOut { double Advr, Advt, Advp, VSr, VSt, VSp, VxBr, VxBt, VxBp, VXir, VXit, VXip, heat, phiTerms; };
 
 // get_nl.f90:213-441 at one grid point.  ct/cn2 carry the hemisphere sign.
 // MAG: magnetic fields present.  EXTRA: anything beyond the Boussinesq curl-form set (u.grad u advection, anelastic
@@ -72,6 +72,14 @@ __device__ __forceinline__ void nl_point(const NlFlags &F, const LevelInfo &L, c
             At = or4 * orho1 * (-p.vr * (p.dvtdr - beta * p.vt) + p.vt * (cn2 * p.vt + p.dvpdp + p.dvrdr) + p.vp * (cn2 * p.vp - p.dvtdp));
             Ap = or4 * orho1 * (-p.vr * (p.dvpdr - beta * p.vp) - p.vt * (p.dvtdp + p.cvr) - p.vp * p.dvpdp);
         }
+    }
+    o.phiTerms = 0;
+    if (EXTRA && F.l_phase_field && nBc == 0) {  // get_nl.f90:333-344: penalty on the velocity in the solid, phase-field source
+        const double pen = 1.0 / F.epsPhase / F.epsPhase / F.penaltyFac / F.penaltyFac;
+        Ar -= p.phi * p.vr * pen;
+        At -= or2 * p.phi * p.vt * pen;
+        Ap -= or2 * p.phi * p.vp * pen;
+        o.phiTerms = -1.0 / (F.epsPhase * F.epsPhase) * p.phi * (1.0 - p.phi) * (F.phaseDiffFac * (1.0 - 2.0 * p.phi) + p.s - F.tmelt);
     }
     // rIter.f90:646-667
     if (F.l_conv_nl && F.l_mag_LF) {
@@ -158,9 +166,9 @@ __global__ void __launch_bounds__(NL_THREADS, EXTRA ? 1 : 2) get_nl_kernel(NlArg
         // Phase 1: issue every load of this point pair before the first use (the warp scheduler is in-order, so a
         // load->use->load sequence would leave only two requests in flight per warp).  Slots follow PointIn.
         const int *fidx = &a.gi.vr;  // GridIn members are declared in PointIn order
-        double re[21], ro[21];
+        double re[22], ro[22];
 #pragma unroll
-        for (int f = 0; f < 21; f++) {
+        for (int f = 0; f < 22; f++) {
             const bool used = f < 7 || (f < 13 ? MAG : EXTRA);
             re[f] = 0.0;
             ro[f] = 0.0;
@@ -173,7 +181,7 @@ __global__ void __launch_bounds__(NL_THREADS, EXTRA ? 1 : 2) get_nl_kernel(NlArg
         PointIn pn, ps;
         double *pnv = &pn.vr, *psv = &ps.vr;
 #pragma unroll
-        for (int f = 0; f < 21; f++) {
+        for (int f = 0; f < 22; f++) {
             pnv[f] = re[f] + ro[f];
             psv[f] = re[f] - ro[f];
         }
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(NL_THREADS, EXTRA ? 1 : 2) get_nl_kernel(NlArg
             nl_point<MAG, EXTRA>(F, L, pn, st, ct, os2, cn2, phi, on);
             nl_point<MAG, EXTRA>(F, L, ps, st, -ct, os2, -cn2, phi, os);
         } else {
-            on = PointOut{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            on = PointOut{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             os = on;
         }
         auto stf = [&](int fidx, double n, double s) {
@@ -230,6 +238,7 @@ __global__ void __launch_bounds__(NL_THREADS, EXTRA ? 1 : 2) get_nl_kernel(NlArg
         if (EXTRA) {
             stf(a.go.VXir, on.VXir, os.VXir); stf(a.go.VXit, on.VXit, os.VXit); stf(a.go.VXip, on.VXip, os.VXip);
             stf(a.go.heat, on.heat, os.heat);
+            stf(a.go.phiTerms, on.phiTerms, os.phiTerms);
         }
         // courant.f90:209-275 (XSH_COURANT == 0)
         if (L.cour_on) {

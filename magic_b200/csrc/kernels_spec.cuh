@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(256) anal_extract_kernel(ExtractArgs a) {
 // get_td epilogue (get_td.f90:133-619) for one chunk of levels; thread per (lm, level).
 struct TdFlags {
     int l_conv, l_mag, l_heat, l_conv_nl, l_mag_nl, l_mag_kin, l_anel, l_corr, l_double_curl, l_single_matrix,
-        l_chemical_conv, l_anelastic_liquid;
+        l_chemical_conv, l_anelastic_liquid, l_phase_field;
     double CorFac, epsc, epscXi;
 };
 struct TdArgs {
@@ -335,11 +335,11 @@ struct TdArgs {
     const int *lm2l, *lm2m;
     const LevelInfo *lev;
     // nonlinear_lm_t members, each [n_lev][lm_max] complex or null
-    const double *AdvrLM, *AdvtLM, *AdvpLM, *VxBrLM, *VxBtLM, *VxBpLM, *VStLM, *VSrLM, *VXitLM, *VXirLM, *heatLM;
+    const double *AdvrLM, *AdvtLM, *AdvpLM, *VxBrLM, *VxBtLM, *VxBpLM, *VStLM, *VSrLM, *VXitLM, *VXirLM, *heatLM, *phiLM;
     // inputs (level-major, first level of the chunk)
     const double *w, *dw, *ddw, *z, *dz;
     // outputs
-    double *dwdt, *dzdt, *dpdt, *dsdt, *dxidt, *dbdt, *djdt, *dVxVhLM, *dVxBhLM, *dVSrLM, *dVXirLM;
+    double *dwdt, *dzdt, *dpdt, *dsdt, *dxidt, *dbdt, *djdt, *dVxVhLM, *dVxBhLM, *dVSrLM, *dVXirLM, *dphidt;
 };
 
 __device__ __forceinline__ double2 ldc(const double *p, size_t i) { return *reinterpret_cast<const double2 *>(p + 2 * i); }
@@ -489,6 +489,8 @@ __device__ __forceinline__ void td_compute(const TdArgs &a, int lm, int lev, siz
         }
         stc(a.dVSrLM, i, (bulk && !L.l_bound) ? ldc(a.VSrLM, inl) : zero);
     }
+    // rIter.f90:698: dphidt = scal_to_SH(phiTerms); get_nl fills phiTerms on bulk levels only (get_nl.f90:333)
+    if (F.l_phase_field && a.dphidt) stc(a.dphidt, i, bulk ? ldc(a.phiLM, inl) : zero);
     if (F.l_chemical_conv) {
         if (bulk) stc(a.dxidt, i, lm == 0 ? make_double2(F.epscXi, 0.0) : c_scale(dLh, ldc(a.VXitLM, inl)));
         stc(a.dVXirLM, i, (bulk && !L.l_bound) ? ldc(a.VXirLM, inl) : zero);
@@ -523,7 +525,7 @@ __global__ void __launch_bounds__(256) get_td_kernel(TdArgs a) {
 // analysis GEMM results with the level index fastest (contiguous in the C matrices) into a shared-memory tile; phase 2
 // runs get_td with the mode index fastest (contiguous in the spectral inputs/outputs).  The nonlinear_lm_t arrays never
 // touch HBM.
-struct TdSlots { int s[11]; };  // tile slot of AdvrLM,AdvtLM,AdvpLM,VxBrLM,VxBtLM,VxBpLM,VStLM,VSrLM,VXitLM,VXirLM,heatLM (-1 absent)
+struct TdSlots { int s[12]; };  // tile slot of AdvrLM,AdvtLM,AdvpLM,VxBrLM,VxBtLM,VxBpLM,VStLM,VSrLM,VXitLM,VXirLM,heatLM,phiLM (-1 absent)
 
 template <int TL>
 __global__ void __launch_bounds__(256) extract_td_kernel(ExtractArgs e, TdArgs t, TdSlots slots) {
@@ -551,9 +553,9 @@ __global__ void __launch_bounds__(256) extract_td_kernel(ExtractArgs e, TdArgs t
     }
     __syncthreads();
     const double *base = reinterpret_cast<const double *>(td_sm);
-    const double **ptrs[11] = {&t.AdvrLM, &t.AdvtLM, &t.AdvpLM, &t.VxBrLM, &t.VxBtLM, &t.VxBpLM, &t.VStLM, &t.VSrLM, &t.VXitLM, &t.VXirLM, &t.heatLM};
+    const double **ptrs[12] = {&t.AdvrLM, &t.AdvtLM, &t.AdvpLM, &t.VxBrLM, &t.VxBtLM, &t.VxBpLM, &t.VStLM, &t.VSrLM, &t.VXitLM, &t.VXirLM, &t.heatLM, &t.phiLM};
 #pragma unroll
-    for (int q = 0; q < 11; q++) *ptrs[q] = slots.s[q] < 0 ? nullptr : base + 2 * (size_t)slots.s[q] * n_lev * TLP;
+    for (int q = 0; q < 12; q++) *ptrs[q] = slots.s[q] < 0 ? nullptr : base + 2 * (size_t)slots.s[q] * n_lev * TLP;
     for (int idx = threadIdx.x; idx < TL * n_lev; idx += blockDim.x) {
         int ll = idx % TL, lev = idx / TL, lm = lm0 + ll;
         if (lm < e.lm_max) td_compute(t, lm, lev, (size_t)lev * TLP + ll);

@@ -20,8 +20,9 @@ class Params(C.Structure):
              "l_temperature_diff", "ktopv", "kbotv", "l_cond_ma", "l_cond_ic", "l_rot_ma", "l_rot_ic", "n_r_max",
              "n_r_LCR"]
     _dbls = ["LFfac", "CorFac", "epsc", "epscXi", "opm", "ViscHeatFac", "OhmLossFac", "oek", "po", "prec_angle",
-             "dilution_fac", "ra", "opr", "omega_ma", "omega_ic", "r_cmb", "r_icb", "courfac", "alffac"]
-    _fields_ = [(n, c_int) for n in _ints] + [(n, c_double) for n in _dbls]
+             "dilution_fac", "ra", "opr", "omega_ma", "omega_ic", "r_cmb", "r_icb", "courfac", "alffac",
+             "epsPhase", "phaseDiffFac", "penaltyFac", "tmelt"]
+    _fields_ = [(n, c_int) for n in _ints] + [(n, c_double) for n in _dbls] + [("l_phase_field", c_int)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -32,8 +33,8 @@ RADIAL_NAMES = ["r", "or1", "or2", "or4", "orho1", "orho2", "beta", "rho0", "ote
 # magic_rloop_diagnostics: mask bits and slots (include/magic_sht.h)
 DIAG_HEL, DIAG_HEMI, DIAG_POWER, DIAG_PERPPAR, DIAG_FLUX, DIAG_VISCBC, DIAG_RMSBULK = 1, 2, 4, 8, 16, 32, 256
 NDIAG = 32
-IN_NAMES = ["w", "dw", "ddw", "z", "dz", "s", "ds", "p", "xi", "b", "db", "ddb", "aj", "dj"]
-OUT_NAMES = ["dwdt", "dzdt", "dpdt", "dsdt", "dxidt", "dbdt", "djdt", "dVxVhLM", "dVxBhLM", "dVSrLM", "dVXirLM"]
+IN_NAMES = ["w", "dw", "ddw", "z", "dz", "s", "ds", "p", "xi", "b", "db", "ddb", "aj", "dj", "phi"]
+OUT_NAMES = ["dwdt", "dzdt", "dpdt", "dsdt", "dxidt", "dbdt", "djdt", "dVxVhLM", "dVxBhLM", "dVSrLM", "dVXirLM", "dphidt"]
 
 
 class _Radial(C.Structure):
@@ -45,7 +46,7 @@ class _FieldsIn(C.Structure):
 
 
 class _FieldsOut(C.Structure):
-    _fields_ = [(n, c_void_p) for n in OUT_NAMES] + [("dtrkc", c_void_p), ("dthkc", c_void_p)]
+    _fields_ = [(n, c_void_p) for n in OUT_NAMES[:11]] + [("dtrkc", c_void_p), ("dthkc", c_void_p), ("dphidt", c_void_p)]
 
 
 def level_chunks(n_r_loc, level_chunk):

@@ -154,6 +154,8 @@ typedef struct {
     double oek, po, prec_angle, dilution_fac, ra, opr;
     double omega_ma, omega_ic, r_cmb, r_icb;
     double courfac, alffac;
+    double epsPhase, phaseDiffFac, penaltyFac, tmelt; /* phase field, get_nl.f90:333-344 */
+    int l_phase_field;
 } orc_params;
 
 /* Radial functions for the n_r levels handed to the loop (all arrays length n_r). */
@@ -167,6 +169,7 @@ typedef struct {
 /* R-distributed spectral inputs [n_r][lm_max] (Fortran X_Rloc(lm, nR)); any may be NULL if unused. */
 typedef struct {
     const orc_cplx *w, *dw, *ddw, *z, *dz, *s, *ds, *p, *xi, *b, *db, *ddb, *aj, *dj;
+    const orc_cplx *phi; /* phase field (l_phase_field) */
 } orc_fields_in;
 
 /* Outputs of radialLoop (rIter.f90:125-147), [n_r][lm_max]; may be NULL when the switch is off. */
@@ -177,6 +180,7 @@ typedef struct {
     /* get_br_v_bcs products [lm_max] (rIter.f90:267-277, nonlinear_bcs.f90:24-74): written when the loop holds the CMB / ICB
      * level and the run has l_b_nl_cmb / l_b_nl_icb (Namelists.f90:713-729); may be NULL */
     orc_cplx *br_vt_lm_cmb, *br_vp_lm_cmb, *br_vt_lm_icb, *br_vp_lm_icb;
+    orc_cplx *dphidt; /* l_phase_field: scal_to_SH(phiTerms), rIter.f90:698 */
 } orc_fields_out;
 
 /* Executes the body of `do nR=nRstart,nRstop` (rIter.f90:190-444) for n_r levels, with all output

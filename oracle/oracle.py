@@ -36,13 +36,13 @@ class Params(C.Structure):
              "l_rot_ma", "l_rot_ic", "n_r_max", "n_r_LCR"]
     _dbls = ["LFfac", "CorFac", "epsc", "epscXi", "opm", "ViscHeatFac", "OhmLossFac", "oek", "po",
              "prec_angle", "dilution_fac", "ra", "opr", "omega_ma", "omega_ic", "r_cmb", "r_icb",
-             "courfac", "alffac"]
-    _fields_ = [(n, c_int) for n in _ints] + [(n, c_double) for n in _dbls]
+             "courfac", "alffac", "epsPhase", "phaseDiffFac", "penaltyFac", "tmelt"]
+    _fields_ = [(n, c_int) for n in _ints] + [(n, c_double) for n in _dbls] + [("l_phase_field", c_int)]
 
 
 _RAD_NAMES = ["r", "or1", "or2", "or4", "orho1", "orho2", "beta", "rho0", "otemp1", "temp0", "visc",
               "lambda_", "epscProf", "delxr2", "delxh2"]
-_IN_NAMES = ["w", "dw", "ddw", "z", "dz", "s", "ds", "p", "xi", "b", "db", "ddb", "aj", "dj"]
+_IN_NAMES = ["w", "dw", "ddw", "z", "dz", "s", "ds", "p", "xi", "b", "db", "ddb", "aj", "dj", "phi"]
 _OUT_NAMES = ["dwdt", "dzdt", "dpdt", "dsdt", "dxidt", "dbdt", "djdt", "dVxVhLM", "dVxBhLM", "dVSrLM",
               "dVXirLM"]
 
@@ -59,7 +59,7 @@ class _FieldsOut(C.Structure):
     _fields_ = [(n, c_void_p) for n in _OUT_NAMES] + [("dtrkc", c_void_p), ("dthkc", c_void_p),
                                                        ("lorentz_torque_ic", c_void_p), ("lorentz_torque_ma", c_void_p),
                                                        ("br_vt_lm_cmb", c_void_p), ("br_vp_lm_cmb", c_void_p),
-                                                       ("br_vt_lm_icb", c_void_p), ("br_vp_lm_icb", c_void_p)]
+                                                       ("br_vt_lm_icb", c_void_p), ("br_vp_lm_icb", c_void_p), ("dphidt", c_void_p)]
 
 
 def _load(fast):
@@ -300,6 +300,9 @@ class Oracle:
         for nm in ("br_vt_lm_cmb", "br_vp_lm_cmb", "br_vt_lm_icb", "br_vp_lm_icb"):  # get_br_v_bcs, rIter.f90:267-277
             out[nm] = np.zeros(self.lm_max, dtype=np.complex128)
             setattr(fout, nm, _p(out[nm]))
+        if getattr(params, "l_phase_field", 0):
+            out["dphidt"] = np.zeros((n_r, self.lm_max), dtype=np.complex128)
+            fout.dphidt = _p(out["dphidt"])
         self.lib.orc_radial_loop(self.h, C.byref(params), C.byref(rad), c_int(n_r), C.byref(fin), C.byref(fout),
                                  c_double(time))
         out["lorentz_torque_ic"], out["lorentz_torque_ma"] = float(tq[0]), float(tq[1])

@@ -197,3 +197,26 @@ def test_lo_map_is_a_balanced_permutation_and_transposes_invert(o16):
     lm_lo = 5
     p = int(np.searchsorted(e, lm_lo + 1))
     assert arr_R[q][1, 0, lo2st[lm_lo]] == arr_LM[p][1, rs[q] - 1, lm_lo - (s[p] - 1)]
+
+
+def test_phase_field_source_of_a_uniform_phase():
+    """get_nl.f90:340-343 / rIter.f90:698: for a uniform phase field phi = c0 (only the (0,0) mode), no flow and no entropy
+    perturbation, phiTerms is the constant -c0 (1 - c0) (phaseDiffFac (1 - 2 c0) - tmelt) / epsPhase^2 on bulk levels, so dphidt
+    has that value times sqrt(4 pi) in its (0,0) entry and nothing else; boundary levels are not written by get_nl."""
+    from magic_b200.workload import make_params, make_radial
+    from oracle.oracle import Oracle, Params
+    o, n_r = Oracle(8), 5
+    p = make_params("hydro", n_r)
+    op = Params()
+    for n, _ in p._fields_:
+        setattr(op, n, getattr(p, n))
+    op.l_phase_field, op.epsPhase, op.phaseDiffFac, op.penaltyFac, op.tmelt = 1, 0.03, 1.0, 0.5, 0.11
+    rad = make_radial(n_r, 8)
+    f = {k: np.zeros((n_r, o.lm_max), dtype=complex) for k in ("w", "dw", "ddw", "z", "dz", "s", "phi")}
+    c0 = 0.3
+    f["phi"][:, 0] = c0 * np.sqrt(4 * np.pi)
+    out = o.radial_loop(op, rad, f)
+    want = -c0 * (1 - c0) * (1.0 * (1 - 2 * c0) - 0.11) / 0.03 ** 2 * np.sqrt(4 * np.pi)
+    assert np.allclose(out["dphidt"][1:-1, 0], want, rtol=1e-13)
+    assert np.abs(out["dphidt"][1:-1, 1:]).max() < 1e-12 * abs(want)
+    assert not out["dphidt"][[0, -1]].any()

@@ -33,6 +33,9 @@ def run_both(l_max, n_r_max, physics, levels, level_chunk=0, ktopv=2, kbotv=2, m
     idx = np.array(levels) - 1
     rad = {k: np.ascontiguousarray(v[idx]) for k, v in rad_full.items()}
     fields = make_fields(physics, o.lm2l, o.lm2m, len(levels), seed)
+    if tweak and tweak.get("l_phase_field"):   # a phase field around 1/2 with structure at every degree
+        fields["phi"] = 0.05 * make_fields("hydro", o.lm2l, o.lm2m, len(levels), seed + 1)["w"]
+        fields["phi"][:, 0] = 0.5 * np.sqrt(4.0 * np.pi)
     rl = RadialLoop(s, p, rad, level_chunk=level_chunk)
     got = rl.radialLoop(fields)
     got["lorentz_torque_ic"], got["lorentz_torque_ma"] = rl.torques()
@@ -211,3 +214,21 @@ def test_conducting_rotating_walls_and_lorentz_torques():
     assert abs(got["lorentz_torque_ma"] / ref["lorentz_torque_ma"] - 1) < 1e-11
     # rotation rates can change from step to step
     assert np.linalg.norm(got["dVxBhLM"][0]) > 0  # moving wall drags field lines: non-zero boundary induction term
+
+
+def test_phase_field_branch():
+    """l_phase_field (get_nl.f90:333-344, rIter.f90:509,698): the phase field is synthesised, penalises the velocity in the
+    advection terms and yields dphidt = scal_to_SH(phiTerms) on bulk levels; Boussinesq hydro with stress-free walls."""
+    tw = dict(l_phase_field=1, epsPhase=0.03, phaseDiffFac=1.0, penaltyFac=0.5, tmelt=0.11)
+    o, p, rad, got, ref, ex = run_both(21, 17, "hydro", [1, 2, 3, 9, 16, 17], ktopv=1, kbotv=1, tweak=tw)
+    compare(o, p, rad, got, ref, ex, HYDRO_OUT + ["dphidt"])
+    o2, p2, rad2, got2, ref2, ex2 = run_both(21, 17, "hydro", [1, 2, 3, 9, 16, 17], ktopv=1, kbotv=1)
+    bulk = (rad["nR"] != 1) & (rad["nR"] != 17)
+    assert rel_l2(got["dwdt"][bulk], got2["dwdt"][bulk]) > 1e-3, "the penalty term is not seen"
+
+
+def test_phase_field_with_mhd_and_u_grad_u():
+    """The same branch next to the magnetic terms and the u.grad u advection form (EXTRA kernel variant with MAG)."""
+    tw = dict(l_phase_field=1, epsPhase=0.05, phaseDiffFac=2.0, penaltyFac=1.0, tmelt=0.3, l_adv_curl=0)
+    o, p, rad, got, ref, ex = run_both(16, 9, "mhd", list(range(1, 10)), tweak=tw)
+    compare(o, p, rad, got, ref, ex, MHD_OUT + ["dphidt"])
