@@ -253,7 +253,10 @@ __host__ __device__ constexpr int fft_last_radix(int H) {
     while (len / fft_pick_radix(len) > 1) len /= fft_pick_radix(len);
     return len;
 }
-__host__ __device__ constexpr int fft2_rows(int H) { return H >= 768 ? 2 : H >= 256 ? 4 : H >= 96 ? 8 : 16; }
+#ifndef MAGIC_FFT_R_BIG
+#define MAGIC_FFT_R_BIG 2
+#endif
+__host__ __device__ constexpr int fft2_rows(int H) { return H >= 768 ? MAGIC_FFT_R_BIG : H >= 256 ? 4 : H >= 96 ? 8 : 16; }
 __host__ __device__ constexpr int fft2_rowlen(int H) { return fft_pad(H) + ((fft_pad(H) % 8) == 4 ? 0 : (12 - fft_pad(H) % 8) % 8); }  // == 4 (mod 8): rows r, r+1 on complementary banks
 __host__ __device__ constexpr int fft2_threads(int H) {
     // one thread per paired first-pass item: R * ceil(NB1 / 2), rounded to warps, at most 256

@@ -44,7 +44,7 @@ def test_oracle_hemispheric_energies_obey_parseval():
     """get_hemi against the spectral energy: north + south of 1/2 int (vr^2/r^2 + (vt^2 + vp^2)/sin^2) dOmega (the grid fields
     are r^2 u_r and r sin(theta) u_h) equals 1/2 sum_lm (2 - delta_m0) [ l^2(l+1)^2/r^2 |w|^2 + l(l+1) (|dw|^2 + |z|^2) ] for
     an orthonormal basis."""
-    l_max, n_r = 12, 5
+    l_max, n_r = 16, 5
     o = _oracle(l_max)
     p, rad, f = _case("mhd", l_max, n_r, o.lm2l, o.lm2m, 3)
     d = o.radial_diagnostics(_oparams(p), rad, f, DIAG_HEMI | DIAG_RMSBULK)
@@ -149,7 +149,7 @@ def test_gpu_diagnostics_device_pointers_and_level_chunks():
 def test_oracle_dtB_products_against_the_per_call_transforms():
     """orc_radial_dtB (get_dtBLM, dtB.f90:144-223) on a bulk level against the same products formed in numpy from the oracle's
     own syntheses and analysed with its per-call transforms."""
-    l_max, n_r = 12, 3
+    l_max, n_r = 16, 3     # n_theta = 24: the reference's grids have n_theta % 4 == 0 (truncation.f90:137-152)
     o = _oracle(l_max)
     p, rad, f = _case("mhd", l_max, n_r, o.lm2l, o.lm2m, 21, anel=True)
     out = o.radial_dtB(_oparams(p), rad, f)

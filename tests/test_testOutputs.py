@@ -12,8 +12,8 @@ are radial integrals of what the radial loop sums on the grid at log steps (rIte
 
 With l_RMS on, lRmsCalc treats the boundary levels as bulk on log steps (rIter.f90:215): MAGIC_DIAG_RMSBULK.
 Host: oracle/lmloop.py ShellHost, which reproduces e_kin.TAG / e_mag_oc.TAG of this run as well (checked here first).  The
-diagnostics come from the CPU oracle (CPU test: rows 0 and 1) or from magic_rloop_diagnostics through the C ABI, with the CUDA
-radial loop in the time loop (GPU test: all 11 rows).  tests/golden/testOutputs_reference.npz holds the five series
+diagnostics come from magic_rloop_diagnostics through the C ABI with the CUDA radial loop in the time loop (GPU test: all 11 rows)
+and from the CPU oracle on the same fields (rows 1 and 5 there; row 0 in the CPU test, more with MAGIC_TESTOUTPUTS_CPU_ROWS).  tests/golden/testOutputs_reference.npz holds the five series
 (tests/golden/make_testOutputs_fixture.py).
 """
 import os
@@ -145,35 +145,47 @@ def _oparams(p):
     return op
 
 
-def test_oracle_diagnostics_reproduce_helicity_hemi_and_power(golden):
-    """CPU oracle: radial loop and diagnostics inside the reference's time loop, rows 0 and 1 (10 steps) of e_kin, e_mag_oc,
-    helicity, hemi and the viscous dissipation of power.TAG; then the negative controls -- with the non-axisymmetric helicity
-    fed the full fields, or a viscous heating without the density-gradient (beta) terms, the rows are missed."""
+def _oracle(golden, fast):
     from oracle.oracle import Oracle
     gs = _sizes(golden)
-    kw = dict(n_theta=gs["n_theta_max"], n_phi=gs["n_phi_max"], m_max=gs["m_max"])
-    o = Oracle(gs["l_max"], **kw)                                              # strict build: the diagnostics under test
-    o_fast = Oracle(gs["l_max"], threads=min(4, os.cpu_count() or 1), fast=True, **kw)   # -O3 build: drives the ten time steps
-    h, p, rad = _setup(golden, o.lm2l, o.lm2m)
-    op = _oparams(p)
-    h.radial_loop = lambda f: o_fast.radial_loop(op, rad, f)
-    diag = lambda f: o.radial_diagnostics(op, rad, f, MASK)
-    _check(golden, h, diag, 0)
-    _run(golden, h, diag, 1)
-    d = diag(h.fields_Rloc())
-    ref = golden["helicity"][1]
+    return Oracle(gs["l_max"], n_theta=gs["n_theta_max"], n_phi=gs["n_phi_max"], m_max=gs["m_max"], threads=min(4, os.cpu_count() or 1),
+                  fast=fast)
+
+
+def _negative_controls(golden, h, o, op, rad, row):
+    """With the non-axisymmetric helicity fed the full fields, or a viscous heating without the density-gradient (beta) terms,
+    the golden row is missed (the beta terms cancel in Hel itself)."""
+    d = o.radial_diagnostics(op, rad, h.fields_Rloc(), MASK)
+    ref = golden["helicity"][row]
     swapped = d.copy()
     swapped[:, 4:8] = d[:, 0:4]
     assert np.abs(helicity_row(h, swapped)[5:] / ref[5:] - 1.0).max() > 1e-3
-    nobeta = dict(rad, beta=0 * rad["beta"])   # the anelastic terms of the viscous heating are seen (they cancel in Hel)
-    d2 = o.radial_diagnostics(op, nobeta, h.fields_Rloc(), MASK)
-    assert abs(visc_diss(h, d2) / golden["power"][0][5] - 1.0) > 1e-4
+    d2 = o.radial_diagnostics(op, dict(rad, beta=0 * rad["beta"]), h.fields_Rloc(), MASK)
+    assert abs(visc_diss(h, d2) / golden["power"][row - 1][5] - 1.0) > 1e-4
+
+
+def test_oracle_diagnostics_on_the_start_fields(golden):
+    """CPU: row 0 (start fields: no flow, the imposed field) of e_kin, e_mag_oc, helicity and hemi with the oracle's diagnostics.
+    The later rows need ten time steps each at l_max = 85 (about a minute per row on four host cores), so the oracle's diagnostics
+    are pinned to them in the GPU leg below, where the CUDA loop does the stepping; MAGIC_TESTOUTPUTS_CPU_ROWS=1 runs the first
+    logged row here as well."""
+    o = _oracle(golden, fast=True)
+    h, p, rad = _setup(golden, o.lm2l, o.lm2m)
+    op = _oparams(p)
+    h.radial_loop = lambda f: o.radial_loop(op, rad, f)
+    diag = lambda f: o.radial_diagnostics(op, rad, f, MASK)
+    _check(golden, h, diag, 0)
+    rows = int(os.environ.get("MAGIC_TESTOUTPUTS_CPU_ROWS", "0"))
+    if rows:
+        _run(golden, h, diag, rows)
+        _negative_controls(golden, h, o, op, rad, rows)
 
 
 @pytest.mark.gpu
 def test_gpu_diagnostics_reproduce_helicity_hemi_and_power(golden):
     """magic_rloop_diagnostics (host field pointers, what rIter_cuda_t holds) with the CUDA radial loop in the time loop: all 11
-    logged rows (100 steps)."""
+    logged rows (100 steps).  On rows 1 and 5 the CPU oracle's diagnostics are evaluated on the same fields and held against the
+    same golden rows (the pin of oracle/magic_oracle_diag.inc), followed by the negative controls."""
     from magic_b200 import RadialLoop, Sht
     gs = _sizes(golden)
     s = Sht(gs["l_max"], m_max=gs["m_max"], n_theta_max=gs["n_theta_max"], n_phi_max=gs["n_phi_max"])
@@ -181,7 +193,17 @@ def test_gpu_diagnostics_reproduce_helicity_hemi_and_power(golden):
     rl = RadialLoop(s, p, rad)
     h.radial_loop = lambda f: rl.radialLoop(f)
     diag = lambda f: rl.diagnostics(f, MASK)
+    o = _oracle(golden, fast=False)
+    op = _oparams(p)
     _check(golden, h, diag, 0)
-    _run(golden, h, diag, len(golden["e_kin"]) - 1)
+    for row in range(1, len(golden["e_kin"])):
+        for _ in range(int(golden["n_log_step"])):
+            h.step()
+        d = _check(golden, h, diag, row)
+        if row in (1, 5):
+            d_orc = _check(golden, h, lambda f: o.radial_diagnostics(op, rad, f, MASK), row)
+            scale = np.abs(d_orc).max(axis=0) + 1e-300
+            assert (np.abs(d - d_orc).max(axis=0) / scale).max() < 1e-12
+    _negative_controls(golden, h, o, op, rad, len(golden["e_kin"]) - 1)
     rl.finalize()
     s.finalize_sht()
