@@ -274,9 +274,15 @@ def run_magic(args, gs):
         return a
 
     nf_dflow = 4 if double_curl else 3  # dflowdt container: dwdt, dzdt, dpdt (, dVxVhLM), dt_fieldsLast.f90:125-214
-    flow_R = rand_container(5, [True] * 5, 0)       # w, dw, ddw, z, dz
-    s_R = rand_container(2, [False, False], 1)      # s, ds
-    field_R = rand_container(5, [True] * 5, 2) if mag else None   # b, db, ddb, aj, dj
+    if gs.get("checkpoint"):   # a real saturated state instead of random spectra
+        from magic_b200.workload import checkpoint_containers
+        ck = checkpoint_containers(os.path.join(ROOT, gs["checkpoint"]), lm_max, n_r_max)
+        mine = slice(tr.nRstart - 1, tr.nRstop)
+        flow_R, s_R, field_R = (torch.from_numpy(np.ascontiguousarray(ck[k][:, mine])).to(dev) for k in ("flow", "s", "field"))
+    else:
+        flow_R = rand_container(5, [True] * 5, 0)       # w, dw, ddw, z, dz
+        s_R = rand_container(2, [False, False], 1)      # s, ds
+        field_R = rand_container(5, [True] * 5, 2) if mag else None   # b, db, ddb, aj, dj
     flow_LM, s_LM = calloc(5, n_r_max, nlm_loc), calloc(2, n_r_max, nlm_loc)
     field_LM = calloc(5, n_r_max, nlm_loc) if mag else None
     torch.cuda.synchronize()
@@ -522,7 +528,9 @@ def run_magic(args, gs):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic: torch.randn, one seeded stream per radial level (20261017+1000*config, level, container), "
+            "data": ("checkpoint: the saturated dynamo of samples/boussBenchSat/checkpoint_end.start (" + gs["checkpoint"] + "), radial "
+                     "derivatives by Chebyshev collocation") if gs.get("checkpoint") else
+                    "synthetic: torch.randn, one seeded stream per radial level (20261017+1000*config, level, container), "
                     "Re,Im~N(0,1)/(l+1), Im(m=0)=0; random-init, no checkpoint",
             "config": config_dict(args, gs, rl_chunk(rl, chunk)),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

@@ -132,6 +132,10 @@ __device__ __forceinline__ bool level_enabled(int lmask, const LevelInfo &L) {
 }
 
 constexpr int PREP_WARPS = 8;   // = levels per CTA
+#ifndef MAGIC_PREP_BATCH
+#define MAGIC_PREP_BATCH 4
+#endif
+constexpr int PREP_BATCH = MAGIC_PREP_BATCH;  // sources loaded per round of phase 1 (divides MAGIC_MAX_SRC)
 constexpr int PREP_LD = 35;     // staging tile: positions 0..33 = degrees l0-1 .. l0+32, odd stride against bank conflicts
 
 __device__ __forceinline__ double2 eval_terms(const Term *t, const double2 *xs /* staging tile of this level */, int pos, int src_stride,
@@ -180,11 +184,11 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) synth_prep_kernel(SynthPrepAr
             // all stall samples on the STS that waited for its own LDG, 2.3 TB/s).
             const size_t off = ok ? 2 * ((size_t)lev * a.lm_max + lm) : 0;
 #pragma unroll
-            for (int s0 = 0; s0 < MAGIC_MAX_SRC; s0 += 4) {
+            for (int s0 = 0; s0 < MAGIC_MAX_SRC; s0 += PREP_BATCH) {
                 if (s0 < a.nsrc) {
-                    double2 x[4];
+                    double2 x[PREP_BATCH];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
+                    for (int q = 0; q < PREP_BATCH; q++) {
                         const double *sp = a.src[s0 + q];
                         const bool have = (s0 + q < a.nsrc) && sp != nullptr && ok;
                         const double *p = have ? sp + off : a.clm;
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) synth_prep_kernel(SynthPrepAr
                         if (!have) x[q] = make_double2(0.0, 0.0);
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; q++)
+                    for (int q = 0; q < PREP_BATCH; q++)
                         if (s0 + q < a.nsrc) prep_sm[((s0 + q) * PREP_WARPS + warp) * PREP_LD + pos] = x[q];
                 }
             }
@@ -301,6 +305,27 @@ __device__ __forceinline__ void pair_combine(const ExtractArgs &e, const ModeRef
     S.y = (-r.dm * a0.x + (r.e * bu.y - r.f * bd.y)) / r.ll1;
     T.x = (-(r.e * au.x - r.f * ad.x) + r.dm * b0.y) / r.ll1;
     T.y = (-(r.e * au.y - r.f * ad.y) - r.dm * b0.x) / r.ll1;
+}
+
+// the same in two halves, so that a caller can issue the loads of several pairs before the first combination
+struct PairLoads { double2 a0, b0, au, bu, ad, bd; };
+__device__ __forceinline__ PairLoads pair_load(const ExtractArgs &e, const ModeRef &r, int i, bool on) {
+    const size_t cb = 2 * (size_t)(e.nf_s + 2 * i) * e.n_lev, ca = cb + 2 * (size_t)e.n_lev;
+    const double2 z = make_double2(0.0, 0.0);
+    PairLoads p;
+    p.a0 = on ? *reinterpret_cast<const double2 *>(r.own + ca) : z;
+    p.b0 = on ? *reinterpret_cast<const double2 *>(r.own + cb) : z;
+    p.au = on ? *reinterpret_cast<const double2 *>(r.up + ca) : z;
+    p.bu = on ? *reinterpret_cast<const double2 *>(r.up + cb) : z;
+    p.ad = (on && r.has_dn) ? *reinterpret_cast<const double2 *>(r.dn + ca) : z;
+    p.bd = (on && r.has_dn) ? *reinterpret_cast<const double2 *>(r.dn + cb) : z;
+    return p;
+}
+__device__ __forceinline__ void pair_math(const ModeRef &r, const PairLoads &p, double2 &S, double2 &T) {
+    S.x = (r.dm * p.a0.y + (r.e * p.bu.x - r.f * p.bd.x)) / r.ll1;
+    S.y = (-r.dm * p.a0.x + (r.e * p.bu.y - r.f * p.bd.y)) / r.ll1;
+    T.x = (-(r.e * p.au.x - r.f * p.ad.x) + r.dm * p.b0.y) / r.ll1;
+    T.y = (-(r.e * p.au.y - r.f * p.ad.y) - r.dm * p.b0.x) / r.ll1;
 }
 
 __global__ void __launch_bounds__(256) anal_extract_kernel(ExtractArgs a) {
@@ -542,13 +567,31 @@ __global__ void __launch_bounds__(256) extract_td_kernel(ExtractArgs e, TdArgs t
             on = e.lm2l[lm] <= e.lev[lev].lcut;
             r = mode_ref(e, lm, lev);
         }
-        for (int f = 0; f < e.nf_s; f++)
-            td_sm[((size_t)f * n_lev + lev) * TLP + ll] = on ? *reinterpret_cast<const double2 *>(r.own + 2 * (size_t)f * n_lev) : z;
-        for (int i = 0; i < e.npair; i++) {
+        // Loads in batches, every load of a batch issued before its first use: up to four scalar columns, then two vector pairs
+        // (12 loads) at a time.  (ncu on the one-at-a-time form: 60 % of all stall samples on the first use of a load that had
+        // just been issued -- the trip counts are run-time values, so the compiler did not overlap the iterations.)
+        for (int f0 = 0; f0 < e.nf_s; f0 += 4) {
+            double2 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                v[q] = (on && f0 + q < e.nf_s) ? *reinterpret_cast<const double2 *>(r.own + 2 * (size_t)(f0 + q) * n_lev) : z;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (f0 + q < e.nf_s) td_sm[((size_t)(f0 + q) * n_lev + lev) * TLP + ll] = v[q];
+        }
+        for (int i0 = 0; i0 < e.npair; i0 += 2) {
+            const bool two = i0 + 1 < e.npair;
+            const PairLoads p0 = pair_load(e, r, i0, on), p1 = pair_load(e, r, two ? i0 + 1 : i0, on && two);
             double2 S = z, T = z;
-            if (on) pair_combine(e, r, i, S, T);
-            td_sm[((size_t)(e.nf_s + 2 * i) * n_lev + lev) * TLP + ll] = S;
-            td_sm[((size_t)(e.nf_s + 2 * i + 1) * n_lev + lev) * TLP + ll] = T;
+            if (on) pair_math(r, p0, S, T);
+            td_sm[((size_t)(e.nf_s + 2 * i0) * n_lev + lev) * TLP + ll] = S;
+            td_sm[((size_t)(e.nf_s + 2 * i0 + 1) * n_lev + lev) * TLP + ll] = T;
+            if (two) {
+                S = z; T = z;
+                if (on) pair_math(r, p1, S, T);
+                td_sm[((size_t)(e.nf_s + 2 * i0 + 2) * n_lev + lev) * TLP + ll] = S;
+                td_sm[((size_t)(e.nf_s + 2 * i0 + 3) * n_lev + lev) * TLP + ll] = T;
+            }
         }
     }
     __syncthreads();

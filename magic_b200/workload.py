@@ -21,6 +21,11 @@ CONFIGS = {
     "full_sphere_l511": dict(l_max=511, minc=1, n_r_max=161, physics="hydro", config_id=3,
                              flags=dict(l_full_sphere=1, l_double_curl=1), l_var_l=True),
     "dynamo_l1023": dict(l_max=1023, minc=1, n_r_max=257, physics="mhd", config_id=4),
+    # the radial loop on a real saturated state -- the spectra of samples/boussBenchSat/checkpoint_end.start (read
+    # with magic_b200.checkpoint and committed as tests/golden/boussBenchSat_ckpt.npz), radial derivatives by the Chebyshev
+    # collocation matrices of the same grid; l_max = 64, minc = 4, n_r_max = 33
+    "boussBenchSat_ckpt": dict(l_max=64, minc=4, n_r_max=33, physics="mhd", config_id=5,
+                               checkpoint="tests/golden/boussBenchSat_ckpt.npz"),
 }
 
 
@@ -135,7 +140,7 @@ def config_sizes(name):
     c = CONFIGS[name]
     gs = grid_sizes(l_max=c["l_max"], n_phi_tot=c.get("n_phi_tot", 0), minc=c["minc"])
     gs.update(n_r_max=c["n_r_max"], minc=c["minc"], physics=c["physics"], config_id=c["config_id"], flags=c.get("flags", {}),
-              l_var_l=c.get("l_var_l", False))
+              l_var_l=c.get("l_var_l", False), checkpoint=c.get("checkpoint"))
     return gs
 
 
@@ -163,3 +168,15 @@ def config_l_R(gs):
 
 def seed_for(config_id, rank):
     return 20261017 + 1000 * config_id + rank
+
+
+def checkpoint_containers(path, lm_max, n_r_max):
+    """R-distributed containers (all levels) of a checkpoint fixture: flow = (w, dw, ddw, z, dz), s = (s, ds), field = (b, db, ddb,
+    aj, dj), complex128 [nf, n_r_max, lm_max]; the radial derivatives are what get_dr / get_ddr return on the Chebyshev grid."""
+    d = np.load(path)
+    assert d["w"].shape == (n_r_max, lm_max), (d["w"].shape, n_r_max, lm_max)
+    D1, D2 = cheb_matrices(n_r_max)
+    dr = lambda D, a: np.einsum("ij,jk->ik", D, a)
+    w, z, s, b, aj = (np.asarray(d[k], dtype=np.complex128) for k in ("w", "z", "s", "b", "aj"))
+    return {"flow": np.stack([w, dr(D1, w), dr(D2, w), z, dr(D1, z)]), "s": np.stack([s, dr(D1, s)]),
+            "field": np.stack([b, dr(D1, b), dr(D2, b), aj, dr(D1, aj)])}
