@@ -60,7 +60,10 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
     constexpr int STAGES = A_KCONTIG ? STAGES_K : STAGES_M;
     constexpr int A_TILE = A_KCONTIG ? A_TILE_K : A_TILE_M;
     constexpr int STAGE = A_TILE + B_TILE;
-    constexpr int DIST = STAGES - 2;  // prefetch distance; the remaining stage is the slack between fastest and slowest warp
+#ifndef MAGIC_GEMM_SLACK
+#define MAGIC_GEMM_SLACK 2
+#endif
+    constexpr int DIST = STAGES - MAGIC_GEMM_SLACK;  // prefetch distance; with 2 the remaining stage is the slack between fastest and slowest warp
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;

@@ -133,7 +133,7 @@ __device__ __forceinline__ bool level_enabled(int lmask, const LevelInfo &L) {
 
 constexpr int PREP_WARPS = 8;   // = levels per CTA
 #ifndef MAGIC_PREP_BATCH
-#define MAGIC_PREP_BATCH 4
+#define MAGIC_PREP_BATCH 8
 #endif
 constexpr int PREP_BATCH = MAGIC_PREP_BATCH;  // sources loaded per round of phase 1 (divides MAGIC_MAX_SRC)
 constexpr int PREP_LD = 35;     // staging tile: positions 0..33 = degrees l0-1 .. l0+32, odd stride against bank conflicts
@@ -178,10 +178,11 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) synth_prep_kernel(SynthPrepAr
             const int l = l0 - 1 + pos;
             const bool ok = lev < a.n_lev && l >= m && l <= a.l_max;
             const size_t lm = (size_t)a.lstart[mc] + (l - m);
-            // Four sources at a time, every load issued before the first store: the loads are unconditional (an absent source
-            // or an out-of-range degree reads a valid dummy address and is zeroed by a select), so the compiler cannot put
-            // a branch between them and each warp keeps four 512-byte requests in flight (ncu on the branchy form: 48 % of
-            // all stall samples on the STS that waited for its own LDG, 2.3 TB/s).
+            // PREP_BATCH sources at a time, every load issued before the first store: the loads are unconditional (an absent
+            // source or an out-of-range degree reads a valid dummy address and is zeroed by a select), so the compiler cannot
+            // put a branch between them and each warp keeps PREP_BATCH 512-byte requests in flight (ncu on the branchy form:
+            // 48 % of all stall samples on the STS that waited for its own LDG, 2.3 TB/s; measured per 16-level chunk at
+            // l_max = 1023: one at a time 1.44 ms, batches of 4 1.18 ms, batches of 8 1.08 ms, 66 registers in each case).
             const size_t off = ok ? 2 * ((size_t)lev * a.lm_max + lm) : 0;
 #pragma unroll
             for (int s0 = 0; s0 < MAGIC_MAX_SRC; s0 += PREP_BATCH) {
