@@ -22,6 +22,17 @@ namespace magic {
 constexpr int BK = 16;  // Legendre GEMM k-tile; all K extents are padded to multiples of BK
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 64;
+// CTA tile of the analysis (A_KCONTIG) form of the Legendre GEMM: 128 x 64 like the synthesis, or "wide" 64 x 128.  Its M dimension
+// is the ragged number of degrees of one (order, parity) problem: with 128-row tiles only 80 % of the warp rows of all tiles hold
+// degrees at l_max = 1023 (89 % with 64-row tiles), fewer at smaller truncations, and a warp without rows idles.  Measured
+// (analysis GEMM, ms): l_max = 255 1.4 -> 1.3, l_max = 511 (32 levels) 7.2 -> 6.4, l_max = 1023 (32 levels) 13.35 -> 13.56: the wide
+// tile is used below l_max = MAGIC_GEMM_WIDE_BELOW (the handle decides, engine.cu).
+#ifndef MAGIC_GEMM_WIDE_BELOW
+#define MAGIC_GEMM_WIDE_BELOW 768
+#endif
+constexpr int GEMM_BM_WIDE = 64, GEMM_BN_WIDE = 128;
+inline int gemm_bm_an(bool wide) { return wide ? GEMM_BM_WIDE : GEMM_BM; }
+inline int gemm_bn_an(bool wide) { return wide ? GEMM_BN_WIDE : GEMM_BN; }
 
 struct GemmProb {
     const double *A0;  // the table operand (P block of one order and parity)

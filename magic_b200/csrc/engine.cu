@@ -139,6 +139,10 @@ int sht_init(magic_sht *h) {
     if (dev_upload_vec(&h->d_tw, tw)) return 1;
     h->fft.tw = h->d_tw;
     MCHECK(gemm_setup_attributes());
+    {   // tile shape of the analysis GEMM (common.cuh): wide below MAGIC_GEMM_WIDE_BELOW, MAGIC_GEMM_AN_WIDE=0/1 forces it
+        const char *e = getenv("MAGIC_GEMM_AN_WIDE");
+        h->an_wide = e ? atoi(e) != 0 : h->l_max < MAGIC_GEMM_WIDE_BELOW;
+    }
     MCHECK(cudaFuncSetAttribute(extract_td_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MCHECK(cudaFuncSetAttribute(extract_td_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MCHECK(cudaFuncSetAttribute(extract_td_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -167,7 +171,8 @@ void layout_sizes(const magic_sht *h, const BatchSpec &spec, int n_lev, Layout &
     L.nf_s = (int)spec.afield_s.size();
     L.npair_a = (int)spec.afield_vt.size();
     L.nfa = L.nf_s + 2 * L.npair_a;
-    L.Na = L.nfa ? pad_up(2 * L.nfa * n_lev, GEMM_BN) : 0;
+    L.an_wide = h->an_wide;
+    L.Na = L.nfa ? pad_up(2 * L.nfa * n_lev, gemm_bn_an(L.an_wide)) : 0;
     L.offB.assign((size_t)n_m * 2, 0);
     L.offC.assign((size_t)n_m * 2, 0);
     long long pb = 0, pc = 0;
@@ -256,8 +261,8 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
                 g.Nvalid = 2 * L.nfa * n_lev;
                 const int pid = (int)pa.size();
                 pa.push_back(g);
-                for (int mt = 0; mt < (K + GEMM_BM - 1) / GEMM_BM; mt++)
-                    for (int nt = 0; nt < L.Na / GEMM_BN; nt++) ta.push_back(make_int2(pid, (mt << 16) | nt));
+                for (int mt = 0; mt < (K + gemm_bm_an(L.an_wide) - 1) / gemm_bm_an(L.an_wide); mt++)
+                    for (int nt = 0; nt < L.Na / gemm_bn_an(L.an_wide); nt++) ta.push_back(make_int2(pid, (mt << 16) | nt));
                 L.flops_an += 2.0 * K * (double)(g.kt0 - g.klo) * BK * L.Na;
             }
         }
@@ -347,7 +352,7 @@ int run_analysis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Buf
     launch_fft_r2c(h->fft, a, spec.nfield_out, h->stream);
     h->launches++;
     if (ev) cudaEventRecord(ev[1], h->stream);
-    launch_legendre_gemm(true, L.d_probs_an, L.d_tiles_an, L.ntiles_an, h->NHP, h->stream);
+    launch_legendre_gemm(true, L.d_probs_an, L.d_tiles_an, L.ntiles_an, h->NHP, h->stream, L.an_wide);
     h->launches++;
     if (ev) cudaEventRecord(ev[2], h->stream);
     if (!extract) { MCHECK(cudaGetLastError()); return 0; }

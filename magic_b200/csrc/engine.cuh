@@ -62,6 +62,7 @@ struct magic_sht {
     int *d_lm2l = nullptr, *d_lm2m = nullptr, *d_lstart = nullptr;
     double2 *d_tw = nullptr;
     magic::FftPlan fft;
+    bool an_wide = false;  // analysis GEMM with the 64 x 128 tile (common.cuh)
     cudaStream_t stream = nullptr;
     struct CallCtx *call = nullptr;  // lazily built single-level pipeline for the per-call API
     long long launches = 0;
@@ -104,6 +105,7 @@ struct Layout {  // descriptors for one chunk size
     ScalCol *d_scal = nullptr;
     VecPair *d_vec = nullptr;
     R2cField *d_r2c = nullptr;
+    bool an_wide = false;                // tile shape of the analysis GEMM this layout was sized for
     double flops_syn = 0, flops_an = 0;  // executed (padded) flops, for diagnostics
 };
 

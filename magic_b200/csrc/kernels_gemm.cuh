@@ -12,7 +12,8 @@
 // instead of meeting all others at a CTA barrier every k-tile (measured at l_max=1023, 16 levels: synthesis 16.18 -> 15.10 ms,
 // analysis 12.04 -> 11.76 ms; bit-identical results).
 //
-//   CTA tile 128 x 64, 8 warps as 4(M) x 2(N), warp tile 32 x 32 = 4x4 DMMA tiles, k-tile 16.
+//   CTA tile 128 x 64, 8 warps as 4(M) x 2(N) (synthesis) or 64 x 128, 2(M) x 4(N) (analysis: ragged M, common.cuh), warp tile
+//   32 x 32 = 4x4 DMMA tiles, k-tile 16.
 //   A_KCONTIG=false (synthesis): A tile stored As[k][m] (m = colatitude contiguous in the table).
 //   A_KCONTIG=true  (analysis) : A tile stored As[m][k] (m = degree row, k = colatitude contiguous).
 //   The [k][m] / [k][n] tiles have leading dimensions == 4 (mod 16) doubles, the [m][k] tile an XOR swizzle (below), so the
@@ -34,10 +35,13 @@ constexpr int LDA_M = GEMM_BM + 4;  // As[k][m]
 #define MAGIC_GEMM_SWZ 1
 #endif
 constexpr int LDA_K = MAGIC_GEMM_SWZ ? BK : BK + 4;  // As[m][k]
-constexpr int LDB_S = GEMM_BN + 4;  // Bs[k][n]
+constexpr int LDB_S = GEMM_BN + 4;       // Bs[k][n], 64-column tile
+constexpr int LDB_W = GEMM_BN_WIDE + 4;  // Bs[k][n], 128-column tile of the wide analysis form (both == 4 mod 16)
 constexpr int A_TILE_M = BK * LDA_M;
 constexpr int A_TILE_K = GEMM_BM * LDA_K;
+constexpr int A_TILE_KW = GEMM_BM_WIDE * LDA_K;
 constexpr int B_TILE = BK * LDB_S;
+constexpr int B_TILE_W = BK * LDB_W;
 constexpr int STAGES_M = 4;
 constexpr int STAGES_K = MAGIC_GEMM_SWZ ? 4 : 3;
 
@@ -53,13 +57,17 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 // 64 levels, one tile per CTA (gridDim.x = ntiles, the default) 36.1 + 26.7 ms, bit-identical: the hardware block scheduler
 // balances the very unequal tiles (polar skipping, ragged edges) better than a static round-robin, and the descriptor chain of
 // the next tile (tile -> problem -> skip table) stalls all warps of the persistent CTA at every tile change.
-template <bool A_KCONTIG>
+template <bool A_KCONTIG, bool WIDE = false>
 __global__ void __launch_bounds__(G_THREADS, 2)
 legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict__ tiles, int ntiles, int lda) {
     extern __shared__ __align__(16) double smem[];
     constexpr int STAGES = A_KCONTIG ? STAGES_K : STAGES_M;
-    constexpr int A_TILE = A_KCONTIG ? A_TILE_K : A_TILE_M;
-    constexpr int STAGE = A_TILE + B_TILE;
+    static_assert(A_KCONTIG || !WIDE, "the wide tile exists for the analysis form only");
+    constexpr int A_TILE = A_KCONTIG ? (WIDE ? A_TILE_KW : A_TILE_K) : A_TILE_M;
+    constexpr int BM = WIDE ? GEMM_BM_WIDE : GEMM_BM, BN = WIDE ? GEMM_BN_WIDE : GEMM_BN;  // CTA tile
+    constexpr int LDB = WIDE ? LDB_W : LDB_S;
+    constexpr int WN = BN / 32;                                                                  // warps along N (8 / WN along M)
+    constexpr int STAGE = A_TILE + BK * LDB;
 #ifndef MAGIC_GEMM_SLACK
 #define MAGIC_GEMM_SLACK 2
 #endif
@@ -67,7 +75,7 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int wm = (warp / WN) * 32, wn = (warp % WN) * 32;
 
     __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES];
     if (tid == 0) {
@@ -83,11 +91,17 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
     // table of order m is negligible polewards of the turning point sin(theta) ~ m/l: a triangle in the (degree, colatitude)
     // plane, of which Mlo / klo only remove the rectangle common to all degrees); -1: the whole tile lies in the polar cap
     auto first_ktile = [&](const GemmProb &pr, int m0) -> int {
-        if (!A_KCONTIG && m0 + GEMM_BM <= pr.Mlo) return -1;
+        if (!A_KCONTIG && m0 + BM <= pr.Mlo) return -1;
         int st0 = pr.klo;
         if (pr.ks0 != nullptr) {
-            const uint4 q = *reinterpret_cast<const uint4 *>(pr.ks0 + (m0 >> 3));
-            const unsigned mn = __vminu4(__vminu4(q.x, q.y), __vminu4(q.z, q.w));
+            unsigned mn;  // byte-wise minimum over the BM / 8 row fragments of the tile
+            if constexpr (BM == 128) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(pr.ks0 + (m0 >> 3));
+                mn = __vminu4(__vminu4(q.x, q.y), __vminu4(q.z, q.w));
+            } else {
+                const uint2 q = *reinterpret_cast<const uint2 *>(pr.ks0 + (m0 >> 3));
+                mn = __vminu4(q.x, q.y);
+            }
             const int f = (int)min(min(mn & 255u, (mn >> 8) & 255u), min((mn >> 16) & 255u, mn >> 24));
             st0 = max(st0, min(f, pr.kt0));
         }
@@ -103,7 +117,7 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
             if (lt >= ntiles) return;
             const int2 tile = tiles[lt];
             const GemmProb &pr = probs[tile.x];
-            const int m0 = (tile.y >> 16) * GEMM_BM, n0 = (tile.y & 0xffff) * GEMM_BN;
+            const int m0 = (tile.y >> 16) * BM, n0 = (tile.y & 0xffff) * BN;
             const int st0 = first_ktile(pr, m0);
             lkt = 0;
             lKT = st0 < 0 ? 0 : pr.kt0 - st0;
@@ -126,16 +140,16 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
         } else {
             const double *Ab = lA + (size_t)lkt * BK;
 #pragma unroll
-            for (int c = 0; c < 4; c++) {  // 128 rows x 8 chunks
+            for (int c = 0; c < BM * 8 / G_THREADS; c++) {  // BM rows x 8 chunks
                 int idx = tid + c * G_THREADS, m = idx >> 3, kc = idx & 7;
                 cp_async16(As + m * LDA_K + (MAGIC_GEMM_SWZ ? kc ^ ((m & 3) << 1) : kc) * 2, Ab + (size_t)m * lda + kc * 2);
             }
         }
         const double *Bb = lB + (size_t)lkt * BK * lldb;
 #pragma unroll
-        for (int c = 0; c < 2; c++) {  // 16 rows x 32 chunks
-            int idx = tid + c * G_THREADS, k = idx >> 5, nc = idx & 31;
-            cp_async16(Bs + k * LDB_S + nc * 2, Bb + (size_t)k * lldb + nc * 2);
+        for (int c = 0; c < BK * (BN / 2) / G_THREADS; c++) {  // 16 rows x BN/2 chunks
+            int idx = tid + c * G_THREADS, k = idx / (BN / 2), nc = idx % (BN / 2);
+            cp_async16(Bs + k * LDB + nc * 2, Bb + (size_t)k * lldb + nc * 2);
         }
         mbar_cp_async_arrive(&bar_full[st]);
         lkt++;
@@ -149,14 +163,14 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
     for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
         const int2 tile = tiles[ti];
         const GemmProb &pr = probs[tile.x];
-        const int m0 = (tile.y >> 16) * GEMM_BM, n0 = (tile.y & 0xffff) * GEMM_BN;
+        const int m0 = (tile.y >> 16) * BM, n0 = (tile.y & 0xffff) * BN;
         const int M = pr.M, ldc = pr.ldc, Nstore = pr.Nstore;
         double *const C = pr.C;
         const int st0 = first_ktile(pr, m0);
         if (st0 < 0) {
             // whole tile lies in the negligible polar cap: its rows of F are exact zeros
-            for (int idx = tid; idx < GEMM_BM * (GEMM_BN / 2); idx += G_THREADS) {
-                int row = m0 + idx / (GEMM_BN / 2), c2 = idx % (GEMM_BN / 2);
+            for (int idx = tid; idx < BM * (BN / 2); idx += G_THREADS) {
+                int row = m0 + idx / (BN / 2), c2 = idx % (BN / 2);
                 if (row < M && n0 + 2 * c2 < Nstore) *reinterpret_cast<double2 *>(C + (size_t)row * ldc + n0 + 2 * c2) = make_double2(0.0, 0.0);
             }
             continue;
@@ -190,7 +204,7 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
                                          : As[(kk * 4 + t) * LDA_M + row];
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) b[j] = Bs[(kk * 4 + t) * LDB_S + wn + j * 8 + g];
+                    for (int j = 0; j < 4; j++) b[j] = Bs[(kk * 4 + t) * LDB + wn + j * 8 + g];
                     if (full) {
 #pragma unroll
                         for (int i = 0; i < 4; i++)
@@ -222,7 +236,8 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
     }
 }
 
-inline size_t gemm_smem_bytes(bool a_kcontig) {
+inline size_t gemm_smem_bytes(bool a_kcontig, bool wide = false) {
+    if (a_kcontig && wide) return sizeof(double) * STAGES_K * (A_TILE_KW + B_TILE_W);
     return sizeof(double) * (a_kcontig ? STAGES_K * (A_TILE_K + B_TILE) : STAGES_M * (A_TILE_M + B_TILE));
 }
 
@@ -232,13 +247,17 @@ inline cudaError_t gemm_setup_attributes() {
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(legendre_gemm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(legendre_gemm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(legendre_gemm_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    e = cudaFuncSetAttribute(legendre_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)gemm_smem_bytes(true, true));
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(legendre_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)gemm_smem_bytes(true));
 }
 
 // grid: one CTA per tile (MAGIC_GEMM_PERSIST=1: two persistent CTAs per SM, see the kernel's header comment)
 inline void launch_legendre_gemm(bool a_kcontig, const GemmProb *probs, const int2 *tiles, int ntiles, int lda,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, bool wide = false) {
     if (ntiles <= 0) return;
     static int ctas = 0;
     if (ctas == 0) {
@@ -249,7 +268,9 @@ inline void launch_legendre_gemm(bool a_kcontig, const GemmProb *probs, const in
         ctas = (e && atoi(e) == 1) ? 2 * sms : (1 << 30);
     }
     const int grid = ntiles < ctas ? ntiles : ctas;
-    if (a_kcontig)
+    if (a_kcontig && wide)
+        legendre_gemm_kernel<true, true><<<grid, G_THREADS, gemm_smem_bytes(true, true), st>>>(probs, tiles, ntiles, lda);
+    else if (a_kcontig)
         legendre_gemm_kernel<true><<<grid, G_THREADS, gemm_smem_bytes(true), st>>>(probs, tiles, ntiles, lda);
     else
         legendre_gemm_kernel<false><<<grid, G_THREADS, gemm_smem_bytes(false), st>>>(probs, tiles, ntiles, lda);
