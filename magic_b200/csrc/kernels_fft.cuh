@@ -253,10 +253,19 @@ __host__ __device__ constexpr int fft_last_radix(int H) {
     while (len / fft_pick_radix(len) > 1) len /= fft_pick_radix(len);
     return len;
 }
-#ifndef MAGIC_FFT_R_BIG
-#define MAGIC_FFT_R_BIG 2
+// Rows per CTA: as many as give about MAGIC_FFT_CTA_THREADS threads (one thread per paired first-pass item), at most 16.
+// Measured (l_max = 511, H = 768: 2 rows = 96 threads 6.1 + 5.6 ms per step, 4 rows = 192 threads 4.7 + 4.2 ms, 8 rows 8.4 + 5.6 ms;
+// l_max = 255, H = 384: 4 / 8 / 16 rows 2.1 + 1.6 / 2.0 + 1.3 / 2.8 + 1.6 ms; l_max = 1023, H = 1536: 1 / 2 / 4 rows 6.7 + 7.5 /
+// 3.9 + 2.6 / 4.7 + 2.8 ms per 16-level chunk): six warps per CTA are the sweet spot at every length from H = 256 up.
+#ifndef MAGIC_FFT_CTA_THREADS
+#define MAGIC_FFT_CTA_THREADS 192
 #endif
-__host__ __device__ constexpr int fft2_rows(int H) { return H >= 768 ? MAGIC_FFT_R_BIG : H >= 256 ? 4 : H >= 96 ? 8 : 16; }
+__host__ __device__ constexpr int fft2_rows(int H) {
+    if (H < 256) return H >= 96 ? 8 : 16;  // short rows: many small CTAs per SM do better (H = 144: 8 rows 0.3 ms, 16 rows 0.5 ms per step)
+    const int ni1 = (H / fft_pick_radix(H) + 1) / 2;
+    const int r = MAGIC_FFT_CTA_THREADS / (ni1 > 0 ? ni1 : 1);
+    return r < 1 ? 1 : r > 16 ? 16 : r;
+}
 __host__ __device__ constexpr int fft2_rowlen(int H) { return fft_pad(H) + ((fft_pad(H) % 8) == 4 ? 0 : (12 - fft_pad(H) % 8) % 8); }  // == 4 (mod 8): rows r, r+1 on complementary banks
 __host__ __device__ constexpr int fft2_threads(int H) {
     // one thread per paired first-pass item: R * ceil(NB1 / 2), rounded to warps, at most 256
@@ -875,7 +884,7 @@ inline void launch_fft_c2r(const FftPlan &pl, const double *F, int ld, int n_m, 
 #define X(h)                                                                                                                      \
     if (H == h) {                                                                                                                 \
         const int ntile = (ncols + fft2_rows(h) - 1) / fft2_rows(h);                                                              \
-        if (fft_use_pf() && fft_pf_smem_c2r(h, n_m) <= 113 * 1024) {                                                              \
+        if (fft_use_pf() && fft_pf_smem_c2r(h, n_m) <= (size_t)(227 * 1024 / MAGIC_FFT_PF_CTAS - 1024)) {                                                              \
             const int tpc = fft_tpc();                                                                                            \
             dim3 g((ntile + tpc - 1) / tpc, 2 * nh);                                                                              \
             fft_c2r_pf_kernel<h><<<g, fft2_threads(h), fft_pf_smem_c2r(h, n_m), st>>>(pl.tw, F, ld, n_m, nh, ncols, colrow, grid, tpc); \
@@ -897,7 +906,7 @@ inline void launch_fft_r2c(const FftPlan &pl, const R2cArgs &a, int nfields, cud
 #define X(h)                                                                                      \
     if (H == h) {                                                                                 \
         const int ntile = (a.n_lev + fft2_rows(h) - 1) / fft2_rows(h);                            \
-        if (fft_use_pf() && fft_pf_smem_r2c(h) <= 110 * 1024) {                                   \
+        if (fft_use_pf() && fft_pf_smem_r2c(h) <= (size_t)(227 * 1024 / MAGIC_FFT_PF_CTAS - 1024)) {                                   \
             const int tpc = fft_tpc();                                                            \
             dim3 g((ntile + tpc - 1) / tpc, 2 * a.nh, nfields);                                   \
             fft_r2c_pf_kernel<h><<<g, fft2_threads(h), fft_pf_smem_r2c(h), st>>>(pl.tw, a, tpc);   \
