@@ -146,8 +146,8 @@ int magic_rloop_get_br_v_bcs(const magic_rloop *rl, int boundary, double *br_vt_
 /* ---- In-loop diagnostics of log steps (rIter.f90:303-373) ------------------------------------------------
  * The reference calls get_helicity (outMisc.f90:1052), get_hemi (:991), get_visc_heat (power.f90:384), get_perpPar
  * (outPar.f90:646), get_fluxes (:470) and get_nlBLayers (:584) on the grid arrays of every level when lHelCalc, lHemiCalc,
- * lPowerCalc, lPerpParCalc, lFluxProfCalc, lViscBcCalc are set.  One call here returns all requested per-level sums: the
- * fields they read are synthesised on the device (lDeriv = .true. on the boundary levels, as rIter.f90:193-205 sets it when
+ * lPowerCalc, lPerpParCalc, lFluxProfCalc, lViscBcCalc are set (and get_ekin_solid_liquid, outMisc.f90:1169, with lPhaseCalc).
+ * One call here returns all requested per-level sums: the fields they read are synthesised on the device (lDeriv = .true. on the boundary levels, as rIter.f90:193-205 sets it when
  * an output flag is on) and reduced by one fused kernel; out is a HOST array [n_r_loc][MAGIC_NDIAG].
  *   mask   MAGIC_DIAG_* bits; MAGIC_DIAG_RMSBULK = lRmsCalc is on, so boundary levels are treated as bulk (rIter.f90:215)
  *   ktops / kbots  thermal boundary types (1 = fixed entropy: horizontal entropy gradient zeroed there, rIter.f90:488-495)
@@ -159,6 +159,9 @@ int magic_rloop_get_br_v_bcs(const magic_rloop *rl, int boundary, double *br_vt_
  *       (fconvASr = temp0*[23] + ViscHeatFac*ThExpNb*alpha0*temp0*orho1*[24], or [23] alone with l_anelastic_liquid:
  *        outPar.f90:511-517 -- radial functions the host holds)
  *   uhASr 28   duhASr 29   gradT2ASr 30
+ *   MAGIC_DIAG_PHASE (get_ekin_solid_liquid, outMisc.f90:1169-1221; needs l_phase_field and in->phi):
+ *   ekinSr 32   ekinLr 33   volSr 34   min(phi) 35   max(phi) 36 over the level's grid (phase_min / phase_max of phase.TAG are
+ *   the extrema of the last two over the levels, outMisc.f90:952-953)
  * magic_rloop_diagnostics takes HOST field pointers (the *_Rloc arrays rIter_cuda_t already holds), the _dev form device
  * pointers.  Not available for full-sphere runs. */
 #define MAGIC_DIAG_HEL 1
@@ -167,8 +170,9 @@ int magic_rloop_get_br_v_bcs(const magic_rloop *rl, int boundary, double *br_vt_
 #define MAGIC_DIAG_PERPPAR 8
 #define MAGIC_DIAG_FLUX 16
 #define MAGIC_DIAG_VISCBC 32
+#define MAGIC_DIAG_PHASE 64
 #define MAGIC_DIAG_RMSBULK 256
-#define MAGIC_NDIAG 32
+#define MAGIC_NDIAG 40
 int magic_rloop_diagnostics(magic_rloop *rl, const magic_fields_in *in, int mask, int ktops, int kbots, double *out);
 int magic_rloop_diagnostics_dev(magic_rloop *rl, const magic_fields_in *in, int mask, int ktops, int kbots, double *out);
 /* get_dtBLM (rIter.f90:392-395, dtB.f90:144-223), what the loop contributes when l_dtB is on: the eleven grid

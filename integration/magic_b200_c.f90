@@ -60,7 +60,7 @@ module magic_b200_c
 
    !-- magic_rloop_diagnostics: mask bits (include/magic_sht.h)
    integer(c_int), parameter :: MAGIC_DIAG_HEL = 1, MAGIC_DIAG_HEMI = 2, MAGIC_DIAG_POWER = 4, MAGIC_DIAG_PERPPAR = 8, &
-   &                            MAGIC_DIAG_FLUX = 16, MAGIC_DIAG_VISCBC = 32, MAGIC_DIAG_RMSBULK = 256
+   &                            MAGIC_DIAG_FLUX = 16, MAGIC_DIAG_VISCBC = 32, MAGIC_DIAG_PHASE = 64, MAGIC_DIAG_RMSBULK = 256
 
    interface
 
@@ -313,7 +313,7 @@ module magic_b200_c
          type(c_ptr), value :: rl
          type(magic_fields_in), intent(in) :: fin
          integer(c_int), value :: mask, ktops, kbots
-         real(c_double), intent(out) :: out(32,*)
+         real(c_double), intent(out) :: out(40,*)
          integer(c_int) :: ierr
       end function magic_rloop_diagnostics
 

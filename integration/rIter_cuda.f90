@@ -15,13 +15,13 @@ module rIter_cuda_mod
    !
    use iso_c_binding
    use precision_mod
-   use truncation, only: lm_max, lm_maxMag, n_r_max
+   use truncation, only: lm_max, lm_maxMag, n_r_max, n_theta_max, n_phi_max, nlat_padded
    use radial_data, only: nRstart, nRstop, nRstartMag, nRstopMag, n_r_cmb, n_r_icb
    use logic, only: l_conv, l_mag, l_heat, l_conv_nl, l_heat_nl, l_mag_nl, l_mag_LF, l_mag_kin, l_anel,    &
        &            l_adv_curl, l_corr, l_double_curl, l_single_matrix, l_chemical_conv, l_precession,      &
        &            l_centrifuge, l_anelastic_liquid, l_cour_alf_damp, l_full_sphere, l_parallel_solve,     &
        &            l_temperature_diff, l_cond_ma, l_cond_ic, l_rot_ma, l_rot_ic, l_b_nl_cmb, l_b_nl_icb,   &
-       &            l_phase_field, l_onset, l_dtB
+       &            l_phase_field, l_onset, l_dtB, l_dtphaseMovie
    use special, only: lGrenoble
    use physical_parameters, only: ktopv, kbotv, n_r_LCR, LFfac, CorFac, epsc, epscXi, opm, ViscHeatFac,     &
        &                          OhmLossFac, oek, po, prec_angle, dilution_fac, ra, opr, ktops, kbots,     &
@@ -30,7 +30,7 @@ module rIter_cuda_mod
        &                       epscProf, l_R, r_cmb, r_icb, alpha0
    !-- per-level sums of the in-loop diagnostics (module variables of the reference, to be made public there)
    use outMisc_mod, only: HelASr, Hel2ASr, HelnaASr, Helna2ASr, HelEAASr, hemi_ekin_r, hemi_vrabs_r,        &
-       &                  hemi_emag_r, hemi_brabs_r
+       &                  hemi_emag_r, hemi_brabs_r, ekinSr, ekinLr, volSr, phase_Rloc, temp_Rloc, dtemp_Rloc
    use power, only: viscASr
    !-- get_dtBLM's per-level results (module variables of dtB_mod, to be made public there) and the routine that consumes them
    use dtB_mod, only: BtVrLM, BpVrLM, BrVtLM, BrVpLM, BtVpLM, BpVtLM, BpVtBtVpCotLM, BpVtBtVpSn2LM, BrVZLM, BtVZLM,   &
@@ -50,7 +50,7 @@ module rIter_cuda_mod
    use rIter_mod, only: rIter_single_t
    use useful, only: abortRun
    use constants, only: zero
-   use sht, only: sht_h
+   use sht, only: sht_h, scal_to_spat
    use magic_b200_c
 
    implicit none
@@ -226,15 +226,16 @@ contains
       integer :: ist, mask, nR
       logical :: l_diag
       real(c_double), allocatable :: dg(:,:)
+      real(cp), allocatable :: grd(:,:)
       complex(c_double_complex), allocatable :: dtb(:,:,:)
 
-      !-- Log steps: get_helicity, get_hemi, get_visc_heat, get_perpPar, get_fluxes and get_nlBLayers (rIter.f90:320-367) are
-      !   evaluated on the device after the batched loop (diagnostics_on_device below).  The remaining output hooks keep the
+      !-- Log steps: get_helicity, get_hemi, get_visc_heat, get_perpPar, get_fluxes, get_nlBLayers and get_ekin_solid_liquid
+      !   (rIter.f90:320-367) are evaluated on the device after the batched loop (diagnostics_on_device below).  The remaining output hooks keep the
       !   reference's level-at-a-time loop (its transforms still run on the GPU)
       if ( l_graph .or. l_frame .or. lTOCalc .or. lTONext .or. lTONext2 .or. lRmsCalc .or. lPressCalc .or.   &
-      &    lGeosCalc .or. lPhaseCalc .or. l_probe_out .or. ( lPressNext .and. l_double_curl ) .or.           &
+      &    lGeosCalc .or. l_probe_out .or. ( lPressNext .and. l_double_curl ) .or.                           &
       &    ( l_full_sphere .and. ( lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or.        &
-      &                            lPerpParCalc .or. lHemiCalc ) ) ) then
+      &                            lPerpParCalc .or. lHemiCalc .or. lPhaseCalc ) ) ) then
          !-- ( lPressNext with the double-curl equation: the reference also calls get_dpdt then (rIter.f90:420); the batched
          !   loop only produces dpdt in the pressure formulation, so that step takes the level-at-a-time loop )
          if ( l_fused_lm ) then   ! the recorded transposes become real: the level-at-a-time loop reads the host R arrays
@@ -255,7 +256,7 @@ contains
       !-- Fused mode: LM-distributed host containers in, LM-distributed explicit terms out -- the transposes on either side of
       !   this call (step_time.f90:485, :612) are part of it (mpi_transp_cuda_mod); the explicit terms go into the slice
       !   tscheme%istage of the time-array containers, which is where transp_Rloc_to_LMloc would put them (step_time.f90:1134-1245)
-      l_diag = lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lHemiCalc
+      l_diag = lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lHemiCalc .or. lPhaseCalc
       if ( l_fused_lm .and. n_pending > 0 .and. .not. ( l_b_nl_cmb .or. l_b_nl_icb .or. l_diag .or. l_dtB .or. l_phase_field ) ) then
          ist = tscheme%istage
          lin  = magic_lm_in(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr)
@@ -366,8 +367,9 @@ contains
          if ( lPerpParCalc )  mask = mask + MAGIC_DIAG_PERPPAR
          if ( lFluxProfCalc ) mask = mask + MAGIC_DIAG_FLUX
          if ( lViscBcCalc )   mask = mask + MAGIC_DIAG_VISCBC
+         if ( lPhaseCalc )    mask = mask + MAGIC_DIAG_PHASE
          if ( lFluxProfCalc ) fin%p = c_loc(p_Rloc)    ! lPressCalc is set with lFluxProfCalc (step_time.f90:399)
-         allocate( dg(32,nRstart:nRstop) )
+         allocate( dg(40,nRstart:nRstop) )
          call magic_check( magic_rloop_diagnostics(this%rl, fin, int(mask,c_int), int(ktops,c_int), int(kbots,c_int), dg), &
               &            'magic_rloop_diagnostics' )
          do nR=nRstart,nRstop
@@ -399,8 +401,27 @@ contains
             if ( lViscBcCalc ) then
                uhASr(nR)=dg(29,nR);  duhASr(nR)=dg(30,nR);  gradT2ASr(nR)=dg(31,nR)
             end if
+            if ( lPhaseCalc ) then                                                  ! outMisc.f90:1217-1219
+               ekinSr(nR)=dg(33,nR);  ekinLr(nR)=dg(34,nR);  volSr(nR)=dg(35,nR)
+            end if
          end do
          deallocate( dg )
+         !-- outPhase locates the melting radius of every (theta,phi) column from the grid values of phi and s that
+         !   get_ekin_solid_liquid keeps (outMisc.f90:1210-1212): two scalar syntheses per level through module sht
+         if ( lPhaseCalc ) then
+            allocate( grd(nlat_padded,n_phi_max) )
+            do nR=nRstart,nRstop
+               call scal_to_spat(phi_Rloc(:,nR), grd, l_R(nR))
+               phase_Rloc(:,:,nR)=grd(1:n_theta_max,:)
+               call scal_to_spat(s_Rloc(:,nR), grd, l_R(nR))
+               temp_Rloc(:,:,nR)=grd(1:n_theta_max,:)
+               if ( l_dtphaseMovie ) then
+                  call scal_to_spat(ds_Rloc(:,nR), grd, l_R(nR))
+                  dtemp_Rloc(:,:,nR)=grd(1:n_theta_max,:)
+               end if
+            end do
+            deallocate( grd )
+         end if
       end if
 
    end subroutine radialLoop

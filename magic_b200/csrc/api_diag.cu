@@ -6,18 +6,18 @@
 // pressure, entropy gradient: rIter.f90:483-527).  Here a log step runs a second, synthesis-only column program over the same
 // spectral inputs -- exactly the fields the requested diagnostics read, with lDeriv = .true. on the boundary levels as the
 // reference sets it (rIter.f90:193-205) -- followed by one fused reduction kernel per level chunk.  The hot path of ordinary
-// steps is untouched; nothing but [n_r_loc][32] doubles crosses PCIe (instead of 20+ grid fields per level).
+// steps is untouched; nothing but [n_r_loc][MAGIC_NDIAG] doubles crosses PCIe (instead of 20+ grid fields per level).
 // Included by lib.cu after api_rloop.cu (it uses magic_rloop).
 #include "kernels_diag.cuh"
 
 struct DiagPipe {
-    int mask = -1, chunk = 0, gx = 0;
+    int mask = -1, chunk = 0, gx = 0, phi_field = -1;
     BatchSpec spec;
     DiagIn di;
     Layout lay;
     Buffers buf;
     LevelInfo *d_lev = nullptr;
-    double *d_gauss = nullptr, *d_means = nullptr, *d_partial = nullptr, *d_out = nullptr, *h_out = nullptr;
+    double *d_gauss = nullptr, *d_means = nullptr, *d_partial = nullptr, *d_partial_ph = nullptr, *d_out = nullptr, *h_out = nullptr;
     double *d_src[S_COUNT] = {nullptr};  // staging of the host-pointer call: complex [chunk][lm_max] per source
     bool need[S_COUNT] = {false};
 };
@@ -26,7 +26,7 @@ static void diag_free(DiagPipe *d) {
     if (!d) return;
     layout_free(d->lay);
     buffers_free(d->buf);
-    cudaFree(d->d_lev); cudaFree(d->d_gauss); cudaFree(d->d_means); cudaFree(d->d_partial); cudaFree(d->d_out);
+    cudaFree(d->d_lev); cudaFree(d->d_gauss); cudaFree(d->d_means); cudaFree(d->d_partial); cudaFree(d->d_partial_ph); cudaFree(d->d_out);
     if (d->h_out) cudaFreeHost(d->h_out);
     for (int i = 0; i < S_COUNT; i++) cudaFree(d->d_src[i]);
     delete d;
@@ -49,6 +49,8 @@ static int diag_build(magic_rloop *rl, int mask) {
     DiagIn &di = d->di;
     const Term N_ = {0, F_NONE};
     const bool flux = mask & DM_FLUX, viscbc = mask & DM_VISCBC;
+    const bool grads = mask & (DM_HEL | DM_POWER | DM_FLUX | DM_VISCBC);  // hemi / perpPar / phase read vr, vt, vp only
+    if ((mask & DM_PHASE) && !P.l_phase_field) MFAIL("magic_rloop_diagnostics: MAGIC_DIAG_PHASE needs l_phase_field");
     const bool mag = (P.l_mag || P.l_mag_LF) && ((mask & DM_HEMI) || flux);
     int nf = 0;
     auto need = [&](std::initializer_list<int> s) { for (int i : s) d->need[i] = true; };
@@ -60,14 +62,18 @@ static int diag_build(magic_rloop *rl, int mask) {
         }
     }
     if (flux && !P.l_anelastic_liquid) { add_scal(S, Term{S_P, F_ONE}, N_, LM_ALL, nf, di.p); need({S_P}); }  // lPressCalc, rIter.f90:503
-    need({S_W, S_DW, S_DDW, S_Z, S_DZ});
+    need({S_W, S_DW, S_Z});
     add_scal(S, Term{S_W, F_DLH}, N_, LM_VEL, nf, di.vr);
     add_pair(S, Term{S_DW, F_ONE}, N_, Term{S_Z, F_ONE}, N_, LM_VEL, nf, di.vt, di.vp);
-    add_scal(S, Term{S_DW, F_DLH}, N_, LM_ALL, nf, di.dvrdr);
-    add_pair(S, Term{S_DDW, F_ONE}, N_, Term{S_DZ, F_ONE}, N_, LM_ALL, nf, di.dvtdr, di.dvpdr);
-    add_scal(S, Term{S_Z, F_DLH}, N_, LM_VEL, nf, di.cvr);
-    add_pair(S, Term{S_W, F_DLH}, N_, N_, N_, LM_VELBULK, nf, di.dvrdt, di.dvrdp);
-    add_pair(S, Term{S_DW, F_IM}, N_, Term{S_Z, F_IM}, N_, LM_VEL, nf, di.dvtdp, di.dvpdp);
+    if (grads) {
+        need({S_DDW, S_DZ});
+        add_scal(S, Term{S_DW, F_DLH}, N_, LM_ALL, nf, di.dvrdr);
+        add_pair(S, Term{S_DDW, F_ONE}, N_, Term{S_DZ, F_ONE}, N_, LM_ALL, nf, di.dvtdr, di.dvpdr);
+        add_scal(S, Term{S_Z, F_DLH}, N_, LM_VEL, nf, di.cvr);
+        add_pair(S, Term{S_W, F_DLH}, N_, N_, N_, LM_VELBULK, nf, di.dvrdt, di.dvrdp);
+        add_pair(S, Term{S_DW, F_IM}, N_, Term{S_Z, F_IM}, N_, LM_VEL, nf, di.dvtdp, di.dvpdp);
+    }
+    if (mask & DM_PHASE) { add_scal(S, Term{S_PHI, F_ONE}, N_, LM_ALL, nf, d->phi_field); need({S_PHI}); }  // rIter.f90:509
     if (mag) {
         need({S_B, S_DB, S_AJ});
         add_scal(S, Term{S_B, F_DLH}, N_, LM_ALL, nf, di.br);
@@ -103,8 +109,10 @@ static int diag_build(magic_rloop *rl, int mask) {
     d->gx = (int)std::min<size_t>((plane + DIAG_THREADS - 1) / DIAG_THREADS, 4 * 148);
     MCHECK(cudaMalloc((void **)&d->d_means, sizeof(double) * DIAG_NMEAN * chunk * 2 * h->nh));
     MCHECK(cudaMalloc((void **)&d->d_partial, sizeof(double) * (size_t)chunk * d->gx * DIAG_NSLOT));
-    MCHECK(cudaMalloc((void **)&d->d_out, sizeof(double) * (size_t)rl->n_r_loc * DIAG_NSLOT));
-    MCHECK(cudaMallocHost((void **)&d->h_out, sizeof(double) * (size_t)rl->n_r_loc * DIAG_NSLOT));
+    MCHECK(cudaMalloc((void **)&d->d_partial_ph, sizeof(double) * (size_t)chunk * d->gx * DIAG_NPHASE));
+    MCHECK(cudaMalloc((void **)&d->d_out, sizeof(double) * (size_t)rl->n_r_loc * DIAG_NOUT));
+    MCHECK(cudaMemset(d->d_out, 0, sizeof(double) * (size_t)rl->n_r_loc * DIAG_NOUT));
+    MCHECK(cudaMallocHost((void **)&d->h_out, sizeof(double) * (size_t)rl->n_r_loc * DIAG_NOUT));
     return 0;
 }
 
@@ -156,13 +164,18 @@ static int diag_run(magic_rloop *rl, const magic_fields_in *in, int mask, int kt
             h->launches++;
         }
         diag_kernel<<<dim3(d->gx, nl), DIAG_THREADS, 0, h->stream>>>(a);
-        diag_finish_kernel<<<(nl * DIAG_NSLOT + 127) / 128, 128, 0, h->stream>>>(d->d_partial, d->gx, nl, d->d_out + (size_t)s0 * DIAG_NSLOT);
+        diag_finish_kernel<<<(nl * DIAG_NSLOT + 127) / 128, 128, 0, h->stream>>>(d->d_partial, d->gx, nl, d->d_out + (size_t)s0 * DIAG_NOUT);
         h->launches += 2;
+        if (mask & DM_PHASE) {
+            diag_phase_kernel<<<dim3(d->gx, nl), DIAG_THREADS, 0, h->stream>>>(a, d->phi_field, d->d_partial_ph);
+            diag_phase_finish_kernel<<<(nl * DIAG_NPHASE + 127) / 128, 128, 0, h->stream>>>(d->d_partial_ph, d->gx, nl, d->d_out + (size_t)s0 * DIAG_NOUT);
+            h->launches += 2;
+        }
         MCHECK(cudaGetLastError());
     }
-    MCHECK(cudaMemcpyAsync(d->h_out, d->d_out, sizeof(double) * (size_t)n_r * DIAG_NSLOT, cudaMemcpyDeviceToHost, h->stream));
+    MCHECK(cudaMemcpyAsync(d->h_out, d->d_out, sizeof(double) * (size_t)n_r * DIAG_NOUT, cudaMemcpyDeviceToHost, h->stream));
     MCHECK(cudaStreamSynchronize(h->stream));
-    memcpy(out, d->h_out, sizeof(double) * (size_t)n_r * DIAG_NSLOT);
+    memcpy(out, d->h_out, sizeof(double) * (size_t)n_r * DIAG_NOUT);
     return 0;
 }
 

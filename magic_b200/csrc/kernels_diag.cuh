@@ -15,7 +15,9 @@ namespace magic {
 // grid field index of every field the diagnostics read (-1 = absent); same order as the loader below
 struct DiagIn { int vr, vt, vp, cvr, dvrdr, dvtdr, dvpdr, dvrdt, dvrdp, dvtdp, dvpdp, s, p, drs, dsdt, dsdp, br, bt, bp, cbt, cbp; };
 constexpr int DIAG_NF = 21;
-constexpr int DIAG_NSLOT = 32;   // = MAGIC_NDIAG
+constexpr int DIAG_NSLOT = 32;   // sums accumulated by diag_kernel (registers)
+constexpr int DIAG_NOUT = 40;    // = MAGIC_NDIAG: doubles per level of the result (slots 32.. come from diag_phase_kernel)
+constexpr int DIAG_NPHASE = 5;   // ekinS, ekinL, volS, min(phi), max(phi)
 constexpr int DIAG_NMEAN = 8;    // phi means of vr, cvr, vt, vp, dvrdp, dvpdr, dvtdr, dvrdt (outMisc.f90:1091-1108)
 constexpr int DIAG_THREADS = 256;
 
@@ -27,7 +29,8 @@ enum DiagSlot {
     DG_FKIN, DG_FCONV_S, DG_FCONV_P, DG_FVISC, DG_FRES, DG_FPOYN,
     DG_UH, DG_DUH, DG_GRADT2
 };
-enum DiagMask { DM_HEL = 1, DM_HEMI = 2, DM_POWER = 4, DM_PERPPAR = 8, DM_FLUX = 16, DM_VISCBC = 32 };
+enum DiagPhaseSlot { DG_PH_EKINS = 32, DG_PH_EKINL, DG_PH_VOLS, DG_PH_MIN, DG_PH_MAX };
+enum DiagMask { DM_HEL = 1, DM_HEMI = 2, DM_POWER = 4, DM_PERPPAR = 8, DM_FLUX = 16, DM_VISCBC = 32, DM_PHASE = 64 };
 
 struct DiagArgs {
     DiagIn di;
@@ -219,14 +222,82 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_kernel(DiagArgs a) {
     }
 }
 
-// CTA partials added in CTA order -> out[lev][slot]
+// CTA partials added in CTA order -> out[lev][slot] (rows of DIAG_NOUT doubles)
 __global__ void diag_finish_kernel(const double *partial, int n_part, int n_lev, double *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_lev * DIAG_NSLOT) return;
     const int lev = i / DIAG_NSLOT, slot = i - lev * DIAG_NSLOT;
     double v = 0.0;
     for (int j = 0; j < n_part; j++) v += partial[((size_t)lev * n_part + j) * DIAG_NSLOT + slot];
-    out[i] = v;
+    out[(size_t)lev * DIAG_NOUT + slot] = v;
+}
+
+// get_ekin_solid_liquid (outMisc.f90:1169-1221): kinetic energy of the points with phi >= 1/2 (solid) and of the others (liquid),
+// the volume of the solid, and the extrema of phi on the grid (the phase_min / phase_max columns of phase.TAG,
+// outMisc.f90:952-953).  Reads vr, vt, vp (a.di) and the phase field (grid field phi_field); same reduction shape as diag_kernel.
+__global__ void __launch_bounds__(DIAG_THREADS) diag_phase_kernel(DiagArgs a, int phi_field, double *partial) {
+    const int lev = blockIdx.y;
+    const LevelInfo L = a.lev[lev];
+    const size_t plane = (size_t)a.nh * a.n_phi;
+    const double pn2 = 6.283185307179586476925286766559 / (double)a.n_phi;
+    double acc[DIAG_NPHASE] = {0.0, 0.0, 0.0, 1e300, -1e300};
+    for (unsigned pt = blockIdx.x * blockDim.x + threadIdx.x; pt < (unsigned)plane; pt += gridDim.x * blockDim.x) {
+        const int k = (int)(pt / (unsigned)a.n_phi);
+        const double st = a.sinth[k], ct = a.costh[k], w2 = pn2 * a.gauss[k], os2 = 1.0 / (st * st);
+        const int fi[4] = {a.di.vr, a.di.vt, a.di.vp, phi_field};
+        double e[4], o[4];
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            const double *base = a.gin + (((size_t)fi[f] * a.n_lev + lev) * 2) * plane + pt;
+            e[f] = __ldg(base);
+            o[f] = __ldg(base + plane);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            double vr = h ? e[0] - o[0] : e[0] + o[0], vt = h ? e[1] - o[1] : e[1] + o[1], vp = h ? e[2] - o[2] : e[2] + o[2];
+            const double phi = h ? e[3] - o[3] : e[3] + o[3];
+            double cvr = 0.0;
+            diag_override(a, L, st, h ? -ct : ct, vr, vt, vp, cvr);
+            const double ekin = 0.5 * L.orho1 * (L.or2 * vr * vr + os2 * vt * vt + os2 * vp * vp);
+            if (phi >= 0.5) {
+                acc[0] += w2 * ekin;
+                acc[2] += w2 * L.r * L.r;
+            } else {
+                acc[1] += w2 * ekin;
+            }
+            acc[3] = fmin(acc[3], phi);
+            acc[4] = fmax(acc[4], phi);
+        }
+    }
+    __shared__ double red[DIAG_THREADS / 32][DIAG_NPHASE];
+#pragma unroll
+    for (int i = 0; i < DIAG_NPHASE; i++) {
+        double v = acc[i];
+        for (int s = 16; s > 0; s >>= 1) {
+            const double u = __shfl_xor_sync(0xffffffffu, v, s);
+            v = i < 3 ? v + u : (i == 3 ? fmin(v, u) : fmax(v, u));
+        }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < DIAG_NPHASE) {
+        const int i = threadIdx.x;
+        double v = red[0][i];
+        for (int w = 1; w < DIAG_THREADS / 32; w++) v = i < 3 ? v + red[w][i] : (i == 3 ? fmin(v, red[w][i]) : fmax(v, red[w][i]));
+        partial[((size_t)lev * gridDim.x + blockIdx.x) * DIAG_NPHASE + i] = v;
+    }
+}
+
+__global__ void diag_phase_finish_kernel(const double *partial, int n_part, int n_lev, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lev * DIAG_NPHASE) return;
+    const int lev = i / DIAG_NPHASE, slot = i - lev * DIAG_NPHASE;
+    double v = partial[((size_t)lev * n_part) * DIAG_NPHASE + slot];
+    for (int j = 1; j < n_part; j++) {
+        const double u = partial[((size_t)lev * n_part + j) * DIAG_NPHASE + slot];
+        v = slot < 3 ? v + u : (slot == 3 ? fmin(v, u) : fmax(v, u));
+    }
+    out[(size_t)lev * DIAG_NOUT + DG_PH_EKINS + slot] = v;
 }
 
 }  // namespace magic

@@ -31,8 +31,8 @@ class Params(C.Structure):
 RADIAL_NAMES = ["r", "or1", "or2", "or4", "orho1", "orho2", "beta", "rho0", "otemp1", "temp0", "visc", "lambda",
                 "epscProf", "delxr2", "delxh2"]
 # magic_rloop_diagnostics: mask bits and slots (include/magic_sht.h)
-DIAG_HEL, DIAG_HEMI, DIAG_POWER, DIAG_PERPPAR, DIAG_FLUX, DIAG_VISCBC, DIAG_RMSBULK = 1, 2, 4, 8, 16, 32, 256
-NDIAG = 32
+DIAG_HEL, DIAG_HEMI, DIAG_POWER, DIAG_PERPPAR, DIAG_FLUX, DIAG_VISCBC, DIAG_PHASE, DIAG_RMSBULK = 1, 2, 4, 8, 16, 32, 64, 256
+NDIAG = 40
 IN_NAMES = ["w", "dw", "ddw", "z", "dz", "s", "ds", "p", "xi", "b", "db", "ddb", "aj", "dj", "phi"]
 OUT_NAMES = ["dwdt", "dzdt", "dpdt", "dsdt", "dxidt", "dbdt", "djdt", "dVxVhLM", "dVxBhLM", "dVSrLM", "dVXirLM", "dphidt"]
 

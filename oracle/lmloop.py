@@ -94,6 +94,7 @@ class ChebShell:
         # below n_cheb_max only (radial_derivatives.f90 get_dcheb with r_scheme%n_max)
         keep = (np.arange(N) < self.n_cheb_max).astype(float)
         self.D1t = ((d1 * drx) * keep[None, :]) @ Tinv
+        self.D2t = ((d2 * drx ** 2) * keep[None, :]) @ Tinv   # get_ddr: second derivative of the same truncated series
         # basis of the reference's coefficient space: f = B0 c with rnorm = sqrt(2/(N-1)) and boundary_fac = 1/2 on the
         # first and last mode (chebyshev.f90; the same convention as costf1)
         wts = np.ones(N)
@@ -188,7 +189,8 @@ class ShellHost:
     def __init__(self, lm2l, lm2m, radial_loop, n_r_max=33, n_cheb_max=None, radratio=0.35, ra=1e5, ek=1e-3, pr=1.0,
                  prmag=5.0, dtmax=1e-4, alpha=0.6, init_s1=404, amp_s1=0.1, init_b1=3, amp_b1=5.0, l_mag=True, ktopv=2,
                  kbotv=2, strat=0.0, polind=2.0, g0=0.0, g1=1.0, g2=0.0, l_correct_AMz=False, l_correct_AMe=False, l_heat=True,
-                 po=0.0, prec_angle=23.5, l_cond_ic=False, l_rot_ic=False, sigma_ratio=1.0, n_r_ic_max=17, n_cheb_ic_max=15, var_cond=None, raxi=0.0, sc=1.0, dif_exp=None):
+                 po=0.0, prec_angle=23.5, l_cond_ic=False, l_rot_ic=False, sigma_ratio=1.0, n_r_ic_max=17, n_cheb_ic_max=15, var_cond=None, raxi=0.0, sc=1.0, dif_exp=None,
+                 phase=None):
         self.lm2l = np.asarray(lm2l)
         self.lm2m = np.asarray(lm2m)
         self.lm_max = len(self.lm2l)
@@ -301,6 +303,24 @@ class ShellHost:
             x = 2.0 * r - g.r_cmb - g.r_icb
             s1 = 1.0 - 3.0 * x ** 2 + 3.0 * x ** 4 - x ** 6
             self.s[:, self._lm(l, m)] += amp_s1 * s1
+        # ---- phase field (l_phase_field; Namelists.f90:565-573, init_fields.f90:1431-1481): phase = dict(stef, tmelt, phaseDiffFac,
+        #      penaltyFac, epsPhase, ktopphi, kbotphi); init_phi = 1: a tanh front of width epsPhase at the melting radius of the
+        #      conductive state, no entropy perturbation in the solid
+        self.l_phase = phase is not None
+        self.phase = phase or {}
+        self.phi = z()
+        self.pr = pr
+        if self.l_phase:
+            temp00 = self.s[:, lm00].real / sq4pi
+            n_melt = None
+            for n in range(1, N):
+                if temp00[n - 1] < phase["tmelt"] <= temp00[n]:
+                    n_melt = n
+            phi0 = 0.5 * (1.0 + np.tanh((r - r[n_melt]) / 2.0 / np.sqrt(2.0) / phase["epsPhase"]))
+            self.phi[:, lm00] = sq4pi * phi0
+            self.s[:, self.lm2l != 0] *= (1.0 - phi0)[:, None]
+            self.phi_top = 0.0 if phase.get("ktopphi", 1) != 1 else sq4pi     # Namelists.f90:567-572
+            self.phi_bot = 0.0
         # ---- initB, init_b1=3, insulating inner core (init_fields.f90:1129-1188)
         if l_mag and init_b1 == 3 and self.l_cond_ic:   # init_fields.f90:1140-1176
             b_pol = amp_b1 * np.sqrt(3.0 * np.pi) / (3.0 + g.r_cmb)
@@ -320,7 +340,7 @@ class ShellHost:
             self.aj[:, self._lm(2, 0)] += b_tor * r * np.sin(np.pi * (r - g.r_icb))
         # ---- time arrays (time_array.f90): old, impl (one level each for CNAB2), expl (two levels)
         self.old, self.impl, self.expl = {}, {}, {}
-        for nm in ("s", "xi", "w", "p", "z", "b", "j"):
+        for nm in ("s", "xi", "phi", "w", "p", "z", "b", "j"):
             self.old[nm], self.impl[nm] = z(), z()
             self.expl[nm] = [z(), z()]
         if self.l_cond_ic:
@@ -329,6 +349,7 @@ class ShellHost:
                 self.expl[nm] = [zi(), zi()]
         self._mats = None
         # startFields.f90:373-432: derivatives and old/implicit terms of the start fields
+        self._rhs_imp_phi()
         self._rhs_imp_s()
         self._rhs_imp_xi()
         self._rhs_imp_wp()
@@ -400,6 +421,7 @@ class ShellHost:
                 raise AttributeError(k)
             setattr(self, k, v)
         self._mats = None
+        self._rhs_imp_phi()
         self._rhs_imp_s()
         self._rhs_imp_xi()
         self._rhs_imp_wp()
@@ -414,12 +436,25 @@ class ShellHost:
     def _rhs_imp_s(self):
         """get_entropy_rhs_imp, updateS.f90:658-756 (entropy diffusion, kappa=1)."""
         g = self.g
-        self.ds = g.D1 @ self.s
-        dds = g.D2 @ self.s
-        self.old["s"] = self.s.copy()
+        # get_ddr differentiates the modes below n_cheb_max only: the same as D1, D2 on solved fields (those hold no higher modes),
+        # not on start fields with a sharp front (initPhi scales the entropy perturbation by 1 - phi0)
+        D1, D2 = (g.D1t, g.D2t) if self.l_phase else (g.D1, g.D2)
+        self.ds = D1 @ self.s
+        dds = D2 @ self.s
+        self.old["s"] = self.s - self.phase["stef"] * self.phi if self.l_phase else self.s.copy()     # updateS.f90:706-716
         self.impl["s"] = self.opr * self.kappa[:, None] * (
             dds + (self.beta + self.dLtemp0 + 2.0 * g.or1 + self.dLkappa)[:, None] * self.ds -
             self.dL[None, :] * g.or2[:, None] * self.s)
+
+    def _rhs_imp_phi(self):
+        """get_phase_rhs_imp, updatePHI.f90:470-542."""
+        if not self.l_phase:
+            return
+        g, ph = self.g, self.phase
+        dphi = g.D1t @ self.phi
+        ddphi = g.D2t @ self.phi
+        self.old["phi"] = 5.0 / 6.0 * ph["stef"] * self.pr * self.phi
+        self.impl["phi"] = ph["phaseDiffFac"] * (ddphi + 2.0 * g.or1[:, None] * dphi - self.dL[None, :] * g.or2[:, None] * self.phi)
 
     def _rhs_imp_xi(self):
         """get_comp_rhs_imp, updateXI.f90:579-650."""
@@ -559,6 +594,12 @@ class ShellHost:
                 g.D2 + (beta + self.dLtemp0[:, None] + 2.0 * or1 + self.dLkappa[:, None]) * g.D1 - dL * or2 * I)
             M[0], M[-1] = I[0], I[-1]
             mats["s"].append(M)
+            if self.l_phase:   # phiMat (updatePHI.f90:805-895): Dirichlet (1) or Neumann boundary rows
+                ph = self.phase
+                M = 5.0 / 6.0 * ph["stef"] * self.pr * I - wl1 * ph["phaseDiffFac"] * (g.D2 + 2.0 * or1 * g.D1 - dL * or2 * I)
+                M[0] = I[0] if ph.get("ktopphi", 1) == 1 else g.D1[0]
+                M[-1] = I[-1] if ph.get("kbotphi", 1) == 1 else g.D1[-1]
+                mats.setdefault("phi", []).append(M)
             # xiMat (updateXI.f90:924-965), ktopxi = kbotxi = 1
             M = I - wl1 * self.osc * (g.D2 + (beta + 2.0 * or1) * g.D1 - dL * or2 * I)
             M[0], M[-1] = I[0], I[-1]
@@ -667,6 +708,8 @@ class ShellHost:
             f["s"] = self.s
         if self.l_chem:
             f["xi"] = self.xi
+        if self.l_phase:
+            f["phi"] = self.phi
         if self.l_mag:
             f.update(b=self.b, db=self.db, ddb=self.ddb, aj=self.aj, dj=self.dj)
         return f
@@ -707,6 +750,8 @@ class ShellHost:
             self.expl["s"][0] = self.orho1[:, None] * (out["dsdt"] - or2 * (g.D1t @ out["dVSrLM"]))   # updateS.f90:587-597
         if self.l_chem:
             self.expl["xi"][0] = self.orho1[:, None] * (out["dxidt"] - or2 * (g.D1t @ out["dVXirLM"]))   # updateXI.f90:495-511
+        if self.l_phase:
+            self.expl["phi"][0] = np.array(out["dphidt"])          # rIter.f90:698, no finish step (LMLoop.f90:390-453)
         self.expl["w"][0] = np.array(out["dwdt"])
         self.expl["p"][0] = np.array(out["dpdt"])
         self.expl["z"][0] = np.array(out["dzdt"])
@@ -742,8 +787,22 @@ class ShellHost:
                 idx = np.nonzero(self.lm2l == l)[0]
                 fn(l, idx)
 
+        # ---- updatePhi (updatePHI.f90:137-297), before updateS (LMLoop.f90:221-229)
+        if self.l_phase:
+            rhs = rhs_of("phi")
+            rhs[0], rhs[-1] = 0.0, 0.0
+            rhs[0, self._lm(0, 0)], rhs[-1, self._lm(0, 0)] = self.phi_top, self.phi_bot
+
+            def up_phi(l, idx):
+                self.phi[:, idx] = g.solve(mats["phi"][l], rhs[:, idx], (0, N - 1), ("phi", l))
+            per_degree(up_phi)
+            self.phi[:, m0] = self.phi[:, m0].real
+            rotate("phi")
+            self._rhs_imp_phi()
         # ---- updateS (updateS.f90:156-342)
         rhs = rhs_of("s")
+        if self.l_phase:
+            rhs = rhs + self.phase["stef"] * self.phi      # updateS.f90:202-209: St dphi/dt with the new phase field
         rhs[0], rhs[-1] = self.tops, self.bots
 
         def up_s(l, idx):

@@ -189,7 +189,7 @@ void orc_radial_loop(const orc_ctx *c, const orc_params *p, const orc_radial *ra
                      const orc_fields_in *in, const orc_fields_out *out, double time);
 
 /* The grid-space diagnostics of rIter.f90:303-373 (get_helicity, get_hemi, get_visc_heat, get_perpPar, get_fluxes,
- * get_nlBLayers) for n_r levels: out[n_r][32], slots as MAGIC_DG_* of include/magic_sht.h; mask = MAGIC_DIAG_* bits;
+ * get_nlBLayers) for n_r levels: out[n_r][40], slots as MAGIC_DG_* of include/magic_sht.h; mask = MAGIC_DIAG_* bits;
  * ktops / kbots: thermal boundary condition types (fixed temperature = 1 zeroes the horizontal entropy gradient on that
  * boundary, rIter.f90:488-495). */
 void orc_radial_diagnostics(const orc_ctx *c, const orc_params *p, const orc_radial *rad, int n_r, const orc_fields_in *in,

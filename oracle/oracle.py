@@ -310,7 +310,7 @@ class Oracle:
 
     def radial_diagnostics(self, params, radial, fields, mask, ktops=1, kbots=1):
         """rIter.f90:303-373 (get_helicity, get_hemi, get_visc_heat, get_perpPar, get_fluxes, get_nlBLayers) for the levels in
-        `radial`: float64 [n_r, 32], slots as MAGIC_DG_* of include/magic_sht.h."""
+        `radial`: float64 [n_r, 40], slots as MAGIC_DG_* of include/magic_sht.h."""
         n_r = len(radial["nR"])
         keep = []
         rad = _Radial()
@@ -330,7 +330,7 @@ class Oracle:
                 assert a.shape == (n_r, self.lm_max)
                 keep.append(a)
                 setattr(fin, nm, _p(a))
-        out = np.zeros((n_r, 32))
+        out = np.zeros((n_r, 40))
         self.lib.orc_radial_diagnostics(self.h, C.byref(params), C.byref(rad), c_int(n_r), C.byref(fin), c_int(mask), c_int(ktops),
                                         c_int(kbots), _p(out))
         return out
