@@ -95,6 +95,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_cp_async_arrive(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
+// the incrementing form: pending count +1 now, -1 when the prior cp.async of this thread have landed (pair it with mbar_arrive)
+__device__ __forceinline__ void mbar_cp_async_arrive_inc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
     unsigned ok = 0;

@@ -68,6 +68,12 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
     constexpr int LDB = WIDE ? LDB_W : LDB_S;
     constexpr int WN = BN / 32;                                                                  // warps along N (8 / WN along M)
     constexpr int STAGE = A_TILE + BK * LDB;
+#ifndef MAGIC_GEMM_ARRIVE_INC
+#define MAGIC_GEMM_ARRIVE_INC 0
+#endif
+#ifndef MAGIC_GEMM_SYNC_AFTER_FULL
+#define MAGIC_GEMM_SYNC_AFTER_FULL 0
+#endif
 #ifndef MAGIC_GEMM_SLACK
 #define MAGIC_GEMM_SLACK 2
 #endif
@@ -151,7 +157,16 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
             int idx = tid + c * G_THREADS, k = idx / (BN / 2), nc = idx % (BN / 2);
             cp_async16(Bs + k * LDB + nc * 2, Bb + (size_t)k * lldb + nc * 2);
         }
+#if MAGIC_GEMM_ARRIVE_INC == 1
+        mbar_cp_async_arrive_inc(&bar_full[st]);  // tracked copies hold the phase open (+1 / -1), the thread's own arrival counts
+        mbar_arrive(&bar_full[st]);
+#elif MAGIC_GEMM_ARRIVE_INC == 2   // diagnostic only (serialises the pipeline): copies completed before a plain arrival
+        cp_async_commit();
+        cp_async_wait_all();
+        mbar_arrive(&bar_full[st]);
+#else
         mbar_cp_async_arrive(&bar_full[st]);
+#endif
         lkt++;
         gl++;
     };
@@ -192,6 +207,9 @@ legendre_gemm_kernel(const GemmProb *__restrict__ probs, const int2 *__restrict_
             load_next();  // k-tile gc + DIST of this CTA's stream (it may belong to the next tile)
             const int st = gc % STAGES;
             mbar_wait(&bar_full[st], (gc / STAGES) & 1);
+#if MAGIC_GEMM_SYNC_AFTER_FULL   // diagnostic only
+            __syncthreads();
+#endif
             const double *As = smem + st * STAGE, *Bs = As + A_TILE;
             if (active) {
 #pragma unroll
