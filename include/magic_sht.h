@@ -175,6 +175,21 @@ int magic_rloop_get_br_v_bcs(const magic_rloop *rl, int boundary, double *br_vt_
 #define MAGIC_NDIAG 40
 int magic_rloop_diagnostics(magic_rloop *rl, const magic_fields_in *in, int mask, int ktops, int kbots, double *out);
 int magic_rloop_diagnostics_dev(magic_rloop *rl, const magic_fields_in *in, int mask, int ktops, int kbots, double *out);
+/* Torsional-oscillation sums (rIter.f90:395-404).  On lTONext steps getTOnext (TO.f90:309-352) keeps the
+ * cylindrical field components Bs, Bp, Bz of every level on the grid; on lTOCalc steps getTO (TO.f90:141-307) forms the azimuthal
+ * means of twenty products of (vr, vt, vp, cvr, dvpdr, br, bt, bp, cbr, cbt, phi) per level and colatitude.  magic_rloop_to_next
+ * synthesises br, bt, bp of all local levels and keeps the three components on the DEVICE; magic_rloop_to returns
+ * out[n_r_loc][MAGIC_NTO][n_theta_max] (HOST), colatitudes in geographic order north -> south (n_theta_cal2ord), arrays in the order
+ *   V2AS 0  VAS 1  dzCorAS 2  dzRstrAS 3  dzAstrAS 4  dzLFAS 5  Bs2AS 6  BspAS 7  BpzAS 8  BszAS 9  BspdAS 10  BpsdAS 11
+ *   BzpdAS 12  BpzdAS 13  dzPenAS 14          (the *_Rloc arrays of torsional_oscillations; magnetic ones 0 without l_mag)
+ * dtLast is getTO's argument (the previous time step).  Boundary levels as in the diagnostics (lDeriv = .true., rigid-wall
+ * values of v_rigid_boundary).  The O(l_max) spectral part of getTOnext / getTOfinish stays with the host (its get_PAS transforms
+ * are magic_toraxi_to_spat).  Host field pointers; the _dev forms take device pointers.  Not available for full-sphere runs. */
+#define MAGIC_NTO 15
+int magic_rloop_to_next(magic_rloop *rl, const magic_fields_in *in);
+int magic_rloop_to_next_dev(magic_rloop *rl, const magic_fields_in *in);
+int magic_rloop_to(magic_rloop *rl, const magic_fields_in *in, double dtLast, double *out);
+int magic_rloop_to_dev(magic_rloop *rl, const magic_fields_in *in, double dtLast, double *out);
 /* get_dtBLM (rIter.f90:392-395, dtB.f90:144-223), what the loop contributes when l_dtB is on: the eleven grid
  * products of (vr, vt, vp, br, bt, bp) and their analyses (2 spat_to_sphertor + 7 scal_to_SH with lcut = l_max) for all local
  * levels, as one more batch on the Legendre GEMM / FFT kernels.  out: HOST complex [11][n_r_loc][lm_max] = BtVrLM, BpVrLM,

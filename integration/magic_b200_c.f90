@@ -60,7 +60,7 @@ module magic_b200_c
 
    !-- magic_rloop_diagnostics: mask bits (include/magic_sht.h)
    integer(c_int), parameter :: MAGIC_DIAG_HEL = 1, MAGIC_DIAG_HEMI = 2, MAGIC_DIAG_POWER = 4, MAGIC_DIAG_PERPPAR = 8, &
-   &                            MAGIC_DIAG_FLUX = 16, MAGIC_DIAG_VISCBC = 32, MAGIC_DIAG_PHASE = 64, MAGIC_DIAG_RMSBULK = 256
+   &                            MAGIC_DIAG_FLUX = 16, MAGIC_DIAG_VISCBC = 32, MAGIC_DIAG_PHASE = 64, MAGIC_DIAG_RMSBULK = 256, MAGIC_NTO = 15
 
    interface
 
@@ -325,6 +325,24 @@ module magic_b200_c
          complex(c_double_complex), intent(out) :: out(*)
          integer(c_int) :: ierr
       end function magic_rloop_dtb
+
+      !-- torsional-oscillation sums (rIter.f90:395-404): getTOnext's grid part keeps Bs, Bp, Bz on the device; getTO returns
+      !   out(n_theta_max, MAGIC_NTO, n_r_loc), colatitudes in geographic order, arrays as listed in include/magic_sht.h
+      function magic_rloop_to_next(rl, fin) bind(C, name='magic_rloop_to_next') result(ierr)
+         import :: c_int, c_ptr, magic_fields_in
+         type(c_ptr), value :: rl
+         type(magic_fields_in), intent(in) :: fin
+         integer(c_int) :: ierr
+      end function magic_rloop_to_next
+
+      function magic_rloop_to(rl, fin, dtLast, out) bind(C, name='magic_rloop_to') result(ierr)
+         import :: c_int, c_ptr, c_double, magic_fields_in
+         type(c_ptr), value :: rl
+         type(magic_fields_in), intent(in) :: fin
+         real(c_double), value :: dtLast
+         real(c_double), intent(out) :: out(*)
+         integer(c_int) :: ierr
+      end function magic_rloop_to
 
       !---------------------------------------------------------------- r <-> LM transposer
       function magic_transp_unique_id(id) bind(C, name='magic_transp_unique_id') result(ierr)

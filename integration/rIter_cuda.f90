@@ -32,6 +32,10 @@ module rIter_cuda_mod
    use outMisc_mod, only: HelASr, Hel2ASr, HelnaASr, Helna2ASr, HelEAASr, hemi_ekin_r, hemi_vrabs_r,        &
        &                  hemi_emag_r, hemi_brabs_r, ekinSr, ekinLr, volSr, phase_Rloc, temp_Rloc, dtemp_Rloc
    use power, only: viscASr
+   !-- torsional oscillations: the (r,theta) arrays getTO fills, and the routines that hold the spectral part
+   use torsional_oscillations, only: prep_TO_axi, getTOnext, getTOfinish, V2AS_Rloc, VAS_Rloc, dzCorAS_Rloc, dzRstrAS_Rloc,   &
+       &                             dzAstrAS_Rloc, dzLFAS_Rloc, Bs2AS_Rloc, BspAS_Rloc, BpzAS_Rloc, BszAS_Rloc, BspdAS_Rloc, &
+       &                             BpsdAS_Rloc, BzpdAS_Rloc, BpzdAS_Rloc, dzPenAS_Rloc
    !-- get_dtBLM's per-level results (module variables of dtB_mod, to be made public there) and the routine that consumes them
    use dtB_mod, only: BtVrLM, BpVrLM, BrVtLM, BrVpLM, BtVpLM, BpVtLM, BpVtBtVpCotLM, BpVtBtVpSn2LM, BrVZLM, BtVZLM,   &
        &              BtVZsn2LM, get_dH_dtBLM
@@ -227,12 +231,15 @@ contains
       logical :: l_diag
       real(c_double), allocatable :: dg(:,:)
       real(cp), allocatable :: grd(:,:)
+      real(c_double), allocatable :: tq(:,:,:)
       complex(c_double_complex), allocatable :: dtb(:,:,:)
 
       !-- Log steps: get_helicity, get_hemi, get_visc_heat, get_perpPar, get_fluxes, get_nlBLayers and get_ekin_solid_liquid
-      !   (rIter.f90:320-367) are evaluated on the device after the batched loop (diagnostics_on_device below).  The remaining output hooks keep the
-      !   reference's level-at-a-time loop (its transforms still run on the GPU)
-      if ( l_graph .or. l_frame .or. lTOCalc .or. lTONext .or. lTONext2 .or. lRmsCalc .or. lPressCalc .or.   &
+      !   (rIter.f90:320-367) and the torsional-oscillation sums (getTOnext / getTO, rIter.f90:395-404) are evaluated on the device
+      !   after the batched loop (below).  The remaining output hooks keep the reference's level-at-a-time loop (its transforms
+      !   still run on the GPU)
+      if ( l_graph .or. l_frame .or. lRmsCalc .or. lPressCalc .or.                                         &
+      &    ( l_full_sphere .and. ( lTOCalc .or. lTONext .or. lTONext2 ) ) .or.                               &
       &    lGeosCalc .or. l_probe_out .or. ( lPressNext .and. l_double_curl ) .or.                           &
       &    ( l_full_sphere .and. ( lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or.        &
       &                            lPerpParCalc .or. lHemiCalc .or. lPhaseCalc ) ) ) then
@@ -256,7 +263,8 @@ contains
       !-- Fused mode: LM-distributed host containers in, LM-distributed explicit terms out -- the transposes on either side of
       !   this call (step_time.f90:485, :612) are part of it (mpi_transp_cuda_mod); the explicit terms go into the slice
       !   tscheme%istage of the time-array containers, which is where transp_Rloc_to_LMloc would put them (step_time.f90:1134-1245)
-      l_diag = lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lHemiCalc .or. lPhaseCalc
+      l_diag = lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lHemiCalc .or. lPhaseCalc &
+      &        .or. lTOCalc .or. lTONext .or. lTONext2
       if ( l_fused_lm .and. n_pending > 0 .and. .not. ( l_b_nl_cmb .or. l_b_nl_icb .or. l_diag .or. l_dtB .or. l_phase_field ) ) then
          ist = tscheme%istage
          lin  = magic_lm_in(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr)
@@ -359,7 +367,40 @@ contains
       !-- rIter.f90:320-367 on log steps: one call returns the per-level sums of all requested routines; they go where the
       !   reference's routines store them (the arrays below are module variables of outMisc_mod, power and outPar_mod, to be
       !   made public there: HelASr .. HelEAASr, hemi_*_r, viscASr, EperpASr .. EparaxiASr, fkinASr .. fpoynASr, uhASr ..)
-      if ( l_diag ) then
+      !-- rIter.f90:220-222, 395-404, 438 on torsional-oscillation steps: the grid part of getTOnext (Bs, Bp, Bz of the step before
+      !   the output) stays on the device, getTO's azimuthal means come back as (theta, array, level); the spectral, axisymmetric
+      !   part (prep_TO_axi, getTOnext's dzdVp / dzddVp bookkeeping, getTOfinish) is the reference's own code, level by level --
+      !   getTOnext gets zero grids: its BsLast / BpLast / BzLast are only read by getTO, which no longer runs on the host
+      if ( lTOCalc .or. lTONext .or. lTONext2 ) then
+         if ( lTONext .and. ( .not. lTONext2 ) .and. l_mag ) &
+         &  call magic_check( magic_rloop_to_next(this%rl, fin), 'magic_rloop_to_next' )
+         if ( lTOCalc ) then
+            allocate( tq(n_theta_max,MAGIC_NTO,nRstart:nRstop) )
+            call magic_check( magic_rloop_to(this%rl, fin, real(dtLast,c_double), tq), 'magic_rloop_to' )
+         end if
+         allocate( grd(n_theta_max,n_phi_max) )
+         grd(:,:)=0.0_cp
+         do nR=nRstart,nRstop
+            call prep_TO_axi(z_Rloc(:,nR), dz_Rloc(:,nR))
+            if ( lTONext .or. lTONext2 ) call getTOnext(grd,grd,grd,lTONext,lTONext2,tscheme%dt(1),dtLast,nR)
+            if ( lTOCalc ) then
+               V2AS_Rloc(:,nR)    =tq(:,1,nR);   VAS_Rloc(:,nR)     =tq(:,2,nR);   dzCorAS_Rloc(:,nR)=tq(:,3,nR)
+               dzRstrAS_Rloc(:,nR)=tq(:,4,nR);   dzAstrAS_Rloc(:,nR)=tq(:,5,nR)
+               if ( l_mag ) then
+                  dzLFAS_Rloc(:,nR)=tq(:,6,nR);   Bs2AS_Rloc(:,nR) =tq(:,7,nR);   BspAS_Rloc(:,nR) =tq(:,8,nR)
+                  BpzAS_Rloc(:,nR) =tq(:,9,nR);   BszAS_Rloc(:,nR) =tq(:,10,nR);  BspdAS_Rloc(:,nR)=tq(:,11,nR)
+                  BpsdAS_Rloc(:,nR)=tq(:,12,nR);  BzpdAS_Rloc(:,nR)=tq(:,13,nR);  BpzdAS_Rloc(:,nR)=tq(:,14,nR)
+               end if
+               if ( l_phase_field ) dzPenAS_Rloc(:,nR)=tq(:,15,nR)
+               call getTOfinish(nR, dtLast)
+            end if
+         end do
+         deallocate( grd )
+         if ( lTOCalc ) deallocate( tq )
+      end if
+
+      if ( l_diag .and. ( lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lHemiCalc .or. &
+      &                   lPhaseCalc ) ) then
          mask = 0
          if ( lHelCalc )      mask = mask + MAGIC_DIAG_HEL
          if ( lHemiCalc )     mask = mask + MAGIC_DIAG_HEMI

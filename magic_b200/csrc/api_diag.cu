@@ -337,3 +337,153 @@ static int dtb_run(magic_rloop *rl, const magic_fields_in *in, double *out, bool
 
 extern "C" int magic_rloop_dtb(magic_rloop *rl, const magic_fields_in *in, double *out) { return dtb_run(rl, in, out, true); }
 extern "C" int magic_rloop_dtb_dev(magic_rloop *rl, const magic_fields_in *in, double *out) { return dtb_run(rl, in, out, false); }
+
+// ------------------------------------------------------------------------------------------------------
+// Torsional-oscillation sums (rIter.f90:395-404; TO.f90:141-352): on lTONext steps the reference keeps three grid fields of every
+// level (BsLast, BpLast, BzLast), on lTOCalc steps it sweeps eleven grid fields per level for the azimuthal means of twenty
+// products.  Here both are one more synthesis-only column program (vr, vt, vp, cvr, dvpdr, br, bt, bp, cbr, cbt, phi with the
+// boundary treatment of the diagnostics) followed by to_next_kernel / to_kernel; the "Last" fields stay on the device between
+// the two calls; [n_r_loc][MAGIC_NTO][n_theta] doubles cross PCIe.  The spectral, axisymmetric part of getTOnext / getTOfinish
+// (TO.f90:322-329, 344-388: O(l_max) per level) stays with the host, its three get_PAS transforms are magic_toraxi_to_spat calls.
+struct ToPipe {
+    int chunk = 0;
+    BatchSpec spec;
+    ToIn ti;
+    Layout lay;
+    Buffers buf;
+    LevelInfo *d_lev = nullptr;
+    double *d_last = nullptr, *d_out = nullptr, *h_out = nullptr;
+    double *d_src[S_COUNT] = {nullptr};
+    bool need[S_COUNT] = {false};
+    bool have_last = false;
+};
+
+static void to_free(ToPipe *d) {
+    if (!d) return;
+    layout_free(d->lay);
+    buffers_free(d->buf);
+    cudaFree(d->d_lev); cudaFree(d->d_last); cudaFree(d->d_out);
+    if (d->h_out) cudaFreeHost(d->h_out);
+    for (int i = 0; i < S_COUNT; i++) cudaFree(d->d_src[i]);
+    delete d;
+}
+
+static int to_build(magic_rloop *rl) {
+    magic_sht *h = rl->h;
+    const magic_params &P = rl->p;
+    if (P.l_full_sphere) MFAIL("magic_rloop_to: full-sphere runs are not supported");
+    if (!(P.l_conv || P.l_mag_kin)) MFAIL("magic_rloop_to: needs a flow (l_conv or l_mag_kin)");
+    ToPipe *d = new ToPipe();
+    rl->to = d;
+    BatchSpec &S = d->spec;
+    int *tip = (int *)&d->ti;
+    for (int i = 0; i < TO_NF; i++) tip[i] = -1;
+    ToIn &ti = d->ti;
+    const Term N_ = {0, F_NONE};
+    int nf = 0, dvtdr = -1, cbp = -1;
+    auto need = [&](std::initializer_list<int> s) { for (int i : s) d->need[i] = true; };
+    need({S_W, S_DW, S_DDW, S_Z, S_DZ});
+    add_scal(S, Term{S_W, F_DLH}, N_, LM_VEL, nf, ti.vr);
+    add_pair(S, Term{S_DW, F_ONE}, N_, Term{S_Z, F_ONE}, N_, LM_VEL, nf, ti.vt, ti.vp);
+    add_scal(S, Term{S_Z, F_DLH}, N_, LM_VEL, nf, ti.cvr);
+    add_pair(S, Term{S_DDW, F_ONE}, N_, Term{S_DZ, F_ONE}, N_, LM_ALL, nf, dvtdr, ti.dvpdr);
+    if (P.l_mag) {
+        need({S_B, S_DB, S_DDB, S_AJ, S_DJ});
+        add_scal(S, Term{S_B, F_DLH}, N_, LM_ALL, nf, ti.br);
+        add_pair(S, Term{S_DB, F_ONE}, N_, Term{S_AJ, F_ONE}, N_, LM_ALL, nf, ti.bt, ti.bp);
+        add_scal(S, Term{S_AJ, F_DLH}, N_, LM_ALL, nf, ti.cbr);
+        add_pair(S, Term{S_DJ, F_ONE}, N_, Term{S_B, F_OR2DLH}, Term{S_DDB, F_NEG}, LM_ALL, nf, ti.cbt, cbp);
+    }
+    if (P.l_phase_field) { add_scal(S, Term{S_PHI, F_ONE}, N_, LM_ALL, nf, ti.phi); need({S_PHI}); }
+    S.nfield_in = nf;
+    S.nfield_out = 0;
+    const size_t plane = (size_t)h->nh * h->n_phi;
+    if (P.l_mag) {
+        cudaError_t e = cudaMalloc((void **)&d->d_last, sizeof(double) * 6 * plane * (size_t)rl->n_r_loc);
+        if (e != cudaSuccess) { cudaGetLastError(); MFAIL("magic_rloop_to: no device memory for BsLast / BpLast / BzLast of all local levels"); }
+        MCHECK(cudaMemset(d->d_last, 0, sizeof(double) * 6 * plane * (size_t)rl->n_r_loc));
+    }
+    size_t free_b = 0, total_b = 0;
+    MCHECK(cudaMemGetInfo(&free_b, &total_b));
+    const double per_level = 2.2 * 8.0 * (double)h->n_theta * h->n_phi * nf + 64.0 * h->lm_max * S_COUNT;
+    int chunk = (int)std::min<double>(32.0, 0.5 * (double)free_b / per_level);
+    chunk = std::max(1, std::min(chunk, rl->n_r_loc));
+    d->chunk = chunk;
+    layout_sizes(h, S, chunk, d->lay);
+    if (buffers_alloc(h, S, d->lay, d->buf)) return 1;
+    if (layout_bind(h, S, d->lay, d->buf)) return 1;
+    std::vector<LevelInfo> lev = rl->lev;   // lDeriv = .true. with lTOCalc (rIter.f90:197-205)
+    for (auto &L : lev) L.lDeriv = 1;
+    if (dev_upload_vec(&d->d_lev, lev)) return 1;
+    const size_t nout = (size_t)rl->n_r_loc * TO_NOUT * h->n_theta;
+    MCHECK(cudaMalloc((void **)&d->d_out, sizeof(double) * nout));
+    MCHECK(cudaMallocHost((void **)&d->h_out, sizeof(double) * nout));
+    return 0;
+}
+
+// mode 0: getTOnext (keep the cylindrical field components), mode 1: getTO
+static int to_run(magic_rloop *rl, const magic_fields_in *in, int mode, double dtLast, double *out, bool host_in) {
+    if (!rl || !in || (mode == 1 && !out)) MFAIL("magic_rloop_to: null argument");
+    magic_sht *h = rl->h;
+    MCHECK(cudaSetDevice(h->dev));
+    if (!rl->to)
+        if (to_build(rl)) return 1;
+    ToPipe *d = rl->to;
+    const magic_params &P = rl->p;
+    if (mode == 0 && !P.l_mag) return 0;  // TO.f90:330: only the magnetic terms keep grid fields
+    if (mode == 1 && !(dtLast > 0.0)) MFAIL("magic_rloop_to: dtLast must be positive");
+    const double *ip[S_COUNT];
+    in_ptrs(in, ip);
+    for (int i = 0; i < S_COUNT; i++)
+        if (d->need[i] && !ip[i]) MFAIL("magic_rloop_to: a required input field is null");
+    const size_t lm2 = 2 * (size_t)h->lm_max, plane = (size_t)h->nh * h->n_phi;
+    const int nl = d->chunk, n_r = rl->n_r_loc;
+    if (host_in)
+        for (int i = 0; i < S_COUNT; i++)
+            if (d->need[i] && !d->d_src[i]) MCHECK(cudaMalloc((void **)&d->d_src[i], sizeof(double) * lm2 * nl));
+    ToArgs a{};
+    a.ti = d->ti; a.gin = d->buf.gin; a.n_lev = nl; a.nh = h->nh; a.n_phi = h->n_phi; a.n_theta = h->n_theta;
+    a.l_mag = P.l_mag ? 1 : 0; a.l_phase_field = P.l_phase_field ? 1 : 0;
+    a.omega_ma = P.omega_ma; a.omega_ic = P.omega_ic; a.r_cmb = P.r_cmb; a.r_icb = P.r_icb; a.CorFac = P.CorFac;
+    a.pen = P.l_phase_field ? 1.0 / (P.epsPhase * P.epsPhase) / (P.penaltyFac * P.penaltyFac) : 0.0;
+    a.o_dtLast = mode == 1 ? 1.0 / dtLast : 0.0;
+    a.sinth = h->d_sinth; a.costh = h->d_costh;
+    const int gx = (int)std::min<size_t>((plane + DIAG_THREADS - 1) / DIAG_THREADS, 8 * 148);
+    for (int l0 = 0; l0 < n_r; l0 += nl) {
+        const int s0 = std::min(l0, n_r - nl);
+        const double *src[MAGIC_MAX_SRC];
+        for (int i = 0; i < MAGIC_MAX_SRC; i++) src[i] = nullptr;
+        for (int i = 0; i < S_COUNT; i++) {
+            if (!d->need[i]) continue;
+            if (host_in) {
+                MCHECK(cudaMemcpyAsync(d->d_src[i], ip[i] + (size_t)s0 * lm2, sizeof(double) * lm2 * nl, cudaMemcpyHostToDevice, h->stream));
+                src[i] = d->d_src[i];
+            } else {
+                src[i] = ip[i] + (size_t)s0 * lm2;
+            }
+        }
+        if (run_synthesis(h, d->spec, d->lay, d->buf, src, d->d_lev + s0, nullptr)) return 1;
+        a.lev = d->d_lev + s0;
+        a.last = d->d_last ? d->d_last + (size_t)s0 * 6 * plane : nullptr;
+        a.out = d->d_out + (size_t)s0 * TO_NOUT * h->n_theta;
+        if (mode == 0) to_next_kernel<<<dim3(gx, nl), DIAG_THREADS, 0, h->stream>>>(a);
+        else to_kernel<<<dim3(h->nh, nl), TO_THREADS, 0, h->stream>>>(a);
+        h->launches++;
+        MCHECK(cudaGetLastError());
+    }
+    if (mode == 0) {
+        d->have_last = true;
+        MCHECK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    const size_t nout = (size_t)n_r * TO_NOUT * h->n_theta;
+    MCHECK(cudaMemcpyAsync(d->h_out, d->d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, h->stream));
+    MCHECK(cudaStreamSynchronize(h->stream));
+    memcpy(out, d->h_out, sizeof(double) * nout);
+    return 0;
+}
+
+extern "C" int magic_rloop_to_next(magic_rloop *rl, const magic_fields_in *in) { return to_run(rl, in, 0, 0.0, nullptr, true); }
+extern "C" int magic_rloop_to_next_dev(magic_rloop *rl, const magic_fields_in *in) { return to_run(rl, in, 0, 0.0, nullptr, false); }
+extern "C" int magic_rloop_to(magic_rloop *rl, const magic_fields_in *in, double dtLast, double *out) { return to_run(rl, in, 1, dtLast, out, true); }
+extern "C" int magic_rloop_to_dev(magic_rloop *rl, const magic_fields_in *in, double dtLast, double *out) { return to_run(rl, in, 1, dtLast, out, false); }

@@ -68,17 +68,21 @@ struct DiagPoint { double vr, vt, vp, cvr, dvrdr, dvtdr, dvpdr, dvrdt, dvrdp, dv
 
 // boundary values of transform_to_grid_space with lDeriv = .true. (rIter.f90:555-602, v_rigid_boundary nonlinear_bcs.f90:120-175);
 // applies to point values and to phi means alike (the overrides do not depend on phi)
-__device__ __forceinline__ void diag_override(const DiagArgs &a, const LevelInfo &L, double st, double ct, double &vr, double &vt, double &vp,
-                                              double &cvr) {
+__device__ __forceinline__ void diag_override_raw(const LevelInfo &L, double omega_ma, double omega_ic, double r_cmb, double r_icb, double st,
+                                                  double ct, double &vr, double &vt, double &vp, double &cvr) {
     if (L.nBc == 1) vr = 0.0;
     if (L.nBc == 2) {
-        const double r2 = (L.nR == 1) ? a.r_cmb * a.r_cmb : a.r_icb * a.r_icb;
-        const double om = (L.nR == 1) ? a.omega_ma : a.omega_ic;
+        const double r2 = (L.nR == 1) ? r_cmb * r_cmb : r_icb * r_icb;
+        const double om = (L.nR == 1) ? omega_ma : omega_ic;
         vr = 0.0;
         vt = 0.0;
         vp = r2 * L.rho0 * (st * st) * om;
         cvr = r2 * L.rho0 * 2.0 * ct * om;
     }
+}
+__device__ __forceinline__ void diag_override(const DiagArgs &a, const LevelInfo &L, double st, double ct, double &vr, double &vt, double &vp,
+                                              double &cvr) {
+    diag_override_raw(L, a.omega_ma, a.omega_ic, a.r_cmb, a.r_icb, st, ct, vr, vt, vp, cvr);
 }
 
 // the sums of one grid point; h = 0 north, 1 south; ct carries the hemisphere sign; m[] = phi means of this hemisphere
@@ -369,6 +373,182 @@ __global__ void __launch_bounds__(DIAG_THREADS) dtb_product_kernel(DtbArgs a) {
             base[0] = pn[q] + ps[q];
             base[plane] = pn[q] - ps[q];
         }
+    }
+}
+
+}  // namespace magic
+
+// ------------------------------------------------------------------------------------------------------
+// Torsional-oscillation sums (rIter.f90:395-404): getTOnext's grid part (TO.f90:330-343) keeps Bs, Bp/s-normalised and Bz of the
+// previous step for every level; getTO (TO.f90:141-307) forms, per level and colatitude, the azimuthal means of some twenty
+// products of (vr, vt, vp, cvr, dvpdr, br, bt, bp, cbr, cbt, phi) and combines them into fifteen (r, theta) arrays.  One CTA per
+// (colatitude pair, level): both hemispheres from one read of the E/O rows, fixed-shape reductions, bitwise repeatable.
+namespace magic {
+
+struct ToIn { int vr, vt, vp, cvr, dvpdr, br, bt, bp, cbr, cbt, phi; };
+constexpr int TO_NF = 11;
+constexpr int TO_NOUT = 15;      // = MAGIC_NTO
+constexpr int TO_NSUM = 20;
+constexpr int TO_THREADS = 128;
+
+enum ToSlot { TO_V2AS = 0, TO_VAS, TO_DZCOR, TO_DZRSTR, TO_DZASTR, TO_DZLF, TO_BS2, TO_BSP, TO_BPZ, TO_BSZ, TO_BSPD, TO_BPSD, TO_BZPD, TO_BPZD,
+              TO_DZPEN };
+
+struct ToArgs {
+    ToIn ti;
+    const double *gin;
+    int n_lev, nh, n_phi, n_theta;
+    int l_mag, l_phase_field;
+    double omega_ma, omega_ic, r_cmb, r_icb, CorFac, pen, o_dtLast;  // pen = 1 / (epsPhase penaltyFac)^2
+    const LevelInfo *lev;
+    const double *sinth, *costh;
+    double *last;   // [n_lev][3 (Bs, Bp, Bz)][2 (north, south)][nh][n_phi] of the chunk's first level on
+    double *out;    // [n_lev][TO_NOUT][n_theta], colatitudes ordered north -> south (n_theta_cal2ord)
+};
+
+// cylindrical components the time derivatives are built from (TO.f90:243-246, :332-337)
+__device__ __forceinline__ void to_bsbpbz(const LevelInfo &L, double st, double ct, double br, double bt, double bp, double &bs, double &bpl,
+                                          double &bz) {
+    bs = st * L.or2 * br + ct / st * L.or1 * bt;
+    bpl = L.or1 * bp / st;
+    bz = ct * L.or2 * br - L.or1 * bt;
+}
+
+__global__ void __launch_bounds__(DIAG_THREADS) to_next_kernel(ToArgs a) {
+    const int lev = blockIdx.y;
+    const LevelInfo L = a.lev[lev];
+    const size_t plane = (size_t)a.nh * a.n_phi;
+    for (unsigned pt = blockIdx.x * blockDim.x + threadIdx.x; pt < (unsigned)plane; pt += gridDim.x * blockDim.x) {
+        const int k = (int)(pt / (unsigned)a.n_phi);
+        const double st = a.sinth[k], ct = a.costh[k];
+        const int fi[3] = {a.ti.br, a.ti.bt, a.ti.bp};
+        double e[3], o[3];
+#pragma unroll
+        for (int f = 0; f < 3; f++) {
+            const double *base = a.gin + (((size_t)fi[f] * a.n_lev + lev) * 2) * plane + pt;
+            e[f] = __ldg(base);
+            o[f] = __ldg(base + plane);
+        }
+        double *dst = a.last + (size_t)lev * 6 * plane + pt;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            double bs, bp, bz;
+            to_bsbpbz(L, st, h ? -ct : ct, h ? e[0] - o[0] : e[0] + o[0], h ? e[1] - o[1] : e[1] + o[1], h ? e[2] - o[2] : e[2] + o[2], bs, bp, bz);
+            dst[(size_t)(0 * 2 + h) * plane] = bs;
+            dst[(size_t)(1 * 2 + h) * plane] = bp;
+            dst[(size_t)(2 * 2 + h) * plane] = bz;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TO_THREADS) to_kernel(ToArgs a) {
+    const int k = blockIdx.x, lev = blockIdx.y;
+    const LevelInfo L = a.lev[lev];
+    const size_t plane = (size_t)a.nh * a.n_phi;
+    const double st = a.sinth[k], ctn = a.costh[k];
+    const double or1 = L.or1, or2 = L.or2, or3 = L.or1 * L.or2, or4 = L.or4, orho1 = L.orho1, beta = L.beta;
+    double acc[2][TO_NSUM];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int i = 0; i < TO_NSUM; i++) acc[h][i] = 0.0;
+    const int *fidx = &a.ti.vr;
+    for (int j = threadIdx.x; j < a.n_phi; j += TO_THREADS) {
+        const size_t pt = (size_t)k * a.n_phi + j;
+        double e[TO_NF], o[TO_NF];
+#pragma unroll
+        for (int f = 0; f < TO_NF; f++) {
+            e[f] = 0.0;
+            o[f] = 0.0;
+            if (fidx[f] >= 0) {
+                const double *base = a.gin + (((size_t)fidx[f] * a.n_lev + lev) * 2) * plane + pt;
+                e[f] = __ldg(base);
+                o[f] = __ldg(base + plane);
+            }
+        }
+        double lastv[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (a.l_mag) {
+            const double *src = a.last + (size_t)lev * 6 * plane + pt;
+#pragma unroll
+            for (int q = 0; q < 6; q++) lastv[q] = __ldg(src + (size_t)q * plane);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const double ct = h ? -ctn : ctn;
+            double v[TO_NF];
+#pragma unroll
+            for (int f = 0; f < TO_NF; f++) v[f] = h ? e[f] - o[f] : e[f] + o[f];
+            double vr = v[0], vt = v[1], vp = v[2], cvr = v[3];
+            const double dvpdr = v[4], br = v[5], bt = v[6], bp = v[7], cbr = v[8], cbt = v[9], phi = v[10];
+            diag_override_raw(L, a.omega_ma, a.omega_ic, a.r_cmb, a.r_icb, st, ct, vr, vt, vp, cvr);
+            double *s = acc[h];
+            s[0] += vr; s[1] += vt; s[2] += vp;
+            s[3] += vr * vr; s[4] += vt * vt; s[5] += vp * vp;
+            s[6] += orho1 * (dvpdr - beta * vp);
+            s[7] += cvr;
+            s[8] += orho1 * vr * (dvpdr - beta * vp);
+            s[9] += orho1 * vt * cvr;
+            if (a.l_phase_field) s[10] += phi * vp;
+            if (a.l_mag) {
+                const double os = 1.0 / st, os2 = os * os;
+                const double Bs2F1 = st * st * or4, Bs2F2 = ct * ct * os2 * or2, Bs2F3 = 2.0 * ct * or3, BspF2 = ct * os2 * or2;
+                const double BpzF1 = ct * os * or3, BpzF2 = or2 * os, BszF1 = st * ct * or4, BszF2 = (2.0 * ct * ct - 1.0) * os * or3,
+                             BszF3 = ct * os * or2;
+                s[11] += cbr * bt - cbt * br;
+                s[12] += Bs2F1 * br * br + Bs2F2 * bt * bt + Bs2F3 * br * bt;
+                s[13] += or3 * br * bp + BspF2 * bt * bp;
+                s[14] += BpzF1 * br * bp - BpzF2 * bt * bp;
+                s[15] += BszF1 * br * br + BszF2 * br * bt - BszF3 * bt * bt;
+                double BsL, BpL, BzL;
+                to_bsbpbz(L, st, ct, br, bt, bp, BsL, BpL, BzL);
+                const double BsO = lastv[0 * 2 + h], BpO = lastv[1 * 2 + h], BzO = lastv[2 * 2 + h];
+                s[16] += BsL * (BpL - BpO);
+                s[17] += BpL * (BsL - BsO);
+                s[18] += BzL * (BpL - BpO);
+                s[19] += BpL * (BzL - BzO);
+            }
+        }
+    }
+    __shared__ double red[TO_THREADS / 32][2 * TO_NSUM];
+    __shared__ double tot[2 * TO_NSUM];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int i = 0; i < TO_NSUM; i++) {
+            double v = acc[h][i];
+            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][h * TO_NSUM + i] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < 2 * TO_NSUM) {
+        double v = 0.0;
+        for (int w = 0; w < TO_THREADS / 32; w++) v += red[w][threadIdx.x];
+        tot[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const int h = threadIdx.x;
+        const double *s = tot + h * TO_NSUM;
+        const double ct = h ? -ctn : ctn, os = 1.0 / st, os2 = os * os, pn = 1.0 / (double)a.n_phi;
+        const int th = h ? a.n_theta - 1 - k : k;   // ordered colatitude index
+        double *o = a.out + (size_t)lev * TO_NOUT * a.n_theta + th;
+        const size_t nt = (size_t)a.n_theta;
+        const double VrMean = s[0], VtMean = s[1], dVpdrMean = s[6], cVrMean = s[7];
+        o[TO_V2AS * nt] = pn * or4 * s[3] + pn * or2 * os2 * s[4] + pn * or2 * os2 * s[5];
+        o[TO_VAS * nt] = orho1 * (pn * or1 * os * s[2]);
+        o[TO_DZCOR * nt] = -pn * 2.0 * a.CorFac * (or2 * st * VrMean + or1 * ct * os * VtMean);
+        o[TO_DZRSTR * nt] = -pn * or3 * os * (s[8] - pn * VrMean * dVpdrMean + s[9] - orho1 * pn * VtMean * cVrMean);
+        o[TO_DZASTR * nt] = -pn * or3 * os * pn * (VrMean * dVpdrMean + orho1 * VtMean * cVrMean);
+        o[TO_DZPEN * nt] = a.l_phase_field ? -pn * s[10] * or1 * os * a.pen : 0.0;
+        o[TO_DZLF * nt] = a.l_mag ? pn * or3 * os * s[11] : 0.0;
+        o[TO_BS2 * nt] = pn * s[12];
+        o[TO_BSP * nt] = pn * s[13];
+        o[TO_BPZ * nt] = pn * s[14];
+        o[TO_BSZ * nt] = pn * s[15];
+        o[TO_BSPD * nt] = pn * (s[16] * a.o_dtLast);
+        o[TO_BPSD * nt] = pn * (s[17] * a.o_dtLast);
+        o[TO_BZPD * nt] = pn * (s[18] * a.o_dtLast);
+        o[TO_BPZD * nt] = pn * (s[19] * a.o_dtLast);
     }
 }
 

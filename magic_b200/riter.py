@@ -33,6 +33,7 @@ RADIAL_NAMES = ["r", "or1", "or2", "or4", "orho1", "orho2", "beta", "rho0", "ote
 # magic_rloop_diagnostics: mask bits and slots (include/magic_sht.h)
 DIAG_HEL, DIAG_HEMI, DIAG_POWER, DIAG_PERPPAR, DIAG_FLUX, DIAG_VISCBC, DIAG_PHASE, DIAG_RMSBULK = 1, 2, 4, 8, 16, 32, 64, 256
 NDIAG = 40
+NTO = 15
 IN_NAMES = ["w", "dw", "ddw", "z", "dz", "s", "ds", "p", "xi", "b", "db", "ddb", "aj", "dj", "phi"]
 OUT_NAMES = ["dwdt", "dzdt", "dpdt", "dsdt", "dxidt", "dbdt", "djdt", "dVxVhLM", "dVxBhLM", "dVSrLM", "dVXirLM", "dphidt"]
 
@@ -158,6 +159,21 @@ class RadialLoop:
         out = np.zeros((11, self.n_r_loc, self.sht.lm_max), dtype=np.complex128)
         fn = self.lib.magic_rloop_dtb_dev if device else self.lib.magic_rloop_dtb
         check(fn(self._h, byref(fin), out.ctypes.data_as(c_void_p)))
+        return out
+
+    def to_next(self, fields, device=False):
+        """getTOnext's grid part (rIter.f90:395-398, TO.f90:330-343): keeps Bs, Bp, Bz of every local level on the device."""
+        fin, _, keep = self._structs(fields, {}, 0 if device else np.zeros(1), 0 if device else np.zeros(1), device=device)
+        fn = self.lib.magic_rloop_to_next_dev if device else self.lib.magic_rloop_to_next
+        check(fn(self._h, byref(fin)))
+
+    def to(self, fields, dtLast, device=False):
+        """getTO (rIter.f90:400-404, TO.f90:141-307) for this rank's levels: float64 [n_r_loc, NTO, n_theta_max], colatitudes north ->
+        south, arrays as documented in include/magic_sht.h."""
+        fin, _, keep = self._structs(fields, {}, 0 if device else np.zeros(1), 0 if device else np.zeros(1), device=device)
+        out = np.zeros((self.n_r_loc, NTO, self.sht.n_theta_max))
+        fn = self.lib.magic_rloop_to_dev if device else self.lib.magic_rloop_to
+        check(fn(self._h, byref(fin), c_double(dtLast), out.ctypes.data_as(c_void_p)))
         return out
 
     def graph_fields(self, fields, level, mag=False, pressure=False):

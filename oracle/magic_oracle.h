@@ -199,6 +199,12 @@ void orc_radial_diagnostics(const orc_ctx *c, const orc_params *p, const orc_rad
  * BpVtBtVpCotLM, BpVtBtVpSn2LM, BrVZLM, BtVZLM, BtVZsn2LM. */
 void orc_radial_dtB(const orc_ctx *c, const orc_params *p, const orc_radial *rad, int n_r, const orc_fields_in *in, orc_cplx *out);
 
+/* Torsional-oscillation sums (rIter.f90:395-404): mode 0 = getTOnext's grid part (TO.f90:330-343; fills last[n_r][3][n_phi][n_theta]
+ * = BsLast, BpLast, BzLast), mode 1 = getTO (TO.f90:141-307): out[n_r][15][n_theta], colatitudes unscrambled, arrays V2AS, VAS,
+ * dzCorAS, dzRstrAS, dzAstrAS, dzLFAS, Bs2AS, BspAS, BpzAS, BszAS, BspdAS, BpsdAS, BzpdAS, BpzdAS, dzPenAS. */
+void orc_radial_TO(const orc_ctx *c, const orc_params *p, const orc_radial *rad, int n_r, const orc_fields_in *in, int mode, double dtLast,
+                   double *last, double *out);
+
 /* get_nl only, on caller-provided grids (get_nl.f90:213-441): in/out arrays are [nphi][nlat] each.
  * in: vr vt vp cvr cvt cvp s br bt bp cbr cbt cbp (13) ; out: Advr Advt Advp LFr LFt LFp VSr VSt VSp
  * VxBr VxBt VxBp (12).  Provided so tests can check the grid-space kernel in isolation. */

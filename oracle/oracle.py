@@ -360,6 +360,38 @@ class Oracle:
         self.lib.orc_radial_dtB(self.h, C.byref(params), C.byref(rad), c_int(n_r), C.byref(fin), _p(out))
         return out
 
+    def radial_TO(self, params, radial, fields, mode, dtLast=1.0, last=None):
+        """rIter.f90:395-404.  mode 0: getTOnext's grid part (TO.f90:330-343), returns last = float64 [n_r, 3, n_phi, n_theta]
+        (BsLast, BpLast, BzLast); mode 1: getTO (TO.f90:141-307) with that `last`, returns float64 [n_r, 15, n_theta] (colatitudes
+        north -> south; V2AS, VAS, dzCorAS, dzRstrAS, dzAstrAS, dzLFAS, Bs2AS, BspAS, BpzAS, BszAS, BspdAS, BpsdAS, BzpdAS, BpzdAS,
+        dzPenAS)."""
+        n_r = len(radial["nR"])
+        keep = []
+        rad = _Radial()
+        for nm in ["nR", "l_R"]:
+            a = np.ascontiguousarray(radial[nm], dtype=np.int32)
+            keep.append(a)
+            setattr(rad, nm, _p(a))
+        for nm in _RAD_NAMES:
+            key = "lambda" if nm == "lambda_" else nm
+            a = np.ascontiguousarray(radial.get(key, np.ones(n_r)), dtype=np.float64)
+            keep.append(a)
+            setattr(rad, nm, _p(a))
+        fin = _FieldsIn()
+        for nm in _IN_NAMES:
+            if nm in fields and fields[nm] is not None:
+                a = self._c(fields[nm])
+                keep.append(a)
+                setattr(fin, nm, _p(a))
+        if last is None:
+            last = np.zeros((n_r, 3, self.n_phi, self.n_theta))
+        last = np.ascontiguousarray(last, dtype=np.float64)
+        assert last.shape == (n_r, 3, self.n_phi, self.n_theta)
+        out = np.zeros((n_r, 15, self.n_theta))
+        self.lib.orc_radial_TO(self.h, C.byref(params), C.byref(rad), c_int(n_r), C.byref(fin), c_int(mode), c_double(dtLast), _p(last),
+                               _p(out))
+        return last if mode == 0 else out
+
     def get_nl_mhd(self, params, nR, nBc, or2, or4, orho1, grids_in):
         """get_nl.f90:213-441 on 13 caller grids -> 12 product grids."""
         ins = [self._r(g) for g in grids_in]
