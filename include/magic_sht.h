@@ -190,6 +190,22 @@ int magic_rloop_to_next(magic_rloop *rl, const magic_fields_in *in);
 int magic_rloop_to_next_dev(magic_rloop *rl, const magic_fields_in *in);
 int magic_rloop_to(magic_rloop *rl, const magic_fields_in *in, double dtLast, double *out);
 int magic_rloop_to_dev(magic_rloop *rl, const magic_fields_in *in, double dtLast, double *out);
+/* R.m.s. force balance, the part inside the radial loop (l_RMS; rIter.f90:215-252, 433-435, 710; RMS.f90:469-610).
+ * On lRmsCalc steps the reference treats every level as bulk, synthesises grad p and all velocity gradients, forms fourteen more
+ * grid products per level (get_nl_RMS) and analyses them (transform_to_lm_RMS).  magic_rloop_rms does that for all local levels as
+ * one more batch on the transform kernels: out is a HOST complex array [MAGIC_NRMS][n_r_loc][lm_max] =
+ *   AdvrLM 0 (the merged radial advection compute_lm_forces receives, rIter.f90:650-688)   LFrLM 1   dtVrLM 2   dpkindrLM 3
+ *   Advt2LM 4   Advp2LM 5   LFt2LM 6   LFp2LM 7   CFt2LM 8   CFp2LM 9   PFt2LM 10   PFp2LM 11   dtVtLM 12   dtVpLM 13
+ * (module variables of RMS.f90; the spectral sums of compute_lm_forces, RMS.f90:612-863, stay with the host).  dt = tscheme%dt(1).
+ * get_nl_RMS keeps the previous step's velocity on the grid (vr_old, vt_old, vp_old, RMS.f90:545-551, updated at every stage-1
+ * call while l_RMS is on); here magic_rloop_rms_keep keeps its potentials w, dw, z on the DEVICE instead -- call it on every
+ * stage-1 step, after magic_rloop_rms on lRmsCalc steps.  in->p is needed (transform_to_grid_RMS).  Host field pointers; the _dev
+ * forms take device input pointers (out stays a host array).  Not for full-sphere runs, precession, centrifugal or phase-field terms. */
+#define MAGIC_NRMS 14
+int magic_rloop_rms_keep(magic_rloop *rl, const magic_fields_in *in);
+int magic_rloop_rms_keep_dev(magic_rloop *rl, const magic_fields_in *in);
+int magic_rloop_rms(magic_rloop *rl, const magic_fields_in *in, double dt, double *out);
+int magic_rloop_rms_dev(magic_rloop *rl, const magic_fields_in *in, double dt, double *out);
 /* get_dtBLM (rIter.f90:392-395, dtB.f90:144-223), what the loop contributes when l_dtB is on: the eleven grid
  * products of (vr, vt, vp, br, bt, bp) and their analyses (2 spat_to_sphertor + 7 scal_to_SH with lcut = l_max) for all local
  * levels, as one more batch on the Legendre GEMM / FFT kernels.  out: HOST complex [11][n_r_loc][lm_max] = BtVrLM, BpVrLM,

@@ -60,7 +60,7 @@ module magic_b200_c
 
    !-- magic_rloop_diagnostics: mask bits (include/magic_sht.h)
    integer(c_int), parameter :: MAGIC_DIAG_HEL = 1, MAGIC_DIAG_HEMI = 2, MAGIC_DIAG_POWER = 4, MAGIC_DIAG_PERPPAR = 8, &
-   &                            MAGIC_DIAG_FLUX = 16, MAGIC_DIAG_VISCBC = 32, MAGIC_DIAG_PHASE = 64, MAGIC_DIAG_RMSBULK = 256, MAGIC_NTO = 15
+   &                            MAGIC_DIAG_FLUX = 16, MAGIC_DIAG_VISCBC = 32, MAGIC_DIAG_PHASE = 64, MAGIC_DIAG_RMSBULK = 256, MAGIC_NTO = 15, MAGIC_NRMS = 14
 
    interface
 
@@ -343,6 +343,24 @@ module magic_b200_c
          real(c_double), intent(out) :: out(*)
          integer(c_int) :: ierr
       end function magic_rloop_to
+
+      !-- r.m.s. force balance (rIter.f90:215-252, 710; RMS.f90:469-610): out(lm_max, n_r_loc, MAGIC_NRMS), arrays as listed in
+      !   include/magic_sht.h; magic_rloop_rms_keep keeps the flow potentials of this step for the next call's dtV terms
+      function magic_rloop_rms_keep(rl, fin) bind(C, name='magic_rloop_rms_keep') result(ierr)
+         import :: c_int, c_ptr, magic_fields_in
+         type(c_ptr), value :: rl
+         type(magic_fields_in), intent(in) :: fin
+         integer(c_int) :: ierr
+      end function magic_rloop_rms_keep
+
+      function magic_rloop_rms(rl, fin, dt, out) bind(C, name='magic_rloop_rms') result(ierr)
+         import :: c_int, c_ptr, c_double, c_double_complex, magic_fields_in
+         type(c_ptr), value :: rl
+         type(magic_fields_in), intent(in) :: fin
+         real(c_double), value :: dt
+         complex(c_double_complex), intent(out) :: out(*)
+         integer(c_int) :: ierr
+      end function magic_rloop_rms
 
       !---------------------------------------------------------------- r <-> LM transposer
       function magic_transp_unique_id(id) bind(C, name='magic_transp_unique_id') result(ierr)

@@ -21,7 +21,7 @@ module rIter_cuda_mod
        &            l_adv_curl, l_corr, l_double_curl, l_single_matrix, l_chemical_conv, l_precession,      &
        &            l_centrifuge, l_anelastic_liquid, l_cour_alf_damp, l_full_sphere, l_parallel_solve,     &
        &            l_temperature_diff, l_cond_ma, l_cond_ic, l_rot_ma, l_rot_ic, l_b_nl_cmb, l_b_nl_icb,   &
-       &            l_phase_field, l_onset, l_dtB, l_dtphaseMovie
+       &            l_phase_field, l_onset, l_dtB, l_dtphaseMovie, l_RMS
    use special, only: lGrenoble
    use physical_parameters, only: ktopv, kbotv, n_r_LCR, LFfac, CorFac, epsc, epscXi, opm, ViscHeatFac,     &
        &                          OhmLossFac, oek, po, prec_angle, dilution_fac, ra, opr, ktops, kbots,     &
@@ -32,6 +32,10 @@ module rIter_cuda_mod
    use outMisc_mod, only: HelASr, Hel2ASr, HelnaASr, Helna2ASr, HelEAASr, hemi_ekin_r, hemi_vrabs_r,        &
        &                  hemi_emag_r, hemi_brabs_r, ekinSr, ekinLr, volSr, phase_Rloc, temp_Rloc, dtemp_Rloc
    use power, only: viscASr
+   !-- r.m.s. force balance: the spectra transform_to_lm_RMS fills (module variables of RMS, to be made public there) and the
+   !   routine that consumes them
+   use RMS, only: compute_lm_forces, dtVrLM, dtVtLM, dtVpLM, dpkindrLM, Advt2LM, Advp2LM, PFt2LM, PFp2LM, LFt2LM, LFp2LM,     &
+       &          CFt2LM, CFp2LM, LFrLM
    !-- torsional oscillations: the (r,theta) arrays getTO fills, and the routines that hold the spectral part
    use torsional_oscillations, only: prep_TO_axi, getTOnext, getTOfinish, V2AS_Rloc, VAS_Rloc, dzCorAS_Rloc, dzRstrAS_Rloc,   &
        &                             dzAstrAS_Rloc, dzLFAS_Rloc, Bs2AS_Rloc, BspAS_Rloc, BpzAS_Rloc, BszAS_Rloc, BspdAS_Rloc, &
@@ -228,17 +232,40 @@ contains
       type(magic_lm_in)      :: lin
       type(magic_lm_out)     :: lout
       integer :: ist, mask, nR
-      logical :: l_diag
+      logical :: l_diag, l_rms_dev
       real(c_double), allocatable :: dg(:,:)
       real(cp), allocatable :: grd(:,:)
       real(c_double), allocatable :: tq(:,:,:)
+      complex(c_double_complex), allocatable :: rq(:,:,:)
       complex(c_double_complex), allocatable :: dtb(:,:,:)
+
+      !-- Inputs: the R-distributed containers of fields.f90:211-268, (lm_max, nRstart:nRstop) each; the library
+      !   ignores the pointers of switched-off physics
+      fin = magic_fields_in(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
+      &                     c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
+      &                     c_null_ptr)
+      if ( l_phase_field ) fin%phi = c_loc(phi_Rloc)
+      if ( l_conv .or. l_mag_kin ) then
+         fin%w = c_loc(w_Rloc);  fin%dw = c_loc(dw_Rloc);  fin%ddw = c_loc(ddw_Rloc)
+         fin%z = c_loc(z_Rloc);  fin%dz = c_loc(dz_Rloc)
+      end if
+      if ( l_heat ) then
+         fin%s = c_loc(s_Rloc);  fin%ds = c_loc(ds_Rloc)
+      end if
+      if ( l_chemical_conv ) fin%xi = c_loc(xi_Rloc)
+      if ( l_mag .or. l_mag_LF ) then
+         fin%b  = c_loc(b_Rloc);   fin%db = c_loc(db_Rloc);  fin%ddb = c_loc(ddb_Rloc)
+         fin%aj = c_loc(aj_Rloc);  fin%dj = c_loc(dj_Rloc)
+      end if
+
+      !-- l_RMS on the device unless the advection carries terms the RMS batch does not form
+      l_rms_dev = l_RMS .and. .not. ( l_full_sphere .or. l_precession .or. l_centrifuge .or. l_phase_field )
 
       !-- Log steps: get_helicity, get_hemi, get_visc_heat, get_perpPar, get_fluxes, get_nlBLayers and get_ekin_solid_liquid
       !   (rIter.f90:320-367) and the torsional-oscillation sums (getTOnext / getTO, rIter.f90:395-404) are evaluated on the device
       !   after the batched loop (below).  The remaining output hooks keep the reference's level-at-a-time loop (its transforms
       !   still run on the GPU)
-      if ( l_graph .or. l_frame .or. lRmsCalc .or. lPressCalc .or.                                         &
+      if ( l_graph .or. l_frame .or. ( l_RMS .and. .not. l_rms_dev ) .or.                                    &
       &    ( l_full_sphere .and. ( lTOCalc .or. lTONext .or. lTONext2 ) ) .or.                               &
       &    lGeosCalc .or. l_probe_out .or. ( lPressNext .and. l_double_curl ) .or.                           &
       &    ( l_full_sphere .and. ( lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or.        &
@@ -250,11 +277,18 @@ contains
             l_outputs_in_lm = .false.
          end if
          call this%single%radialLoop(l_graph,l_frame,time,timeStage,tscheme,dtLast,lTOCalc,lTONext,lTONext2,   &
-              &                      lHelCalc,lPowerCalc,lRmsCalc,lPressCalc,lPressNext,lViscBcCalc,           &
+              &                      lHelCalc,lPowerCalc,lRmsCalc .and. .not. l_rms_dev,lPressCalc,lPressNext, &
+              &                      lViscBcCalc,                                                              &
               &                      lFluxProfCalc,lPerpParCalc,lGeosCalc,lHemiCalc,lPhaseCalc,l_probe_out,    &
               &                      dsdt,dwdt,dzdt,dpdt,dxidt,dphidt,dbdt,djdt,dVxVhLM,dVxBhLM,dVSrLM,dVXirLM,&
               &                      lorentz_torque_ic,lorentz_torque_ma,br_vt_lm_cmb,br_vp_lm_cmb,            &
               &                      br_vt_lm_icb,br_vp_lm_icb,dtrkc,dthkc)
+         !-- the r.m.s. batch of this step still runs on the device (with lRmsCalc off the host loop's get_nl_RMS only refreshes
+         !   its own copy of the previous velocity): one owner of vr_old on every step
+         if ( l_rms_dev ) then
+            if ( .not. c_associated(this%rl) ) call this%create_plan(tscheme)
+            call rms_on_device()
+         end if
          return
       end if
 
@@ -264,7 +298,7 @@ contains
       !   this call (step_time.f90:485, :612) are part of it (mpi_transp_cuda_mod); the explicit terms go into the slice
       !   tscheme%istage of the time-array containers, which is where transp_Rloc_to_LMloc would put them (step_time.f90:1134-1245)
       l_diag = lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lHemiCalc .or. lPhaseCalc &
-      &        .or. lTOCalc .or. lTONext .or. lTONext2
+      &        .or. lTOCalc .or. lTONext .or. lTONext2 .or. l_RMS
       if ( l_fused_lm .and. n_pending > 0 .and. .not. ( l_b_nl_cmb .or. l_b_nl_icb .or. l_diag .or. l_dtB .or. l_phase_field ) ) then
          ist = tscheme%istage
          lin  = magic_lm_in(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr)
@@ -289,25 +323,6 @@ contains
       if ( l_fused_lm ) then   ! (nonlinear magnetic boundary products need the R-distributed path: rIter.f90:267-277)
          call run_pending_lm2r()
          l_outputs_in_lm = .false.
-      end if
-
-      !-- Inputs: the R-distributed containers of fields.f90:211-268, (lm_max, nRstart:nRstop) each; the library
-      !   ignores the pointers of switched-off physics
-      fin = magic_fields_in(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
-      &                     c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
-      &                     c_null_ptr)
-      if ( l_phase_field ) fin%phi = c_loc(phi_Rloc)
-      if ( l_conv .or. l_mag_kin ) then
-         fin%w = c_loc(w_Rloc);  fin%dw = c_loc(dw_Rloc);  fin%ddw = c_loc(ddw_Rloc)
-         fin%z = c_loc(z_Rloc);  fin%dz = c_loc(dz_Rloc)
-      end if
-      if ( l_heat ) then
-         fin%s = c_loc(s_Rloc);  fin%ds = c_loc(ds_Rloc)
-      end if
-      if ( l_chemical_conv ) fin%xi = c_loc(xi_Rloc)
-      if ( l_mag .or. l_mag_LF ) then
-         fin%b  = c_loc(b_Rloc);   fin%db = c_loc(db_Rloc);  fin%ddb = c_loc(ddb_Rloc)
-         fin%aj = c_loc(aj_Rloc);  fin%dj = c_loc(dj_Rloc)
       end if
 
       fout = magic_fields_out(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
@@ -364,9 +379,8 @@ contains
          deallocate( dtb )
       end if
 
-      !-- rIter.f90:320-367 on log steps: one call returns the per-level sums of all requested routines; they go where the
-      !   reference's routines store them (the arrays below are module variables of outMisc_mod, power and outPar_mod, to be
-      !   made public there: HelASr .. HelEAASr, hemi_*_r, viscASr, EperpASr .. EparaxiASr, fkinASr .. fpoynASr, uhASr ..)
+      if ( l_rms_dev ) call rms_on_device()
+
       !-- rIter.f90:220-222, 395-404, 438 on torsional-oscillation steps: the grid part of getTOnext (Bs, Bp, Bz of the step before
       !   the output) stays on the device, getTO's azimuthal means come back as (theta, array, level); the spectral, axisymmetric
       !   part (prep_TO_axi, getTOnext's dzdVp / dzddVp bookkeeping, getTOfinish) is the reference's own code, level by level --
@@ -399,6 +413,9 @@ contains
          if ( lTOCalc ) deallocate( tq )
       end if
 
+      !-- rIter.f90:320-367 on log steps: one call returns the per-level sums of all requested routines; they go where the
+      !   reference's routines store them (the arrays below are module variables of outMisc_mod, power and outPar_mod, to be
+      !   made public there: HelASr .. HelEAASr, hemi_*_r, viscASr, EperpASr .. EparaxiASr, fkinASr .. fpoynASr, uhASr ..)
       if ( l_diag .and. ( lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lHemiCalc .or. &
       &                   lPhaseCalc ) ) then
          mask = 0
@@ -407,6 +424,7 @@ contains
          if ( lPowerCalc )    mask = mask + MAGIC_DIAG_POWER
          if ( lPerpParCalc )  mask = mask + MAGIC_DIAG_PERPPAR
          if ( lFluxProfCalc ) mask = mask + MAGIC_DIAG_FLUX
+         if ( lRmsCalc )      mask = mask + MAGIC_DIAG_RMSBULK   ! boundary levels are bulk levels on these steps (rIter.f90:215)
          if ( lViscBcCalc )   mask = mask + MAGIC_DIAG_VISCBC
          if ( lPhaseCalc )    mask = mask + MAGIC_DIAG_PHASE
          if ( lFluxProfCalc ) fin%p = c_loc(p_Rloc)    ! lPressCalc is set with lFluxProfCalc (step_time.f90:399)
@@ -464,6 +482,32 @@ contains
             deallocate( grd )
          end if
       end if
+
+   contains
+
+      subroutine rms_on_device()
+         !-- l_RMS (rIter.f90:215-252, 433-435, 710): on lRmsCalc steps one more batch returns the fourteen spectra of
+         !   transform_to_lm_RMS for all levels (every level treated as bulk, as rIter.f90:215 does); they go into RMS's module arrays
+         !   level by level and compute_lm_forces -- the reference's own spectral sums -- runs on them.  get_nl_RMS keeps the previous
+         !   step's velocity on the grid at every stage-1 call; here its potentials stay on the device (magic_rloop_rms_keep)
+         if ( l_rms_dev ) then
+            if ( lRmsCalc ) then
+               allocate( rq(lm_max,nRstart:nRstop,MAGIC_NRMS) )
+               fin%p = c_loc(p_Rloc)
+               call magic_check( magic_rloop_rms(this%rl, fin, real(tscheme%dt(1),c_double), rq), 'magic_rloop_rms' )
+               do nR=nRstart,nRstop
+                  LFrLM(:)  =rq(:,nR,2);   dtVrLM(:) =rq(:,nR,3)
+                  if ( l_adv_curl ) dpkindrLM(:)=rq(:,nR,4)
+                  Advt2LM(:)=rq(:,nR,5);   Advp2LM(:)=rq(:,nR,6);   LFt2LM(:)=rq(:,nR,7);    LFp2LM(:)=rq(:,nR,8)
+                  CFt2LM(:) =rq(:,nR,9);   CFp2LM(:) =rq(:,nR,10);  PFt2LM(:)=rq(:,nR,11);   PFp2LM(:)=rq(:,nR,12)
+                  dtVtLM(:) =rq(:,nR,13);  dtVpLM(:) =rq(:,nR,14)
+                  call compute_lm_forces(nR, rq(:,nR,1))
+               end do
+               deallocate( rq )
+            end if
+            if ( tscheme%istage == 1 ) call magic_check( magic_rloop_rms_keep(this%rl, fin), 'magic_rloop_rms_keep' )
+         end if
+      end subroutine rms_on_device
 
    end subroutine radialLoop
 !------------------------------------------------------------------------------

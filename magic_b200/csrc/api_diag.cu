@@ -487,3 +487,175 @@ extern "C" int magic_rloop_to_next(magic_rloop *rl, const magic_fields_in *in) {
 extern "C" int magic_rloop_to_next_dev(magic_rloop *rl, const magic_fields_in *in) { return to_run(rl, in, 0, 0.0, nullptr, false); }
 extern "C" int magic_rloop_to(magic_rloop *rl, const magic_fields_in *in, double dtLast, double *out) { return to_run(rl, in, 1, dtLast, out, true); }
 extern "C" int magic_rloop_to_dev(magic_rloop *rl, const magic_fields_in *in, double dtLast, double *out) { return to_run(rl, in, 1, dtLast, out, false); }
+
+// ------------------------------------------------------------------------------------------------------
+// R.m.s. force balance (l_RMS; rIter.f90:215-252, 433-435, 710; RMS.f90:469-610).  On lRmsCalc steps the reference
+// treats every level as bulk, synthesises the pressure gradient and all velocity gradients, forms fourteen more grid products per
+// level (get_nl_RMS) and analyses them (transform_to_lm_RMS: 4 scal_to_SH + 5 spat_to_sphertor).  Here: one more column program
+// on the batched pipeline -- up to 24 synthesised fields, rms_kernel, 14 analysed fields.  The velocity of the previous step, which
+// get_nl_RMS keeps on the grid (vr_old ..., RMS.f90:545-551), is kept as its three potentials instead (magic_rloop_rms_keep: w, dw,
+// z of every local level on the DEVICE) and synthesised with the rest.  out: HOST complex [MAGIC_NRMS][n_r_loc][lm_max] in the order
+// AdvrLM, LFrLM, dtVrLM, dpkindrLM, Advt2LM, Advp2LM, LFt2LM, LFp2LM, CFt2LM, CFp2LM, PFt2LM, PFp2LM, dtVtLM, dtVpLM; the spectral
+// sums of compute_lm_forces (RMS.f90:612-863) stay with the host.
+static const int S_WOLD = S_XI, S_DWOLD = S_DS, S_ZOLD = S_PHI;  // source slots this column program does not use otherwise
+
+struct RmsPipe {
+    int chunk = 0, gx = 0;
+    BatchSpec spec;
+    RmsIn ri;
+    Layout lay;
+    Buffers buf;
+    LevelInfo *d_lev = nullptr;          // nBc = 0, lDeriv = 1 everywhere (rIter.f90:215)
+    double *d_old[3] = {nullptr};        // w, dw, z of the previous stage-1 call: complex [n_r_loc][lm_max]
+    double *d_src[S_COUNT] = {nullptr};
+    bool need[S_COUNT] = {false};
+    bool have_old = false;
+};
+
+static void rms_free(RmsPipe *d) {
+    if (!d) return;
+    layout_free(d->lay);
+    buffers_free(d->buf);
+    cudaFree(d->d_lev);
+    for (int i = 0; i < 3; i++) cudaFree(d->d_old[i]);
+    for (int i = 0; i < S_COUNT; i++) cudaFree(d->d_src[i]);
+    delete d;
+}
+
+static int rms_build(magic_rloop *rl) {
+    magic_sht *h = rl->h;
+    const magic_params &P = rl->p;
+    if (P.l_full_sphere) MFAIL("magic_rloop_rms: full-sphere runs are not supported");
+    if (!(P.l_conv || P.l_mag_kin)) MFAIL("magic_rloop_rms: needs a flow (l_conv or l_mag_kin)");
+    if (P.l_precession || P.l_centrifuge || P.l_phase_field)
+        MFAIL("magic_rloop_rms: precession, centrifugal and phase-field terms of the advection are not part of this column program");
+    RmsPipe *d = new RmsPipe();
+    rl->rms = d;
+    BatchSpec &S = d->spec;
+    int *rip = (int *)&d->ri;
+    for (int i = 0; i < RMS_NF; i++) rip[i] = -1;
+    RmsIn &ri = d->ri;
+    const Term N_ = {0, F_NONE};
+    int nf = 0;
+    auto need = [&](std::initializer_list<int> s) { for (int i : s) d->need[i] = true; };
+    need({S_W, S_DW, S_DDW, S_Z, S_DZ, S_P});
+    add_scal(S, Term{S_W, F_DLH}, N_, LM_ALL, nf, ri.vr);
+    add_pair(S, Term{S_DW, F_ONE}, N_, Term{S_Z, F_ONE}, N_, LM_ALL, nf, ri.vt, ri.vp);
+    add_scal(S, Term{S_DW, F_DLH}, N_, LM_ALL, nf, ri.dvrdr);
+    add_pair(S, Term{S_DDW, F_ONE}, N_, Term{S_DZ, F_ONE}, N_, LM_ALL, nf, ri.dvtdr, ri.dvpdr);
+    add_scal(S, Term{S_Z, F_DLH}, N_, LM_ALL, nf, ri.cvr);
+    if (P.l_adv_curl) add_pair(S, Term{S_DZ, F_ONE}, N_, Term{S_W, F_OR2DLH}, Term{S_DDW, F_NEG}, LM_ALL, nf, ri.cvt, ri.cvp);
+    add_pair(S, Term{S_W, F_DLH}, N_, N_, N_, LM_ALL, nf, ri.dvrdt, ri.dvrdp);
+    add_pair(S, Term{S_DW, F_IM}, N_, Term{S_Z, F_IM}, N_, LM_ALL, nf, ri.dvtdp, ri.dvpdp);
+    if (P.l_mag || P.l_mag_LF) {
+        need({S_B, S_DB, S_DDB, S_AJ, S_DJ});
+        add_scal(S, Term{S_B, F_DLH}, N_, LM_ALL, nf, ri.br);
+        add_pair(S, Term{S_DB, F_ONE}, N_, Term{S_AJ, F_ONE}, N_, LM_ALL, nf, ri.bt, ri.bp);
+        add_scal(S, Term{S_AJ, F_DLH}, N_, LM_ALL, nf, ri.cbr);
+        add_pair(S, Term{S_DJ, F_ONE}, N_, Term{S_B, F_OR2DLH}, Term{S_DDB, F_NEG}, LM_ALL, nf, ri.cbt, ri.cbp);
+    }
+    add_pair(S, Term{S_P, F_ONE}, N_, N_, N_, LM_ALL, nf, ri.dpdt, ri.dpdp);                              // transform_to_grid_RMS
+    add_scal(S, Term{S_WOLD, F_DLH}, N_, LM_ALL, nf, ri.vro);
+    add_pair(S, Term{S_DWOLD, F_ONE}, N_, Term{S_ZOLD, F_ONE}, N_, LM_ALL, nf, ri.vto, ri.vpo);
+    S.nfield_in = nf;
+    S.afield_s = {0, 1, 2, 3};
+    S.afield_vt = {4, 6, 8, 10, 12};
+    S.afield_vp = {5, 7, 9, 11, 13};
+    S.nfield_out = RMS_NOUT;
+    const size_t lm2 = 2 * (size_t)h->lm_max;
+    for (int i = 0; i < 3; i++) MCHECK(cudaMalloc((void **)&d->d_old[i], sizeof(double) * lm2 * (size_t)rl->n_r_loc));
+    size_t free_b = 0, total_b = 0;
+    MCHECK(cudaMemGetInfo(&free_b, &total_b));
+    const double per_level = 2.2 * 8.0 * (double)h->n_theta * h->n_phi * (nf + RMS_NOUT) + 64.0 * h->lm_max * (S_COUNT + RMS_NOUT);
+    int chunk = (int)std::min<double>(32.0, 0.5 * (double)free_b / per_level);
+    chunk = std::max(1, std::min(chunk, rl->n_r_loc));
+    d->chunk = chunk;
+    layout_sizes(h, S, chunk, d->lay);
+    if (buffers_alloc(h, S, d->lay, d->buf)) return 1;
+    if (layout_bind(h, S, d->lay, d->buf)) return 1;
+    std::vector<LevelInfo> lev = rl->lev;
+    for (auto &L : lev) { L.lDeriv = 1; L.nBc = 0; }
+    if (dev_upload_vec(&d->d_lev, lev)) return 1;
+    const size_t plane = (size_t)h->nh * h->n_phi;
+    d->gx = (int)std::min<size_t>((plane + DIAG_THREADS - 1) / DIAG_THREADS, 8 * 148);
+    return 0;
+}
+
+// keeps w, dw, z of all local levels (the reference's vr_old, vt_old, vp_old of RMS.f90:549-551, in spectral form)
+static int rms_keep(magic_rloop *rl, const magic_fields_in *in, bool host_in) {
+    if (!rl || !in) MFAIL("magic_rloop_rms_keep: null argument");
+    magic_sht *h = rl->h;
+    MCHECK(cudaSetDevice(h->dev));
+    if (!rl->rms)
+        if (rms_build(rl)) return 1;
+    RmsPipe *d = rl->rms;
+    if (!in->w || !in->dw || !in->z) MFAIL("magic_rloop_rms_keep: w, dw, z are needed");
+    const size_t bytes = sizeof(double) * 2 * (size_t)h->lm_max * (size_t)rl->n_r_loc;
+    const double *src[3] = {in->w, in->dw, in->z};
+    for (int i = 0; i < 3; i++)
+        MCHECK(cudaMemcpyAsync(d->d_old[i], src[i], bytes, host_in ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+    MCHECK(cudaStreamSynchronize(h->stream));
+    d->have_old = true;
+    return 0;
+}
+
+static int rms_run(magic_rloop *rl, const magic_fields_in *in, double dt, double *out, bool host_in) {
+    if (!rl || !in || !out) MFAIL("magic_rloop_rms: null argument");
+    magic_sht *h = rl->h;
+    MCHECK(cudaSetDevice(h->dev));
+    if (!rl->rms)
+        if (rms_build(rl)) return 1;
+    RmsPipe *d = rl->rms;
+    const magic_params &P = rl->p;
+    if (!d->have_old) MFAIL("magic_rloop_rms: no previous velocity kept (call magic_rloop_rms_keep on every stage-1 step while l_RMS is on)");
+    if (!(dt > 0.0)) MFAIL("magic_rloop_rms: dt must be positive");
+    const double *ip[S_COUNT];
+    in_ptrs(in, ip);
+    for (int i = 0; i < S_COUNT; i++)
+        if (d->need[i] && !ip[i]) MFAIL("magic_rloop_rms: a required input field is null (w, dw, ddw, z, dz, p and the magnetic potentials)");
+    const size_t lm2 = 2 * (size_t)h->lm_max;
+    const int nl = d->chunk, n_r = rl->n_r_loc;
+    if (host_in)
+        for (int i = 0; i < S_COUNT; i++)
+            if (d->need[i] && !d->d_src[i]) MCHECK(cudaMalloc((void **)&d->d_src[i], sizeof(double) * lm2 * nl));
+    RmsArgs a{};
+    a.ri = d->ri; a.gin = d->buf.gin; a.gout = d->buf.gout; a.n_lev = nl; a.nh = h->nh; a.n_phi = h->n_phi;
+    a.l_conv_nl = P.l_conv_nl; a.l_mag_LF = P.l_mag_LF; a.l_mag_nl = P.l_mag_nl; a.l_adv_curl = P.l_adv_curl; a.n_r_LCR = P.n_r_LCR;
+    a.LFfac = P.LFfac; a.CorFac = P.CorFac; a.o_dt = 1.0 / dt;
+    a.sinth = h->d_sinth; a.costh = h->d_costh;
+    for (int l0 = 0; l0 < n_r; l0 += nl) {
+        const int s0 = std::min(l0, n_r - nl);
+        const double *src[MAGIC_MAX_SRC];
+        for (int i = 0; i < MAGIC_MAX_SRC; i++) src[i] = nullptr;
+        for (int i = 0; i < S_COUNT; i++) {
+            if (!d->need[i]) continue;
+            if (host_in) {
+                MCHECK(cudaMemcpyAsync(d->d_src[i], ip[i] + (size_t)s0 * lm2, sizeof(double) * lm2 * nl, cudaMemcpyHostToDevice, h->stream));
+                src[i] = d->d_src[i];
+            } else {
+                src[i] = ip[i] + (size_t)s0 * lm2;
+            }
+        }
+        src[S_WOLD] = d->d_old[0] + (size_t)s0 * lm2;
+        src[S_DWOLD] = d->d_old[1] + (size_t)s0 * lm2;
+        src[S_ZOLD] = d->d_old[2] + (size_t)s0 * lm2;
+        if (run_synthesis(h, d->spec, d->lay, d->buf, src, d->d_lev + s0, nullptr)) return 1;
+        a.lev = d->d_lev + s0;
+        rms_kernel<<<dim3(d->gx, nl), DIAG_THREADS, 0, h->stream>>>(a);
+        h->launches++;
+        MCHECK(cudaGetLastError());
+        if (run_analysis(h, d->spec, d->lay, d->buf, d->d_lev + s0, nullptr, true)) return 1;
+        // nl_s: [4][nl][lm_max] -> out 0..3; nl_v: [S0, T0, ..., S4, T4][nl][lm_max] -> out 4..13
+        for (int q = 0; q < RMS_NOUT; q++) {
+            const double *srcq = q < 4 ? d->buf.nl_s + (size_t)q * nl * lm2 : d->buf.nl_v + (size_t)(q - 4) * nl * lm2;
+            MCHECK(cudaMemcpyAsync(out + ((size_t)q * n_r + s0) * lm2, srcq, sizeof(double) * lm2 * nl, cudaMemcpyDeviceToHost, h->stream));
+        }
+        MCHECK(cudaStreamSynchronize(h->stream));  // the result buffers are reused by the next chunk
+    }
+    return 0;
+}
+
+extern "C" int magic_rloop_rms_keep(magic_rloop *rl, const magic_fields_in *in) { return rms_keep(rl, in, true); }
+extern "C" int magic_rloop_rms_keep_dev(magic_rloop *rl, const magic_fields_in *in) { return rms_keep(rl, in, false); }
+extern "C" int magic_rloop_rms(magic_rloop *rl, const magic_fields_in *in, double dt, double *out) { return rms_run(rl, in, dt, out, true); }
+extern "C" int magic_rloop_rms_dev(magic_rloop *rl, const magic_fields_in *in, double dt, double *out) { return rms_run(rl, in, dt, out, false); }

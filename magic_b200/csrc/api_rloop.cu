@@ -34,6 +34,7 @@ struct magic_rloop {
     struct DiagPipe *diag = nullptr;  // log-step diagnostics (api_diag.cu), built on first use
     struct DtbPipe *dtb = nullptr;    // get_dtBLM batch (api_diag.cu), built on first use
     struct ToPipe *to = nullptr;      // torsional-oscillation sums (api_diag.cu), built on first use
+    struct RmsPipe *rms = nullptr;    // r.m.s. force balance batch (api_diag.cu), built on first use
     // LM-side prologue / epilogue: the host's radial scheme as dense matrices, radial functions on all levels
     std::vector<double> D1h, D2h, lmrad_h;  // [n_r][n_r] row-major x2; [4][n_r]: or2, orho1, dentropy0, l_R
     int n_r_mat = 0, lm_derivs = 0, lm_finish = 0;
@@ -127,6 +128,7 @@ static void lmpipe_free(struct LmPipe *p);
 static void diag_free(struct DiagPipe *d);
 static void dtb_free(struct DtbPipe *d);
 static void to_free(struct ToPipe *d);
+static void rms_free(struct RmsPipe *d);
 
 // Tapered variant for the pipelined multi-rank call: a short first and last chunk (`taper` levels each) so that the inbound
 // transpose of the first chunk and the outbound transpose of the last one -- the two that cannot hide under any compute --
@@ -202,6 +204,7 @@ extern "C" int magic_rloop_destroy(magic_rloop *rl) {
     diag_free(rl->diag);
     dtb_free(rl->dtb);
     to_free(rl->to);
+    rms_free(rl->rms);
     if (rl->h_torque) cudaFreeHost(rl->h_torque);
     for (int i = 0; i < 16; i++) cudaEventDestroy(rl->ev[i]);
     for (auto e : rl->up_done) cudaEventDestroy(e);

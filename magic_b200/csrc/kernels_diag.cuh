@@ -553,3 +553,109 @@ __global__ void __launch_bounds__(TO_THREADS) to_kernel(ToArgs a) {
 }
 
 }  // namespace magic
+
+// ------------------------------------------------------------------------------------------------------
+// R.m.s. force balance inside the radial loop on lRmsCalc steps (rIter.f90:215-252, 710): get_nl with every level treated as bulk
+// (get_nl.f90:242-310), get_nl_RMS (RMS.f90:469-560) and the merge of transform_to_lm_space (rIter.f90:650-667), fused into one
+// pass over the synthesised grid fields.  Writes the fourteen grid products transform_to_lm_RMS analyses, as (N+S, N-S) rows:
+//   0 Advr (merged)  1 LFr  2 dtVr  3 dpkindr  |  4,5 Advt2, Advp2  6,7 LFt2, LFp2  8,9 CFt2, CFp2  10,11 PFt, PFp  12,13 dtVt, dtVp
+namespace magic {
+
+struct RmsIn { int vr, vt, vp, dvrdr, dvtdr, dvpdr, cvr, cvt, cvp, dvrdt, dvrdp, dvtdp, dvpdp, br, bt, bp, cbr, cbt, cbp, dpdt, dpdp, vro, vto, vpo; };
+constexpr int RMS_NF = 24;
+constexpr int RMS_NOUT = 14;   // = MAGIC_NRMS
+
+struct RmsArgs {
+    RmsIn ri;
+    const double *gin;
+    double *gout;
+    int n_lev, nh, n_phi;
+    int l_conv_nl, l_mag_LF, l_mag_nl, l_adv_curl, n_r_LCR;
+    double LFfac, CorFac, o_dt;
+    const LevelInfo *lev;
+    const double *sinth, *costh;
+};
+
+__global__ void __launch_bounds__(DIAG_THREADS) rms_kernel(RmsArgs a) {
+    const int lev = blockIdx.y;
+    const LevelInfo L = a.lev[lev];
+    const size_t plane = (size_t)a.nh * a.n_phi;
+    const double r = L.r, or1 = L.or1, or2 = L.or2, or3 = L.or1 * L.or2, or4 = L.or4, orho1 = L.orho1, beta = L.beta;
+    const bool lf = a.l_mag_LF && L.nR > a.n_r_LCR;
+    const int *fidx = &a.ri.vr;
+    for (unsigned pt = blockIdx.x * blockDim.x + threadIdx.x; pt < (unsigned)plane; pt += gridDim.x * blockDim.x) {
+        const int k = (int)(pt / (unsigned)a.n_phi);
+        const double st = a.sinth[k], ctn = a.costh[k], os = 1.0 / st, os2 = os * os;
+        double e[RMS_NF], o[RMS_NF];
+#pragma unroll
+        for (int f = 0; f < RMS_NF; f++) {
+            e[f] = 0.0;
+            o[f] = 0.0;
+            if (fidx[f] >= 0) {
+                const double *base = a.gin + (((size_t)fidx[f] * a.n_lev + lev) * 2) * plane + pt;
+                e[f] = __ldg(base);
+                o[f] = __ldg(base + plane);
+            }
+        }
+        double res[2][RMS_NOUT];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const double ct = h ? -ctn : ctn, cn2 = ct * os2;
+            double v[RMS_NF];
+#pragma unroll
+            for (int f = 0; f < RMS_NF; f++) v[f] = h ? e[f] - o[f] : e[f] + o[f];
+            const double vr = v[0], vt = v[1], vp = v[2], dvrdr = v[3], dvtdr = v[4], dvpdr = v[5], cvr = v[6], cvt = v[7], cvp = v[8], dvrdt = v[9],
+                         dvrdp = v[10], dvtdp = v[11] * os2, dvpdp = v[12] * os2,  // torpol_to_dphspat post-scaling, sht_native.f90:263-270
+                         br = v[13], bt = v[14], bp = v[15], cbr = v[16], cbt = v[17], cbp = v[18];
+            double LFr = 0.0, LFt = 0.0, LFp = 0.0, Ar = 0.0, At = 0.0, Ap = 0.0;
+            if (lf) {
+                LFr = a.LFfac * os2 * (cbt * bp - cbp * bt);
+                LFt = a.LFfac * or4 * (cbp * br - cbr * bp);
+                LFp = a.LFfac * or4 * (cbr * bt - cbt * br);
+            }
+            if (a.l_conv_nl) {
+                if (a.l_adv_curl) {
+                    Ar = -os2 * (cvt * vp - cvp * vt);
+                    At = -or4 * (cvp * vr - cvr * vp);
+                    Ap = -or4 * (cvr * vt - cvt * vr);
+                } else {
+                    Ar = -or2 * orho1 * (vr * (dvrdr - (2.0 * or1 + beta) * vr) + os2 * (vt * (dvrdt - r * vt) + vp * (dvrdp - r * vp)));
+                    At = or4 * orho1 * (-vr * (dvtdr - beta * vt) + vt * (cn2 * vt + dvpdp + dvrdr) + vp * (cn2 * vp - dvtdp));
+                    Ap = or4 * orho1 * (-vr * (dvpdr - beta * vp) - vt * (dvtdp + cvr) - vp * dvpdp);
+                }
+            }
+            double *q = res[h];
+            double PFt = v[19] * or1, PFp = v[20] * or1;
+            q[8] = -2.0 * a.CorFac * ct * vp * or1;
+            q[9] = 2.0 * a.CorFac * st * (or1 * ct * os * vt + or2 * st * vr);
+            double At2 = a.l_conv_nl ? r * At : 0.0, Ap2 = a.l_conv_nl ? r * Ap : 0.0;
+            q[6] = (lf && a.l_mag_nl) ? r * LFt : 0.0;
+            q[7] = (lf && a.l_mag_nl) ? r * LFp : 0.0;
+            q[3] = 0.0;
+            if (a.l_adv_curl) {
+                const double X = or3 * (or2 * vr * dvrdt - vt * (dvrdr + dvpdp + cn2 * vt) + vp * (cvr + dvtdp - cn2 * vp));
+                const double Y = or3 * (or2 * vr * dvrdp + vt * dvtdp + vp * dvpdp);
+                PFt -= X;
+                PFp -= Y;
+                if (a.l_conv_nl) { At2 -= X; Ap2 -= Y; }
+                q[3] = or4 * vr * (dvrdr - 2.0 * or1 * vr) + or2 * os2 * (vt * (dvtdr - or1 * vt) + vp * (dvpdr - or1 * vp));
+            }
+            q[4] = At2; q[5] = Ap2; q[10] = PFt; q[11] = PFp;
+            q[2] = a.o_dt * or2 * (vr - v[21]);
+            q[12] = a.o_dt * or1 * (vt - v[22]);
+            q[13] = a.o_dt * or1 * (vp - v[23]);
+            if (a.l_conv_nl && a.l_mag_LF) { if (lf) Ar += LFr; }   // rIter.f90:650-667
+            else if (a.l_mag_LF) Ar = lf ? LFr : 0.0;
+            q[0] = Ar;
+            q[1] = LFr;
+        }
+#pragma unroll
+        for (int q = 0; q < RMS_NOUT; q++) {
+            double *base = a.gout + (((size_t)q * a.n_lev + lev) * 2) * plane + pt;
+            base[0] = res[0][q] + res[1][q];
+            base[plane] = res[0][q] - res[1][q];
+        }
+    }
+}
+
+}  // namespace magic

@@ -20,7 +20,7 @@ SYMBOLS = [
     "magic_pol_to_curlr_spat", "magic_torpol_to_curl_spat", "magic_scal_to_SH", "magic_spat_to_qst",
     "magic_spat_to_sphertor", "magic_axi_to_spat", "magic_toraxi_to_spat",
     "magic_rloop_create", "magic_rloop_destroy", "magic_level_chunks", "magic_rloop_run", "magic_rloop_run_dev", "magic_rloop_sync",
-    "magic_rloop_set_rotation", "magic_rloop_get_torques", "magic_rloop_get_br_v_bcs", "magic_rloop_diagnostics", "magic_rloop_diagnostics_dev", "magic_rloop_graph_fields", "magic_rloop_dtb", "magic_rloop_dtb_dev", "magic_rloop_to_next", "magic_rloop_to_next_dev", "magic_rloop_to", "magic_rloop_to_dev", "magic_rloop_launch_count", "magic_rloop_last_timing", "magic_rloop_last_exposed", "magic_rloop_legendre_flops", "magic_rloop_legendre_units", "magic_rloop_pin_host", "magic_rloop_unpin_host", "magic_rloop_level_chunk",
+    "magic_rloop_set_rotation", "magic_rloop_get_torques", "magic_rloop_get_br_v_bcs", "magic_rloop_diagnostics", "magic_rloop_diagnostics_dev", "magic_rloop_graph_fields", "magic_rloop_dtb", "magic_rloop_dtb_dev", "magic_rloop_to_next", "magic_rloop_to_next_dev", "magic_rloop_to", "magic_rloop_to_dev", "magic_rloop_rms_keep", "magic_rloop_rms_keep_dev", "magic_rloop_rms", "magic_rloop_rms_dev", "magic_rloop_launch_count", "magic_rloop_last_timing", "magic_rloop_last_exposed", "magic_rloop_legendre_flops", "magic_rloop_legendre_units", "magic_rloop_pin_host", "magic_rloop_unpin_host", "magic_rloop_level_chunk",
     "magic_transp_unique_id", "magic_transp_create", "magic_transp_destroy", "magic_transp_extents",
     "magic_transp_create_part", "magic_transp_set_stream", "magic_transp_info", "magic_rloop_run_lm_dev", "magic_rloop_run_lm", "magic_rloop_set_radial_matrices", "magic_rloop_set_lm_radial", "magic_rloop_lm_options",
     "magic_transp_lm2r_dev", "magic_transp_r2lm_dev", "magic_transp_lm2r_dev_n", "magic_transp_r2lm_dev_n", "magic_transp_lm2r", "magic_transp_r2lm",

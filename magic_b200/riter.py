@@ -34,6 +34,7 @@ RADIAL_NAMES = ["r", "or1", "or2", "or4", "orho1", "orho2", "beta", "rho0", "ote
 DIAG_HEL, DIAG_HEMI, DIAG_POWER, DIAG_PERPPAR, DIAG_FLUX, DIAG_VISCBC, DIAG_PHASE, DIAG_RMSBULK = 1, 2, 4, 8, 16, 32, 64, 256
 NDIAG = 40
 NTO = 15
+NRMS = 14
 IN_NAMES = ["w", "dw", "ddw", "z", "dz", "s", "ds", "p", "xi", "b", "db", "ddb", "aj", "dj", "phi"]
 OUT_NAMES = ["dwdt", "dzdt", "dpdt", "dsdt", "dxidt", "dbdt", "djdt", "dVxVhLM", "dVxBhLM", "dVSrLM", "dVXirLM", "dphidt"]
 
@@ -174,6 +175,21 @@ class RadialLoop:
         out = np.zeros((self.n_r_loc, NTO, self.sht.n_theta_max))
         fn = self.lib.magic_rloop_to_dev if device else self.lib.magic_rloop_to
         check(fn(self._h, byref(fin), c_double(dtLast), out.ctypes.data_as(c_void_p)))
+        return out
+
+    def rms_keep(self, fields, device=False):
+        """Keeps w, dw, z of every local level on the device: the previous step's velocity of get_nl_RMS (RMS.f90:545-551)."""
+        fin, _, keep = self._structs(fields, {}, 0 if device else np.zeros(1), 0 if device else np.zeros(1), device=device)
+        fn = self.lib.magic_rloop_rms_keep_dev if device else self.lib.magic_rloop_rms_keep
+        check(fn(self._h, byref(fin)))
+
+    def rms(self, fields, dt, device=False):
+        """The r.m.s. force balance inside the radial loop on lRmsCalc steps (rIter.f90:215-252, 710; RMS.f90:469-610) for this
+        rank's levels: complex128 [NRMS, n_r_loc, lm_max], arrays as documented in include/magic_sht.h."""
+        fin, _, keep = self._structs(fields, {}, 0 if device else np.zeros(1), 0 if device else np.zeros(1), device=device)
+        out = np.zeros((NRMS, self.n_r_loc, self.sht.lm_max), dtype=np.complex128)
+        fn = self.lib.magic_rloop_rms_dev if device else self.lib.magic_rloop_rms
+        check(fn(self._h, byref(fin), c_double(dt), out.ctypes.data_as(c_void_p)))
         return out
 
     def graph_fields(self, fields, level, mag=False, pressure=False):

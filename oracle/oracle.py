@@ -392,6 +392,34 @@ class Oracle:
                                _p(out))
         return last if mode == 0 else out
 
+    def radial_RMS(self, params, radial, fields, old, dt):
+        """The r.m.s. force balance inside the radial loop on lRmsCalc steps (rIter.f90:215-252, 710; RMS.f90:469-610): complex128
+        [14, n_r, lm_max] (AdvrLM, LFrLM, dtVrLM, dpkindrLM, Advt2LM, Advp2LM, LFt2LM, LFp2LM, CFt2LM, CFp2LM, PFt2LM, PFp2LM, dtVtLM,
+        dtVpLM).  old: dict with the w, dw, z of the previous stage-1 call."""
+        n_r = len(radial["nR"])
+        keep = []
+        rad = _Radial()
+        for nm in ["nR", "l_R"]:
+            a = np.ascontiguousarray(radial[nm], dtype=np.int32)
+            keep.append(a)
+            setattr(rad, nm, _p(a))
+        for nm in _RAD_NAMES:
+            key = "lambda" if nm == "lambda_" else nm
+            a = np.ascontiguousarray(radial.get(key, np.ones(n_r)), dtype=np.float64)
+            keep.append(a)
+            setattr(rad, nm, _p(a))
+        fin = _FieldsIn()
+        for nm in _IN_NAMES:
+            if nm in fields and fields[nm] is not None:
+                a = self._c(fields[nm])
+                keep.append(a)
+                setattr(fin, nm, _p(a))
+        o = [self._c(old[k]) for k in ("w", "dw", "z")]
+        out = np.zeros((14, n_r, self.lm_max), dtype=np.complex128)
+        self.lib.orc_radial_RMS(self.h, C.byref(params), C.byref(rad), c_int(n_r), C.byref(fin), _p(o[0]), _p(o[1]), _p(o[2]), c_double(dt),
+                                _p(out))
+        return out
+
     def get_nl_mhd(self, params, nR, nBc, or2, or4, orho1, grids_in):
         """get_nl.f90:213-441 on 13 caller grids -> 12 product grids."""
         ins = [self._r(g) for g in grids_in]
