@@ -10,12 +10,55 @@
 // Included by lib.cu after api_rloop.cu (it uses magic_rloop).
 #include "kernels_diag.cuh"
 
+// ---- the shared workspace of the batches in this file (magic_rloop::aux) ------------------------------------------------------
+// level chunk of a batch: bounded by the memory that is free or already held by the shared workspace
+static int aux_chunk(const magic_rloop *rl, double bytes_per_level) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+    const double avail = (double)free_b + (double)rl->aux.bytes;
+    int chunk = (int)std::min<double>(32.0, 0.5 * avail / bytes_per_level);
+    return std::max(1, std::min(chunk, rl->n_r_loc));
+}
+
+// binds a batch to the workspace before it runs: grows the arena if this batch needs more (every batch then re-binds its
+// descriptors on its next run), carves the batch's arrays, and clears them when another batch used the arena last (the transform
+// kernels rely on zero padding, as after buffers_alloc)
+static int aux_acquire(magic_rloop *rl, const void *pipe, const BatchSpec &S, int chunk, Layout &lay, Buffers &buf, int &gen) {
+    magic_sht *h = rl->h;
+    if (lay.n_lev != chunk) layout_sizes(h, S, chunk, lay);
+    const size_t need = buffers_bytes(h, S, lay);
+    auto &A = rl->aux;
+    if (need > A.bytes) {
+        MCHECK(cudaStreamSynchronize(h->stream));
+        cudaFree(A.p);
+        A.p = nullptr; A.bytes = 0; A.gen++; A.owner = nullptr;
+        if (cudaMalloc((void **)&A.p, need) != cudaSuccess) {
+            cudaGetLastError();
+            MFAIL("log-step batch: no device memory for its workspace");
+        }
+        A.bytes = need;
+    }
+    if (gen != A.gen) {
+        layout_free(lay);
+        layout_sizes(h, S, chunk, lay);
+        buffers_carve(h, S, lay, A.p, buf);
+        if (layout_bind(h, S, lay, buf)) return 1;
+        gen = A.gen;
+    }
+    if (A.owner != pipe) {
+        MCHECK(cudaMemsetAsync(A.p, 0, need, h->stream));
+        A.owner = pipe;
+    }
+    return 0;
+}
+
 struct DiagPipe {
     int mask = -1, chunk = 0, gx = 0, phi_field = -1;
     BatchSpec spec;
     DiagIn di;
     Layout lay;
-    Buffers buf;
+    Buffers buf;   // carved from magic_rloop::aux by aux_acquire
+    int gen = -1;
     LevelInfo *d_lev = nullptr;
     double *d_gauss = nullptr, *d_means = nullptr, *d_partial = nullptr, *d_partial_ph = nullptr, *d_out = nullptr, *h_out = nullptr;
     double *d_src[S_COUNT] = {nullptr};  // staging of the host-pointer call: complex [chunk][lm_max] per source
@@ -25,7 +68,6 @@ struct DiagPipe {
 static void diag_free(DiagPipe *d) {
     if (!d) return;
     layout_free(d->lay);
-    buffers_free(d->buf);
     cudaFree(d->d_lev); cudaFree(d->d_gauss); cudaFree(d->d_means); cudaFree(d->d_partial); cudaFree(d->d_partial_ph); cudaFree(d->d_out);
     if (d->h_out) cudaFreeHost(d->h_out);
     for (int i = 0; i < S_COUNT; i++) cudaFree(d->d_src[i]);
@@ -38,6 +80,7 @@ static int diag_build(magic_rloop *rl, int mask) {
     const magic_params &P = rl->p;
     if (P.l_full_sphere) MFAIL("magic_rloop_diagnostics: full-sphere runs (v_center_sphere on the r = 0 level) are not supported");
     if (!(P.l_conv || P.l_mag_kin)) MFAIL("magic_rloop_diagnostics: needs a flow (l_conv or l_mag_kin)");
+    if (rl->aux.owner == rl->diag) rl->aux.owner = nullptr;  // the next DiagPipe may get the same address: never trust stale contents
     diag_free(rl->diag);
     rl->diag = nullptr;
     DiagPipe *d = new DiagPipe();
@@ -86,15 +129,9 @@ static int diag_build(magic_rloop *rl, int mask) {
     S.nfield_in = nf;
     S.nfield_out = 0;
     // level chunk: bounded by free memory (grid + (theta,m) space + operands are about 2.2 grid fields per synthesised field)
-    size_t free_b = 0, total_b = 0;
-    MCHECK(cudaMemGetInfo(&free_b, &total_b));
     const double per_level = 2.2 * 8.0 * (double)h->n_theta * h->n_phi * nf + 64.0 * h->lm_max * S_COUNT;
-    int chunk = (int)std::min<double>(32.0, 0.5 * (double)free_b / per_level);
-    chunk = std::max(1, std::min(chunk, rl->n_r_loc));
-    d->chunk = chunk;
-    layout_sizes(h, S, chunk, d->lay);
-    if (buffers_alloc(h, S, d->lay, d->buf)) return 1;
-    if (layout_bind(h, S, d->lay, d->buf)) return 1;
+    const int chunk = aux_chunk(rl, per_level);
+    d->chunk = chunk;   // the workspace itself is bound by aux_acquire at run time
     // the diagnostics' levels: lDeriv = .true. everywhere (rIter.f90:193-205), boundary levels bulk with lRmsCalc (:215)
     std::vector<LevelInfo> lev = rl->lev;
     for (auto &L : lev) {
@@ -123,6 +160,7 @@ static int diag_run(magic_rloop *rl, const magic_fields_in *in, int mask, int kt
     if (!rl->diag || rl->diag->mask != mask)
         if (diag_build(rl, mask)) return 1;
     DiagPipe *d = rl->diag;
+    if (aux_acquire(rl, d, d->spec, d->chunk, d->lay, d->buf, d->gen)) return 1;
     const magic_params &P = rl->p;
     const double *ip[S_COUNT];
     in_ptrs(in, ip);
@@ -227,7 +265,8 @@ struct DtbPipe {
     int chunk = 0, gx = 0;
     BatchSpec spec;
     Layout lay;
-    Buffers buf;
+    Buffers buf;   // carved from magic_rloop::aux by aux_acquire
+    int gen = -1;
     LevelInfo *d_lev_an = nullptr;  // lcut = l_max for the analysis (dtB.f90:210-221)
     double *d_means = nullptr;
     double *d_src[S_COUNT] = {nullptr};
@@ -236,7 +275,6 @@ struct DtbPipe {
 static void dtb_free(DtbPipe *d) {
     if (!d) return;
     layout_free(d->lay);
-    buffers_free(d->buf);
     cudaFree(d->d_lev_an); cudaFree(d->d_means);
     for (int i = 0; i < S_COUNT; i++) cudaFree(d->d_src[i]);
     delete d;
@@ -261,15 +299,9 @@ static int dtb_build(magic_rloop *rl) {
     S.afield_vp = {1, 3};
     S.afield_s = {4, 5, 6, 7, 8, 9, 10};
     S.nfield_out = 11;
-    size_t free_b = 0, total_b = 0;
-    MCHECK(cudaMemGetInfo(&free_b, &total_b));
     const double per_level = 2.2 * 8.0 * (double)h->n_theta * h->n_phi * (6 + 11) + 64.0 * h->lm_max * 17;
-    int chunk = (int)std::min<double>(32.0, 0.5 * (double)free_b / per_level);
-    chunk = std::max(1, std::min(chunk, rl->n_r_loc));
-    d->chunk = chunk;
-    layout_sizes(h, S, chunk, d->lay);
-    if (buffers_alloc(h, S, d->lay, d->buf)) return 1;
-    if (layout_bind(h, S, d->lay, d->buf)) return 1;
+    const int chunk = aux_chunk(rl, per_level);
+    d->chunk = chunk;   // the workspace itself is bound by aux_acquire at run time
     std::vector<LevelInfo> lev = rl->lev;
     for (auto &L : lev) L.lcut = h->l_max;
     if (dev_upload_vec(&d->d_lev_an, lev)) return 1;
@@ -286,6 +318,7 @@ static int dtb_run(magic_rloop *rl, const magic_fields_in *in, double *out, bool
     if (!rl->dtb)
         if (dtb_build(rl)) return 1;
     DtbPipe *d = rl->dtb;
+    if (aux_acquire(rl, d, d->spec, d->chunk, d->lay, d->buf, d->gen)) return 1;
     const magic_params &P = rl->p;
     const double *ip[S_COUNT];
     in_ptrs(in, ip);
@@ -350,7 +383,8 @@ struct ToPipe {
     BatchSpec spec;
     ToIn ti;
     Layout lay;
-    Buffers buf;
+    Buffers buf;   // carved from magic_rloop::aux by aux_acquire
+    int gen = -1;
     LevelInfo *d_lev = nullptr;
     double *d_last = nullptr, *d_out = nullptr, *h_out = nullptr;
     double *d_src[S_COUNT] = {nullptr};
@@ -361,7 +395,6 @@ struct ToPipe {
 static void to_free(ToPipe *d) {
     if (!d) return;
     layout_free(d->lay);
-    buffers_free(d->buf);
     cudaFree(d->d_lev); cudaFree(d->d_last); cudaFree(d->d_out);
     if (d->h_out) cudaFreeHost(d->h_out);
     for (int i = 0; i < S_COUNT; i++) cudaFree(d->d_src[i]);
@@ -403,15 +436,9 @@ static int to_build(magic_rloop *rl) {
         if (e != cudaSuccess) { cudaGetLastError(); MFAIL("magic_rloop_to: no device memory for BsLast / BpLast / BzLast of all local levels"); }
         MCHECK(cudaMemset(d->d_last, 0, sizeof(double) * 6 * plane * (size_t)rl->n_r_loc));
     }
-    size_t free_b = 0, total_b = 0;
-    MCHECK(cudaMemGetInfo(&free_b, &total_b));
     const double per_level = 2.2 * 8.0 * (double)h->n_theta * h->n_phi * nf + 64.0 * h->lm_max * S_COUNT;
-    int chunk = (int)std::min<double>(32.0, 0.5 * (double)free_b / per_level);
-    chunk = std::max(1, std::min(chunk, rl->n_r_loc));
-    d->chunk = chunk;
-    layout_sizes(h, S, chunk, d->lay);
-    if (buffers_alloc(h, S, d->lay, d->buf)) return 1;
-    if (layout_bind(h, S, d->lay, d->buf)) return 1;
+    const int chunk = aux_chunk(rl, per_level);
+    d->chunk = chunk;   // the workspace itself is bound by aux_acquire at run time
     std::vector<LevelInfo> lev = rl->lev;   // lDeriv = .true. with lTOCalc (rIter.f90:197-205)
     for (auto &L : lev) L.lDeriv = 1;
     if (dev_upload_vec(&d->d_lev, lev)) return 1;
@@ -431,6 +458,7 @@ static int to_run(magic_rloop *rl, const magic_fields_in *in, int mode, double d
     ToPipe *d = rl->to;
     const magic_params &P = rl->p;
     if (mode == 0 && !P.l_mag) return 0;  // TO.f90:330: only the magnetic terms keep grid fields
+    if (aux_acquire(rl, d, d->spec, d->chunk, d->lay, d->buf, d->gen)) return 1;
     if (mode == 1 && !(dtLast > 0.0)) MFAIL("magic_rloop_to: dtLast must be positive");
     const double *ip[S_COUNT];
     in_ptrs(in, ip);
@@ -504,7 +532,8 @@ struct RmsPipe {
     BatchSpec spec;
     RmsIn ri;
     Layout lay;
-    Buffers buf;
+    Buffers buf;   // carved from magic_rloop::aux by aux_acquire
+    int gen = -1;
     LevelInfo *d_lev = nullptr;          // nBc = 0, lDeriv = 1 everywhere (rIter.f90:215)
     double *d_old[3] = {nullptr};        // w, dw, z of the previous stage-1 call: complex [n_r_loc][lm_max]
     double *d_src[S_COUNT] = {nullptr};
@@ -515,7 +544,6 @@ struct RmsPipe {
 static void rms_free(RmsPipe *d) {
     if (!d) return;
     layout_free(d->lay);
-    buffers_free(d->buf);
     cudaFree(d->d_lev);
     for (int i = 0; i < 3; i++) cudaFree(d->d_old[i]);
     for (int i = 0; i < S_COUNT; i++) cudaFree(d->d_src[i]);
@@ -564,15 +592,9 @@ static int rms_build(magic_rloop *rl) {
     S.nfield_out = RMS_NOUT;
     const size_t lm2 = 2 * (size_t)h->lm_max;
     for (int i = 0; i < 3; i++) MCHECK(cudaMalloc((void **)&d->d_old[i], sizeof(double) * lm2 * (size_t)rl->n_r_loc));
-    size_t free_b = 0, total_b = 0;
-    MCHECK(cudaMemGetInfo(&free_b, &total_b));
     const double per_level = 2.2 * 8.0 * (double)h->n_theta * h->n_phi * (nf + RMS_NOUT) + 64.0 * h->lm_max * (S_COUNT + RMS_NOUT);
-    int chunk = (int)std::min<double>(32.0, 0.5 * (double)free_b / per_level);
-    chunk = std::max(1, std::min(chunk, rl->n_r_loc));
-    d->chunk = chunk;
-    layout_sizes(h, S, chunk, d->lay);
-    if (buffers_alloc(h, S, d->lay, d->buf)) return 1;
-    if (layout_bind(h, S, d->lay, d->buf)) return 1;
+    const int chunk = aux_chunk(rl, per_level);
+    d->chunk = chunk;   // the workspace itself is bound by aux_acquire at run time
     std::vector<LevelInfo> lev = rl->lev;
     for (auto &L : lev) { L.lDeriv = 1; L.nBc = 0; }
     if (dev_upload_vec(&d->d_lev, lev)) return 1;
@@ -607,6 +629,7 @@ static int rms_run(magic_rloop *rl, const magic_fields_in *in, double dt, double
         if (rms_build(rl)) return 1;
     RmsPipe *d = rl->rms;
     const magic_params &P = rl->p;
+    if (aux_acquire(rl, d, d->spec, d->chunk, d->lay, d->buf, d->gen)) return 1;
     if (!d->have_old) MFAIL("magic_rloop_rms: no previous velocity kept (call magic_rloop_rms_keep on every stage-1 step while l_RMS is on)");
     if (!(dt > 0.0)) MFAIL("magic_rloop_rms: dt must be positive");
     const double *ip[S_COUNT];

@@ -31,6 +31,9 @@ struct magic_rloop {
     // of chunk c is queued; they queue the transposes of that chunk on the communication stream
     std::function<int(int)> hook_before, hook_after;
     struct LmPipe *lmpipe = nullptr;
+    // one workspace for the log-step batches below (they never run concurrently): grown to the largest request; `gen` tells a
+    // batch that its descriptors point into an arena that no longer exists, `owner` whose data the arena holds
+    struct { char *p = nullptr; size_t bytes = 0; int gen = 0; const void *owner = nullptr; } aux;
     struct DiagPipe *diag = nullptr;  // log-step diagnostics (api_diag.cu), built on first use
     struct DtbPipe *dtb = nullptr;    // get_dtBLM batch (api_diag.cu), built on first use
     struct ToPipe *to = nullptr;      // torsional-oscillation sums (api_diag.cu), built on first use
@@ -205,6 +208,7 @@ extern "C" int magic_rloop_destroy(magic_rloop *rl) {
     dtb_free(rl->dtb);
     to_free(rl->to);
     rms_free(rl->rms);
+    cudaFree(rl->aux.p);
     if (rl->h_torque) cudaFreeHost(rl->h_torque);
     for (int i = 0; i < 16; i++) cudaEventDestroy(rl->ev[i]);
     for (auto e : rl->up_done) cudaEventDestroy(e);

@@ -207,6 +207,37 @@ int buffers_alloc(magic_sht *h, const BatchSpec &spec, const Layout &L, Buffers 
     return 0;
 }
 
+// The same eight arrays (+ the Courant maxima) carved out of one caller-owned arena: the log-step batches (api_diag.cu) never run
+// concurrently, so they share one workspace instead of holding one each.  Every array starts on a 256-byte boundary.
+static void buffers_items(const magic_sht *h, const BatchSpec &spec, const Layout &L, long long n[9]) {
+    const long long plane = (long long)2 * h->nh * h->n_phi;
+    const long long items[9] = {L.szB, L.szF, plane * spec.nfield_in * L.n_lev, plane * spec.nfield_out * L.n_lev, L.szBa, L.szCa,
+                                (long long)2 * L.nf_s * L.n_lev * h->lm_max, (long long)4 * L.npair_a * L.n_lev * h->lm_max,
+                                (long long)2 * std::max(L.n_lev, 1)};
+    for (int i = 0; i < 9; i++) n[i] = std::max<long long>(items[i], 1);
+}
+
+size_t buffers_bytes(const magic_sht *h, const BatchSpec &spec, const Layout &L) {
+    long long n[9];
+    buffers_items(h, spec, L, n);
+    size_t tot = 0;
+    for (int i = 0; i < 9; i++) tot += ((size_t)n[i] * 8 + 255) / 256 * 256;
+    return tot;
+}
+
+void buffers_carve(const magic_sht *h, const BatchSpec &spec, const Layout &L, char *base, Buffers &b) {
+    long long n[9];
+    buffers_items(h, spec, L, n);
+    double **ps[8] = {&b.B, &b.F, &b.gin, &b.gout, &b.Ba, &b.Ca, &b.nl_s, &b.nl_v};
+    size_t off = 0;
+    for (int i = 0; i < 9; i++) {
+        if (i < 8) *ps[i] = reinterpret_cast<double *>(base + off);
+        else b.courmax = reinterpret_cast<unsigned long long *>(base + off);
+        off += ((size_t)n[i] * 8 + 255) / 256 * 256;
+    }
+    b.bytes = off;
+}
+
 void buffers_free(Buffers &b) {
     double *ps[] = {b.B, b.F, b.gin, b.gout, b.Ba, b.Ca, b.nl_s, b.nl_v};
     for (double *p : ps) cudaFree(p);

@@ -115,6 +115,8 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
 void layout_free(Layout &L);
 int buffers_alloc(magic_sht *h, const BatchSpec &spec, const Layout &Lmax, Buffers &buf);
 void buffers_free(Buffers &buf);
+size_t buffers_bytes(const magic_sht *h, const BatchSpec &spec, const Layout &L);                     // arena form: bytes needed ...
+void buffers_carve(const magic_sht *h, const BatchSpec &spec, const Layout &L, char *base, Buffers &buf);  // ... and the carving
 
 // pipeline stages (all asynchronous on h->stream)
 // ev (optional): 4 events for synthesis (start, after prep, after Legendre, after FFT); 3 for analysis

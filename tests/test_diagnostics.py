@@ -211,3 +211,32 @@ def test_gpu_graph_fields_are_the_per_call_transforms():
         assert np.linalg.norm(got - ref) < 1e-12 * np.linalg.norm(ref)
     rl.finalize()
     s.finalize_sht()
+
+
+@pytest.mark.gpu
+def test_gpu_log_step_batches_share_one_workspace():
+    """The diagnostics, get_dtBLM, TO and RMS batches are carved from one device workspace (they never run concurrently): used in
+    turn on one plan, with the workspace growing and changing hands in between, each returns bit for bit what it returns on a
+    plan of its own."""
+    from magic_b200 import RadialLoop, Sht
+    l_max, n_r = 21, 9
+    s = Sht(l_max)
+    p, rad, f = _case("mhd", l_max, n_r, s.lm2l, s.lm2m, 17)
+    old = {k: 0.9 * f[k] for k in ("w", "dw", "z")}
+    calls = {
+        "hemi": lambda rl: rl.diagnostics(f, DIAG_HEMI),
+        "all": lambda rl: rl.diagnostics(f, ALL),
+        "dtb": lambda rl: rl.dtb(f),
+        "to": lambda rl: (rl.to_next(f), rl.to(f, 1e-3))[1],
+        "rms": lambda rl: (rl.rms_keep(old), rl.rms(f, 1e-3))[1],
+    }
+    alone = {}
+    for nm, fn in calls.items():
+        rl = RadialLoop(s, p, rad)
+        alone[nm] = fn(rl)
+        rl.finalize()
+    rl = RadialLoop(s, p, rad)
+    for nm in ("hemi", "dtb", "all", "rms", "to", "hemi", "rms", "dtb", "all", "to"):   # small -> large -> small requests, every hand-over
+        assert np.array_equal(calls[nm](rl), alone[nm]), nm
+    rl.finalize()
+    s.finalize_sht()
