@@ -77,6 +77,11 @@ module rIter_cuda_mod
       procedure, private :: create_plan
    end type rIter_cuda_t
 
+   !-- results of the r.m.s. and dtB batches: (lm_max, nRstart:nRstop, 14 / 11), allocated on first use and page-locked (a pageable
+   !   destination takes these gigabytes at a tenth of the PCIe rate); module variables because c_loc needs a target and the
+   !   passed-object dummy of the deferred radialLoop interface (rIteration.f90:43) is not one
+   complex(c_double_complex), allocatable, target, save :: rq(:,:,:), dtb(:,:,:)
+
 contains
 
    subroutine initialize(this)
@@ -96,6 +101,8 @@ contains
       class(rIter_cuda_t) :: this
 
       if ( c_associated(this%rl) ) call magic_check( magic_rloop_destroy(this%rl), 'magic_rloop_destroy' )
+      if ( allocated(rq) ) deallocate( rq )      ! after the plan: magic_rloop_destroy releases the page locks it holds
+      if ( allocated(dtb) ) deallocate( dtb )
       this%rl = c_null_ptr
       if ( allocated(this%rad) ) deallocate( this%rad, this%nR_loc, this%l_R_loc )
       call this%single%finalize()
@@ -236,8 +243,6 @@ contains
       real(c_double), allocatable :: dg(:,:)
       real(cp), allocatable :: grd(:,:)
       real(c_double), allocatable :: tq(:,:,:)
-      complex(c_double_complex), allocatable :: rq(:,:,:)
-      complex(c_double_complex), allocatable :: dtb(:,:,:)
 
       !-- Inputs: the R-distributed containers of fields.f90:211-268, (lm_max, nRstart:nRstop) each; the library
       !   ignores the pointers of switched-off physics
@@ -368,15 +373,19 @@ contains
       !-- rIter.f90:388-395, 442 with l_dtB: the eleven products of get_dtBLM and their analyses for all local levels as one
       !   batch on the device; get_dH_dtBLM then combines them level by level as in the reference
       if ( l_dtB ) then
-         allocate( dtb(lm_max,nRstart:nRstop,11) )
+         if ( .not. allocated(dtb) ) then
+            allocate( dtb(lm_max,nRstart:nRstop,11) )
+            call magic_check( magic_rloop_pin_host(this%rl, c_loc(dtb), int(16,c_size_t)*size(dtb,kind=c_size_t)), &
+                 &            'magic_rloop_pin_host' )
+         end if
          call magic_check( magic_rloop_dtb(this%rl, fin, dtb), 'magic_rloop_dtb' )
          do nR=nRstart,nRstop
             BtVrLM(:)=dtb(:,nR,1);  BpVrLM(:)=dtb(:,nR,2);  BrVtLM(:)=dtb(:,nR,3);  BrVpLM(:)=dtb(:,nR,4)
-            BtVpLM(:)=dtb(:,nR,5);  BpVtLM(:)=dtb(:,nR,6);  BpVtBtVpCotLM(:)=dtb(:,nR,7);  BpVtBtVpSn2LM(:)=dtb(:,nR,8)
+            BtVpLM(:)=dtb(:,nR,5);  BpVtLM(:)=dtb(:,nR,6);  BpVtBtVpCotLM(:)=dtb(:,nR,7)
+            BpVtBtVpSn2LM(:)=dtb(:,nR,8)
             BrVZLM(:)=dtb(:,nR,9);  BtVZLM(:)=dtb(:,nR,10);  BtVZsn2LM(:)=dtb(:,nR,11)
             call get_dH_dtBLM(nR)
          end do
-         deallocate( dtb )
       end if
 
       if ( l_rms_dev ) call rms_on_device()
@@ -492,7 +501,11 @@ contains
          !   step's velocity on the grid at every stage-1 call; here its potentials stay on the device (magic_rloop_rms_keep)
          if ( l_rms_dev ) then
             if ( lRmsCalc ) then
-               allocate( rq(lm_max,nRstart:nRstop,MAGIC_NRMS) )
+               if ( .not. allocated(rq) ) then
+                  allocate( rq(lm_max,nRstart:nRstop,MAGIC_NRMS) )
+                  call magic_check( magic_rloop_pin_host(this%rl, c_loc(rq), int(16,c_size_t)*size(rq,kind=c_size_t)), &
+                       &            'magic_rloop_pin_host' )
+               end if
                fin%p = c_loc(p_Rloc)
                call magic_check( magic_rloop_rms(this%rl, fin, real(tscheme%dt(1),c_double), rq), 'magic_rloop_rms' )
                do nR=nRstart,nRstop
@@ -503,7 +516,6 @@ contains
                   dtVtLM(:) =rq(:,nR,13);  dtVpLM(:) =rq(:,nR,14)
                   call compute_lm_forces(nR, rq(:,nR,1))
                end do
-               deallocate( rq )
             end if
             if ( tscheme%istage == 1 ) call magic_check( magic_rloop_rms_keep(this%rl, fin), 'magic_rloop_rms_keep' )
          end if
