@@ -160,7 +160,10 @@ __device__ __forceinline__ void diag_point(const DiagArgs &a, const LevelInfo &L
     }
 }
 
-__global__ void __launch_bounds__(DIAG_THREADS) diag_kernel(DiagArgs a) {
+#ifndef MAGIC_DIAG_MINB
+#define MAGIC_DIAG_MINB 1   // resident CTAs per SM asked of ptxas (2 caps the kernel at 128 registers)
+#endif
+__global__ void __launch_bounds__(DIAG_THREADS, MAGIC_DIAG_MINB) diag_kernel(DiagArgs a) {
     const int lev = blockIdx.y;
     const LevelInfo L = a.lev[lev];
     const size_t plane = (size_t)a.nh * a.n_phi;

@@ -153,11 +153,19 @@ class RadialLoop:
         check(fn(self._h, byref(fin), c_int(mask), c_int(ktops), c_int(kbots), out.ctypes.data_as(c_void_p)))
         return out
 
-    def dtb(self, fields, device=False):
+    @staticmethod
+    def _result(out, shape):
+        if out is None:
+            return np.zeros(shape, dtype=np.complex128)
+        if out.shape != shape or out.dtype != np.complex128 or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous complex128 array of shape {shape}")
+        return out
+
+    def dtb(self, fields, device=False, out=None):
         """get_dtBLM (dtB.f90:144-223) for this rank's levels: complex128 [11, n_r_loc, lm_max] (BtVrLM, BpVrLM, BrVtLM, BrVpLM,
-        BtVpLM, BpVtLM, BpVtBtVpCotLM, BpVtBtVpSn2LM, BrVZLM, BtVZLM, BtVZsn2LM)."""
+        BtVpLM, BpVtLM, BpVtBtVpCotLM, BpVtBtVpSn2LM, BrVZLM, BtVZLM, BtVZsn2LM).  `out`: a host array to fill."""
         fin, _, keep = self._structs(fields, {}, 0 if device else np.zeros(1), 0 if device else np.zeros(1), device=device)
-        out = np.zeros((11, self.n_r_loc, self.sht.lm_max), dtype=np.complex128)
+        out = self._result(out, (11, self.n_r_loc, self.sht.lm_max))
         fn = self.lib.magic_rloop_dtb_dev if device else self.lib.magic_rloop_dtb
         check(fn(self._h, byref(fin), out.ctypes.data_as(c_void_p)))
         return out
@@ -183,11 +191,12 @@ class RadialLoop:
         fn = self.lib.magic_rloop_rms_keep_dev if device else self.lib.magic_rloop_rms_keep
         check(fn(self._h, byref(fin)))
 
-    def rms(self, fields, dt, device=False):
+    def rms(self, fields, dt, device=False, out=None):
         """The r.m.s. force balance inside the radial loop on lRmsCalc steps (rIter.f90:215-252, 710; RMS.f90:469-610) for this
-        rank's levels: complex128 [NRMS, n_r_loc, lm_max], arrays as documented in include/magic_sht.h."""
+        rank's levels: complex128 [NRMS, n_r_loc, lm_max], arrays as documented in include/magic_sht.h.  `out`: a host array
+        to fill (page-locked memory takes the result at PCIe speed)."""
         fin, _, keep = self._structs(fields, {}, 0 if device else np.zeros(1), 0 if device else np.zeros(1), device=device)
-        out = np.zeros((NRMS, self.n_r_loc, self.sht.lm_max), dtype=np.complex128)
+        out = self._result(out, (NRMS, self.n_r_loc, self.sht.lm_max))
         fn = self.lib.magic_rloop_rms_dev if device else self.lib.magic_rloop_rms
         check(fn(self._h, byref(fin), c_double(dt), out.ctypes.data_as(c_void_p)))
         return out

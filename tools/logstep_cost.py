@@ -45,6 +45,9 @@ t1 = timed("getTO", lambda: rl.to(ptr, 1e-4, device=True))
 timed("rms_keep", lambda: rl.rms_keep(ptr, device=True))
 r1 = timed("get_nl_RMS batch (14 spectra to the host)", lambda: rl.rms(ptr, 1e-4, device=True))
 b1 = timed("get_dtBLM batch (11 spectra to the host)", lambda: rl.dtb(ptr, device=True))
+pinned = torch.empty((14, n_lev, s.lm_max), dtype=torch.complex128).pin_memory()
+rp = timed("get_nl_RMS batch into page-locked memory", lambda: rl.rms(ptr, 1e-4, device=True, out=pinned.numpy()))
+print("pinned result equals the pageable one:", bool(np.array_equal(rp, r1)))
 d2 = rl.diagnostics(ptr, ALL, device=True)
 print("diagnostics bitwise repeatable after the workspace changed hands:", bool(np.array_equal(d1, d2)),
       "| workspace + kept fields GB:", round((free0 - torch.cuda.mem_get_info()[0]) / 1e9, 1))
