@@ -71,7 +71,7 @@ def test_oracle_radial_loop_reproduces_reference_energies(golden):
     from oracle.oracle import Oracle, Params as OParams, grid_sizes
     gs = grid_sizes(n_phi_tot=int(golden["n_phi_tot"]))
     o = Oracle(gs["l_max"], n_theta=gs["n_theta_max"], n_phi=gs["n_phi_max"], m_max=gs["m_max"],
-               threads=min(4, os.cpu_count() or 1))  # ~2 s per radial loop; more threads only add scheduling noise on small boxes
+               threads=min(4, os.cpu_count() or 1), fast=True)  # the -O3 build of the same oracle source: ~3 s per radial loop at l_max = 96
     h, p, rad = _setup(golden, o.lm2l, o.lm2m)
     op = OParams()
     for n, _ in p._fields_:
