@@ -176,6 +176,48 @@ def test_radial_loop_against_the_oracle(l_max, n_r_max, physics):
     s.finalize_sht()
 
 
+def test_l255_log_step_batches_against_the_oracle():
+    """BASELINE config 3 size: the log-step batches (in-loop diagnostics, get_dtBLM, getTO, the r.m.s. batch) on one boundary and
+    two bulk levels against the oracle.  Sums of 2e5 grid points and analyses of products: relative to the largest entry of
+    each slot / array (a pair of spheroidal / toroidal spectra shares its scale)."""
+    from oracle.oracle import Oracle, Params as OParams
+    from magic_b200.riter import DIAG_FLUX, DIAG_HEL, DIAG_HEMI, DIAG_PERPPAR, DIAG_POWER, DIAG_VISCBC
+    l_max, n_r_max = 255, 121
+    s, p, rad, fields, rl = _loop_setup(l_max, n_r_max, "mhd", [1, 2, n_r_max // 2])
+    fields["p"] = 0.4 * fields["s"] + 0.1 * fields["w"]
+    fields["ds"] = 0.6 * fields["s"]
+    old = {k: 0.8 * fields[k] for k in ("w", "dw", "z")}
+    op = OParams()
+    for n, _ in p._fields_:
+        setattr(op, n, getattr(p, n))
+    o = Oracle(l_max, threads=8, fast=False)
+    mask = DIAG_HEL | DIAG_HEMI | DIAG_POWER | DIAG_PERPPAR | DIAG_FLUX | DIAG_VISCBC
+    dt = 1e-4
+
+    def worst(got, ref, axis, pairs=False):
+        w = 0.0
+        for q in range(ref.shape[axis]):
+            g, r = np.take(got, q, axis), np.take(ref, q, axis)
+            q2 = q if not pairs or q < 4 else (q + 1 if q % 2 == 0 else q - 1)
+            scale = max(np.abs(r).max(), np.abs(np.take(ref, q2, axis)).max())
+            if scale > 0:
+                w = max(w, np.abs(g - r).max() / scale)
+            else:
+                assert not g.any()
+        return w
+    res = {"diagnostics": worst(rl.diagnostics(fields, mask), o.radial_diagnostics(op, rad, fields, mask), 1),
+           "get_dtBLM": worst(rl.dtb(fields), o.radial_dtB(op, rad, fields), 0)}
+    rl.to_next(old | {k: 0.8 * fields[k] for k in ("b", "db", "ddb", "aj", "dj")})
+    last = o.radial_TO(op, rad, {k: 0.8 * v for k, v in fields.items()}, 0)
+    res["getTO"] = worst(rl.to(fields, dt), o.radial_TO(op, rad, fields, 1, dtLast=dt, last=last), 1)
+    rl.rms_keep(old)
+    res["rms batch"] = worst(rl.rms(fields, dt), o.radial_RMS(op, rad, fields, old, dt), 0, pairs=True)
+    print("log-step batches vs oracle, l_max=255 mhd:", {k: f"{v:.2e}" for k, v in res.items()})
+    assert max(res.values()) < 1e-11, res
+    rl.finalize()
+    s.finalize_sht()
+
+
 def test_l1023_one_level_against_the_oracle():
     """BASELINE config 5: one bulk level of the l_max = 1023 MHD loop against the oracle (12.9 GB of host tables)."""
     from oracle.oracle import Oracle, Params as OParams
