@@ -47,7 +47,7 @@ module magic_b200_c
       type(c_ptr) :: dphidt
    end type magic_fields_out
 
-   !-- LM-distributed containers of magic_rloop_run_lm (fields.f90:211-268, dt_fieldsLast.f90:125-214)
+   !-- LM-distributed containers of magic_rloop_run_lm (fields.f90:211-268, dt_fieldsLast.f90:125-214, module fieldsLast)
    type, bind(C) :: magic_lm_in
       type(c_ptr) :: flow, s, field, xi
    end type magic_lm_in

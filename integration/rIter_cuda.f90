@@ -49,7 +49,7 @@ module rIter_cuda_mod
    use fields, only: s_Rloc, ds_Rloc, z_Rloc, dz_Rloc, p_Rloc, b_Rloc, db_Rloc, ddb_Rloc, aj_Rloc, dj_Rloc, phi_Rloc, &
        &             w_Rloc, dw_Rloc, ddw_Rloc, xi_Rloc, omega_ic, omega_ma,                                &
        &             flow_LMloc_container, s_LMloc_container, field_LMloc_container, xi_LMloc_container
-   use dt_fieldsLast, only: dflowdt_LMloc_container, dsdt_LMloc_container, dbdt_LMloc_container,            &
+   use fieldsLast, only:    dflowdt_LMloc_container, dsdt_LMloc_container, dbdt_LMloc_container,            &
        &                    dxidt_LMloc_container
    use blocking, only: llm
    use mpi_transp_cuda_mod, only: l_fused_lm, l_outputs_in_lm, n_pending, transp5, run_pending_lm2r

@@ -141,3 +141,45 @@ def test_a_fortran_parser_accepts_the_two_plain_modules():
                 "torpol_to_dphspat": 5, "pol_to_curlr_spat": 3, "torpol_to_curl_spat": 9, "scal_to_sh": 3, "spat_to_qst": 7,
                 "spat_to_sphertor": 5, "axi_to_spat": 2, "toraxi_to_spat": 4}        # sht_native.f90:24-405
     assert {k: len(v) for k, v in sht.items()} == expected
+
+
+def test_log_step_batches_are_bound():
+    names = re.findall(r"bind\(C, name='(\w+)'\)", _read("integration", "magic_b200_c.f90"))
+    for n in ("magic_rloop_diagnostics", "magic_rloop_dtb", "magic_rloop_to_next", "magic_rloop_to", "magic_rloop_rms_keep",
+              "magic_rloop_rms", "magic_rloop_pin_host"):
+        assert n in names, n
+    src = _read("integration", "rIter_cuda.f90")
+    for n in ("magic_rloop_diagnostics", "magic_rloop_dtb", "magic_rloop_to_next", "magic_rloop_to", "magic_rloop_rms_keep",
+              "magic_rloop_rms"):
+        assert re.search(r"\b%s\(" % n, src), n
+
+
+def test_names_imported_from_the_reference_exist_there():
+    """No Fortran compiler here: at least every entity the shims `use` from a reference module must occur in that module's
+    source (catches misspelt or renamed imports).  Needs the reference tree; skipped where it is absent (GPU box)."""
+    import glob
+    import pytest
+    ref = "/root/reference/src"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present")
+    modules = {}
+    for path in glob.glob(os.path.join(ref, "*.f90")) + glob.glob(os.path.join(ref, "*.F90")):
+        text = open(path, errors="replace").read()
+        for m in re.findall(r"^\s*module\s+(\w+)\s*$", text, re.M | re.I):
+            modules.setdefault(m.lower(), "")
+            modules[m.lower()] += text.lower()     # a module may have several flavours (sht_native / shtns, fft variants)
+    own = {"magic_b200_c", "sht", "mpi_transp_cuda_mod", "riter_cuda_mod", "iso_c_binding"}
+    checked = 0
+    for f in ("rIter_cuda.f90", "mpi_transp_cuda.f90", "sht_cuda.f90"):
+        src = re.sub(r"&\s*\n\s*&?", " ", _read("integration", f))
+        src = "\n".join(l.split("!")[0] for l in src.splitlines())
+        for mod, names in re.findall(r"^\s*use\s+(\w+)\s*,\s*only\s*:\s*(.*)$", src, re.M | re.I):
+            if mod.lower() in own:
+                continue
+            assert mod.lower() in modules, f"{f}: module {mod} is not in the reference"
+            for n in names.split(","):
+                n = n.split("=>")[-1].strip()
+                if n:
+                    assert re.search(r"\b%s\b" % re.escape(n.lower()), modules[mod.lower()]), f"{f}: {mod} has no {n}"
+                    checked += 1
+    assert checked > 150
