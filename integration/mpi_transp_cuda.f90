@@ -106,8 +106,8 @@ contains
          if ( n_pending == n_pending_max ) call abortRun('! type_mpicuda: too many pending transposes')
          n_pending = n_pending+1
          pending_t(n_pending)  = this%t
-         pending_lm(n_pending) = c_loc(arr_LMloc)
-         pending_r(n_pending)  = c_loc(arr_Rloc)
+         pending_lm(n_pending) = addr_z(arr_LMloc)   ! (the dummies of the deferred interface are no targets: magic_b200_c)
+         pending_r(n_pending)  = addr_z(arr_Rloc)
          return
       end if
       call magic_check( magic_transp_lm2r(this%t, arr_LMloc, arr_Rloc), 'magic_transp_lm2r' )

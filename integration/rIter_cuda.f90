@@ -249,7 +249,7 @@ contains
       fin = magic_fields_in(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
       &                     c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
       &                     c_null_ptr)
-      if ( l_phase_field ) fin%phi = c_loc(phi_Rloc)
+      if ( l_phase_field ) fin%phi = addr_z(phi_Rloc)   ! allocatable without TARGET in fields.f90:47
       if ( l_conv .or. l_mag_kin ) then
          fin%w = c_loc(w_Rloc);  fin%dw = c_loc(dw_Rloc);  fin%ddw = c_loc(ddw_Rloc)
          fin%z = c_loc(z_Rloc);  fin%dz = c_loc(dz_Rloc)
