@@ -58,3 +58,22 @@ def test_params_struct_layout_matches_header():
         stmt = re.sub(r"^(int|double)\s+", "", stmt)
         names += [n.strip() for n in stmt.split(",")]
     assert names == [n for n, _ in Params._fields_]
+
+
+def test_log_step_entry_points_reject_null_handles_loudly():
+    """Argument checks come before any device work: a null plan is an error with a message, never a crash or a silent no-op."""
+    from ctypes import c_double, c_int, c_void_p
+    from magic_b200.lib import load_library
+    lib = load_library()
+    null = c_void_p(None)
+    calls = {
+        "magic_rloop_diagnostics": (null, null, c_int(1), c_int(1), c_int(1), null),
+        "magic_rloop_dtb": (null, null, null),
+        "magic_rloop_to_next": (null, null),
+        "magic_rloop_to": (null, null, c_double(1e-3), null),
+        "magic_rloop_rms_keep": (null, null),
+        "magic_rloop_rms": (null, null, c_double(1e-3), null),
+    }
+    for name, args in calls.items():
+        assert getattr(lib, name)(*args) != 0, name
+        assert b"null argument" in lib.magic_last_error(), (name, lib.magic_last_error())
