@@ -199,8 +199,10 @@ int magic_rloop_to_dev(magic_rloop *rl, const magic_fields_in *in, double dtLast
  * (module variables of RMS.f90; the spectral sums of compute_lm_forces, RMS.f90:612-863, stay with the host).  dt = tscheme%dt(1).
  * get_nl_RMS keeps the previous step's velocity on the grid (vr_old, vt_old, vp_old, RMS.f90:545-551, updated at every stage-1
  * call while l_RMS is on); here magic_rloop_rms_keep keeps its potentials w, dw, z on the DEVICE instead -- call it on every
- * stage-1 step, after magic_rloop_rms on lRmsCalc steps.  in->p is needed (transform_to_grid_RMS).  Host field pointers; the _dev
- * forms take device input pointers (out stays a host array).  Not for full-sphere runs, precession, centrifugal or phase-field terms. */
+ * stage-1 step, after magic_rloop_rms on lRmsCalc steps.  in->p is needed (transform_to_grid_RMS), in->s with l_centrifuge, in->phi
+ * with l_phase_field; the precession terms take the `time` of the last pass of the loop (call magic_rloop_rms after magic_rloop_run
+ * of the same stage, as rIter.f90 does).  Host field pointers; the _dev forms take device input pointers (out stays a host array).
+ * Not for full-sphere runs. */
 #define MAGIC_NRMS 14
 int magic_rloop_rms_keep(magic_rloop *rl, const magic_fields_in *in);
 int magic_rloop_rms_keep_dev(magic_rloop *rl, const magic_fields_in *in);

@@ -263,8 +263,8 @@ contains
          fin%aj = c_loc(aj_Rloc);  fin%dj = c_loc(dj_Rloc)
       end if
 
-      !-- l_RMS on the device unless the advection carries terms the RMS batch does not form
-      l_rms_dev = l_RMS .and. .not. ( l_full_sphere .or. l_precession .or. l_centrifuge .or. l_phase_field )
+      !-- l_RMS on the device (the batch has no r = 0 level: full-sphere runs keep the reference's loop)
+      l_rms_dev = l_RMS .and. .not. l_full_sphere
 
       !-- Log steps: get_helicity, get_hemi, get_visc_heat, get_perpPar, get_fluxes, get_nlBLayers and get_ekin_solid_liquid
       !   (rIter.f90:320-367) and the torsional-oscillation sums (getTOnext / getTO, rIter.f90:395-404) are evaluated on the device

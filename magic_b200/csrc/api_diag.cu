@@ -524,8 +524,10 @@ extern "C" int magic_rloop_to_dev(magic_rloop *rl, const magic_fields_in *in, do
 // get_nl_RMS keeps on the grid (vr_old ..., RMS.f90:545-551), is kept as its three potentials instead (magic_rloop_rms_keep: w, dw,
 // z of every local level on the DEVICE) and synthesised with the rest.  out: HOST complex [MAGIC_NRMS][n_r_loc][lm_max] in the order
 // AdvrLM, LFrLM, dtVrLM, dpkindrLM, Advt2LM, Advp2LM, LFt2LM, LFp2LM, CFt2LM, CFp2LM, PFt2LM, PFp2LM, dtVtLM, dtVpLM; the spectral
-// sums of compute_lm_forces (RMS.f90:612-863) stay with the host.
-static const int S_WOLD = S_XI, S_DWOLD = S_DS, S_ZOLD = S_PHI;  // source slots this column program does not use otherwise
+// sums of compute_lm_forces (RMS.f90:612-863) stay with the host.  Phase-field penalty, precession and centrifugal terms are formed as
+// get_nl does (the latter two only enter AdvrLM, rIter.f90:669-678); the precession phase uses the time of the last pass of the loop.
+static const int S_WOLD = S_XI, S_DWOLD = S_DS, S_ZOLD = S_COUNT;  // source slots this column program does not use otherwise
+static_assert(S_COUNT < MAGIC_MAX_SRC, "one spare source slot is needed for the kept toroidal potential");
 
 struct RmsPipe {
     int chunk = 0, gx = 0;
@@ -555,8 +557,6 @@ static int rms_build(magic_rloop *rl) {
     const magic_params &P = rl->p;
     if (P.l_full_sphere) MFAIL("magic_rloop_rms: full-sphere runs are not supported");
     if (!(P.l_conv || P.l_mag_kin)) MFAIL("magic_rloop_rms: needs a flow (l_conv or l_mag_kin)");
-    if (P.l_precession || P.l_centrifuge || P.l_phase_field)
-        MFAIL("magic_rloop_rms: precession, centrifugal and phase-field terms of the advection are not part of this column program");
     RmsPipe *d = new RmsPipe();
     rl->rms = d;
     BatchSpec &S = d->spec;
@@ -585,6 +585,8 @@ static int rms_build(magic_rloop *rl) {
     add_pair(S, Term{S_P, F_ONE}, N_, N_, N_, LM_ALL, nf, ri.dpdt, ri.dpdp);                              // transform_to_grid_RMS
     add_scal(S, Term{S_WOLD, F_DLH}, N_, LM_ALL, nf, ri.vro);
     add_pair(S, Term{S_DWOLD, F_ONE}, N_, Term{S_ZOLD, F_ONE}, N_, LM_ALL, nf, ri.vto, ri.vpo);
+    if (P.l_centrifuge) { add_scal(S, Term{S_S, F_ONE}, N_, LM_ALL, nf, ri.s); need({S_S}); }          // CAr reads the entropy
+    if (P.l_phase_field) { add_scal(S, Term{S_PHI, F_ONE}, N_, LM_ALL, nf, ri.phi); need({S_PHI}); }   // the penalty reads phi
     S.nfield_in = nf;
     S.afield_s = {0, 1, 2, 3};
     S.afield_vt = {4, 6, 8, 10, 12};
@@ -645,6 +647,11 @@ static int rms_run(magic_rloop *rl, const magic_fields_in *in, double dt, double
     a.ri = d->ri; a.gin = d->buf.gin; a.gout = d->buf.gout; a.n_lev = nl; a.nh = h->nh; a.n_phi = h->n_phi;
     a.l_conv_nl = P.l_conv_nl; a.l_mag_LF = P.l_mag_LF; a.l_mag_nl = P.l_mag_nl; a.l_adv_curl = P.l_adv_curl; a.n_r_LCR = P.n_r_LCR;
     a.LFfac = P.LFfac; a.CorFac = P.CorFac; a.o_dt = 1.0 / dt;
+    a.l_phase_field = P.l_phase_field; a.l_precession = P.l_precession; a.l_centrifuge = P.l_centrifuge; a.minc = h->minc;
+    a.pen = P.l_phase_field ? 1.0 / (P.epsPhase * P.epsPhase) / (P.penaltyFac * P.penaltyFac) : 0.0;
+    a.posnalp = -2.0 * P.oek * P.po * sin(P.prec_angle);
+    a.oek_time = P.oek * rl->last_time;
+    a.cafac = P.dilution_fac * P.ra * P.opr;
     a.sinth = h->d_sinth; a.costh = h->d_costh;
     for (int l0 = 0; l0 < n_r; l0 += nl) {
         const int s0 = std::min(l0, n_r - nl);

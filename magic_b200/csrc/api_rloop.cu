@@ -38,6 +38,7 @@ struct magic_rloop {
     struct DtbPipe *dtb = nullptr;    // get_dtBLM batch (api_diag.cu), built on first use
     struct ToPipe *to = nullptr;      // torsional-oscillation sums (api_diag.cu), built on first use
     struct RmsPipe *rms = nullptr;    // r.m.s. force balance batch (api_diag.cu), built on first use
+    double last_time = 0.0;           // `time` of the last pass of the loop (the precession terms of the r.m.s. batch use it)
     // LM-side prologue / epilogue: the host's radial scheme as dense matrices, radial functions on all levels
     std::vector<double> D1h, D2h, lmrad_h;  // [n_r][n_r] row-major x2; [4][n_r]: or2, orho1, dentropy0, l_R
     int n_r_mat = 0, lm_derivs = 0, lm_finish = 0;
@@ -420,6 +421,7 @@ static int rloop_begin(magic_rloop *rl, const magic_fields_in *in, const magic_f
         if (rl->need_out[i] && !x.op[i]) MFAIL("magic_rloop: a required output field is null");
     if (!out->dtrkc || !out->dthkc) MFAIL("magic_rloop: dtrkc/dthkc are null");
     x.dtrkc = out->dtrkc; x.dthkc = out->dthkc; x.time = time;
+    rl->last_time = time;
     cudaEventRecord(rl->ev[15], h->stream);
     MCHECK(cudaMemsetAsync(rl->d_torque, 0, sizeof(double) * 2, h->stream));  // rIter.f90:177-178
     return 0;

@@ -564,8 +564,8 @@ __global__ void __launch_bounds__(TO_THREADS) to_kernel(ToArgs a) {
 //   0 Advr (merged)  1 LFr  2 dtVr  3 dpkindr  |  4,5 Advt2, Advp2  6,7 LFt2, LFp2  8,9 CFt2, CFp2  10,11 PFt, PFp  12,13 dtVt, dtVp
 namespace magic {
 
-struct RmsIn { int vr, vt, vp, dvrdr, dvtdr, dvpdr, cvr, cvt, cvp, dvrdt, dvrdp, dvtdp, dvpdp, br, bt, bp, cbr, cbt, cbp, dpdt, dpdp, vro, vto, vpo; };
-constexpr int RMS_NF = 24;
+struct RmsIn { int vr, vt, vp, dvrdr, dvtdr, dvpdr, cvr, cvt, cvp, dvrdt, dvrdp, dvtdp, dvpdp, br, bt, bp, cbr, cbt, cbp, dpdt, dpdp, vro, vto, vpo, s, phi; };
+constexpr int RMS_NF = 26;
 constexpr int RMS_NOUT = 14;   // = MAGIC_NRMS
 
 struct RmsArgs {
@@ -573,8 +573,9 @@ struct RmsArgs {
     const double *gin;
     double *gout;
     int n_lev, nh, n_phi;
-    int l_conv_nl, l_mag_LF, l_mag_nl, l_adv_curl, n_r_LCR;
+    int l_conv_nl, l_mag_LF, l_mag_nl, l_adv_curl, n_r_LCR, l_phase_field, l_precession, l_centrifuge, minc;
     double LFfac, CorFac, o_dt;
+    double pen, posnalp, oek_time, cafac;   // 1 / (epsPhase penaltyFac)^2;  -2 oek po sin(prec_angle);  oek * time;  dilution_fac ra opr
     const LevelInfo *lev;
     const double *sinth, *costh;
 };
@@ -587,8 +588,14 @@ __global__ void __launch_bounds__(DIAG_THREADS) rms_kernel(RmsArgs a) {
     const bool lf = a.l_mag_LF && L.nR > a.n_r_LCR;
     const int *fidx = &a.ri.vr;
     for (unsigned pt = blockIdx.x * blockDim.x + threadIdx.x; pt < (unsigned)plane; pt += gridDim.x * blockDim.x) {
-        const int k = (int)(pt / (unsigned)a.n_phi);
+        const int k = (int)(pt / (unsigned)a.n_phi), j = (int)(pt - (unsigned)k * (unsigned)a.n_phi);
         const double st = a.sinth[k], ctn = a.costh[k], os = 1.0 / st, os2 = os * os;
+        double cph = 0.0, sph = 0.0;
+        if (a.l_precession) {  // get_nl.f90:346-357: phase oek * time + longitude
+            const double ph = a.oek_time + (double)j * (6.283185307179586476925286766559 / (double)(a.n_phi * a.minc));
+            cph = cos(ph);
+            sph = sin(ph);
+        }
         double e[RMS_NF], o[RMS_NF];
 #pragma unroll
         for (int f = 0; f < RMS_NF; f++) {
@@ -627,6 +634,11 @@ __global__ void __launch_bounds__(DIAG_THREADS) rms_kernel(RmsArgs a) {
                     Ap = or4 * orho1 * (-vr * (dvpdr - beta * vp) - vt * (dvtdp + cvr) - vp * dvpdp);
                 }
             }
+            if (a.l_phase_field) {  // get_nl.f90:333-339: the penalty is part of Advr, Advt, Advp before get_nl_RMS reads them
+                Ar -= v[25] * vr * a.pen;
+                At -= or2 * v[25] * vt * a.pen;
+                Ap -= or2 * v[25] * vp * a.pen;
+            }
             double *q = res[h];
             double PFt = v[19] * or1, PFp = v[20] * or1;
             q[8] = -2.0 * a.CorFac * ct * vp * or1;
@@ -649,6 +661,8 @@ __global__ void __launch_bounds__(DIAG_THREADS) rms_kernel(RmsArgs a) {
             q[13] = a.o_dt * or1 * (vp - v[23]);
             if (a.l_conv_nl && a.l_mag_LF) { if (lf) Ar += LFr; }   // rIter.f90:650-667
             else if (a.l_mag_LF) Ar = lf ? LFr : 0.0;
+            if (a.l_precession) Ar += a.posnalp * os * r * (cph * vp * ct + sph * vt);       // PCr, rIter.f90:669-673
+            if (a.l_centrifuge) Ar += -a.cafac * r * (st * st * st * st) * v[24];            // CAr, rIter.f90:675-678
             q[0] = Ar;
             q[1] = LFr;
         }

@@ -201,9 +201,10 @@ void orc_radial_dtB(const orc_ctx *c, const orc_params *p, const orc_radial *rad
 
 /* R.m.s. force balance inside the radial loop on lRmsCalc steps (rIter.f90:215-252, 710; RMS.f90:469-610): out[14][n_r][lm_max] =
  * AdvrLM, LFrLM, dtVrLM, dpkindrLM, Advt2LM, Advp2LM, LFt2LM, LFp2LM, CFt2LM, CFp2LM, PFt2LM, PFp2LM, dtVtLM, dtVpLM; w_old, dw_old,
- * z_old [n_r][lm_max]: the flow potentials of the previous stage-1 call (for vr_old, vt_old, vp_old); dt = tscheme%dt(1). */
+ * z_old [n_r][lm_max]: the flow potentials of the previous stage-1 call (for vr_old, vt_old, vp_old); dt = tscheme%dt(1); time
+ * enters the precession terms. */
 void orc_radial_RMS(const orc_ctx *c, const orc_params *p, const orc_radial *rad, int n_r, const orc_fields_in *in, const orc_cplx *w_old,
-                    const orc_cplx *dw_old, const orc_cplx *z_old, double dt, orc_cplx *out);
+                    const orc_cplx *dw_old, const orc_cplx *z_old, double dt, double time, orc_cplx *out);
 
 /* Torsional-oscillation sums (rIter.f90:395-404): mode 0 = getTOnext's grid part (TO.f90:330-343; fills last[n_r][3][n_phi][n_theta]
  * = BsLast, BpLast, BzLast), mode 1 = getTO (TO.f90:141-307): out[n_r][15][n_theta], colatitudes unscrambled, arrays V2AS, VAS,

@@ -392,7 +392,7 @@ class Oracle:
                                _p(out))
         return last if mode == 0 else out
 
-    def radial_RMS(self, params, radial, fields, old, dt):
+    def radial_RMS(self, params, radial, fields, old, dt, time=0.0):
         """The r.m.s. force balance inside the radial loop on lRmsCalc steps (rIter.f90:215-252, 710; RMS.f90:469-610): complex128
         [14, n_r, lm_max] (AdvrLM, LFrLM, dtVrLM, dpkindrLM, Advt2LM, Advp2LM, LFt2LM, LFp2LM, CFt2LM, CFp2LM, PFt2LM, PFp2LM, dtVtLM,
         dtVpLM).  old: dict with the w, dw, z of the previous stage-1 call."""
@@ -417,7 +417,7 @@ class Oracle:
         o = [self._c(old[k]) for k in ("w", "dw", "z")]
         out = np.zeros((14, n_r, self.lm_max), dtype=np.complex128)
         self.lib.orc_radial_RMS(self.h, C.byref(params), C.byref(rad), c_int(n_r), C.byref(fin), _p(o[0]), _p(o[1]), _p(o[2]), c_double(dt),
-                                _p(out))
+                                c_double(time), _p(out))
         return out
 
     def get_nl_mhd(self, params, nR, nBc, or2, or4, orho1, grids_in):

@@ -7,7 +7,8 @@ CPU: the oracle's restatement (oracle/magic_oracle_diag.inc orc_radial_RMS) agai
   * the same grid products formed in numpy from the oracle's golden-pinned per-call transforms and analysed with the per-call
     analyses (Coriolis, pressure-gradient and advection terms in both forms, dpkindr, the Lorentz terms, the merged AdvrLM).
 GPU (-m gpu): magic_rloop_rms_keep / magic_rloop_rms through the C ABI against the oracle on the same seeded spectra (MHD in curl
-form, anelastic hydro in u.grad u form, Boussinesq hydro; more levels than one chunk; device pointers).
+form, anelastic hydro in u.grad u form, Boussinesq hydro, MHD with precession + centrifugal acceleration + a phase field; more
+levels than one chunk; device pointers).
 "parity unpinned": samples/testRMSOutputs compares dtVrms.TAG / dtBrms.TAG, which need compute_lm_forces and the radial
 integration of dtVrms on the host.
 """
@@ -34,10 +35,15 @@ def _oparams(p):
     return op
 
 
-def _case(physics, l_max, n_r_max, lm2l, lm2m, seed, anel=False, **kw):
+def _case(physics, l_max, n_r_max, lm2l, lm2m, seed, anel=False, extra=False, **kw):
     p = make_params(physics, n_r_max, **kw)
     rad = make_radial(n_r_max, l_max, anel=anel)
     f = make_fields(physics, lm2l, lm2m, n_r_max, seed)
+    if extra:   # precession, centrifugal acceleration and a phase field: the terms that only enter AdvrLM / the penalty
+        p.l_precession, p.po, p.prec_angle, p.oek = 1, 0.3, 0.4, 1e3
+        p.l_centrifuge, p.dilution_fac, p.ra, p.opr = 1, 0.02, 1e5, 1.0
+        p.l_phase_field, p.epsPhase, p.penaltyFac, p.phaseDiffFac, p.tmelt = 1, 0.05, 0.7, 1.0, 0.3
+        f["phi"] = 0.4 * f["s"] + 0.2 * f["w"]
     rng = np.random.default_rng(seed + 3)
     f["p"] = f["s"] * (0.3 + rng.random()) + 0.1 * f["w"]
     old = {k: 0.7 * f[k] + 0.2 * f[q] for k, q in (("w", "z"), ("dw", "dz"), ("z", "w"))}
@@ -61,14 +67,14 @@ def test_oracle_rms_closed_forms_in_spectral_space():
         assert np.abs(g - r).max() <= 1e-12 * max(np.abs(r).max(), np.abs(f["p"]).max()), nm
 
 
-@pytest.mark.parametrize("physics,anel", [("mhd", False), ("anel", True)])
-def test_oracle_rms_against_products_of_the_per_call_transforms(physics, anel):
+@pytest.mark.parametrize("physics,anel,extra", [("mhd", False, False), ("anel", True, False), ("hydro", False, True)])
+def test_oracle_rms_against_products_of_the_per_call_transforms(physics, anel, extra):
     l_max, n_r = 16, 4
     o = _oracle(l_max)
-    p, rad, f, old = _case(physics, l_max, n_r, o.lm2l, o.lm2m, 9, anel=anel)
+    p, rad, f, old = _case(physics, l_max, n_r, o.lm2l, o.lm2m, 9, anel=anel, extra=extra)
     p.CorFac = 321.0
-    dt = 1e-3
-    got = o.radial_RMS(_oparams(p), rad, f, old, dt)
+    dt, time = 1e-3, 0.37
+    got = o.radial_RMS(_oparams(p), rad, f, old, dt, time=time)
     st, ct = np.sin(np.arccos(o.cosTheta))[None, :], o.cosTheta[None, :]          # grids are [n_phi, n_theta]
     os2, cn2 = 1.0 / st ** 2, ct / st ** 2
     for i in (0, 2):                                                               # a boundary level (bulk with lRmsCalc) and a bulk one
@@ -87,6 +93,10 @@ def test_oracle_rms_against_products_of_the_per_call_transforms(physics, anel):
             Ar = -or2 * orho1 * (vr * (dvrdr - (2 * or1 + beta) * vr) + os2 * (vt * (dvrdt - r * vt) + vp * (dvrdp - r * vp)))
             At = or4 * orho1 * (-vr * (dvtdr - beta * vt) + vt * (cn2 * vt + dvpdp + dvrdr) + vp * (cn2 * vp - dvtdp))
             Ap = or4 * orho1 * (-vr * (dvpdr - beta * vp) - vt * (dvtdp + cvr) - vp * dvpdp)
+        if p.l_phase_field:                                                        # get_nl.f90:333-339
+            phi = o.scal_to_spat(f["phi"][i], l_max)
+            pen = 1.0 / p.epsPhase ** 2 / p.penaltyFac ** 2
+            Ar, At, Ap = Ar - phi * vr * pen, At - or2 * phi * vt * pen, Ap - or2 * phi * vp * pen
         PFt, PFp, At2, Ap2 = or1 * dpdt, or1 * dpdp, r * At, r * Ap
         ref = {}
         if p.l_adv_curl:
@@ -106,6 +116,11 @@ def test_oracle_rms_against_products_of_the_per_call_transforms(physics, anel):
             ref["LFrLM"] = o.scal_to_SH(LFr, l_max)
             ref["LFt2LM"], ref["LFp2LM"] = o.spat_to_sphertor(r * LFt, r * LFp, l_max)
             Ar = Ar + LFr
+        if p.l_precession:                                                         # get_nl.f90:346-357, merged at rIter.f90:669-673
+            ph = (p.oek * time + 2.0 * np.pi * np.arange(o.n_phi) / (o.n_phi * o.minc))[:, None]
+            Ar = Ar - 2.0 * p.oek * p.po * np.sin(p.prec_angle) / st * r * (np.cos(ph) * vp * ct + np.sin(ph) * vt)
+        if p.l_centrifuge:                                                         # get_nl.f90:359-367, merged at rIter.f90:675-678
+            Ar = Ar - p.dilution_fac * r * st ** 4 * p.ra * p.opr * o.scal_to_spat(f["s"][i], l_max)
         ref["AdvrLM"] = o.scal_to_SH(Ar, l_max)
         for nm, rv in ref.items():
             g = got[NAMES.index(nm), i]
@@ -132,15 +147,17 @@ def _compare(got, ref, label, tol=1e-12):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("physics,l_max,n_r,anel,ktopv", [("mhd", 21, 7, False, 2), ("anel", 16, 6, True, 1), ("hydro", 32, 40, False, 2)])
-def test_gpu_rms_batch_matches_oracle(physics, l_max, n_r, anel, ktopv):
+@pytest.mark.parametrize("physics,l_max,n_r,anel,ktopv,extra", [("mhd", 21, 7, False, 2, False), ("anel", 16, 6, True, 1, False),
+                                                                 ("hydro", 32, 40, False, 2, False), ("mhd", 16, 6, False, 2, True)])
+def test_gpu_rms_batch_matches_oracle(physics, l_max, n_r, anel, ktopv, extra):
     from magic_b200 import RadialLoop, Sht
     s = Sht(l_max)
     o = _oracle(l_max)
-    p, rad, f, old = _case(physics, l_max, n_r, s.lm2l, s.lm2m, 31, anel=anel, ktopv=ktopv, kbotv=ktopv)
-    dt = 4e-4
-    ref = o.radial_RMS(_oparams(p), rad, f, old, dt)
+    p, rad, f, old = _case(physics, l_max, n_r, s.lm2l, s.lm2m, 31, anel=anel, extra=extra, ktopv=ktopv, kbotv=ktopv)
+    dt, time = 4e-4, 0.37
+    ref = o.radial_RMS(_oparams(p), rad, f, old, dt, time=time)
     rl = RadialLoop(s, p, rad)
+    rl.radialLoop(f, time=time)            # the batch follows a pass of the loop and takes its time for the precession terms
     with pytest.raises(Exception):
         rl.rms(f, dt)                      # nothing kept yet: loud
     rl.rms_keep(old)
