@@ -220,3 +220,32 @@ def test_phase_field_source_of_a_uniform_phase():
     assert np.allclose(out["dphidt"][1:-1, 0], want, rtol=1e-13)
     assert np.abs(out["dphidt"][1:-1, 1:]).max() < 1e-12 * abs(want)
     assert not out["dphidt"][[0, -1]].any()
+
+
+def test_centre_level_of_a_full_sphere_feeds_no_output():
+    """v_center_sphere (nonlinear_bcs.f90:177-224) builds the l = 1 vector field at r = 0, but the centre is a boundary level
+    (nBc = kbotv /= 0): get_td writes only dVxBhLM ~ r^2 there (get_td.f90: boundary branches), which vanishes at r = 0.  So no
+    explicit term depends on it -- it matters to the grid outputs (graphics, movies) alone, which stay with the host.  That is
+    why no golden energy series can pin it, and why nothing needs to."""
+    from magic_b200.workload import make_fields, make_params, make_radial
+    from oracle.oracle import Oracle, Params as OParams
+    l_max, n_r = 16, 6
+    o = Oracle(l_max)
+    p = make_params("mhd", n_r, ktopv=1, kbotv=1)
+    p.l_full_sphere = 1
+    rad = {k: v.copy() for k, v in make_radial(n_r, l_max).items()}
+    for k in ("r", "or1", "or2", "or4"):
+        rad[k][-1] = 0.0
+    f = make_fields("mhd", o.lm2l, o.lm2m, n_r, 3)
+    op = OParams()
+    for n, _ in p._fields_:
+        setattr(op, n, getattr(p, n))
+    a = o.radial_loop(op, rad, f)
+    g = {k: v.copy() for k, v in f.items()}
+    g["ddw"][-1, o.lm2l == 1] *= 3.7
+    g["ddb"][-1, o.lm2l == 1] *= -2.1
+    b = o.radial_loop(op, rad, g)
+    for k, v in a.items():
+        if getattr(v, "ndim", 0) == 2:
+            assert not v[-1].any() and np.array_equal(v, b[k]), k
+    assert np.abs(a["dwdt"][1:-1]).max() > 0
