@@ -158,7 +158,7 @@ static int diag_run(magic_rloop *rl, const magic_fields_in *in, int mask, int kt
     magic_sht *h = rl->h;
     MCHECK(cudaSetDevice(h->dev));
     if (!rl->diag || rl->diag->mask != mask)
-        if (diag_build(rl, mask)) return 1;
+        if (diag_build(rl, mask)) { if (rl->aux.owner == rl->diag) rl->aux.owner = nullptr; diag_free(rl->diag); rl->diag = nullptr; return 1; }
     DiagPipe *d = rl->diag;
     if (aux_acquire(rl, d, d->spec, d->chunk, d->lay, d->buf, d->gen)) return 1;
     const magic_params &P = rl->p;
@@ -316,7 +316,7 @@ static int dtb_run(magic_rloop *rl, const magic_fields_in *in, double *out, bool
     magic_sht *h = rl->h;
     MCHECK(cudaSetDevice(h->dev));
     if (!rl->dtb)
-        if (dtb_build(rl)) return 1;
+        if (dtb_build(rl)) { dtb_free(rl->dtb); rl->dtb = nullptr; return 1; }
     DtbPipe *d = rl->dtb;
     if (aux_acquire(rl, d, d->spec, d->chunk, d->lay, d->buf, d->gen)) return 1;
     const magic_params &P = rl->p;
@@ -454,7 +454,7 @@ static int to_run(magic_rloop *rl, const magic_fields_in *in, int mode, double d
     magic_sht *h = rl->h;
     MCHECK(cudaSetDevice(h->dev));
     if (!rl->to)
-        if (to_build(rl)) return 1;
+        if (to_build(rl)) { to_free(rl->to); rl->to = nullptr; return 1; }
     ToPipe *d = rl->to;
     const magic_params &P = rl->p;
     if (mode == 0 && !P.l_mag) return 0;  // TO.f90:330: only the magnetic terms keep grid fields
@@ -611,7 +611,7 @@ static int rms_keep(magic_rloop *rl, const magic_fields_in *in, bool host_in) {
     magic_sht *h = rl->h;
     MCHECK(cudaSetDevice(h->dev));
     if (!rl->rms)
-        if (rms_build(rl)) return 1;
+        if (rms_build(rl)) { rms_free(rl->rms); rl->rms = nullptr; return 1; }
     RmsPipe *d = rl->rms;
     if (!in->w || !in->dw || !in->z) MFAIL("magic_rloop_rms_keep: w, dw, z are needed");
     const size_t bytes = sizeof(double) * 2 * (size_t)h->lm_max * (size_t)rl->n_r_loc;
@@ -628,7 +628,7 @@ static int rms_run(magic_rloop *rl, const magic_fields_in *in, double dt, double
     magic_sht *h = rl->h;
     MCHECK(cudaSetDevice(h->dev));
     if (!rl->rms)
-        if (rms_build(rl)) return 1;
+        if (rms_build(rl)) { rms_free(rl->rms); rl->rms = nullptr; return 1; }
     RmsPipe *d = rl->rms;
     const magic_params &P = rl->p;
     if (aux_acquire(rl, d, d->spec, d->chunk, d->lay, d->buf, d->gen)) return 1;
