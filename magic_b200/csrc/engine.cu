@@ -147,6 +147,7 @@ int sht_init(magic_sht *h) {
     MCHECK(cudaFuncSetAttribute(extract_td_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MCHECK(cudaFuncSetAttribute(extract_td_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MCHECK(cudaFuncSetAttribute(synth_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_WARPS * MAGIC_MAX_SRC * PREP_LD * (int)sizeof(double2)));
+    cudaFuncSetAttribute(synth_prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  // its occupancy is set by the staging tile
     MCHECK(fft_setup_attributes(h->fft.H));
     MCHECK(cudaStreamSynchronize(h->stream));
     cudaFree(d_pmm);
@@ -315,10 +316,28 @@ int layout_bind(magic_sht *h, const BatchSpec &spec, Layout &L, const Buffers &b
         r2c[spec.afield_vt[i]] = R2cField{L.nf_s + 2 * i, R_WS};
         r2c[spec.afield_vp[i]] = R2cField{L.nf_s + 2 * i + 1, R_WS};
     }
+    // source slots the columns really read, renumbered densely: the operand assembly stages one shared-memory row per source and
+    // level, so unused slots (ds, p, xi in an MHD run) would cost occupancy
+    std::vector<ScalCol> scal = spec.scal;
+    std::vector<VecPair> vec = spec.vec;
+    int dense[MAGIC_MAX_SRC];
+    bool used[MAGIC_MAX_SRC] = {false};
+    auto mark = [&](const Term &t) { if (t.ftype != F_NONE) used[t.src] = true; };
+    for (const auto &c : scal) { mark(c.t[0]); mark(c.t[1]); }
+    for (const auto &v : vec) { mark(v.S[0]); mark(v.S[1]); mark(v.T[0]); mark(v.T[1]); }
+    L.nsrc = 0;
+    for (int i = 0; i < MAGIC_MAX_SRC; i++) {
+        dense[i] = -1;
+        if (used[i]) { dense[i] = L.nsrc; L.src_slot[L.nsrc++] = i; }
+    }
+    if (L.nsrc == 0) L.nsrc = -1;  // a layout whose terms are patched per call (api_sht.cu): the caller's numbering is kept
+    auto remap = [&](Term &t) { if (t.ftype != F_NONE) t.src = dense[t.src]; };
+    for (auto &c : scal) { remap(c.t[0]); remap(c.t[1]); }
+    for (auto &v : vec) { remap(v.S[0]); remap(v.S[1]); remap(v.T[0]); remap(v.T[1]); }
     if (dev_upload_vec(&L.d_offB, L.offB) || dev_upload_vec(&L.d_offC, L.offC) || dev_upload_vec(&L.d_prep_blks, blks) ||
         dev_upload_vec(&L.d_probs_syn, ps) || dev_upload_vec(&L.d_probs_an, pa) || dev_upload_vec(&L.d_tiles_syn, ts) ||
         dev_upload_vec(&L.d_tiles_an, ta) || dev_upload_vec(&L.d_colrow, cr) ||
-        dev_upload_vec(&L.d_scal, spec.scal) || dev_upload_vec(&L.d_vec, spec.vec) || dev_upload_vec(&L.d_r2c, r2c))
+        dev_upload_vec(&L.d_scal, scal) || dev_upload_vec(&L.d_vec, vec) || dev_upload_vec(&L.d_r2c, r2c))
         return 1;
     return 0;
 }
@@ -333,14 +352,18 @@ int run_synthesis(magic_sht *h, const BatchSpec &spec, const Layout &L, const Bu
                   const LevelInfo *d_lev, cudaEvent_t *ev) {
     (void)spec;
     SynthPrepArgs a{};
-    for (int i = 0; i < MAGIC_MAX_SRC; i++) a.src[i] = src[i];
+    for (int i = 0; i < MAGIC_MAX_SRC; i++)  // dense numbering of layout_bind, or the caller's own (nsrc < 0)
+        a.src[i] = L.nsrc < 0 ? src[i] : (i < L.nsrc ? src[L.src_slot[i]] : nullptr);
     a.scal = L.d_scal; a.vec = L.d_vec;
     a.ncol_s = L.ncol_s; a.npair_v = L.npair_v; a.n_lev = L.n_lev; a.lm_max = h->lm_max;
     a.N = L.N; a.lev = d_lev; a.lstart = h->d_lstart; a.clm = h->d_clm; a.l_max = h->l_max; a.minc = h->minc;
     a.B = buf.B; a.offB = L.d_offB; a.blks = L.d_prep_blks;
-    a.nsrc = 0;
-    for (int i = 0; i < MAGIC_MAX_SRC; i++)
-        if (src[i]) a.nsrc = i + 1;
+    a.nsrc = L.nsrc;
+    if (L.nsrc < 0) {
+        a.nsrc = 0;
+        for (int i = 0; i < MAGIC_MAX_SRC; i++)
+            if (src[i]) a.nsrc = i + 1;
+    }
     if (ev) cudaEventRecord(ev[0], h->stream);
     if (L.ncol && L.n_prep_blks) {
         size_t smem = (size_t)PREP_WARPS * a.nsrc * PREP_LD * sizeof(double2);

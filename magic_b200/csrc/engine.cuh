@@ -106,6 +106,7 @@ struct Layout {  // descriptors for one chunk size
     VecPair *d_vec = nullptr;
     R2cField *d_r2c = nullptr;
     bool an_wide = false;                // tile shape of the analysis GEMM this layout was sized for
+    int nsrc = 0, src_slot[MAGIC_MAX_SRC] = {0};  // sources the synthesis columns read: dense index -> caller's slot
     double flops_syn = 0, flops_an = 0;  // executed (padded) flops, for diagnostics
 };
 

@@ -161,7 +161,10 @@ __device__ __forceinline__ double2 eval_terms(const Term *t, const double2 *xs /
 //            values go to a shared tile xs[src][level][position];
 //   phase 2: thread (degree d = tid/8, level lv = tid%8) evaluates all columns of its (degree, level) and stores them: the 8
 //            lanes of a degree write 128 contiguous bytes of one operand row.
-__global__ void __launch_bounds__(PREP_WARPS * 32) synth_prep_kernel(SynthPrepArgs a) {
+#ifndef MAGIC_PREP_MINB
+#define MAGIC_PREP_MINB 4   // 64 registers: with the dense source numbering of layout_bind (11 staged sources in an MHD run, 49 KB
+#endif                      // per CTA) four CTAs fit an SM instead of three: 1.08 -> 0.95 ms per 16-level chunk at l_max = 1023
+__global__ void __launch_bounds__(PREP_WARPS * 32, MAGIC_PREP_MINB) synth_prep_kernel(SynthPrepArgs a) {
     extern __shared__ __align__(16) double2 prep_sm[];
     const int2 blk = a.blks[blockIdx.x];
     const int mc = blk.x, jt = blk.y, m = mc * a.minc;
