@@ -183,3 +183,42 @@ def test_names_imported_from_the_reference_exist_there():
                     assert re.search(r"\b%s\b" % re.escape(n.lower()), modules[mod.lower()]), f"{f}: {mod} has no {n}"
                     checked += 1
     assert checked > 150
+
+
+def test_bind_c_interfaces_have_the_arity_of_the_c_prototypes():
+    """Every bind(C) function interface lists as many dummies as its C prototype has parameters, and every call of a bound
+    function in the shims passes that many actual arguments."""
+    h = re.sub(r"/\*.*?\*/", "", _read("include", "magic_sht.h"), flags=re.S)
+    cproto = {}
+    for m in re.finditer(r"\b(?:int|void\s*\*|long long|double|const char\s*\*)\s*(magic_\w+)\s*\(([^;]*?)\)\s*;", h, re.S):
+        cproto[m.group(1)] = [p for p in (q.strip() for q in m.group(2).replace("\n", " ").split(",")) if p and p != "void"]
+    iface = re.sub(r"&\s*\n\s*&?", " ", _read("integration", "magic_b200_c.f90"))
+    arity = {}
+    for m in re.finditer(r"function\s+(magic_\w+)\s*\(([^)]*)\)\s*bind\(C,\s*name='(\w+)'\)", iface, re.I):
+        n = len([a for a in m.group(2).split(",") if a.strip()])
+        assert m.group(3) in cproto, m.group(3)
+        assert n == len(cproto[m.group(3)]), (m.group(3), n, cproto[m.group(3)])
+        arity[m.group(1).lower()] = n
+    assert len(arity) >= 35
+    calls = 0
+    for f in ("rIter_cuda.f90", "mpi_transp_cuda.f90", "sht_cuda.f90"):
+        src = "\n".join(re.sub(r"'[^']*'", "''", l).split("!")[0] for l in _read("integration", f).splitlines())
+        src = re.sub(r"&\s*\n\s*&?", " ", src)
+        for m in re.finditer(r"\b(magic_\w+)\s*\(", src):
+            name = m.group(1).lower()
+            if name not in arity:
+                continue
+            depth, j, args, cur = 1, m.end(), 0, ""
+            while depth > 0:
+                ch = src[j]
+                depth += ch == "("
+                depth -= ch == ")"
+                if (ch == "," and depth == 1) or depth == 0:
+                    args += bool(cur.strip())
+                    cur = ""
+                else:
+                    cur += ch
+                j += 1
+            assert args == arity[name], (f, name, args, arity[name])
+            calls += 1
+    assert calls >= 40
