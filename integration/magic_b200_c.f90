@@ -60,7 +60,8 @@ module magic_b200_c
 
    !-- magic_rloop_diagnostics: mask bits (include/magic_sht.h)
    integer(c_int), parameter :: MAGIC_DIAG_HEL = 1, MAGIC_DIAG_HEMI = 2, MAGIC_DIAG_POWER = 4, MAGIC_DIAG_PERPPAR = 8, &
-   &                            MAGIC_DIAG_FLUX = 16, MAGIC_DIAG_VISCBC = 32, MAGIC_DIAG_PHASE = 64, MAGIC_DIAG_RMSBULK = 256, MAGIC_NTO = 15, MAGIC_NRMS = 14
+   &                            MAGIC_DIAG_FLUX = 16, MAGIC_DIAG_VISCBC = 32, MAGIC_DIAG_PHASE = 64, MAGIC_DIAG_RMSBULK = 256, &
+   &                            MAGIC_NTO = 15, MAGIC_NRMS = 14
 
    interface
 

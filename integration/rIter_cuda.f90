@@ -171,7 +171,8 @@ contains
       if ( l_heat ) call pin(c_loc(s_Rloc), size(s_Rloc))
       if ( l_chemical_conv ) call pin(c_loc(xi_Rloc), size(xi_Rloc))
       if ( l_mag .or. l_mag_LF ) then
-         call pin(c_loc(b_Rloc), size(b_Rloc));   call pin(c_loc(db_Rloc), size(db_Rloc));  call pin(c_loc(ddb_Rloc), size(ddb_Rloc))
+         call pin(c_loc(b_Rloc), size(b_Rloc));   call pin(c_loc(db_Rloc), size(db_Rloc))
+         call pin(c_loc(ddb_Rloc), size(ddb_Rloc))
          call pin(c_loc(aj_Rloc), size(aj_Rloc)); call pin(c_loc(dj_Rloc), size(dj_Rloc))
       end if
 
@@ -304,7 +305,8 @@ contains
       !   tscheme%istage of the time-array containers, which is where transp_Rloc_to_LMloc would put them (step_time.f90:1134-1245)
       l_diag = lHelCalc .or. lPowerCalc .or. lViscBcCalc .or. lFluxProfCalc .or. lPerpParCalc .or. lHemiCalc .or. lPhaseCalc &
       &        .or. lTOCalc .or. lTONext .or. lTONext2 .or. l_RMS
-      if ( l_fused_lm .and. n_pending > 0 .and. .not. ( l_b_nl_cmb .or. l_b_nl_icb .or. l_diag .or. l_dtB .or. l_phase_field ) ) then
+      if ( l_fused_lm .and. n_pending > 0 .and.                                                    &
+      &    .not. ( l_b_nl_cmb .or. l_b_nl_icb .or. l_diag .or. l_dtB .or. l_phase_field ) ) then
          ist = tscheme%istage
          lin  = magic_lm_in(c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr)
          lout = magic_lm_out(c_null_ptr, c_null_ptr, c_null_ptr, addr_r(dtrkc), addr_r(dthkc), c_null_ptr)
@@ -496,9 +498,10 @@ contains
 
       subroutine rms_on_device()
          !-- l_RMS (rIter.f90:215-252, 433-435, 710): on lRmsCalc steps one more batch returns the fourteen spectra of
-         !   transform_to_lm_RMS for all levels (every level treated as bulk, as rIter.f90:215 does); they go into RMS's module arrays
-         !   level by level and compute_lm_forces -- the reference's own spectral sums -- runs on them.  get_nl_RMS keeps the previous
-         !   step's velocity on the grid at every stage-1 call; here its potentials stay on the device (magic_rloop_rms_keep)
+         !   transform_to_lm_RMS for all levels (every level treated as bulk, as rIter.f90:215 does); they go into RMS's module
+         !   arrays level by level and compute_lm_forces -- the reference's own spectral sums -- runs on them.  get_nl_RMS keeps
+         !   the previous step's velocity on the grid at every stage-1 call; here its potentials stay on the device
+         !   (magic_rloop_rms_keep)
          if ( l_rms_dev ) then
             if ( lRmsCalc ) then
                if ( .not. allocated(rq) ) then

@@ -222,3 +222,10 @@ def test_bind_c_interfaces_have_the_arity_of_the_c_prototypes():
             assert args == arity[name], (f, name, args, arity[name])
             calls += 1
     assert calls >= 40
+
+
+def test_free_form_line_length():
+    """gfortran truncates free-form lines at 132 characters unless told otherwise; the shims stay below."""
+    for f in ("rIter_cuda.f90", "mpi_transp_cuda.f90", "sht_cuda.f90", "magic_b200_c.f90"):
+        for n, line in enumerate(_read("integration", f).splitlines(), 1):
+            assert len(line) <= 132, (f, n, len(line))
