@@ -736,6 +736,7 @@ class ShellHost:
             else:
                 self.expl[nm][1] = self.expl[nm][0]
 
+        self._expl_w_stage = self.expl["w"][0]     # dwdt%expl(:,:,1) of a multistep scheme: the newest explicit term
         self._lm_loop(lambda nm: self._imex_rhs(nm, wts),
                       lambda: wimp * d["old"] + wl2 * d["impl"] + we1 * d["expl"][0] + we2 * d["expl"][1], wl1, rotate)
         self.n_steps += 1
@@ -857,7 +858,18 @@ class ShellHost:
 
         def up_wp(l, idx):
             if l == 0:
-                self.w[:, idx] = 0.0     # p(l=0) (get_p0Mat) does not feed back into the flow; left untouched
+                # updateWP.f90:358-394 with get_p0Mat (:2117-2190; Boussinesq / ThExpNb ViscHeatFac = 0 branch): (d/dr - beta) p00 =
+                # rho0 (BuoFac rgrav s00 + ChemFac rgrav xi00) + the explicit term of THIS stage, p00(r_cmb) = 0.  It does not feed
+                # back into the flow; the r.m.s. force balance reads it (pressure gradient and buoyancy of the l = 0 mode)
+                self.w[:, idx] = 0.0
+                ex = self._expl_w_stage
+                rhs0 = (self.rho0 * self.rgrav)[:, None] * (self.BuoFac * self.s[:, idx].real + self.ChemFac * self.xi[:, idx].real)
+                if ex is not None:
+                    rhs0 = rhs0 + ex[:, idx].real
+                rhs0[0] = 0.0
+                M0 = g.D1 - np.diag(self.beta)
+                M0[0] = np.eye(N)[0]
+                self.p[:, idx] = g.solve(M0, rhs0.astype(complex), (0,), ("p0",))
                 return
             sol = g.solve(mats["wp"][l], np.concatenate([rw[:, idx], rp[:, idx]], axis=0), (0, N - 1, N, 2 * N - 1), ("wp", l))
             self.w[:, idx] = sol[:N]
@@ -1006,6 +1018,7 @@ class DirkShellHost(ShellHost):
             def dom_rhs(ist=ist):
                 return dom_old1 + dt * sum(self.a_exp[ist, j] * dom_expl[j] + self.a_imp[ist, j] * dom_impl[j] for j in range(ist))
 
+            self._expl_w_stage = expl["w"][ist - 1]   # dwdt%expl(:,:,istage); a stage without explicit evaluation reads zeros
             self._lm_loop(rhs_of, dom_rhs, wl1, lambda nm: None)
             for nm in names:                   # get_*_rhs_imp(..., istage+1): implicit term of the new stage state
                 impl[nm].append(self.impl[nm].copy())

@@ -1,0 +1,22 @@
+"""Extracts the golden vectors of samples/testRMSOutputs from the reference tree (run in the build container).
+
+samples/testRMSOutputs/unitTest.py compares `cat dtVrms.start dtBrms.start dtVrms.continue dtBrms.continue dtVrms.FD dtBrms.FD` with
+reference.out.  The first run (input.nml, tag "start") restarts the saturated benchmark dynamo of samples/boussBenchSat (its
+checkpoint, same physics: tests/golden/boussBenchSat_ckpt.npz) with l_RMS = .true., rCut = 1e-2 and advances it by 50 BPR353 steps,
+logging every 10: the first five rows of reference.out are dtVrms.start (RMS.f90:1178-1186):
+  time, InerRms, CorRms, LFRms, AdvRms, DifRms, Buo_tempRms, Buo_xiRms, PreRms (ES16.8), then GeoRms/(Cor+Pre), MagRms/(Cor+Pre+LF),
+  ArcRms/(Cor+Pre+Buo), ArcMagRms/(Cor+Pre+LF+Buo), CLFRms/(Cor+LF), PLFRms/(Pre+LF), CIARms/(Cor+Pre+Buo+Iner+LF) (ES14.6).
+All but DifRms are built on the fourteen spectra that transform_to_lm_RMS returns from the radial loop (RMS.f90:576-610).
+"""
+import os
+
+import numpy as np
+
+REF = "/root/reference/samples/testRMSOutputs"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+rows = [np.array(l.split(), dtype=float) for l in open(os.path.join(REF, "reference.out")) if l.strip()]
+dtVrms = np.array(rows[:5])
+assert dtVrms.shape == (5, 16) and len(rows[5]) == 11        # dtBrms.start follows
+np.savez_compressed(os.path.join(HERE, "testRMSOutputs_reference.npz"), dtVrms=dtVrms, n_log_step=10, n_time_steps=50, rCut=1e-2, rDea=0.0)
+print(dtVrms[:, :5])

@@ -82,6 +82,7 @@ def _oracle_host(golden, tweak=None):
             tweak(op)
         return o.radial_loop(op, rad, f)
     h.radial_loop = loop
+    h._oracle, h._oparams, h._rad = o, op, rad      # for tests that run further oracle batches on the same state (test_testRMSOutputs)
     return h
 
 
