@@ -151,3 +151,92 @@ class RmsHost:
         return np.array([h.time, Iner, Cor, LFR, Adv, F(Dif2), Buoy, chem, Pre, Geo_ / (Cor + Pre), Mag_ / (Cor + Pre + LFR),
                          Arc_ / (Cor + Pre + Buoy + chem), ArcMag_ / (Cor + Pre + LFR + Buoy + chem), CLF_ / (Cor + LFR), PLF_ / (Pre + LFR),
                          CIA_ / (Cor + Pre + Buoy + chem + Iner + LFR)])
+
+
+class DtbHost:
+    """What the reference does with the eleven spectra of get_dtBLM (dtB.f90:144-223) on the way to dtBrms.TAG:
+
+      get_dH_dtBLM      dtB.f90:225-337    horizontal-derivative terms: poloidal / toroidal stretching, advection, omega effect
+      get_dtBLMfinish   dtB.f90:339-451    + the radial-derivative parts, and the diffusion terms from b, aj
+      get_PolTorRms     RMS_helpers.f90:30-100
+      dtBrms            RMS.f90:1239-1417  the row of dtBrms.TAG; its first two columns (the time derivative of B, updateB.f90:1638-1643
+                                           with lRmsNext) need the field at the start of the step that has just ended
+    dtb is the batch result [11, n_r, lm_max] in the order of include/magic_sht.h."""
+
+    def __init__(self, h):
+        self.h = h
+        g = h.g
+        l, m = h.lm2l.astype(int), h.lm2m.astype(int)
+        self.l, self.m, self.l_max = l, m, int(l.max())
+        clm = lambda ll, mm: np.sqrt(((ll + mm) * (ll - mm)) / ((2.0 * ll - 1.0) * (2.0 * ll + 1.0)))
+        lf, mf = l.astype(float), m.astype(float)
+        self.dTheta1S = (lf + 1.0) * clm(lf, mf)              # horizontal.f90:219-220
+        self.dTheta1A = lf * clm(lf + 1.0, mf)
+        lm = np.arange(len(l))
+        self.lmA = np.where(l < self.l_max, lm + 1, -1)
+        self.lmS = np.where(l > m, lm - 1, -1)
+        self.vol_oc = 4.0 / 3.0 * np.pi * (g.r_cmb ** 3 - g.r_icb ** 3)
+
+    def _nb(self, f, idx):          # f at the neighbouring degree (0 where there is none: its coefficient vanishes there)
+        return np.where(idx[None, :] >= 0, f[:, np.maximum(idx, 0)], 0.0)
+
+    def _poltor(self, Pol, drPol, Tor):
+        """get_PolTorRms: (PolRms, TorRms, PolAsRms, TorAsRms)."""
+        g = self.h.g
+        dLh = (self.l * (self.l + 1.0))[None, :]
+        m = self.m[None, :]
+        P = dLh * (dLh * g.or2[:, None] * _cc2real(Pol, m) + _cc2real(drPol, m))
+        T = dLh * _cc2real(Tor, m)
+        ax = (self.m == 0)
+        out = []
+        for q in (P.sum(axis=1), T.sum(axis=1), P[:, ax].sum(axis=1), T[:, ax].sum(axis=1)):
+            out.append(np.sqrt(g.rInt_R(q) / self.vol_oc))
+        return out
+
+    def row(self, dtb, b_start, aj_start, dt):
+        h, g = self.h, self.h.g
+        BtVr, BpVr, BrVt, BrVp, BtVp, BpVt, Cot, Sn2, BrVZ, BtVZ, _ = dtb
+        or1, or2 = g.or1[:, None], g.or2[:, None]
+        or3 = or1 * or2
+        dLh = (self.l * (self.l + 1.0))[None, :]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            fac = np.where(dLh > 0, or2 / np.where(dLh > 0, dLh, 1.0), 0.0)
+        not0 = (self.l > 0)[None, :]
+        dPhi2 = -(self.m.astype(float) ** 2)[None, :]                       # dPhi(lm)**2 = (i m)^2
+        d1S, d1A = self.dTheta1S[None, :], self.dTheta1A[None, :]
+        cotS, cotA = self._nb(Cot, self.lmS), self._nb(Cot, self.lmA)
+        vzS, vzA = self._nb(BrVZ, self.lmS), self._nb(BrVZ, self.lmA)
+        # get_dH_dtBLM
+        Pstr, Padv = not0 * or2 * BtVr, not0 * or2 * BrVt
+        TstrR, TadvR = not0 * or1 * BrVp, not0 * or2 * BpVr
+        hor = fac * (d1S * cotS - d1A * cotA) - fac * dPhi2 * Sn2
+        Tstr = not0 * (-or2 * BtVp + or3 * BpVr + hor)
+        Tadv = not0 * (-or2 * BpVt + or3 * BrVp + hor)
+        TomeR = not0 * fac * (d1S * vzS - d1A * vzA)
+        Tome = not0 * (-or2 * BtVZ) - or1 * TomeR
+        # get_dtBLMfinish
+        D1 = g.D1t
+        Tome, Tstr, Tadv = Tome + or1 * (D1 @ TomeR), Tstr + or1 * (D1 @ TstrR), Tadv + or1 * (D1 @ TadvR)
+        lam = h.lam[:, None] if hasattr(h, "lam") else 1.0
+        dLlam = h.dLlam[:, None] if hasattr(h, "dLlam") else 0.0
+        Pdif = h.opm * lam * (h.ddb - dLh * or2 * h.b)
+        Tdif = h.opm * lam * (g.D2 @ h.aj + dLlam * h.dj - dLh * or2 * h.aj)
+        # dtBrms
+        Pdyn, drPdyn, Tdyn = Pstr - Padv, D1 @ Pstr - D1 @ Padv, Tstr - Tadv
+        PdynRms, TdynRms, _, _ = self._poltor(Pdyn, drPdyn, Tdyn)
+        drPdif = D1 @ Pdif
+        PdifRms, TdifRms, _, _ = self._poltor(Pdif, drPdif, Tdif)
+        _, TomeRms, _, TomeAsRms = self._poltor(Pdif, drPdif, Tome)
+        dip = ((self.l == 1) & (self.m <= 1))[None, :]
+        DdynRms, _, DdynAsRms, _ = self._poltor(np.where(dip, Pdyn, 0.0), np.where(dip, drPdyn, 0.0), Tdyn)
+        # time derivative of the field over the step that has just ended (updateB.f90:1638-1643)
+        dtP = dLh * or2 / dt * (h.b - b_start)
+        dtT = dLh * or2 / dt * (h.aj - aj_start)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dtBPolLMr = np.where(dLh > 0, g.r[:, None] ** 2 / np.where(dLh > 0, dLh, 1.0) * dtP, 0.0)
+            tor = np.where(dLh > 0, g.r[:, None] ** 4 / np.where(dLh > 0, dLh, 1.0) * _cc2real(dtT, self.m[None, :]), 0.0)
+        pol = g.r[:, None] ** 2 * _cc2real(dtP, self.m[None, :]) + dLh * _cc2real(D1 @ dtBPolLMr, self.m[None, :])
+        dtBPolRms = np.sqrt(g.rInt_R((not0 * pol).sum(axis=1)) / self.vol_oc)
+        dtBTorRms = np.sqrt(g.rInt_R((not0 * tor).sum(axis=1)) / self.vol_oc)
+        return np.array([h.time, dtBPolRms, dtBTorRms, PdynRms, TdynRms, PdifRms, TdifRms, TomeRms / TdynRms, TomeAsRms / TdynRms, DdynRms,
+                         DdynAsRms])
