@@ -240,3 +240,207 @@ class DtbHost:
         dtBTorRms = np.sqrt(g.rInt_R((not0 * tor).sum(axis=1)) / self.vol_oc)
         return np.array([h.time, dtBPolRms, dtBTorRms, PdynRms, TdynRms, PdifRms, TdifRms, TomeRms / TdynRms, TomeAsRms / TdynRms, DdynRms,
                          DdynAsRms])
+
+
+def simps(f, r):
+    """integration.f90 simps: Simpson's rule on a non-uniform, DEcreasing grid."""
+    f, r = np.asarray(f, dtype=float), np.asarray(r, dtype=float)
+    n = len(f)
+
+    def seg(i):   # 0-based centre i: points i-1, i, i+1
+        h2, h1 = r[i + 1] - r[i], r[i] - r[i - 1]
+        return (h1 + h2) / 6.0 * (f[i - 1] * (2.0 * h1 - h2) / h1 + f[i] * (h1 + h2) * (h1 + h2) / (h1 * h2) + f[i + 1] * (2.0 * h2 - h1) / h2)
+    if n % 2 == 1:
+        return -sum(seg(i) for i in range(1, n - 1, 2))
+    tot = 0.5 * (r[1] - r[0]) * (f[1] + f[0])
+    tot += sum(seg(i) for i in range(2, n - 1, 2))
+    tot += 0.5 * (r[n - 1] - r[n - 2]) * (f[n - 1] + f[n - 2])
+    tot += sum(seg(i) for i in range(1, n - 1, 2))
+    return -0.5 * tot
+
+
+class ToHost:
+    """What the reference does with getTO's (r, theta) arrays on the way to Tay.TAG (out_TO.f90:213-556): the z-averages on a
+    cylindrical grid (cylmean_otc / cylmean_itc, integration.f90:157-533: fourth-order Lagrange interpolation in r and theta,
+    Simpson in z), the Taylorisation measures and the geostrophic flow energy; and getTOfinish's axisymmetric viscous stress
+    (TO.f90:354-390, get_PAS :392-425).  to is the batch result [n_r, 15, n_theta] in the order of include/magic_sht.h."""
+
+    def __init__(self, h, theta_ord, toraxi_to_spat, sDens=1.0, zDens=1.0):
+        self.h, self.theta, self.toraxi_to_spat, self.zDens = h, np.asarray(theta_ord, dtype=float), toraxi_to_spat, zDens
+        g = h.g
+        N = len(g.r)
+        self.n_s_max = int(sDens * (N + int(g.r_icb * N)))                      # preCalculations.f90:768-769
+        smin, smax = g.r_cmb * np.sin(self.theta[0]), g.r_cmb
+        ds = (smax - smin) / (self.n_s_max - 1)
+        self.cyl = g.r_cmb - np.arange(self.n_s_max) * ds                       # out_TO.f90:98-103
+        self.hh = np.zeros(self.n_s_max)
+        for i, s in enumerate(self.cyl):
+            if s >= g.r_icb:
+                self.hh[i] = 2.0 * np.sqrt(g.r_cmb ** 2 - s ** 2)
+                self.n_s_otc = i + 1                                            # last index (1-based) outside the tangent cylinder
+            else:
+                self.hh[i] = np.sqrt(g.r_cmb ** 2 - s ** 2) - np.sqrt(g.r_icb ** 2 - s ** 2)
+        k = self.n_s_otc
+        self.volcyl_oc = 2.0 * np.pi * (simps(self.hh * self.cyl, self.cyl) + simps(self.hh[k:] * self.cyl[k:], self.cyl[k:]))
+        self.vol_oc = 4.0 / 3.0 * np.pi * (g.r_cmb ** 3 - g.r_icb ** 3)
+
+    def _interp(self, a, rc, thet, south):
+        """The Lagrange interpolation shared by cylmean_otc and cylmean_itc; a is [n_theta, n_r] (ordered colatitudes)."""
+        r, theta = self.h.g.r, self.theta
+        n_r_max, n_theta_max = len(r), len(theta)
+        n_r2 = n_r_max - 1                       # 1-based indices as in the reference
+        for n_r in range(n_r_max - 1, 0, -1):
+            if r[n_r - 1] >= rc:
+                n_r2 = n_r
+                break
+        if n_r2 == n_r_max - 1:
+            n_r2 = n_r_max - 2
+        if n_r2 == 1:
+            n_r2 = 2
+        n_r3, n_r1, n_r0 = n_r2 - 1, n_r2 + 1, n_r2 + 2
+        if thet < theta[0]:
+            n_th1 = 1
+        else:
+            n_th1 = n_theta_max
+            for n_th in range(n_theta_max, 0, -1):
+                if theta[n_th - 1] <= thet:
+                    n_th1 = n_th
+                    break
+        if n_th1 == n_theta_max:
+            n_th1 = n_theta_max - 2
+        if n_th1 == n_theta_max - 1:
+            n_th1 = n_theta_max - 2
+        if n_th1 == 1:
+            n_th1 = 2
+        n_th2, n_th3, n_th0 = n_th1 + 1, n_th1 + 2, n_th1 - 1
+        R = lambda i: r[i - 1]
+        T = lambda i: theta[i - 1]
+        rr0, rr1, rr2, rr3 = rc - R(n_r0), rc - R(n_r1), rc - R(n_r2), rc - R(n_r3)
+        r10, r20, r30 = 1.0 / (R(n_r1) - R(n_r0)), 1.0 / (R(n_r2) - R(n_r0)), 1.0 / (R(n_r3) - R(n_r0))
+        r21, r31, r32 = 1.0 / (R(n_r2) - R(n_r1)), 1.0 / (R(n_r3) - R(n_r1)), 1.0 / (R(n_r3) - R(n_r2))
+        tt0, tt1, tt2, tt3 = thet - T(n_th0), thet - T(n_th1), thet - T(n_th2), thet - T(n_th3)
+        t10, t20, t30 = 1.0 / (T(n_th1) - T(n_th0)), 1.0 / (T(n_th2) - T(n_th0)), 1.0 / (T(n_th3) - T(n_th0))
+        t21, t31, t32 = 1.0 / (T(n_th2) - T(n_th1)), 1.0 / (T(n_th3) - T(n_th1)), 1.0 / (T(n_th3) - T(n_th2))
+        ait = [0.0] * 4
+        for itr in range(4):
+            n_th = n_th0 + itr
+            if south:
+                n_th = n_theta_max + 1 - n_th
+            A = lambda nr: a[n_th - 1, nr - 1]
+            a01 = (rr0 * A(n_r1) - rr1 * A(n_r0)) * r10
+            a12 = (rr1 * A(n_r2) - rr2 * A(n_r1)) * r21
+            a23 = (rr2 * A(n_r3) - rr3 * A(n_r2)) * r32
+            a012 = (rr0 * a12 - rr2 * a01) * r20
+            a123 = (rr1 * a23 - rr3 * a12) * r31
+            ait[itr] = (rr0 * a123 - rr3 * a012) * r30
+        a01 = (tt0 * ait[1] - tt1 * ait[0]) * t10
+        a12 = (tt1 * ait[2] - tt2 * ait[1]) * t21
+        a23 = (tt2 * ait[3] - tt3 * ait[2]) * t32
+        a012 = (tt0 * a12 - tt2 * a01) * t20
+        a123 = (tt1 * a23 - tt3 * a12) * t31
+        return (tt0 * a123 - tt3 * a012) * t30
+
+    def cylmean(self, a):
+        """out_TO.f90 cylmean: z-averages (north, south) of a[n_theta, n_r] on the cylindrical grid."""
+        g = self.h.g
+        r_cmb, r_icb = g.r[0], g.r[-1]
+        eps = 10.0 * np.finfo(float).eps
+        n_s_max, n_theta_max = self.n_s_max, len(self.theta)
+        vN, vS = np.zeros(n_s_max), np.zeros(n_s_max)
+
+        def angle(s, z, rc):
+            if s == 0.0 or z > rc:
+                return 0.0
+            return np.arccos(z / rc)
+        for n_s in range(1, self.n_s_otc + 1):                      # cylmean_otc
+            s = self.cyl[n_s - 1]
+            zmax, zmin = np.sqrt(r_cmb * r_cmb - s * s), 0.0
+            nz = 2 * int(n_s_max * (zmax - zmin) / (2.0 * r_cmb))
+            nz = max(int(self.zDens * nz), 4)
+            dz = (zmax - zmin) / nz
+            ac = {}
+            for n_z in range(-nz, nz + 1):
+                z = zmin + dz * n_z
+                rc = np.sqrt(s * s + z * z)
+                if rc >= r_cmb:
+                    rc = r_cmb - eps
+                ac[n_z] = self._interp(a, rc, angle(s, z, rc), False)
+            tot = ac[-nz] + ac[nz]
+            tot += sum(4.0 * ac[n_z] for n_z in range(-nz + 1, nz, 2))
+            tot += sum(2.0 * ac[n_z] for n_z in range(-nz + 2, nz - 1, 2))
+            vN[n_s - 1] = vS[n_s - 1] = tot / (6.0 * nz)
+        vN[0] = vS[0] = 0.5 * (a[n_theta_max // 2 - 1, 0] + a[n_theta_max // 2, 0])
+        for n_s in range(self.n_s_otc + 1, n_s_max + 1):            # cylmean_itc
+            s = self.cyl[n_s - 1]
+            zmax, zmin = np.sqrt(r_cmb * r_cmb - s * s), np.sqrt(r_icb * r_icb - s * s)
+            nz = 2 * int(n_s_max * (zmax - zmin) / (2.0 * r_cmb))
+            nz = max(int(self.zDens * nz), 4)
+            dz = (zmax - zmin) / nz
+            acn, acs = [], []
+            for n_z in range(0, nz + 1):
+                z = zmin + dz * n_z
+                rc = np.sqrt(s * s + z * z)
+                if rc >= r_cmb:
+                    rc = r_cmb - eps
+                if rc <= r_icb:
+                    rc = r_icb + eps
+                th = angle(s, z, rc)
+                acn.append(self._interp(a, rc, th, False))
+                acs.append(self._interp(a, rc, th, True))
+            for ac, v in ((acn, vN), (acs, vS)):
+                tot = ac[0] + ac[nz]
+                tot += sum(4.0 * ac[n_z] for n_z in range(1, nz, 2))
+                tot += sum(2.0 * ac[n_z] for n_z in range(2, nz - 1, 2))
+                v[n_s - 1] = tot / (3.0 * nz)
+        return vN, vS
+
+    def dzStrAS(self):
+        """getTOfinish's viscous stress of the axisymmetric toroidal flow, TO.f90:372-386 + get_PAS: [n_theta (ordered), n_r]."""
+        h, g = self.h, self.h.g
+        m0 = np.nonzero(h.lm2m == 0)[0]
+        l = h.lm2l[m0].astype(float)
+        z, dz, ddz = h.z[:, m0].real, h.dz[:, m0].real, (g.D2 @ h.z)[:, m0].real
+        dLh = l * (l + 1.0)
+        out = np.zeros((len(self.theta), len(g.r)))
+        n = len(self.theta)
+        ordered = np.array([t // 2 if t % 2 == 0 else n - 1 - t // 2 for t in range(n)])
+        for i in range(len(g.r)):
+            strl = ddz[i] - h.beta[i] * dz[i] - (dLh * g.or2[i] + h.dbeta[i] + 2.0 * h.beta[i] * g.or1[i]) * z[i]
+            strl[l == 0] = 0.0
+            _, tmpp = self.toraxi_to_spat(strl.astype(complex), int(l.max()))
+            sin_scr = np.zeros(n)
+            sin_scr[:] = np.sin(self.theta[ordered])
+            out[ordered, i] = tmpp / sin_scr * g.or1[i]
+        return out
+
+    def row(self, to, e_kin_cols):
+        """One row of Tay.TAG (out_TO.f90:515-553)."""
+        h = self.h
+        VAS, dzRstr, dzLF = (np.ascontiguousarray(to[:, q, :].T) for q in (1, 3, 5))
+        dzStr = self.dzStrAS()
+        VpN, VpS = self.cylmean(VAS)
+        LFN, LFS = self.cylmean(dzLF)
+        TayN, TayS = self.cylmean(np.abs(dzLF))
+        RstrN, RstrS = self.cylmean(dzRstr)
+        TayRN, TayRS = self.cylmean(np.abs(dzRstr))
+        StrN, StrS = self.cylmean(dzStr)
+        TayVN, TayVS = self.cylmean(np.abs(dzStr))
+
+        def ratio(num, den):      # out_TO.f90:338-349 (the test is on the northern value for both hemispheres)
+            return np.where(np.abs(den[0]) > 0.0, num[0] / np.where(den[0] != 0, den[0], 1.0), den[0]), \
+                   np.where(np.abs(den[0]) > 0.0, num[1] / np.where(den[1] != 0, den[1], 1.0), den[1])
+        TayN, TayS = ratio((LFN, LFS), (TayN, TayS))
+        TayRN, TayRS = ratio((RstrN, RstrS), (TayRN, TayRS))
+        TayVN, TayVS = ratio((StrN, StrS), (TayVN, TayVS))
+        cyl, hh, k = self.cyl, self.hh, self.n_s_otc
+
+        def integ(fn, fs):
+            return simps(fn * cyl * hh, cyl) + simps(fs[k:] * cyl[k:] * hh[k:], cyl[k:])
+        VgRMS = np.sqrt(2.0 * np.pi * integ(VpN * VpN, VpS * VpS) / self.volcyl_oc)
+        TayRMS, TayRRMS, TayVRMS = (2.0 * np.pi * integ(np.abs(a), np.abs(b)) / self.volcyl_oc
+                                    for a, b in ((TayN, TayS), (TayRN, TayRS), (TayVN, TayVS)))
+        eKin, eKinTAS = e_kin_cols[0] + e_kin_cols[1], e_kin_cols[3]
+        VRMS, VpRMS = np.sqrt(2.0 * eKin / self.vol_oc), np.sqrt(2.0 * eKinTAS / self.vol_oc)
+        if VRMS != 0.0:
+            VpRMS, VgRMS = VpRMS / VRMS, VgRMS / VRMS
+        return np.array([h.time, VpRMS ** 2, VgRMS ** 2, TayRMS, TayRRMS, TayVRMS, eKin])

@@ -1,0 +1,23 @@
+"""Extracts the golden vectors of samples/testTOGeosOutputs from the reference tree (run in the build container).
+
+samples/testTOGeosOutputs/unitTest.py compares `cat geos.start Tay.start tmp` with reference.out, tmp being points of the TO movie,
+of TOnhs / TOshs and of the geos movies printed with four decimals.  The run restarts the saturated benchmark dynamo of
+samples/boussBenchSat (its checkpoint, same physics: tests/golden/boussBenchSat_ckpt.npz) with l_TO = .true., n_TO_step = 5 and
+advances it by 25 BPR353 steps.  Rows 7-11 of reference.out are Tay.start (out_TO.f90:552-553):
+  time, VpRMS^2, VgRMS^2, TayRMS, TayRRMS, TayVRMS, eKin   (ES16.8)
+-- the energy fractions of the axisymmetric / geostrophic azimuthal flow and the Taylorisation measures of the Lorentz, Reynolds and
+viscous stresses, z-averaged on a cylindrical grid from the (r, theta) arrays VAS, dzLFAS, dzRstrAS that getTO fills inside the
+radial loop (TO.f90:141-307) and dzStrAS of getTOfinish.
+"""
+import os
+
+import numpy as np
+
+REF = "/root/reference/samples/testTOGeosOutputs"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+rows = [np.array(l.split(), dtype=float) for l in open(os.path.join(REF, "reference.out")) if l.strip()]
+tay = np.array([r for r in rows if len(r) == 7 and r[0] > 100.0])
+assert tay.shape == (5, 7)
+np.savez_compressed(os.path.join(HERE, "testTOGeosOutputs_reference.npz"), Tay=tay, n_TO_step=5, n_time_steps=25)
+print(tay)
