@@ -39,9 +39,20 @@
  *       the 25 BPR353 steps of samples/doubleDiffusion and of samples/boussBenchSat (saturated dynamo, conducting rotating
  *       inner core) from their shipped checkpoints (tests/test_doubleDiffusion.py, tests/test_boussBenchSat.py);
  *   (10) for a radially varying viscosity in the viscous heating: the 250 steps of samples/varProps (tests/test_varProps.py).
+ *   (11) for the in-loop diagnostics of log steps (orc_radial_diagnostics: get_helicity, get_hemi, get_visc_heat): helicity.TAG,
+ *       hemi.TAG and the viscous column of power.TAG of samples/testOutputs (tests/test_testOutputs.py);
+ *   (12) for the phase-field branch of get_nl and get_ekin_solid_liquid: e_kin.TAG and all fifteen columns of phase.TAG of the
+ *       Chebyshev stage of samples/phase_field (tests/test_phase_field.py);
+ *   (13) for the r.m.s. force-balance batch (orc_radial_RMS) and get_dtBLM (orc_radial_dtB): all sixteen columns of dtVrms.TAG and
+ *       all eleven of dtBrms.TAG of samples/testRMSOutputs, host side restated in oracle/rms_host.py (tests/test_testRMSOutputs.py);
+ *   (14) for getTO (orc_radial_TO): all seven columns of Tay.TAG of samples/testTOGeosOutputs through the cylindrical averaging of
+ *       outTO restated in oracle/rms_host.py (tests/test_testTOGeosOutputs.py).
+ * Every one of these tests has a -m gpu leg in which the CUDA library takes the oracle's place in the same time loop.
  * Still "parity unpinned" (no reference vectors reachable here, literal line-cited restatements only): the r = 0 level
- * itself (v_center_sphere: the energies of (5) are insensitive to it, measured) and the inner-core (_IC) and axisymmetric
- * syntheses (diagnostics, not called by the radial loop).
+ * itself (v_center_sphere: it feeds no output of the loop, tests/test_oracle_analytic.py), get_perpPar / get_fluxes /
+ * get_nlBLayers (samples/testRadialOutputs lacks its checkpoint: closed forms only), the arrays of getTO and the eleventh product
+ * of get_dtBLM that only movie frames read, and the inner-core (_IC) and axisymmetric syntheses (per-call diagnostics; the
+ * toroidal one is exercised by (14)).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may call
  * into this library.  The product path (magic_b200/) never links or imports it.
