@@ -19,5 +19,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 rows = [np.array(l.split(), dtype=float) for l in open(os.path.join(REF, "reference.out")) if l.strip()]
 tay = np.array([r for r in rows if len(r) == 7 and r[0] > 100.0])
 assert tay.shape == (5, 7)
-np.savez_compressed(os.path.join(HERE, "testTOGeosOutputs_reference.npz"), Tay=tay, n_TO_step=5, n_time_steps=25)
-print(tay)
+# the line after Tay.start: seven points of the TO movie (unitTest.py:50-53; frames are written on the TO steps, single precision,
+# printed with four decimals): to.asVphi[0, 13, 3], to.rey[1, 21, 22], to.adv[1, 52, 11], to.visc[0, 12, 25], to.lorentz[0, 73, 30],
+# to.coriolis[1, 33, 3], to.dtVp[1, 88, 7] -- [frame, theta (ordered), r] of VAS, dzRstrAS, dzAstrAS, dzStrAS, LFfac dzLFAS, dzCorAS,
+# dzdVpAS (out_TO.f90:564-575, python/magic/TOreaders.py:122-135)
+mov = [r for r in rows if len(r) == 7 and r[0] < 100.0]
+assert len(mov) == 1
+points = np.array([[0, 13, 3], [1, 21, 22], [1, 52, 11], [0, 12, 25], [0, 73, 30], [1, 33, 3], [1, 88, 7]])
+np.savez_compressed(os.path.join(HERE, "testTOGeosOutputs_reference.npz"), Tay=tay, n_TO_step=5, n_time_steps=25, movie_values=mov[0],
+                    movie_points=points)
+print(tay, mov[0])

@@ -10,7 +10,9 @@ Host: oracle/lmloop.py DirkShellHost (as tests/test_boussBenchSat.py) and oracle
 simps, the row of Tay.TAG, getTOfinish's viscous stress through toraxi_to_spat).  getTO is the CPU oracle's orc_radial_TO with the
 oracle's loop in the time loop (CPU leg: first row) or magic_rloop_to_next / magic_rloop_to through the C ABI with the CUDA loop
 (GPU leg: all five rows, called on the steps rIter_cuda_t calls them on; the device's fifteen arrays are also held against the
-oracle's, kept fields included).  Fixture: tests/golden/testTOGeosOutputs_reference.npz + boussBenchSat_ckpt.npz.
+oracle's, kept fields included).  The autotest also prints seven points of the TO movie with four decimals: single values of VAS,
+dzRstrAS, dzAstrAS, dzStrAS, dzLFAS and dzCorAS at given (theta, r) of the first two TO steps (e.g. dzCorAS = 422.0722,
+LFfac dzLFAS = -3903.9583), compared here as well -- frame 0 in the CPU leg, frames 0 and 1 in the GPU leg.  Fixture: tests/golden/testTOGeosOutputs_reference.npz + boussBenchSat_ckpt.npz.
 """
 import os
 
@@ -36,6 +38,19 @@ def _fields(h):
     return {k: np.ascontiguousarray(v) for k, v in h.fields_Rloc().items()}
 
 
+def _check_movie_points(golden, h, to_host, arrays, frame):
+    """The TO movie stores VAS, dzRstrAS, dzAstrAS, dzStrAS, LFfac dzLFAS, dzCorAS (and dzdVpAS) of every TO step in single
+    precision; the autotest prints seven of its points with four decimals (unitTest.py:50-53)."""
+    LFfac = 1.0 / (float(golden["ek"]) * float(golden["prmag"]))
+    get = {0: lambda t, r: arrays[r, 1, t], 1: lambda t, r: arrays[r, 3, t], 2: lambda t, r: arrays[r, 4, t],
+           3: lambda t, r: to_host.dzStrAS()[t, r], 4: lambda t, r: LFfac * arrays[r, 5, t], 5: lambda t, r: arrays[r, 2, t]}
+    for q, ((fr, t, r), ref) in enumerate(zip(golden["movie_points"], golden["movie_values"])):
+        if fr != frame or q not in get:
+            continue
+        got = float(np.float32(get[q](t, r)))
+        assert abs(got - ref) <= 5.1e-5 + 1e-7 * abs(ref), (q, got, ref)
+
+
 def _run(golden, h, to_host, to_next, to, n_rows):
     """step_time.f90:355-382 with n_TO_step = 5: getTOnext's kept fields at the first stage of steps 5, 10, ..., getTO (with the
     previous time step as dtLast) and outTO at the first stage of steps 6, 11, ..."""
@@ -45,8 +60,10 @@ def _run(golden, h, to_host, to_next, to, n_rows):
     for step in range(1, n_rows * n_to + 2):        # `step` = n_time_step of the reference; its first stage sees `step - 1` steps done
         f = _fields(h)
         if step > 2 and (step - 1) % n_to == 0:
-            rows.append(to_host.row(to(f, dt), h.e_kin()))
+            arrays = to(f, dt)
+            rows.append(to_host.row(arrays, h.e_kin()))
             np.testing.assert_allclose(rows[-1], golden["Tay"][len(rows) - 1], rtol=RTOL, err_msg=f"Tay row {len(rows) - 1}")
+            _check_movie_points(golden, h, to_host, arrays, frame=len(rows) - 1)
             if len(rows) == n_rows:
                 break
         if step % n_to == 0:
