@@ -413,25 +413,35 @@ class ToHost:
             out[ordered, i] = tmpp / sin_scr * g.or1[i]
         return out
 
-    def row(self, to, e_kin_cols):
-        """One row of Tay.TAG (out_TO.f90:515-553)."""
-        h = self.h
+    def cyl_means(self, to, with_hemi_files=False):
+        """The z-averages outTO forms (out_TO.f90:278-350): name -> (north, south) on the cylindrical grid.  with_hemi_files adds
+        what only TOnhs / TOshs.TAG hold (:477-507): the axisymmetric stress and the relative geostrophic flow VpRInt."""
         VAS, dzRstr, dzLF = (np.ascontiguousarray(to[:, q, :].T) for q in (1, 3, 5))
         dzStr = self.dzStrAS()
-        VpN, VpS = self.cylmean(VAS)
-        LFN, LFS = self.cylmean(dzLF)
-        TayN, TayS = self.cylmean(np.abs(dzLF))
-        RstrN, RstrS = self.cylmean(dzRstr)
-        TayRN, TayRS = self.cylmean(np.abs(dzRstr))
-        StrN, StrS = self.cylmean(dzStr)
-        TayVN, TayVS = self.cylmean(np.abs(dzStr))
+        c = {"Vp": self.cylmean(VAS), "LF": self.cylmean(dzLF), "Rstr": self.cylmean(dzRstr), "Str": self.cylmean(dzStr)}
 
         def ratio(num, den):      # out_TO.f90:338-349 (the test is on the northern value for both hemispheres)
             return np.where(np.abs(den[0]) > 0.0, num[0] / np.where(den[0] != 0, den[0], 1.0), den[0]), \
                    np.where(np.abs(den[0]) > 0.0, num[1] / np.where(den[1] != 0, den[1], 1.0), den[1])
-        TayN, TayS = ratio((LFN, LFS), (TayN, TayS))
-        TayRN, TayRS = ratio((RstrN, RstrS), (TayRN, TayRS))
-        TayVN, TayVS = ratio((StrN, StrS), (TayVN, TayVS))
+        c["Tay"] = ratio(c["LF"], self.cylmean(np.abs(dzLF)))
+        c["TayR"] = ratio(c["Rstr"], self.cylmean(np.abs(dzRstr)))
+        c["TayV"] = ratio(c["Str"], self.cylmean(np.abs(dzStr)))
+        if with_hemi_files:
+            c["Astr"] = self.cylmean(np.ascontiguousarray(to[:, 4, :].T))
+            V2 = self.cylmean(np.ascontiguousarray(to[:, 0, :].T))
+            vpr = []
+            for vp, v2 in zip(c["Vp"], V2):          # out_TO.f90:318-335
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    q = np.where(v2 < 0.0, 1.0, np.where(np.abs(v2) <= 10.0 * np.finfo(float).eps, 0.0, np.abs(vp) / np.sqrt(np.abs(v2))))
+                vpr.append(np.minimum(1.0, q))
+            c["VpR"] = tuple(vpr)
+        return c
+
+    def row(self, to, e_kin_cols, means=None):
+        """One row of Tay.TAG (out_TO.f90:515-553)."""
+        h = self.h
+        c = means if means is not None else self.cyl_means(to)
+        (VpN, VpS), (TayN, TayS), (TayRN, TayRS), (TayVN, TayVS) = c["Vp"], c["Tay"], c["TayR"], c["TayV"]
         cyl, hh, k = self.cyl, self.hh, self.n_s_otc
 
         def integ(fn, fs):

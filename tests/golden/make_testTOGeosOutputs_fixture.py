@@ -26,6 +26,10 @@ assert tay.shape == (5, 7)
 mov = [r for r in rows if len(r) == 7 and r[0] < 100.0]
 assert len(mov) == 1
 points = np.array([[0, 13, 3], [1, 21, 22], [1, 52, 11], [0, 12, 25], [0, 73, 30], [1, 33, 3], [1, 88, 7]])
+# the two lines after that: points of TOnhs.TAG and TOshs.TAG (unitTest.py:56-63; z-averages on the cylindrical grid, [TO step, n_s]):
+# north  to.vp[2, 18], to.rstr[3, 11], to.astr[0, 30], to.LF[2, 21];  south  to.dvp[3, 12], to.viscstr[1, 9], to.tay[4, 27], to.vpr[2, 21]
+hemi = [r for r in rows if len(r) == 4]
+assert len(hemi) == 2
 np.savez_compressed(os.path.join(HERE, "testTOGeosOutputs_reference.npz"), Tay=tay, n_TO_step=5, n_time_steps=25, movie_values=mov[0],
-                    movie_points=points)
-print(tay, mov[0])
+                    movie_points=points, nhs_values=hemi[0], shs_values=hemi[1])
+print(tay, mov[0], hemi)

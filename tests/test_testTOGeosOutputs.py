@@ -12,7 +12,9 @@ oracle's loop in the time loop (CPU leg: first row) or magic_rloop_to_next / mag
 (GPU leg: all five rows, called on the steps rIter_cuda_t calls them on; the device's fifteen arrays are also held against the
 oracle's, kept fields included).  The autotest also prints seven points of the TO movie with four decimals: single values of VAS,
 dzRstrAS, dzAstrAS, dzStrAS, dzLFAS and dzCorAS at given (theta, r) of the first two TO steps (e.g. dzCorAS = 422.0722,
-LFfac dzLFAS = -3903.9583), compared here as well -- frame 0 in the CPU leg, frames 0 and 1 in the GPU leg.  Fixture: tests/golden/testTOGeosOutputs_reference.npz + boussBenchSat_ckpt.npz.
+LFfac dzLFAS = -3903.9583), compared here as well -- frame 0 in the CPU leg, frames 0 and 1 in the GPU leg -- and eight points of
+TOnhs.TAG / TOshs.TAG (z-averages of VAS, the Reynolds, axisymmetric, Lorentz and viscous stresses, the Taylorisation and the
+relative geostrophic flow, which brings in V2AS) spread over the five TO steps (GPU leg; MAGIC_TO_CPU_ROWS=5 runs them on the CPU).  Fixture: tests/golden/testTOGeosOutputs_reference.npz + boussBenchSat_ckpt.npz.
 """
 import os
 
@@ -51,6 +53,20 @@ def _check_movie_points(golden, h, to_host, arrays, frame):
         assert abs(got - ref) <= 5.1e-5 + 1e-7 * abs(ref), (q, got, ref)
 
 
+def _check_hemi_points(golden, means, frame):
+    """Eight points of TOnhs.TAG / TOshs.TAG (z-averages on the cylindrical grid, single precision, four printed decimals;
+    unitTest.py:56-63).  `frame` counts the TO steps from 1: entry [k, n_s] of the readers is TO step k + 1."""
+    LFfac = 1.0 / (float(golden["ek"]) * float(golden["prmag"]))
+    north = [("Vp", 2, 18, 1.0), ("Rstr", 3, 11, 1.0), ("Astr", 0, 30, 1.0), ("LF", 2, 21, LFfac)]
+    south = [(None, 3, 12, 1.0), ("Str", 1, 9, 1.0), ("Tay", 4, 27, 1.0), ("VpR", 2, 21, 1.0)]      # dvp: host-only, ~ 0
+    for hemi, pts, ref in ((0, north, golden["nhs_values"]), (1, south, golden["shs_values"])):
+        for (name, k, n_s, fac), r in zip(pts, ref):
+            if name is None or k + 1 != frame:
+                continue
+            got = float(np.float32(fac * means[name][hemi][n_s]))
+            assert abs(got - r) <= 5.1e-5 + 1e-7 * abs(r), (name, hemi, got, r)
+
+
 def _run(golden, h, to_host, to_next, to, n_rows):
     """step_time.f90:355-382 with n_TO_step = 5: getTOnext's kept fields at the first stage of steps 5, 10, ..., getTO (with the
     previous time step as dtLast) and outTO at the first stage of steps 6, 11, ..."""
@@ -61,7 +77,9 @@ def _run(golden, h, to_host, to_next, to, n_rows):
         f = _fields(h)
         if step > 2 and (step - 1) % n_to == 0:
             arrays = to(f, dt)
-            rows.append(to_host.row(arrays, h.e_kin()))
+            means = to_host.cyl_means(arrays, with_hemi_files=True)
+            rows.append(to_host.row(arrays, h.e_kin(), means))
+            _check_hemi_points(golden, means, frame=len(rows))
             np.testing.assert_allclose(rows[-1], golden["Tay"][len(rows) - 1], rtol=RTOL, err_msg=f"Tay row {len(rows) - 1}")
             _check_movie_points(golden, h, to_host, arrays, frame=len(rows) - 1)
             if len(rows) == n_rows:
@@ -83,8 +101,9 @@ def test_oracle_getTO_reproduces_Tay(golden):
         return op
     rows = _run(golden, h, ToHost(h, o.theta_ord, o.toraxi_to_spat),
                 to_next=lambda f: state.update(last=o.radial_TO(with_omega(), rad, f, 0)),
-                to=lambda f, dt: o.radial_TO(with_omega(), rad, f, 1, dtLast=dt, last=state["last"]), n_rows=1)
-    assert rows.shape == (1, 7)
+                to=lambda f, dt: o.radial_TO(with_omega(), rad, f, 1, dtLast=dt, last=state["last"]),
+                n_rows=int(os.environ.get("MAGIC_TO_CPU_ROWS", "1")))
+    assert rows.shape[1] == 7
     # negative control: the Taylorisation of the Lorentz stress needs dzLFAS -- with the field halved it is unchanged (a ratio),
     # with br and bt of one sign flipped ... simpler: the Reynolds measure collapses to 1 for an axisymmetric flow
     f = _fields(h)
