@@ -240,3 +240,37 @@ def test_gpu_log_step_batches_share_one_workspace():
         assert np.array_equal(calls[nm](rl), alone[nm]), nm
     rl.finalize()
     s.finalize_sht()
+
+
+def test_oracle_convective_flux_sums_obey_parseval():
+    """get_fluxes (outPar.f90:470-582): the two grid sums of the convective flux, int vr s dOmega and int vr p dOmega (slots 23, 24;
+    vr = r^2 u_r = sum l(l+1) w_lm Y_lm), equal sum_lm (2 - delta_m0) l(l+1) Re(w_lm conj(s_lm)) for an orthonormal basis --
+    a closed form that does not go through the grid.  Bulk levels (on rigid walls vr is set to zero)."""
+    l_max, n_r = 16, 5
+    o = _oracle(l_max)
+    p, rad, f = _case("mhd", l_max, n_r, o.lm2l, o.lm2m, 12)
+    d = o.radial_diagnostics(_oparams(p), rad, f, DIAG_FLUX)
+    fac = np.where(o.lm2m == 0, 1.0, 2.0)
+    dLh = o.lm2l * (o.lm2l + 1.0)
+    for i in range(1, n_r - 1):
+        for slot, nm in ((23, "s"), (24, "p")):
+            ref = np.sum(fac * dLh * (f["w"][i] * np.conj(f[nm][i])).real)
+            assert abs(d[i, slot] - ref) < 1e-12 * max(abs(ref), np.abs(f["w"][i]).max() * np.abs(f[nm][i]).max() * dLh.max())
+    assert not d[0, 23] and not d[-1, 23]
+
+
+def test_oracle_boundary_layer_and_perpPar_sums_against_spectral_forms():
+    """get_nlBLayers (outPar.f90:584-644): gradT2ASr = (1 / 2 pi) int |grad s|^2 dOmega = (1 / 2 pi) sum (2 - delta_m0) (|ds_lm|^2 +
+    l(l+1) |s_lm|^2 / r^2); get_perpPar (outPar.f90:646-726): E_perp + E_par is the kinetic energy density that get_hemi sums
+    (golden-pinned through hemi.TAG), 2 pi (EperpASr + EparASr) = (ekin_N + ekin_S) / r^2 for orho = 1."""
+    l_max, n_r = 16, 5
+    o = _oracle(l_max)
+    p, rad, f = _case("mhd", l_max, n_r, o.lm2l, o.lm2m, 21)
+    d = o.radial_diagnostics(_oparams(p), rad, f, DIAG_VISCBC | DIAG_PERPPAR | DIAG_HEMI | DIAG_RMSBULK, ktops=2, kbots=2)
+    fac = np.where(o.lm2m == 0, 1.0, 2.0)
+    dLh = o.lm2l * (o.lm2l + 1.0)
+    for i in range(n_r):
+        ref = (np.sum(fac * np.abs(f["ds"][i]) ** 2) + rad["or2"][i] * np.sum(fac * dLh * np.abs(f["s"][i]) ** 2)) / (2.0 * np.pi)
+        assert abs(d[i, 30] - ref) < 1e-12 * ref
+        np.testing.assert_allclose(2.0 * np.pi * (d[i, 18] + d[i, 19]), (d[i, 9] + d[i, 10]) * rad["or2"][i], rtol=1e-12)
+        assert d[i, 20] <= d[i, 18] and d[i, 21] <= d[i, 19] + 1e-15          # the axisymmetric parts are parts
